@@ -1,0 +1,250 @@
+"""Record golden vectors from the UNMODIFIED reference (run in the build container only).
+
+    PYTHONHASHSEED=0 python tests/golden/make_golden.py
+
+Imports ``/root/reference/src/sc_supertree/scs.py`` through ``oracle/cogent3_shim.py`` and writes,
+next to this script:
+
+* ``kat_cases.json``      -- the inline known-answer cases of the reference's own tests
+  (ref: tests/test_spectral_cluster_supertree.py:30-274, README.md:71-78) as data: input Newick,
+  weights, weighting, flags, expected Newick;
+* ``fixture_*.json``      -- the reference's three fixture sets (ref: tests/test_data/*.tre):
+  source Newick lines, weighting and the expected tree;
+* ``pcg_<case>.npz``      -- outputs of the reference's ``_proper_cluster_graph_edges``,
+  ``_get_graph_components`` and ``_contract_proper_cluster_graph`` on each case, made dense with
+  vertex id = rank of the taxon in sorted(names);
+* ``trace_<case>.json``   -- one record per recursion node of the reference's own
+  ``construct_supertree`` run (sorted vertex names, number of components, and for nodes that
+  reached ``spectral_cluster_graph`` the matrix size, its two smallest Laplacian eigenvalues +
+  the third, and the partition returned), plus the final supertree.
+
+The reference is unseeded and iterates over sets; the run is pinned with PYTHONHASHSEED=0 and
+``RandomState(0)`` (SURVEY.md section 8c "Reproducibility of the oracle").
+"""
+
+from __future__ import annotations
+
+import json
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+ROOT = HERE.parent.parent
+sys.path.insert(0, str(ROOT))
+
+from oracle import cogent3_shim, scs_oracle  # noqa: E402
+from spectralclustersupertree_b200.synthetic import make_problem  # noqa: E402
+from spectralclustersupertree_b200.tree import load_tree, make_tree  # noqa: E402
+
+REF_DATA = Path("/root/reference/tests/test_data")
+
+# name, trees, expected, kwargs -- transcribed as data from the reference's tests (file:line in "src")
+KAT = [
+    ("agreeable_1", ["((a,b),(c,d))", "((a,b),(c,(d,e)))"], "((a,b),(c,(d,e)))", {}, "test_spectral_cluster_supertree.py:35-40"),
+    ("agreeable_2", ["(((a,b),(c,d)),(z,(x,y)))", "((a,((f,g),b)),(c,(d,e)))"], "(((a,(b,(f,g))),(c,(d,e))),((x,y),z))", {}, "test_spectral_cluster_supertree.py:42-47"),
+    ("simple_inconsistency", ["(a,(b,c))", "(b,(c,d))", "(d,(a,b))"], "((a,b),(c,d))", {}, "test_spectral_cluster_supertree.py:72-77"),
+    ("two_squares", ["((a,b),(c,d))", "((e,f),(g,h))", "(e,(a,c))", "(g,(b,d))", "(a,(e,g))", "(b,(f,h))", "(a,(b,e))", "(h,(d,g))"], "(((a,b),(c,d)),((e,f),(g,h)))", {}, "test_spectral_cluster_supertree.py:96-106"),
+    ("simple_contraction", ["(((a,b),c),(d,e))", "((a,b),(c,d))"], "(((a,b),c),(d,e))", {}, "test_spectral_cluster_supertree.py:113-117"),
+    ("size_two_a", ["(a,b)", "(b,c)", "(c,d)"], "(a,b,c,d)", {}, "test_spectral_cluster_supertree.py:124-130"),
+    ("size_two_b", ["(a,b)"], "(a,b)", {}, "test_spectral_cluster_supertree.py:132"),
+    ("size_two_c", ["(a,b)", "(a,b)"], "(a,b)", {}, "test_spectral_cluster_supertree.py:133"),
+    ("size_two_d", ["(a,b)", "(b,a)"], "(a,b)", {}, "test_spectral_cluster_supertree.py:134"),
+    ("weights_2_1", ["(a,(b,c))", "(c,(a,b))"], "(a,(b,c))", {"weights": [2, 1]}, "test_spectral_cluster_supertree.py:144"),
+    ("weights_1001_1", ["(a,(b,c))", "(c,(a,b))"], "(a,(b,c))", {"weights": [1.001, 1]}, "test_spectral_cluster_supertree.py:145"),
+    ("weights_1_2", ["(a,(b,c))", "(c,(a,b))"], "(c,(a,b))", {"weights": [1, 2]}, "test_spectral_cluster_supertree.py:147"),
+    ("weights_1_1001", ["(a,(b,c))", "(c,(a,b))"], "(c,(a,b))", {"weights": [1, 1.001]}, "test_spectral_cluster_supertree.py:148"),
+    ("depth_one", ["(a,(b,(c,(d,e))))", "(d,(f,(a,b)))"], "((f,a),(b,(c,(d,e))))", {"pcg_weighting": "one", "contract_edges": False}, "test_spectral_cluster_supertree.py:162-167"),
+    ("depth_depth", ["(a,(b,(c,(d,e))))", "(d,(f,(a,b)))"], "((f,(a,b)),(c,(d,e)))", {"pcg_weighting": "depth", "contract_edges": False}, "test_spectral_cluster_supertree.py:168-173"),
+    ("depth_branch", ["(a,(b,(c,(d,e))))", "(d,(f,(a,b)))"], "((f,(a,b)),(c,(d,e)))", {"pcg_weighting": "branch", "contract_edges": False}, "test_spectral_cluster_supertree.py:174-179"),
+    ("branch_one", ["(a:1,(b:1,(c:1,(d:1,e:1):1):1):1)", "(d:0.1,(f:0.1,(a:0.1,b:0.1):0.1):0.1)"], "((f,a),(b,(c,(d,e))))", {"pcg_weighting": "one", "contract_edges": False}, "test_spectral_cluster_supertree.py:192-197"),
+    ("branch_depth", ["(a:1,(b:1,(c:1,(d:1,e:1):1):1):1)", "(d:0.1,(f:0.1,(a:0.1,b:0.1):0.1):0.1)"], "((f,(a,b)),(c,(d,e)))", {"pcg_weighting": "depth", "contract_edges": False}, "test_spectral_cluster_supertree.py:198-203"),
+    ("branch_branch", ["(a:1,(b:1,(c:1,(d:1,e:1):1):1):1)", "(d:0.1,(f:0.1,(a:0.1,b:0.1):0.1):0.1)"], "((f,a),(b,(c,(d,e))))", {"pcg_weighting": "branch", "contract_edges": False}, "test_spectral_cluster_supertree.py:204-209"),
+    ("bootstrap_one", ["(a,(b,(c,(d,e)100)100)100)", "(a,(b,(d,(c,e)45)100)100)100", "(a,(b,(d,(c,e)50)100)100)100"], "(a,(b,(d,(c,e))))", {"pcg_weighting": "one", "contract_edges": False}, "test_spectral_cluster_supertree.py:224-229"),
+    ("bootstrap_depth", ["(a,(b,(c,(d,e)100)100)100)", "(a,(b,(d,(c,e)45)100)100)100", "(a,(b,(d,(c,e)50)100)100)100"], "(a,(b,(d,(c,e))))", {"pcg_weighting": "depth", "contract_edges": False}, "test_spectral_cluster_supertree.py:230-235"),
+    ("bootstrap_bootstrap", ["(a,(b,(c,(d,e)100)100)100)", "(a,(b,(d,(c,e)45)100)100)100", "(a,(b,(d,(c,e)50)100)100)100"], "(a,(b,(c,(d,e))))", {"pcg_weighting": "bootstrap", "contract_edges": False}, "test_spectral_cluster_supertree.py:236-241"),
+    ("readme_weights", ["(a,(b,c))", "(c,(b,a))"], "(c,(b,a))", {"weights": [1, 1.5]}, "README.md:71-78"),
+]  # fmt: skip
+
+FIXTURES = [
+    ("dcm", "dcm_source_trees.tre", "dcm_model_tree.tre", "one"),
+    ("dcm_iq", "dcm_iq_source.tre", "dcm_iq_expected.tre", "branch"),
+    ("supertriplets", "supertriplets_source.tre", "supertriplets_expected.tre", "depth"),
+]
+
+# (case name, n, T, weighting, seed, tree weights?) -- seed = 1000 * config index + replicate
+SYNTHETIC = [
+    ("c1_100x30_depth", 100, 30, "depth", 1000, False),
+    ("c2_500x50_branch", 500, 50, "branch", 2000, False),
+    ("s_200x40_bootstrap", 200, 40, "bootstrap", 9000, False),
+    ("s_300x40_branch_weighted", 300, 40, "branch", 9001, True),
+    ("s_150x40_one", 150, 40, "one", 9002, False),
+]
+
+
+def dense_from_reference(ref, trees, weights, weighting):
+    """Run the reference's PCG functions and densify their dict outputs."""
+    names: set[str] = set()
+    for t in trees:
+        names.update(t.get_tip_names())
+    names = sorted(names)
+    tid = {name: i for i, name in enumerate(names)}
+    n = len(names)
+    vertices = {(name,) for name in names}
+    edges, ew, occ_d, cooc = ref._proper_cluster_graph_edges(vertices, trees, weights, weighting)
+    W = np.zeros((n, n))
+    C = np.zeros((n, n), dtype=np.int32)
+    occ = np.zeros(n, dtype=np.int32)
+    for (u, v), x in ew.items():
+        W[tid[u[0]], tid[v[0]]] = W[tid[v[0]], tid[u[0]]] = x
+    for (u, v), x in cooc.items():
+        C[tid[u[0]], tid[v[0]]] = C[tid[v[0]], tid[u[0]]] = x
+    for u, x in occ_d.items():
+        occ[tid[u[0]]] = x
+    comps = ref._get_graph_components(vertices, edges)
+    label = np.zeros(n, dtype=np.int32)
+    for comp in comps:
+        ids = sorted(tid[v[0]] for v in comp)
+        label[ids] = ids[0]
+    out = {"W": W, "C": C, "occ": occ, "label": label}
+    # contraction is only defined by the reference on a connected graph, but the function itself
+    # runs on any graph; record it whenever the PCG has edges
+    v2 = set(vertices)
+    e2 = {k: set(s) for k, s in edges.items()}
+    w2 = dict(ew)
+    ref._contract_proper_cluster_graph(v2, e2, w2, occ_d, cooc)
+    new_vertices = sorted(v2, key=lambda v: min(tid[x] for x in v))
+    vid = {v: i for i, v in enumerate(new_vertices)}
+    group = np.zeros(n, dtype=np.int32)
+    for v in new_vertices:
+        for x in v:
+            group[tid[x]] = vid[v]
+    m = len(new_vertices)
+    Wc = np.zeros((m, m))
+    Ac = np.zeros((m, m), dtype=bool)
+    for (u, v), x in w2.items():
+        Wc[vid[u], vid[v]] = Wc[vid[v], vid[u]] = x
+        Ac[vid[u], vid[v]] = Ac[vid[v], vid[u]] = True
+    out.update({"group": group, "Wc": Wc, "Ac": Ac})
+    return names, out
+
+
+def traced_run(ref, trees, weights, weighting, contract_edges=True):
+    """The reference's construct_supertree with its module-level functions wrapped to record."""
+    records = []
+    orig_spectral = ref.spectral_cluster_graph
+    orig_components = ref._get_graph_components
+    state = {}
+
+    def components(vertices, edges):
+        comps = orig_components(vertices, edges)
+        if state.get("in_contract"):
+            return comps
+        state["last"] = {
+            "names": sorted(x for v in vertices for x in v),
+            "n_components": len(comps),
+        }
+        records.append(state["last"])
+        return comps
+
+    orig_contract = ref._contract_proper_cluster_graph
+
+    def contract(*args, **kwargs):
+        state["in_contract"] = True
+        try:
+            return orig_contract(*args, **kwargs)
+        finally:
+            state["in_contract"] = False
+
+    def spectral(vertices, edge_weights, random_state):
+        vlist = sorted(vertices)
+        m = len(vlist)
+        A = np.zeros((m, m))
+        for i, v1 in enumerate(vlist):
+            for j, v2 in enumerate(vlist):
+                A[i, j] = edge_weights.get(ref.edge_tuple(v1, v2), 0)
+        parts = orig_spectral(vertices, edge_weights, random_state)
+        vals, emb = scs_oracle.normalized_affinity_eigs(A, 3)
+        rec = state["last"]
+        rec["contracted_size"] = m
+        rec["eigenvalues"] = [float(x) for x in vals]
+        rec["partition"] = [sorted(x for v in part for x in v) for part in parts]
+        # smallest normalised distance of a Fiedler coordinate to the 2-means boundary
+        if m > 2:
+            u1 = emb[:, 1]
+            side = np.array([0 if v in parts[0] else 1 for v in vlist])
+            if 0 < side.sum() < m:
+                mid = 0.5 * (u1[side == 0].mean() + u1[side == 1].mean())
+                rec["margin"] = float(np.abs(u1 - mid).min() / max(np.ptp(u1), 1e-300))
+        return parts
+
+    ref.spectral_cluster_graph = spectral
+    ref._get_graph_components = components
+    ref._contract_proper_cluster_graph = contract
+    try:
+        tree = ref.construct_supertree(
+            trees, weights, weighting, contract_edges=contract_edges, random_state=np.random.RandomState(0)
+        )
+    finally:
+        ref.spectral_cluster_graph = orig_spectral
+        ref._get_graph_components = orig_components
+        ref._contract_proper_cluster_graph = orig_contract
+    return tree, records
+
+
+def main() -> None:
+    if os.environ.get("PYTHONHASHSEED") != "0":
+        sys.exit("run with PYTHONHASHSEED=0 so the reference's set iteration order is pinned")
+    ref = cogent3_shim.load_reference()
+    if ref is None:
+        sys.exit("reference not mounted")
+
+    # 1. inline KATs: confirm the reference reproduces its own expected answers, then store as data
+    kat_out = []
+    for name, newicks, expected, kwargs, src in KAT:
+        for seed in range(3):
+            res = ref.construct_supertree(
+                [make_tree(s) for s in newicks], random_state=np.random.RandomState(seed), **kwargs
+            )
+            assert res.sorted().same_shape(make_tree(expected).sorted()), (name, str(res))
+        kat_out.append({"name": name, "trees": newicks, "expected": expected, "kwargs": kwargs, "src": src})
+    (HERE / "kat_cases.json").write_text(json.dumps(kat_out, indent=1) + "\n")
+
+    cases = []
+    for name, src_file, exp_file, weighting in FIXTURES:
+        lines = [ln.strip() for ln in (REF_DATA / src_file).read_text().splitlines() if ln.strip()]
+        expected = (REF_DATA / exp_file).read_text().strip()
+        (HERE / f"fixture_{name}.json").write_text(
+            json.dumps({"name": name, "weighting": weighting, "trees": lines, "expected": expected,
+                        "src": f"tests/test_data/{src_file} -> {exp_file}"}) + "\n"
+        )  # fmt: skip
+        cases.append((name, lines, None, weighting, expected))
+    for name, n, T, weighting, seed, tw in SYNTHETIC:
+        prob = make_problem(n, T, weighting, seed, tree_weights=tw)
+        cases.append((name, prob.newick_lines(), prob.weights, weighting, None))
+
+    for name, lines, weights, weighting, expected in cases:
+        trees = [make_tree(s) for s in lines]
+        w = [1.0] * len(trees) if weights is None else list(weights)
+        names, dense = dense_from_reference(ref, trees, w, weighting)
+        np.savez_compressed(HERE / f"pcg_{name}.npz", **dense)
+        tree, records = traced_run(ref, [make_tree(s) for s in lines], w, weighting)
+        if expected is not None:
+            assert tree.sorted().same_shape(load_tree_text(expected).sorted()), name
+        (HERE / f"trace_{name}.json").write_text(
+            json.dumps({"name": name, "weighting": weighting, "weights": weights, "trees": lines if expected is None else None,
+                        "fixture": None if expected is None else f"fixture_{name}.json",
+                        "names": names, "supertree": tree.get_newick(), "nodes": records}) + "\n"
+        )  # fmt: skip
+        spectral = sum(1 for r in records if "partition" in r)
+        print(f"{name}: n={len(names)} T={len(trees)} nodes={len(records)} spectral={spectral}")
+
+
+def load_tree_text(text: str):
+    return make_tree(text)
+
+
+if __name__ == "__main__":
+    main()
