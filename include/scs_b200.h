@@ -1,0 +1,198 @@
+/* scs_b200.h -- C ABI of libscs_b200.so, the B200 (sm_100a) engine for the hot path of
+ * Spectral Cluster Supertree.
+ *
+ * The reference (rmcar17/SpectralClusterSupertree) has no FFI: the seam this library fills is
+ * the four private Python functions its recursion calls once per recursion node
+ * (src/sc_supertree/scs.py:110-134).  Each entry point below names the reference function it
+ * replaces.  The graph the reference keeps as dicts of name tuples is dense here:
+ * vertex id = rank of the taxon name in sorted(all names of the node); W, C are row-major n x n.
+ *
+ * Conventions
+ *   - every function returns an scs_status (0 = OK, negative = error); no C++ exception and no
+ *     torch type crosses this boundary;
+ *   - "_dev" pointers are device pointers owned by the caller; functions taking them only
+ *     enqueue work on the context's CUDA stream and return without synchronising, unless they
+ *     write a host result (then they synchronise the stream before returning);
+ *   - functions ending in "_host" take host pointers, copy in, compute on the GPU and copy the
+ *     result out before returning (the per-recursion-node call a Python/cgo/JNI caller binds);
+ *   - a context owns its workspace and is not thread-safe; use one context per thread per GPU.
+ *
+ * Source trees are passed as leaf tours: the leaves of every tree in depth-first order plus,
+ * for each pair of consecutive leaves, the depth and the weighting value of their lowest common
+ * ancestor (see spectralclustersupertree_b200/flatten.py).  The weighting strategy is already
+ * folded into adj_val, so the kernels are weighting-agnostic:
+ *   one -> 1, depth -> depth of the LCA, branch -> root-to-LCA length, bootstrap -> support
+ *   (scs.py:555-567).
+ */
+#ifndef SCS_B200_H
+#define SCS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct scs_ctx scs_ctx;
+
+typedef enum {
+    SCS_OK = 0,
+    SCS_ERR_INVALID = -1,     /* bad argument (null pointer, negative size, ...) */
+    SCS_ERR_CUDA = -2,        /* a CUDA runtime call failed; see scs_last_error */
+    SCS_ERR_NO_DEVICE = -3,   /* no usable CUDA device */
+    SCS_ERR_TOO_SMALL = -4,   /* fewer than 2 vertices handed to the spectral step
+                                 (sklearn raises ValueError there, _spectral.py:699) */
+    SCS_ERR_NO_CONVERGE = -5, /* eigensolver hit its restart limit */
+    SCS_ERR_INPUT = -6        /* malformed leaf tour (taxon id out of range, ...) */
+} scs_status;
+
+/* What happened at one recursion node (the "near-ties reported" clause of the parity contract). */
+typedef struct {
+    int32_t n_components;    /* components of the proper cluster graph (adjacency = co-occurred) */
+    int32_t contracted_size; /* vertices handed to the spectral step (n if nothing contracted) */
+    int32_t spectral_ran;    /* 1 if the node went through the spectral step */
+    int32_t solver;          /* 0 none, 1 trivial (m = 2), 2 dense Jacobi (one CTA), 3 Lanczos */
+    int32_t matvecs;         /* operator applications in the Lanczos solver */
+    int32_t restarts;
+    int32_t tie_flag;        /* 1 if eigengap or 2-means margin is below the thresholds */
+    int32_t reserved;
+    double eig[3];           /* three smallest eigenvalues of L = I - D^-1/2 W D^-1/2 (eig[0] = 0;
+                                eig[2] is the solver's estimate, NaN if not available) */
+    double residual;         /* || N y - theta y ||_2 of the Fiedler Ritz pair */
+    double margin;           /* min_i |u_i - midpoint| / range(u): distance to the 2-means cut */
+} scs_node_stats;
+
+/* ---- context ---------------------------------------------------------------------------- */
+int scs_version(void);
+const char *scs_status_string(int status);
+/* Text of the last error raised on this context ("" if none). */
+const char *scs_last_error(const scs_ctx *ctx);
+/* stream: a cudaStream_t to run on, or NULL to let the context create its own. */
+int scs_ctx_create(int device, void *stream, scs_ctx **out);
+int scs_ctx_destroy(scs_ctx *ctx);
+int scs_ctx_synchronize(scs_ctx *ctx);
+/* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
+int64_t scs_ctx_launch_count(const scs_ctx *ctx);
+
+/* ---- proper cluster graph: replaces _proper_cluster_graph_edges + _dfs_pcg_weights
+ *      (scs.py:495-583, 586-663) ---------------------------------------------------------- *
+ * in : n vertices, T trees, L leaves in total;
+ *      leaf_offsets[T+1] (int64), leaf_taxon[L] (vertex id), adj_depth[L], adj_val[L],
+ *      root_depth[T] (the adj_depth value that means "LCA is the root"), tree_weight[T].
+ * out: W[n*n]  sum over trees, in tree order, of fl(adj_val(LCA) * tree_weight)   (scs.py:655-657)
+ *      C[n*n]  number of trees in which the pair is a proper cluster (may be NULL)  (scs.py:658)
+ *      occ[n]  number of trees containing the taxon                                 (scs.py:580-581)
+ *      adj_bits[n * scs_bit_words(n)]  bit b of word j of row a = C[a][32j+b] > 0   (scs.py:651-652)
+ *      max_bits[...]                   ... = C[a][b] > 0 && C[a][b] == max(occ[a], occ[b])
+ *                                      (the max-graph of scs.py:302-313; may be NULL)
+ *      degree[n] row sums of W (may be NULL)
+ * No atomics touch W: each row is accumulated by one CTA in tree input order, so W is
+ * reproducible and symmetric bit for bit. */
+int scs_bit_words(int n);
+int scs_pcg_build_dev(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offsets_dev,
+                      const int32_t *leaf_taxon_dev, const int32_t *adj_depth_dev,
+                      const double *adj_val_dev, const int32_t *root_depth_dev,
+                      const double *tree_weight_dev, double *W_dev, int32_t *C_dev,
+                      int32_t *occ_dev, uint32_t *adj_bits_dev, uint32_t *max_bits_dev,
+                      double *degree_dev);
+
+/* ---- connected components: replaces _get_graph_components (scs.py:458-492) ---------------- *
+ * label[v] = smallest vertex id of v's component; *n_components_host receives the count. */
+int scs_components_dev(scs_ctx *ctx, int n, const uint32_t *bits_dev, int32_t *label_dev,
+                       int32_t *n_components_host);
+
+/* ---- contraction: replaces _contract_proper_cluster_graph (scs.py:261-387) ---------------- *
+ * group[v] = contracted vertex holding v, numbered by smallest member; *m_host their number;
+ * Wc[m*m] (leading dimension m) = max of W over the existing edges between two groups, 0 where
+ * there is none; degree_c[m] = row sums of Wc (may be NULL).  Wc_dev must hold n*n doubles. */
+int scs_contract_dev(scs_ctx *ctx, int n, const double *W_dev, const uint32_t *adj_bits_dev,
+                     const uint32_t *max_bits_dev, int32_t *group_dev, int32_t *m_host,
+                     double *Wc_dev, double *degree_c_dev);
+
+/* ---- spectral bipartition: replaces spectral_cluster_graph (scs.py:210-258), i.e.
+ *      sklearn SpectralClustering(2, affinity="precomputed") ------------------------------ *
+ * W[m*m] symmetric, zero diagonal.  side[m] in {0,1}: 2-means on the Fiedler coordinate of the
+ * normalised Laplacian.  degree_dev may be NULL (computed here).  seed picks the start vector. */
+int scs_spectral_bipartition_dev(scs_ctx *ctx, int m, const double *W_dev, const double *degree_dev,
+                                 uint64_t seed, int32_t *side_dev, scs_node_stats *stats_host);
+
+/* y = D^-1/2 W D^-1/2 x on device vectors: the Laplacian matvec the eigensolver iterates
+ * (exposed for the roofline measurement; inv_sqrt_deg = 1/sqrt(degree), 1 where degree is 0). */
+int scs_normalized_matvec_dev(scs_ctx *ctx, int m, const double *W_dev,
+                              const double *inv_sqrt_deg_dev, const double *x_dev, double *y_dev);
+
+/* ---- one recursion node ------------------------------------------------------------------- *
+ * Replaces the block scs.py:110-134: build the graph, find its components; if it is connected,
+ * optionally contract it and split it in two.  part[n] receives, per vertex, the component
+ * index (0..n_components-1, numbered by smallest member) when the graph is disconnected,
+ * otherwise the side (0/1) of the spectral bipartition.
+ * _host: host buffers in and out (copies inside the call, returns after the result landed).
+ * _dev : tours and part are device pointers; stats are still written on the host. */
+int scs_node_split_host(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offsets,
+                        const int32_t *leaf_taxon, const int32_t *adj_depth, const double *adj_val,
+                        const int32_t *root_depth, const double *tree_weight, int contract_edges,
+                        uint64_t seed, int32_t *part, scs_node_stats *stats);
+int scs_node_split_dev(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offsets_dev,
+                       const int32_t *leaf_taxon_dev, const int32_t *adj_depth_dev,
+                       const double *adj_val_dev, const int32_t *root_depth_dev,
+                       const double *tree_weight_dev, int contract_edges, uint64_t seed,
+                       int32_t *part_dev, scs_node_stats *stats_host);
+
+/* Device pointers of the node most recently processed by scs_node_split_* (valid until the
+ * next call on this context); for parity tests and profiling.  Any out pointer may be NULL.
+ * *n / *m are that node's vertex count and contracted vertex count (0 if it never contracted). */
+int scs_node_last_buffers(scs_ctx *ctx, int *n, int *m, double **W_dev, uint32_t **adj_bits_dev,
+                          uint32_t **max_bits_dev, int32_t **occ_dev, double **degree_dev,
+                          double **Wc_dev, int32_t **group_dev);
+
+/* Plain device memory helpers for callers without a CUDA runtime binding of their own
+ * (ctypes / cgo / JNI); synchronous with respect to the context's stream. */
+int scs_dev_alloc(scs_ctx *ctx, size_t bytes, void **out);
+int scs_dev_free(scs_ctx *ctx, void *ptr);
+int scs_memcpy_h2d(scs_ctx *ctx, void *dev, const void *host, size_t bytes);
+int scs_memcpy_d2h(scs_ctx *ctx, void *host, const void *dev, size_t bytes);
+
+/* ---- source-tree store (host side): replaces the PhyloNode lists the reference's recursion
+ *      carries and _generate_induced_trees_with_weights (scs.py:411-455) -------------------- *
+ * A forest holds T trees as flat arrays: nodes in depth-first pre-order, node_offsets[T+1];
+ * parent[M] = index of the parent within the tree (-1 for the root, always < the node's own
+ * index); length[M], support[M] with NaN for "missing" (either array may be NULL = all missing);
+ * taxon[M] = global taxon id for tips (0..num_taxa-1), -1 for internal nodes.  Global taxon ids
+ * are ranks in the sorted list of all tip names, so increasing id = sorted name order. */
+typedef struct scs_forest scs_forest;
+int scs_forest_create(int T, const int64_t *node_offsets, const int32_t *parent, const double *length,
+                      const double *support, const int32_t *taxon, const double *tree_weight,
+                      int num_taxa, scs_forest **out);
+int scs_forest_destroy(scs_forest *f);
+int scs_forest_num_trees(const scs_forest *f);
+int64_t scs_forest_num_nodes(const scs_forest *f);
+int64_t scs_forest_num_leaves(const scs_forest *f);
+int scs_forest_num_taxa(const scs_forest *f);
+/* sum over trees of k (k - 1): ordered leaf pairs the graph build visits */
+int64_t scs_forest_pair_visits(const scs_forest *f);
+int scs_forest_tree_info(const scs_forest *f, int t, int64_t *num_nodes, double *weight, int32_t *source);
+int scs_forest_tree(const scs_forest *f, int t, int32_t *parent, double *length, double *support,
+                    int32_t *taxon);
+/* present[num_taxa] = 1 where the taxon is a tip of some tree (scs.py:708-725); returns the
+ * number present, or a negative status. */
+int scs_forest_taxa(const scs_forest *f, uint8_t *present);
+/* Restrict every tree to the taxa with keep[taxon] != 0, as PhyloNode.get_sub_tree(names,
+ * ignore_missing=True, as_rooted=True) does; trees left with < 2 tips are dropped with their
+ * weight (scs.py:444-453). */
+int scs_forest_induce(const scs_forest *f, const uint8_t *keep, scs_forest **out);
+/* Leaf tours of the forest for one weighting (0 one, 1 branch, 2 depth, 3 bootstrap;
+ * scs.py:555-567); local_id[num_taxa] maps global taxon id -> vertex id.  Output arrays are
+ * sized by scs_forest_num_trees / scs_forest_num_leaves. */
+int scs_forest_tours(const scs_forest *f, int weighting, const int32_t *local_id, int64_t *leaf_offsets,
+                     int32_t *leaf_taxon, int32_t *adj_depth, double *adj_val, int32_t *root_depth,
+                     double *tree_weight);
+/* One recursion node straight from a forest (scs.py:102-134): vertices = taxa present, in
+ * increasing global id.  taxa_out / part_out must hold num_taxa entries; *n_out receives n. */
+int scs_forest_split(scs_ctx *ctx, const scs_forest *f, int weighting, int contract_edges, uint64_t seed,
+                     int32_t *n_out, int32_t *taxa_out, int32_t *part_out, scs_node_stats *stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCS_B200_H */

@@ -1,0 +1,142 @@
+"""ctypes binding of ``libscs_b200.so`` (C ABI: ``include/scs_b200.h``).
+
+There is no CPU fallback: if the library has not been built, or no CUDA device is usable, the
+functions here raise.  The binding mirrors the header one to one; `INTEGRATION.md` shows the
+same stub for a maintainer of the reference.
+"""
+
+from __future__ import annotations
+
+import ctypes
+from ctypes import POINTER, c_char_p, c_double, c_int, c_int32, c_int64, c_size_t, c_uint8, c_uint64, c_void_p
+from pathlib import Path
+
+LIB_PATH = Path(__file__).resolve().parent / "libscs_b200.so"
+
+SCS_OK = 0
+SCS_ERR_INVALID = -1
+SCS_ERR_CUDA = -2
+SCS_ERR_NO_DEVICE = -3
+SCS_ERR_TOO_SMALL = -4
+SCS_ERR_NO_CONVERGE = -5
+SCS_ERR_INPUT = -6
+
+
+class NodeStats(ctypes.Structure):
+    """``scs_node_stats`` of include/scs_b200.h."""
+
+    _fields_ = [
+        ("n_components", c_int32),
+        ("contracted_size", c_int32),
+        ("spectral_ran", c_int32),
+        ("solver", c_int32),
+        ("matvecs", c_int32),
+        ("restarts", c_int32),
+        ("tie_flag", c_int32),
+        ("reserved", c_int32),
+        ("eig", c_double * 3),
+        ("residual", c_double),
+        ("margin", c_double),
+    ]
+
+    def as_dict(self) -> dict:
+        return {
+            "n_components": self.n_components,
+            "contracted_size": self.contracted_size,
+            "spectral_ran": bool(self.spectral_ran),
+            "solver": self.solver,
+            "matvecs": self.matvecs,
+            "restarts": self.restarts,
+            "tie_flag": self.tie_flag,
+            "eig": [self.eig[0], self.eig[1], self.eig[2]],
+            "residual": self.residual,
+            "margin": self.margin,
+        }
+
+
+class LibraryMissingError(RuntimeError):
+    """``libscs_b200.so`` is not built: the CUDA path is the only path."""
+
+
+_P = c_void_p  # every array argument is passed as a raw address
+
+# name -> (restype, argtypes); one entry per function declared in include/scs_b200.h
+SIGNATURES: dict[str, tuple] = {
+    "scs_version": (c_int, []),
+    "scs_status_string": (c_char_p, [c_int]),
+    "scs_last_error": (c_char_p, [_P]),
+    "scs_ctx_create": (c_int, [c_int, _P, POINTER(_P)]),
+    "scs_ctx_destroy": (c_int, [_P]),
+    "scs_ctx_synchronize": (c_int, [_P]),
+    "scs_ctx_launch_count": (c_int64, [_P]),
+    "scs_bit_words": (c_int, [c_int]),
+    "scs_pcg_build_dev": (c_int, [_P, c_int, c_int, c_int64] + [_P] * 12),
+    "scs_components_dev": (c_int, [_P, c_int, _P, _P, POINTER(c_int32)]),
+    "scs_contract_dev": (c_int, [_P, c_int, _P, _P, _P, _P, POINTER(c_int32), _P, _P]),
+    "scs_spectral_bipartition_dev": (c_int, [_P, c_int, _P, _P, c_uint64, _P, POINTER(NodeStats)]),
+    "scs_normalized_matvec_dev": (c_int, [_P, c_int, _P, _P, _P, _P]),
+    "scs_node_split_host": (
+        c_int,
+        [_P, c_int, c_int, c_int64, _P, _P, _P, _P, _P, _P, c_int, c_uint64, _P, POINTER(NodeStats)],
+    ),
+    "scs_node_split_dev": (
+        c_int,
+        [_P, c_int, c_int, c_int64, _P, _P, _P, _P, _P, _P, c_int, c_uint64, _P, POINTER(NodeStats)],
+    ),
+    "scs_node_last_buffers": (c_int, [_P, POINTER(c_int), POINTER(c_int)] + [POINTER(_P)] * 7),
+    "scs_dev_alloc": (c_int, [_P, c_size_t, POINTER(_P)]),
+    "scs_dev_free": (c_int, [_P, _P]),
+    "scs_memcpy_h2d": (c_int, [_P, _P, _P, c_size_t]),
+    "scs_memcpy_d2h": (c_int, [_P, _P, _P, c_size_t]),
+    "scs_forest_create": (c_int, [c_int, _P, _P, _P, _P, _P, _P, c_int, POINTER(_P)]),
+    "scs_forest_destroy": (c_int, [_P]),
+    "scs_forest_num_trees": (c_int, [_P]),
+    "scs_forest_num_nodes": (c_int64, [_P]),
+    "scs_forest_num_leaves": (c_int64, [_P]),
+    "scs_forest_num_taxa": (c_int, [_P]),
+    "scs_forest_pair_visits": (c_int64, [_P]),
+    "scs_forest_tree_info": (c_int, [_P, c_int, POINTER(c_int64), POINTER(c_double), POINTER(c_int32)]),
+    "scs_forest_tree": (c_int, [_P, c_int, _P, _P, _P, _P]),
+    "scs_forest_taxa": (c_int, [_P, _P]),
+    "scs_forest_induce": (c_int, [_P, _P, POINTER(_P)]),
+    "scs_forest_tours": (c_int, [_P, c_int, _P, _P, _P, _P, _P, _P, _P]),
+    "scs_forest_split": (
+        c_int,
+        [_P, _P, c_int, c_int, c_uint64, POINTER(c_int32), _P, _P, POINTER(NodeStats)],
+    ),
+}
+
+_LIB: ctypes.CDLL | None = None
+
+
+def load() -> ctypes.CDLL:
+    """The loaded library with every signature set; raises if it is missing."""
+    global _LIB  # noqa: PLW0603
+    if _LIB is not None:
+        return _LIB
+    if not LIB_PATH.is_file():
+        msg = (
+            f"{LIB_PATH} is missing: build it with `python -m spectralclustersupertree_b200.build` "
+            "(there is no CPU fallback for the CUDA path)"
+        )
+        raise LibraryMissingError(msg)
+    lib = ctypes.CDLL(str(LIB_PATH))
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _LIB = lib
+    return lib
+
+
+def ptr(array) -> int | None:
+    """Address of a C-contiguous numpy array (None for None)."""
+    if array is None:
+        return None
+    if not array.flags["C_CONTIGUOUS"]:
+        msg = "array must be C-contiguous"
+        raise ValueError(msg)
+    return array.ctypes.data
+
+
+__all__ = ["LIB_PATH", "SIGNATURES", "LibraryMissingError", "NodeStats", "c_uint8", "load", "ptr"]

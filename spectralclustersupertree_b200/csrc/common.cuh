@@ -1,0 +1,145 @@
+// Internal definitions shared by the translation units of libscs_b200.so.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "scs_b200.h"
+
+namespace scs {
+
+// A grow-only device allocation; a context keeps one per purpose so steady-state recursion
+// nodes allocate nothing.
+struct DeviceBuffer {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+};
+
+enum Slot : int {
+    // leaf tours copied in by the host-facing call
+    SLOT_TOUR_OFFSETS = 0,
+    SLOT_TOUR_TAXON,
+    SLOT_TOUR_DEPTH,
+    SLOT_TOUR_VAL,
+    SLOT_TOUR_ROOT,
+    SLOT_TOUR_WEIGHT,
+    // proper cluster graph
+    SLOT_W,
+    SLOT_WC,
+    SLOT_OCC,
+    SLOT_ADJ_BITS,
+    SLOT_MAX_BITS,
+    SLOT_DEGREE,
+    SLOT_DEGREE_C,
+    SLOT_LEAF_TREE,
+    SLOT_ROW_PTR,
+    SLOT_CURSOR,
+    SLOT_INV,
+    SLOT_INV_SORTED,
+    SLOT_DEGREE_PART,
+    // components / contraction
+    SLOT_UF_PARENT,
+    SLOT_LABEL,
+    SLOT_GROUP,
+    SLOT_GROUP_PTR,
+    SLOT_GROUP_MEMBERS,
+    SLOT_SCALARS,
+    SLOT_PART,
+    // spectral
+    SLOT_ISD,
+    SLOT_UVEC,
+    SLOT_BASIS,
+    SLOT_WORK,
+    SLOT_COEF,
+    SLOT_TRIDIAG,
+    SLOT_RITZ,
+    SLOT_EMBED,
+    SLOT_SORTED,
+    SLOT_SIDE,
+    SLOT_SPEC_SCALARS,
+    SLOT_COUNT
+};
+
+}  // namespace scs
+
+struct scs_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    int64_t launches = 0;
+    std::string last_error;
+    scs::DeviceBuffer slots[scs::SLOT_COUNT];
+    void *pinned = nullptr;  // host staging for small results
+    size_t pinned_bytes = 0;
+    void *pinned_io = nullptr;  // host staging for the tours of scs_node_split_host
+    size_t pinned_io_bytes = 0;
+    // shape of the node most recently processed by scs_node_split_host
+    int last_n = 0;
+    int last_m = 0;
+};
+
+namespace scs {
+
+int fail(scs_ctx *ctx, int status, const char *what, cudaError_t err = cudaSuccess);
+
+#define SCS_CUDA(ctx, call)                                                   \
+    do {                                                                      \
+        cudaError_t err__ = (call);                                           \
+        if (err__ != cudaSuccess) return scs::fail(ctx, SCS_ERR_CUDA, #call, err__); \
+    } while (0)
+
+// Check the launch that was just issued and count it.
+#define SCS_LAUNCHED(ctx, name)                                               \
+    do {                                                                      \
+        cudaError_t err__ = cudaGetLastError();                               \
+        if (err__ != cudaSuccess) return scs::fail(ctx, SCS_ERR_CUDA, name, err__); \
+        (ctx)->launches += 1;                                                 \
+    } while (0)
+
+// Device memory for `slot`, at least `bytes` large (contents undefined after growth).
+int reserve(scs_ctx *ctx, Slot slot, size_t bytes, void **out);
+
+template <typename T>
+inline int reserve_as(scs_ctx *ctx, Slot slot, size_t count, T **out) {
+    void *p = nullptr;
+    int rc = reserve(ctx, slot, count * sizeof(T), &p);
+    *out = static_cast<T *>(p);
+    return rc;
+}
+
+int reserve_pinned(scs_ctx *ctx, size_t bytes, void **out);
+
+inline int ceil_div(int64_t a, int64_t b) { return static_cast<int>((a + b - 1) / b); }
+
+// out[i] = in[0] + ... + in[i-1] for i in [0, n]  (out has n + 1 entries)
+int exclusive_scan(scs_ctx *ctx, int n, const int32_t *in, int32_t *out);
+
+// ---- stage entry points implemented in the other translation units ------------------------
+int pcg_build(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offsets,
+              const int32_t *leaf_taxon, const int32_t *adj_depth, const double *adj_val,
+              const int32_t *root_depth, const double *tree_weight, double *W, int32_t *C,
+              int32_t *occ, uint32_t *adj_bits, uint32_t *max_bits, double *degree);
+
+int components(scs_ctx *ctx, int n, const uint32_t *bits, int32_t *label, int32_t *n_components_host);
+
+int contract(scs_ctx *ctx, int n, const double *W, const uint32_t *adj_bits, const uint32_t *max_bits,
+             int32_t *group, int32_t *m_host, double *Wc, double *degree_c);
+
+int spectral_bipartition(scs_ctx *ctx, int m, const double *W, const double *degree, uint64_t seed,
+                         int32_t *side, scs_node_stats *stats_host);
+
+int normalized_matvec(scs_ctx *ctx, int m, const double *W, const double *isd, const double *x, double *y);
+
+int node_split(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offsets, const int32_t *leaf_taxon,
+               const int32_t *adj_depth, const double *adj_val, const int32_t *root_depth,
+               const double *tree_weight, int contract_edges, uint64_t seed, int32_t *part_dev,
+               scs_node_stats *stats);
+
+}  // namespace scs

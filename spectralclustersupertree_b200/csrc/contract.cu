@@ -1,0 +1,161 @@
+// Edge contraction of the proper cluster graph.
+//
+// Replaces _contract_proper_cluster_graph of the reference
+// (/root/reference/src/sc_supertree/scs.py:261-387): taxa that sit in the same proper cluster in
+// every tree containing either of them (co-occurrence == max of the two occurrence counts,
+// scs.py:302-305 -- the max-graph bits the row kernel emitted) are merged; the merged vertices
+// are the components of that max-graph (scs.py:316); parallel edges between two merged vertices
+// keep the MAXIMUM weight (scs.py:382-387) and edges inside a merged vertex vanish
+// (scs.py:352-354).  max is order-free, so shared-memory atomics keep this exact.
+
+#include "common.cuh"
+
+namespace scs {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr unsigned long long kSign = 0x8000000000000000ull;
+
+// monotone map double -> uint64 (0 is below every real number: used for "no edge")
+__device__ __forceinline__ unsigned long long order_key(double x) {
+    unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(x));
+    return (b & kSign) ? ~b : (b | kSign);
+}
+__device__ __forceinline__ double order_value(unsigned long long k) {
+    unsigned long long b = (k & kSign) ? (k & ~kSign) : ~k;
+    return __longlong_as_double(static_cast<long long>(b));
+}
+
+__global__ void mark_representatives(int n, const int32_t *__restrict__ label, int32_t *__restrict__ is_rep) {
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v < n) is_rep[v] = label[v] == v;
+}
+
+__global__ void assign_groups(int n, const int32_t *__restrict__ label, const int32_t *__restrict__ rep_rank,
+                              int32_t *__restrict__ group, int32_t *__restrict__ group_size) {
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    int gidx = rep_rank[label[v]];
+    group[v] = gidx;
+    atomicAdd(&group_size[gidx], 1);
+}
+
+__global__ void fill_members(int n, const int32_t *__restrict__ group, const int32_t *__restrict__ group_ptr,
+                             int32_t *__restrict__ cursor, int32_t *__restrict__ members) {
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    int gidx = group[v];
+    members[group_ptr[gidx] + atomicAdd(&cursor[gidx], 1)] = v;
+}
+
+// one CTA per contracted vertex A (and per column chunk of the contracted matrix)
+__global__ void __launch_bounds__(kThreads)
+contract_rows(int n, int m, int words, int cols_per_chunk, const double *__restrict__ W,
+              const uint32_t *__restrict__ adj_bits, const int32_t *__restrict__ group,
+              const int32_t *__restrict__ group_ptr, const int32_t *__restrict__ members,
+              double *__restrict__ Wc, double *__restrict__ degree_part) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long *best = reinterpret_cast<unsigned long long *>(smem_raw);
+    __shared__ double warp_sum[kThreads / 32];
+    const int A = blockIdx.x;
+    const int c0 = blockIdx.y * cols_per_chunk;
+    const int ncols = min(cols_per_chunk, m - c0);
+    const int tid = threadIdx.x;
+    for (int c = tid; c < ncols; c += kThreads) best[c] = 0ull;
+    __syncthreads();
+    const int mb = group_ptr[A], me = group_ptr[A + 1];
+    for (int mi = mb; mi < me; ++mi) {
+        const int u = members[mi];
+        const uint32_t *bits_u = adj_bits + static_cast<size_t>(u) * words;
+        const double *W_u = W + static_cast<size_t>(u) * n;
+        for (int v = tid; v < n; v += kThreads) {
+            if ((bits_u[v >> 5] >> (v & 31)) & 1u) {
+                const int B = group[v];
+                const int c = B - c0;
+                if (B != A && static_cast<unsigned>(c) < static_cast<unsigned>(ncols))
+                    atomicMax(&best[c], order_key(W_u[v]));
+            }
+        }
+    }
+    __syncthreads();
+    double partial = 0.0;
+    double *out = Wc + static_cast<size_t>(A) * m + c0;
+    for (int c = tid; c < ncols; c += kThreads) {
+        const unsigned long long k = best[c];
+        const double x = k ? order_value(k) : 0.0;
+        out[c] = x;
+        partial += x;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) partial += __shfl_down_sync(0xffffffffu, partial, off);
+    if ((tid & 31) == 0) warp_sum[tid >> 5] = partial;
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0.0;
+        for (int wi = 0; wi < kThreads / 32; ++wi) s += warp_sum[wi];
+        degree_part[static_cast<size_t>(blockIdx.y) * m + A] = s;
+    }
+}
+
+__global__ void sum_parts(int m, int nchunks, const double *__restrict__ part, double *__restrict__ out) {
+    int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= m) return;
+    double s = 0.0;
+    for (int c = 0; c < nchunks; ++c) s += part[static_cast<size_t>(c) * m + a];
+    out[a] = s;
+}
+
+}  // namespace
+
+int contract(scs_ctx *ctx, int n, const double *W, const uint32_t *adj_bits, const uint32_t *max_bits,
+             int32_t *group, int32_t *m_host, double *Wc, double *degree_c) {
+    if (n <= 0 || !W || !adj_bits || !max_bits || !group || !m_host || !Wc)
+        return fail(ctx, SCS_ERR_INVALID, "contract: bad argument");
+    const int words = scs_bit_words(n);
+    int32_t *label, *flags, *rank, *gptr, *cursor, *members;
+    int rc;
+    if ((rc = reserve_as(ctx, SLOT_LABEL, static_cast<size_t>(n), &label))) return rc;
+    int m = 0;
+    if ((rc = components(ctx, n, max_bits, label, &m))) return rc;  // synchronises: m is known
+    *m_host = m;
+    // scratch: flags[n] | rank[n+1] | gptr[n+1] | cursor[n]
+    if ((rc = reserve_as(ctx, SLOT_GROUP_PTR, 4 * static_cast<size_t>(n) + 8, &flags))) return rc;
+    rank = flags + n;
+    gptr = rank + n + 1;
+    cursor = gptr + n + 1;
+    if ((rc = reserve_as(ctx, SLOT_GROUP_MEMBERS, static_cast<size_t>(n), &members))) return rc;
+    const int blocks = ceil_div(n, 256);
+    mark_representatives<<<blocks, 256, 0, ctx->stream>>>(n, label, flags);
+    SCS_LAUNCHED(ctx, "mark_representatives");
+    if ((rc = exclusive_scan(ctx, n, flags, rank))) return rc;
+    // group sizes reuse `flags` (m <= n entries), then become offsets in gptr
+    SCS_CUDA(ctx, cudaMemsetAsync(cursor, 0, sizeof(int32_t) * n, ctx->stream));
+    assign_groups<<<blocks, 256, 0, ctx->stream>>>(n, label, rank, group, cursor);
+    SCS_LAUNCHED(ctx, "assign_groups");
+    if (m == n) return SCS_OK;  // nothing merged: the caller keeps using W
+    if ((rc = exclusive_scan(ctx, m, cursor, gptr))) return rc;
+    SCS_CUDA(ctx, cudaMemsetAsync(cursor, 0, sizeof(int32_t) * n, ctx->stream));
+    fill_members<<<blocks, 256, 0, ctx->stream>>>(n, group, gptr, cursor, members);
+    SCS_LAUNCHED(ctx, "fill_members");
+
+    const size_t budget = ctx->smem_optin > 4096 ? ctx->smem_optin - 2048 : 46 * 1024;
+    const int max_cols = static_cast<int>(budget / sizeof(unsigned long long));
+    int nchunks = ceil_div(m, max_cols);
+    const int cols_per_chunk = ceil_div(m, nchunks);
+    nchunks = ceil_div(m, cols_per_chunk);
+    const size_t smem = static_cast<size_t>(cols_per_chunk) * sizeof(unsigned long long);
+    double *part;
+    if ((rc = reserve_as(ctx, SLOT_DEGREE_PART, static_cast<size_t>(m) * nchunks, &part))) return rc;
+    SCS_CUDA(ctx, cudaFuncSetAttribute(contract_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    contract_rows<<<dim3(m, nchunks), kThreads, smem, ctx->stream>>>(n, m, words, cols_per_chunk, W, adj_bits, group,
+                                                                     gptr, members, Wc, part);
+    SCS_LAUNCHED(ctx, "contract_rows");
+    if (degree_c) {
+        sum_parts<<<ceil_div(m, 256), 256, 0, ctx->stream>>>(m, nchunks, part, degree_c);
+        SCS_LAUNCHED(ctx, "sum_parts");
+    }
+    return SCS_OK;
+}
+
+}  // namespace scs

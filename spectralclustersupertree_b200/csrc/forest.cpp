@@ -1,0 +1,290 @@
+// Host-side source-tree store of libscs_b200.so: flat trees, restriction to a taxon subset, and
+// flattening into the leaf tours the kernels consume.
+//
+// The reference keeps cogent3 PhyloNode objects and, at every recursion node, restricts every
+// source tree to the taxa of a component with PhyloNode.get_sub_tree(names, ignore_missing=True,
+// as_rooted=True) (/root/reference/src/sc_supertree/scs.py:411-455).  Here a forest is a set of
+// flat arrays -- nodes in depth-first pre-order with a parent index -- so the same restriction is
+// one linear pass per tree with the same arithmetic:
+//   * tips outside the subset vanish; an internal node left with one child is merged into that
+//     child, whose length becomes  length(node) + length(child)  (missing if either is missing),
+//     applied bottom-up exactly in that operand order;
+//   * a root left with one child is replaced by its first branching descendant, whose own length
+//     is dropped;
+//   * trees left with fewer than two tips are dropped together with their weight (scs.py:447-448).
+// Tours follow the reference's length_function top-down (scs.py:555-567, 628).
+
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "scs_b200.h"
+
+struct scs_forest {
+    int num_taxa = 0;
+    std::vector<int64_t> node_offsets{0};  // [T + 1]
+    std::vector<int32_t> parent;           // index within the tree, -1 for the root; parent < child
+    std::vector<double> length;            // NaN = missing
+    std::vector<double> support;           // NaN = missing
+    std::vector<int32_t> taxon;            // tips: global taxon id, internal nodes: -1
+    std::vector<double> weight;            // [T]
+    std::vector<int32_t> source;           // [T] index of the tree in the forest first created
+    std::vector<int64_t> leaf_offsets{0};  // [T + 1] tips that appear in tours (a lone tip has none)
+    int num_trees() const { return static_cast<int>(weight.size()); }
+};
+
+namespace {
+
+bool is_tip(const scs_forest &f, int64_t base, int64_t count, int64_t k) {
+    // pre-order: a node is a tip iff the next node is not its child
+    return k + 1 >= count || f.parent[base + k + 1] != k;
+}
+
+void finish_tree(scs_forest &f, int64_t base, int64_t count) {
+    int64_t tips = 0;
+    if (count > 1)
+        for (int64_t k = 0; k < count; ++k) tips += f.taxon[base + k] >= 0;
+    f.leaf_offsets.push_back(f.leaf_offsets.back() + tips);
+}
+
+}  // namespace
+
+extern "C" {
+
+int scs_forest_create(int T, const int64_t *node_offsets, const int32_t *parent, const double *length,
+                      const double *support, const int32_t *taxon, const double *tree_weight, int num_taxa,
+                      scs_forest **out) {
+    if (!out) return SCS_ERR_INVALID;
+    *out = nullptr;
+    if (T < 0 || num_taxa < 0 || !node_offsets) return SCS_ERR_INVALID;
+    const int64_t M = node_offsets[T];
+    if (M < 0 || (M > 0 && (!parent || !taxon))) return SCS_ERR_INVALID;
+    if (T > 0 && !tree_weight) return SCS_ERR_INVALID;
+    scs_forest *f = new (std::nothrow) scs_forest();
+    if (!f) return SCS_ERR_INVALID;
+    f->num_taxa = num_taxa;
+    f->node_offsets.assign(node_offsets, node_offsets + T + 1);
+    f->parent.assign(parent, parent + M);
+    f->taxon.assign(taxon, taxon + M);
+    if (length) f->length.assign(length, length + M);
+    else f->length.assign(M, std::nan(""));
+    if (support) f->support.assign(support, support + M);
+    else f->support.assign(M, std::nan(""));
+    f->weight.assign(tree_weight, tree_weight + T);
+    f->source.resize(T);
+    for (int t = 0; t < T; ++t) {
+        f->source[t] = t;
+        const int64_t base = node_offsets[t], count = node_offsets[t + 1] - base;
+        bool ok = count >= 1 && parent[base] == -1;
+        for (int64_t k = 1; ok && k < count; ++k) ok = parent[base + k] >= 0 && parent[base + k] < k;
+        for (int64_t k = 0; ok && k < count; ++k) {
+            const bool tip = is_tip(*f, base, count, k);
+            const int32_t x = taxon[base + k];
+            ok = tip ? (x >= 0 && x < num_taxa) : x == -1;
+        }
+        if (!ok) {
+            delete f;
+            return SCS_ERR_INPUT;
+        }
+        finish_tree(*f, base, count);
+    }
+    *out = f;
+    return SCS_OK;
+}
+
+int scs_forest_destroy(scs_forest *f) {
+    delete f;
+    return SCS_OK;
+}
+
+int scs_forest_num_trees(const scs_forest *f) { return f ? f->num_trees() : 0; }
+int64_t scs_forest_num_nodes(const scs_forest *f) { return f ? f->node_offsets.back() : 0; }
+int64_t scs_forest_num_leaves(const scs_forest *f) { return f ? f->leaf_offsets.back() : 0; }
+int scs_forest_num_taxa(const scs_forest *f) { return f ? f->num_taxa : 0; }
+
+int scs_forest_tree_info(const scs_forest *f, int t, int64_t *num_nodes, double *weight, int32_t *source) {
+    if (!f || t < 0 || t >= f->num_trees()) return SCS_ERR_INVALID;
+    if (num_nodes) *num_nodes = f->node_offsets[t + 1] - f->node_offsets[t];
+    if (weight) *weight = f->weight[t];
+    if (source) *source = f->source[t];
+    return SCS_OK;
+}
+
+int scs_forest_tree(const scs_forest *f, int t, int32_t *parent, double *length, double *support, int32_t *taxon) {
+    if (!f || t < 0 || t >= f->num_trees()) return SCS_ERR_INVALID;
+    const int64_t base = f->node_offsets[t], count = f->node_offsets[t + 1] - base;
+    if (parent) std::memcpy(parent, f->parent.data() + base, sizeof(int32_t) * count);
+    if (length) std::memcpy(length, f->length.data() + base, sizeof(double) * count);
+    if (support) std::memcpy(support, f->support.data() + base, sizeof(double) * count);
+    if (taxon) std::memcpy(taxon, f->taxon.data() + base, sizeof(int32_t) * count);
+    return SCS_OK;
+}
+
+/* present[x] = 1 iff taxon x is a tip of some tree (scs.py:708-725); returns how many are. */
+int scs_forest_taxa(const scs_forest *f, uint8_t *present) {
+    if (!f || !present) return SCS_ERR_INVALID;
+    std::memset(present, 0, f->num_taxa);
+    int n = 0;
+    for (int32_t x : f->taxon)
+        if (x >= 0 && !present[x]) {
+            present[x] = 1;
+            ++n;
+        }
+    return n;
+}
+
+int scs_forest_induce(const scs_forest *f, const uint8_t *keep, scs_forest **out) {
+    if (!f || !keep || !out) return SCS_ERR_INVALID;
+    *out = nullptr;
+    scs_forest *g = new (std::nothrow) scs_forest();
+    if (!g) return SCS_ERR_INVALID;
+    g->num_taxa = f->num_taxa;
+    std::vector<int32_t> cnt, live_children, new_index;
+    for (int t = 0; t < f->num_trees(); ++t) {
+        const int64_t base = f->node_offsets[t], count = f->node_offsets[t + 1] - base;
+        const int32_t *par = f->parent.data() + base;
+        const int32_t *tax = f->taxon.data() + base;
+        const double *len = f->length.data() + base;
+        const double *sup = f->support.data() + base;
+        cnt.assign(count, 0);
+        live_children.assign(count, 0);
+        for (int64_t k = 0; k < count; ++k)
+            if (tax[k] >= 0 && keep[tax[k]]) cnt[k] = 1;
+        for (int64_t k = count - 1; k >= 1; --k) cnt[par[k]] += cnt[k];
+        if (cnt[0] < 2) continue;  // scs.py:447-448
+        for (int64_t k = 1; k < count; ++k)
+            if (cnt[k] > 0) live_children[par[k]] += 1;
+        // retained: kept tips and nodes that still branch
+        new_index.assign(count, -1);
+        const int64_t out_base = static_cast<int64_t>(g->parent.size());
+        int32_t next = 0;
+        for (int64_t k = 0; k < count; ++k) {
+            const bool retained = cnt[k] > 0 && (tax[k] >= 0 || live_children[k] >= 2);
+            if (!retained) continue;
+            new_index[k] = next++;
+            if (new_index[k] == 0) {  // first retained node in pre-order: the new root
+                g->parent.push_back(-1);
+                g->length.push_back(std::nan(""));
+            } else {
+                double acc = len[k];
+                int64_t a = par[k];
+                while (new_index[a] < 0) {  // merged unary ancestors, bottom-up
+                    acc = len[a] + acc;     // NaN (missing) propagates like None
+                    a = par[a];
+                }
+                g->parent.push_back(new_index[a]);
+                g->length.push_back(acc);
+            }
+            g->support.push_back(sup[k]);
+            g->taxon.push_back(tax[k]);
+        }
+        g->node_offsets.push_back(out_base + next);
+        g->weight.push_back(f->weight[t]);
+        g->source.push_back(f->source[t]);
+        finish_tree(*g, out_base, next);
+    }
+    *out = g;
+    return SCS_OK;
+}
+
+/* weighting: 0 one, 1 branch, 2 depth, 3 bootstrap (order of the reference's docs, scs.py:41-50).
+ * local_id[x] = vertex id of global taxon x at this recursion node.
+ * Returns SCS_ERR_INPUT if bootstrap weighting meets an internal node without support that is the
+ * LCA of a leaf pair (the reference raises TypeError there: None * weight, scs.py:655-657). */
+int scs_forest_tours(const scs_forest *f, int weighting, const int32_t *local_id, int64_t *leaf_offsets,
+                     int32_t *leaf_taxon, int32_t *adj_depth, double *adj_val, int32_t *root_depth,
+                     double *tree_weight) {
+    if (!f || !local_id || !leaf_offsets || weighting < 0 || weighting > 3) return SCS_ERR_INVALID;
+    const int T = f->num_trees();
+    if (f->leaf_offsets.back() > 0 && (!leaf_taxon || !adj_depth || !adj_val)) return SCS_ERR_INVALID;
+    if (T > 0 && (!root_depth || !tree_weight)) return SCS_ERR_INVALID;
+    std::vector<int32_t> depth;
+    std::vector<double> val;
+    int status = SCS_OK;
+    leaf_offsets[0] = 0;
+    for (int t = 0; t < T; ++t) {
+        const int64_t base = f->node_offsets[t], count = f->node_offsets[t + 1] - base;
+        const int32_t *par = f->parent.data() + base;
+        const int32_t *tax = f->taxon.data() + base;
+        const double *len = f->length.data() + base;
+        const double *sup = f->support.data() + base;
+        int64_t o = f->leaf_offsets[t];
+        leaf_offsets[t + 1] = f->leaf_offsets[t + 1];
+        root_depth[t] = 0;
+        tree_weight[t] = f->weight[t];
+        if (count <= 1) continue;  // a lone tip has no sides (scs.py:570)
+        depth.assign(count, 0);
+        val.assign(count, 0.0);  // the value handed to the root's children is 0 (scs.py:577)
+        for (int64_t k = 1; k < count; ++k) {
+            if (tax[k] >= 0) continue;
+            const int32_t p = par[k];
+            depth[k] = depth[p] + 1;
+            switch (weighting) {
+            case 0: val[k] = 1.0; break;
+            case 1: val[k] = val[p] + (std::isnan(len[k]) ? 1.0 : len[k]); break;
+            case 2: val[k] = val[p] + 1.0; break;
+            default: val[k] = sup[k]; break;
+            }
+        }
+        for (int64_t k = 0; k < count; ++k) {
+            if (tax[k] < 0) continue;
+            leaf_taxon[o] = local_id[tax[k]];
+            if (k + 1 < count) {
+                const int32_t lca = par[k + 1];  // the next pre-order node hangs off the LCA with the next tip
+                adj_depth[o] = depth[lca];
+                adj_val[o] = val[lca];
+                if (lca != 0 && std::isnan(val[lca])) status = SCS_ERR_INPUT;
+            } else {
+                adj_depth[o] = -1;
+                adj_val[o] = 0.0;
+            }
+            ++o;
+        }
+    }
+    return status;
+}
+
+/* Number of ordered leaf pairs the row kernel visits: sum over trees of k (k - 1). */
+int64_t scs_forest_pair_visits(const scs_forest *f) {
+    if (!f) return 0;
+    int64_t total = 0;
+    for (int t = 0; t < f->num_trees(); ++t) {
+        const int64_t k = f->leaf_offsets[t + 1] - f->leaf_offsets[t];
+        total += k * (k - 1);
+    }
+    return total;
+}
+
+/* One recursion node straight from a forest (scs.py:102-134): the vertices are the taxa present,
+ * numbered in increasing global id; taxa_out[n] receives their global ids and part_out[n] the
+ * component index or spectral side of each.  taxa_out / part_out must hold num_taxa entries. */
+int scs_forest_split(scs_ctx *ctx, const scs_forest *f, int weighting, int contract_edges, uint64_t seed,
+                     int32_t *n_out, int32_t *taxa_out, int32_t *part_out, scs_node_stats *stats) {
+    if (!ctx || !f || !n_out || !taxa_out || !part_out) return SCS_ERR_INVALID;
+    std::vector<uint8_t> present(f->num_taxa ? f->num_taxa : 1);
+    const int n = scs_forest_taxa(f, present.data());
+    std::vector<int32_t> local(f->num_taxa ? f->num_taxa : 1, -1);
+    int next = 0;
+    for (int x = 0; x < f->num_taxa; ++x)
+        if (present[x]) {
+            local[x] = next;
+            taxa_out[next++] = x;
+        }
+    *n_out = n;
+    if (n == 0) return SCS_ERR_INVALID;
+    const int T = f->num_trees();
+    const int64_t L = f->leaf_offsets.back();
+    std::vector<int64_t> leaf_offsets(T + 1);
+    std::vector<int32_t> leaf_taxon(L + 1), adj_depth(L + 1), root_depth(T + 1);
+    std::vector<double> adj_val(L + 1), tree_weight(T + 1);
+    int rc = scs_forest_tours(f, weighting, local.data(), leaf_offsets.data(), leaf_taxon.data(), adj_depth.data(),
+                              adj_val.data(), root_depth.data(), tree_weight.data());
+    if (rc) return rc;
+    return scs_node_split_host(ctx, n, T, L, leaf_offsets.data(), leaf_taxon.data(), adj_depth.data(),
+                               adj_val.data(), root_depth.data(), tree_weight.data(), contract_edges, seed, part_out,
+                               stats);
+}
+
+}  // extern "C"

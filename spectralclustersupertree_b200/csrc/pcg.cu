@@ -1,0 +1,392 @@
+// Proper-cluster-graph build on the GPU.
+//
+// Replaces _proper_cluster_graph_edges + _dfs_pcg_weights of the reference
+// (/root/reference/src/sc_supertree/scs.py:495-583, 586-663).
+//
+// Layout.  Source trees arrive as leaf tours (flatten.py): leaves in depth-first order and, for
+// consecutive leaves i, i+1, the depth and weighting value of their LCA.  For a leaf at tour
+// position p, the LCA with the leaf at position q > p is the shallowest entry of adj[p..q-1]; for
+// q < p of adj[q..p-1].  So one leaf's whole row of contributions from one tree is two running
+// minima walking away from p -- a segmented min-scan, no pointer chasing and no RMQ table.
+//
+// Kernel shape.  One CTA owns one row `a` of W (one taxon) and keeps the row's accumulators in
+// shared memory (8 B weight + 2/4 B count per column).  It visits the trees containing `a` in
+// input order; for each, the CTA scans the tour outward from a's position and adds
+// fl(val(LCA) * w_t) to the column of every other leaf whose LCA with `a` is not the root
+// (scs.py:570-579, 644-658).  Within a tree every leaf is a distinct column, so threads never
+// collide; trees are separated by the scan's __syncthreads, so every W entry is summed in tree
+// input order with separately rounded multiply and add (scs.py:655-657) -- bit-identical to the
+// reference, no atomics on W, and W[a][b] == W[b][a] bit for bit.  The finished row is written
+// once, coalesced, together with its adjacency bits (C > 0, scs.py:651-652), max-graph bits
+// (C == max(occ_a, occ_b), scs.py:302-305) and its row sum (the degree the spectral step needs),
+// so the co-occurrence matrix never has to be written to HBM unless the caller asks for it.
+//
+// Rows wider than shared memory (n > ~22k columns) are split into column chunks (gridDim.y);
+// each chunk CTA rescans the same tours and keeps only its columns.
+
+#include "common.cuh"
+
+namespace scs {
+
+namespace {
+
+constexpr int kRowThreads = 256;
+constexpr int kPerThread = 4;  // tour elements per thread per tile
+constexpr int kTile = kRowThreads * kPerThread;
+constexpr int kWarps = kRowThreads / 32;
+constexpr unsigned long long kNoKey = ~0ull;
+
+// ---- index: leaf -> tree, occurrences, taxon -> leaves ------------------------------------
+__global__ void pcg_index_leaves(int n, int T, int64_t L, const int64_t *__restrict__ leaf_offsets,
+                                 const int32_t *__restrict__ leaf_taxon, int32_t *__restrict__ leaf_tree,
+                                 int32_t *__restrict__ occ, int32_t *__restrict__ bad) {
+    int64_t g = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (g >= L) return;
+    int lo = 0, hi = T;  // largest t with leaf_offsets[t] <= g
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (leaf_offsets[mid] <= g) lo = mid; else hi = mid;
+    }
+    leaf_tree[g] = lo;
+    int a = leaf_taxon[g];
+    if (a < 0 || a >= n) { *bad = 1; return; }
+    atomicAdd(&occ[a], 1);
+}
+
+// out[i] = sum of in[0..i), out[n] = total.  One block.
+__global__ void exclusive_scan_i32(int n, const int32_t *__restrict__ in, int32_t *__restrict__ out) {
+    __shared__ int32_t warp_sum[32];
+    __shared__ int32_t carry_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += blockDim.x) {
+        int i = base + threadIdx.x;
+        int32_t v = i < n ? in[i] : 0;
+        int32_t inc = v;
+        for (int off = 1; off < 32; off <<= 1) {
+            int32_t o = __shfl_up_sync(0xffffffffu, inc, off);
+            if (lane >= off) inc += o;
+        }
+        if (lane == 31) warp_sum[warp] = inc;
+        __syncthreads();
+        int32_t before = carry_s;
+        for (int w = 0; w < warp; ++w) before += warp_sum[w];
+        if (i < n) out[i] = before + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int32_t tot = carry_s;
+            for (int w = 0; w < nwarp; ++w) tot += warp_sum[w];
+            carry_s = tot;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[n] = carry_s;
+}
+
+__global__ void pcg_fill_inverse(int n, int64_t L, const int32_t *__restrict__ leaf_taxon,
+                                 const int32_t *__restrict__ row_ptr, int32_t *__restrict__ cursor,
+                                 int32_t *__restrict__ inv) {
+    int64_t g = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (g >= L) return;
+    int a = leaf_taxon[g];
+    if (a < 0 || a >= n) return;  // flagged by pcg_index_leaves
+    int slot = atomicAdd(&cursor[a], 1);
+    inv[row_ptr[a] + slot] = static_cast<int32_t>(g);
+}
+
+// The atomics above leave each taxon's leaf list in arbitrary order; leaves are numbered tree
+// by tree, so sorting a list ascending restores tree input order.  Rank sort, one CTA per row.
+__global__ void pcg_sort_inverse(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ inv,
+                                 int32_t *__restrict__ inv_sorted) {
+    __shared__ int32_t stage[1024];
+    const int a = blockIdx.x;
+    const int base = row_ptr[a];
+    const int cnt = row_ptr[a + 1] - base;
+    for (int i0 = 0; i0 < cnt; i0 += blockDim.x) {
+        const int i = i0 + threadIdx.x;
+        const int32_t mine = i < cnt ? inv[base + i] : 0;
+        int rank = 0;
+        for (int j0 = 0; j0 < cnt; j0 += 1024) {
+            const int len = min(1024, cnt - j0);
+            __syncthreads();
+            for (int j = threadIdx.x; j < len; j += blockDim.x) stage[j] = inv[base + j0 + j];
+            __syncthreads();
+            if (i < cnt)
+                for (int j = 0; j < len; ++j) rank += stage[j] < mine;
+        }
+        if (i < cnt) inv_sorted[base + rank] = mine;
+    }
+}
+
+// ---- the row kernel -----------------------------------------------------------------------
+struct SegKey {
+    unsigned long long key;  // (depth << 32) | tour index of the adjacent-LCA entry
+    bool head;               // a segment start lies at or before this element (within the scope)
+};
+
+__device__ __forceinline__ SegKey seg_combine(const SegKey &left, const SegKey &right) {
+    SegKey r;
+    r.key = right.head ? right.key : (left.key < right.key ? left.key : right.key);
+    r.head = left.head || right.head;
+    return r;
+}
+
+template <typename CountT, bool kWriteC>
+__global__ void __launch_bounds__(kRowThreads)
+pcg_rows_kernel(int n, int words_per_row, int cols_per_chunk,
+                const int64_t *__restrict__ leaf_offsets, const int32_t *__restrict__ leaf_taxon,
+                const int32_t *__restrict__ adj_depth, const double *__restrict__ adj_val,
+                const int32_t *__restrict__ root_depth, const double *__restrict__ tree_weight,
+                const int32_t *__restrict__ leaf_tree, const int32_t *__restrict__ row_ptr,
+                const int32_t *__restrict__ inv_sorted, const int32_t *__restrict__ occ,
+                double *__restrict__ W, int32_t *__restrict__ C, uint32_t *__restrict__ adj_bits,
+                uint32_t *__restrict__ max_bits, double *__restrict__ degree_part) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *accW = reinterpret_cast<double *>(smem_raw);
+    CountT *accC = reinterpret_cast<CountT *>(accW + cols_per_chunk);
+    __shared__ unsigned long long warp_key[2][kWarps];
+    __shared__ int warp_head[2][kWarps];
+    __shared__ double warp_sum[kWarps];
+
+    const int a = blockIdx.x;
+    const int col0 = blockIdx.y * cols_per_chunk;
+    const int ncols = min(cols_per_chunk, n - col0);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (int c = tid; c < cols_per_chunk; c += kRowThreads) {
+        accW[c] = 0.0;
+        accC[c] = 0;
+    }
+    // the first tile's __syncthreads orders this initialisation before any update
+
+    const int ebase = row_ptr[a];
+    const int cnt = row_ptr[a + 1] - ebase;
+    int parity = 0;
+    for (int ei = 0; ei < cnt; ++ei) {
+        const int g = inv_sorted[ebase + ei];
+        const int t = leaf_tree[g];
+        const int64_t tb = leaf_offsets[t];
+        const int k = static_cast<int>(leaf_offsets[t + 1] - tb);
+        const int p = static_cast<int>(g - tb);
+        const double w = tree_weight[t];
+        const int rd = root_depth[t];
+        const int nv = k - 1;  // virtual sequence: v < p walks left from p, v >= p walks right
+        const int32_t *depth_t = adj_depth + tb;
+        const double *val_t = adj_val + tb;
+        const int32_t *taxon_t = leaf_taxon + tb;
+
+        unsigned long long carry = kNoKey;  // running minimum entering the tile
+        for (int v0 = 0; v0 < nv; v0 += kTile) {
+            const int vb = v0 + tid * kPerThread;
+            unsigned long long pre[kPerThread];
+            unsigned long long run = kNoKey;
+            bool head = false;
+#pragma unroll
+            for (int e = 0; e < kPerThread; ++e) {
+                const int v = vb + e;
+                unsigned long long key = kNoKey;
+                if (v < nv) {
+                    const int kidx = v < p ? p - 1 - v : v;
+                    key = (static_cast<unsigned long long>(static_cast<uint32_t>(depth_t[kidx])) << 32) |
+                          static_cast<uint32_t>(kidx);
+                }
+                if (v == p) {  // the right-hand walk starts here
+                    run = kNoKey;
+                    head = true;
+                }
+                run = key < run ? key : run;
+                pre[e] = run;
+            }
+            // inclusive segmented scan of the per-thread aggregates across the warp
+            SegKey agg{run, head};
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                SegKey left;
+                left.key = __shfl_up_sync(0xffffffffu, agg.key, off);
+                left.head = __shfl_up_sync(0xffffffffu, static_cast<int>(agg.head), off) != 0;
+                if (lane >= off) agg = seg_combine(left, agg);
+            }
+            if (lane == 31) {
+                warp_key[parity][warp] = agg.key;
+                warp_head[parity][warp] = agg.head;
+            }
+            SegKey excl;  // aggregate of the preceding lanes of this warp
+            excl.key = __shfl_up_sync(0xffffffffu, agg.key, 1);
+            excl.head = __shfl_up_sync(0xffffffffu, static_cast<int>(agg.head), 1) != 0;
+            if (lane == 0) excl = SegKey{kNoKey, false};
+            __syncthreads();
+            SegKey before{carry, false};  // everything before this warp, tile carry included
+            SegKey total{carry, false};
+#pragma unroll
+            for (int wi = 0; wi < kWarps; ++wi) {
+                SegKey wa{warp_key[parity][wi], warp_head[parity][wi] != 0};
+                if (wi < warp) before = seg_combine(before, wa);
+                total = seg_combine(total, wa);
+            }
+            carry = total.key;
+            parity ^= 1;
+            const SegKey enter = seg_combine(before, excl);
+
+            bool seen_head = false;
+#pragma unroll
+            for (int e = 0; e < kPerThread; ++e) {
+                const int v = vb + e;
+                if (v == p) seen_head = true;
+                if (v < nv) {
+                    unsigned long long m = pre[e];
+                    if (!seen_head && enter.key < m) m = enter.key;
+                    const int d = static_cast<int>(m >> 32);
+                    if (d != rd) {
+                        const int q = v < p ? p - 1 - v : v + 1;
+                        const int c = taxon_t[q] - col0;
+                        if (static_cast<unsigned>(c) < static_cast<unsigned>(ncols)) {
+                            const double term = __dmul_rn(val_t[static_cast<uint32_t>(m)], w);
+                            accW[c] = __dadd_rn(accW[c], term);
+                            accC[c] = static_cast<CountT>(accC[c] + 1);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- write the finished row --------------------------------------------------------------
+    const int occ_a = occ[a];
+    double *Wrow = W + static_cast<size_t>(a) * n + col0;
+    double partial = 0.0;
+    for (int c = tid; c < ncols; c += kRowThreads) {
+        const double x = accW[c];
+        Wrow[c] = x;
+        partial += x;
+        if (kWriteC) C[static_cast<size_t>(a) * n + col0 + c] = static_cast<int32_t>(accC[c]);
+    }
+    const int word0 = col0 >> 5;
+    const int nwords = (ncols + 31) >> 5;
+    for (int j = warp; j < nwords; j += kWarps) {
+        const int c = (j << 5) + lane;
+        bool edge = false, top = false;
+        if (c < ncols) {
+            const int cc = static_cast<int>(accC[c]);
+            edge = cc > 0;
+            if (edge && max_bits != nullptr) top = cc == max(occ_a, occ[col0 + c]);
+        }
+        const uint32_t eb = __ballot_sync(0xffffffffu, edge);
+        const uint32_t tb2 = __ballot_sync(0xffffffffu, top);
+        if (lane == 0) {
+            adj_bits[static_cast<size_t>(a) * words_per_row + word0 + j] = eb;
+            if (max_bits != nullptr) max_bits[static_cast<size_t>(a) * words_per_row + word0 + j] = tb2;
+        }
+    }
+    // row sum in a fixed order: strided per-thread sums, shuffle tree, then warps in order
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) partial += __shfl_down_sync(0xffffffffu, partial, off);
+    if (lane == 0) warp_sum[warp] = partial;
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0.0;
+        for (int wi = 0; wi < kWarps; ++wi) s += warp_sum[wi];
+        degree_part[static_cast<size_t>(blockIdx.y) * n + a] = s;
+    }
+}
+
+__global__ void pcg_sum_degree_parts(int n, int nchunks, const double *__restrict__ part, double *__restrict__ degree) {
+    int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    double s = 0.0;
+    for (int c = 0; c < nchunks; ++c) s += part[static_cast<size_t>(c) * n + a];
+    degree[a] = s;
+}
+
+template <typename CountT, bool kWriteC>
+int launch_rows(scs_ctx *ctx, int n, int words, int cols_per_chunk, int nchunks, size_t smem,
+                const int64_t *leaf_offsets, const int32_t *leaf_taxon, const int32_t *adj_depth,
+                const double *adj_val, const int32_t *root_depth, const double *tree_weight,
+                const int32_t *leaf_tree, const int32_t *row_ptr, const int32_t *inv_sorted,
+                const int32_t *occ, double *W, int32_t *C, uint32_t *adj_bits, uint32_t *max_bits,
+                double *degree_part) {
+    auto kernel = pcg_rows_kernel<CountT, kWriteC>;
+    SCS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    dim3 grid(n, nchunks);
+    kernel<<<grid, kRowThreads, smem, ctx->stream>>>(n, words, cols_per_chunk, leaf_offsets, leaf_taxon, adj_depth,
+                                                     adj_val, root_depth, tree_weight, leaf_tree, row_ptr,
+                                                     inv_sorted, occ, W, C, adj_bits, max_bits, degree_part);
+    SCS_LAUNCHED(ctx, "pcg_rows_kernel");
+    return SCS_OK;
+}
+
+}  // namespace
+
+int exclusive_scan(scs_ctx *ctx, int n, const int32_t *in, int32_t *out) {
+    exclusive_scan_i32<<<1, 1024, 0, ctx->stream>>>(n, in, out);
+    SCS_LAUNCHED(ctx, "exclusive_scan_i32");
+    return SCS_OK;
+}
+
+int pcg_build(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offsets,
+              const int32_t *leaf_taxon, const int32_t *adj_depth, const double *adj_val,
+              const int32_t *root_depth, const double *tree_weight, double *W, int32_t *C,
+              int32_t *occ, uint32_t *adj_bits, uint32_t *max_bits, double *degree) {
+    if (n <= 0 || T < 0 || L < 0 || L >= (1ll << 31) || !W || !occ || !adj_bits)
+        return fail(ctx, SCS_ERR_INVALID, "pcg_build: bad argument");
+    if (T > 0 && (!leaf_offsets || !root_depth || !tree_weight))
+        return fail(ctx, SCS_ERR_INVALID, "pcg_build: null tour array");
+    if (L > 0 && (!leaf_taxon || !adj_depth || !adj_val))
+        return fail(ctx, SCS_ERR_INVALID, "pcg_build: null tour array");
+    const int words = scs_bit_words(n);
+
+    int32_t *leaf_tree, *row_ptr, *cursor, *inv, *inv_sorted, *scalars;
+    double *degree_part;
+    int rc;
+    if ((rc = reserve_as(ctx, SLOT_LEAF_TREE, static_cast<size_t>(L) + 1, &leaf_tree))) return rc;
+    if ((rc = reserve_as(ctx, SLOT_ROW_PTR, static_cast<size_t>(n) + 1, &row_ptr))) return rc;
+    if ((rc = reserve_as(ctx, SLOT_CURSOR, static_cast<size_t>(n), &cursor))) return rc;
+    if ((rc = reserve_as(ctx, SLOT_INV, static_cast<size_t>(L) + 1, &inv))) return rc;
+    if ((rc = reserve_as(ctx, SLOT_INV_SORTED, static_cast<size_t>(L) + 1, &inv_sorted))) return rc;
+    if ((rc = reserve_as(ctx, SLOT_SCALARS, 64, &scalars))) return rc;
+
+    SCS_CUDA(ctx, cudaMemsetAsync(occ, 0, sizeof(int32_t) * n, ctx->stream));
+    SCS_CUDA(ctx, cudaMemsetAsync(cursor, 0, sizeof(int32_t) * n, ctx->stream));
+    SCS_CUDA(ctx, cudaMemsetAsync(scalars, 0, sizeof(int32_t) * 64, ctx->stream));
+    if (L > 0) {
+        pcg_index_leaves<<<ceil_div(L, 256), 256, 0, ctx->stream>>>(n, T, L, leaf_offsets, leaf_taxon, leaf_tree, occ,
+                                                                   scalars);
+        SCS_LAUNCHED(ctx, "pcg_index_leaves");
+    }
+    if ((rc = exclusive_scan(ctx, n, occ, row_ptr))) return rc;
+    if (L > 0) {
+        pcg_fill_inverse<<<ceil_div(L, 256), 256, 0, ctx->stream>>>(n, L, leaf_taxon, row_ptr, cursor, inv);
+        SCS_LAUNCHED(ctx, "pcg_fill_inverse");
+        pcg_sort_inverse<<<n, 128, 0, ctx->stream>>>(row_ptr, inv, inv_sorted);
+        SCS_LAUNCHED(ctx, "pcg_sort_inverse");
+    }
+
+    // column chunking: the whole row if it fits in shared memory, else equal chunks of 32-multiples
+    const bool narrow = T < 65536;
+    const size_t per_col = sizeof(double) + (narrow ? sizeof(uint16_t) : sizeof(int32_t));
+    const size_t budget = ctx->smem_optin > 4096 ? ctx->smem_optin - 2048 : 46 * 1024;
+    const int max_cols = static_cast<int>((budget / per_col) / 32 * 32);
+    const int padded = words * 32;
+    int nchunks = ceil_div(padded, max_cols);
+    int cols_per_chunk = ceil_div(ceil_div(padded, nchunks), 32) * 32;
+    nchunks = ceil_div(n, cols_per_chunk);
+    const size_t smem = static_cast<size_t>(cols_per_chunk) * per_col + 16;
+    if ((rc = reserve_as(ctx, SLOT_DEGREE_PART, static_cast<size_t>(n) * nchunks, &degree_part))) return rc;
+
+#define SCS_ROWS(CT, WC)                                                                                       \
+    launch_rows<CT, WC>(ctx, n, words, cols_per_chunk, nchunks, smem, leaf_offsets, leaf_taxon, adj_depth,    \
+                        adj_val, root_depth, tree_weight, leaf_tree, row_ptr, inv_sorted, occ, W, C, adj_bits, \
+                        max_bits, degree_part)
+    if (narrow) rc = C ? SCS_ROWS(uint16_t, true) : SCS_ROWS(uint16_t, false);
+    else rc = C ? SCS_ROWS(int32_t, true) : SCS_ROWS(int32_t, false);
+#undef SCS_ROWS
+    if (rc) return rc;
+    if (degree) {
+        pcg_sum_degree_parts<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(n, nchunks, degree_part, degree);
+        SCS_LAUNCHED(ctx, "pcg_sum_degree_parts");
+    }
+    return SCS_OK;
+}
+
+}  // namespace scs

@@ -1,0 +1,740 @@
+// Spectral bipartition of the (contracted) proper cluster graph on the GPU.
+//
+// Replaces spectral_cluster_graph of the reference (/root/reference/src/sc_supertree/scs.py:210-258),
+// i.e. sklearn.cluster.SpectralClustering(2, affinity="precomputed", assign_labels="kmeans"):
+//   L = I - D^-1/2 W D^-1/2   (scipy csgraph.laplacian(normed=True): degree 0 is scaled by 1)
+//   x_0, x_1 = eigenvectors of the two smallest eigenvalues (sklearn: shift-invert ARPACK after a
+//              dense LU of L); embedding rows u_k = x_k / sqrt(d); sign flip; 2-means.
+//
+// Here nothing is factorised.  With N = D^-1/2 W D^-1/2 the smallest eigenpair of L is known in
+// closed form (eigenvalue 0, x_0 = sqrt(d) / |sqrt(d)|), so the Fiedler pair is the LARGEST
+// eigenpair of N on the orthogonal complement of x_0: Lanczos with full (twice-applied classical
+// Gram-Schmidt) re-orthogonalisation against x_0 and the whole basis.  The operator is the fused
+// matvec  y = isd .* (W (isd .* v))  -- W is read once per application, straight from HBM, in
+// fp64 (the parity contract needs a 1e-3 tree-weight difference and 1e-6 eigenvalues to survive).
+// The projected tridiagonal problem is solved on the device (Sturm multi-section + twisted
+// factorisation), so the host only reads back a residual estimate to decide when to stop.
+// u_0 is constant on a connected graph, so sklearn's 2-means on (u_0, u_1) is 1-D 2-means on the
+// Fiedler coordinate; it is solved exactly (sort, prefix sums, best split) instead of by ten
+// random Lloyd restarts, which makes the partition deterministic.
+
+#include "common.cuh"
+
+#include <cmath>
+
+namespace scs {
+
+namespace {
+
+constexpr int kMaxBasis = 256;        // Lanczos vectors per (re)start
+constexpr int kMaxRestarts = 8;
+constexpr double kResidualTol = 1e-12;  // |beta_j s_j| of the Fiedler Ritz pair (|N| <= 1)
+constexpr double kBreakdown = 1e-13;
+constexpr double kGapTie = 1e-7;      // lambda_3 - lambda_2 below this: eigenvector is ill-defined
+constexpr double kMarginTie = 1e-9;   // a vertex this close (relative) to the 2-means boundary
+
+constexpr int kMvThreads = 256;
+constexpr int kVecThreads = 256;
+constexpr int kOneCta = 1024;
+
+// ---- small helpers --------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    return v;
+}
+
+// Sum over the block in a fixed order; result valid in every thread.  `scratch` holds 33 doubles.
+__device__ __forceinline__ double block_sum(double v, double *scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();  // scratch may still be read from a previous call
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        double t = lane < nwarp ? scratch[lane] : 0.0;
+        t = warp_sum(t);
+        if (lane == 0) scratch[32] = t;
+    }
+    __syncthreads();
+    return scratch[32];
+}
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+// ---- degree and scaling ---------------------------------------------------------------------
+// one warp per row: d[a] = sum_b W[a][b]   (scipy _laplacian.py:543: column sums of a symmetric matrix)
+__global__ void row_sums(int m, const double *__restrict__ W, double *__restrict__ degree) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= m) return;
+    const double *w = W + static_cast<size_t>(row) * m;
+    double acc = 0.0;
+    for (int j = lane; j < m; j += 32) acc += w[j];
+    acc = warp_sum(acc);
+    if (lane == 0) degree[row] = acc;
+}
+
+// isd = 1/sqrt(d) (1 where d == 0, scipy _laplacian.py:544-545); q0 = sqrt(d)/|sqrt(d)|; one CTA.
+// flags[0] is raised if a degree is negative or not finite (sklearn would produce NaNs there).
+__global__ void __launch_bounds__(kOneCta)
+prepare_scaling(int m, const double *__restrict__ degree, double *__restrict__ isd, double *__restrict__ q0,
+                int32_t *__restrict__ flags) {
+    __shared__ double scratch[33];
+    double vol = 0.0;
+    bool bad = false;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        const double d = degree[i];
+        if (!(d >= 0.0) || isinf(d)) bad = true;
+        vol += d > 0.0 ? d : 0.0;
+    }
+    vol = block_sum(vol, scratch);
+    if (bad) flags[0] = 1;
+    const double inv_norm = vol > 0.0 ? 1.0 / sqrt(vol) : 0.0;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        const double d = degree[i];
+        const double s = d > 0.0 ? sqrt(d) : 0.0;
+        isd[i] = d > 0.0 ? 1.0 / s : 1.0;
+        q0[i] = s * inv_norm;
+    }
+}
+
+__global__ void scale_vector(int m, const double *__restrict__ isd, const double *__restrict__ x,
+                             double *__restrict__ z) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) z[i] = isd[i] * x[i];
+}
+
+// ---- the operator: y = isd .* (W z) ----------------------------------------------------------
+// Streams W exactly once with 16-byte loads that bypass L1 allocation; z (8 m bytes) stays in
+// L1/L2.  Rows are 8 m bytes apart, so odd rows of an odd-m matrix start on an 8-byte boundary:
+// each row is split into an optional 1-element head, an aligned double2 body and a tail.
+__device__ __forceinline__ double2 load_stream(const double2 *p) {
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+
+// Partial dot product of one row with z over the calling group of `nthr` threads (`t` = rank).
+__device__ __forceinline__ double row_dot_partial(const double *__restrict__ row, const double *__restrict__ z,
+                                                  int m, int t, int nthr) {
+    const int head = static_cast<int>((reinterpret_cast<uintptr_t>(row) >> 3) & 1u);
+    const int nvec = (m - head) >> 1;
+    const double2 *body = reinterpret_cast<const double2 *>(row + head);
+    const double *zb = z + head;
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+    int v = t;
+    // four independent 16-byte loads in flight per thread per iteration
+    for (; v + 3 * nthr < nvec; v += 4 * nthr) {
+        const double2 a = load_stream(body + v);
+        const double2 b = load_stream(body + v + nthr);
+        const double2 c = load_stream(body + v + 2 * nthr);
+        const double2 d = load_stream(body + v + 3 * nthr);
+        acc0 = fma(a.x, zb[2 * v], acc0);
+        acc0 = fma(a.y, zb[2 * v + 1], acc0);
+        acc1 = fma(b.x, zb[2 * (v + nthr)], acc1);
+        acc1 = fma(b.y, zb[2 * (v + nthr) + 1], acc1);
+        acc2 = fma(c.x, zb[2 * (v + 2 * nthr)], acc2);
+        acc2 = fma(c.y, zb[2 * (v + 2 * nthr) + 1], acc2);
+        acc3 = fma(d.x, zb[2 * (v + 3 * nthr)], acc3);
+        acc3 = fma(d.y, zb[2 * (v + 3 * nthr) + 1], acc3);
+    }
+    for (; v < nvec; v += nthr) {
+        const double2 a = load_stream(body + v);
+        acc0 = fma(a.x, zb[2 * v], acc0);
+        acc0 = fma(a.y, zb[2 * v + 1], acc0);
+    }
+    double acc = (acc0 + acc1) + (acc2 + acc3);
+    if (t == 0) {
+        if (head) acc = fma(row[0], z[0], acc);
+        if ((m - head) & 1) acc = fma(row[m - 1], z[m - 1], acc);
+    }
+    return acc;
+}
+
+// one CTA per row (m large: a row is tens of KB)
+__global__ void __launch_bounds__(kMvThreads)
+matvec_row_per_cta(int m, const double *__restrict__ W, const double *__restrict__ isd,
+                   const double *__restrict__ z, double *__restrict__ y) {
+    __shared__ double part[kMvThreads / 32];
+    const int row = blockIdx.x;
+    double acc = row_dot_partial(W + static_cast<size_t>(row) * m, z, m, threadIdx.x, kMvThreads);
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < kMvThreads / 32; ++w) s += part[w];
+        y[row] = isd[row] * s;
+    }
+}
+
+// one warp per row (m small: the whole matrix is L2-resident and rows are short)
+__global__ void __launch_bounds__(kMvThreads)
+matvec_row_per_warp(int m, const double *__restrict__ W, const double *__restrict__ isd,
+                    const double *__restrict__ z, double *__restrict__ y) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= m) return;
+    double acc = row_dot_partial(W + static_cast<size_t>(row) * m, z, m, lane, 32);
+    acc = warp_sum(acc);
+    if (lane == 0) y[row] = isd[row] * acc;
+}
+
+int launch_matvec(scs_ctx *ctx, int m, const double *W, const double *isd, const double *z, double *y) {
+    if (m >= 2048) {
+        matvec_row_per_cta<<<m, kMvThreads, 0, ctx->stream>>>(m, W, isd, z, y);
+        SCS_LAUNCHED(ctx, "matvec_row_per_cta");
+    } else {
+        matvec_row_per_warp<<<ceil_div(static_cast<int64_t>(m) * 32, kMvThreads), kMvThreads, 0, ctx->stream>>>(
+            m, W, isd, z, y);
+        SCS_LAUNCHED(ctx, "matvec_row_per_warp");
+    }
+    return SCS_OK;
+}
+
+// ---- Lanczos vector kernels ------------------------------------------------------------------
+// start vector: uniform(-1, 1) from a counter-based generator (sklearn: random_state.uniform(-1, 1, n),
+// _arpack.py:31-33)
+__global__ void random_start(int m, uint64_t seed, double *__restrict__ w) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const uint64_t r = splitmix64(seed * 0xD1342543DE82EF95ull + static_cast<uint64_t>(i) + 1ull);
+    w[i] = 2.0 * (static_cast<double>(r >> 11) * (1.0 / 9007199254740992.0)) - 1.0;
+}
+
+// h[k] = basis[k] . w   for k in [0, nb); one CTA per basis vector, fixed summation order
+__global__ void __launch_bounds__(kVecThreads)
+multi_dot(int m, const double *__restrict__ basis, const double *__restrict__ w, double *__restrict__ h) {
+    __shared__ double scratch[33];
+    const double *b = basis + static_cast<size_t>(blockIdx.x) * m;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < m; i += kVecThreads) acc = fma(b[i], w[i], acc);
+    acc = block_sum(acc, scratch);
+    if (threadIdx.x == 0) h[blockIdx.x] = acc;
+}
+
+// w -= sum_k h[k] basis[k]
+__global__ void __launch_bounds__(kVecThreads)
+multi_axpy(int m, int nb, const double *__restrict__ basis, const double *__restrict__ h, double *__restrict__ w) {
+    extern __shared__ double hs[];
+    for (int k = threadIdx.x; k < nb; k += kVecThreads) hs[k] = h[k];
+    __syncthreads();
+    const int i = blockIdx.x * kVecThreads + threadIdx.x;
+    if (i >= m) return;
+    double acc = w[i];
+    for (int k = 0; k < nb; ++k) acc = fma(-hs[k], basis[static_cast<size_t>(k) * m + i], acc);
+    w[i] = acc;
+}
+
+// beta = |w|; next = w / beta; z = isd .* next; records alpha_j = h1[j] + h2[j] and beta_j.
+// j == 0 is the normalisation of the start vector (nothing recorded).  One CTA.
+__global__ void __launch_bounds__(kOneCta)
+normalize_step(int m, int j, const double *__restrict__ w, const double *__restrict__ isd,
+               const double *__restrict__ h1, const double *__restrict__ h2, double *__restrict__ alpha,
+               double *__restrict__ beta, double *__restrict__ next, double *__restrict__ z) {
+    __shared__ double scratch[33];
+    double ss = 0.0;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) ss = fma(w[i], w[i], ss);
+    ss = block_sum(ss, scratch);
+    const double b = sqrt(ss);
+    if (threadIdx.x == 0) {
+        beta[j] = b;
+        if (j > 0) alpha[j] = h1[j] + h2[j];
+    }
+    const double inv = b > 0.0 ? 1.0 / b : 0.0;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        const double v = w[i] * inv;
+        next[i] = v;
+        z[i] = isd[i] * v;
+    }
+}
+
+// ---- projected problem ------------------------------------------------------------------------
+// T = tridiag(alpha[1..j]; beta[1..j-1]).  Finds its two largest eigenvalues by Sturm-count
+// multi-section (blockDim.x probes per round), the eigenvector s of the largest by a twisted
+// factorisation, and the Lanczos residual estimate beta[j] * |s_j|.
+// out: [0] theta1, [1] theta2 (NaN if j == 1), [2] residual estimate, [3] beta[j]
+__device__ __forceinline__ int sturm_count(const double *a, const double *b2, int j, double x, double pivmin) {
+    int cnt = 0;
+    double q = a[1] - x;
+    if (fabs(q) < pivmin) q = -pivmin;
+    cnt += q < 0.0;
+    for (int i = 2; i <= j; ++i) {
+        q = (a[i] - x) - b2[i - 1] / q;
+        if (fabs(q) < pivmin) q = -pivmin;
+        cnt += q < 0.0;
+    }
+    return cnt;  // number of eigenvalues below x
+}
+
+__global__ void __launch_bounds__(256)
+tridiag_ritz(int j, const double *__restrict__ alpha, const double *__restrict__ beta, double *__restrict__ coef,
+             double *__restrict__ out) {
+    extern __shared__ double sm[];
+    double *a = sm;                 // [j + 2], 1-based
+    double *b = a + (j + 2);        // [j + 2]
+    double *b2 = b + (j + 2);       // squares
+    double *dplus = b2 + (j + 2);
+    double *dminus = dplus + (j + 2);
+    __shared__ int counts[256];
+    __shared__ double bounds[2];
+    __shared__ double theta[2];
+    const int tid = threadIdx.x, P = blockDim.x;
+    for (int i = tid + 1; i <= j; i += P) {
+        a[i] = alpha[i];
+        b[i] = beta[i];
+        b2[i] = beta[i] * beta[i];
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double lo = a[1], hi = a[1], bmax = 0.0;
+        for (int i = 1; i <= j; ++i) {
+            const double left = i > 1 ? fabs(b[i - 1]) : 0.0;
+            const double right = i < j ? fabs(b[i]) : 0.0;
+            lo = fmin(lo, a[i] - left - right);
+            hi = fmax(hi, a[i] + left + right);
+            bmax = fmax(bmax, right);
+        }
+        const double span = fmax(hi - lo, 1e-300);
+        bounds[0] = lo - 1e-12 * span - 1e-300;
+        bounds[1] = hi + 1e-12 * span + 1e-300;
+    }
+    __syncthreads();
+    const double pivmin = 1e-290;
+    const double glo = bounds[0], ghi = bounds[1];
+    const int wanted = j >= 2 ? 2 : 1;
+    for (int which = 0; which < wanted; ++which) {
+        const int k = j - which;  // k-th smallest eigenvalue
+        double lo = glo, hi = which == 0 ? ghi : theta[0];
+        if (which == 1) hi = hi + fabs(hi) * 4.5e-16 + 1e-300;
+        for (int round = 0; round < 9; ++round) {
+            const double step = (hi - lo) / (P + 1);
+            const double x = lo + step * (tid + 1);
+            counts[tid] = sturm_count(a, b2, j, x, pivmin);
+            __syncthreads();
+            // first probe with count >= k bounds the eigenvalue from above
+            if (tid == 0) {
+                int first = P;
+                for (int p = 0; p < P; ++p)
+                    if (counts[p] >= k) { first = p; break; }
+                const double nlo = first == 0 ? lo : lo + step * first;
+                const double nhi = first == P ? hi : lo + step * (first + 1);
+                bounds[0] = nlo;
+                bounds[1] = nhi;
+            }
+            __syncthreads();
+            lo = bounds[0];
+            hi = bounds[1];
+            __syncthreads();
+            if (!(hi > lo) || (hi - lo) <= 2.3e-16 * fmax(fabs(lo), fabs(hi))) break;
+        }
+        if (tid == 0) theta[which] = 0.5 * (lo + hi);
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const double th = theta[0];
+        // twisted factorisation of T - th I
+        double d = a[1] - th;
+        if (fabs(d) < pivmin) d = pivmin;
+        dplus[1] = d;
+        for (int i = 2; i <= j; ++i) {
+            d = (a[i] - th) - b2[i - 1] / dplus[i - 1];
+            if (fabs(d) < pivmin) d = pivmin;
+            dplus[i] = d;
+        }
+        d = a[j] - th;
+        if (fabs(d) < pivmin) d = pivmin;
+        dminus[j] = d;
+        for (int i = j - 1; i >= 1; --i) {
+            d = (a[i] - th) - b2[i] / dminus[i + 1];
+            if (fabs(d) < pivmin) d = pivmin;
+            dminus[i] = d;
+        }
+        int kbest = 1;
+        double gbest = INFINITY;
+        for (int i = 1; i <= j; ++i) {
+            const double g = fabs(dplus[i] + dminus[i] - (a[i] - th));
+            if (g < gbest) { gbest = g; kbest = i; }
+        }
+        // solve outward from the twist index (coef reuses no shared memory: written straight out)
+        // going down needs dplus[i] for i < kbest, going up needs dminus[i] for i > kbest;
+        // the unnormalised vector is kept in b2 (no longer needed)
+        double prev = 1.0;
+        double norm2 = 1.0;
+        b2[kbest] = 1.0;
+        for (int i = kbest - 1; i >= 1; --i) {
+            prev = -(b[i] / dplus[i]) * prev;
+            b2[i] = prev;
+            norm2 += prev * prev;
+        }
+        prev = 1.0;
+        for (int i = kbest + 1; i <= j; ++i) {
+            prev = -(b[i - 1] / dminus[i]) * prev;
+            b2[i] = prev;
+            norm2 += prev * prev;
+        }
+        const double inv = 1.0 / sqrt(norm2);
+        for (int i = 1; i <= j; ++i) coef[i] = b2[i] * inv;
+        coef[0] = 0.0;  // no component along the deflated vector
+        out[0] = th;
+        out[1] = j >= 2 ? theta[1] : nan("");
+        out[2] = fabs(b[j] * b2[j] * inv);
+        out[3] = b[j];
+    }
+}
+
+// y = sum_{k=1..j} coef[k] basis[k], normalised;  z = isd .* y.  One CTA.
+__global__ void __launch_bounds__(kOneCta)
+ritz_vector(int m, int j, const double *__restrict__ basis, const double *__restrict__ coef,
+            const double *__restrict__ isd, double *__restrict__ y, double *__restrict__ z) {
+    __shared__ double scratch[33];
+    extern __shared__ double cs[];
+    for (int k = threadIdx.x; k <= j; k += blockDim.x) cs[k] = coef[k];
+    __syncthreads();
+    double ss = 0.0;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        double acc = 0.0;
+        for (int k = 1; k <= j; ++k) acc = fma(cs[k], basis[static_cast<size_t>(k) * m + i], acc);
+        y[i] = acc;
+        ss = fma(acc, acc, ss);
+    }
+    ss = block_sum(ss, scratch);
+    const double inv = ss > 0.0 ? 1.0 / sqrt(ss) : 0.0;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        const double v = y[i] * inv;
+        y[i] = v;
+        z[i] = isd[i] * v;
+    }
+}
+
+// out[0] = | Ny - theta y |, out[1] = y . Ny   (Ny given).  One CTA.
+__global__ void __launch_bounds__(kOneCta)
+true_residual(int m, const double *__restrict__ y, const double *__restrict__ Ny, const double *__restrict__ ritz,
+              double *__restrict__ out) {
+    __shared__ double scratch[33];
+    const double th = ritz[0];
+    double rr = 0.0, rq = 0.0;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        const double r = Ny[i] - th * y[i];
+        rr = fma(r, r, rr);
+        rq = fma(y[i], Ny[i], rq);
+    }
+    rr = block_sum(rr, scratch);
+    rq = block_sum(rq, scratch);
+    if (threadIdx.x == 0) {
+        out[0] = sqrt(rr);
+        out[1] = rq;
+    }
+}
+
+// ---- embedding, sign flip, exact 1-D 2-means --------------------------------------------------
+// u = y .* isd is the Fiedler coordinate sklearn clusters (_spectral_embedding.py:378-381); its sign is
+// fixed so that the entry of largest magnitude is positive (extmath.py:1283-1286).  The 2-means optimum
+// in one dimension is a threshold on the sorted values: sort, prefix sums, best split.
+// result: [0] margin, [1] lower centroid, [2] upper centroid, [3] size of the upper part
+template <bool kShared>
+__global__ void __launch_bounds__(kOneCta)
+two_means_1d(int m, int P, const double *__restrict__ y, const double *__restrict__ isd, double *__restrict__ u,
+             double *__restrict__ sorted_g, int32_t *__restrict__ side, double *__restrict__ result) {
+    extern __shared__ double sort_s[];
+    __shared__ double scratch[33];
+    __shared__ double best_score[32];
+    __shared__ int best_index[32];
+    __shared__ double bcast[4];
+    __shared__ int ibcast;
+    double *keys = kShared ? sort_s : sorted_g;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+
+    // sign: entry of largest magnitude (smallest index on ties) must be positive
+    double amax = -1.0;
+    int imax = 0x7fffffff;
+    for (int i = tid; i < m; i += nthr) {
+        const double v = fabs(y[i] * isd[i]);
+        if (v > amax) { amax = v; imax = i; }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        const double oa = __shfl_down_sync(0xffffffffu, amax, off);
+        const int oi = __shfl_down_sync(0xffffffffu, imax, off);
+        if (oa > amax || (oa == amax && oi < imax)) { amax = oa; imax = oi; }
+    }
+    if ((tid & 31) == 0) { best_score[tid >> 5] = amax; best_index[tid >> 5] = imax; }
+    __syncthreads();
+    if (tid == 0) {
+        double ba = best_score[0];
+        int bi = best_index[0];
+        for (int w = 1; w < (nthr >> 5); ++w)
+            if (best_score[w] > ba || (best_score[w] == ba && best_index[w] < bi)) { ba = best_score[w]; bi = best_index[w]; }
+        ibcast = bi;
+    }
+    __syncthreads();
+    const int arg = ibcast < m ? ibcast : 0;
+    const double sign = y[arg] * isd[arg] < 0.0 ? -1.0 : 1.0;
+
+    double total = 0.0;
+    for (int i = tid; i < P; i += nthr) {
+        double v = INFINITY;
+        if (i < m) {
+            v = sign * (y[i] * isd[i]);
+            u[i] = v;
+            total += v;
+        }
+        keys[i] = v;
+    }
+    total = block_sum(total, scratch);
+    const double mean = total / m;
+    __syncthreads();
+
+    // bitonic sort, ascending
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int jj = k >> 1; jj > 0; jj >>= 1) {
+            for (int i = tid; i < P; i += nthr) {
+                const int partner = i ^ jj;
+                if (partner > i) {
+                    const double x0 = kShared ? keys[i] : __ldcg(keys + i);
+                    const double x1 = kShared ? keys[partner] : __ldcg(keys + partner);
+                    const bool up = (i & k) == 0;
+                    if ((x0 > x1) == up) {
+                        if (kShared) { keys[i] = x1; keys[partner] = x0; }
+                        else { __stcg(keys + i, x1); __stcg(keys + partner, x0); }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+
+    // prefix sums of the centred sorted values: thread t owns a contiguous segment
+    const int seg = (m + nthr - 1) / nthr;
+    const int lo = min(tid * seg, m), hi = min(lo + seg, m);
+    double local = 0.0;
+    for (int i = lo; i < hi; ++i) local += (kShared ? keys[i] : __ldcg(keys + i)) - mean;
+    // exclusive scan of the per-thread sums (warp scan, then warps in order)
+    double incl = local;
+    for (int off = 1; off < 32; off <<= 1) {
+        const double o = __shfl_up_sync(0xffffffffu, incl, off);
+        if ((tid & 31) >= off) incl += o;
+    }
+    __syncthreads();
+    if ((tid & 31) == 31) scratch[tid >> 5] = incl;
+    __syncthreads();
+    double before = 0.0;
+    for (int w = 0; w < (tid >> 5); ++w) before += scratch[w];
+    double all = 0.0;
+    for (int w = 0; w < (nthr >> 5); ++w) all += scratch[w];
+    double prefix = before + incl - local;  // sum of the elements before `lo`
+    // split after i elements (i = 1..m-1) maximises P_i^2 / i + (S - P_i)^2 / (m - i)
+    double bscore = -1.0;
+    int bidx = 0x7fffffff;
+    for (int i = lo; i < hi; ++i) {
+        prefix += (kShared ? keys[i] : __ldcg(keys + i)) - mean;
+        const int cnt = i + 1;
+        if (cnt < m) {
+            const double rest = all - prefix;
+            const double score = prefix * prefix / cnt + rest * rest / (m - cnt);
+            if (score > bscore) { bscore = score; bidx = cnt; }
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        const double os = __shfl_down_sync(0xffffffffu, bscore, off);
+        const int oi = __shfl_down_sync(0xffffffffu, bidx, off);
+        if (os > bscore || (os == bscore && oi < bidx)) { bscore = os; bidx = oi; }
+    }
+    __syncthreads();
+    if ((tid & 31) == 0) { best_score[tid >> 5] = bscore; best_index[tid >> 5] = bidx; }
+    __syncthreads();
+    if (tid == 0) {
+        double bs = best_score[0];
+        int bi = best_index[0];
+        for (int w = 1; w < (nthr >> 5); ++w)
+            if (best_score[w] > bs || (best_score[w] == bs && best_index[w] < bi)) { bs = best_score[w]; bi = best_index[w]; }
+        if (bi >= m) bi = 1;  // degenerate (m == 1 never reaches here)
+        // centroids of the two parts
+        double lower = 0.0;
+        for (int i = 0; i < bi; ++i) lower += (kShared ? keys[i] : __ldcg(keys + i)) - mean;
+        const double c0 = mean + lower / bi;
+        const double c1 = mean + (all - lower) / (m - bi);
+        const double mid = 0.5 * (c0 + c1);
+        const double below = kShared ? keys[bi - 1] : __ldcg(keys + bi - 1);
+        const double above = kShared ? keys[bi] : __ldcg(keys + bi);
+        const double first = kShared ? keys[0] : __ldcg(keys);
+        const double last = kShared ? keys[m - 1] : __ldcg(keys + m - 1);
+        const double range = fmax(last - first, 1e-300);
+        result[0] = fmin(fabs(below - mid), fabs(above - mid)) / range;
+        result[1] = c0;
+        result[2] = c1;
+        result[3] = static_cast<double>(m - bi);
+        bcast[0] = above;
+    }
+    __syncthreads();
+    const double threshold = bcast[0];
+    for (int i = tid; i < m; i += nthr) side[i] = u[i] >= threshold ? 1 : 0;
+}
+
+__global__ void trivial_pair(int32_t *side) {
+    side[0] = 0;
+    side[1] = 1;
+}
+
+int next_pow2(int x) {
+    int p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+}  // namespace
+
+int normalized_matvec(scs_ctx *ctx, int m, const double *W, const double *isd, const double *x, double *y) {
+    if (m <= 0 || !W || !isd || !x || !y) return fail(ctx, SCS_ERR_INVALID, "normalized_matvec: bad argument");
+    double *z;
+    int rc;
+    if ((rc = reserve_as(ctx, SLOT_UVEC, static_cast<size_t>(m), &z))) return rc;
+    scale_vector<<<ceil_div(m, 256), 256, 0, ctx->stream>>>(m, isd, x, z);
+    SCS_LAUNCHED(ctx, "scale_vector");
+    return launch_matvec(ctx, m, W, isd, z, y);
+}
+
+int spectral_bipartition(scs_ctx *ctx, int m, const double *W, const double *degree, uint64_t seed, int32_t *side,
+                         scs_node_stats *stats) {
+    if (m < 2 || !W || !side || !stats) return fail(ctx, SCS_ERR_INVALID, "spectral_bipartition: bad argument");
+    int rc;
+    if (m == 2) {
+        // sklearn falls back to a dense eigh (arpack.py:1691-1707); two vertices always separate
+        trivial_pair<<<1, 1, 0, ctx->stream>>>(side);
+        SCS_LAUNCHED(ctx, "trivial_pair");
+        stats->solver = 1;
+        stats->eig[1] = 2.0;  // L = [[1,-1],[-1,1]] whatever the weight
+        stats->residual = 0.0;
+        stats->margin = 0.5;
+        return SCS_OK;
+    }
+    const int jmax = m - 1 < kMaxBasis ? m - 1 : kMaxBasis;  // the deflated space has dimension m - 1
+    double *isd, *basis, *w, *z, *coef, *tri, *ritz, *embed, *sorted, *deg_own;
+    int32_t *flags;
+    if ((rc = reserve_as(ctx, SLOT_ISD, static_cast<size_t>(m), &isd))) return rc;
+    if ((rc = reserve_as(ctx, SLOT_BASIS, static_cast<size_t>(jmax + 2) * m, &basis))) return rc;
+    if ((rc = reserve_as(ctx, SLOT_WORK, 2 * static_cast<size_t>(m), &w))) return rc;
+    if ((rc = reserve_as(ctx, SLOT_UVEC, static_cast<size_t>(m), &z))) return rc;
+    if ((rc = reserve_as(ctx, SLOT_COEF, 3 * static_cast<size_t>(kMaxBasis + 4), &coef))) return rc;
+    if ((rc = reserve_as(ctx, SLOT_TRIDIAG, 2 * static_cast<size_t>(kMaxBasis + 4), &tri))) return rc;
+    if ((rc = reserve_as(ctx, SLOT_RITZ, 16, &ritz))) return rc;
+    if ((rc = reserve_as(ctx, SLOT_EMBED, static_cast<size_t>(m), &embed))) return rc;
+    const int P = next_pow2(m);
+    if ((rc = reserve_as(ctx, SLOT_SORTED, static_cast<size_t>(P), &sorted))) return rc;
+    if ((rc = reserve_as(ctx, SLOT_SPEC_SCALARS, 16, &flags))) return rc;
+    double *h1 = coef + (kMaxBasis + 4), *h2 = h1 + (kMaxBasis + 4);
+    double *alpha = tri, *beta = tri + (kMaxBasis + 4);
+    double *yvec = w + m;
+    void *pin_v;
+    if ((rc = reserve_pinned(ctx, 256, &pin_v))) return rc;
+    double *pin = static_cast<double *>(pin_v);
+
+    SCS_CUDA(ctx, cudaMemsetAsync(flags, 0, 16 * sizeof(int32_t), ctx->stream));
+    if (!degree) {
+        if ((rc = reserve_as(ctx, SLOT_DEGREE_C, static_cast<size_t>(m), &deg_own))) return rc;
+        row_sums<<<ceil_div(static_cast<int64_t>(m) * 32, 256), 256, 0, ctx->stream>>>(m, W, deg_own);
+        SCS_LAUNCHED(ctx, "row_sums");
+        degree = deg_own;
+    }
+    prepare_scaling<<<1, kOneCta, 0, ctx->stream>>>(m, degree, isd, basis, flags);
+    SCS_LAUNCHED(ctx, "prepare_scaling");
+
+    const int vec_blocks = ceil_div(m, kVecThreads);
+    auto orthogonalise = [&](int nb, double *h) -> int {
+        multi_dot<<<nb, kVecThreads, 0, ctx->stream>>>(m, basis, w, h);
+        SCS_LAUNCHED(ctx, "multi_dot");
+        multi_axpy<<<vec_blocks, kVecThreads, nb * sizeof(double), ctx->stream>>>(m, nb, basis, h, w);
+        SCS_LAUNCHED(ctx, "multi_axpy");
+        return SCS_OK;
+    };
+
+    stats->solver = 3;
+    stats->matvecs = 0;
+    stats->restarts = 0;
+    double theta1 = std::nan(""), theta2 = std::nan(""), est = std::nan("");
+    int jdone = 0;
+    bool converged = false;
+    for (int attempt = 0; attempt <= kMaxRestarts && !converged; ++attempt) {
+        if (attempt == 0) {
+            random_start<<<vec_blocks, kVecThreads, 0, ctx->stream>>>(m, seed, w);
+            SCS_LAUNCHED(ctx, "random_start");
+        } else {
+            // explicit restart from the current Ritz vector
+            SCS_CUDA(ctx, cudaMemcpyAsync(w, yvec, sizeof(double) * m, cudaMemcpyDeviceToDevice, ctx->stream));
+            stats->restarts = attempt;
+        }
+        if ((rc = orthogonalise(1, h1))) return rc;
+        if ((rc = orthogonalise(1, h2))) return rc;
+        normalize_step<<<1, kOneCta, 0, ctx->stream>>>(m, 0, w, isd, h1, h2, alpha, beta, basis + m, z);
+        SCS_LAUNCHED(ctx, "normalize_step");
+        for (int j = 1; j <= jmax; ++j) {
+            if ((rc = launch_matvec(ctx, m, W, isd, z, w))) return rc;
+            stats->matvecs += 1;
+            if ((rc = orthogonalise(j + 1, h1))) return rc;
+            if ((rc = orthogonalise(j + 1, h2))) return rc;
+            normalize_step<<<1, kOneCta, 0, ctx->stream>>>(m, j, w, isd, h1, h2, alpha, beta,
+                                                           basis + static_cast<size_t>(j + 1) * m, z);
+            SCS_LAUNCHED(ctx, "normalize_step");
+            jdone = j;
+            const bool check = j == jmax || (j >= 6 && (j % 4) == 0);
+            if (!check) continue;
+            tridiag_ritz<<<1, 256, 5 * (j + 2) * sizeof(double), ctx->stream>>>(j, alpha, beta, coef, ritz);
+            SCS_LAUNCHED(ctx, "tridiag_ritz");
+            SCS_CUDA(ctx, cudaMemcpyAsync(pin, ritz, 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            SCS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            theta1 = pin[0];
+            theta2 = pin[1];
+            est = pin[2];
+            const double bj = pin[3];
+            if (est <= kResidualTol || bj <= kBreakdown) {
+                converged = true;
+                break;
+            }
+        }
+        // Ritz vector of the current basis (also the restart vector)
+        ritz_vector<<<1, kOneCta, (jdone + 1) * sizeof(double), ctx->stream>>>(m, jdone, basis, coef, isd, yvec, z);
+        SCS_LAUNCHED(ctx, "ritz_vector");
+    }
+
+    // true residual of the accepted pair: one more operator application
+    if ((rc = launch_matvec(ctx, m, W, isd, z, w))) return rc;
+    stats->matvecs += 1;
+    true_residual<<<1, kOneCta, 0, ctx->stream>>>(m, yvec, w, ritz, ritz + 4);
+    SCS_LAUNCHED(ctx, "true_residual");
+
+    if (P <= 8192) {
+        auto kernel = two_means_1d<true>;
+        const size_t smem = static_cast<size_t>(P) * sizeof(double);
+        if (smem > 48 * 1024)
+            SCS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        kernel<<<1, kOneCta, smem, ctx->stream>>>(m, P, yvec, isd, embed, sorted, side, ritz + 8);
+    } else {
+        two_means_1d<false><<<1, kOneCta, 0, ctx->stream>>>(m, P, yvec, isd, embed, sorted, side, ritz + 8);
+    }
+    SCS_LAUNCHED(ctx, "two_means_1d");
+    SCS_CUDA(ctx, cudaMemcpyAsync(pin, ritz, 12 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SCS_CUDA(ctx, cudaMemcpyAsync(pin + 12, flags, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SCS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    theta1 = pin[0];
+    theta2 = pin[1];
+    stats->eig[0] = 0.0;
+    stats->eig[1] = 1.0 - theta1;
+    stats->eig[2] = 1.0 - theta2;
+    stats->residual = pin[4];
+    stats->margin = pin[8];
+    const int32_t bad_degree = reinterpret_cast<const int32_t *>(pin + 12)[0];
+    stats->tie_flag = 0;
+    if (!std::isnan(theta2) && (theta1 - theta2) < kGapTie) stats->tie_flag |= 1;
+    if (!(stats->margin >= kMarginTie)) stats->tie_flag |= 2;
+    if (!converged) stats->tie_flag |= 4;  // accepted at the restart limit: see stats->residual
+    if (bad_degree) stats->tie_flag |= 8;  // negative / non-finite degree: sklearn's result is NaN-driven
+    return SCS_OK;
+}
+
+}  // namespace scs

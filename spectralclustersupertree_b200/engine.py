@@ -1,0 +1,467 @@
+"""Host-side handles over the C ABI: a GPU context (``Engine``) and a source-tree store (``Forest``).
+
+``Engine`` owns one ``scs_ctx`` (one CUDA stream + workspace on one GPU).  ``Forest`` owns one
+``scs_forest``: the flat-array form of the list of source trees the reference's recursion
+carries (ref: src/sc_supertree/scs.py:18-25, 411-455).  Everything numeric happens inside
+``libscs_b200.so``; this module only moves numpy arrays across the boundary.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+from collections.abc import Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import NodeStats, ptr
+
+WEIGHTINGS = ("one", "branch", "depth", "bootstrap")  # codes of scs_forest_tours
+
+
+class ScsError(RuntimeError):
+    """A call into libscs_b200.so failed."""
+
+    def __init__(self, status: int, detail: str = "") -> None:
+        self.status = status
+        text = _lib.load().scs_status_string(status).decode()
+        super().__init__(f"libscs_b200: {text}" + (f" ({detail})" if detail else ""))
+
+
+def _check(status: int, ctx=None) -> None:
+    if status == _lib.SCS_OK:
+        return
+    detail = ""
+    if ctx is not None:
+        detail = _lib.load().scs_last_error(ctx).decode()
+    raise ScsError(status, detail)
+
+
+class Engine:
+    """One GPU context.  Not thread-safe; use one per thread per GPU."""
+
+    def __init__(self, device: int | None = None) -> None:
+        self._lib = _lib.load()
+        if device is None:
+            device = int(os.environ.get("SCS_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+        handle = ctypes.c_void_p()
+        status = self._lib.scs_ctx_create(device, None, ctypes.byref(handle))
+        if status != _lib.SCS_OK:
+            raise ScsError(status, f"scs_ctx_create(device={device}); the CUDA path has no CPU fallback")
+        self._ctx = handle
+        self.device = device
+
+    # -- lifetime ----------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_ctx", None):
+            self._lib.scs_ctx_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self) -> None:  # pragma: no cover - interpreter shutdown order
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001, S110
+            pass
+
+    def __enter__(self) -> "Engine":
+        return self
+
+    def __exit__(self, *exc) -> None:
+        self.close()
+
+    @property
+    def handle(self):
+        return self._ctx
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.scs_ctx_launch_count(self._ctx))
+
+    def synchronize(self) -> None:
+        _check(self._lib.scs_ctx_synchronize(self._ctx), self._ctx)
+
+    # -- raw device memory (tests, bench) -------------------------------------------------------
+    def alloc(self, nbytes: int) -> int:
+        out = ctypes.c_void_p()
+        _check(self._lib.scs_dev_alloc(self._ctx, nbytes, ctypes.byref(out)), self._ctx)
+        return out.value
+
+    def free(self, dev: int) -> None:
+        _check(self._lib.scs_dev_free(self._ctx, dev), self._ctx)
+
+    def to_device(self, array: np.ndarray) -> int:
+        array = np.ascontiguousarray(array)
+        dev = self.alloc(max(array.nbytes, 16))
+        if array.nbytes:
+            _check(self._lib.scs_memcpy_h2d(self._ctx, dev, ptr(array), array.nbytes), self._ctx)
+        return dev
+
+    def to_host(self, dev: int, shape, dtype) -> np.ndarray:
+        out = np.empty(shape, dtype=dtype)
+        if out.nbytes:
+            _check(self._lib.scs_memcpy_d2h(self._ctx, ptr(out), dev, out.nbytes), self._ctx)
+        return out
+
+    # -- one recursion node from host tours (ref: scs.py:110-134) --------------------------------
+    def node_split(self, tours, contract_edges: bool = True, seed: int = 0):
+        """``(part, stats)`` for the leaf tours of one recursion node (``flatten.LeafTours``)."""
+        part = np.empty(tours.n, dtype=np.int32)
+        stats = NodeStats()
+        status = self._lib.scs_node_split_host(
+            self._ctx, tours.n, tours.num_trees, tours.num_leaves, ptr(tours.leaf_offsets), ptr(tours.leaf_taxon),
+            ptr(tours.adj_depth), ptr(tours.adj_val), ptr(tours.root_depth), ptr(tours.tree_weight),
+            int(bool(contract_edges)), seed & 0xFFFFFFFFFFFFFFFF, ptr(part), ctypes.byref(stats),
+        )  # fmt: skip
+        _check(status, self._ctx)
+        return part, stats
+
+    def forest_split(self, forest: "Forest", weighting: str, contract_edges: bool = True, seed: int = 0):
+        """``(taxa, part, stats)``: the vertices (global taxon ids, ascending) of the recursion node
+        holding ``forest`` and, per vertex, its component index or spectral side."""
+        cap = max(forest.num_taxa, 1)
+        taxa = np.empty(cap, dtype=np.int32)
+        part = np.empty(cap, dtype=np.int32)
+        n = ctypes.c_int32(0)
+        stats = NodeStats()
+        status = self._lib.scs_forest_split(
+            self._ctx, forest.handle, WEIGHTINGS.index(weighting), int(bool(contract_edges)),
+            seed & 0xFFFFFFFFFFFFFFFF, ctypes.byref(n), ptr(taxa), ptr(part), ctypes.byref(stats),
+        )  # fmt: skip
+        if status == _lib.SCS_ERR_INPUT and weighting == "bootstrap":
+            # the reference multiplies a missing support by the tree weight (ref: scs.py:655-657)
+            msg = "unsupported operand type(s) for *: 'NoneType' and 'float'"
+            raise TypeError(msg)
+        _check(status, self._ctx)
+        return taxa[: n.value].copy(), part[: n.value].copy(), stats
+
+    # -- single stages on explicit device buffers (parity tests, profiling, bench) ---------------
+    def upload_tours(self, tours) -> dict:
+        """Device copies of a ``LeafTours`` (free with ``free_tours``)."""
+        return {
+            "n": tours.n, "T": tours.num_trees, "L": tours.num_leaves,
+            "leaf_offsets": self.to_device(tours.leaf_offsets), "leaf_taxon": self.to_device(tours.leaf_taxon),
+            "adj_depth": self.to_device(tours.adj_depth), "adj_val": self.to_device(tours.adj_val),
+            "root_depth": self.to_device(tours.root_depth), "tree_weight": self.to_device(tours.tree_weight),
+        }  # fmt: skip
+
+    def free_tours(self, dev: dict) -> None:
+        for key in ("leaf_offsets", "leaf_taxon", "adj_depth", "adj_val", "root_depth", "tree_weight"):
+            self.free(dev[key])
+
+    def node_split_dev(self, dev: dict, part_dev: int, contract_edges: bool = True, seed: int = 0) -> NodeStats:
+        """One recursion node on tours already resident in HBM (``upload_tours``)."""
+        stats = NodeStats()
+        status = self._lib.scs_node_split_dev(
+            self._ctx, dev["n"], dev["T"], dev["L"], dev["leaf_offsets"], dev["leaf_taxon"], dev["adj_depth"],
+            dev["adj_val"], dev["root_depth"], dev["tree_weight"], int(bool(contract_edges)),
+            seed & 0xFFFFFFFFFFFFFFFF, part_dev, ctypes.byref(stats),
+        )  # fmt: skip
+        _check(status, self._ctx)
+        return stats
+
+    def pcg_build(self, tours, want_counts: bool = True) -> dict:
+        """``scs_pcg_build_dev`` on fresh device buffers; returns host copies of every output."""
+        n = tours.n
+        words = self._lib.scs_bit_words(n)
+        dev = self.upload_tours(tours)
+        bufs = {
+            "W": self.alloc(8 * n * n), "C": self.alloc(4 * n * n) if want_counts else None,
+            "occ": self.alloc(4 * n), "adj_bits": self.alloc(4 * n * words), "max_bits": self.alloc(4 * n * words),
+            "degree": self.alloc(8 * n),
+        }  # fmt: skip
+        try:
+            status = self._lib.scs_pcg_build_dev(
+                self._ctx, n, dev["T"], dev["L"], dev["leaf_offsets"], dev["leaf_taxon"], dev["adj_depth"],
+                dev["adj_val"], dev["root_depth"], dev["tree_weight"], bufs["W"], bufs["C"], bufs["occ"],
+                bufs["adj_bits"], bufs["max_bits"], bufs["degree"],
+            )  # fmt: skip
+            _check(status, self._ctx)
+            self.synchronize()
+            out = {
+                "W": self.to_host(bufs["W"], (n, n), np.float64),
+                "occ": self.to_host(bufs["occ"], (n,), np.int32),
+                "adj_bits": self.to_host(bufs["adj_bits"], (n, words), np.uint32),
+                "max_bits": self.to_host(bufs["max_bits"], (n, words), np.uint32),
+                "degree": self.to_host(bufs["degree"], (n,), np.float64),
+            }
+            if want_counts:
+                out["C"] = self.to_host(bufs["C"], (n, n), np.int32)
+            return out
+        finally:
+            self.free_tours(dev)
+            for b in bufs.values():
+                if b:
+                    self.free(b)
+
+    def components(self, bits: np.ndarray, n: int) -> tuple[np.ndarray, int]:
+        """``scs_components_dev``: (label = smallest vertex of the component, number of components)."""
+        d_bits = self.to_device(bits)
+        d_label = self.alloc(4 * n)
+        count = ctypes.c_int32(0)
+        try:
+            _check(self._lib.scs_components_dev(self._ctx, n, d_bits, d_label, ctypes.byref(count)), self._ctx)
+            return self.to_host(d_label, (n,), np.int32), count.value
+        finally:
+            self.free(d_bits)
+            self.free(d_label)
+
+    def contract(self, W: np.ndarray, adj_bits: np.ndarray, max_bits: np.ndarray):
+        """``scs_contract_dev``: (group, m, Wc[m, m], degree_c[m])."""
+        n = W.shape[0]
+        d_W, d_adj, d_max = self.to_device(W), self.to_device(adj_bits), self.to_device(max_bits)
+        d_group, d_Wc, d_deg = self.alloc(4 * n), self.alloc(8 * n * n), self.alloc(8 * n)
+        m = ctypes.c_int32(0)
+        try:
+            status = self._lib.scs_contract_dev(self._ctx, n, d_W, d_adj, d_max, d_group, ctypes.byref(m), d_Wc, d_deg)
+            _check(status, self._ctx)
+            m = m.value
+            group = self.to_host(d_group, (n,), np.int32)
+            if m == n:
+                return group, m, W.copy(), W.sum(axis=1)
+            return group, m, self.to_host(d_Wc, (m, m), np.float64), self.to_host(d_deg, (m,), np.float64)
+        finally:
+            for d in (d_W, d_adj, d_max, d_group, d_Wc, d_deg):
+                self.free(d)
+
+    def spectral_bipartition(self, W: np.ndarray, seed: int = 0, degree: np.ndarray | None = None):
+        """``scs_spectral_bipartition_dev``: (side[m], stats)."""
+        W = np.ascontiguousarray(W, dtype=np.float64)
+        m = W.shape[0]
+        d_W = self.to_device(W)
+        d_deg = None if degree is None else self.to_device(np.ascontiguousarray(degree, dtype=np.float64))
+        d_side = self.alloc(4 * max(m, 1))
+        stats = NodeStats()
+        try:
+            status = self._lib.scs_spectral_bipartition_dev(
+                self._ctx, m, d_W, d_deg, seed & 0xFFFFFFFFFFFFFFFF, d_side, ctypes.byref(stats)
+            )
+            _check(status, self._ctx)
+            return self.to_host(d_side, (m,), np.int32), stats
+        finally:
+            self.free(d_W)
+            self.free(d_side)
+            if d_deg:
+                self.free(d_deg)
+
+    def normalized_matvec(self, W: np.ndarray, inv_sqrt_deg: np.ndarray, x: np.ndarray) -> np.ndarray:
+        """``scs_normalized_matvec_dev``: D^-1/2 W D^-1/2 x."""
+        m = W.shape[0]
+        d_W, d_s, d_x, d_y = self.to_device(W), self.to_device(inv_sqrt_deg), self.to_device(x), self.alloc(8 * m)
+        try:
+            _check(self._lib.scs_normalized_matvec_dev(self._ctx, m, d_W, d_s, d_x, d_y), self._ctx)
+            return self.to_host(d_y, (m,), np.float64)
+        finally:
+            for d in (d_W, d_s, d_x, d_y):
+                self.free(d)
+
+    def last_node_buffers(self) -> dict:
+        """Host copies of the device buffers of the node most recently split (parity tests)."""
+        n, m = ctypes.c_int(0), ctypes.c_int(0)
+        ptrs = [ctypes.c_void_p() for _ in range(7)]
+        _check(
+            self._lib.scs_node_last_buffers(self._ctx, ctypes.byref(n), ctypes.byref(m), *[ctypes.byref(p) for p in ptrs]),
+            self._ctx,
+        )
+        n, m = n.value, m.value
+        words = self._lib.scs_bit_words(n)
+        W, adj, mx, occ, deg, Wc, group = (p.value for p in ptrs)
+        out = {"n": n, "m": m}
+        out["W"] = self.to_host(W, (n, n), np.float64)
+        out["adj_bits"] = self.to_host(adj, (n, words), np.uint32)
+        out["occ"] = self.to_host(occ, (n,), np.int32)
+        out["degree"] = self.to_host(deg, (n,), np.float64)
+        if mx:
+            out["max_bits"] = self.to_host(mx, (n, words), np.uint32)
+        if m and m != n and Wc and group:
+            out["Wc"] = self.to_host(Wc, (m, m), np.float64)
+            out["group"] = self.to_host(group, (n,), np.int32)
+        return out
+
+
+_DEFAULT: Engine | None = None
+
+
+def default_engine() -> Engine:
+    """The process-wide engine used by ``construct_supertree`` (device from ``SCS_B200_DEVICE``)."""
+    global _DEFAULT  # noqa: PLW0603
+    if _DEFAULT is None:
+        _DEFAULT = Engine()
+    return _DEFAULT
+
+
+def unpack_bits(bits: np.ndarray, n: int) -> np.ndarray:
+    """Bit matrix (n x words uint32, bit b of word j = column 32 j + b) -> boolean n x n."""
+    as_bytes = bits.view(np.uint8).reshape(bits.shape[0], -1)
+    return np.unpackbits(as_bytes, axis=1, bitorder="little")[:, :n].astype(bool)
+
+
+class Forest:
+    """Flat source trees + weights (owner of one ``scs_forest``)."""
+
+    def __init__(self, handle, names: Sequence[str]) -> None:
+        self._lib = _lib.load()
+        self._handle = handle
+        self.names = names  # global taxon id -> name (sorted)
+
+    # -- construction --------------------------------------------------------------------------
+    @classmethod
+    def from_arrays(cls, node_offsets, parent, length, support, taxon, weights, names: Sequence[str]) -> "Forest":
+        lib = _lib.load()
+        node_offsets = np.ascontiguousarray(node_offsets, dtype=np.int64)
+        parent = np.ascontiguousarray(parent, dtype=np.int32)
+        taxon = np.ascontiguousarray(taxon, dtype=np.int32)
+        length = None if length is None else np.ascontiguousarray(length, dtype=np.float64)
+        support = None if support is None else np.ascontiguousarray(support, dtype=np.float64)
+        weights = np.ascontiguousarray(weights, dtype=np.float64)
+        handle = ctypes.c_void_p()
+        status = lib.scs_forest_create(
+            len(weights), ptr(node_offsets), ptr(parent), ptr(length), ptr(support), ptr(taxon), ptr(weights),
+            len(names), ctypes.byref(handle),
+        )  # fmt: skip
+        if status != _lib.SCS_OK:
+            raise ScsError(status, "scs_forest_create")
+        return cls(handle, names)
+
+    @classmethod
+    def from_trees(cls, trees: Sequence, weights: Sequence[float], names: Sequence[str] | None = None) -> "Forest":
+        """Flatten tree objects exposing the PhyloNode surface (children iteration, ``name``,
+        ``length``, ``support``; ref: scs.py:570,624-631,560-564)."""
+        if names is None:
+            found: set[str] = set()
+            for tree in trees:
+                found.update(tree.get_tip_names())
+            names = sorted(found)
+        taxon_id = {name: i for i, name in enumerate(names)}
+        offsets = [0]
+        parent: list[int] = []
+        length: list[float] = []
+        support: list[float] = []
+        taxon: list[int] = []
+        nan = float("nan")
+        for tree in trees:
+            base = len(parent)
+            stack = [(tree, -1)]
+            while stack:
+                node, up = stack.pop()
+                k = len(parent) - base
+                parent.append(up)
+                ln, sp = node.length, getattr(node, "support", None)
+                length.append(nan if ln is None else float(ln))
+                support.append(nan if sp is None else float(sp))
+                kids = list(node)
+                if kids:
+                    taxon.append(-1)
+                    stack.extend((child, k) for child in reversed(kids))
+                else:
+                    taxon.append(taxon_id[node.name])
+            offsets.append(len(parent))
+        return cls.from_arrays(offsets, parent, length, support, taxon, list(weights), names)
+
+    def close(self) -> None:
+        if getattr(self, "_handle", None):
+            self._lib.scs_forest_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self) -> None:  # pragma: no cover
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001, S110
+            pass
+
+    # -- queries -------------------------------------------------------------------------------
+    @property
+    def handle(self):
+        return self._handle
+
+    @property
+    def num_trees(self) -> int:
+        return self._lib.scs_forest_num_trees(self._handle)
+
+    @property
+    def num_nodes(self) -> int:
+        return self._lib.scs_forest_num_nodes(self._handle)
+
+    @property
+    def num_leaves(self) -> int:
+        return self._lib.scs_forest_num_leaves(self._handle)
+
+    @property
+    def num_taxa(self) -> int:
+        return self._lib.scs_forest_num_taxa(self._handle)
+
+    @property
+    def pair_visits(self) -> int:
+        return self._lib.scs_forest_pair_visits(self._handle)
+
+    def taxa(self) -> np.ndarray:
+        """Global ids of the taxa present, ascending (ref: scs.py:708-725)."""
+        present = np.zeros(max(self.num_taxa, 1), dtype=np.uint8)
+        n = self._lib.scs_forest_taxa(self._handle, ptr(present))
+        if n < 0:
+            raise ScsError(n, "scs_forest_taxa")
+        return np.flatnonzero(present[: self.num_taxa]).astype(np.int32)
+
+    def tree_arrays(self, t: int):
+        """``(parent, length, support, taxon)`` of tree ``t`` (pre-order)."""
+        count = ctypes.c_int64(0)
+        status = self._lib.scs_forest_tree_info(self._handle, t, ctypes.byref(count), None, None)
+        if status != _lib.SCS_OK:
+            raise ScsError(status, "scs_forest_tree_info")
+        m = count.value
+        parent = np.empty(m, dtype=np.int32)
+        length = np.empty(m, dtype=np.float64)
+        support = np.empty(m, dtype=np.float64)
+        taxon = np.empty(m, dtype=np.int32)
+        status = self._lib.scs_forest_tree(self._handle, t, ptr(parent), ptr(length), ptr(support), ptr(taxon))
+        if status != _lib.SCS_OK:
+            raise ScsError(status, "scs_forest_tree")
+        return parent, length, support, taxon
+
+    def weights(self) -> np.ndarray:
+        out = np.empty(self.num_trees, dtype=np.float64)
+        w = ctypes.c_double(0.0)
+        for t in range(self.num_trees):
+            self._lib.scs_forest_tree_info(self._handle, t, None, ctypes.byref(w), None)
+            out[t] = w.value
+        return out
+
+    # -- operations ----------------------------------------------------------------------------
+    def induce(self, keep_ids: np.ndarray) -> "Forest":
+        """Restrict every tree to the given global taxon ids (ref: scs.py:411-455)."""
+        keep = np.zeros(max(self.num_taxa, 1), dtype=np.uint8)
+        keep[keep_ids] = 1
+        handle = ctypes.c_void_p()
+        status = self._lib.scs_forest_induce(self._handle, ptr(keep), ctypes.byref(handle))
+        if status != _lib.SCS_OK:
+            raise ScsError(status, "scs_forest_induce")
+        return Forest(handle, self.names)
+
+    def tours(self, weighting: str, local_id: np.ndarray | None = None):
+        """Leaf tours (``flatten.LeafTours``) with vertex ids = rank among the taxa present."""
+        from .flatten import LeafTours
+
+        present = self.taxa()
+        if local_id is None:
+            local_id = np.full(max(self.num_taxa, 1), -1, dtype=np.int32)
+            local_id[present] = np.arange(len(present), dtype=np.int32)
+        T, L = self.num_trees, self.num_leaves
+        out = LeafTours(
+            n=len(present),
+            leaf_offsets=np.zeros(T + 1, dtype=np.int64),
+            leaf_taxon=np.zeros(L, dtype=np.int32),
+            adj_depth=np.zeros(L, dtype=np.int32),
+            adj_val=np.zeros(L, dtype=np.float64),
+            root_depth=np.zeros(T, dtype=np.int32),
+            tree_weight=np.zeros(T, dtype=np.float64),
+        )
+        status = self._lib.scs_forest_tours(
+            self._handle, WEIGHTINGS.index(weighting), ptr(local_id), ptr(out.leaf_offsets), ptr(out.leaf_taxon),
+            ptr(out.adj_depth), ptr(out.adj_val), ptr(out.root_depth), ptr(out.tree_weight),
+        )  # fmt: skip
+        if status == _lib.SCS_ERR_INPUT and weighting == "bootstrap":
+            msg = "unsupported operand type(s) for *: 'NoneType' and 'float'"
+            raise TypeError(msg)
+        if status != _lib.SCS_OK:
+            raise ScsError(status, "scs_forest_tours")
+        return out

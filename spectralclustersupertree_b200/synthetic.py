@@ -302,6 +302,52 @@ class Problem:
     def phylonodes(self) -> list[PhyloNode]:
         return [s.to_phylonode() for s in self.sources]
 
+    def names(self) -> list[str]:
+        """Sorted names of every taxon that occurs in a source tree (global taxon id = index)."""
+        found: set[str] = set()
+        for s in self.sources:
+            found.update(name for name, kids in zip(s.tip_name, s.children, strict=True) if not kids)
+        return sorted(found)
+
+    def forest_arrays(self) -> dict:
+        """The source trees as the flat pre-order arrays of ``scs_forest_create`` (include/scs_b200.h),
+        built straight from the child lists without per-node Python objects."""
+        names = self.names()
+        taxon_id = {name: i for i, name in enumerate(names)}
+        keep_lengths = self.weighting == "branch"
+        keep_support = self.weighting == "bootstrap"
+        offsets = [0]
+        parent: list[int] = []
+        taxon: list[int] = []
+        length: list[float] = []
+        support: list[float] = []
+        nan = float("nan")
+        for s in self.sources:
+            base = len(parent)
+            stack = [(s.root, -1)]
+            while stack:
+                x, up = stack.pop()
+                k = len(parent) - base
+                parent.append(up)
+                kids = s.children[x]
+                taxon.append(-1 if kids else taxon_id[s.tip_name[x]])
+                ln = s.length[x] if keep_lengths else None
+                sp = s.support[x] if keep_support else None
+                length.append(nan if ln is None else float(ln))
+                support.append(nan if sp is None else float(sp))
+                stack.extend((c, k) for c in reversed(kids))
+            offsets.append(len(parent))
+        weights = [1.0] * len(self.sources) if self.weights is None else list(self.weights)
+        return {
+            "names": names,
+            "node_offsets": np.asarray(offsets, dtype=np.int64),
+            "parent": np.asarray(parent, dtype=np.int32),
+            "length": np.asarray(length, dtype=np.float64),
+            "support": np.asarray(support, dtype=np.float64),
+            "taxon": np.asarray(taxon, dtype=np.int32),
+            "weights": np.asarray(weights, dtype=np.float64),
+        }
+
     def newick_lines(self) -> list[str]:
         return [s.to_newick(with_lengths=self.weighting == "branch", with_support=self.weighting == "bootstrap")
                 for s in self.sources]  # fmt: skip

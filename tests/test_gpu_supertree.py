@@ -1,0 +1,109 @@
+"""GPU: the drop-in ``construct_supertree`` / ``load_trees`` / ``scs`` against the reference's
+known-answer tests (ref: tests/test_spectral_cluster_supertree.py, tests/test_cli.py), its fixture
+files, and node-by-node against traces of the reference's own runs."""
+
+from __future__ import annotations
+
+import json
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN, compare_with_reference_trace, kat_cases, load_case, parse, rf
+from spectralclustersupertree_b200 import construct_supertree, load_trees
+from spectralclustersupertree_b200.tree import NotCompleted, make_tree
+
+pytestmark = pytest.mark.gpu
+
+
+def scs_test(in_trees, expected, engine, **kwargs):
+    """ref: tests/test_spectral_cluster_supertree.py:12-27"""
+    result = construct_supertree([make_tree(s) for s in in_trees], engine=engine, **kwargs).sorted()
+    assert result.same_shape(make_tree(expected).sorted()), str(result)
+
+
+@pytest.mark.parametrize("case", kat_cases(), ids=lambda c: c["name"])
+def test_reference_known_answers(engine, case):
+    scs_test(case["trees"], case["expected"], engine, **case["kwargs"])
+    scs_test(case["trees"], case["expected"], engine, random_state=np.random.RandomState(7), **case["kwargs"])
+
+
+@pytest.mark.parametrize("name", ["dcm", "dcm_iq", "supertriplets"])
+def test_reference_fixtures(engine, name):
+    fixture = json.loads((GOLDEN / f"fixture_{name}.json").read_text())
+    result = construct_supertree(parse(fixture["trees"]), pcg_weighting=fixture["weighting"], engine=engine)
+    assert rf(result, make_tree(fixture["expected"])) == 0
+
+
+@pytest.mark.parametrize(
+    "name",
+    ["dcm", "dcm_iq", "supertriplets", "c1_100x30_depth", "c2_500x50_branch", "s_200x40_bootstrap",
+     "s_300x40_branch_weighted", "s_150x40_one"],
+)  # fmt: skip
+def test_node_by_node_against_reference_trace(engine, name):
+    case = load_case(name)
+    trace: list = []
+    tree = construct_supertree(
+        parse(case["lines"]), case["weights"], case["weighting"], engine=engine, trace=trace
+    )
+    report = compare_with_reference_trace(trace, case["nodes"])
+    by_names = {tuple(r["names"]): r for r in case["nodes"]}
+    for rec in trace:
+        ref = by_names.get(tuple(rec["names"]))
+        if ref is None or "eigenvalues" not in ref or rec["contracted_size"] < 3:
+            continue
+        assert abs(rec["stats"]["eig"][1] - ref["eigenvalues"][1]) < 1e-6, rec["names"]
+    assert sorted(tree.get_tip_names()) == case["names"]
+    if report["tie_divergences"] == 0:
+        assert len(trace) == len(case["nodes"])
+        assert rf(tree, make_tree(case["supertree"])) == 0
+    print(name, report)
+
+
+def test_argument_errors(engine):
+    with pytest.raises(ValueError, match="at least one tree"):
+        construct_supertree([], engine=engine)
+    with pytest.raises(ValueError, match="Invalid weighting strategy selected: 'bogus'"):
+        construct_supertree([make_tree("(a,b)")], pcg_weighting="bogus", engine=engine)
+    with pytest.raises(ValueError, match=r"The number of trees \(2\) and tree weights \(1\) must match."):
+        construct_supertree([make_tree("(a,b)"), make_tree("(b,c)")], weights=[1.0], engine=engine)
+    with pytest.raises(ValueError, match="at least one tree"):
+        construct_supertree([NotCompleted()], engine=engine)
+    with pytest.raises(TypeError):
+        construct_supertree([make_tree("(a,(b,(c,d)))"), make_tree("(a,(c,(b,d)))")], pcg_weighting="bootstrap",
+                            engine=engine)  # fmt: skip
+
+
+def test_not_completed(engine):
+    """ref: tests/test_spectral_cluster_supertree.py:258-274"""
+    t1, t2 = "(a,(b,(c,d)))", "(a,(c,(b,d)))"
+    nc = NotCompleted("ERROR", "test", "failed upstream")
+    for trees, weights, expected in [
+        ([make_tree(t1), nc, make_tree(t2)], [3, 100, 1], t1),
+        ([make_tree(t1), nc, make_tree(t2)], [1, 100, 3], t2),
+        ([nc, make_tree(t1)], None, t1),
+    ]:
+        result = construct_supertree(trees, weights, engine=engine)
+        assert result.sorted().same_shape(make_tree(expected).sorted())
+
+
+def test_load_trees_and_cli(engine, tmp_path, monkeypatch):
+    """ref: tests/test_cli.py:14-49"""
+    from click.testing import CliRunner
+
+    from spectralclustersupertree_b200 import engine as engine_mod
+    from spectralclustersupertree_b200.cli import scs
+
+    monkeypatch.setattr(engine_mod, "_DEFAULT", engine)
+    fixture = json.loads((GOLDEN / "fixture_supertriplets.json").read_text())
+    in_file = tmp_path / "in.tre"
+    out_file = tmp_path / "out.tre"
+    in_file.write_text("\n".join(fixture["trees"]) + "\n")
+    loaded = load_trees(in_file)
+    assert len(loaded) == len(fixture["trees"])
+    runner = CliRunner()
+    result = runner.invoke(scs, ["-i", str(in_file), "-o", str(out_file), "-p", "DEPTH"])
+    assert result.exit_code == 0, result.output
+    assert rf(make_tree(out_file.read_text().strip()), make_tree(fixture["expected"])) == 0
+    assert runner.invoke(scs, []).exit_code in (0, 2)  # no_args_is_help
+    assert "version" in runner.invoke(scs, ["--version"]).output.lower()

@@ -1,0 +1,115 @@
+"""CPU: the flat source-tree store (csrc/forest.cpp) against the PhyloNode restatement.
+
+``Forest.induce`` must reproduce ``PhyloNode.get_sub_tree(names, ignore_missing=True,
+as_rooted=True)`` as the reference uses it (ref: scs.py:444-453) -- including the order of the
+floating-point additions when unary nodes are merged -- and ``Forest.tours`` must reproduce the
+Python flattening of ``flatten.py`` for every weighting."""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from helpers import load_case, parse
+from spectralclustersupertree_b200.engine import Forest
+from spectralclustersupertree_b200.flatten import flatten_trees
+from spectralclustersupertree_b200.tree import make_tree
+
+
+def assert_same_tours(a, b):
+    assert a.n == b.n
+    for field in ("leaf_offsets", "leaf_taxon", "adj_depth", "root_depth", "tree_weight"):
+        assert np.array_equal(getattr(a, field), getattr(b, field)), field
+    assert np.array_equal(a.adj_val, b.adj_val), "adj_val"  # bit-exact
+
+
+@pytest.mark.parametrize(
+    ("name", "weighting"),
+    [("supertriplets", "depth"), ("supertriplets", "one"), ("dcm_iq", "branch"), ("s_200x40_bootstrap", "bootstrap"),
+     ("s_300x40_branch_weighted", "branch"), ("c1_100x30_depth", "depth")],
+)  # fmt: skip
+def test_tours_match_python_flatten(name, weighting):
+    case = load_case(name)
+    trees = parse(case["lines"])
+    tid = {x: i for i, x in enumerate(case["names"])}
+    forest = Forest.from_trees(trees, case["weights"], case["names"])
+    assert forest.num_trees == len(trees)
+    assert np.array_equal(forest.taxa(), np.arange(len(case["names"])))
+    assert_same_tours(forest.tours(weighting), flatten_trees(trees, case["weights"], weighting, tid))
+
+
+@pytest.mark.parametrize("name", ["dcm_iq", "s_300x40_branch_weighted", "s_200x40_bootstrap", "supertriplets"])
+def test_induce_matches_get_sub_tree(name):
+    case = load_case(name)
+    trees = parse(case["lines"])
+    names = case["names"]
+    forest = Forest.from_trees(trees, case["weights"], names)
+    rng = np.random.RandomState(5)
+    for frac in (0.7, 0.3, 0.05):
+        keep = np.flatnonzero(rng.random_sample(len(names)) < frac).astype(np.int32)
+        if len(keep) < 3:
+            continue
+        kept_names = {names[i] for i in keep}
+        sub = forest.induce(keep)
+        ref_trees, ref_weights = [], []
+        for tree, w in zip(trees, case["weights"], strict=True):  # ref: scs.py:444-453
+            if len(kept_names.intersection(tree.get_tip_names())) < 2:
+                continue
+            s = tree.get_sub_tree(kept_names, ignore_missing=True, as_rooted=True)
+            s.name = "root"
+            ref_trees.append(s)
+            ref_weights.append(w)
+        assert sub.num_trees == len(ref_trees)
+        assert np.array_equal(sub.weights(), np.asarray(ref_weights))
+        present = sub.taxa()
+        local_names = [names[i] for i in present]
+        tid = {x: i for i, x in enumerate(local_names)}
+        for weighting in ("one", "depth", "branch", "bootstrap"):
+            if weighting == "bootstrap" and case["weighting"] != "bootstrap":
+                continue
+            assert_same_tours(sub.tours(weighting), flatten_trees(ref_trees, ref_weights, weighting, tid))
+        # a second restriction of the restricted forest behaves the same (the recursion nests them)
+        keep2 = present[:: 2]
+        if len(keep2) >= 3:
+            sub2 = sub.induce(keep2)
+            names2 = {names[i] for i in keep2}
+            ref2 = [t.get_sub_tree(names2, ignore_missing=True, as_rooted=True) for t in ref_trees
+                    if len(names2.intersection(t.get_tip_names())) >= 2]  # fmt: skip
+            w2 = [w for t, w in zip(ref_trees, ref_weights, strict=True)
+                  if len(names2.intersection(t.get_tip_names())) >= 2]  # fmt: skip
+            tid2 = {names[x]: i for i, x in enumerate(sub2.taxa())}
+            assert_same_tours(sub2.tours(case["weighting"]), flatten_trees(ref2, w2, case["weighting"], tid2))
+
+
+def test_unary_nodes_polytomies_and_lone_tips():
+    lines = ["((a:1,b:2):3,((c:1):2,(d:1,e:2,f:3):4):5);", "(a,(b,(c)));", "x;", "((x,a),b);"]
+    trees = parse(lines)
+    names = sorted({n for t in trees for n in t.get_tip_names()})
+    tid = {x: i for i, x in enumerate(names)}
+    forest = Forest.from_trees(trees, [1.0, 2.0, 3.0, 4.0], names)
+    assert forest.num_trees == 4
+    for weighting in ("one", "depth", "branch"):
+        assert_same_tours(forest.tours(weighting), flatten_trees(trees, [1.0, 2.0, 3.0, 4.0], weighting, tid))
+    sub = forest.induce(np.array([tid[x] for x in "acdx"], dtype=np.int32))
+    ref = [t.get_sub_tree(set("acdx"), ignore_missing=True, as_rooted=True) for t in trees
+           if len(set("acdx") & set(t.get_tip_names())) >= 2]  # fmt: skip
+    assert sub.num_trees == len(ref) == 3
+    tid2 = {names[x]: i for i, x in enumerate(sub.taxa())}
+    assert_same_tours(sub.tours("branch"), flatten_trees(ref, [1.0, 2.0, 4.0], "branch", tid2))
+
+
+def test_bootstrap_without_support_raises_type_error():
+    trees = [make_tree("(a,(b,(c,d)));"), make_tree("(a,(b,c));")]
+    names = ["a", "b", "c", "d"]
+    forest = Forest.from_trees(trees, [1.0, 1.0], names)
+    with pytest.raises(TypeError):
+        forest.tours("bootstrap")
+
+
+def test_forest_rejects_malformed_arrays():
+    from spectralclustersupertree_b200.engine import ScsError
+
+    with pytest.raises(ScsError):  # parent index not smaller than the node's own index
+        Forest.from_arrays([0, 3], [-1, 2, 0], None, None, [-1, 0, 1], [1.0], ["a", "b"])
+    with pytest.raises(ScsError):  # tip without a taxon id
+        Forest.from_arrays([0, 3], [-1, 0, 0], None, None, [-1, 0, -1], [1.0], ["a", "b"])
