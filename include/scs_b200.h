@@ -75,6 +75,20 @@ int scs_ctx_synchronize(scs_ctx *ctx);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 int64_t scs_ctx_launch_count(const scs_ctx *ctx);
 
+/* Bytes the *_host entry points copied host->device / device->host since the context was made. */
+int scs_ctx_io_bytes(const scs_ctx *ctx, int64_t *h2d, int64_t *d2h);
+/* A CUDA-event stopwatch on the context's stream (stop waits for the stream to reach it). */
+int scs_ctx_timer_start(scs_ctx *ctx);
+int scs_ctx_timer_stop(scs_ctx *ctx, double *ms);
+/* Evict the L2 cache by writing a 256 MB scratch buffer (benchmark hygiene between timed steps). */
+int scs_ctx_flush_l2(scs_ctx *ctx);
+/* Per-launch CUDA-event timing of the two heavy kernels on matrices of >= 2048 vertices:
+ * kind 0 = Laplacian matvec (units = flops), kind 1 = graph-build row kernel (units = ordered leaf
+ * pairs visited, known for host-tour calls).  _read sums and clears the records of one kind:
+ * launches, total ms, total algorithmic bytes, total units. */
+int scs_ctx_profile_enable(scs_ctx *ctx, int on);
+int scs_ctx_profile_read(scs_ctx *ctx, int kind, int64_t *launches, double *ms, double *bytes, double *units);
+
 /* ---- proper cluster graph: replaces _proper_cluster_graph_edges + _dfs_pcg_weights
  *      (scs.py:495-583, 586-663) ---------------------------------------------------------- *
  * in : n vertices, T trees, L leaves in total;

@@ -69,6 +69,12 @@ SIGNATURES: dict[str, tuple] = {
     "scs_ctx_destroy": (c_int, [_P]),
     "scs_ctx_synchronize": (c_int, [_P]),
     "scs_ctx_launch_count": (c_int64, [_P]),
+    "scs_ctx_io_bytes": (c_int, [_P, POINTER(c_int64), POINTER(c_int64)]),
+    "scs_ctx_timer_start": (c_int, [_P]),
+    "scs_ctx_timer_stop": (c_int, [_P, POINTER(c_double)]),
+    "scs_ctx_flush_l2": (c_int, [_P]),
+    "scs_ctx_profile_enable": (c_int, [_P, c_int]),
+    "scs_ctx_profile_read": (c_int, [_P, c_int, POINTER(c_int64), POINTER(c_double), POINTER(c_double), POINTER(c_double)]),
     "scs_bit_words": (c_int, [c_int]),
     "scs_pcg_build_dev": (c_int, [_P, c_int, c_int, c_int64] + [_P] * 12),
     "scs_components_dev": (c_int, [_P, c_int, _P, _P, POINTER(c_int32)]),

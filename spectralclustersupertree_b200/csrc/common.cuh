@@ -62,6 +62,7 @@ enum Slot : int {
     SLOT_SORTED,
     SLOT_SIDE,
     SLOT_SPEC_SCALARS,
+    SLOT_L2_FLUSH,
     SLOT_COUNT
 };
 
@@ -80,6 +81,19 @@ struct scs_ctx {
     size_t pinned_bytes = 0;
     void *pinned_io = nullptr;  // host staging for the tours of scs_node_split_host
     size_t pinned_io_bytes = 0;
+    int64_t h2d_bytes = 0;  // bytes copied by the *_host entry points
+    int64_t d2h_bytes = 0;
+    // optional per-launch timing of the two heavy kernels (bench.py's roofline figures)
+    bool profile_on = false;
+    struct ProfileRecord {
+        cudaEvent_t start, stop;
+        int kind;
+        double bytes, units;
+    };
+    std::vector<ProfileRecord> profile;
+    int flush_value = 0;
+    double pending_units = 0.0;  // leaf-pair visits of the node being built (set by host entry points)
+    cudaEvent_t timer_start = nullptr, timer_stop = nullptr;
     // shape of the node most recently processed by scs_node_split_host
     int last_n = 0;
     int last_m = 0;
@@ -115,6 +129,13 @@ inline int reserve_as(scs_ctx *ctx, Slot slot, size_t count, T **out) {
 }
 
 int reserve_pinned(scs_ctx *ctx, size_t bytes, void **out);
+
+enum ProfileKind : int { PROFILE_MATVEC = 0, PROFILE_PCG_ROWS = 1, PROFILE_KINDS = 2 };
+constexpr int kProfileMinSize = 2048;  // below this the matrices are L2-resident: no HBM roofline
+
+// Bracket the launch that follows / preceded with events when profiling is on.
+void profile_begin(scs_ctx *ctx, int kind, double bytes, double units);
+void profile_end(scs_ctx *ctx);
 
 inline int ceil_div(int64_t a, int64_t b) { return static_cast<int>((a + b - 1) / b); }
 

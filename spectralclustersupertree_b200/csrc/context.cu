@@ -62,6 +62,22 @@ int reserve_pinned(scs_ctx *ctx, size_t bytes, void **out) {
     return SCS_OK;
 }
 
+void profile_begin(scs_ctx *ctx, int kind, double bytes, double units) {
+    if (!ctx->profile_on) return;
+    scs_ctx::ProfileRecord rec;
+    rec.kind = kind;
+    rec.bytes = bytes;
+    rec.units = units;
+    if (cudaEventCreate(&rec.start) != cudaSuccess || cudaEventCreate(&rec.stop) != cudaSuccess) return;
+    cudaEventRecord(rec.start, ctx->stream);
+    ctx->profile.push_back(rec);
+}
+
+void profile_end(scs_ctx *ctx) {
+    if (!ctx->profile_on || ctx->profile.empty()) return;
+    cudaEventRecord(ctx->profile.back().stop, ctx->stream);
+}
+
 namespace {
 
 struct DeviceGuard {
@@ -254,6 +270,12 @@ int scs_ctx_destroy(scs_ctx *ctx) {
         if (buf.ptr) cudaFree(buf.ptr);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->pinned_io) cudaFreeHost(ctx->pinned_io);
+    for (auto &rec : ctx->profile) {
+        cudaEventDestroy(rec.start);
+        cudaEventDestroy(rec.stop);
+    }
+    if (ctx->timer_start) cudaEventDestroy(ctx->timer_start);
+    if (ctx->timer_stop) cudaEventDestroy(ctx->timer_stop);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return SCS_OK;
@@ -267,6 +289,85 @@ int scs_ctx_synchronize(scs_ctx *ctx) {
 }
 
 int64_t scs_ctx_launch_count(const scs_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int scs_ctx_io_bytes(const scs_ctx *ctx, int64_t *h2d, int64_t *d2h) {
+    if (!ctx) return SCS_ERR_INVALID;
+    if (h2d) *h2d = ctx->h2d_bytes;
+    if (d2h) *d2h = ctx->d2h_bytes;
+    return SCS_OK;
+}
+
+int scs_ctx_timer_start(scs_ctx *ctx) {
+    if (!ctx) return SCS_ERR_INVALID;
+    DeviceGuard guard(ctx->device);
+    if (!ctx->timer_start) {
+        SCS_CUDA(ctx, cudaEventCreate(&ctx->timer_start));
+        SCS_CUDA(ctx, cudaEventCreate(&ctx->timer_stop));
+    }
+    SCS_CUDA(ctx, cudaEventRecord(ctx->timer_start, ctx->stream));
+    return SCS_OK;
+}
+
+int scs_ctx_timer_stop(scs_ctx *ctx, double *ms) {
+    if (!ctx || !ms || !ctx->timer_start) return SCS_ERR_INVALID;
+    DeviceGuard guard(ctx->device);
+    SCS_CUDA(ctx, cudaEventRecord(ctx->timer_stop, ctx->stream));
+    SCS_CUDA(ctx, cudaEventSynchronize(ctx->timer_stop));
+    float t = 0.0f;
+    SCS_CUDA(ctx, cudaEventElapsedTime(&t, ctx->timer_start, ctx->timer_stop));
+    *ms = t;
+    return SCS_OK;
+}
+
+int scs_ctx_flush_l2(scs_ctx *ctx) {
+    if (!ctx) return SCS_ERR_INVALID;
+    DeviceGuard guard(ctx->device);
+    const size_t bytes = 256u << 20;  // twice the 126 MB L2
+    void *buf;
+    int rc = reserve(ctx, SLOT_L2_FLUSH, bytes, &buf);
+    if (rc) return rc;
+    ctx->flush_value += 1;
+    SCS_CUDA(ctx, cudaMemsetAsync(buf, ctx->flush_value & 0xff, bytes, ctx->stream));
+    SCS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SCS_OK;
+}
+
+int scs_ctx_profile_enable(scs_ctx *ctx, int on) {
+    if (!ctx) return SCS_ERR_INVALID;
+    ctx->profile_on = on != 0;
+    return SCS_OK;
+}
+
+int scs_ctx_profile_read(scs_ctx *ctx, int kind, int64_t *launches, double *ms, double *bytes, double *units) {
+    if (!ctx || kind < 0 || kind >= PROFILE_KINDS) return SCS_ERR_INVALID;
+    DeviceGuard guard(ctx->device);
+    SCS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int64_t count = 0;
+    double total_ms = 0.0, total_bytes = 0.0, total_units = 0.0;
+    std::vector<scs_ctx::ProfileRecord> keep;
+    for (auto &rec : ctx->profile) {
+        if (rec.kind != kind) {
+            keep.push_back(rec);
+            continue;
+        }
+        float t = 0.0f;
+        if (cudaEventElapsedTime(&t, rec.start, rec.stop) == cudaSuccess) {
+            count += 1;
+            total_ms += t;
+            total_bytes += rec.bytes;
+            total_units += rec.units;
+        }
+        cudaEventDestroy(rec.start);
+        cudaEventDestroy(rec.stop);
+    }
+    cudaGetLastError();
+    ctx->profile.swap(keep);
+    if (launches) *launches = count;
+    if (ms) *ms = total_ms;
+    if (bytes) *bytes = total_bytes;
+    if (units) *units = total_units;
+    return SCS_OK;
+}
 
 int scs_pcg_build_dev(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offsets_dev,
                       const int32_t *leaf_taxon_dev, const int32_t *adj_depth_dev, const double *adj_val_dev,
@@ -381,6 +482,12 @@ int scs_node_split_host(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *le
         std::memcpy(stage + o_dep, adj_depth, b_dep);
     }
     SCS_CUDA(ctx, cudaMemcpyAsync(dev_stage, stage, total - 64, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->h2d_bytes += static_cast<int64_t>(total - 64);
+    ctx->pending_units = 0.0;
+    for (int t = 0; t < T; ++t) {
+        const double k = static_cast<double>(leaf_offsets[t + 1] - leaf_offsets[t]);
+        ctx->pending_units += k * (k - 1.0);
+    }
 
     int32_t *part_dev;
     if ((rc = reserve_as(ctx, SLOT_PART, static_cast<size_t>(n), &part_dev))) return rc;
@@ -393,6 +500,8 @@ int scs_node_split_host(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *le
     if (rc) return rc;
     SCS_CUDA(ctx, cudaMemcpyAsync(part, part_dev, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
     SCS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->d2h_bytes += static_cast<int64_t>(sizeof(int32_t)) * n;
+    ctx->pending_units = 0.0;
     return SCS_OK;
 }
 

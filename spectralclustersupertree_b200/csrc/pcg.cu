@@ -309,9 +309,15 @@ int launch_rows(scs_ctx *ctx, int n, int words, int cols_per_chunk, int nchunks,
     auto kernel = pcg_rows_kernel<CountT, kWriteC>;
     SCS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     dim3 grid(n, nchunks);
+    if (n >= kProfileMinSize) {
+        // algorithmic bytes: W + both bit matrices + occ/degree written once, C if asked
+        const double out_bytes = 8.0 * n * n + (C ? 4.0 * n * n : 0.0) + 8.0 * n * words + 12.0 * n;
+        profile_begin(ctx, PROFILE_PCG_ROWS, out_bytes, ctx->pending_units);
+    }
     kernel<<<grid, kRowThreads, smem, ctx->stream>>>(n, words, cols_per_chunk, leaf_offsets, leaf_taxon, adj_depth,
                                                      adj_val, root_depth, tree_weight, leaf_tree, row_ptr,
                                                      inv_sorted, occ, W, C, adj_bits, max_bits, degree_part);
+    if (n >= kProfileMinSize) profile_end(ctx);
     SCS_LAUNCHED(ctx, "pcg_rows_kernel");
     return SCS_OK;
 }

@@ -29,7 +29,7 @@ namespace {
 constexpr int kMaxBasis = 256;        // Lanczos vectors per (re)start
 constexpr int kMaxRestarts = 8;
 constexpr double kResidualTol = 1e-12;  // |beta_j s_j| of the Fiedler Ritz pair (|N| <= 1)
-constexpr double kBreakdown = 1e-13;
+constexpr double kBreakdown = 1e-11;  // beta_j below this: the Krylov space is invariant
 constexpr double kGapTie = 1e-7;      // lambda_3 - lambda_2 below this: eigenvector is ill-defined
 constexpr double kMarginTie = 1e-9;   // a vertex this close (relative) to the 2-means boundary
 
@@ -189,7 +189,10 @@ matvec_row_per_warp(int m, const double *__restrict__ W, const double *__restric
 
 int launch_matvec(scs_ctx *ctx, int m, const double *W, const double *isd, const double *z, double *y) {
     if (m >= 2048) {
+        // algorithmic bytes: W once + read z, isd, write y
+        if (m >= kProfileMinSize) profile_begin(ctx, PROFILE_MATVEC, 8.0 * m * m + 24.0 * m, 2.0 * m * m);
         matvec_row_per_cta<<<m, kMvThreads, 0, ctx->stream>>>(m, W, isd, z, y);
+        if (m >= kProfileMinSize) profile_end(ctx);
         SCS_LAUNCHED(ctx, "matvec_row_per_cta");
     } else {
         matvec_row_per_warp<<<ceil_div(static_cast<int64_t>(m) * 32, kMvThreads), kMvThreads, 0, ctx->stream>>>(
@@ -233,12 +236,15 @@ multi_axpy(int m, int nb, const double *__restrict__ basis, const double *__rest
     w[i] = acc;
 }
 
-// beta = |w|; next = w / beta; z = isd .* next; records alpha_j = h1[j] + h2[j] and beta_j.
-// j == 0 is the normalisation of the start vector (nothing recorded).  One CTA.
+// beta = |w|; next = w / beta; z = isd .* next; records alpha_j = h1[hj] + h2[hj] (hj = position of
+// v_j in the basis) and beta_j.  j == 0 is the normalisation of the start vector (nothing recorded).
+// The first j whose beta_j is negligible (the Krylov space is invariant: later vectors are noise)
+// is latched in state[0]; the projected problem is then solved on the leading block only.  One CTA.
 __global__ void __launch_bounds__(kOneCta)
-normalize_step(int m, int j, const double *__restrict__ w, const double *__restrict__ isd,
+normalize_step(int m, int j, int hj, const double *__restrict__ w, const double *__restrict__ isd,
                const double *__restrict__ h1, const double *__restrict__ h2, double *__restrict__ alpha,
-               double *__restrict__ beta, double *__restrict__ next, double *__restrict__ z) {
+               double *__restrict__ beta, double *__restrict__ next, double *__restrict__ z,
+               int32_t *__restrict__ state) {
     __shared__ double scratch[33];
     double ss = 0.0;
     for (int i = threadIdx.x; i < m; i += blockDim.x) ss = fma(w[i], w[i], ss);
@@ -246,7 +252,12 @@ normalize_step(int m, int j, const double *__restrict__ w, const double *__restr
     const double b = sqrt(ss);
     if (threadIdx.x == 0) {
         beta[j] = b;
-        if (j > 0) alpha[j] = h1[j] + h2[j];
+        if (j > 0) {
+            alpha[j] = h1[hj] + h2[hj];
+            if (b <= kBreakdown && state[0] == 0) state[0] = j;
+        } else {
+            state[0] = 0;
+        }
     }
     const double inv = b > 0.0 ? 1.0 / b : 0.0;
     for (int i = threadIdx.x; i < m; i += blockDim.x) {
@@ -260,7 +271,9 @@ normalize_step(int m, int j, const double *__restrict__ w, const double *__restr
 // T = tridiag(alpha[1..j]; beta[1..j-1]).  Finds its two largest eigenvalues by Sturm-count
 // multi-section (blockDim.x probes per round), the eigenvector s of the largest by a twisted
 // factorisation, and the Lanczos residual estimate beta[j] * |s_j|.
-// out: [0] theta1, [1] theta2 (NaN if j == 1), [2] residual estimate, [3] beta[j]
+// If state[0] latched a breakdown step jb <= j, only the leading jb x jb block is solved.
+// out: [0] theta1, [1] theta2 (NaN if the block is 1 x 1), [2] residual estimate, [3] beta[j_eff],
+//      [4] j_eff
 __device__ __forceinline__ int sturm_count(const double *a, const double *b2, int j, double x, double pivmin) {
     int cnt = 0;
     double q = a[1] - x;
@@ -275,9 +288,11 @@ __device__ __forceinline__ int sturm_count(const double *a, const double *b2, in
 }
 
 __global__ void __launch_bounds__(256)
-tridiag_ritz(int j, const double *__restrict__ alpha, const double *__restrict__ beta, double *__restrict__ coef,
-             double *__restrict__ out) {
+tridiag_ritz(int jrun, const double *__restrict__ alpha, const double *__restrict__ beta,
+             const int32_t *__restrict__ state, double *__restrict__ coef, double *__restrict__ out) {
     extern __shared__ double sm[];
+    const int latched = state[0];
+    const int j = latched > 0 && latched < jrun ? latched : jrun;
     double *a = sm;                 // [j + 2], 1-based
     double *b = a + (j + 2);        // [j + 2]
     double *b2 = b + (j + 2);       // squares
@@ -382,7 +397,9 @@ tridiag_ritz(int j, const double *__restrict__ alpha, const double *__restrict__
         }
         const double inv = 1.0 / sqrt(norm2);
         for (int i = 1; i <= j; ++i) coef[i] = b2[i] * inv;
-        coef[0] = 0.0;  // no component along the deflated vector
+        for (int i = j + 1; i <= jrun; ++i) coef[i] = 0.0;  // vectors after a breakdown are noise
+        coef[0] = 0.0;
+        out[4] = static_cast<double>(j);
         out[0] = th;
         out[1] = j >= 2 ? theta[1] : nan("");
         out[2] = fabs(b[j] * b2[j] * inv);
@@ -390,7 +407,8 @@ tridiag_ritz(int j, const double *__restrict__ alpha, const double *__restrict__
     }
 }
 
-// y = sum_{k=1..j} coef[k] basis[k], normalised;  z = isd .* y.  One CTA.
+// y = sum_{k=1..j} coef[k] v_k, normalised (`basis` points at v_0, the row before v_1);
+// z = isd .* y.  One CTA.
 __global__ void __launch_bounds__(kOneCta)
 ritz_vector(int m, int j, const double *__restrict__ basis, const double *__restrict__ coef,
             const double *__restrict__ isd, double *__restrict__ y, double *__restrict__ z) {
@@ -600,6 +618,93 @@ int normalized_matvec(scs_ctx *ctx, int m, const double *W, const double *isd, c
     return launch_matvec(ctx, m, W, isd, z, y);
 }
 
+namespace {
+
+struct LanczosOutcome {
+    double theta1 = 0.0, theta2 = 0.0, estimate = 0.0;
+    int steps = 0;        // size of the projected problem that produced the pair
+    bool converged = false;
+    bool invariant = false;  // stopped on a breakdown: the Krylov space is an invariant subspace
+    int matvecs = 0;
+    int restarts = 0;
+};
+
+struct LanczosBuffers {
+    double *isd, *basis, *w, *z, *coef, *h1, *h2, *alpha, *beta, *ritz;
+    int32_t *state;
+    double *pin;
+};
+
+// Largest eigenpair of N = D^-1/2 W D^-1/2 on the orthogonal complement of the first `ndefl` rows of
+// `basis`.  Lanczos vectors go to rows ndefl, ndefl+1, ...; the Ritz vector to `y` (and isd .* y to z).
+int lanczos_largest(scs_ctx *ctx, int m, const double *W, const LanczosBuffers &b, int ndefl, uint64_t seed,
+                    double *y, LanczosOutcome *out) {
+    const int dim = m - ndefl;  // dimension of the deflated space
+    const int jmax = dim < kMaxBasis ? dim : kMaxBasis;
+    const int vec_blocks = ceil_div(m, kVecThreads);
+    double *v0 = b.basis + static_cast<size_t>(ndefl - 1) * m;  // v_k lives at v0 + k m
+    auto orthogonalise = [&](int nb, double *h) -> int {
+        multi_dot<<<nb, kVecThreads, 0, ctx->stream>>>(m, b.basis, b.w, h);
+        SCS_LAUNCHED(ctx, "multi_dot");
+        multi_axpy<<<vec_blocks, kVecThreads, nb * sizeof(double), ctx->stream>>>(m, nb, b.basis, h, b.w);
+        SCS_LAUNCHED(ctx, "multi_axpy");
+        return SCS_OK;
+    };
+    int rc;
+    int jdone = 0;
+    for (int attempt = 0; attempt <= kMaxRestarts && !out->converged; ++attempt) {
+        if (attempt == 0) {
+            random_start<<<vec_blocks, kVecThreads, 0, ctx->stream>>>(m, seed, b.w);
+            SCS_LAUNCHED(ctx, "random_start");
+        } else {
+            // explicit restart from the current Ritz vector
+            SCS_CUDA(ctx, cudaMemcpyAsync(b.w, y, sizeof(double) * m, cudaMemcpyDeviceToDevice, ctx->stream));
+            out->restarts = attempt;
+        }
+        if ((rc = orthogonalise(ndefl, b.h1))) return rc;
+        if ((rc = orthogonalise(ndefl, b.h2))) return rc;
+        normalize_step<<<1, kOneCta, 0, ctx->stream>>>(m, 0, 0, b.w, b.isd, b.h1, b.h2, b.alpha, b.beta, v0 + m, b.z,
+                                                       b.state);
+        SCS_LAUNCHED(ctx, "normalize_step");
+        for (int j = 1; j <= jmax; ++j) {
+            if ((rc = launch_matvec(ctx, m, W, b.isd, b.z, b.w))) return rc;
+            out->matvecs += 1;
+            if ((rc = orthogonalise(ndefl + j, b.h1))) return rc;
+            if ((rc = orthogonalise(ndefl + j, b.h2))) return rc;
+            normalize_step<<<1, kOneCta, 0, ctx->stream>>>(m, j, ndefl - 1 + j, b.w, b.isd, b.h1, b.h2, b.alpha, b.beta,
+                                                           v0 + static_cast<size_t>(j + 1) * m, b.z, b.state);
+            SCS_LAUNCHED(ctx, "normalize_step");
+            jdone = j;
+            const bool check = j == jmax || (j % 4) == 0;
+            if (!check) continue;
+            tridiag_ritz<<<1, 256, 5 * (j + 2) * sizeof(double), ctx->stream>>>(j, b.alpha, b.beta, b.state, b.coef,
+                                                                               b.ritz);
+            SCS_LAUNCHED(ctx, "tridiag_ritz");
+            SCS_CUDA(ctx, cudaMemcpyAsync(b.pin, b.ritz, 5 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            SCS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            out->theta1 = b.pin[0];
+            out->theta2 = b.pin[1];
+            out->estimate = b.pin[2];
+            out->steps = static_cast<int>(b.pin[4]);
+            if (b.pin[3] <= kBreakdown) {
+                out->converged = true;
+                out->invariant = true;
+                break;
+            }
+            if (out->estimate <= kResidualTol) {
+                out->converged = true;
+                break;
+            }
+        }
+        // Ritz vector of the current basis (also the restart vector); coefficients past a breakdown are 0
+        ritz_vector<<<1, kOneCta, (jdone + 1) * sizeof(double), ctx->stream>>>(m, jdone, v0, b.coef, b.isd, y, b.z);
+        SCS_LAUNCHED(ctx, "ritz_vector");
+    }
+    return SCS_OK;
+}
+
+}  // namespace
+
 int spectral_bipartition(scs_ctx *ctx, int m, const double *W, const double *degree, uint64_t seed, int32_t *side,
                          scs_node_stats *stats) {
     if (m < 2 || !W || !side || !stats) return fail(ctx, SCS_ERR_INVALID, "spectral_bipartition: bad argument");
@@ -614,26 +719,32 @@ int spectral_bipartition(scs_ctx *ctx, int m, const double *W, const double *deg
         stats->margin = 0.5;
         return SCS_OK;
     }
-    const int jmax = m - 1 < kMaxBasis ? m - 1 : kMaxBasis;  // the deflated space has dimension m - 1
-    double *isd, *basis, *w, *z, *coef, *tri, *ritz, *embed, *sorted, *deg_own;
+    const int jcap = m - 1 < kMaxBasis ? m - 1 : kMaxBasis;
+    LanczosBuffers b;
+    double *tri, *embed, *sorted, *deg_own, *work;
     int32_t *flags;
-    if ((rc = reserve_as(ctx, SLOT_ISD, static_cast<size_t>(m), &isd))) return rc;
-    if ((rc = reserve_as(ctx, SLOT_BASIS, static_cast<size_t>(jmax + 2) * m, &basis))) return rc;
-    if ((rc = reserve_as(ctx, SLOT_WORK, 2 * static_cast<size_t>(m), &w))) return rc;
-    if ((rc = reserve_as(ctx, SLOT_UVEC, static_cast<size_t>(m), &z))) return rc;
-    if ((rc = reserve_as(ctx, SLOT_COEF, 3 * static_cast<size_t>(kMaxBasis + 4), &coef))) return rc;
-    if ((rc = reserve_as(ctx, SLOT_TRIDIAG, 2 * static_cast<size_t>(kMaxBasis + 4), &tri))) return rc;
-    if ((rc = reserve_as(ctx, SLOT_RITZ, 16, &ritz))) return rc;
+    if ((rc = reserve_as(ctx, SLOT_ISD, static_cast<size_t>(m), &b.isd))) return rc;
+    if ((rc = reserve_as(ctx, SLOT_BASIS, static_cast<size_t>(jcap + 3) * m, &b.basis))) return rc;
+    if ((rc = reserve_as(ctx, SLOT_WORK, 3 * static_cast<size_t>(m), &work))) return rc;
+    if ((rc = reserve_as(ctx, SLOT_UVEC, static_cast<size_t>(m), &b.z))) return rc;
+    if ((rc = reserve_as(ctx, SLOT_COEF, 3 * static_cast<size_t>(kMaxBasis + 8), &b.coef))) return rc;
+    if ((rc = reserve_as(ctx, SLOT_TRIDIAG, 2 * static_cast<size_t>(kMaxBasis + 8), &tri))) return rc;
+    if ((rc = reserve_as(ctx, SLOT_RITZ, 32, &b.ritz))) return rc;
     if ((rc = reserve_as(ctx, SLOT_EMBED, static_cast<size_t>(m), &embed))) return rc;
     const int P = next_pow2(m);
     if ((rc = reserve_as(ctx, SLOT_SORTED, static_cast<size_t>(P), &sorted))) return rc;
     if ((rc = reserve_as(ctx, SLOT_SPEC_SCALARS, 16, &flags))) return rc;
-    double *h1 = coef + (kMaxBasis + 4), *h2 = h1 + (kMaxBasis + 4);
-    double *alpha = tri, *beta = tri + (kMaxBasis + 4);
-    double *yvec = w + m;
+    b.h1 = b.coef + (kMaxBasis + 8);
+    b.h2 = b.h1 + (kMaxBasis + 8);
+    b.alpha = tri;
+    b.beta = tri + (kMaxBasis + 8);
+    b.w = work;
+    b.state = flags + 4;
+    double *yvec = work + m, *y2 = work + 2 * static_cast<size_t>(m);
     void *pin_v;
     if ((rc = reserve_pinned(ctx, 256, &pin_v))) return rc;
-    double *pin = static_cast<double *>(pin_v);
+    b.pin = static_cast<double *>(pin_v);
+    double *pin = b.pin;
 
     SCS_CUDA(ctx, cudaMemsetAsync(flags, 0, 16 * sizeof(int32_t), ctx->stream));
     if (!degree) {
@@ -642,98 +753,61 @@ int spectral_bipartition(scs_ctx *ctx, int m, const double *W, const double *deg
         SCS_LAUNCHED(ctx, "row_sums");
         degree = deg_own;
     }
-    prepare_scaling<<<1, kOneCta, 0, ctx->stream>>>(m, degree, isd, basis, flags);
+    prepare_scaling<<<1, kOneCta, 0, ctx->stream>>>(m, degree, b.isd, b.basis, flags);
     SCS_LAUNCHED(ctx, "prepare_scaling");
 
-    const int vec_blocks = ceil_div(m, kVecThreads);
-    auto orthogonalise = [&](int nb, double *h) -> int {
-        multi_dot<<<nb, kVecThreads, 0, ctx->stream>>>(m, basis, w, h);
-        SCS_LAUNCHED(ctx, "multi_dot");
-        multi_axpy<<<vec_blocks, kVecThreads, nb * sizeof(double), ctx->stream>>>(m, nb, basis, h, w);
-        SCS_LAUNCHED(ctx, "multi_axpy");
-        return SCS_OK;
-    };
-
     stats->solver = 3;
-    stats->matvecs = 0;
-    stats->restarts = 0;
-    double theta1 = std::nan(""), theta2 = std::nan(""), est = std::nan("");
-    int jdone = 0;
-    bool converged = false;
-    for (int attempt = 0; attempt <= kMaxRestarts && !converged; ++attempt) {
-        if (attempt == 0) {
-            random_start<<<vec_blocks, kVecThreads, 0, ctx->stream>>>(m, seed, w);
-            SCS_LAUNCHED(ctx, "random_start");
-        } else {
-            // explicit restart from the current Ritz vector
-            SCS_CUDA(ctx, cudaMemcpyAsync(w, yvec, sizeof(double) * m, cudaMemcpyDeviceToDevice, ctx->stream));
-            stats->restarts = attempt;
-        }
-        if ((rc = orthogonalise(1, h1))) return rc;
-        if ((rc = orthogonalise(1, h2))) return rc;
-        normalize_step<<<1, kOneCta, 0, ctx->stream>>>(m, 0, w, isd, h1, h2, alpha, beta, basis + m, z);
-        SCS_LAUNCHED(ctx, "normalize_step");
-        for (int j = 1; j <= jmax; ++j) {
-            if ((rc = launch_matvec(ctx, m, W, isd, z, w))) return rc;
-            stats->matvecs += 1;
-            if ((rc = orthogonalise(j + 1, h1))) return rc;
-            if ((rc = orthogonalise(j + 1, h2))) return rc;
-            normalize_step<<<1, kOneCta, 0, ctx->stream>>>(m, j, w, isd, h1, h2, alpha, beta,
-                                                           basis + static_cast<size_t>(j + 1) * m, z);
-            SCS_LAUNCHED(ctx, "normalize_step");
-            jdone = j;
-            const bool check = j == jmax || (j >= 6 && (j % 4) == 0);
-            if (!check) continue;
-            tridiag_ritz<<<1, 256, 5 * (j + 2) * sizeof(double), ctx->stream>>>(j, alpha, beta, coef, ritz);
-            SCS_LAUNCHED(ctx, "tridiag_ritz");
-            SCS_CUDA(ctx, cudaMemcpyAsync(pin, ritz, 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-            SCS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            theta1 = pin[0];
-            theta2 = pin[1];
-            est = pin[2];
-            const double bj = pin[3];
-            if (est <= kResidualTol || bj <= kBreakdown) {
-                converged = true;
-                break;
-            }
-        }
-        // Ritz vector of the current basis (also the restart vector)
-        ritz_vector<<<1, kOneCta, (jdone + 1) * sizeof(double), ctx->stream>>>(m, jdone, basis, coef, isd, yvec, z);
-        SCS_LAUNCHED(ctx, "ritz_vector");
-    }
+    LanczosOutcome first;
+    if ((rc = lanczos_largest(ctx, m, W, b, 1, seed, yvec, &first))) return rc;
+    stats->matvecs = first.matvecs;
+    stats->restarts = first.restarts;
 
-    // true residual of the accepted pair: one more operator application
-    if ((rc = launch_matvec(ctx, m, W, isd, z, w))) return rc;
+    // true residual of the accepted pair: one more operator application (z = isd .* y is current)
+    if ((rc = launch_matvec(ctx, m, W, b.isd, b.z, b.w))) return rc;
     stats->matvecs += 1;
-    true_residual<<<1, kOneCta, 0, ctx->stream>>>(m, yvec, w, ritz, ritz + 4);
+    true_residual<<<1, kOneCta, 0, ctx->stream>>>(m, yvec, b.w, b.ritz, b.ritz + 8);
     SCS_LAUNCHED(ctx, "true_residual");
+    SCS_CUDA(ctx, cudaMemcpyAsync(pin + 8, b.ritz + 8, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+
+    // The second Ritz value of the same Krylov space only bounds the next eigenvalue from below.  If the
+    // space closed early (fewer than m - 1 steps), an eigenvalue of N is repeated -- possibly the Fiedler
+    // one.  Settle it with a second run deflated by the Fiedler vector as well.
+    double theta_next = first.theta2;
+    if (first.invariant && first.steps < m - 1 && m >= 3) {
+        SCS_CUDA(ctx, cudaMemcpyAsync(b.basis + m, yvec, sizeof(double) * m, cudaMemcpyDeviceToDevice, ctx->stream));
+        LanczosOutcome second;
+        b.ritz += 16;  // keep the first pair's scalars
+        rc = lanczos_largest(ctx, m, W, b, 2, seed + 0x5bd1e995u, y2, &second);
+        b.ritz -= 16;
+        if (rc) return rc;
+        stats->matvecs += second.matvecs;
+        theta_next = second.theta1;
+    }
 
     if (P <= 8192) {
         auto kernel = two_means_1d<true>;
         const size_t smem = static_cast<size_t>(P) * sizeof(double);
         if (smem > 48 * 1024)
             SCS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        kernel<<<1, kOneCta, smem, ctx->stream>>>(m, P, yvec, isd, embed, sorted, side, ritz + 8);
+        kernel<<<1, kOneCta, smem, ctx->stream>>>(m, P, yvec, b.isd, embed, sorted, side, b.ritz + 12);
     } else {
-        two_means_1d<false><<<1, kOneCta, 0, ctx->stream>>>(m, P, yvec, isd, embed, sorted, side, ritz + 8);
+        two_means_1d<false><<<1, kOneCta, 0, ctx->stream>>>(m, P, yvec, b.isd, embed, sorted, side, b.ritz + 12);
     }
     SCS_LAUNCHED(ctx, "two_means_1d");
-    SCS_CUDA(ctx, cudaMemcpyAsync(pin, ritz, 12 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    SCS_CUDA(ctx, cudaMemcpyAsync(pin + 12, flags, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SCS_CUDA(ctx, cudaMemcpyAsync(pin + 12, b.ritz + 12, 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SCS_CUDA(ctx, cudaMemcpyAsync(pin + 16, flags, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     SCS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    theta1 = pin[0];
-    theta2 = pin[1];
     stats->eig[0] = 0.0;
-    stats->eig[1] = 1.0 - theta1;
-    stats->eig[2] = 1.0 - theta2;
-    stats->residual = pin[4];
-    stats->margin = pin[8];
-    const int32_t bad_degree = reinterpret_cast<const int32_t *>(pin + 12)[0];
+    stats->eig[1] = 1.0 - first.theta1;
+    stats->eig[2] = 1.0 - theta_next;
+    stats->residual = pin[8];
+    stats->margin = pin[12];
+    const int32_t bad_degree = reinterpret_cast<const int32_t *>(pin + 16)[0];
     stats->tie_flag = 0;
-    if (!std::isnan(theta2) && (theta1 - theta2) < kGapTie) stats->tie_flag |= 1;
+    if (!std::isnan(theta_next) && (first.theta1 - theta_next) < kGapTie) stats->tie_flag |= 1;
     if (!(stats->margin >= kMarginTie)) stats->tie_flag |= 2;
-    if (!converged) stats->tie_flag |= 4;  // accepted at the restart limit: see stats->residual
-    if (bad_degree) stats->tie_flag |= 8;  // negative / non-finite degree: sklearn's result is NaN-driven
+    if (!first.converged) stats->tie_flag |= 4;  // accepted at the restart limit: see stats->residual
+    if (bad_degree) stats->tie_flag |= 8;        // negative / non-finite degree: sklearn's result is NaN-driven
     return SCS_OK;
 }
 

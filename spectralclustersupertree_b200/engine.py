@@ -81,6 +81,36 @@ class Engine:
     def synchronize(self) -> None:
         _check(self._lib.scs_ctx_synchronize(self._ctx), self._ctx)
 
+    def io_bytes(self) -> tuple[int, int]:
+        """(host->device, device->host) bytes copied by the host-buffer entry points so far."""
+        h2d, d2h = ctypes.c_int64(0), ctypes.c_int64(0)
+        _check(self._lib.scs_ctx_io_bytes(self._ctx, ctypes.byref(h2d), ctypes.byref(d2h)), self._ctx)
+        return h2d.value, d2h.value
+
+    def timer_start(self) -> None:
+        _check(self._lib.scs_ctx_timer_start(self._ctx), self._ctx)
+
+    def timer_stop(self) -> float:
+        """Milliseconds since ``timer_start`` on the context's stream (CUDA events)."""
+        ms = ctypes.c_double(0.0)
+        _check(self._lib.scs_ctx_timer_stop(self._ctx, ctypes.byref(ms)), self._ctx)
+        return ms.value
+
+    def flush_l2(self) -> None:
+        _check(self._lib.scs_ctx_flush_l2(self._ctx), self._ctx)
+
+    def profile(self, on: bool) -> None:
+        _check(self._lib.scs_ctx_profile_enable(self._ctx, int(on)), self._ctx)
+
+    def profile_read(self, kind: int) -> dict:
+        """Summed per-launch event timings of one kernel kind (0 matvec, 1 graph-build rows)."""
+        n, ms, nbytes, units = ctypes.c_int64(0), ctypes.c_double(0), ctypes.c_double(0), ctypes.c_double(0)
+        status = self._lib.scs_ctx_profile_read(
+            self._ctx, kind, ctypes.byref(n), ctypes.byref(ms), ctypes.byref(nbytes), ctypes.byref(units)
+        )
+        _check(status, self._ctx)
+        return {"launches": n.value, "ms": ms.value, "bytes": nbytes.value, "units": units.value}
+
     # -- raw device memory (tests, bench) -------------------------------------------------------
     def alloc(self, nbytes: int) -> int:
         out = ctypes.c_void_p()

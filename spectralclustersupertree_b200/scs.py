@@ -98,8 +98,12 @@ def supertree_of_forest(
     seed: int = 0,
     engine: Engine | None = None,
     trace: list | None = None,
+    node_hook=None,
 ) -> PhyloNode:
-    """The recursion of ``construct_supertree`` (ref: scs.py:96-174) on a flat ``Forest``."""
+    """The recursion of ``construct_supertree`` (ref: scs.py:96-174) on a flat ``Forest``.
+
+    ``node_hook(forest, seed)``, if given, is called for every recursion node that reaches the GPU,
+    just before it is split (bench.py records the nodes with it)."""
     if pcg_weighting not in WEIGHTINGS:
         msg = f"Invalid weighting strategy selected: '{pcg_weighting}'"
         raise ValueError(msg)
@@ -127,6 +131,8 @@ def supertree_of_forest(
         if len(present) <= 2:  # ref: scs.py:105-106
             place(parent, slot, _star([names[x] for x in present]))
             continue
+        if node_hook is not None:
+            node_hook(current, seed + node_counter)
         taxa, part, stats = engine.forest_split(
             current, pcg_weighting, contract_edges=contract_edges, seed=seed + node_counter
         )
