@@ -55,12 +55,18 @@ typedef struct {
     int32_t solver;          /* 0 none, 1 trivial (m = 2), 2 dense Jacobi (one CTA), 3 Lanczos */
     int32_t matvecs;         /* operator applications in the Lanczos solver */
     int32_t restarts;
-    int32_t tie_flag;        /* 1 if eigengap or 2-means margin is below the thresholds */
-    int32_t reserved;
+    int32_t tie_flag;        /* bit 0: eigengap lambda_3 - lambda_2 < 1e-7; bit 1: a vertex within 1e-9
+                                (relative) of the 2-means boundary; bit 2: eigensolver stopped at its
+                                restart limit; bit 3: a degree is negative or not finite; bit 4: the
+                                1-D 2-means has more than one Lloyd-stable split, i.e. sklearn's
+                                k-means outcome depends on its random initialisation */
+    int32_t kmeans_stable_splits; /* number of Lloyd-stable splits of the Fiedler coordinate */
     double eig[3];           /* three smallest eigenvalues of L = I - D^-1/2 W D^-1/2 (eig[0] = 0;
                                 eig[2] is the solver's estimate, NaN if not available) */
     double residual;         /* || N y - theta y ||_2 of the Fiedler Ritz pair */
     double margin;           /* min_i |u_i - midpoint| / range(u): distance to the 2-means cut */
+    double kmeans_runner_up; /* between-cluster score of the best other stable split / the optimum's
+                                (0 if the optimum is the only stable split) */
 } scs_node_stats;
 
 /* ---- context ---------------------------------------------------------------------------- */

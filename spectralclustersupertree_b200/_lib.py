@@ -33,10 +33,11 @@ class NodeStats(ctypes.Structure):
         ("matvecs", c_int32),
         ("restarts", c_int32),
         ("tie_flag", c_int32),
-        ("reserved", c_int32),
+        ("kmeans_stable_splits", c_int32),
         ("eig", c_double * 3),
         ("residual", c_double),
         ("margin", c_double),
+        ("kmeans_runner_up", c_double),
     ]
 
     def as_dict(self) -> dict:
@@ -51,6 +52,8 @@ class NodeStats(ctypes.Structure):
             "eig": [self.eig[0], self.eig[1], self.eig[2]],
             "residual": self.residual,
             "margin": self.margin,
+            "kmeans_stable_splits": self.kmeans_stable_splits,
+            "kmeans_runner_up": self.kmeans_runner_up,
         }
 
 

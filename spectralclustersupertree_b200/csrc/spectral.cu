@@ -456,7 +456,8 @@ true_residual(int m, const double *__restrict__ y, const double *__restrict__ Ny
 // u = y .* isd is the Fiedler coordinate sklearn clusters (_spectral_embedding.py:378-381); its sign is
 // fixed so that the entry of largest magnitude is positive (extmath.py:1283-1286).  The 2-means optimum
 // in one dimension is a threshold on the sorted values: sort, prefix sums, best split.
-// result: [0] margin, [1] lower centroid, [2] upper centroid, [3] size of the upper part
+// result: [0] margin, [1] lower centroid, [2] upper centroid, [3] size of the upper part,
+//         [4] number of Lloyd-stable splits, [5] best other stable split's score / the optimum's
 template <bool kShared>
 __global__ void __launch_bounds__(kOneCta)
 two_means_1d(int m, int P, const double *__restrict__ y, const double *__restrict__ isd, double *__restrict__ u,
@@ -573,6 +574,45 @@ two_means_1d(int m, int P, const double *__restrict__ y, const double *__restric
         for (int w = 1; w < (nthr >> 5); ++w)
             if (best_score[w] > bs || (best_score[w] == bs && best_index[w] < bi)) { bs = best_score[w]; bi = best_index[w]; }
         if (bi >= m) bi = 1;  // degenerate (m == 1 never reaches here)
+        ibcast = bi;
+        bcast[1] = bs;
+    }
+    __syncthreads();
+    // Lloyd-stable splits (both neighbours of the cut on their own side of the centroid midpoint):
+    // k-means as a local search can stop at any of them, so more than one means the reference's
+    // answer depends on its random initialisation.  Count them and score the best runner-up.
+    {
+        const int chosen = ibcast;
+        double p2 = before + incl - local;
+        double stable = 0.0, runner = -1.0;
+        for (int i = lo; i < hi; ++i) {
+            const double key = kShared ? keys[i] : __ldcg(keys + i);
+            p2 += key - mean;
+            const int cnt = i + 1;
+            if (cnt < m) {
+                const double rest = all - p2;
+                const double mid = mean + 0.5 * (p2 / cnt + rest / (m - cnt));
+                const double next = kShared ? keys[i + 1] : __ldcg(keys + i + 1);
+                if (key < mid && mid < next) {
+                    stable += 1.0;
+                    if (cnt != chosen) runner = fmax(runner, p2 * p2 / cnt + rest * rest / (m - cnt));
+                }
+            }
+        }
+        stable = block_sum(stable, scratch);
+        for (int off = 16; off > 0; off >>= 1) runner = fmax(runner, __shfl_down_sync(0xffffffffu, runner, off));
+        __syncthreads();
+        if ((tid & 31) == 0) best_score[tid >> 5] = runner;
+        __syncthreads();
+        if (tid == 0) {
+            double r = best_score[0];
+            for (int w = 1; w < (nthr >> 5); ++w) r = fmax(r, best_score[w]);
+            result[4] = stable;
+            result[5] = (r >= 0.0 && bcast[1] > 0.0) ? r / bcast[1] : 0.0;
+        }
+    }
+    if (tid == 0) {
+        const int bi = ibcast;
         // centroids of the two parts
         double lower = 0.0;
         for (int i = 0; i < bi; ++i) lower += (kShared ? keys[i] : __ldcg(keys + i)) - mean;
@@ -794,20 +834,23 @@ int spectral_bipartition(scs_ctx *ctx, int m, const double *W, const double *deg
         two_means_1d<false><<<1, kOneCta, 0, ctx->stream>>>(m, P, yvec, b.isd, embed, sorted, side, b.ritz + 12);
     }
     SCS_LAUNCHED(ctx, "two_means_1d");
-    SCS_CUDA(ctx, cudaMemcpyAsync(pin + 12, b.ritz + 12, 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    SCS_CUDA(ctx, cudaMemcpyAsync(pin + 16, flags, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SCS_CUDA(ctx, cudaMemcpyAsync(pin + 12, b.ritz + 12, 6 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SCS_CUDA(ctx, cudaMemcpyAsync(pin + 20, flags, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     SCS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     stats->eig[0] = 0.0;
     stats->eig[1] = 1.0 - first.theta1;
     stats->eig[2] = 1.0 - theta_next;
     stats->residual = pin[8];
     stats->margin = pin[12];
-    const int32_t bad_degree = reinterpret_cast<const int32_t *>(pin + 16)[0];
+    const int32_t bad_degree = reinterpret_cast<const int32_t *>(pin + 20)[0];
+    stats->kmeans_stable_splits = static_cast<int32_t>(pin[16]);
+    stats->kmeans_runner_up = pin[17];
     stats->tie_flag = 0;
     if (!std::isnan(theta_next) && (first.theta1 - theta_next) < kGapTie) stats->tie_flag |= 1;
     if (!(stats->margin >= kMarginTie)) stats->tie_flag |= 2;
     if (!first.converged) stats->tie_flag |= 4;  // accepted at the restart limit: see stats->residual
     if (bad_degree) stats->tie_flag |= 8;        // negative / non-finite degree: sklearn's result is NaN-driven
+    if (stats->kmeans_stable_splits > 1) stats->tie_flag |= 16;  // k-means has several local optima
     return SCS_OK;
 }
 

@@ -131,6 +131,41 @@ def dense_from_reference(ref, trees, weights, weighting):
     return names, out
 
 
+def kmeans_report(spectral, vertices, edge_weights, vlist, u1, parts):
+    """How well-determined the reference's k-means step is at one spectral node."""
+    m = len(u1)
+    order = np.argsort(u1, kind="stable")
+    s = u1[order]
+    c = s - s.mean()
+    prefix = np.cumsum(c)[:-1]
+    cnt = np.arange(1, m)
+    score = prefix**2 / cnt + (c.sum() - prefix) ** 2 / (m - cnt)
+    best = int(np.argmax(score)) + 1
+    stable = []  # splits that Lloyd's iteration leaves unchanged
+    for i in range(1, m):
+        mid = 0.5 * (s[:i].mean() + s[i:].mean())
+        if s[i - 1] < mid < s[i]:
+            stable.append(i)
+    lower = {vlist[k] for k in order[:best]}
+    optimal = [sorted(x for v in vlist if (v in lower) == flag for x in v) for flag in (True, False)]
+    ref_part = [sorted(x for v in part for x in v) for part in parts]
+    is_optimal = {frozenset(p) for p in optimal} == {frozenset(p) for p in ref_part}
+    seeds_agree = True
+    for seed in (1, 2, 3):
+        again = spectral(set(vertices), dict(edge_weights), np.random.RandomState(seed))
+        again = {frozenset(x for v in part for x in v) for part in again}
+        if again != {frozenset(p) for p in ref_part}:
+            seeds_agree = False
+            break
+    out = {"stable_splits": len(stable), "reference_is_optimal": bool(is_optimal), "seed_stable": bool(seeds_agree)}
+    if len(stable) > 1:
+        top = sorted((float(score[i - 1]) for i in stable), reverse=True)
+        out["second_best_relative"] = top[1] / top[0] if top[0] > 0 else 1.0
+    if not is_optimal:
+        out["optimal_partition"] = optimal
+    return out
+
+
 def traced_run(ref, trees, weights, weighting, contract_edges=True):
     """The reference's construct_supertree with its module-level functions wrapped to record."""
     records = []
@@ -178,6 +213,9 @@ def traced_run(ref, trees, weights, weighting, contract_edges=True):
             if 0 < side.sum() < m:
                 mid = 0.5 * (u1[side == 0].mean() + u1[side == 1].mean())
                 rec["margin"] = float(np.abs(u1 - mid).min() / max(np.ptp(u1), 1e-300))
+            # k-means is a local search: is the reference's split the global 1-D 2-means optimum, is it
+            # the only Lloyd-stable split, and does it depend on the RNG seed?
+            rec["kmeans"] = kmeans_report(orig_spectral, vertices, edge_weights, vlist, u1, parts)
         return parts
 
     ref.spectral_cluster_graph = spectral
