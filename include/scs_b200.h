@@ -86,6 +86,10 @@ int scs_ctx_io_bytes(const scs_ctx *ctx, int64_t *h2d, int64_t *d2h);
 /* A CUDA-event stopwatch on the context's stream (stop waits for the stream to reach it). */
 int scs_ctx_timer_start(scs_ctx *ctx);
 int scs_ctx_timer_stop(scs_ctx *ctx, double *ms);
+/* Recursion nodes with at most `limit` vertices (default and maximum 64) run components, contraction
+ * and the spectral split in one single-CTA launch (dense Jacobi); larger ones take the staged path
+ * (union-find, max-merge, Lanczos).  0 sends every node down the staged path. */
+int scs_ctx_set_small_node_limit(scs_ctx *ctx, int limit);
 /* Evict the L2 cache by writing a 256 MB scratch buffer (benchmark hygiene between timed steps). */
 int scs_ctx_flush_l2(scs_ctx *ctx);
 /* Per-launch CUDA-event timing of the two heavy kernels on matrices of >= 2048 vertices:

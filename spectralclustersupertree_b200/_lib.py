@@ -75,6 +75,7 @@ SIGNATURES: dict[str, tuple] = {
     "scs_ctx_io_bytes": (c_int, [_P, POINTER(c_int64), POINTER(c_int64)]),
     "scs_ctx_timer_start": (c_int, [_P]),
     "scs_ctx_timer_stop": (c_int, [_P, POINTER(c_double)]),
+    "scs_ctx_set_small_node_limit": (c_int, [_P, c_int]),
     "scs_ctx_flush_l2": (c_int, [_P]),
     "scs_ctx_profile_enable": (c_int, [_P, c_int]),
     "scs_ctx_profile_read": (c_int, [_P, c_int, POINTER(c_int64), POINTER(c_double), POINTER(c_double), POINTER(c_double)]),

@@ -63,6 +63,7 @@ enum Slot : int {
     SLOT_SIDE,
     SLOT_SPEC_SCALARS,
     SLOT_L2_FLUSH,
+    SLOT_NODE_STATS,
     SLOT_COUNT
 };
 
@@ -92,6 +93,8 @@ struct scs_ctx {
     };
     std::vector<ProfileRecord> profile;
     int flush_value = 0;
+    bool small_configured = false;
+    int small_limit = 64;  // nodes up to this size take the one-CTA path (0 disables it)
     double pending_units = 0.0;  // leaf-pair visits of the node being built (set by host entry points)
     cudaEvent_t timer_start = nullptr, timer_stop = nullptr;
     // shape of the node most recently processed by scs_node_split_host
@@ -131,6 +134,7 @@ inline int reserve_as(scs_ctx *ctx, Slot slot, size_t count, T **out) {
 int reserve_pinned(scs_ctx *ctx, size_t bytes, void **out);
 
 enum ProfileKind : int { PROFILE_MATVEC = 0, PROFILE_PCG_ROWS = 1, PROFILE_KINDS = 2 };
+constexpr int kSmallNode = 64;  // recursion nodes up to this many vertices take the one-CTA path (small.cu)
 constexpr int kProfileMinSize = 2048;  // below this the matrices are L2-resident: no HBM roofline
 
 // Bracket the launch that follows / preceded with events when profiling is on.
@@ -141,6 +145,21 @@ inline int ceil_div(int64_t a, int64_t b) { return static_cast<int>((a + b - 1) 
 
 // out[i] = in[0] + ... + in[i-1] for i in [0, n]  (out has n + 1 entries)
 int exclusive_scan(scs_ctx *ctx, int n, const int32_t *in, int32_t *out);
+
+// monotone map double -> uint64 for max-reductions with integer atomics (0 is below every real
+// number: used for "no edge")
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned long long order_key(double x) {
+    const unsigned long long sign = 0x8000000000000000ull;
+    unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(x));
+    return (b & sign) ? ~b : (b | sign);
+}
+__device__ __forceinline__ double order_value(unsigned long long k) {
+    const unsigned long long sign = 0x8000000000000000ull;
+    unsigned long long b = (k & sign) ? (k & ~sign) : ~k;
+    return __longlong_as_double(static_cast<long long>(b));
+}
+#endif
 
 // ---- stage entry points implemented in the other translation units ------------------------
 int pcg_build(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offsets,
@@ -158,9 +177,17 @@ int spectral_bipartition(scs_ctx *ctx, int m, const double *W, const double *deg
 
 int normalized_matvec(scs_ctx *ctx, int m, const double *W, const double *isd, const double *x, double *y);
 
+// Components, contraction and the spectral split of a graph of <= kSmallNode vertices in one launch;
+// part / out_dev / group_out / Wc_out are device pointers (the last two may be null).
+int small_node(scs_ctx *ctx, int n, int contract_edges, const double *W, const uint32_t *adj_bits,
+               const uint32_t *max_bits, int32_t *part, scs_node_stats *out_dev, int32_t *group_out,
+               double *Wc_out);
+
+// One recursion node on device-resident tours.  part_dev[n] receives the component index or side;
+// if part_host is not null the result is also copied there before the function returns.
 int node_split(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offsets, const int32_t *leaf_taxon,
                const int32_t *adj_depth, const double *adj_val, const int32_t *root_depth,
                const double *tree_weight, int contract_edges, uint64_t seed, int32_t *part_dev,
-               scs_node_stats *stats);
+               int32_t *part_host, scs_node_stats *stats);
 
 }  // namespace scs

@@ -127,11 +127,11 @@ void clear_stats(scs_node_stats *s) {
 int node_split(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offsets, const int32_t *leaf_taxon,
                const int32_t *adj_depth, const double *adj_val, const int32_t *root_depth,
                const double *tree_weight, int contract_edges, uint64_t seed, int32_t *part_dev,
-               scs_node_stats *stats) {
+               int32_t *part_host, scs_node_stats *stats) {
     const int words = scs_bit_words(n);
     const size_t nn = static_cast<size_t>(n) * n;
     double *W, *Wc, *degree, *degree_c;
-    int32_t *occ, *label, *group, *side;
+    int32_t *occ, *label, *group, *side, *scalars;
     uint32_t *adj_bits, *max_bits;
     int rc;
     if ((rc = reserve_as(ctx, SLOT_W, nn, &W))) return rc;
@@ -140,24 +140,52 @@ int node_split(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offset
     if ((rc = reserve_as(ctx, SLOT_MAX_BITS, static_cast<size_t>(n) * words, &max_bits))) return rc;
     if ((rc = reserve_as(ctx, SLOT_DEGREE, static_cast<size_t>(n), &degree))) return rc;
     if ((rc = reserve_as(ctx, SLOT_LABEL, static_cast<size_t>(n), &label))) return rc;
+    if ((rc = reserve_as(ctx, SLOT_SCALARS, 64, &scalars))) return rc;
     ctx->last_n = n;
     ctx->last_m = 0;
+    void *pin_v;
+    if ((rc = reserve_pinned(ctx, 512, &pin_v))) return rc;
+    unsigned char *pin = static_cast<unsigned char *>(pin_v);
+    auto fetch_part = [&]() -> int {
+        if (part_host) {
+            SCS_CUDA(ctx, cudaMemcpyAsync(part_host, part_dev, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+            ctx->d2h_bytes += static_cast<int64_t>(sizeof(int32_t)) * n;
+        }
+        return SCS_OK;
+    };
 
     if ((rc = pcg_build(ctx, n, T, L, leaf_offsets, leaf_taxon, adj_depth, adj_val, root_depth, tree_weight, W,
                         nullptr, occ, adj_bits, contract_edges ? max_bits : nullptr, degree)))
         return rc;
+
+    if (n <= ctx->small_limit) {
+        // everything after the graph build in one launch; one round trip for the whole node
+        scs_node_stats *stats_dev;
+        if ((rc = reserve_as(ctx, SLOT_NODE_STATS, 1, &stats_dev))) return rc;
+        if ((rc = reserve_as(ctx, SLOT_WC, nn, &Wc))) return rc;
+        if ((rc = reserve_as(ctx, SLOT_GROUP, static_cast<size_t>(n), &group))) return rc;
+        if ((rc = small_node(ctx, n, contract_edges, W, adj_bits, max_bits, part_dev, stats_dev, group, Wc))) return rc;
+        SCS_CUDA(ctx, cudaMemcpyAsync(pin, stats_dev, sizeof(scs_node_stats), cudaMemcpyDeviceToHost, ctx->stream));
+        SCS_CUDA(ctx, cudaMemcpyAsync(pin + 256, scalars, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        if ((rc = fetch_part())) return rc;
+        SCS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (*reinterpret_cast<int32_t *>(pin + 256) != 0)
+            return fail(ctx, SCS_ERR_INPUT, "leaf tour: taxon id out of range");
+        std::memcpy(stats, pin, sizeof(scs_node_stats));
+        ctx->last_m = stats->contracted_size;
+        if (stats->solver == -1) {
+            stats->solver = 0;
+            return fail(ctx, SCS_ERR_TOO_SMALL, "spectral step on a graph contracted to one vertex");
+        }
+        return SCS_OK;
+    }
+
     // malformed tours are flagged by the index kernel (scalars[0]); read together with the count
     int ncomp = 0;
     if ((rc = components(ctx, n, adj_bits, label, &ncomp))) return rc;
-    {
-        int32_t *scalars;
-        if ((rc = reserve_as(ctx, SLOT_SCALARS, 64, &scalars))) return rc;
-        void *pin;
-        if ((rc = reserve_pinned(ctx, 64, &pin))) return rc;
-        SCS_CUDA(ctx, cudaMemcpyAsync(pin, scalars, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-        SCS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        if (*static_cast<int32_t *>(pin) != 0) return fail(ctx, SCS_ERR_INPUT, "leaf tour: taxon id out of range");
-    }
+    SCS_CUDA(ctx, cudaMemcpyAsync(pin + 256, scalars, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SCS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (*reinterpret_cast<int32_t *>(pin + 256) != 0) return fail(ctx, SCS_ERR_INPUT, "leaf tour: taxon id out of range");
     stats->n_components = ncomp;
     stats->contracted_size = n;
     const int blocks = ceil_div(n, 256);
@@ -172,6 +200,8 @@ int node_split(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offset
         if ((rc = exclusive_scan(ctx, n, flag, rank))) return rc;
         relabel_components<<<blocks, 256, 0, ctx->stream>>>(n, label, rank, part_dev);
         SCS_LAUNCHED(ctx, "relabel_components");
+        if ((rc = fetch_part())) return rc;
+        if (part_host) SCS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         return SCS_OK;
     }
 
@@ -202,6 +232,8 @@ int node_split(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offset
     if ((rc = spectral_bipartition(ctx, m, Wm, deg_m, seed, side, stats))) return rc;
     expand_sides<<<blocks, 256, 0, ctx->stream>>>(n, group_m, side, part_dev);
     SCS_LAUNCHED(ctx, "expand_sides");
+    if ((rc = fetch_part())) return rc;
+    if (part_host) SCS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return SCS_OK;
 }
 
@@ -319,6 +351,12 @@ int scs_ctx_timer_stop(scs_ctx *ctx, double *ms) {
     return SCS_OK;
 }
 
+int scs_ctx_set_small_node_limit(scs_ctx *ctx, int limit) {
+    if (!ctx || limit < 0) return SCS_ERR_INVALID;
+    ctx->small_limit = limit > kSmallNode ? kSmallNode : limit;
+    return SCS_OK;
+}
+
 int scs_ctx_flush_l2(scs_ctx *ctx) {
     if (!ctx) return SCS_ERR_INVALID;
     DeviceGuard guard(ctx->device);
@@ -425,7 +463,7 @@ int scs_node_split_dev(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *lea
     scs_node_stats *stats = stats_host ? stats_host : &local;
     clear_stats(stats);
     return node_split(ctx, n, T, L, leaf_offsets_dev, leaf_taxon_dev, adj_depth_dev, adj_val_dev, root_depth_dev,
-                      tree_weight_dev, contract_edges, seed, part_dev, stats);
+                      tree_weight_dev, contract_edges, seed, part_dev, nullptr, stats);
 }
 
 int scs_node_split_host(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offsets,
@@ -496,13 +534,9 @@ int scs_node_split_host(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *le
                     reinterpret_cast<const int32_t *>(dev_stage + o_dep),
                     reinterpret_cast<const double *>(dev_stage + o_val),
                     reinterpret_cast<const int32_t *>(dev_stage + o_root),
-                    reinterpret_cast<const double *>(dev_stage + o_w), contract_edges, seed, part_dev, stats);
-    if (rc) return rc;
-    SCS_CUDA(ctx, cudaMemcpyAsync(part, part_dev, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
-    SCS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->d2h_bytes += static_cast<int64_t>(sizeof(int32_t)) * n;
+                    reinterpret_cast<const double *>(dev_stage + o_w), contract_edges, seed, part_dev, part, stats);
     ctx->pending_units = 0.0;
-    return SCS_OK;
+    return rc;
 }
 
 int scs_node_last_buffers(scs_ctx *ctx, int *n, int *m, double **W_dev, uint32_t **adj_bits_dev,

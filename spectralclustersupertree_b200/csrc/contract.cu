@@ -15,18 +15,6 @@ namespace scs {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr unsigned long long kSign = 0x8000000000000000ull;
-
-// monotone map double -> uint64 (0 is below every real number: used for "no edge")
-__device__ __forceinline__ unsigned long long order_key(double x) {
-    unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(x));
-    return (b & kSign) ? ~b : (b | kSign);
-}
-__device__ __forceinline__ double order_value(unsigned long long k) {
-    unsigned long long b = (k & kSign) ? (k & ~kSign) : ~k;
-    return __longlong_as_double(static_cast<long long>(b));
-}
-
 __global__ void mark_representatives(int n, const int32_t *__restrict__ label, int32_t *__restrict__ is_rep) {
     int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v < n) is_rep[v] = label[v] == v;

@@ -96,6 +96,10 @@ class Engine:
         _check(self._lib.scs_ctx_timer_stop(self._ctx, ctypes.byref(ms)), self._ctx)
         return ms.value
 
+    def set_small_node_limit(self, limit: int) -> None:
+        """Largest recursion node (vertices) that takes the one-CTA path; 0 forces the staged path."""
+        _check(self._lib.scs_ctx_set_small_node_limit(self._ctx, limit), self._ctx)
+
     def flush_l2(self) -> None:
         _check(self._lib.scs_ctx_flush_l2(self._ctx), self._ctx)
 

@@ -107,3 +107,38 @@ def test_load_trees_and_cli(engine, tmp_path, monkeypatch):
     assert rf(make_tree(out_file.read_text().strip()), make_tree(fixture["expected"])) == 0
     assert runner.invoke(scs, []).exit_code in (0, 2)  # no_args_is_help
     assert "version" in runner.invoke(scs, ["--version"]).output.lower()
+
+
+@pytest.mark.parametrize("name", ["supertriplets", "s_300x40_branch_weighted", "s_200x40_bootstrap"])
+def test_small_node_path_agrees_with_staged_path(engine, name):
+    """The one-CTA path (dense Jacobi) and the staged path (union-find, max-merge, Lanczos) must give
+    the same components, contraction sizes, eigenvalues and partitions on every recursion node."""
+    case = load_case(name)
+    fused: list = []
+    staged: list = []
+    construct_supertree(parse(case["lines"]), case["weights"], case["weighting"], engine=engine, trace=fused)
+    engine.set_small_node_limit(0)
+    try:
+        construct_supertree(parse(case["lines"]), case["weights"], case["weighting"], engine=engine, trace=staged)
+    finally:
+        engine.set_small_node_limit(64)
+    by_names = {tuple(r["names"]): r for r in staged}
+    small_nodes = 0
+    for rec in fused:
+        other = by_names.get(tuple(rec["names"]))
+        if other is None:
+            continue  # below a tie where the two solvers may legitimately differ
+        assert rec["n_components"] == other["n_components"]
+        if "partition" not in rec:
+            continue
+        assert rec["contracted_size"] == other["contracted_size"]
+        a, b = rec["stats"], other["stats"]
+        if rec["contracted_size"] >= 3:
+            small_nodes += a["solver"] == 2
+            assert abs(a["eig"][1] - b["eig"][1]) < 1e-9
+            assert a["residual"] < 1e-10
+        tie = (a["tie_flag"] | b["tie_flag"]) & 3
+        if not tie:
+            assert {frozenset(p) for p in rec["partition"]} == {frozenset(p) for p in other["partition"]}
+            assert a["kmeans_stable_splits"] == b["kmeans_stable_splits"]
+    assert small_nodes >= 10
