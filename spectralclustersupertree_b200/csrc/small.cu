@@ -238,6 +238,7 @@ small_node_kernel(int n, int words, int contract_edges, const double *__restrict
     // ---- parallel cyclic Jacobi ------------------------------------------------------------------
     const int me = (m + 1) & ~1;  // even number of players; the extra one is a bye
     const int half = me >> 1;
+    if (tid == 0) S.ired[1] = 0;  // sweeps done
     for (int sweep = 0; sweep < 30; ++sweep) {
         double off = 0.0, diag = 0.0;
         for (int e = tid; e < m * m; e += kThreads) {
@@ -247,7 +248,10 @@ small_node_kernel(int n, int words, int contract_edges, const double *__restrict
         }
         off = block_sum_small(off, S.red);
         diag = block_sum_small(diag, S.red);
-        if (off <= 1e-30 * (diag + off) || off < 1e-300) break;
+        // off-diagonal Frobenius norm below 1e-14 of the whole: eigenvalues are then converged to
+        // rounding (their error is quadratic in it) and eigenvectors to ~1e-14 / gap
+        if (off <= 1e-28 * (diag + off) || off < 1e-300) break;
+        if (tid == 0) S.ired[1] = sweep + 1;
         for (int step = 0; step < me - 1; ++step) {
             if (tid < half) {
                 int p, q;
@@ -376,6 +380,7 @@ small_node_kernel(int n, int words, int contract_edges, const double *__restrict
         const double margin = fmin(fabs(S.sorted[bi - 1] - mid), fabs(S.sorted[bi] - mid)) / range;
         S.red[3] = S.sorted[bi];
         out->solver = 2;
+        out->matvecs = S.ired[1];  // Jacobi sweeps (the dense solver applies no matvec)
         out->eig[1] = 1.0 - theta1;
         out->eig[2] = 1.0 - theta2;
         out->margin = margin;
