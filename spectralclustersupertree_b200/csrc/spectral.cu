@@ -334,15 +334,18 @@ tridiag_ritz(int jrun, const double *__restrict__ alpha, const double *__restric
             const double x = lo + step * (tid + 1);
             counts[tid] = sturm_count(a, b2, j, x, pivmin);
             __syncthreads();
-            // first probe with count >= k bounds the eigenvalue from above
-            if (tid == 0) {
-                int first = P;
-                for (int p = 0; p < P; ++p)
-                    if (counts[p] >= k) { first = p; break; }
-                const double nlo = first == 0 ? lo : lo + step * first;
-                const double nhi = first == P ? hi : lo + step * (first + 1);
-                bounds[0] = nlo;
-                bounds[1] = nhi;
+            // the first probe with count >= k bounds the eigenvalue from above; counts are monotone,
+            // so exactly one thread sees the step (or the last thread sees none)
+            {
+                const bool here = counts[tid] >= k;
+                const bool before = tid > 0 && counts[tid - 1] >= k;
+                if (here && !before) {
+                    bounds[0] = tid == 0 ? lo : lo + step * tid;
+                    bounds[1] = lo + step * (tid + 1);
+                } else if (tid == P - 1 && !here) {
+                    bounds[0] = lo + step * P;
+                    bounds[1] = hi;
+                }
             }
             __syncthreads();
             lo = bounds[0];
