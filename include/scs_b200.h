@@ -44,7 +44,9 @@ typedef enum {
     SCS_ERR_TOO_SMALL = -4,   /* fewer than 2 vertices handed to the spectral step
                                  (sklearn raises ValueError there, _spectral.py:699) */
     SCS_ERR_NO_CONVERGE = -5, /* eigensolver hit its restart limit */
-    SCS_ERR_INPUT = -6        /* malformed leaf tour (taxon id out of range, ...) */
+    SCS_ERR_INPUT = -6,       /* malformed leaf tour (taxon id out of range, ...) */
+    SCS_ERR_EMPTY = -7        /* a recursion node was left without source trees (the reference raises
+                                 ValueError "There must be at least one tree ...", scs.py:63-65) */
 } scs_status;
 
 /* What happened at one recursion node (the "near-ties reported" clause of the parity contract). */
@@ -215,6 +217,44 @@ int scs_forest_tours(const scs_forest *f, int weighting, const int32_t *local_id
  * increasing global id.  taxa_out / part_out must hold num_taxa entries; *n_out receives n. */
 int scs_forest_split(scs_ctx *ctx, const scs_forest *f, int weighting, int contract_edges, uint64_t seed,
                      int32_t *n_out, int32_t *taxa_out, int32_t *part_out, scs_node_stats *stats);
+
+/* ---- many small recursion nodes in one launch --------------------------------------------- *
+ * Nodes with at most 64 vertices, one CTA each: graph build, components, contraction and spectral
+ * split (scs.py:108-134 for every node of the batch).  The nodes' tours are concatenated:
+ * node b owns leaves [leaf_base, leaf_base + its leaf count), trees [tree_base, tree_base + num_trees)
+ * of root_depth / tree_weight, offsets leaf_offsets[tree_base + b .. tree_base + b + num_trees]
+ * (relative to leaf_base, starting at 0) and vertices [vertex_base, vertex_base + n) of part. */
+typedef struct {
+    int32_t n;
+    int32_t num_trees;
+    int64_t leaf_base;
+    int64_t tree_base;
+    int64_t vertex_base;
+} scs_small_node;
+int scs_nodes_split_small_host(scs_ctx *ctx, int num_nodes, const scs_small_node *nodes, int64_t L_total,
+                               int64_t T_total, const int64_t *leaf_offsets, const int32_t *leaf_taxon,
+                               const int32_t *adj_depth, const double *adj_val, const int32_t *root_depth,
+                               const double *tree_weight, int contract_edges, int32_t *part,
+                               scs_node_stats *stats);
+
+/* ---- the whole recursion (scs.py:96-174) as a native work-list ------------------------------- *
+ * Breadth-first over the independent sub-problems: every frontier node with <= 64 taxa goes to the
+ * GPU in one batched launch, larger ones through scs_node_split_host.  The result is the supertree
+ * as flat arrays: parent[i] < i (-1 for the root), taxon[i] = global taxon id for tips, -1 for
+ * internal nodes; children are in index order.  With record_nodes != 0 every recursion node that
+ * reached the GPU is kept (vertices, part, stats) for node-by-node parity checks. */
+typedef struct scs_supertree scs_supertree;
+int scs_supertree_build(scs_ctx *ctx, const scs_forest *forest, int weighting, int contract_edges,
+                        uint64_t seed, int record_nodes, scs_supertree **out);
+int scs_supertree_destroy(scs_supertree *tree);
+int64_t scs_supertree_num_nodes(const scs_supertree *tree);
+int scs_supertree_nodes(const scs_supertree *tree, int32_t *parent, int32_t *taxon);
+int scs_supertree_counters(const scs_supertree *tree, int64_t *nodes_small, int64_t *nodes_large,
+                           int64_t *waves, int64_t *pair_visits);
+int64_t scs_supertree_num_records(const scs_supertree *tree);
+int scs_supertree_record_size(const scs_supertree *tree, int64_t index);
+int scs_supertree_record(const scs_supertree *tree, int64_t index, int32_t *taxa, int32_t *part,
+                         scs_node_stats *stats);
 
 #ifdef __cplusplus
 }

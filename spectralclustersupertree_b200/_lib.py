@@ -20,6 +20,7 @@ SCS_ERR_NO_DEVICE = -3
 SCS_ERR_TOO_SMALL = -4
 SCS_ERR_NO_CONVERGE = -5
 SCS_ERR_INPUT = -6
+SCS_ERR_EMPTY = -7
 
 
 class NodeStats(ctypes.Structure):
@@ -114,6 +115,18 @@ SIGNATURES: dict[str, tuple] = {
         c_int,
         [_P, _P, c_int, c_int, c_uint64, POINTER(c_int32), _P, _P, POINTER(NodeStats)],
     ),
+    "scs_nodes_split_small_host": (
+        c_int,
+        [_P, c_int, _P, c_int64, c_int64, _P, _P, _P, _P, _P, _P, c_int, _P, _P],
+    ),
+    "scs_supertree_build": (c_int, [_P, _P, c_int, c_int, c_uint64, c_int, POINTER(_P)]),
+    "scs_supertree_destroy": (c_int, [_P]),
+    "scs_supertree_num_nodes": (c_int64, [_P]),
+    "scs_supertree_nodes": (c_int, [_P, _P, _P]),
+    "scs_supertree_counters": (c_int, [_P, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)]),
+    "scs_supertree_num_records": (c_int64, [_P]),
+    "scs_supertree_record_size": (c_int, [_P, c_int64]),
+    "scs_supertree_record": (c_int, [_P, c_int64, _P, _P, POINTER(NodeStats)]),
 }
 
 _LIB: ctypes.CDLL | None = None

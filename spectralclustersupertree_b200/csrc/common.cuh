@@ -94,6 +94,7 @@ struct scs_ctx {
     std::vector<ProfileRecord> profile;
     int flush_value = 0;
     bool small_configured = false;
+    bool batch_configured = false;
     int small_limit = 64;  // nodes up to this size take the one-CTA path (0 disables it)
     double pending_units = 0.0;  // leaf-pair visits of the node being built (set by host entry points)
     cudaEvent_t timer_start = nullptr, timer_stop = nullptr;
@@ -182,6 +183,12 @@ int normalized_matvec(scs_ctx *ctx, int m, const double *W, const double *isd, c
 int small_node(scs_ctx *ctx, int n, int contract_edges, const double *W, const uint32_t *adj_bits,
                const uint32_t *max_bits, int32_t *part, scs_node_stats *out_dev, int32_t *group_out,
                double *Wc_out);
+
+// A batch of small nodes, one CTA each, graph build included; all pointers are device pointers.
+int small_batch(scs_ctx *ctx, int num_nodes, const scs_small_node *nodes_dev, const int64_t *leaf_offsets,
+                const int32_t *leaf_taxon, const int32_t *adj_depth, const double *adj_val, const int32_t *root_depth,
+                const double *tree_weight, int contract_edges, int32_t *part_dev, scs_node_stats *stats_dev,
+                int32_t *bad_dev);
 
 // One recursion node on device-resident tours.  part_dev[n] receives the component index or side;
 // if part_host is not null the result is also copied there before the function returns.

@@ -254,6 +254,7 @@ const char *scs_status_string(int status) {
     case SCS_ERR_TOO_SMALL: return "fewer than two vertices in the spectral step";
     case SCS_ERR_NO_CONVERGE: return "eigensolver did not converge";
     case SCS_ERR_INPUT: return "malformed input";
+    case SCS_ERR_EMPTY: return "there must be at least one tree to make a supertree";
     default: return "unknown status";
     }
 }

@@ -29,6 +29,11 @@ constexpr double kMarginTie = 1e-9;
 struct SmallShared {
     double A[kN][kN + 1];   // W, then Wc, then M (padded: column sweeps hit distinct banks)
     double V[kN][kN + 1];   // Jacobi eigenvectors
+    double B[kN][kN + 1];   // the (contracted) weights the split was computed from: residual check
+    unsigned short cnt[kN][kN];  // co-occurrence counts (batched path: graph built in shared memory)
+    int occ[kN];
+    int tour_taxon[kN], tour_depth[kN];
+    double tour_val[kN];
     double cs[kN / 2][2];
     double deg[kN], isd[kN], q0[kN], u[kN], sorted[kN];
     unsigned long long adj[kN], mx[kN], reach[kN];
@@ -76,29 +81,14 @@ __device__ void closure(int n, const unsigned long long *rows, unsigned long lon
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(kThreads)
-small_node_kernel(int n, int words, int contract_edges, const double *__restrict__ W,
-                  const uint32_t *__restrict__ adj_bits, const uint32_t *__restrict__ max_bits,
-                  int32_t *__restrict__ part, scs_node_stats *__restrict__ out,
-                  int32_t *__restrict__ group_out, double *__restrict__ Wc_out) {
-    extern __shared__ __align__(16) unsigned char raw[];
-    SmallShared &S = *reinterpret_cast<SmallShared *>(raw);
+// Everything after the graph build for one node whose weights are in S.A (n x n) and whose adjacency /
+// max-graph rows are in S.adj / S.mx.  part, out, group_out, Wc_out are global pointers (the last two
+// may be null).
+__device__ void small_finish(SmallShared &S, int n, int contract_edges, int32_t *__restrict__ part,
+                             scs_node_stats *__restrict__ out, int32_t *__restrict__ group_out,
+                             double *__restrict__ Wc_out) {
     const int tid = threadIdx.x;
     const double nan_v = __longlong_as_double(0x7ff8000000000000ll);
-
-    // ---- load --------------------------------------------------------------------------------
-    for (int e = tid; e < n * n; e += kThreads) S.A[e / n][e % n] = W[e];
-    if (tid < n) {
-        unsigned long long a = adj_bits[static_cast<size_t>(tid) * words];
-        unsigned long long m = max_bits ? max_bits[static_cast<size_t>(tid) * words] : 0ull;
-        if (words > 1) {
-            a |= static_cast<unsigned long long>(adj_bits[static_cast<size_t>(tid) * words + 1]) << 32;
-            if (max_bits) m |= static_cast<unsigned long long>(max_bits[static_cast<size_t>(tid) * words + 1]) << 32;
-        }
-        S.adj[tid] = a;
-        S.mx[tid] = m;
-    }
-    __syncthreads();
 
     // ---- components (scs.py:458-492) -----------------------------------------------------------
     closure(n, S.adj, S.reach, S.label);
@@ -196,6 +186,7 @@ small_node_kernel(int n, int words, int contract_edges, const double *__restrict
         return;
     }
 
+    for (int e = tid; e < m * m; e += kThreads) S.B[e / m][e % m] = S.A[e / m][e % m];
     // ---- normalised affinity, trivial pair shifted away ------------------------------------------
     if (tid < m) {
         double d = 0.0;
@@ -399,17 +390,12 @@ small_node_kernel(int n, int words, int contract_edges, const double *__restrict
     __syncthreads();
     if (tid < n) part[tid] = S.side[S.group[tid]];
 
-    // residual of the accepted pair against the operator it was computed from: |N y - theta y| with
-    // N rebuilt from the weights kept in global memory (contracted weights are in Wc_out / W)
+    // residual of the accepted pair against the operator it was computed from: |N y - theta y|
     if (tid < m) {
-        const double *Wsrc = (m != n && Wc_out) ? Wc_out : W;
-        const int ld = (m != n && Wc_out) ? m : n;
         double acc = 0.0;
-        if (m == n || Wc_out) {
-            for (int j = 0; j < m; ++j)
-                if (j != tid) acc += S.isd[tid] * Wsrc[static_cast<size_t>(tid) * ld + j] * S.isd[j] * S.V[j][col];
-            acc -= theta1 * S.V[tid][col];
-        }
+        for (int j = 0; j < m; ++j)
+            if (j != tid) acc += S.isd[tid] * S.B[tid][j] * S.isd[j] * S.V[j][col];
+        acc -= theta1 * S.V[tid][col];
         S.deg[tid] = acc * acc;
     }
     __syncthreads();
@@ -418,6 +404,109 @@ small_node_kernel(int n, int words, int contract_edges, const double *__restrict
         for (int i = 0; i < m; ++i) rr += S.deg[i];
         out->residual = sqrt(rr);
     }
+}
+
+// ---- per-node entry: graph already built in global memory (csrc/pcg.cu) ------------------------------
+__global__ void __launch_bounds__(kThreads)
+small_node_kernel(int n, int words, int contract_edges, const double *__restrict__ W,
+                  const uint32_t *__restrict__ adj_bits, const uint32_t *__restrict__ max_bits,
+                  int32_t *__restrict__ part, scs_node_stats *__restrict__ out,
+                  int32_t *__restrict__ group_out, double *__restrict__ Wc_out) {
+    extern __shared__ __align__(16) unsigned char raw[];
+    SmallShared &S = *reinterpret_cast<SmallShared *>(raw);
+    const int tid = threadIdx.x;
+    for (int e = tid; e < n * n; e += kThreads) S.A[e / n][e % n] = W[e];
+    if (tid < n) {
+        unsigned long long a = adj_bits[static_cast<size_t>(tid) * words];
+        unsigned long long m = max_bits ? max_bits[static_cast<size_t>(tid) * words] : 0ull;
+        if (words > 1) {
+            a |= static_cast<unsigned long long>(adj_bits[static_cast<size_t>(tid) * words + 1]) << 32;
+            if (max_bits) m |= static_cast<unsigned long long>(max_bits[static_cast<size_t>(tid) * words + 1]) << 32;
+        }
+        S.adj[tid] = a;
+        S.mx[tid] = m;
+    }
+    __syncthreads();
+    small_finish(S, n, contract_edges, part, out, group_out, Wc_out);
+}
+
+// ---- batched entry: one CTA per node builds the node's graph from its leaf tours in shared memory
+//      (the reference's _proper_cluster_graph_edges, scs.py:495-663) and finishes it ------------------
+// Trees are taken in input order with a barrier between them; inside a tree thread i owns the pairs
+// (i, j > i) and walks j upwards with a running minimum of the consecutive-leaf LCA depths, so every
+// W entry receives its terms in tree order with separately rounded multiply and add -- the same sums,
+// bit for bit, as pcg_rows_kernel and the reference.
+__global__ void __launch_bounds__(kThreads)
+small_batch_kernel(const scs_small_node *__restrict__ nodes, const int64_t *__restrict__ leaf_offsets,
+                   const int32_t *__restrict__ leaf_taxon, const int32_t *__restrict__ adj_depth,
+                   const double *__restrict__ adj_val, const int32_t *__restrict__ root_depth,
+                   const double *__restrict__ tree_weight, int contract_edges, int32_t *__restrict__ part,
+                   scs_node_stats *__restrict__ stats, int32_t *__restrict__ bad) {
+    extern __shared__ __align__(16) unsigned char raw[];
+    SmallShared &S = *reinterpret_cast<SmallShared *>(raw);
+    const int tid = threadIdx.x;
+    const scs_small_node node = nodes[blockIdx.x];
+    const int n = node.n;
+    for (int e = tid; e < n * n; e += kThreads) {
+        S.A[e / n][e % n] = 0.0;
+        S.cnt[e / n][e % n] = 0;
+    }
+    if (tid < n) S.occ[tid] = 0;
+    __syncthreads();
+    const int64_t *offs = leaf_offsets + node.tree_base + blockIdx.x;  // T + 1 offsets per node
+    for (int t = 0; t < node.num_trees; ++t) {
+        const int64_t tb = node.leaf_base + offs[t];
+        const int k = static_cast<int>(offs[t + 1] - offs[t]);
+        const double w = tree_weight[node.tree_base + t];
+        const int rd = root_depth[node.tree_base + t];
+        if (k > n) {  // more leaves than vertices: malformed input
+            if (tid == 0) *bad = 1;
+            continue;
+        }
+        if (tid < k) {
+            const int a = leaf_taxon[tb + tid];
+            S.tour_taxon[tid] = a;
+            S.tour_depth[tid] = adj_depth[tb + tid];
+            S.tour_val[tid] = adj_val[tb + tid];
+            if (a < 0 || a >= n) *bad = 1;
+        }
+        __syncthreads();
+        if (tid < k) {
+            const int a = S.tour_taxon[tid];
+            if (a >= 0 && a < n) {
+                S.occ[a] += 1;
+                int best_depth = 0x7fffffff, best_idx = tid;
+                for (int j = tid + 1; j < k; ++j) {
+                    const int d = S.tour_depth[j - 1];
+                    if (d < best_depth) { best_depth = d; best_idx = j - 1; }  // leftmost shallowest entry
+                    if (best_depth == rd) break;  // the root separates everything further right too
+                    const int b = S.tour_taxon[j];
+                    if (b < 0 || b >= n) continue;
+                    const double term = __dmul_rn(S.tour_val[best_idx], w);
+                    S.A[a][b] = __dadd_rn(S.A[a][b], term);
+                    S.A[b][a] = __dadd_rn(S.A[b][a], term);
+                    S.cnt[a][b] += 1;
+                    S.cnt[b][a] += 1;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (tid < n) {
+        unsigned long long a = 0, m = 0;
+        const int occ_a = S.occ[tid];
+        for (int b = 0; b < n; ++b) {
+            const int c = S.cnt[tid][b];
+            if (c > 0) {
+                a |= 1ull << b;
+                if (c == max(occ_a, S.occ[b])) m |= 1ull << b;
+            }
+        }
+        S.adj[tid] = a;
+        S.mx[tid] = contract_edges ? m : 0ull;
+    }
+    __syncthreads();
+    small_finish(S, n, contract_edges, part + node.vertex_base, stats + blockIdx.x, nullptr, nullptr);
 }
 
 }  // namespace
@@ -436,6 +525,24 @@ int small_node(scs_ctx *ctx, int n, int contract_edges, const double *W, const u
                                                          contract_edges ? max_bits : nullptr, part, out_dev, group_out,
                                                          Wc_out);
     SCS_LAUNCHED(ctx, "small_node_kernel");
+    return SCS_OK;
+}
+
+int small_batch(scs_ctx *ctx, int num_nodes, const scs_small_node *nodes_dev, const int64_t *leaf_offsets,
+                const int32_t *leaf_taxon, const int32_t *adj_depth, const double *adj_val, const int32_t *root_depth,
+                const double *tree_weight, int contract_edges, int32_t *part_dev, scs_node_stats *stats_dev,
+                int32_t *bad_dev) {
+    if (num_nodes <= 0) return SCS_OK;
+    const size_t smem = sizeof(SmallShared);
+    if (!ctx->batch_configured) {
+        SCS_CUDA(ctx, cudaFuncSetAttribute(small_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(smem)));
+        ctx->batch_configured = true;
+    }
+    small_batch_kernel<<<num_nodes, kThreads, smem, ctx->stream>>>(nodes_dev, leaf_offsets, leaf_taxon, adj_depth,
+                                                                  adj_val, root_depth, tree_weight, contract_edges,
+                                                                  part_dev, stats_dev, bad_dev);
+    SCS_LAUNCHED(ctx, "small_batch_kernel");
     return SCS_OK;
 }
 

@@ -169,6 +169,46 @@ class Engine:
         _check(status, self._ctx)
         return taxa[: n.value].copy(), part[: n.value].copy(), stats
 
+    # -- the whole recursion, natively (csrc/driver.cu) --------------------------------------------
+    def supertree_build(self, forest: "Forest", weighting: str, contract_edges: bool = True, seed: int = 0,
+                        record: bool = False) -> dict:
+        """``scs_supertree_build``: the supertree as flat arrays (``parent[i] < i``, ``taxon`` = global
+        taxon id for tips, -1 otherwise), the driver's counters and, if ``record``, one
+        ``(taxa, part, stats)`` per recursion node that reached the GPU."""
+        handle = ctypes.c_void_p()
+        status = self._lib.scs_supertree_build(
+            self._ctx, forest.handle, WEIGHTINGS.index(weighting), int(bool(contract_edges)),
+            seed & 0xFFFFFFFFFFFFFFFF, int(bool(record)), ctypes.byref(handle),
+        )  # fmt: skip
+        if status == _lib.SCS_ERR_INPUT and weighting == "bootstrap":
+            msg = "unsupported operand type(s) for *: 'NoneType' and 'float'"
+            raise TypeError(msg)
+        if status == _lib.SCS_ERR_EMPTY:  # ref: scs.py:63-65, reached through the recursion
+            msg = "There must be at least one tree to make a supertree."
+            raise ValueError(msg)
+        _check(status, self._ctx)
+        try:
+            count = self._lib.scs_supertree_num_nodes(handle)
+            parent = np.empty(count, dtype=np.int32)
+            taxon = np.empty(count, dtype=np.int32)
+            _check(self._lib.scs_supertree_nodes(handle, ptr(parent), ptr(taxon)), self._ctx)
+            small, large, waves, pairs = (ctypes.c_int64(0) for _ in range(4))
+            self._lib.scs_supertree_counters(handle, ctypes.byref(small), ctypes.byref(large), ctypes.byref(waves),
+                                             ctypes.byref(pairs))  # fmt: skip
+            out = {"parent": parent, "taxon": taxon, "nodes_small": small.value, "nodes_large": large.value,
+                   "waves": waves.value, "pair_visits": pairs.value, "records": []}  # fmt: skip
+            if record:
+                for i in range(self._lib.scs_supertree_num_records(handle)):
+                    n = self._lib.scs_supertree_record_size(handle, i)
+                    taxa = np.empty(n, dtype=np.int32)
+                    part = np.empty(n, dtype=np.int32)
+                    stats = NodeStats()
+                    self._lib.scs_supertree_record(handle, i, ptr(taxa), ptr(part), ctypes.byref(stats))
+                    out["records"].append((taxa, part, stats))
+            return out
+        finally:
+            self._lib.scs_supertree_destroy(handle)
+
     # -- single stages on explicit device buffers (parity tests, profiling, bench) ---------------
     def upload_tours(self, tours) -> dict:
         """Device copies of a ``LeafTours`` (free with ``free_tours``)."""

@@ -99,17 +99,35 @@ def supertree_of_forest(
     engine: Engine | None = None,
     trace: list | None = None,
     node_hook=None,
+    native: bool | None = None,
 ) -> PhyloNode:
     """The recursion of ``construct_supertree`` (ref: scs.py:96-174) on a flat ``Forest``.
 
+    By default the recursion itself runs natively (``csrc/driver.cu``): breadth-first over the
+    independent sub-problems, all small frontier nodes in one batched launch.  ``native=False`` runs
+    the same recursion from Python, one C-ABI call per node (the reference-shaped loop below);
     ``node_hook(forest, seed)``, if given, is called for every recursion node that reaches the GPU,
-    just before it is split (bench.py records the nodes with it)."""
+    just before it is split (bench.py records the nodes with it) and implies ``native=False``."""
     if pcg_weighting not in WEIGHTINGS:
         msg = f"Invalid weighting strategy selected: '{pcg_weighting}'"
         raise ValueError(msg)
     if engine is None:
         engine = default_engine()
     names = forest.names
+    if native is None:
+        native = node_hook is None
+    if native:
+        built = engine.supertree_build(forest, pcg_weighting, contract_edges=contract_edges, seed=seed,
+                                       record=trace is not None)  # fmt: skip
+        if trace is not None:
+            for taxa, part, stats in built["records"]:
+                record = {"names": [names[x] for x in taxa], "n_components": int(stats.n_components)}
+                if stats.n_components == 1:
+                    record["contracted_size"] = int(stats.contracted_size)
+                    record["partition"] = [[names[x] for x in taxa[part == c]] for c in (0, 1)]
+                    record["stats"] = stats.as_dict()
+                trace.append(record)
+        return _tree_from_flat(built["parent"], built["taxon"], names)
     holder = PhyloNode("holder")
     holder.children = [None]
     stack: list[tuple[Forest, PhyloNode, int]] = [(forest, holder, 0)]
@@ -173,6 +191,15 @@ def supertree_of_forest(
     result = holder.children[0]
     result.parent = None
     return result
+
+
+def _tree_from_flat(parent, taxon, names: Sequence[str]) -> PhyloNode:
+    """PhyloNode tree of the native driver's flat result (parent[i] < i, children in index order)."""
+    nodes = [PhyloNode(names[x]) if x >= 0 else PhyloNode("root") for x in taxon.tolist()]
+    for k, up in enumerate(parent.tolist()):
+        if up >= 0:
+            nodes[up].append(nodes[k])
+    return nodes[0]
 
 
 def _star(names: Sequence[str]) -> PhyloNode:

@@ -142,3 +142,49 @@ def test_small_node_path_agrees_with_staged_path(engine, name):
             assert {frozenset(p) for p in rec["partition"]} == {frozenset(p) for p in other["partition"]}
             assert a["kmeans_stable_splits"] == b["kmeans_stable_splits"]
     assert small_nodes >= 10
+
+
+@pytest.mark.parametrize("name", ["dcm", "supertriplets", "c2_500x50_branch", "s_200x40_bootstrap", "s_150x40_one"])
+def test_native_driver_matches_python_recursion(engine, name):
+    """csrc/driver.cu (breadth-first, batched small nodes) against the per-node Python recursion."""
+    from spectralclustersupertree_b200.engine import Forest
+    from spectralclustersupertree_b200.scs import supertree_of_forest
+
+    case = load_case(name)
+    trees = parse(case["lines"])
+    a_trace: list = []
+    b_trace: list = []
+    a = supertree_of_forest(Forest.from_trees(trees, case["weights"], case["names"]), case["weighting"],
+                            engine=engine, trace=a_trace, native=True)  # fmt: skip
+    b = supertree_of_forest(Forest.from_trees(trees, case["weights"], case["names"]), case["weighting"],
+                            engine=engine, trace=b_trace, native=False)  # fmt: skip
+    by_names = {tuple(r["names"]): r for r in b_trace}
+    ties = 0
+    for rec in a_trace:
+        other = by_names.get(tuple(rec["names"]))
+        if other is None:
+            continue
+        assert rec["n_components"] == other["n_components"]
+        if "partition" in rec:
+            assert rec["contracted_size"] == other["contracted_size"]
+            same = {frozenset(p) for p in rec["partition"]} == {frozenset(p) for p in other["partition"]}
+            if not same:
+                assert (rec["stats"]["tie_flag"] | other["stats"]["tie_flag"]) & 3
+                ties += 1
+    if ties == 0:
+        assert len(a_trace) == len(b_trace)
+        assert rf(a, b) == 0
+    assert sorted(a.get_tip_names()) == sorted(b.get_tip_names())
+
+
+def test_batched_small_nodes_are_bit_exact(engine):
+    """Graphs built inside small_batch_kernel equal the ones pcg_rows_kernel builds: same eigenvalues to
+    rounding, same partitions, on every small node of a job (native driver vs per-node path with the
+    staged graph build)."""
+    case = load_case("s_300x40_branch_weighted")
+    trees = parse(case["lines"])
+    fused: list = []
+    construct_supertree(trees, case["weights"], case["weighting"], engine=engine, trace=fused)
+    ref = load_case("s_300x40_branch_weighted")["nodes"]
+    report = compare_with_reference_trace(fused, ref)
+    assert report["compared"] >= 100
