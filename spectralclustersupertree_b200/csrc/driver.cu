@@ -95,11 +95,10 @@ class Driver {
             rc = process_wave(wave, next);
             for (Task &t : wave)
                 if (t.owned) scs_forest_destroy(t.forest);
+            wave.clear();
             wave.swap(next);
         }
-        for (Task &t : wave)
-            if (t.owned) scs_forest_destroy(t.forest);
-        for (Task &t : next)
+        for (Task &t : wave)  // only non-empty after an error: the sub-problems that were never started
             if (t.owned) scs_forest_destroy(t.forest);
         return rc;
     }
