@@ -251,6 +251,9 @@ int64_t scs_supertree_num_nodes(const scs_supertree *tree);
 int scs_supertree_nodes(const scs_supertree *tree, int32_t *parent, int32_t *taxon);
 int scs_supertree_counters(const scs_supertree *tree, int64_t *nodes_small, int64_t *nodes_large,
                            int64_t *waves, int64_t *pair_visits);
+/* Host wall-clock seconds the build spent in: [0] large-node splits, [1] small-node batches,
+ * [2] restricting forests, [3] flattening tours. */
+int scs_supertree_seconds(const scs_supertree *tree, double *seconds4);
 int64_t scs_supertree_num_records(const scs_supertree *tree);
 int scs_supertree_record_size(const scs_supertree *tree, int64_t index);
 int scs_supertree_record(const scs_supertree *tree, int64_t index, int32_t *taxa, int32_t *part,

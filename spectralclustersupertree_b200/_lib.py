@@ -124,6 +124,7 @@ SIGNATURES: dict[str, tuple] = {
     "scs_supertree_num_nodes": (c_int64, [_P]),
     "scs_supertree_nodes": (c_int, [_P, _P, _P]),
     "scs_supertree_counters": (c_int, [_P, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)]),
+    "scs_supertree_seconds": (c_int, [_P, _P]),
     "scs_supertree_num_records": (c_int64, [_P]),
     "scs_supertree_record_size": (c_int, [_P, c_int64]),
     "scs_supertree_record": (c_int, [_P, c_int64, _P, _P, POINTER(NodeStats)]),

@@ -16,6 +16,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <memory>
 
@@ -31,11 +32,19 @@ struct scs_supertree {
     std::vector<Record> records;  // one per recursion node that reached the GPU (if requested)
     int64_t nodes_small = 0, nodes_large = 0, waves = 0;
     int64_t pair_visits = 0;
+    double seconds[4] = {0, 0, 0, 0};  // large-node splits, small-node batches, restriction, tours
 };
 
 namespace scs {
 
 namespace {
+
+struct Stopwatch {
+    double *sink;
+    std::chrono::steady_clock::time_point t0;
+    explicit Stopwatch(double *s) : sink(s), t0(std::chrono::steady_clock::now()) {}
+    ~Stopwatch() { *sink += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+};
 
 struct Task {
     scs_forest *forest;
@@ -148,6 +157,7 @@ class Driver {
 
     int tours_of(const scs_forest *f, const std::vector<int32_t> &taxa, int64_t *leaf_offsets, int32_t *leaf_taxon,
                  int32_t *adj_depth, double *adj_val, int32_t *root_depth, double *tree_weight) {
+        Stopwatch sw(&out_.seconds[3]);
         for (size_t v = 0; v < taxa.size(); ++v) local_[taxa[v]] = static_cast<int32_t>(v);
         return scs_forest_tours(f, weighting_, local_.data(), leaf_offsets, leaf_taxon, adj_depth, adj_val, root_depth,
                                 tree_weight);
@@ -168,6 +178,7 @@ class Driver {
         if (rc) return rc;
         part_.resize(n);
         scs_node_stats stats;
+        Stopwatch sw(&out_.seconds[0]);
         rc = scs_node_split_host(ctx_, n, T, L, off_.data(), tax_.data(), dep_.data(), val_.data(), root_.data(),
                                  wgt_.data(), contract_, seed_ + static_cast<uint64_t>(out_.nodes_large + out_.nodes_small),
                                  part_.data(), &stats);
@@ -209,9 +220,13 @@ class Driver {
         }
         part_.resize(N_total);
         std::vector<scs_node_stats> stats(B);
-        int rc = scs_nodes_split_small_host(ctx_, B, nodes.data(), L_total, T_total, off_.data(), tax_.data(),
+        int rc;
+        {
+            Stopwatch sw(&out_.seconds[1]);
+            rc = scs_nodes_split_small_host(ctx_, B, nodes.data(), L_total, T_total, off_.data(), tax_.data(),
                                             dep_.data(), val_.data(), root_.data(), wgt_.data(), contract_,
                                             part_.data(), stats.data());
+        }
         if (rc) return rc;
         out_.nodes_small += B;
         for (int b = 0; b < B; ++b) {
@@ -254,7 +269,11 @@ class Driver {
             }
             for (int i = 0; i < size; ++i) keep_[comp[i]] = 1;
             scs_forest *child_forest = nullptr;
-            int rc = scs_forest_induce(task.forest, keep_.data(), &child_forest);
+            int rc;
+            {
+                Stopwatch sw(&out_.seconds[2]);
+                rc = scs_forest_induce(task.forest, keep_.data(), &child_forest);
+            }
             for (int i = 0; i < size; ++i) keep_[comp[i]] = 0;
             if (rc) return rc;
             const int32_t child = add_node(out_, task.slot, -1);
@@ -399,6 +418,12 @@ int scs_supertree_nodes(const scs_supertree *tree, int32_t *parent, int32_t *tax
     if (!tree || !parent || !taxon) return SCS_ERR_INVALID;
     std::memcpy(parent, tree->parent.data(), sizeof(int32_t) * tree->parent.size());
     std::memcpy(taxon, tree->taxon.data(), sizeof(int32_t) * tree->taxon.size());
+    return SCS_OK;
+}
+
+int scs_supertree_seconds(const scs_supertree *tree, double *seconds4) {
+    if (!tree || !seconds4) return SCS_ERR_INVALID;
+    for (int i = 0; i < 4; ++i) seconds4[i] = tree->seconds[i];
     return SCS_OK;
 }
 

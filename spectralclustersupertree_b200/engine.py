@@ -195,8 +195,11 @@ class Engine:
             small, large, waves, pairs = (ctypes.c_int64(0) for _ in range(4))
             self._lib.scs_supertree_counters(handle, ctypes.byref(small), ctypes.byref(large), ctypes.byref(waves),
                                              ctypes.byref(pairs))  # fmt: skip
+            seconds = np.zeros(4)
+            self._lib.scs_supertree_seconds(handle, ptr(seconds))
             out = {"parent": parent, "taxon": taxon, "nodes_small": small.value, "nodes_large": large.value,
-                   "waves": waves.value, "pair_visits": pairs.value, "records": []}  # fmt: skip
+                   "waves": waves.value, "pair_visits": pairs.value, "records": [],
+                   "seconds": dict(zip(("large_nodes", "small_batches", "restrict", "tours"), seconds.tolist(), strict=True))}  # fmt: skip
             if record:
                 for i in range(self._lib.scs_supertree_num_records(handle)):
                     n = self._lib.scs_supertree_record_size(handle, i)
