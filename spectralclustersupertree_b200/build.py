@@ -24,8 +24,9 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
     "--fmad=true",  # contraction is wanted in the matvec; the graph build uses __dmul_rn/__dadd_rn
-    "-Xcompiler", "-fPIC,-O2,-Wall",
+    "-Xcompiler", "-fPIC,-O2,-Wall,-fopenmp",
     "-shared",
+    "-lgomp",
 ]  # fmt: skip
 
 

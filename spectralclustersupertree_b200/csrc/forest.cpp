@@ -26,6 +26,8 @@
 
 namespace {
 
+constexpr int64_t kParallelNodes = 1 << 15;  // forests with more nodes are processed by all host threads
+
 bool is_tip(const scs_forest &f, int64_t base, int64_t count, int64_t k) {
     // pre-order: a node is a tip iff the next node is not its child
     return k + 1 >= count || f.parent[base + k + 1] != k;
@@ -130,49 +132,88 @@ int scs_forest_induce(const scs_forest *f, const uint8_t *keep, scs_forest **out
     scs_forest *g = new (std::nothrow) scs_forest();
     if (!g) return SCS_ERR_INVALID;
     g->num_taxa = f->num_taxa;
-    std::vector<int32_t> cnt, live_children, new_index;
-    for (int t = 0; t < f->num_trees(); ++t) {
+    const int T = f->num_trees();
+    const int64_t M = f->node_offsets.back();
+    // pass 1 (trees in parallel): which nodes survive, and their index in the restricted tree
+    std::vector<int32_t> new_index(M > 0 ? M : 1);
+    std::vector<int32_t> kept_nodes(T + 1, 0), kept_tips(T + 1, 0);
+    const bool threaded = M > kParallelNodes;
+#pragma omp parallel if (threaded)
+    {
+        std::vector<int32_t> cnt, live_children;
+#pragma omp for schedule(dynamic, 4)
+        for (int t = 0; t < T; ++t) {
+            const int64_t base = f->node_offsets[t], count = f->node_offsets[t + 1] - base;
+            const int32_t *par = f->parent.data() + base;
+            const int32_t *tax = f->taxon.data() + base;
+            int32_t *idx = new_index.data() + base;
+            cnt.assign(count, 0);
+            live_children.assign(count, 0);
+            for (int64_t k = 0; k < count; ++k)
+                if (tax[k] >= 0 && keep[tax[k]]) cnt[k] = 1;
+            for (int64_t k = count - 1; k >= 1; --k) cnt[par[k]] += cnt[k];
+            if (cnt[0] < 2) continue;  // scs.py:447-448: the tree is dropped
+            for (int64_t k = 1; k < count; ++k)
+                if (cnt[k] > 0) live_children[par[k]] += 1;
+            int32_t next = 0, tips = 0;
+            for (int64_t k = 0; k < count; ++k) {
+                // retained: kept tips and nodes that still branch
+                const bool retained = cnt[k] > 0 && (tax[k] >= 0 || live_children[k] >= 2);
+                idx[k] = retained ? next++ : -1;
+                tips += retained && tax[k] >= 0;
+            }
+            kept_nodes[t] = next;
+            kept_tips[t] = tips;
+        }
+    }
+    // output layout
+    std::vector<int64_t> out_base(T + 1, 0);
+    std::vector<int32_t> out_tree(T + 1, -1);
+    int kept_trees = 0;
+    for (int t = 0; t < T; ++t) {
+        out_base[t + 1] = out_base[t] + kept_nodes[t];
+        if (kept_nodes[t] == 0) continue;
+        out_tree[t] = kept_trees++;
+        g->node_offsets.push_back(out_base[t + 1]);
+        g->leaf_offsets.push_back(g->leaf_offsets.back() + kept_tips[t]);
+        g->weight.push_back(f->weight[t]);
+        g->source.push_back(f->source[t]);
+    }
+    const int64_t M_out = out_base[T];
+    g->parent.resize(M_out);
+    g->length.resize(M_out);
+    g->support.resize(M_out);
+    g->taxon.resize(M_out);
+    // pass 2 (trees in parallel): write the restricted trees
+#pragma omp parallel for schedule(dynamic, 4) if (threaded)
+    for (int t = 0; t < T; ++t) {
+        if (kept_nodes[t] == 0) continue;
         const int64_t base = f->node_offsets[t], count = f->node_offsets[t + 1] - base;
         const int32_t *par = f->parent.data() + base;
         const int32_t *tax = f->taxon.data() + base;
         const double *len = f->length.data() + base;
         const double *sup = f->support.data() + base;
-        cnt.assign(count, 0);
-        live_children.assign(count, 0);
-        for (int64_t k = 0; k < count; ++k)
-            if (tax[k] >= 0 && keep[tax[k]]) cnt[k] = 1;
-        for (int64_t k = count - 1; k >= 1; --k) cnt[par[k]] += cnt[k];
-        if (cnt[0] < 2) continue;  // scs.py:447-448
-        for (int64_t k = 1; k < count; ++k)
-            if (cnt[k] > 0) live_children[par[k]] += 1;
-        // retained: kept tips and nodes that still branch
-        new_index.assign(count, -1);
-        const int64_t out_base = static_cast<int64_t>(g->parent.size());
-        int32_t next = 0;
+        const int32_t *idx = new_index.data() + base;
+        const int64_t ob = out_base[t];
         for (int64_t k = 0; k < count; ++k) {
-            const bool retained = cnt[k] > 0 && (tax[k] >= 0 || live_children[k] >= 2);
-            if (!retained) continue;
-            new_index[k] = next++;
-            if (new_index[k] == 0) {  // first retained node in pre-order: the new root
-                g->parent.push_back(-1);
-                g->length.push_back(std::nan(""));
+            const int32_t j = idx[k];
+            if (j < 0) continue;
+            if (j == 0) {  // first retained node in pre-order: the new root, its own length is dropped
+                g->parent[ob] = -1;
+                g->length[ob] = std::nan("");
             } else {
                 double acc = len[k];
                 int64_t a = par[k];
-                while (new_index[a] < 0) {  // merged unary ancestors, bottom-up
-                    acc = len[a] + acc;     // NaN (missing) propagates like None
+                while (idx[a] < 0) {     // merged unary ancestors, bottom-up
+                    acc = len[a] + acc;  // NaN (missing) propagates like None
                     a = par[a];
                 }
-                g->parent.push_back(new_index[a]);
-                g->length.push_back(acc);
+                g->parent[ob + j] = idx[a];
+                g->length[ob + j] = acc;
             }
-            g->support.push_back(sup[k]);
-            g->taxon.push_back(tax[k]);
+            g->support[ob + j] = sup[k];
+            g->taxon[ob + j] = tax[k];
         }
-        g->node_offsets.push_back(out_base + next);
-        g->weight.push_back(f->weight[t]);
-        g->source.push_back(f->source[t]);
-        finish_tree(*g, out_base, next);
     }
     *out = g;
     return SCS_OK;
@@ -189,47 +230,55 @@ int scs_forest_tours(const scs_forest *f, int weighting, const int32_t *local_id
     const int T = f->num_trees();
     if (f->leaf_offsets.back() > 0 && (!leaf_taxon || !adj_depth || !adj_val)) return SCS_ERR_INVALID;
     if (T > 0 && (!root_depth || !tree_weight)) return SCS_ERR_INVALID;
-    std::vector<int32_t> depth;
-    std::vector<double> val;
     int status = SCS_OK;
     leaf_offsets[0] = 0;
-    for (int t = 0; t < T; ++t) {
-        const int64_t base = f->node_offsets[t], count = f->node_offsets[t + 1] - base;
-        const int32_t *par = f->parent.data() + base;
-        const int32_t *tax = f->taxon.data() + base;
-        const double *len = f->length.data() + base;
-        const double *sup = f->support.data() + base;
-        int64_t o = f->leaf_offsets[t];
-        leaf_offsets[t + 1] = f->leaf_offsets[t + 1];
-        root_depth[t] = 0;
-        tree_weight[t] = f->weight[t];
-        if (count <= 1) continue;  // a lone tip has no sides (scs.py:570)
-        depth.assign(count, 0);
-        val.assign(count, 0.0);  // the value handed to the root's children is 0 (scs.py:577)
-        for (int64_t k = 1; k < count; ++k) {
-            if (tax[k] >= 0) continue;
-            const int32_t p = par[k];
-            depth[k] = depth[p] + 1;
-            switch (weighting) {
-            case 0: val[k] = 1.0; break;
-            case 1: val[k] = val[p] + (std::isnan(len[k]) ? 1.0 : len[k]); break;
-            case 2: val[k] = val[p] + 1.0; break;
-            default: val[k] = sup[k]; break;
+    const bool threaded = f->node_offsets.back() > kParallelNodes;
+#pragma omp parallel if (threaded)
+    {
+        std::vector<int32_t> depth;
+        std::vector<double> val;
+#pragma omp for schedule(dynamic, 4)
+        for (int t = 0; t < T; ++t) {
+            const int64_t base = f->node_offsets[t], count = f->node_offsets[t + 1] - base;
+            const int32_t *par = f->parent.data() + base;
+            const int32_t *tax = f->taxon.data() + base;
+            const double *len = f->length.data() + base;
+            const double *sup = f->support.data() + base;
+            int64_t o = f->leaf_offsets[t];
+            leaf_offsets[t + 1] = f->leaf_offsets[t + 1];
+            root_depth[t] = 0;
+            tree_weight[t] = f->weight[t];
+            if (count <= 1) continue;  // a lone tip has no sides (scs.py:570)
+            depth.assign(count, 0);
+            val.assign(count, 0.0);  // the value handed to the root's children is 0 (scs.py:577)
+            for (int64_t k = 1; k < count; ++k) {
+                if (tax[k] >= 0) continue;
+                const int32_t p = par[k];
+                depth[k] = depth[p] + 1;
+                switch (weighting) {
+                case 0: val[k] = 1.0; break;
+                case 1: val[k] = val[p] + (std::isnan(len[k]) ? 1.0 : len[k]); break;
+                case 2: val[k] = val[p] + 1.0; break;
+                default: val[k] = sup[k]; break;
+                }
             }
-        }
-        for (int64_t k = 0; k < count; ++k) {
-            if (tax[k] < 0) continue;
-            leaf_taxon[o] = local_id[tax[k]];
-            if (k + 1 < count) {
-                const int32_t lca = par[k + 1];  // the next pre-order node hangs off the LCA with the next tip
-                adj_depth[o] = depth[lca];
-                adj_val[o] = val[lca];
-                if (lca != 0 && std::isnan(val[lca])) status = SCS_ERR_INPUT;
-            } else {
-                adj_depth[o] = -1;
-                adj_val[o] = 0.0;
+            for (int64_t k = 0; k < count; ++k) {
+                if (tax[k] < 0) continue;
+                leaf_taxon[o] = local_id[tax[k]];
+                if (k + 1 < count) {
+                    const int32_t lca = par[k + 1];  // the next pre-order node hangs off the LCA with the next tip
+                    adj_depth[o] = depth[lca];
+                    adj_val[o] = val[lca];
+                    if (lca != 0 && std::isnan(val[lca])) {
+#pragma omp atomic write
+                        status = SCS_ERR_INPUT;
+                    }
+                } else {
+                    adj_depth[o] = -1;
+                    adj_val[o] = 0.0;
+                }
+                ++o;
             }
-            ++o;
         }
     }
     return status;
