@@ -20,6 +20,8 @@
 #include <cmath>
 #include <memory>
 
+#include <omp.h>
+
 #include "forest.hpp"
 
 struct scs_supertree {
@@ -49,7 +51,46 @@ struct Stopwatch {
 struct Task {
     scs_forest *forest;
     bool owned;
-    int32_t slot;  // output node this task fills in
+    int32_t slot;                // output node this task fills in
+    std::vector<int32_t> taxa;   // taxa present in the forest, ascending (scs.py:708-725)
+};
+
+// What one split recursion node turns into (scs.py:136-171), computed off the critical path.
+struct Child {
+    std::vector<int32_t> star;     // <= 2 taxa: a tip or a star (scs.py:143-145) ...
+    scs_forest *forest = nullptr;  // ... else the restricted forest of the component
+    std::vector<int32_t> taxa;     // taxa present in that forest
+    std::vector<int32_t> missing;  // taxa of the component in no restricted tree (scs.py:168-171)
+};
+
+struct SplitResult {
+    size_t task = 0;
+    std::vector<int32_t> part;
+    scs_node_stats stats;
+    std::vector<Child> children;
+    int rc = SCS_OK;
+};
+
+// Per-thread scratch sized by the number of taxa of the job.
+struct Scratch {
+    std::vector<uint8_t> keep;
+    std::vector<int32_t> stamp;
+    int stamp_id = 0;
+    void reset(int num_taxa) {
+        keep.assign(num_taxa > 0 ? num_taxa : 1, 0);
+        stamp.assign(num_taxa > 0 ? num_taxa : 1, 0);
+        stamp_id = 0;
+    }
+    void present_taxa(const scs_forest *f, std::vector<int32_t> &taxa) {
+        taxa.clear();
+        ++stamp_id;
+        for (int32_t x : f->taxon)
+            if (x >= 0 && stamp[x] != stamp_id) {
+                stamp[x] = stamp_id;
+                taxa.push_back(x);
+            }
+        std::sort(taxa.begin(), taxa.end());
+    }
 };
 
 struct ForestDeleter {
@@ -91,12 +132,13 @@ class Driver {
 
     int run(const scs_forest *root) {
         num_taxa_ = scs_forest_num_taxa(root);
-        stamp_.assign(num_taxa_ > 0 ? num_taxa_ : 1, 0);
         local_.assign(num_taxa_ > 0 ? num_taxa_ : 1, -1);
-        keep_.assign(num_taxa_ > 0 ? num_taxa_ : 1, 0);
+        scratch_.resize(static_cast<size_t>(omp_get_max_threads()));
+        for (Scratch &sc : scratch_) sc.reset(num_taxa_);
         std::vector<Task> wave, next;
         const int32_t root_slot = add_node(out_, -1, -1);
-        wave.push_back(Task{const_cast<scs_forest *>(root), false, root_slot});
+        wave.push_back(Task{const_cast<scs_forest *>(root), false, root_slot, {}});
+        scratch_[0].present_taxa(root, wave[0].taxa);
         int rc = SCS_OK;
         while (!wave.empty() && rc == SCS_OK) {
             out_.waves += 1;
@@ -113,22 +155,9 @@ class Driver {
     }
 
   private:
-    // taxa present in f, ascending (scs.py:708-725); O(nodes of f), not O(num_taxa)
-    void present_taxa(const scs_forest *f, std::vector<int32_t> &taxa) {
-        taxa.clear();
-        ++stamp_id_;
-        for (int32_t x : f->taxon)
-            if (x >= 0 && stamp_[x] != stamp_id_) {
-                stamp_[x] = stamp_id_;
-                taxa.push_back(x);
-            }
-        std::sort(taxa.begin(), taxa.end());
-    }
-
     int process_wave(std::vector<Task> &wave, std::vector<Task> &next) {
         std::vector<size_t> small;
-        std::vector<std::vector<int32_t>> small_taxa;
-        std::vector<int32_t> taxa;
+        std::vector<SplitResult> results;
         int rc;
         for (size_t i = 0; i < wave.size(); ++i) {
             Task &task = wave[i];
@@ -138,20 +167,40 @@ class Driver {
                 if ((rc = fill_tree(out_, task.slot, task.forest))) return rc;
                 continue;
             }
-            present_taxa(task.forest, taxa);
-            const int n = static_cast<int>(taxa.size());
+            const int n = static_cast<int>(task.taxa.size());
             if (n <= 2) {
-                fill_star(out_, task.slot, taxa.data(), n);
+                fill_star(out_, task.slot, task.taxa.data(), n);
                 continue;
             }
             if (n <= ctx_->small_limit) {
                 small.push_back(i);
-                small_taxa.push_back(taxa);
                 continue;
             }
-            if ((rc = split_large(task, taxa, next))) return rc;
+            results.emplace_back();
+            results.back().task = i;
+            if ((rc = split_large(task, results.back()))) return rc;
         }
-        if (!small.empty() && (rc = split_small(wave, small, small_taxa, next))) return rc;
+        if (!small.empty() && (rc = split_small(wave, small, results))) return rc;
+
+        // children of every split node: restriction of the forests is independent per node, so the
+        // nodes of a wave are planned by all host threads; emission into the output stays serial
+        {
+            Stopwatch sw(&out_.seconds[2]);
+            const int count = static_cast<int>(results.size());
+#pragma omp parallel for schedule(dynamic, 1) if (count >= 8)
+            for (int r = 0; r < count; ++r)
+                plan(wave[results[r].task], results[r], scratch_[static_cast<size_t>(omp_get_thread_num())]);
+        }
+        for (SplitResult &res : results) {
+            if (res.rc) rc = res.rc;
+        }
+        if (rc) {
+            for (SplitResult &res : results)
+                for (Child &child : res.children)
+                    if (child.forest) scs_forest_destroy(child.forest);
+            return rc;
+        }
+        for (SplitResult &res : results) emit(wave[res.task], res, next);
         return SCS_OK;
     }
 
@@ -163,8 +212,9 @@ class Driver {
                                 tree_weight);
     }
 
-    int split_large(Task &task, const std::vector<int32_t> &taxa, std::vector<Task> &next) {
+    int split_large(Task &task, SplitResult &res) {
         const scs_forest *f = task.forest;
+        const std::vector<int32_t> &taxa = task.taxa;
         const int n = static_cast<int>(taxa.size());
         const int T = scs_forest_num_trees(f);
         const int64_t L = scs_forest_num_leaves(f);
@@ -176,26 +226,24 @@ class Driver {
         wgt_.resize(T + 1);
         int rc = tours_of(f, taxa, off_.data(), tax_.data(), dep_.data(), val_.data(), root_.data(), wgt_.data());
         if (rc) return rc;
-        part_.resize(n);
-        scs_node_stats stats;
+        res.part.resize(n);
         Stopwatch sw(&out_.seconds[0]);
         rc = scs_node_split_host(ctx_, n, T, L, off_.data(), tax_.data(), dep_.data(), val_.data(), root_.data(),
                                  wgt_.data(), contract_, seed_ + static_cast<uint64_t>(out_.nodes_large + out_.nodes_small),
-                                 part_.data(), &stats);
+                                 res.part.data(), &res.stats);
         if (rc) return rc;
         out_.nodes_large += 1;
         out_.pair_visits += scs_forest_pair_visits(f);
-        return expand(task, taxa, part_.data(), stats, next);
+        return SCS_OK;
     }
 
-    int split_small(std::vector<Task> &wave, const std::vector<size_t> &small,
-                    const std::vector<std::vector<int32_t>> &small_taxa, std::vector<Task> &next) {
+    int split_small(std::vector<Task> &wave, const std::vector<size_t> &small, std::vector<SplitResult> &results) {
         const int B = static_cast<int>(small.size());
         std::vector<scs_small_node> nodes(B);
         int64_t L_total = 0, T_total = 0, N_total = 0;
         for (int b = 0; b < B; ++b) {
             const scs_forest *f = wave[small[b]].forest;
-            nodes[b].n = static_cast<int32_t>(small_taxa[b].size());
+            nodes[b].n = static_cast<int32_t>(wave[small[b]].taxa.size());
             nodes[b].num_trees = scs_forest_num_trees(f);
             nodes[b].leaf_base = L_total;
             nodes[b].tree_base = T_total;
@@ -213,7 +261,7 @@ class Driver {
         wgt_.resize(T_total + 1);
         for (int b = 0; b < B; ++b) {
             const scs_forest *f = wave[small[b]].forest;
-            int rc = tours_of(f, small_taxa[b], off_.data() + nodes[b].tree_base + b, tax_.data() + nodes[b].leaf_base,
+            int rc = tours_of(f, wave[small[b]].taxa, off_.data() + nodes[b].tree_base + b, tax_.data() + nodes[b].leaf_base,
                               dep_.data() + nodes[b].leaf_base, val_.data() + nodes[b].leaf_base,
                               root_.data() + nodes[b].tree_base, wgt_.data() + nodes[b].tree_base);
             if (rc) return rc;
@@ -230,65 +278,81 @@ class Driver {
         if (rc) return rc;
         out_.nodes_small += B;
         for (int b = 0; b < B; ++b) {
-            rc = expand(wave[small[b]], small_taxa[b], part_.data() + nodes[b].vertex_base, stats[b], next);
-            if (rc) return rc;
+            results.emplace_back();
+            SplitResult &res = results.back();
+            res.task = small[b];
+            res.part.assign(part_.data() + nodes[b].vertex_base, part_.data() + nodes[b].vertex_base + nodes[b].n);
+            res.stats = stats[b];
         }
         return SCS_OK;
     }
 
-    // ref: scs.py:136-174 -- children of a split node
-    int expand(Task &task, const std::vector<int32_t> &taxa, const int32_t *part, const scs_node_stats &stats,
-               std::vector<Task> &next) {
+    // ref: scs.py:136-171 -- what the children of a split node are (thread-safe: touches only `res`)
+    void plan(const Task &task, SplitResult &res, Scratch &scratch) {
+        const std::vector<int32_t> &taxa = task.taxa;
         const int n = static_cast<int>(taxa.size());
-        const int parts = stats.n_components != 1 ? stats.n_components : 2;
-        if (record_) {
-            scs_supertree::Record rec;
-            rec.taxa = taxa;
-            rec.part.assign(part, part + n);
-            rec.stats = stats;
-            out_.records.push_back(std::move(rec));
-        }
+        const int parts = res.stats.n_components != 1 ? res.stats.n_components : 2;
+        const int32_t *part = res.part.data();
         // bucket the vertices by part, keeping ascending taxon order inside each
         std::vector<int32_t> start(parts + 1, 0);
         for (int v = 0; v < n; ++v) {
-            if (part[v] < 0 || part[v] >= parts) return fail(ctx_, SCS_ERR_INVALID, "part index out of range");
+            if (part[v] < 0 || part[v] >= parts) {
+                res.rc = SCS_ERR_INVALID;
+                return;
+            }
             start[part[v] + 1] += 1;
         }
         for (int c = 0; c < parts; ++c) start[c + 1] += start[c];
         std::vector<int32_t> members(n), cursor(start.begin(), start.end() - 1);
         for (int v = 0; v < n; ++v) members[cursor[part[v]]++] = taxa[v];
-        std::vector<int32_t> covered;
         for (int c = 0; c < parts; ++c) {
             const int32_t *comp = members.data() + start[c];
             const int size = start[c + 1] - start[c];
             if (size == 0) continue;
+            res.children.emplace_back();
+            Child &child = res.children.back();
             if (size <= 2) {  // ref: scs.py:143-145
-                const int32_t child = add_node(out_, task.slot, -1);
-                fill_star(out_, child, comp, size);
+                child.star.assign(comp, comp + size);
                 continue;
             }
-            for (int i = 0; i < size; ++i) keep_[comp[i]] = 1;
-            scs_forest *child_forest = nullptr;
-            int rc;
-            {
-                Stopwatch sw(&out_.seconds[2]);
-                rc = scs_forest_induce(task.forest, keep_.data(), &child_forest);
+            for (int i = 0; i < size; ++i) scratch.keep[comp[i]] = 1;
+            const int rc = scs_forest_induce(task.forest, scratch.keep.data(), &child.forest);
+            for (int i = 0; i < size; ++i) scratch.keep[comp[i]] = 0;
+            if (rc) {
+                res.rc = rc;
+                return;
             }
-            for (int i = 0; i < size; ++i) keep_[comp[i]] = 0;
-            if (rc) return rc;
-            const int32_t child = add_node(out_, task.slot, -1);
-            next.push_back(Task{child_forest, true, child});
-            if (scs_forest_num_trees(child_forest) == 0) continue;  // raises when its wave is processed
-            present_taxa(child_forest, covered);
-            if (static_cast<int>(covered.size()) != size) {  // ref: scs.py:168-171
+            if (scs_forest_num_trees(child.forest) == 0) continue;  // raises when its wave is processed
+            scratch.present_taxa(child.forest, child.taxa);
+            if (static_cast<int>(child.taxa.size()) != size) {  // ref: scs.py:168-171
                 size_t ci = 0;
                 for (int i = 0; i < size; ++i) {
-                    while (ci < covered.size() && covered[ci] < comp[i]) ++ci;
-                    if (ci >= covered.size() || covered[ci] != comp[i]) add_node(out_, task.slot, comp[i]);
+                    while (ci < child.taxa.size() && child.taxa[ci] < comp[i]) ++ci;
+                    if (ci >= child.taxa.size() || child.taxa[ci] != comp[i]) child.missing.push_back(comp[i]);
                 }
             }
         }
-        return SCS_OK;
+    }
+
+    // ref: scs.py:139-174 -- attach the children to the output tree and queue the sub-problems
+    void emit(Task &task, SplitResult &res, std::vector<Task> &next) {
+        if (record_) {
+            scs_supertree::Record rec;
+            rec.taxa = task.taxa;
+            rec.part = res.part;
+            rec.stats = res.stats;
+            out_.records.push_back(std::move(rec));
+        }
+        for (Child &child : res.children) {
+            const int32_t slot = add_node(out_, task.slot, -1);
+            if (!child.forest) {
+                fill_star(out_, slot, child.star.data(), static_cast<int>(child.star.size()));
+                continue;
+            }
+            next.push_back(Task{child.forest, true, slot, std::move(child.taxa)});
+            child.forest = nullptr;
+            for (int32_t x : child.missing) add_node(out_, task.slot, x);
+        }
     }
 
     scs_ctx *ctx_;
@@ -297,9 +361,8 @@ class Driver {
     bool record_;
     scs_supertree &out_;
     int num_taxa_ = 0;
-    int stamp_id_ = 0;
-    std::vector<int32_t> stamp_, local_;
-    std::vector<uint8_t> keep_;
+    std::vector<int32_t> local_;
+    std::vector<Scratch> scratch_;
     std::vector<int64_t> off_;
     std::vector<int32_t> tax_, dep_, root_, part_;
     std::vector<double> val_, wgt_;
