@@ -8,10 +8,13 @@ is quoted on).  Three clocks are reported in one JSON line:
 
 * ``value``  -- the hot path alone with inputs resident in HBM: every recursion node of the job
   (graph build, components, contraction, spectral split) replayed from leaf tours that were uploaded
-  before the timed region; CUDA events on the engine's stream.
-* ``e2e``    -- the same job through the public host-buffer path (``supertree_of_forest`` over the
-  C ABI): flat source trees in host memory in, supertree out; host recursion, tree restriction,
-  H2D of every node's tours and D2H of every node's partition inside the timed region.
+  before the timed region -- nodes with more than 64 taxa one by one, all smaller ones in one batched
+  launch; CUDA events on the engine's stream.
+* ``e2e``    -- the same job through the public host-buffer path over the C ABI
+  (``scs_forest_create`` + ``scs_supertree_build``): flat source trees in host memory in, flat
+  supertree out; native breadth-first recursion, tree restriction, per-wave H2D of tours and D2H of
+  partitions inside the timed region.  With N > 1 the frontier of independent sub-problems is dealt
+  out over the ranks (no data-path collective) and the outputs are all-gathered.
 * ``roofline`` -- the Laplacian matvec (the kernel BASELINE.json's metric names), timed per launch
   with CUDA events inside the timed steps, against the measured HBM peak.
 
@@ -38,6 +41,10 @@ if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
 
 METRIC = "construct_supertree wall-time at 10k taxa/1k trees"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of matvec_row_per_cta at m = 8765, from the
+# round-1 `ncu --set full` capture (profiles/r01_ncu_full_matvec_raw.csv); algorithmic bytes 614.8 MB
+NCU_MATVEC_TRAFFIC = {"bytes_per_launch": 618.2e6, "algorithmic_bytes": 614.8e6, "m": 8765,
+                      "source": "profiles/r01_ncu_full_matvec_raw.csv"}
 
 # name -> (taxa, trees, weighting, seed, tree weights)   (BASELINE.json configs; seed = 1000 * index)
 WORKLOADS = {
@@ -253,42 +260,104 @@ def reference_line(args, arrays: dict) -> dict:
 # the GPU arm
 # ---------------------------------------------------------------------------------------------
 class Replay:
-    """Every recursion node's leaf tours, resident in HBM, for the device-only timed pass."""
+    """The recursion nodes one rank processes, as leaf tours resident in HBM, for the device-only
+    timed pass: every node with more than 64 taxa through ``scs_node_split_dev``, all smaller ones in
+    one launch of the batched small-node kernel (``scs_nodes_split_small_dev``)."""
 
-    def __init__(self, engine, nodes: list) -> None:
+    FIELDS = (("leaf_offsets", np.int64), ("leaf_taxon", np.int32), ("adj_depth", np.int32),
+              ("adj_val", np.float64), ("root_depth", np.int32), ("tree_weight", np.float64))  # fmt: skip
+
+    def __init__(self, engine, nodes: list, small_limit: int = 64) -> None:
+        from spectralclustersupertree_b200 import _lib
+
         self.engine = engine
-        self.nodes = []
+        self.lib = _lib.load()
         self.pair_visits = [t.pair_updates() for t, _ in nodes]
-        cat = lambda field, dtype: np.concatenate([getattr(t, field) for t, _ in nodes]).astype(dtype)  # noqa: E731
-        host = {
-            "leaf_offsets": cat("leaf_offsets", np.int64), "leaf_taxon": cat("leaf_taxon", np.int32),
-            "adj_depth": cat("adj_depth", np.int32), "adj_val": cat("adj_val", np.float64),
-            "root_depth": cat("root_depth", np.int32), "tree_weight": cat("tree_weight", np.float64),
-        }  # fmt: skip
-        self.bytes = sum(a.nbytes for a in host.values())
-        self.dev = {k: engine.to_device(v) for k, v in host.items()}
-        size = {k: v.itemsize for k, v in host.items()}
-        pos = dict.fromkeys(host, 0)
-        n_max = 1
-        for tours, seed in nodes:
-            T, L = tours.num_trees, tours.num_leaves
-            entry = {"n": tours.n, "T": T, "L": L, "seed": seed}
-            for key, count in (("leaf_offsets", T + 1), ("leaf_taxon", L), ("adj_depth", L), ("adj_val", L),
-                               ("root_depth", T), ("tree_weight", T)):  # fmt: skip
-                entry[key] = self.dev[key] + pos[key] * size[key]
-                pos[key] += count
-            self.nodes.append(entry)
-            n_max = max(n_max, tours.n)
-        self.part = engine.alloc(4 * n_max)
+        large = [(t, seed) for t, seed in nodes if t.n > small_limit]
+        small = [t for t, _ in nodes if t.n <= small_limit]
+        self.bytes = 0
+        self.buffers = []
+        # large nodes: concatenated arrays, one entry of device pointers per node
+        self.large = []
+        if large:
+            host = {k: np.concatenate([getattr(t, k) for t, _ in large]).astype(d) for k, d in self.FIELDS}
+            dev = {k: self._upload(v) for k, v in host.items()}
+            pos = dict.fromkeys(host, 0)
+            for tours, seed in large:
+                T, L = tours.num_trees, tours.num_leaves
+                entry = {"n": tours.n, "T": T, "L": L, "seed": seed}
+                for key, count in (("leaf_offsets", T + 1), ("leaf_taxon", L), ("adj_depth", L), ("adj_val", L),
+                                   ("root_depth", T), ("tree_weight", T)):  # fmt: skip
+                    entry[key] = dev[key] + pos[key] * host[key].itemsize
+                    pos[key] += count
+                self.large.append(entry)
+        self.part = engine.alloc(4 * max([t.n for t, _ in nodes] + [1]))
+        # small nodes: the layout of scs_small_node (include/scs_b200.h)
+        self.small_count = len(small)
+        if small:
+            desc = np.zeros(len(small), dtype=np.dtype([("n", "<i4"), ("num_trees", "<i4"), ("leaf_base", "<i8"),
+                                                        ("tree_base", "<i8"), ("vertex_base", "<i8")]))  # fmt: skip
+            L = T = N = 0
+            for b, t in enumerate(small):
+                desc[b] = (t.n, t.num_trees, L, T, N)
+                L += t.num_leaves
+                T += t.num_trees
+                N += t.n
+            host = {k: np.concatenate([getattr(t, k) for t in small]).astype(d) for k, d in self.FIELDS}
+            self.small_dev = {k: self._upload(v) for k, v in host.items()}
+            self.small_desc = self._upload(desc)
+            self.small_part = engine.alloc(4 * max(N, 1))
+            self.small_stats = engine.alloc(80 * len(small))
+            self.buffers += [self.small_part, self.small_stats]
+        self.buffers.append(self.part)
+
+    def _upload(self, array: np.ndarray) -> int:
+        self.bytes += array.nbytes
+        dev = self.engine.to_device(array)
+        self.buffers.append(dev)
+        return dev
 
     def run(self, contract_edges: bool = True) -> None:
-        for entry in self.nodes:
+        for entry in self.large:
             self.engine.node_split_dev(entry, self.part, contract_edges=contract_edges, seed=entry["seed"])
+        if self.small_count:
+            d = self.small_dev
+            status = self.lib.scs_nodes_split_small_dev(
+                self.engine.handle, self.small_count, self.small_desc, d["leaf_offsets"], d["leaf_taxon"],
+                d["adj_depth"], d["adj_val"], d["root_depth"], d["tree_weight"], int(contract_edges),
+                self.small_part, self.small_stats,
+            )  # fmt: skip
+            if status != 0:
+                raise RuntimeError(f"scs_nodes_split_small_dev failed with status {status}")
 
     def close(self) -> None:
-        for d in self.dev.values():
+        for d in self.buffers:
             self.engine.free(d)
-        self.engine.free(self.part)
+
+
+def gather_supertree(dist, built: dict, local_rank: int):
+    """All ranks' flat outputs joined on every rank (tiny: 2 int32 per output node)."""
+    import torch
+
+    from spectralclustersupertree_b200.engine import merge_sharded
+
+    device = torch.device("cuda", local_rank)
+    world = dist.get_world_size()
+    size = torch.tensor([len(built["parent"]), built["shared_prefix"]], device=device, dtype=torch.int64)
+    sizes = [torch.zeros_like(size) for _ in range(world)]
+    dist.all_gather(sizes, size)
+    longest = int(max(int(s[0]) for s in sizes))
+    mine = torch.full((2, longest), -2, device=device, dtype=torch.int32)
+    mine[0, : len(built["parent"])] = torch.from_numpy(built["parent"]).to(device)
+    mine[1, : len(built["taxon"])] = torch.from_numpy(built["taxon"]).to(device)
+    everyone = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(everyone, mine)
+    parts = []
+    for r in range(world):
+        count, prefix = int(sizes[r][0]), int(sizes[r][1])
+        host = everyone[r].cpu().numpy()
+        parts.append((host[0, :count], host[1, :count], prefix))
+    return merge_sharded(parts)
 
 
 def gpu_line(args, arrays: dict) -> dict:
@@ -313,24 +382,38 @@ def gpu_line(args, arrays: dict) -> dict:
         return Forest.from_arrays(arrays["node_offsets"], arrays["parent"], arrays["length"], arrays["support"],
                                   arrays["taxon"], arrays["weights"], arrays["names"])  # fmt: skip
 
-    # recording pass (untimed): the recursion nodes of this job, for the device-resident replay
-    recorded: list = []
-    trace: list = []
-    tree = supertree_of_forest(new_forest(), weighting, engine=engine, trace=trace,
-                               node_hook=lambda f, seed: recorded.append((f.tours(weighting), seed)))  # fmt: skip
-    n_tips = len(tree.get_tip_names())
-    replay = Replay(engine, recorded)
-    spectral = [r for r in trace if r["n_components"] == 1]
+    def e2e_step():
+        """The product path: flat host arrays in, flat supertree out (joined over the ranks)."""
+        built = engine.supertree_build(new_forest(), weighting, rank=rank, world=world)
+        if dist is None:
+            return built, (built["parent"], built["taxon"])
+        return built, gather_supertree(dist, built, local_rank)
+
+    # recording pass (untimed): every recursion node's leaf tours, keyed by its vertex set, from the
+    # per-node Python recursion; then the nodes THIS rank processes in the (sharded) native build
+    recorded: dict = {}
+    supertree_of_forest(new_forest(), weighting, engine=engine, native=False,
+                        node_hook=lambda f, seed: recorded.__setitem__(f.taxa().tobytes(), (f.tours(weighting), seed)))  # fmt: skip
+    traced = engine.supertree_build(new_forest(), weighting, record=True, rank=rank, world=world)
+    mine = [recorded[taxa.tobytes()] for taxa, _, _ in traced["records"]]
+    replay = Replay(engine, mine)
+    spectral = [st for _, _, st in traced["records"] if st.n_components == 1]
+    all_visits = [t.pair_updates() for t, _ in recorded.values()]
     job = {
-        "recursion_nodes": len(trace),
-        "spectral_nodes": len(spectral),
-        "largest_spectral_m": max((r["contracted_size"] for r in spectral), default=0),
-        "matvecs": sum(r["stats"]["matvecs"] for r in spectral),
-        "tie_nodes": sum(1 for r in spectral if r["stats"]["tie_flag"]),
-        "pair_visits_total": int(sum(replay.pair_visits)),
-        "pair_visits_top": int(replay.pair_visits[0]) if replay.pair_visits else 0,
-        "tour_bytes": int(replay.bytes),
-        "supertree_tips": n_tips,
+        "recursion_nodes": len(recorded),
+        "recursion_nodes_this_rank": len(mine),
+        "spectral_nodes_this_rank": len(spectral),
+        "largest_spectral_m": max((st.contracted_size for st in spectral), default=0),
+        "lanczos_matvecs_this_rank": sum(st.matvecs for st in spectral if st.solver == 3),
+        "tie_nodes_this_rank": sum(1 for st in spectral if st.tie_flag & 3),
+        "pair_visits_total": int(sum(all_visits)),
+        "pair_visits_top": int(max(all_visits)) if all_visits else 0,
+        "waves": traced["waves"],
+        "wave_tasks": traced["wave_tasks"],
+        "wave_max_n": traced["wave_max_n"],
+        "nodes_small": traced["nodes_small"],
+        "nodes_large": traced["nodes_large"],
+        "resident_tour_bytes": int(replay.bytes),
     }
 
     def barrier():
@@ -338,13 +421,11 @@ def gpu_line(args, arrays: dict) -> dict:
         if dist is not None:
             dist.barrier()
 
-    def e2e_step():
-        return supertree_of_forest(new_forest(), weighting, engine=engine)
-
     for _ in range(args.warmup):
-        e2e_step()
+        _, merged = e2e_step()
         replay.run()
     engine.synchronize()
+    tips = int((merged[1] >= 0).sum())
 
     sampler = ClockSampler(local_rank)
     # ---- timed: device-resident replay (value) with per-launch matvec / row-kernel timing ----------
@@ -365,13 +446,16 @@ def gpu_line(args, arrays: dict) -> dict:
     # ---- timed: end to end from host buffers (e2e) -----------------------------------------------
     h2d0, d2h0 = engine.io_bytes()
     e2e_s = []
+    host_split = dict.fromkeys(("large_nodes", "small_batches", "restrict", "tours"), 0.0)
     for _ in range(args.steps):
         engine.flush_l2()
         barrier()
         t0 = time.perf_counter()
-        e2e_step()
+        built, merged = e2e_step()
         engine.synchronize()
         e2e_s.append(time.perf_counter() - t0)
+        for k in host_split:
+            host_split[k] += built["seconds"][k] / args.steps
         barrier()
     h2d1, d2h1 = engine.io_bytes()
     clocks = sampler.stop()
@@ -395,13 +479,15 @@ def gpu_line(args, arrays: dict) -> dict:
             "avg_launch_us": 1e3 * matvec["ms"] / matvec["launches"],
             "bytes_per_launch": matvec["bytes"] / matvec["launches"],
             "share_of_step": matvec["ms"] / sum(dev_ms),
+            "traffic": NCU_MATVEC_TRAFFIC,
         })  # fmt: skip
     roofline_rows = None
     if rows["launches"] and rows["ms"] > 0:
+        visits = sum(v for (t, _), v in zip(mine, replay.pair_visits, strict=True) if t.n >= 2048) * args.steps
         roofline_rows = {
-            "kernel": "pcg_rows_kernel (leaf-pair LCA weighting -> W rows, adjacency bits, degree)",
-            "bound": "shared-memory / issue (not HBM): leaf-pair visits per second",
-            "pair_visits_per_s": rows["units"] / (rows["ms"] * 1e-3),
+            "kernel": "pcg_rows_kernel (leaf-pair LCA weighting -> W rows, adjacency bits, degree), n >= 2048",
+            "bound": "shared-memory / issue (not HBM): ordered leaf-pair visits per second",
+            "pair_visits_per_s": visits / (rows["ms"] * 1e-3),
             "write_GBps": rows["bytes"] / (rows["ms"] * 1e-3) / 1e9,
             "launches": rows["launches"],
             "share_of_step": rows["ms"] / sum(dev_ms),
@@ -413,8 +499,15 @@ def gpu_line(args, arrays: dict) -> dict:
         "config": {
             "workload": describe(args.workload),
             "l2": "flushed between timed steps (256 MB write); the top-level W (0.8 GB) exceeds L2 by itself",
-            "value_is": "all recursion nodes replayed from leaf tours resident in HBM (CUDA events)",
-            "e2e_is": "supertree_of_forest over the C ABI from flat host arrays (wall clock)",
+            "value_is": "every recursion node of this rank's share of the job replayed from leaf tours resident in "
+                        "HBM: nodes > 64 taxa one by one, all smaller nodes in one batched launch (CUDA events; max "
+                        "over ranks)",
+            "e2e_is": "scs_forest_create + scs_supertree_build over the C ABI from flat host arrays to the flat "
+                      "supertree (wall clock; native breadth-first recursion, per-wave H2D of tours and D2H of "
+                      "partitions; for N > 1 the frontier is dealt out over the ranks and the outputs are "
+                      "all-gathered)",
+            "e2e_host_seconds": host_split,
+            "supertree_tips": tips,
             "job": job,
         },
         "clocks": clocks,

@@ -237,6 +237,14 @@ int scs_nodes_split_small_host(scs_ctx *ctx, int num_nodes, const scs_small_node
                                const double *tree_weight, int contract_edges, int32_t *part,
                                scs_node_stats *stats);
 
+/* Same, on device-resident inputs and outputs; only enqueues the launch (stats_dev is a device array
+ * of num_nodes scs_node_stats). */
+int scs_nodes_split_small_dev(scs_ctx *ctx, int num_nodes, const scs_small_node *nodes_dev,
+                              const int64_t *leaf_offsets_dev, const int32_t *leaf_taxon_dev,
+                              const int32_t *adj_depth_dev, const double *adj_val_dev,
+                              const int32_t *root_depth_dev, const double *tree_weight_dev,
+                              int contract_edges, int32_t *part_dev, scs_node_stats *stats_dev);
+
 /* ---- the whole recursion (scs.py:96-174) as a native work-list ------------------------------- *
  * Breadth-first over the independent sub-problems: every frontier node with <= 64 taxa goes to the
  * GPU in one batched launch, larger ones through scs_node_split_host.  The result is the supertree
@@ -246,6 +254,17 @@ int scs_nodes_split_small_host(scs_ctx *ctx, int num_nodes, const scs_small_node
 typedef struct scs_supertree scs_supertree;
 int scs_supertree_build(scs_ctx *ctx, const scs_forest *forest, int weighting, int contract_edges,
                         uint64_t seed, int record_nodes, scs_supertree **out);
+/* One job over `world` GPUs, one process each, no collective on the data path: every rank runs the
+ * first waves redundantly (deterministic kernels => identical frontier and identical output prefix),
+ * then the frontier is dealt out by estimated cost and each rank finishes its own sub-problems.
+ * Output nodes [0, scs_supertree_shared_prefix) are the same on every rank; the caller appends the
+ * other ranks' nodes past the prefix (parents >= prefix shift by the append offset). */
+int scs_supertree_build_sharded(scs_ctx *ctx, const scs_forest *forest, int weighting, int contract_edges,
+                                uint64_t seed, int record_nodes, int rank, int world, scs_supertree **out);
+int64_t scs_supertree_shared_prefix(const scs_supertree *tree);
+/* Per wave of the breadth-first recursion: number of sub-problems and the largest one's taxon count.
+ * Returns the number of waves; either array may be NULL (size them with scs_supertree_counters). */
+int scs_supertree_wave_info(const scs_supertree *tree, int32_t *tasks, int32_t *max_n);
 int scs_supertree_destroy(scs_supertree *tree);
 int64_t scs_supertree_num_nodes(const scs_supertree *tree);
 int scs_supertree_nodes(const scs_supertree *tree, int32_t *parent, int32_t *taxon);

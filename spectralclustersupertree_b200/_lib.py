@@ -119,7 +119,11 @@ SIGNATURES: dict[str, tuple] = {
         c_int,
         [_P, c_int, _P, c_int64, c_int64, _P, _P, _P, _P, _P, _P, c_int, _P, _P],
     ),
+    "scs_nodes_split_small_dev": (c_int, [_P, c_int, _P, _P, _P, _P, _P, _P, _P, c_int, _P, _P]),
     "scs_supertree_build": (c_int, [_P, _P, c_int, c_int, c_uint64, c_int, POINTER(_P)]),
+    "scs_supertree_build_sharded": (c_int, [_P, _P, c_int, c_int, c_uint64, c_int, c_int, c_int, POINTER(_P)]),
+    "scs_supertree_shared_prefix": (c_int64, [_P]),
+    "scs_supertree_wave_info": (c_int, [_P, _P, _P]),
     "scs_supertree_destroy": (c_int, [_P]),
     "scs_supertree_num_nodes": (c_int64, [_P]),
     "scs_supertree_nodes": (c_int, [_P, _P, _P]),

@@ -35,6 +35,8 @@ struct scs_supertree {
     int64_t nodes_small = 0, nodes_large = 0, waves = 0;
     int64_t pair_visits = 0;
     double seconds[4] = {0, 0, 0, 0};  // large-node splits, small-node batches, restriction, tours
+    std::vector<int32_t> wave_tasks, wave_max_n;  // per wave: sub-problems in it, largest taxon count
+    int64_t shared_prefix = 0;  // sharded build: output nodes [0, shared_prefix) are identical on every rank
 };
 
 namespace scs {
@@ -127,8 +129,10 @@ int fill_tree(scs_supertree &out, int32_t slot, const scs_forest *f) {
 
 class Driver {
   public:
-    Driver(scs_ctx *ctx, int weighting, int contract_edges, uint64_t seed, bool record, scs_supertree *out)
-        : ctx_(ctx), weighting_(weighting), contract_(contract_edges), seed_(seed), record_(record), out_(*out) {}
+    Driver(scs_ctx *ctx, int weighting, int contract_edges, uint64_t seed, bool record, int rank, int world,
+           scs_supertree *out)
+        : ctx_(ctx), weighting_(weighting), contract_(contract_edges), seed_(seed), record_(record), rank_(rank),
+          world_(world), out_(*out) {}
 
     int run(const scs_forest *root) {
         num_taxa_ = scs_forest_num_taxa(root);
@@ -141,7 +145,13 @@ class Driver {
         scratch_[0].present_taxa(root, wave[0].taxa);
         int rc = SCS_OK;
         while (!wave.empty() && rc == SCS_OK) {
+            if (world_ > 1 && !partitioned_ && should_partition(wave)) partition(wave);
+            if (wave.empty()) break;
             out_.waves += 1;
+            int32_t max_n = 0;
+            for (const Task &t : wave) max_n = std::max<int32_t>(max_n, static_cast<int32_t>(t.taxa.size()));
+            out_.wave_tasks.push_back(static_cast<int32_t>(wave.size()));
+            out_.wave_max_n.push_back(max_n);
             next.clear();
             rc = process_wave(wave, next);
             for (Task &t : wave)
@@ -155,6 +165,54 @@ class Driver {
     }
 
   private:
+    // ---- sharding over ranks (one process per GPU) ----------------------------------------------------
+    // Sub-problems are independent (scs.py:139-166), so one job is spread over GPUs by giving each rank
+    // a share of the frontier.  Every rank runs the first waves redundantly -- the kernels are
+    // deterministic, so all ranks hold the same frontier and the same output prefix without talking --
+    // until the frontier is wide enough; then the frontier is dealt out (largest estimated cost first,
+    // to the least loaded rank) and each rank finishes only its own sub-problems.  The caller
+    // concatenates the ranks' outputs past the shared prefix (no collective on the data path).
+    static double task_cost(const Task &t) {
+        const double n = static_cast<double>(t.taxa.size());
+        return static_cast<double>(scs_forest_pair_visits(t.forest)) + 64.0 * n * n + 2.0e4;
+    }
+
+    bool should_partition(const std::vector<Task> &wave) const {
+        if (static_cast<int>(wave.size()) >= 8 * world_) return true;
+        // or: the frontier can already be balanced to within ~20 % of an even share
+        if (static_cast<int>(wave.size()) < world_) return false;
+        double total = 0.0, largest = 0.0;
+        for (const Task &t : wave) {
+            const double c = task_cost(t);
+            total += c;
+            largest = std::max(largest, c);
+        }
+        return largest <= 1.2 * total / world_;
+    }
+
+    void partition(std::vector<Task> &wave) {
+        partitioned_ = true;
+        out_.shared_prefix = static_cast<int64_t>(out_.parent.size());
+        std::vector<size_t> order(wave.size());
+        for (size_t i = 0; i < order.size(); ++i) order[i] = i;
+        std::vector<double> cost(wave.size());
+        for (size_t i = 0; i < wave.size(); ++i) cost[i] = task_cost(wave[i]);
+        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return cost[a] > cost[b]; });
+        std::vector<double> load(world_, 0.0);
+        std::vector<int> owner(wave.size(), 0);
+        for (size_t i : order) {
+            const int r = static_cast<int>(std::min_element(load.begin(), load.end()) - load.begin());
+            owner[i] = r;
+            load[r] += cost[i];
+        }
+        std::vector<Task> mine;
+        for (size_t i = 0; i < wave.size(); ++i) {
+            if (owner[i] == rank_) mine.push_back(std::move(wave[i]));
+            else if (wave[i].owned) scs_forest_destroy(wave[i].forest);
+        }
+        wave.swap(mine);
+    }
+
     int process_wave(std::vector<Task> &wave, std::vector<Task> &next) {
         std::vector<size_t> small;
         std::vector<SplitResult> results;
@@ -359,6 +417,8 @@ class Driver {
     int weighting_, contract_;
     uint64_t seed_;
     bool record_;
+    int rank_ = 0, world_ = 1;
+    bool partitioned_ = false;
     scs_supertree &out_;
     int num_taxa_ = 0;
     std::vector<int32_t> local_;
@@ -457,17 +517,48 @@ int scs_nodes_split_small_host(scs_ctx *ctx, int num_nodes, const scs_small_node
     return SCS_OK;
 }
 
-int scs_supertree_build(scs_ctx *ctx, const scs_forest *forest, int weighting, int contract_edges, uint64_t seed,
-                        int record_nodes, scs_supertree **out) {
-    if (!ctx || !forest || !out || weighting < 0 || weighting > 3) return SCS_ERR_INVALID;
+int scs_nodes_split_small_dev(scs_ctx *ctx, int num_nodes, const scs_small_node *nodes_dev,
+                              const int64_t *leaf_offsets_dev, const int32_t *leaf_taxon_dev,
+                              const int32_t *adj_depth_dev, const double *adj_val_dev, const int32_t *root_depth_dev,
+                              const double *tree_weight_dev, int contract_edges, int32_t *part_dev,
+                              scs_node_stats *stats_dev) {
+    if (!ctx || num_nodes < 0 || !nodes_dev || !part_dev || !stats_dev) return SCS_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    int32_t *bad_dev;
+    int rc;
+    if ((rc = reserve_as(ctx, SLOT_SCALARS, 64, &bad_dev))) return rc;
+    return small_batch(ctx, num_nodes, nodes_dev, leaf_offsets_dev, leaf_taxon_dev, adj_depth_dev, adj_val_dev,
+                       root_depth_dev, tree_weight_dev, contract_edges, part_dev, stats_dev, bad_dev);
+}
+
+int scs_supertree_build_sharded(scs_ctx *ctx, const scs_forest *forest, int weighting, int contract_edges,
+                                uint64_t seed, int record_nodes, int rank, int world, scs_supertree **out) {
+    if (!ctx || !forest || !out || weighting < 0 || weighting > 3 || world < 1 || rank < 0 || rank >= world)
+        return SCS_ERR_INVALID;
     *out = nullptr;
     cudaSetDevice(ctx->device);
     std::unique_ptr<scs_supertree> result(new scs_supertree());
-    Driver driver(ctx, weighting, contract_edges, seed, record_nodes != 0, result.get());
+    Driver driver(ctx, weighting, contract_edges, seed, record_nodes != 0, rank, world, result.get());
     int rc = driver.run(forest);
     if (rc) return rc;
+    if (world > 1 && result->shared_prefix == 0) result->shared_prefix = static_cast<int64_t>(result->parent.size());
     *out = result.release();
     return SCS_OK;
+}
+
+int scs_supertree_build(scs_ctx *ctx, const scs_forest *forest, int weighting, int contract_edges, uint64_t seed,
+                        int record_nodes, scs_supertree **out) {
+    return scs_supertree_build_sharded(ctx, forest, weighting, contract_edges, seed, record_nodes, 0, 1, out);
+}
+
+int64_t scs_supertree_shared_prefix(const scs_supertree *tree) { return tree ? tree->shared_prefix : 0; }
+
+int scs_supertree_wave_info(const scs_supertree *tree, int32_t *tasks, int32_t *max_n) {
+    if (!tree) return SCS_ERR_INVALID;
+    const size_t count = tree->wave_tasks.size();
+    if (tasks) std::memcpy(tasks, tree->wave_tasks.data(), sizeof(int32_t) * count);
+    if (max_n) std::memcpy(max_n, tree->wave_max_n.data(), sizeof(int32_t) * count);
+    return static_cast<int>(count);
 }
 
 int scs_supertree_destroy(scs_supertree *tree) {

@@ -171,14 +171,14 @@ class Engine:
 
     # -- the whole recursion, natively (csrc/driver.cu) --------------------------------------------
     def supertree_build(self, forest: "Forest", weighting: str, contract_edges: bool = True, seed: int = 0,
-                        record: bool = False) -> dict:
+                        record: bool = False, rank: int = 0, world: int = 1) -> dict:
         """``scs_supertree_build``: the supertree as flat arrays (``parent[i] < i``, ``taxon`` = global
         taxon id for tips, -1 otherwise), the driver's counters and, if ``record``, one
         ``(taxa, part, stats)`` per recursion node that reached the GPU."""
         handle = ctypes.c_void_p()
-        status = self._lib.scs_supertree_build(
+        status = self._lib.scs_supertree_build_sharded(
             self._ctx, forest.handle, WEIGHTINGS.index(weighting), int(bool(contract_edges)),
-            seed & 0xFFFFFFFFFFFFFFFF, int(bool(record)), ctypes.byref(handle),
+            seed & 0xFFFFFFFFFFFFFFFF, int(bool(record)), rank, world, ctypes.byref(handle),
         )  # fmt: skip
         if status == _lib.SCS_ERR_INPUT and weighting == "bootstrap":
             msg = "unsupported operand type(s) for *: 'NoneType' and 'float'"
@@ -197,8 +197,13 @@ class Engine:
                                              ctypes.byref(pairs))  # fmt: skip
             seconds = np.zeros(4)
             self._lib.scs_supertree_seconds(handle, ptr(seconds))
+            wave_tasks = np.zeros(max(waves.value, 1), dtype=np.int32)
+            wave_max_n = np.zeros(max(waves.value, 1), dtype=np.int32)
+            self._lib.scs_supertree_wave_info(handle, ptr(wave_tasks), ptr(wave_max_n))
             out = {"parent": parent, "taxon": taxon, "nodes_small": small.value, "nodes_large": large.value,
                    "waves": waves.value, "pair_visits": pairs.value, "records": [],
+                   "shared_prefix": int(self._lib.scs_supertree_shared_prefix(handle)),
+                   "wave_tasks": wave_tasks[: waves.value].tolist(), "wave_max_n": wave_max_n[: waves.value].tolist(),
                    "seconds": dict(zip(("large_nodes", "small_batches", "restrict", "tours"), seconds.tolist(), strict=True))}  # fmt: skip
             if record:
                 for i in range(self._lib.scs_supertree_num_records(handle)):
@@ -354,6 +359,34 @@ class Engine:
             out["Wc"] = self.to_host(Wc, (m, m), np.float64)
             out["group"] = self.to_host(group, (n,), np.int32)
         return out
+
+
+def merge_sharded(parts: list[tuple[np.ndarray, np.ndarray, int]]) -> tuple[np.ndarray, np.ndarray]:
+    """Join the outputs of ``supertree_build(rank=r, world=N)`` for r = 0..N-1.
+
+    ``parts[r] = (parent, taxon, shared_prefix)``.  Nodes ``[0, shared_prefix)`` are identical on
+    every rank; each rank's remaining nodes hang below its own sub-problems, so they are appended
+    with their parent indices shifted."""
+    parent0, taxon0, prefix = parts[0]
+    parents = [np.asarray(parent0, dtype=np.int32)]
+    taxa = [np.asarray(taxon0, dtype=np.int32)]
+    # a tip placed into a shared slot by its owner (a sub-problem that resolved to a single tip) must win
+    head_taxon = taxa[0][:prefix].copy()
+    offset = len(parent0)
+    for parent, taxon, p in parts[1:]:
+        if p != prefix:
+            msg = f"ranks disagree on the shared prefix ({p} != {prefix})"
+            raise ValueError(msg)
+        parent = np.asarray(parent, dtype=np.int32)
+        taxon = np.asarray(taxon, dtype=np.int32)
+        head_taxon = np.maximum(head_taxon, taxon[:prefix])
+        tail = parent[prefix:].copy()
+        tail[tail >= prefix] += offset - prefix
+        parents.append(tail)
+        taxa.append(taxon[prefix:])
+        offset += len(tail)
+    taxa[0] = np.concatenate([head_taxon, taxa[0][prefix:]])
+    return np.concatenate(parents), np.concatenate(taxa)
 
 
 _DEFAULT: Engine | None = None

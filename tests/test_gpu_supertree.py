@@ -188,3 +188,32 @@ def test_batched_small_nodes_are_bit_exact(engine):
     ref = load_case("s_300x40_branch_weighted")["nodes"]
     report = compare_with_reference_trace(fused, ref)
     assert report["compared"] >= 100
+
+
+@pytest.mark.parametrize(("name", "world"), [("c2_500x50_branch", 2), ("c2_500x50_branch", 4), ("supertriplets", 3)])
+def test_sharded_build_joins_to_the_same_supertree(engine, name, world):
+    """scs_supertree_build_sharded: the ranks' outputs (computed here one after the other on one GPU)
+    concatenate past the shared prefix into the supertree of the unsharded build."""
+    from spectralclustersupertree_b200.engine import Forest, merge_sharded
+    from spectralclustersupertree_b200.scs import _tree_from_flat
+
+    case = load_case(name)
+    trees = parse(case["lines"])
+    forest = Forest.from_trees(trees, case["weights"], case["names"])
+    whole = engine.supertree_build(forest, case["weighting"])
+    parts = []
+    nodes = 0
+    for rank in range(world):
+        built = engine.supertree_build(forest, case["weighting"], rank=rank, world=world)
+        parts.append((built["parent"], built["taxon"], built["shared_prefix"]))
+        nodes += built["nodes_small"] + built["nodes_large"]
+    assert len({p for _, _, p in parts}) == 1
+    parent, taxon = merge_sharded(parts)
+    assert len(parent) == len(whole["parent"])
+    assert (parent[1:] < np.arange(1, len(parent))).all()
+    a = _tree_from_flat(parent, taxon, case["names"])
+    b = _tree_from_flat(whole["parent"], whole["taxon"], case["names"])
+    assert sorted(a.get_tip_names()) == sorted(b.get_tip_names())
+    assert rf(a, b) == 0
+    # the replicated waves are solved by every rank, the rest exactly once
+    assert nodes >= whole["nodes_small"] + whole["nodes_large"]
