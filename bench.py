@@ -377,6 +377,11 @@ def gpu_line(args, arrays: dict) -> dict:
         dist = dist_mod
     engine = Engine(local_rank)
     weighting = arrays["weighting"]
+    # torchrun exports OMP_NUM_THREADS=1; give every rank its share of the host cores instead
+    from spectralclustersupertree_b200.engine import set_host_threads
+
+    host_threads = max(1, min(16, (os.cpu_count() or 1) // world))
+    set_host_threads(host_threads)
 
     def new_forest():
         return Forest.from_arrays(arrays["node_offsets"], arrays["parent"], arrays["length"], arrays["support"],
@@ -507,6 +512,7 @@ def gpu_line(args, arrays: dict) -> dict:
                       "partitions; for N > 1 the frontier is dealt out over the ranks and the outputs are "
                       "all-gathered)",
             "e2e_host_seconds": host_split,
+            "host_threads_per_rank": host_threads,
             "supertree_tips": tips,
             "job": job,
         },

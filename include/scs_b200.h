@@ -187,6 +187,9 @@ int scs_memcpy_d2h(scs_ctx *ctx, void *host, const void *dev, size_t bytes);
  * taxon[M] = global taxon id for tips (0..num_taxa-1), -1 for internal nodes.  Global taxon ids
  * are ranks in the sorted list of all tip names, so increasing id = sorted name order. */
 typedef struct scs_forest scs_forest;
+/* Host threads the forest operations and the recursion driver may use (process-wide; 0 = the OpenMP
+ * default, which launchers such as torchrun pin to 1 through OMP_NUM_THREADS). */
+int scs_set_host_threads(int threads);
 int scs_forest_create(int T, const int64_t *node_offsets, const int32_t *parent, const double *length,
                       const double *support, const int32_t *taxon, const double *tree_weight,
                       int num_taxa, scs_forest **out);

@@ -99,6 +99,7 @@ SIGNATURES: dict[str, tuple] = {
     "scs_dev_free": (c_int, [_P, _P]),
     "scs_memcpy_h2d": (c_int, [_P, _P, _P, c_size_t]),
     "scs_memcpy_d2h": (c_int, [_P, _P, _P, c_size_t]),
+    "scs_set_host_threads": (c_int, [c_int]),
     "scs_forest_create": (c_int, [c_int, _P, _P, _P, _P, _P, _P, c_int, POINTER(_P)]),
     "scs_forest_destroy": (c_int, [_P]),
     "scs_forest_num_trees": (c_int, [_P]),

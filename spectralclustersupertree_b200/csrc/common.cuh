@@ -45,6 +45,7 @@ enum Slot : int {
     // components / contraction
     SLOT_UF_PARENT,
     SLOT_LABEL,
+    SLOT_LABEL2,
     SLOT_GROUP,
     SLOT_GROUP_PTR,
     SLOT_GROUP_MEMBERS,
@@ -95,6 +96,7 @@ struct scs_ctx {
     int flush_value = 0;
     bool small_configured = false;
     bool batch_configured = false;
+    bool tail_configured = false;
     int small_limit = 64;  // nodes up to this size take the one-CTA path (0 disables it)
     double pending_units = 0.0;  // leaf-pair visits of the node being built (set by host entry points)
     cudaEvent_t timer_start = nullptr, timer_stop = nullptr;
@@ -170,8 +172,12 @@ int pcg_build(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offsets
 
 int components(scs_ctx *ctx, int n, const uint32_t *bits, int32_t *label, int32_t *n_components_host);
 
+int components_async(scs_ctx *ctx, int n, const uint32_t *bits, int32_t *label, int32_t *count_dev);
+
 int contract(scs_ctx *ctx, int n, const double *W, const uint32_t *adj_bits, const uint32_t *max_bits,
              int32_t *group, int32_t *m_host, double *Wc, double *degree_c);
+int contract_with_labels(scs_ctx *ctx, int n, const double *W, const uint32_t *adj_bits, const int32_t *label, int m,
+                         int32_t *group, double *Wc, double *degree_c);
 
 int spectral_bipartition(scs_ctx *ctx, int m, const double *W, const double *degree, uint64_t seed,
                          int32_t *side, scs_node_stats *stats_host);

@@ -82,21 +82,30 @@ __global__ void uf_flatten(int n, int32_t *parent, int32_t *label, int32_t *n_ro
 
 }  // namespace
 
-int components(scs_ctx *ctx, int n, const uint32_t *bits, int32_t *label, int32_t *n_components_host) {
-    if (n <= 0 || !bits || !label) return fail(ctx, SCS_ERR_INVALID, "components: bad argument");
+// Enqueue only: label[v] = smallest vertex of v's component, *count_dev = number of components.
+int components_async(scs_ctx *ctx, int n, const uint32_t *bits, int32_t *label, int32_t *count_dev) {
+    if (n <= 0 || !bits || !label || !count_dev) return fail(ctx, SCS_ERR_INVALID, "components: bad argument");
     const int words = scs_bit_words(n);
-    int32_t *parent, *scalars;
+    int32_t *parent;
     int rc;
+    // the union-find forest is built in `label` itself, then flattened in place
     if ((rc = reserve_as(ctx, SLOT_UF_PARENT, static_cast<size_t>(n), &parent))) return rc;
-    if ((rc = reserve_as(ctx, SLOT_SCALARS, 64, &scalars))) return rc;
-    int32_t *n_roots = scalars + 8;
-    SCS_CUDA(ctx, cudaMemsetAsync(n_roots, 0, sizeof(int32_t), ctx->stream));
+    SCS_CUDA(ctx, cudaMemsetAsync(count_dev, 0, sizeof(int32_t), ctx->stream));
     uf_init<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(n, parent);
     SCS_LAUNCHED(ctx, "uf_init");
     uf_hook_rows<<<ceil_div(static_cast<int64_t>(n) * 32, 256), 256, 0, ctx->stream>>>(n, words, bits, parent);
     SCS_LAUNCHED(ctx, "uf_hook_rows");
-    uf_flatten<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(n, parent, label, n_roots);
+    uf_flatten<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(n, parent, label, count_dev);
     SCS_LAUNCHED(ctx, "uf_flatten");
+    return SCS_OK;
+}
+
+int components(scs_ctx *ctx, int n, const uint32_t *bits, int32_t *label, int32_t *n_components_host) {
+    int32_t *scalars;
+    int rc;
+    if ((rc = reserve_as(ctx, SLOT_SCALARS, 64, &scalars))) return rc;
+    int32_t *n_roots = scalars + 8;
+    if ((rc = components_async(ctx, n, bits, label, n_roots))) return rc;
     if (n_components_host) {
         void *pin;
         if ((rc = reserve_pinned(ctx, 64, &pin))) return rc;

@@ -180,12 +180,19 @@ int node_split(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offset
         return SCS_OK;
     }
 
-    // malformed tours are flagged by the index kernel (scalars[0]); read together with the count
-    int ncomp = 0;
-    if ((rc = components(ctx, n, adj_bits, label, &ncomp))) return rc;
-    SCS_CUDA(ctx, cudaMemcpyAsync(pin + 256, scalars, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    // components of the graph and (speculatively) of the max-graph, then ONE round trip for: the
+    // malformed-tour flag of the index kernel (scalars[0]), both component counts
+    int32_t *label2 = nullptr;
+    if ((rc = components_async(ctx, n, adj_bits, label, scalars + 8))) return rc;
+    if (contract_edges) {
+        if ((rc = reserve_as(ctx, SLOT_LABEL2, static_cast<size_t>(n), &label2))) return rc;
+        if ((rc = components_async(ctx, n, max_bits, label2, scalars + 9))) return rc;
+    }
+    SCS_CUDA(ctx, cudaMemcpyAsync(pin + 256, scalars, 16 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     SCS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (*reinterpret_cast<int32_t *>(pin + 256) != 0) return fail(ctx, SCS_ERR_INPUT, "leaf tour: taxon id out of range");
+    const int32_t *host_scalars = reinterpret_cast<const int32_t *>(pin + 256);
+    if (host_scalars[0] != 0) return fail(ctx, SCS_ERR_INPUT, "leaf tour: taxon id out of range");
+    const int ncomp = host_scalars[8];
     stats->n_components = ncomp;
     stats->contracted_size = n;
     const int blocks = ceil_div(n, 256);
@@ -210,10 +217,11 @@ int node_split(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offset
     const double *deg_m = degree;
     const int32_t *group_m = nullptr;
     if (contract_edges) {
+        m = host_scalars[9];
         if ((rc = reserve_as(ctx, SLOT_WC, nn, &Wc))) return rc;
         if ((rc = reserve_as(ctx, SLOT_DEGREE_C, static_cast<size_t>(n), &degree_c))) return rc;
         if ((rc = reserve_as(ctx, SLOT_GROUP, static_cast<size_t>(n), &group))) return rc;
-        if ((rc = contract(ctx, n, W, adj_bits, max_bits, group, &m, Wc, degree_c))) return rc;
+        if ((rc = contract_with_labels(ctx, n, W, adj_bits, label2, m, group, Wc, degree_c))) return rc;
         if (m != n) {
             Wm = Wc;
             deg_m = degree_c;

@@ -96,17 +96,12 @@ __global__ void sum_parts(int m, int nchunks, const double *__restrict__ part, d
 
 }  // namespace
 
-int contract(scs_ctx *ctx, int n, const double *W, const uint32_t *adj_bits, const uint32_t *max_bits,
-             int32_t *group, int32_t *m_host, double *Wc, double *degree_c) {
-    if (n <= 0 || !W || !adj_bits || !max_bits || !group || !m_host || !Wc)
-        return fail(ctx, SCS_ERR_INVALID, "contract: bad argument");
+// The merge itself, given the max-graph component labels (label[v] = smallest member) and their number m.
+int contract_with_labels(scs_ctx *ctx, int n, const double *W, const uint32_t *adj_bits, const int32_t *label, int m,
+                         int32_t *group, double *Wc, double *degree_c) {
     const int words = scs_bit_words(n);
-    int32_t *label, *flags, *rank, *gptr, *cursor, *members;
+    int32_t *flags, *rank, *gptr, *cursor, *members;
     int rc;
-    if ((rc = reserve_as(ctx, SLOT_LABEL, static_cast<size_t>(n), &label))) return rc;
-    int m = 0;
-    if ((rc = components(ctx, n, max_bits, label, &m))) return rc;  // synchronises: m is known
-    *m_host = m;
     // scratch: flags[n] | rank[n+1] | gptr[n+1] | cursor[n]
     if ((rc = reserve_as(ctx, SLOT_GROUP_PTR, 4 * static_cast<size_t>(n) + 8, &flags))) return rc;
     rank = flags + n;
@@ -117,7 +112,7 @@ int contract(scs_ctx *ctx, int n, const double *W, const uint32_t *adj_bits, con
     mark_representatives<<<blocks, 256, 0, ctx->stream>>>(n, label, flags);
     SCS_LAUNCHED(ctx, "mark_representatives");
     if ((rc = exclusive_scan(ctx, n, flags, rank))) return rc;
-    // group sizes reuse `flags` (m <= n entries), then become offsets in gptr
+    // group sizes go to `cursor` (m <= n entries), then become offsets in gptr
     SCS_CUDA(ctx, cudaMemsetAsync(cursor, 0, sizeof(int32_t) * n, ctx->stream));
     assign_groups<<<blocks, 256, 0, ctx->stream>>>(n, label, rank, group, cursor);
     SCS_LAUNCHED(ctx, "assign_groups");
@@ -144,6 +139,19 @@ int contract(scs_ctx *ctx, int n, const double *W, const uint32_t *adj_bits, con
         SCS_LAUNCHED(ctx, "sum_parts");
     }
     return SCS_OK;
+}
+
+int contract(scs_ctx *ctx, int n, const double *W, const uint32_t *adj_bits, const uint32_t *max_bits,
+             int32_t *group, int32_t *m_host, double *Wc, double *degree_c) {
+    if (n <= 0 || !W || !adj_bits || !max_bits || !group || !m_host || !Wc)
+        return fail(ctx, SCS_ERR_INVALID, "contract: bad argument");
+    int32_t *label;
+    int rc;
+    if ((rc = reserve_as(ctx, SLOT_LABEL2, static_cast<size_t>(n), &label))) return rc;
+    int m = 0;
+    if ((rc = components(ctx, n, max_bits, label, &m))) return rc;  // synchronises: m is known
+    *m_host = m;
+    return contract_with_labels(ctx, n, W, adj_bits, label, m, group, Wc, degree_c);
 }
 
 }  // namespace scs

@@ -137,7 +137,7 @@ class Driver {
     int run(const scs_forest *root) {
         num_taxa_ = scs_forest_num_taxa(root);
         local_.assign(num_taxa_ > 0 ? num_taxa_ : 1, -1);
-        scratch_.resize(static_cast<size_t>(omp_get_max_threads()));
+        scratch_.resize(static_cast<size_t>(scs_host_threads()));
         for (Scratch &sc : scratch_) sc.reset(num_taxa_);
         std::vector<Task> wave, next;
         const int32_t root_slot = add_node(out_, -1, -1);
@@ -245,7 +245,7 @@ class Driver {
         {
             Stopwatch sw(&out_.seconds[2]);
             const int count = static_cast<int>(results.size());
-#pragma omp parallel for schedule(dynamic, 1) if (count >= 8)
+#pragma omp parallel for schedule(dynamic, 1) if (count >= 8) num_threads(scs_host_threads())
             for (int r = 0; r < count; ++r)
                 plan(wave[results[r].task], results[r], scratch_[static_cast<size_t>(omp_get_thread_num())]);
         }

@@ -24,6 +24,12 @@
 
 #include "forest.hpp"
 
+#include <omp.h>
+
+static int g_host_threads = 0;
+
+int scs_host_threads() { return g_host_threads > 0 ? g_host_threads : omp_get_max_threads(); }
+
 namespace {
 
 constexpr int64_t kParallelNodes = 1 << 15;  // forests with more nodes are processed by all host threads
@@ -43,6 +49,12 @@ void finish_tree(scs_forest &f, int64_t base, int64_t count) {
 }  // namespace
 
 extern "C" {
+
+int scs_set_host_threads(int threads) {
+    if (threads < 0) return SCS_ERR_INVALID;
+    g_host_threads = threads;
+    return SCS_OK;
+}
 
 int scs_forest_create(int T, const int64_t *node_offsets, const int32_t *parent, const double *length,
                       const double *support, const int32_t *taxon, const double *tree_weight, int num_taxa,
@@ -138,7 +150,7 @@ int scs_forest_induce(const scs_forest *f, const uint8_t *keep, scs_forest **out
     std::vector<int32_t> new_index(M > 0 ? M : 1);
     std::vector<int32_t> kept_nodes(T + 1, 0), kept_tips(T + 1, 0);
     const bool threaded = M > kParallelNodes;
-#pragma omp parallel if (threaded)
+#pragma omp parallel if (threaded) num_threads(scs_host_threads())
     {
         std::vector<int32_t> cnt, live_children;
 #pragma omp for schedule(dynamic, 4)
@@ -185,7 +197,7 @@ int scs_forest_induce(const scs_forest *f, const uint8_t *keep, scs_forest **out
     g->support.resize(M_out);
     g->taxon.resize(M_out);
     // pass 2 (trees in parallel): write the restricted trees
-#pragma omp parallel for schedule(dynamic, 4) if (threaded)
+#pragma omp parallel for schedule(dynamic, 4) if (threaded) num_threads(scs_host_threads())
     for (int t = 0; t < T; ++t) {
         if (kept_nodes[t] == 0) continue;
         const int64_t base = f->node_offsets[t], count = f->node_offsets[t + 1] - base;
@@ -233,7 +245,7 @@ int scs_forest_tours(const scs_forest *f, int weighting, const int32_t *local_id
     int status = SCS_OK;
     leaf_offsets[0] = 0;
     const bool threaded = f->node_offsets.back() > kParallelNodes;
-#pragma omp parallel if (threaded)
+#pragma omp parallel if (threaded) num_threads(scs_host_threads())
     {
         std::vector<int32_t> depth;
         std::vector<double> val;

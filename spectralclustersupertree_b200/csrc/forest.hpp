@@ -17,3 +17,6 @@ struct scs_forest {
     int num_trees() const { return static_cast<int>(weight.size()); }
 };
 
+
+// Host threads used by the forest operations and the recursion driver (0 = OpenMP's default).
+int scs_host_threads();

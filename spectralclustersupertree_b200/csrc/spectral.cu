@@ -20,6 +20,7 @@
 
 #include "common.cuh"
 
+#include <algorithm>
 #include <cmath>
 
 namespace scs {
@@ -160,8 +161,9 @@ __device__ __forceinline__ double row_dot_partial(const double *__restrict__ row
 // one CTA per row (m large: a row is tens of KB)
 __global__ void __launch_bounds__(kMvThreads)
 matvec_row_per_cta(int m, const double *__restrict__ W, const double *__restrict__ isd,
-                   const double *__restrict__ z, double *__restrict__ y) {
+                   const double *__restrict__ z, double *__restrict__ y, const int32_t *__restrict__ done) {
     __shared__ double part[kMvThreads / 32];
+    if (done && *done) return;
     const int row = blockIdx.x;
     double acc = row_dot_partial(W + static_cast<size_t>(row) * m, z, m, threadIdx.x, kMvThreads);
     acc = warp_sum(acc);
@@ -178,25 +180,26 @@ matvec_row_per_cta(int m, const double *__restrict__ W, const double *__restrict
 // one warp per row (m small: the whole matrix is L2-resident and rows are short)
 __global__ void __launch_bounds__(kMvThreads)
 matvec_row_per_warp(int m, const double *__restrict__ W, const double *__restrict__ isd,
-                    const double *__restrict__ z, double *__restrict__ y) {
+                    const double *__restrict__ z, double *__restrict__ y, const int32_t *__restrict__ done) {
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (row >= m) return;
+    if (row >= m || (done && *done)) return;
     double acc = row_dot_partial(W + static_cast<size_t>(row) * m, z, m, lane, 32);
     acc = warp_sum(acc);
     if (lane == 0) y[row] = isd[row] * acc;
 }
 
-int launch_matvec(scs_ctx *ctx, int m, const double *W, const double *isd, const double *z, double *y) {
+int launch_matvec(scs_ctx *ctx, int m, const double *W, const double *isd, const double *z, double *y,
+                  const int32_t *done = nullptr) {
     if (m >= 2048) {
         // algorithmic bytes: W once + read z, isd, write y
         if (m >= kProfileMinSize) profile_begin(ctx, PROFILE_MATVEC, 8.0 * m * m + 24.0 * m, 2.0 * m * m);
-        matvec_row_per_cta<<<m, kMvThreads, 0, ctx->stream>>>(m, W, isd, z, y);
+        matvec_row_per_cta<<<m, kMvThreads, 0, ctx->stream>>>(m, W, isd, z, y, done);
         if (m >= kProfileMinSize) profile_end(ctx);
         SCS_LAUNCHED(ctx, "matvec_row_per_cta");
     } else {
         matvec_row_per_warp<<<ceil_div(static_cast<int64_t>(m) * 32, kMvThreads), kMvThreads, 0, ctx->stream>>>(
-            m, W, isd, z, y);
+            m, W, isd, z, y, done);
         SCS_LAUNCHED(ctx, "matvec_row_per_warp");
     }
     return SCS_OK;
@@ -287,10 +290,10 @@ __device__ __forceinline__ int sturm_count(const double *a, const double *b2, in
     return cnt;  // number of eigenvalues below x
 }
 
-__global__ void __launch_bounds__(256)
-tridiag_ritz(int jrun, const double *__restrict__ alpha, const double *__restrict__ beta,
-             const int32_t *__restrict__ state, double *__restrict__ coef, double *__restrict__ out) {
-    extern __shared__ double sm[];
+// All threads of the CTA take part.  sm: 5 (jrun + 2) doubles, counts: blockDim.x ints, pair: 4 doubles.
+// (No __restrict__ here: the fused tail writes alpha / beta / state in the same launch that reads them.)
+__device__ void tridiag_solve(int jrun, const double *alpha, const double *beta, const int32_t *state, double *coef,
+                              double *out, double *sm, int *counts, double *pair) {
     const int latched = state[0];
     const int j = latched > 0 && latched < jrun ? latched : jrun;
     double *a = sm;                 // [j + 2], 1-based
@@ -298,10 +301,9 @@ tridiag_ritz(int jrun, const double *__restrict__ alpha, const double *__restric
     double *b2 = b + (j + 2);       // squares
     double *dplus = b2 + (j + 2);
     double *dminus = dplus + (j + 2);
-    __shared__ int counts[256];
-    __shared__ double bounds[2];
-    __shared__ double theta[2];
+    double *bounds = pair, *theta = pair + 2;
     const int tid = threadIdx.x, P = blockDim.x;
+    __syncthreads();  // sm / counts may still be in use by the caller
     for (int i = tid + 1; i <= j; i += P) {
         a[i] = alpha[i];
         b[i] = beta[i];
@@ -407,6 +409,93 @@ tridiag_ritz(int jrun, const double *__restrict__ alpha, const double *__restric
         out[1] = j >= 2 ? theta[1] : nan("");
         out[2] = fabs(b[j] * b2[j] * inv);
         out[3] = b[j];
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+tridiag_ritz(int jrun, const double *__restrict__ alpha, const double *__restrict__ beta,
+             const int32_t *__restrict__ state, double *__restrict__ coef, double *__restrict__ out) {
+    extern __shared__ double sm[];
+    __shared__ int counts[256];
+    __shared__ double pair[4];
+    tridiag_solve(jrun, alpha, beta, state, coef, out, sm, counts, pair);
+}
+
+// ---- fused Lanczos step tail (m <= kFusedMax) -----------------------------------------------------
+// Everything of a Lanczos step except the operator application, in one single-CTA launch: both
+// Gram-Schmidt passes against the nb leading basis vectors, the norm, the next basis vector and its
+// scaled copy, and -- at check steps -- the projected eigenproblem, whose verdict is latched in
+// state[1] so that the launches already queued behind it (matvec and tail both test the flag) fall
+// through.  The host therefore synchronises once per chunk of steps instead of once per check.
+// state: [0] breakdown step, [1] done, [2] step at which done was raised.
+constexpr int kFusedMax = 4096;
+constexpr int kFusedPerThread = kFusedMax / kOneCta;
+
+__global__ void __launch_bounds__(kOneCta)
+lanczos_tail(int m, int j, int nb, int hj, int check, const double *basis, const double *__restrict__ w_in,
+             const double *__restrict__ isd, double *alpha, double *beta, double *next, double *__restrict__ z,
+             int32_t *state, double *coef, double *ritz) {
+    extern __shared__ double dyn[];
+    double *w = dyn;                      // [m]
+    double *h = w + m;                    // [nb] coefficients of one pass
+    double *tri = h + (kMaxBasis + 8);    // 5 (j + 2) doubles for the projected problem
+    __shared__ double scratch[33];
+    __shared__ int counts[kOneCta];
+    __shared__ double pair[4];
+    if (state[1]) return;  // converged earlier in this chunk
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < m; i += kOneCta) w[i] = w_in[i];
+    __syncthreads();
+    double hkeep = 0.0;  // coefficient along v_j summed over both passes (thread 0 of warp owning it)
+    for (int pass = 0; pass < 2; ++pass) {
+        // h[k] = basis[k] . w : one warp per basis vector
+        for (int k = warp; k < nb; k += kOneCta / 32) {
+            const double *b = basis + static_cast<size_t>(k) * m;
+            double acc = 0.0;
+            for (int i = lane; i < m; i += 32) acc = fma(b[i], w[i], acc);
+            acc = warp_sum(acc);
+            if (lane == 0) h[k] = acc;
+        }
+        __syncthreads();
+        if (tid == 0 && j > 0) hkeep += h[hj];
+        // w -= sum_k h[k] basis[k]
+        for (int i = tid; i < m; i += kOneCta) {
+            double acc = w[i];
+            for (int k = 0; k < nb; ++k) acc = fma(-h[k], basis[static_cast<size_t>(k) * m + i], acc);
+            w[i] = acc;
+        }
+        __syncthreads();
+    }
+    double ss = 0.0;
+    for (int i = tid; i < m; i += kOneCta) ss = fma(w[i], w[i], ss);
+    ss = block_sum(ss, scratch);
+    const double bnorm = sqrt(ss);
+    if (tid == 0) {
+        beta[j] = bnorm;
+        if (j > 0) {
+            alpha[j] = hkeep;
+            if (bnorm <= kBreakdown && state[0] == 0) state[0] = j;
+        } else {
+            state[0] = 0;
+        }
+    }
+    const double inv = bnorm > 0.0 ? 1.0 / bnorm : 0.0;
+    for (int i = tid; i < m; i += kOneCta) {
+        const double v = w[i] * inv;
+        next[i] = v;
+        z[i] = isd[i] * v;
+    }
+    __syncthreads();  // alpha / beta / state written by thread 0 are read below
+    if (check && j > 0) {
+        tridiag_solve(j, alpha, beta, state, coef, ritz, tri, counts, pair);
+        if (tid == 0) {
+            ritz[5] = static_cast<double>(j);
+            if (ritz[3] <= kBreakdown || ritz[2] <= kResidualTol) {
+                state[1] = 1;
+                state[2] = j;
+            }
+        }
     }
 }
 
@@ -695,6 +784,13 @@ int lanczos_largest(scs_ctx *ctx, int m, const double *W, const LanczosBuffers &
     };
     int rc;
     int jdone = 0;
+    const bool fused = m <= kFusedMax;
+    if (fused && !ctx->tail_configured) {
+        SCS_CUDA(ctx, cudaFuncSetAttribute(lanczos_tail, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>((kFusedMax + 6 * (kMaxBasis + 8)) * sizeof(double))));
+        ctx->tail_configured = true;
+    }
+    const size_t tail_smem = (static_cast<size_t>(m) + 6 * (kMaxBasis + 8)) * sizeof(double);
     for (int attempt = 0; attempt <= kMaxRestarts && !out->converged; ++attempt) {
         if (attempt == 0) {
             random_start<<<vec_blocks, kVecThreads, 0, ctx->stream>>>(m, seed, b.w);
@@ -704,39 +800,80 @@ int lanczos_largest(scs_ctx *ctx, int m, const double *W, const LanczosBuffers &
             SCS_CUDA(ctx, cudaMemcpyAsync(b.w, y, sizeof(double) * m, cudaMemcpyDeviceToDevice, ctx->stream));
             out->restarts = attempt;
         }
-        if ((rc = orthogonalise(ndefl, b.h1))) return rc;
-        if ((rc = orthogonalise(ndefl, b.h2))) return rc;
-        normalize_step<<<1, kOneCta, 0, ctx->stream>>>(m, 0, 0, b.w, b.isd, b.h1, b.h2, b.alpha, b.beta, v0 + m, b.z,
-                                                       b.state);
-        SCS_LAUNCHED(ctx, "normalize_step");
-        for (int j = 1; j <= jmax; ++j) {
-            if ((rc = launch_matvec(ctx, m, W, b.isd, b.z, b.w))) return rc;
-            out->matvecs += 1;
-            if ((rc = orthogonalise(ndefl + j, b.h1))) return rc;
-            if ((rc = orthogonalise(ndefl + j, b.h2))) return rc;
-            normalize_step<<<1, kOneCta, 0, ctx->stream>>>(m, j, ndefl - 1 + j, b.w, b.isd, b.h1, b.h2, b.alpha, b.beta,
-                                                           v0 + static_cast<size_t>(j + 1) * m, b.z, b.state);
-            SCS_LAUNCHED(ctx, "normalize_step");
-            jdone = j;
-            const bool check = j == jmax || (j % 4) == 0;
-            if (!check) continue;
-            tridiag_ritz<<<1, 256, 5 * (j + 2) * sizeof(double), ctx->stream>>>(j, b.alpha, b.beta, b.state, b.coef,
-                                                                               b.ritz);
-            SCS_LAUNCHED(ctx, "tridiag_ritz");
-            SCS_CUDA(ctx, cudaMemcpyAsync(b.pin, b.ritz, 5 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-            SCS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            out->theta1 = b.pin[0];
-            out->theta2 = b.pin[1];
-            out->estimate = b.pin[2];
-            out->steps = static_cast<int>(b.pin[4]);
-            if (b.pin[3] <= kBreakdown) {
-                out->converged = true;
-                out->invariant = true;
-                break;
+        if (fused) {
+            SCS_CUDA(ctx, cudaMemsetAsync(b.state, 0, 4 * sizeof(int32_t), ctx->stream));
+            lanczos_tail<<<1, kOneCta, tail_smem, ctx->stream>>>(m, 0, ndefl, 0, 0, b.basis, b.w, b.isd, b.alpha, b.beta,
+                                                                v0 + m, b.z, b.state, b.coef, b.ritz);
+            SCS_LAUNCHED(ctx, "lanczos_tail");
+            // steps are queued a chunk at a time; the tail of a check step latches convergence on the
+            // device and everything queued behind it falls through
+            int j = 1;
+            int attempt_matvecs = 0;
+            bool done = false;
+            while (j <= jmax && !done) {
+                const int chunk_end = std::min(jmax, j == 1 ? 23 : j + 7);
+                for (; j <= chunk_end; ++j) {
+                    if ((rc = launch_matvec(ctx, m, W, b.isd, b.z, b.w, b.state + 1))) return rc;
+                    const int check = j == jmax || (j % 4) == 0;
+                    lanczos_tail<<<1, kOneCta, tail_smem, ctx->stream>>>(
+                        m, j, ndefl + j, ndefl - 1 + j, check, b.basis, b.w, b.isd, b.alpha, b.beta,
+                        v0 + static_cast<size_t>(j + 1) * m, b.z, b.state, b.coef, b.ritz);
+                    SCS_LAUNCHED(ctx, "lanczos_tail");
+                }
+                SCS_CUDA(ctx, cudaMemcpyAsync(b.pin, b.ritz, 6 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+                SCS_CUDA(ctx, cudaMemcpyAsync(b.pin + 6, b.state, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+                SCS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                const int32_t *st = reinterpret_cast<const int32_t *>(b.pin + 6);
+                out->theta1 = b.pin[0];
+                out->theta2 = b.pin[1];
+                out->estimate = b.pin[2];
+                out->steps = static_cast<int>(b.pin[4]);
+                jdone = static_cast<int>(b.pin[5]);  // the step of the last check that ran
+                if (st[1]) {
+                    done = true;
+                    out->converged = true;
+                    out->invariant = b.pin[3] <= kBreakdown;
+                    attempt_matvecs = st[2];  // steps actually applied before the flag went up
+                } else {
+                    attempt_matvecs = chunk_end;
+                }
             }
-            if (out->estimate <= kResidualTol) {
-                out->converged = true;
-                break;
+            out->matvecs += attempt_matvecs;
+        } else {
+            if ((rc = orthogonalise(ndefl, b.h1))) return rc;
+            if ((rc = orthogonalise(ndefl, b.h2))) return rc;
+            normalize_step<<<1, kOneCta, 0, ctx->stream>>>(m, 0, 0, b.w, b.isd, b.h1, b.h2, b.alpha, b.beta, v0 + m, b.z,
+                                                           b.state);
+            SCS_LAUNCHED(ctx, "normalize_step");
+            for (int j = 1; j <= jmax; ++j) {
+                if ((rc = launch_matvec(ctx, m, W, b.isd, b.z, b.w))) return rc;
+                out->matvecs += 1;
+                if ((rc = orthogonalise(ndefl + j, b.h1))) return rc;
+                if ((rc = orthogonalise(ndefl + j, b.h2))) return rc;
+                normalize_step<<<1, kOneCta, 0, ctx->stream>>>(m, j, ndefl - 1 + j, b.w, b.isd, b.h1, b.h2, b.alpha,
+                                                               b.beta, v0 + static_cast<size_t>(j + 1) * m, b.z, b.state);
+                SCS_LAUNCHED(ctx, "normalize_step");
+                jdone = j;
+                const bool check = j == jmax || (j % 4) == 0;
+                if (!check) continue;
+                tridiag_ritz<<<1, 256, 5 * (j + 2) * sizeof(double), ctx->stream>>>(j, b.alpha, b.beta, b.state, b.coef,
+                                                                                   b.ritz);
+                SCS_LAUNCHED(ctx, "tridiag_ritz");
+                SCS_CUDA(ctx, cudaMemcpyAsync(b.pin, b.ritz, 5 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+                SCS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                out->theta1 = b.pin[0];
+                out->theta2 = b.pin[1];
+                out->estimate = b.pin[2];
+                out->steps = static_cast<int>(b.pin[4]);
+                if (b.pin[3] <= kBreakdown) {
+                    out->converged = true;
+                    out->invariant = true;
+                    break;
+                }
+                if (out->estimate <= kResidualTol) {
+                    out->converged = true;
+                    break;
+                }
             }
         }
         // Ritz vector of the current basis (also the restart vector); coefficients past a breakdown are 0

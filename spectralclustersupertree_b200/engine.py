@@ -389,6 +389,13 @@ def merge_sharded(parts: list[tuple[np.ndarray, np.ndarray, int]]) -> tuple[np.n
     return np.concatenate(parents), np.concatenate(taxa)
 
 
+def set_host_threads(threads: int) -> None:
+    """Host threads for tree restriction / flattening / the recursion driver (0 = OpenMP default)."""
+    status = _lib.load().scs_set_host_threads(int(threads))
+    if status != _lib.SCS_OK:
+        raise ScsError(status, "scs_set_host_threads")
+
+
 _DEFAULT: Engine | None = None
 
 
