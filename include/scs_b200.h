@@ -92,6 +92,10 @@ int scs_ctx_timer_stop(scs_ctx *ctx, double *ms);
  * and the spectral split in one single-CTA launch (dense Jacobi); larger ones take the staged path
  * (union-find, max-merge, Lanczos).  0 sends every node down the staged path. */
 int scs_ctx_set_small_node_limit(scs_ctx *ctx, int limit);
+/* Host wall clock spent per stage of the staged (> 64 vertices) node path since the last reset:
+ * [0] enqueue graph build + components, [1] wait for them, [2] enqueue contraction, [3] spectral step,
+ * [4] result copy, [5] Lanczos iterations within [3]. */
+int scs_ctx_stage_seconds(scs_ctx *ctx, double *seconds8, int reset);
 /* Evict the L2 cache by writing a 256 MB scratch buffer (benchmark hygiene between timed steps). */
 int scs_ctx_flush_l2(scs_ctx *ctx);
 /* Per-launch CUDA-event timing of the two heavy kernels on matrices of >= 2048 vertices:

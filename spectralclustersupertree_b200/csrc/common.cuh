@@ -94,6 +94,7 @@ struct scs_ctx {
     };
     std::vector<ProfileRecord> profile;
     int flush_value = 0;
+    double stage_seconds[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // host wall clock per stage of the staged node path
     bool small_configured = false;
     bool batch_configured = false;
     bool tail_configured = false;

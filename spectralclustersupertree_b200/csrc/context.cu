@@ -7,6 +7,7 @@
 
 #include "common.cuh"
 
+#include <chrono>
 #include <cmath>
 
 namespace scs {
@@ -154,6 +155,13 @@ int node_split(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offset
         return SCS_OK;
     };
 
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto lap = [&](int slot, std::chrono::steady_clock::time_point &since) {
+        const auto t = now();
+        ctx->stage_seconds[slot] += std::chrono::duration<double>(t - since).count();
+        since = t;
+    };
+    auto mark = now();
     if ((rc = pcg_build(ctx, n, T, L, leaf_offsets, leaf_taxon, adj_depth, adj_val, root_depth, tree_weight, W,
                         nullptr, occ, adj_bits, contract_edges ? max_bits : nullptr, degree)))
         return rc;
@@ -189,7 +197,9 @@ int node_split(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offset
         if ((rc = components_async(ctx, n, max_bits, label2, scalars + 9))) return rc;
     }
     SCS_CUDA(ctx, cudaMemcpyAsync(pin + 256, scalars, 16 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    lap(0, mark);  // enqueue of graph build + both component passes
     SCS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    lap(1, mark);  // their execution
     const int32_t *host_scalars = reinterpret_cast<const int32_t *>(pin + 256);
     if (host_scalars[0] != 0) return fail(ctx, SCS_ERR_INPUT, "leaf tour: taxon id out of range");
     const int ncomp = host_scalars[8];
@@ -237,11 +247,14 @@ int node_split(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offset
         // it raises (ensure_min_samples=2, _spectral.py:699)
         return fail(ctx, SCS_ERR_TOO_SMALL, "spectral step on a graph contracted to one vertex");
     }
+    lap(2, mark);  // enqueue of the contraction
     if ((rc = spectral_bipartition(ctx, m, Wm, deg_m, seed, side, stats))) return rc;
+    lap(3, mark);  // spectral step (contraction execution included)
     expand_sides<<<blocks, 256, 0, ctx->stream>>>(n, group_m, side, part_dev);
     SCS_LAUNCHED(ctx, "expand_sides");
     if ((rc = fetch_part())) return rc;
     if (part_host) SCS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    lap(4, mark);  // result copy
     return SCS_OK;
 }
 
@@ -363,6 +376,15 @@ int scs_ctx_timer_stop(scs_ctx *ctx, double *ms) {
 int scs_ctx_set_small_node_limit(scs_ctx *ctx, int limit) {
     if (!ctx || limit < 0) return SCS_ERR_INVALID;
     ctx->small_limit = limit > kSmallNode ? kSmallNode : limit;
+    return SCS_OK;
+}
+
+int scs_ctx_stage_seconds(scs_ctx *ctx, double *seconds8, int reset) {
+    if (!ctx || !seconds8) return SCS_ERR_INVALID;
+    for (int i = 0; i < 8; ++i) {
+        seconds8[i] = ctx->stage_seconds[i];
+        if (reset) ctx->stage_seconds[i] = 0.0;
+    }
     return SCS_OK;
 }
 

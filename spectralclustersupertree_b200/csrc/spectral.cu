@@ -21,6 +21,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 
 namespace scs {
@@ -938,7 +939,9 @@ int spectral_bipartition(scs_ctx *ctx, int m, const double *W, const double *deg
 
     stats->solver = 3;
     LanczosOutcome first;
+    const auto t_lanczos = std::chrono::steady_clock::now();
     if ((rc = lanczos_largest(ctx, m, W, b, 1, seed, yvec, &first))) return rc;
+    ctx->stage_seconds[5] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_lanczos).count();
     stats->matvecs = first.matvecs;
     stats->restarts = first.restarts;
 

@@ -100,6 +100,13 @@ class Engine:
         """Largest recursion node (vertices) that takes the one-CTA path; 0 forces the staged path."""
         _check(self._lib.scs_ctx_set_small_node_limit(self._ctx, limit), self._ctx)
 
+    def stage_seconds(self, reset: bool = True) -> dict:
+        """Host wall clock per stage of the staged node path (``scs_ctx_stage_seconds``)."""
+        out = np.zeros(8)
+        _check(self._lib.scs_ctx_stage_seconds(self._ctx, ptr(out), int(reset)), self._ctx)
+        keys = ("enqueue_graph", "wait_graph", "enqueue_contract", "spectral", "result_copy", "lanczos_in_spectral")
+        return dict(zip(keys, out[:6].tolist(), strict=True))
+
     def flush_l2(self) -> None:
         _check(self._lib.scs_ctx_flush_l2(self._ctx), self._ctx)
 

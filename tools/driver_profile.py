@@ -23,7 +23,9 @@ def main() -> None:
                                     a["weights"], a["names"])  # fmt: skip
         t1 = time.perf_counter()
         launches = engine.launch_count
+        engine.stage_seconds(reset=True)
         built = engine.supertree_build(forest, a["weighting"])
+        stages = engine.stage_seconds(reset=True)
         t2 = time.perf_counter()
         sec = built["seconds"]
         other = (t2 - t1) - sum(sec.values())
@@ -31,6 +33,7 @@ def main() -> None:
               ", ".join(f"{k} {v:.3f}" for k, v in sec.items()) + f", other {other:.3f}; "
               f"small {built['nodes_small']} large {built['nodes_large']} waves {built['waves']} "
               f"launches {engine.launch_count - launches}")
+        print("   staged path: " + ", ".join(f"{k} {v:.3f}" for k, v in stages.items()))
 
 
 if __name__ == "__main__":
