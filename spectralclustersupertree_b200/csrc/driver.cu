@@ -95,10 +95,6 @@ struct Scratch {
     }
 };
 
-struct ForestDeleter {
-    void operator()(scs_forest *f) const { scs_forest_destroy(f); }
-};
-
 int32_t add_node(scs_supertree &out, int32_t parent, int32_t taxon) {
     out.parent.push_back(parent);
     out.taxon.push_back(taxon);

@@ -3,26 +3,28 @@
 // Replaces _proper_cluster_graph_edges + _dfs_pcg_weights of the reference
 // (/root/reference/src/sc_supertree/scs.py:495-583, 586-663).
 //
-// Layout.  Source trees arrive as leaf tours (flatten.py): leaves in depth-first order and, for
-// consecutive leaves i, i+1, the depth and weighting value of their LCA.  For a leaf at tour
-// position p, the LCA with the leaf at position q > p is the shallowest entry of adj[p..q-1]; for
-// q < p of adj[q..p-1].  So one leaf's whole row of contributions from one tree is two running
-// minima walking away from p -- a segmented min-scan, no pointer chasing and no RMQ table.
+// Layout.  Source trees arrive as leaf tours (flatten.py / forest.cpp): leaves in depth-first order
+// and, for consecutive leaves i, i+1, the depth and weighting value of their LCA.  The LCA of the
+// leaves at tour positions p < q is the shallowest entry of adj[p..q-1]: a range-minimum query.
+// pcg_sparse_table builds, once per tree, the classic doubling table over (depth, position) keys
+// (level j holds the minimum of 2^j consecutive entries), so every leaf pair's LCA is two table
+// reads and a min -- no pointer chasing, no per-row rescan of the tour.
 //
 // Kernel shape.  One CTA owns one row `a` of W (one taxon) and keeps the row's accumulators in
 // shared memory (8 B weight + 2/4 B count per column).  It visits the trees containing `a` in
-// input order; for each, the CTA scans the tour outward from a's position and adds
-// fl(val(LCA) * w_t) to the column of every other leaf whose LCA with `a` is not the root
-// (scs.py:570-579, 644-658).  Within a tree every leaf is a distinct column, so threads never
-// collide; trees are separated by the scan's __syncthreads, so every W entry is summed in tree
-// input order with separately rounded multiply and add (scs.py:655-657) -- bit-identical to the
-// reference, no atomics on W, and W[a][b] == W[b][a] bit for bit.  The finished row is written
-// once, coalesced, together with its adjacency bits (C > 0, scs.py:651-652), max-graph bits
-// (C == max(occ_a, occ_b), scs.py:302-305) and its row sum (the degree the spectral step needs),
-// so the co-occurrence matrix never has to be written to HBM unless the caller asks for it.
+// input order (their headers are staged 64 at a time, so the dependent loads that locate a tree
+// overlap); for each, every thread takes other leaves q of the tree, looks up LCA(a, q) and, unless
+// it is the root (scs.py:570-579: pairs separated by the root are not proper clusters), adds
+// fl(val(LCA) * w_t) to column taxon(q) (scs.py:644-658).  Within a tree every leaf is a distinct
+// column, so threads never collide; one barrier separates consecutive trees, so every W entry is
+// summed in tree input order with separately rounded multiply and add (scs.py:655-657) --
+// bit-identical to the reference, no atomics on W, and W[a][b] == W[b][a] bit for bit.  The finished
+// row is written once, coalesced, together with its adjacency bits (C > 0, scs.py:651-652),
+// max-graph bits (C == max(occ_a, occ_b), scs.py:302-305) and its row sum (the degree the spectral
+// step needs), so the co-occurrence matrix never has to be written to HBM unless the caller asks.
 //
 // Rows wider than shared memory (n > ~22k columns) are split into column chunks (gridDim.y);
-// each chunk CTA rescans the same tours and keeps only its columns.
+// each chunk CTA walks the same trees and keeps only its columns.
 
 #include "common.cuh"
 
@@ -31,9 +33,8 @@ namespace scs {
 namespace {
 
 constexpr int kRowThreads = 256;
-constexpr int kPerThread = 4;  // tour elements per thread per tile
-constexpr int kTile = kRowThreads * kPerThread;
 constexpr int kWarps = kRowThreads / 32;
+constexpr int kHeaderBatch = 64;  // (row, tree) incidences whose headers are staged together
 constexpr unsigned long long kNoKey = ~0ull;
 
 // ---- index: leaf -> tree, occurrences, taxon -> leaves ------------------------------------
@@ -119,34 +120,54 @@ __global__ void pcg_sort_inverse(const int32_t *__restrict__ row_ptr, const int3
     }
 }
 
-// ---- the row kernel -----------------------------------------------------------------------
-struct SegKey {
-    unsigned long long key;  // (depth << 32) | tour index of the adjacent-LCA entry
-    bool head;               // a segment start lies at or before this element (within the scope)
-};
-
-__device__ __forceinline__ SegKey seg_combine(const SegKey &left, const SegKey &right) {
-    SegKey r;
-    r.key = right.head ? right.key : (left.key < right.key ? left.key : right.key);
-    r.head = left.head || right.head;
-    return r;
+// ---- range-minimum table over the consecutive-leaf LCAs --------------------------------------------
+// st[j * L + g] = min over adj entries [g, g + 2^j) of the same tree of (depth << 32 | position in tree);
+// one CTA per tree builds all levels of its tree.
+__global__ void __launch_bounds__(kRowThreads)
+pcg_sparse_table(int64_t L, int levels, const int64_t *__restrict__ leaf_offsets,
+                 const int32_t *__restrict__ adj_depth, unsigned long long *st) {
+    const int t = blockIdx.x;
+    const int64_t tb = leaf_offsets[t];
+    const int k = static_cast<int>(leaf_offsets[t + 1] - tb);
+    const int entries = k - 1;  // adj entries of this tree (the last leaf has none)
+    for (int i = threadIdx.x; i < k; i += kRowThreads)
+        st[tb + i] = i < entries
+                         ? (static_cast<unsigned long long>(static_cast<uint32_t>(adj_depth[tb + i])) << 32) | static_cast<uint32_t>(i)
+                         : kNoKey;
+    for (int j = 1; j < levels; ++j) {
+        const int span = 1 << j;
+        if (span > entries) break;
+        __syncthreads();
+        const unsigned long long *prev = st + static_cast<size_t>(j - 1) * L + tb;
+        unsigned long long *cur = st + static_cast<size_t>(j) * L + tb;
+        for (int i = threadIdx.x; i + span <= entries; i += kRowThreads) {
+            const unsigned long long x = prev[i], y = prev[i + (span >> 1)];
+            cur[i] = x < y ? x : y;
+        }
+    }
 }
+
+// ---- the row kernel -----------------------------------------------------------------------
+struct TreeHeader {
+    int64_t base;  // first leaf of the tree in the tour arrays
+    double weight;
+    int leaves, position, root_depth, pad;
+};
 
 template <typename CountT, bool kWriteC>
 __global__ void __launch_bounds__(kRowThreads)
-pcg_rows_kernel(int n, int words_per_row, int cols_per_chunk,
+pcg_rows_kernel(int n, int words_per_row, int cols_per_chunk, int64_t L,
                 const int64_t *__restrict__ leaf_offsets, const int32_t *__restrict__ leaf_taxon,
-                const int32_t *__restrict__ adj_depth, const double *__restrict__ adj_val,
+                const unsigned long long *__restrict__ st, const double *__restrict__ adj_val,
                 const int32_t *__restrict__ root_depth, const double *__restrict__ tree_weight,
                 const int32_t *__restrict__ leaf_tree, const int32_t *__restrict__ row_ptr,
                 const int32_t *__restrict__ inv_sorted, const int32_t *__restrict__ occ,
                 double *__restrict__ W, int32_t *__restrict__ C, uint32_t *__restrict__ adj_bits,
-                uint32_t *__restrict__ max_bits, double *__restrict__ degree_part) {
+                uint32_t *__restrict__ max_bits, double *__restrict__ degree_part, int32_t *__restrict__ bad) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *accW = reinterpret_cast<double *>(smem_raw);
     CountT *accC = reinterpret_cast<CountT *>(accW + cols_per_chunk);
-    __shared__ unsigned long long warp_key[2][kWarps];
-    __shared__ int warp_head[2][kWarps];
+    __shared__ TreeHeader headers[kHeaderBatch];
     __shared__ double warp_sum[kWarps];
 
     const int a = blockIdx.x;
@@ -158,96 +179,55 @@ pcg_rows_kernel(int n, int words_per_row, int cols_per_chunk,
         accW[c] = 0.0;
         accC[c] = 0;
     }
-    // the first tile's __syncthreads orders this initialisation before any update
 
     const int ebase = row_ptr[a];
     const int cnt = row_ptr[a + 1] - ebase;
-    int parity = 0;
-    for (int ei = 0; ei < cnt; ++ei) {
-        const int g = inv_sorted[ebase + ei];
-        const int t = leaf_tree[g];
-        const int64_t tb = leaf_offsets[t];
-        const int k = static_cast<int>(leaf_offsets[t + 1] - tb);
-        const int p = static_cast<int>(g - tb);
-        const double w = tree_weight[t];
-        const int rd = root_depth[t];
-        const int nv = k - 1;  // virtual sequence: v < p walks left from p, v >= p walks right
-        const int32_t *depth_t = adj_depth + tb;
-        const double *val_t = adj_val + tb;
-        const int32_t *taxon_t = leaf_taxon + tb;
-
-        unsigned long long carry = kNoKey;  // running minimum entering the tile
-        for (int v0 = 0; v0 < nv; v0 += kTile) {
-            const int vb = v0 + tid * kPerThread;
-            unsigned long long pre[kPerThread];
-            unsigned long long run = kNoKey;
-            bool head = false;
-#pragma unroll
-            for (int e = 0; e < kPerThread; ++e) {
-                const int v = vb + e;
-                unsigned long long key = kNoKey;
-                if (v < nv) {
-                    const int kidx = v < p ? p - 1 - v : v;
-                    key = (static_cast<unsigned long long>(static_cast<uint32_t>(depth_t[kidx])) << 32) |
-                          static_cast<uint32_t>(kidx);
-                }
-                if (v == p) {  // the right-hand walk starts here
-                    run = kNoKey;
-                    head = true;
-                }
-                run = key < run ? key : run;
-                pre[e] = run;
+    for (int e0 = 0; e0 < cnt; e0 += kHeaderBatch) {
+        const int batch = min(kHeaderBatch, cnt - e0);
+        __syncthreads();  // the previous batch's headers (and the initialisation) are done with
+        if (tid < batch) {
+            const int g = inv_sorted[ebase + e0 + tid];
+            const int t = leaf_tree[g];
+            const int64_t tb = leaf_offsets[t];
+            TreeHeader h;
+            h.base = tb;
+            h.weight = tree_weight[t];
+            h.leaves = static_cast<int>(leaf_offsets[t + 1] - tb);
+            if (h.leaves > n) {  // more leaves than taxa: a taxon is repeated, the table would be too shallow
+                *bad = 1;
+                h.leaves = 0;
             }
-            // inclusive segmented scan of the per-thread aggregates across the warp
-            SegKey agg{run, head};
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                SegKey left;
-                left.key = __shfl_up_sync(0xffffffffu, agg.key, off);
-                left.head = __shfl_up_sync(0xffffffffu, static_cast<int>(agg.head), off) != 0;
-                if (lane >= off) agg = seg_combine(left, agg);
-            }
-            if (lane == 31) {
-                warp_key[parity][warp] = agg.key;
-                warp_head[parity][warp] = agg.head;
-            }
-            SegKey excl;  // aggregate of the preceding lanes of this warp
-            excl.key = __shfl_up_sync(0xffffffffu, agg.key, 1);
-            excl.head = __shfl_up_sync(0xffffffffu, static_cast<int>(agg.head), 1) != 0;
-            if (lane == 0) excl = SegKey{kNoKey, false};
-            __syncthreads();
-            SegKey before{carry, false};  // everything before this warp, tile carry included
-            SegKey total{carry, false};
-#pragma unroll
-            for (int wi = 0; wi < kWarps; ++wi) {
-                SegKey wa{warp_key[parity][wi], warp_head[parity][wi] != 0};
-                if (wi < warp) before = seg_combine(before, wa);
-                total = seg_combine(total, wa);
-            }
-            carry = total.key;
-            parity ^= 1;
-            const SegKey enter = seg_combine(before, excl);
-
-            bool seen_head = false;
-#pragma unroll
-            for (int e = 0; e < kPerThread; ++e) {
-                const int v = vb + e;
-                if (v == p) seen_head = true;
-                if (v < nv) {
-                    unsigned long long m = pre[e];
-                    if (!seen_head && enter.key < m) m = enter.key;
-                    const int d = static_cast<int>(m >> 32);
-                    if (d != rd) {
-                        const int q = v < p ? p - 1 - v : v + 1;
-                        const int c = taxon_t[q] - col0;
-                        if (static_cast<unsigned>(c) < static_cast<unsigned>(ncols)) {
-                            const double term = __dmul_rn(val_t[static_cast<uint32_t>(m)], w);
-                            accW[c] = __dadd_rn(accW[c], term);
-                            accC[c] = static_cast<CountT>(accC[c] + 1);
-                        }
+            h.position = static_cast<int>(g - tb);
+            h.root_depth = root_depth[t];
+            h.pad = 0;
+            headers[tid] = h;
+        }
+        __syncthreads();
+        for (int ei = 0; ei < batch; ++ei) {
+            const TreeHeader h = headers[ei];
+            const int p = h.position;
+            const unsigned long long *st_t = st + h.base;
+            const int32_t *taxon_t = leaf_taxon + h.base;
+            const double *val_t = adj_val + h.base;
+            // v enumerates the other leaves: v < p is leaf v, v >= p is leaf v + 1
+            for (int v = tid; v < h.leaves - 1; v += kRowThreads) {
+                const int q = v < p ? v : v + 1;
+                const int lo = v < p ? q : p;        // adj entries [lo, lo + len) lie between the two leaves
+                const int len = v < p ? p - q : q - p;
+                const int j = 31 - __clz(len);
+                const unsigned long long *level = st_t + static_cast<size_t>(j) * L;
+                const unsigned long long x = level[lo], y = level[lo + len - (1 << j)];
+                const unsigned long long key = x < y ? x : y;
+                if (static_cast<int>(key >> 32) != h.root_depth) {
+                    const int c = taxon_t[q] - col0;
+                    if (static_cast<unsigned>(c) < static_cast<unsigned>(ncols)) {
+                        const double term = __dmul_rn(val_t[static_cast<uint32_t>(key)], h.weight);
+                        accW[c] = __dadd_rn(accW[c], term);
+                        accC[c] = static_cast<CountT>(accC[c] + 1);
                     }
                 }
             }
+            __syncthreads();  // tree order: the next tree may touch the same columns from other threads
         }
     }
     __syncthreads();
@@ -300,12 +280,12 @@ __global__ void pcg_sum_degree_parts(int n, int nchunks, const double *__restric
 }
 
 template <typename CountT, bool kWriteC>
-int launch_rows(scs_ctx *ctx, int n, int words, int cols_per_chunk, int nchunks, size_t smem,
-                const int64_t *leaf_offsets, const int32_t *leaf_taxon, const int32_t *adj_depth,
+int launch_rows(scs_ctx *ctx, int n, int words, int cols_per_chunk, int nchunks, size_t smem, int64_t L,
+                const int64_t *leaf_offsets, const int32_t *leaf_taxon, const unsigned long long *st,
                 const double *adj_val, const int32_t *root_depth, const double *tree_weight,
                 const int32_t *leaf_tree, const int32_t *row_ptr, const int32_t *inv_sorted,
                 const int32_t *occ, double *W, int32_t *C, uint32_t *adj_bits, uint32_t *max_bits,
-                double *degree_part) {
+                double *degree_part, int32_t *bad) {
     auto kernel = pcg_rows_kernel<CountT, kWriteC>;
     SCS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     dim3 grid(n, nchunks);
@@ -314,9 +294,9 @@ int launch_rows(scs_ctx *ctx, int n, int words, int cols_per_chunk, int nchunks,
         const double out_bytes = 8.0 * n * n + (C ? 4.0 * n * n : 0.0) + 8.0 * n * words + 12.0 * n;
         profile_begin(ctx, PROFILE_PCG_ROWS, out_bytes, ctx->pending_units);
     }
-    kernel<<<grid, kRowThreads, smem, ctx->stream>>>(n, words, cols_per_chunk, leaf_offsets, leaf_taxon, adj_depth,
+    kernel<<<grid, kRowThreads, smem, ctx->stream>>>(n, words, cols_per_chunk, L, leaf_offsets, leaf_taxon, st,
                                                      adj_val, root_depth, tree_weight, leaf_tree, row_ptr,
-                                                     inv_sorted, occ, W, C, adj_bits, max_bits, degree_part);
+                                                     inv_sorted, occ, W, C, adj_bits, max_bits, degree_part, bad);
     if (n >= kProfileMinSize) profile_end(ctx);
     SCS_LAUNCHED(ctx, "pcg_rows_kernel");
     return SCS_OK;
@@ -367,6 +347,16 @@ int pcg_build(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offsets
         pcg_sort_inverse<<<n, 128, 0, ctx->stream>>>(row_ptr, inv, inv_sorted);
         SCS_LAUNCHED(ctx, "pcg_sort_inverse");
     }
+    // a tree has at most n leaves (distinct taxa), so ceil(log2(n)) doubling levels always suffice
+    int levels = 1;
+    while ((1 << levels) < n) ++levels;
+    unsigned long long *st;
+    if ((rc = reserve_as(ctx, SLOT_SPARSE, static_cast<size_t>(levels) * static_cast<size_t>(L > 0 ? L : 1), &st)))
+        return rc;
+    if (L > 0 && T > 0) {
+        pcg_sparse_table<<<T, kRowThreads, 0, ctx->stream>>>(L, levels, leaf_offsets, adj_depth, st);
+        SCS_LAUNCHED(ctx, "pcg_sparse_table");
+    }
 
     // column chunking: the whole row if it fits in shared memory, else equal chunks of 32-multiples
     const bool narrow = T < 65536;
@@ -380,10 +370,10 @@ int pcg_build(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offsets
     const size_t smem = static_cast<size_t>(cols_per_chunk) * per_col + 16;
     if ((rc = reserve_as(ctx, SLOT_DEGREE_PART, static_cast<size_t>(n) * nchunks, &degree_part))) return rc;
 
-#define SCS_ROWS(CT, WC)                                                                                       \
-    launch_rows<CT, WC>(ctx, n, words, cols_per_chunk, nchunks, smem, leaf_offsets, leaf_taxon, adj_depth,    \
-                        adj_val, root_depth, tree_weight, leaf_tree, row_ptr, inv_sorted, occ, W, C, adj_bits, \
-                        max_bits, degree_part)
+#define SCS_ROWS(CT, WC)                                                                                      \
+    launch_rows<CT, WC>(ctx, n, words, cols_per_chunk, nchunks, smem, L, leaf_offsets, leaf_taxon, st, adj_val, \
+                        root_depth, tree_weight, leaf_tree, row_ptr, inv_sorted, occ, W, C, adj_bits, max_bits, \
+                        degree_part, scalars)
     if (narrow) rc = C ? SCS_ROWS(uint16_t, true) : SCS_ROWS(uint16_t, false);
     else rc = C ? SCS_ROWS(int32_t, true) : SCS_ROWS(int32_t, false);
 #undef SCS_ROWS

@@ -431,7 +431,6 @@ tridiag_ritz(int jrun, const double *__restrict__ alpha, const double *__restric
 // through.  The host therefore synchronises once per chunk of steps instead of once per check.
 // state: [0] breakdown step, [1] done, [2] step at which done was raised.
 constexpr int kFusedMax = 4096;
-constexpr int kFusedPerThread = kFusedMax / kOneCta;
 
 __global__ void __launch_bounds__(kOneCta)
 lanczos_tail(int m, int j, int nb, int hj, int check, const double *basis, const double *__restrict__ w_in,
