@@ -811,7 +811,7 @@ int lanczos_largest(scs_ctx *ctx, int m, const double *W, const LanczosBuffers &
             int attempt_matvecs = 0;
             bool done = false;
             while (j <= jmax && !done) {
-                const int chunk_end = std::min(jmax, j == 1 ? 23 : j + 7);
+                const int chunk_end = std::min(jmax, j == 1 ? 16 : j + 3);  // chunks end on check steps
                 for (; j <= chunk_end; ++j) {
                     if ((rc = launch_matvec(ctx, m, W, b.isd, b.z, b.w, b.state + 1))) return rc;
                     const int check = j == jmax || (j % 4) == 0;
