@@ -154,6 +154,68 @@ struct TreeHeader {
     int leaves, position, root_depth, pad;
 };
 
+constexpr int kPerThread = 4;                          // visits per thread per segment
+constexpr int kSegment = kRowThreads * kPerThread;     // visits per segment
+
+struct Pending {
+    int col[kPerThread];     // column of the chunk, or -1
+    double term[kPerThread];  // fl(val(LCA) * w_t)
+};
+
+// Everything a segment needs from global memory, into registers.  v enumerates the other leaves of the
+// tree: v < p is leaf v, v >= p is leaf v + 1.
+__device__ __forceinline__ void load_segment(const TreeHeader &h, int seg, int64_t L,
+                                             const unsigned long long *__restrict__ st,
+                                             const int32_t *__restrict__ leaf_taxon,
+                                             const double *__restrict__ adj_val, int col0, int ncols, int tid,
+                                             Pending &out) {
+    const int p = h.position;
+    const unsigned long long *st_t = st + h.base;
+    const int32_t *taxon_t = leaf_taxon + h.base;
+    const double *val_t = adj_val + h.base;
+    unsigned long long key[kPerThread];
+    int q[kPerThread];
+#pragma unroll
+    for (int r = 0; r < kPerThread; ++r) {
+        const int v = seg * kSegment + r * kRowThreads + tid;
+        key[r] = kNoKey;
+        q[r] = -1;
+        if (v < h.leaves - 1) {
+            q[r] = v < p ? v : v + 1;
+            const int lo = v < p ? q[r] : p;  // adj entries [lo, lo + len) lie between the two leaves
+            const int len = v < p ? p - q[r] : q[r] - p;
+            const int j = 31 - __clz(len);
+            const unsigned long long *level = st_t + static_cast<size_t>(j) * L;
+            const unsigned long long x = level[lo], y = level[lo + len - (1 << j)];
+            key[r] = x < y ? x : y;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < kPerThread; ++r) {
+        out.col[r] = -1;
+        out.term[r] = 0.0;
+        if (q[r] >= 0 && static_cast<int>(key[r] >> 32) != h.root_depth) {
+            const int c = taxon_t[q[r]] - col0;
+            if (static_cast<unsigned>(c) < static_cast<unsigned>(ncols)) {
+                out.col[r] = c;
+                out.term[r] = __dmul_rn(val_t[static_cast<uint32_t>(key[r])], h.weight);
+            }
+        }
+    }
+}
+
+// next (tree, segment) of the batch
+__device__ __forceinline__ void advance(const TreeHeader *headers, int batch, int &e, int &seg) {
+    if (e >= batch) return;
+    ++seg;
+    if (seg * kSegment >= headers[e].leaves - 1) {
+        seg = 0;
+        do {
+            ++e;
+        } while (e < batch && headers[e].leaves < 2);
+    }
+}
+
 template <typename CountT, bool kWriteC>
 __global__ void __launch_bounds__(kRowThreads)
 pcg_rows_kernel(int n, int words_per_row, int cols_per_chunk, int64_t L,
@@ -203,31 +265,32 @@ pcg_rows_kernel(int n, int words_per_row, int cols_per_chunk, int64_t L,
             headers[tid] = h;
         }
         __syncthreads();
-        for (int ei = 0; ei < batch; ++ei) {
-            const TreeHeader h = headers[ei];
-            const int p = h.position;
-            const unsigned long long *st_t = st + h.base;
-            const int32_t *taxon_t = leaf_taxon + h.base;
-            const double *val_t = adj_val + h.base;
-            // v enumerates the other leaves: v < p is leaf v, v >= p is leaf v + 1
-            for (int v = tid; v < h.leaves - 1; v += kRowThreads) {
-                const int q = v < p ? v : v + 1;
-                const int lo = v < p ? q : p;        // adj entries [lo, lo + len) lie between the two leaves
-                const int len = v < p ? p - q : q - p;
-                const int j = 31 - __clz(len);
-                const unsigned long long *level = st_t + static_cast<size_t>(j) * L;
-                const unsigned long long x = level[lo], y = level[lo + len - (1 << j)];
-                const unsigned long long key = x < y ? x : y;
-                if (static_cast<int>(key >> 32) != h.root_depth) {
-                    const int c = taxon_t[q] - col0;
-                    if (static_cast<unsigned>(c) < static_cast<unsigned>(ncols)) {
-                        const double term = __dmul_rn(val_t[static_cast<uint32_t>(key)], h.weight);
-                        accW[c] = __dadd_rn(accW[c], term);
-                        accC[c] = static_cast<CountT>(accC[c] + 1);
-                    }
+        // Software pipeline over segments of kSegment visits: the loads of the next segment (table,
+        // taxon, value: three dependent L2 round trips) are issued before the shared-memory updates of
+        // the current one, and each thread keeps kPerThread independent chains in flight.  Only the
+        // updates are ordered: a barrier whenever the tree changes (segments of one tree touch
+        // distinct columns).
+        int next_e = 0, next_seg = 0;
+        Pending cur, nxt;
+        load_segment(headers[0], 0, L, st, leaf_taxon, adj_val, col0, ncols, tid, cur);
+        int cur_e = 0;
+        advance(headers, batch, next_e, next_seg);
+        while (true) {
+            const bool more = next_e < batch;
+            if (more) load_segment(headers[next_e], next_seg, L, st, leaf_taxon, adj_val, col0, ncols, tid, nxt);
+#pragma unroll
+            for (int r = 0; r < kPerThread; ++r) {
+                const int c = cur.col[r];
+                if (c >= 0) {
+                    accW[c] = __dadd_rn(accW[c], cur.term[r]);
+                    accC[c] = static_cast<CountT>(accC[c] + 1);
                 }
             }
-            __syncthreads();  // tree order: the next tree may touch the same columns from other threads
+            if (!more) break;
+            if (next_e != cur_e) __syncthreads();  // tree order: the next tree may touch the same columns
+            cur = nxt;
+            cur_e = next_e;
+            advance(headers, batch, next_e, next_seg);
         }
     }
     __syncthreads();
