@@ -32,7 +32,7 @@ namespace scs {
 
 namespace {
 
-constexpr int kRowThreads = 256;
+constexpr int kRowThreads = 512;  // 2 CTAs/SM at n = 10^4 (100 KB of row accumulators each): 32 warps/SM
 constexpr int kWarps = kRowThreads / 32;
 constexpr int kHeaderBatch = 64;  // (row, tree) incidences whose headers are staged together
 constexpr unsigned long long kNoKey = ~0ull;
@@ -121,28 +121,39 @@ __global__ void pcg_sort_inverse(const int32_t *__restrict__ row_ptr, const int3
 }
 
 // ---- range-minimum table over the consecutive-leaf LCAs --------------------------------------------
-// st[j * L + g] = min over adj entries [g, g + 2^j) of the same tree of (depth << 32 | position in tree);
-// one CTA per tree builds all levels of its tree.
-__global__ void __launch_bounds__(kRowThreads)
+// st[j * L + g] = the shallowest adj entry among [g, g + 2^j) of the same tree, as {key, value} with
+// key = depth << 32 | position in tree (ties: leftmost; equal depth in a range means the same node) and
+// value = the weighting value of that LCA, so a lookup needs no second, dependent read.
+// One CTA per tree builds all levels of its tree.
+struct __align__(16) LcaEntry {
+    unsigned long long key;
+    double val;
+};
+
+__global__ void __launch_bounds__(256)
 pcg_sparse_table(int64_t L, int levels, const int64_t *__restrict__ leaf_offsets,
-                 const int32_t *__restrict__ adj_depth, unsigned long long *st) {
+                 const int32_t *__restrict__ adj_depth, const double *__restrict__ adj_val, LcaEntry *st) {
     const int t = blockIdx.x;
     const int64_t tb = leaf_offsets[t];
     const int k = static_cast<int>(leaf_offsets[t + 1] - tb);
     const int entries = k - 1;  // adj entries of this tree (the last leaf has none)
-    for (int i = threadIdx.x; i < k; i += kRowThreads)
-        st[tb + i] = i < entries
-                         ? (static_cast<unsigned long long>(static_cast<uint32_t>(adj_depth[tb + i])) << 32) | static_cast<uint32_t>(i)
-                         : kNoKey;
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        LcaEntry e;
+        e.key = i < entries
+                    ? (static_cast<unsigned long long>(static_cast<uint32_t>(adj_depth[tb + i])) << 32) | static_cast<uint32_t>(i)
+                    : kNoKey;
+        e.val = i < entries ? adj_val[tb + i] : 0.0;
+        st[tb + i] = e;
+    }
     for (int j = 1; j < levels; ++j) {
         const int span = 1 << j;
         if (span > entries) break;
         __syncthreads();
-        const unsigned long long *prev = st + static_cast<size_t>(j - 1) * L + tb;
-        unsigned long long *cur = st + static_cast<size_t>(j) * L + tb;
-        for (int i = threadIdx.x; i + span <= entries; i += kRowThreads) {
-            const unsigned long long x = prev[i], y = prev[i + (span >> 1)];
-            cur[i] = x < y ? x : y;
+        const LcaEntry *prev = st + static_cast<size_t>(j - 1) * L + tb;
+        LcaEntry *cur = st + static_cast<size_t>(j) * L + tb;
+        for (int i = threadIdx.x; i + span <= entries; i += blockDim.x) {
+            const LcaEntry x = prev[i], y = prev[i + (span >> 1)];
+            cur[i] = x.key < y.key ? x : y;
         }
     }
 }
@@ -154,7 +165,7 @@ struct TreeHeader {
     int leaves, position, root_depth, pad;
 };
 
-constexpr int kPerThread = 4;                          // visits per thread per segment
+constexpr int kPerThread = 2;                          // visits per thread per segment
 constexpr int kSegment = kRowThreads * kPerThread;     // visits per segment
 
 struct Pending {
@@ -164,43 +175,47 @@ struct Pending {
 
 // Everything a segment needs from global memory, into registers.  v enumerates the other leaves of the
 // tree: v < p is leaf v, v >= p is leaf v + 1.
+__device__ __forceinline__ LcaEntry load_entry(const LcaEntry *p) {
+    const ulonglong2 raw = *reinterpret_cast<const ulonglong2 *>(p);  // one 16-byte load
+    LcaEntry e;
+    e.key = raw.x;
+    e.val = __longlong_as_double(static_cast<long long>(raw.y));
+    return e;
+}
+
 __device__ __forceinline__ void load_segment(const TreeHeader &h, int seg, int64_t L,
-                                             const unsigned long long *__restrict__ st,
-                                             const int32_t *__restrict__ leaf_taxon,
-                                             const double *__restrict__ adj_val, int col0, int ncols, int tid,
+                                             const LcaEntry *__restrict__ st,
+                                             const int32_t *__restrict__ leaf_taxon, int col0, int ncols, int tid,
                                              Pending &out) {
     const int p = h.position;
-    const unsigned long long *st_t = st + h.base;
+    const LcaEntry *st_t = st + h.base;
     const int32_t *taxon_t = leaf_taxon + h.base;
-    const double *val_t = adj_val + h.base;
-    unsigned long long key[kPerThread];
-    int q[kPerThread];
+    LcaEntry x[kPerThread], y[kPerThread];
+    int col[kPerThread];
 #pragma unroll
     for (int r = 0; r < kPerThread; ++r) {
         const int v = seg * kSegment + r * kRowThreads + tid;
-        key[r] = kNoKey;
-        q[r] = -1;
+        col[r] = -1;
+        x[r].key = y[r].key = kNoKey;
+        x[r].val = y[r].val = 0.0;
         if (v < h.leaves - 1) {
-            q[r] = v < p ? v : v + 1;
-            const int lo = v < p ? q[r] : p;  // adj entries [lo, lo + len) lie between the two leaves
-            const int len = v < p ? p - q[r] : q[r] - p;
+            const int q = v < p ? v : v + 1;
+            const int lo = v < p ? q : p;  // adj entries [lo, lo + len) lie between the two leaves
+            const int len = v < p ? p - q : q - p;
             const int j = 31 - __clz(len);
-            const unsigned long long *level = st_t + static_cast<size_t>(j) * L;
-            const unsigned long long x = level[lo], y = level[lo + len - (1 << j)];
-            key[r] = x < y ? x : y;
+            const LcaEntry *level = st_t + static_cast<size_t>(j) * L;
+            x[r] = load_entry(level + lo);
+            y[r] = load_entry(level + lo + len - (1 << j));
+            col[r] = taxon_t[q] - col0;
         }
     }
 #pragma unroll
     for (int r = 0; r < kPerThread; ++r) {
-        out.col[r] = -1;
-        out.term[r] = 0.0;
-        if (q[r] >= 0 && static_cast<int>(key[r] >> 32) != h.root_depth) {
-            const int c = taxon_t[q[r]] - col0;
-            if (static_cast<unsigned>(c) < static_cast<unsigned>(ncols)) {
-                out.col[r] = c;
-                out.term[r] = __dmul_rn(val_t[static_cast<uint32_t>(key[r])], h.weight);
-            }
-        }
+        const LcaEntry e = x[r].key < y[r].key ? x[r] : y[r];
+        const bool proper = col[r] != -1 && static_cast<int>(e.key >> 32) != h.root_depth &&
+                            static_cast<unsigned>(col[r]) < static_cast<unsigned>(ncols);
+        out.col[r] = proper ? col[r] : -1;
+        out.term[r] = __dmul_rn(e.val, h.weight);
     }
 }
 
@@ -220,8 +235,8 @@ template <typename CountT, bool kWriteC>
 __global__ void __launch_bounds__(kRowThreads)
 pcg_rows_kernel(int n, int words_per_row, int cols_per_chunk, int64_t L,
                 const int64_t *__restrict__ leaf_offsets, const int32_t *__restrict__ leaf_taxon,
-                const unsigned long long *__restrict__ st, const double *__restrict__ adj_val,
-                const int32_t *__restrict__ root_depth, const double *__restrict__ tree_weight,
+                const LcaEntry *__restrict__ st, const int32_t *__restrict__ root_depth,
+                const double *__restrict__ tree_weight,
                 const int32_t *__restrict__ leaf_tree, const int32_t *__restrict__ row_ptr,
                 const int32_t *__restrict__ inv_sorted, const int32_t *__restrict__ occ,
                 double *__restrict__ W, int32_t *__restrict__ C, uint32_t *__restrict__ adj_bits,
@@ -272,12 +287,12 @@ pcg_rows_kernel(int n, int words_per_row, int cols_per_chunk, int64_t L,
         // distinct columns).
         int next_e = 0, next_seg = 0;
         Pending cur, nxt;
-        load_segment(headers[0], 0, L, st, leaf_taxon, adj_val, col0, ncols, tid, cur);
+        load_segment(headers[0], 0, L, st, leaf_taxon, col0, ncols, tid, cur);
         int cur_e = 0;
         advance(headers, batch, next_e, next_seg);
         while (true) {
             const bool more = next_e < batch;
-            if (more) load_segment(headers[next_e], next_seg, L, st, leaf_taxon, adj_val, col0, ncols, tid, nxt);
+            if (more) load_segment(headers[next_e], next_seg, L, st, leaf_taxon, col0, ncols, tid, nxt);
 #pragma unroll
             for (int r = 0; r < kPerThread; ++r) {
                 const int c = cur.col[r];
@@ -344,8 +359,8 @@ __global__ void pcg_sum_degree_parts(int n, int nchunks, const double *__restric
 
 template <typename CountT, bool kWriteC>
 int launch_rows(scs_ctx *ctx, int n, int words, int cols_per_chunk, int nchunks, size_t smem, int64_t L,
-                const int64_t *leaf_offsets, const int32_t *leaf_taxon, const unsigned long long *st,
-                const double *adj_val, const int32_t *root_depth, const double *tree_weight,
+                const int64_t *leaf_offsets, const int32_t *leaf_taxon, const LcaEntry *st,
+                const int32_t *root_depth, const double *tree_weight,
                 const int32_t *leaf_tree, const int32_t *row_ptr, const int32_t *inv_sorted,
                 const int32_t *occ, double *W, int32_t *C, uint32_t *adj_bits, uint32_t *max_bits,
                 double *degree_part, int32_t *bad) {
@@ -358,7 +373,7 @@ int launch_rows(scs_ctx *ctx, int n, int words, int cols_per_chunk, int nchunks,
         profile_begin(ctx, PROFILE_PCG_ROWS, out_bytes, ctx->pending_units);
     }
     kernel<<<grid, kRowThreads, smem, ctx->stream>>>(n, words, cols_per_chunk, L, leaf_offsets, leaf_taxon, st,
-                                                     adj_val, root_depth, tree_weight, leaf_tree, row_ptr,
+                                                     root_depth, tree_weight, leaf_tree, row_ptr,
                                                      inv_sorted, occ, W, C, adj_bits, max_bits, degree_part, bad);
     if (n >= kProfileMinSize) profile_end(ctx);
     SCS_LAUNCHED(ctx, "pcg_rows_kernel");
@@ -413,11 +428,11 @@ int pcg_build(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offsets
     // a tree has at most n leaves (distinct taxa), so ceil(log2(n)) doubling levels always suffice
     int levels = 1;
     while ((1 << levels) < n) ++levels;
-    unsigned long long *st;
+    LcaEntry *st;
     if ((rc = reserve_as(ctx, SLOT_SPARSE, static_cast<size_t>(levels) * static_cast<size_t>(L > 0 ? L : 1), &st)))
         return rc;
     if (L > 0 && T > 0) {
-        pcg_sparse_table<<<T, kRowThreads, 0, ctx->stream>>>(L, levels, leaf_offsets, adj_depth, st);
+        pcg_sparse_table<<<T, 256, 0, ctx->stream>>>(L, levels, leaf_offsets, adj_depth, adj_val, st);
         SCS_LAUNCHED(ctx, "pcg_sparse_table");
     }
 
@@ -434,7 +449,7 @@ int pcg_build(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offsets
     if ((rc = reserve_as(ctx, SLOT_DEGREE_PART, static_cast<size_t>(n) * nchunks, &degree_part))) return rc;
 
 #define SCS_ROWS(CT, WC)                                                                                      \
-    launch_rows<CT, WC>(ctx, n, words, cols_per_chunk, nchunks, smem, L, leaf_offsets, leaf_taxon, st, adj_val, \
+    launch_rows<CT, WC>(ctx, n, words, cols_per_chunk, nchunks, smem, L, leaf_offsets, leaf_taxon, st,          \
                         root_depth, tree_weight, leaf_tree, row_ptr, inv_sorted, occ, W, C, adj_bits, max_bits, \
                         degree_part, scalars)
     if (narrow) rc = C ? SCS_ROWS(uint16_t, true) : SCS_ROWS(uint16_t, false);
