@@ -76,11 +76,12 @@ struct SplitResult {
 // Per-thread scratch sized by the number of taxa of the job.
 struct Scratch {
     std::vector<uint8_t> keep;
-    std::vector<int32_t> stamp;
+    std::vector<int32_t> stamp, local;
     int stamp_id = 0;
     void reset(int num_taxa) {
         keep.assign(num_taxa > 0 ? num_taxa : 1, 0);
         stamp.assign(num_taxa > 0 ? num_taxa : 1, 0);
+        local.assign(num_taxa > 0 ? num_taxa : 1, -1);
         stamp_id = 0;
     }
     void present_taxa(const scs_forest *f, std::vector<int32_t> &taxa) {
@@ -132,7 +133,6 @@ class Driver {
 
     int run(const scs_forest *root) {
         num_taxa_ = scs_forest_num_taxa(root);
-        local_.assign(num_taxa_ > 0 ? num_taxa_ : 1, -1);
         scratch_.resize(static_cast<size_t>(scs_host_threads()));
         for (Scratch &sc : scratch_) sc.reset(num_taxa_);
         std::vector<Task> wave, next;
@@ -258,11 +258,12 @@ class Driver {
         return SCS_OK;
     }
 
-    int tours_of(const scs_forest *f, const std::vector<int32_t> &taxa, int64_t *leaf_offsets, int32_t *leaf_taxon,
-                 int32_t *adj_depth, double *adj_val, int32_t *root_depth, double *tree_weight) {
-        Stopwatch sw(&out_.seconds[3]);
-        for (size_t v = 0; v < taxa.size(); ++v) local_[taxa[v]] = static_cast<int32_t>(v);
-        return scs_forest_tours(f, weighting_, local_.data(), leaf_offsets, leaf_taxon, adj_depth, adj_val, root_depth,
+    // local[] maps global taxon id -> vertex id of the node; only the node's own taxa are ever read
+    int tours_of(const scs_forest *f, const std::vector<int32_t> &taxa, std::vector<int32_t> &local,
+                 int64_t *leaf_offsets, int32_t *leaf_taxon, int32_t *adj_depth, double *adj_val, int32_t *root_depth,
+                 double *tree_weight) {
+        for (size_t v = 0; v < taxa.size(); ++v) local[taxa[v]] = static_cast<int32_t>(v);
+        return scs_forest_tours(f, weighting_, local.data(), leaf_offsets, leaf_taxon, adj_depth, adj_val, root_depth,
                                 tree_weight);
     }
 
@@ -278,7 +279,12 @@ class Driver {
         val_.resize(L + 1);
         root_.resize(T + 1);
         wgt_.resize(T + 1);
-        int rc = tours_of(f, taxa, off_.data(), tax_.data(), dep_.data(), val_.data(), root_.data(), wgt_.data());
+        int rc;
+        {
+            Stopwatch sw(&out_.seconds[3]);
+            rc = tours_of(f, taxa, scratch_[0].local, off_.data(), tax_.data(), dep_.data(), val_.data(), root_.data(),
+                          wgt_.data());
+        }
         if (rc) return rc;
         res.part.resize(n);
         Stopwatch sw(&out_.seconds[0]);
@@ -313,13 +319,23 @@ class Driver {
         val_.resize(L_total + 1);
         root_.resize(T_total + 1);
         wgt_.resize(T_total + 1);
-        for (int b = 0; b < B; ++b) {
-            const scs_forest *f = wave[small[b]].forest;
-            int rc = tours_of(f, wave[small[b]].taxa, off_.data() + nodes[b].tree_base + b, tax_.data() + nodes[b].leaf_base,
-                              dep_.data() + nodes[b].leaf_base, val_.data() + nodes[b].leaf_base,
-                              root_.data() + nodes[b].tree_base, wgt_.data() + nodes[b].tree_base);
-            if (rc) return rc;
+        int tours_rc = SCS_OK;
+        {
+            Stopwatch sw(&out_.seconds[3]);
+#pragma omp parallel for schedule(dynamic, 8) if (B >= 32) num_threads(scs_host_threads())
+            for (int b = 0; b < B; ++b) {
+                const scs_forest *f = wave[small[b]].forest;
+                const int rc = tours_of(f, wave[small[b]].taxa, scratch_[static_cast<size_t>(omp_get_thread_num())].local,
+                                        off_.data() + nodes[b].tree_base + b, tax_.data() + nodes[b].leaf_base,
+                                        dep_.data() + nodes[b].leaf_base, val_.data() + nodes[b].leaf_base,
+                                        root_.data() + nodes[b].tree_base, wgt_.data() + nodes[b].tree_base);
+                if (rc) {
+#pragma omp atomic write
+                    tours_rc = rc;
+                }
+            }
         }
+        if (tours_rc) return tours_rc;
         part_.resize(N_total);
         std::vector<scs_node_stats> stats(B);
         int rc;
@@ -417,7 +433,6 @@ class Driver {
     bool partitioned_ = false;
     scs_supertree &out_;
     int num_taxa_ = 0;
-    std::vector<int32_t> local_;
     std::vector<Scratch> scratch_;
     std::vector<int64_t> off_;
     std::vector<int32_t> tax_, dep_, root_, part_;
