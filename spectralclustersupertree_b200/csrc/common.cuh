@@ -96,6 +96,7 @@ struct scs_ctx {
     std::vector<ProfileRecord> profile;
     int flush_value = 0;
     double stage_seconds[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // host wall clock per stage of the staged node path
+    std::vector<scs_ctx *> workers;  // extra contexts on the same GPU for concurrent staged nodes
     bool small_configured = false;
     bool batch_configured = false;
     bool tail_configured = false;
@@ -165,6 +166,9 @@ __device__ __forceinline__ double order_value(unsigned long long k) {
     return __longlong_as_double(static_cast<long long>(b));
 }
 #endif
+
+// Make sure ctx->workers holds at least `count - 1` extra contexts (the main context is worker 0).
+int ensure_workers(scs_ctx *ctx, int count);
 
 // ---- stage entry points implemented in the other translation units ------------------------
 int pcg_build(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offsets,

@@ -63,6 +63,18 @@ int reserve_pinned(scs_ctx *ctx, size_t bytes, void **out) {
     return SCS_OK;
 }
 
+int ensure_workers(scs_ctx *ctx, int count) {
+    while (static_cast<int>(ctx->workers.size()) < count - 1) {
+        scs_ctx *worker = nullptr;
+        const int rc = scs_ctx_create(ctx->device, nullptr, &worker);
+        if (rc) return fail(ctx, rc, "creating a worker context");
+        worker->small_limit = ctx->small_limit;
+        ctx->workers.push_back(worker);
+    }
+    for (scs_ctx *worker : ctx->workers) worker->small_limit = ctx->small_limit;
+    return SCS_OK;
+}
+
 void profile_begin(scs_ctx *ctx, int kind, double bytes, double units) {
     if (!ctx->profile_on) return;
     scs_ctx::ProfileRecord rec;
@@ -319,6 +331,8 @@ int scs_ctx_create(int device, void *stream, scs_ctx **out) {
 int scs_ctx_destroy(scs_ctx *ctx) {
     if (!ctx) return SCS_OK;
     DeviceGuard guard(ctx->device);
+    for (scs_ctx *worker : ctx->workers) scs_ctx_destroy(worker);
+    ctx->workers.clear();
     cudaStreamSynchronize(ctx->stream);
     for (auto &buf : ctx->slots)
         if (buf.ptr) cudaFree(buf.ptr);

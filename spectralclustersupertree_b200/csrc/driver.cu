@@ -43,6 +43,9 @@ namespace scs {
 
 namespace {
 
+constexpr int kMaxWorkers = 4;        // host threads (contexts) driving staged nodes concurrently
+constexpr int kConcurrentMax = 4096;  // nodes above this many taxa run one at a time on the main context
+
 struct Stopwatch {
     double *sink;
     std::chrono::steady_clock::time_point t0;
@@ -133,7 +136,7 @@ class Driver {
 
     int run(const scs_forest *root) {
         num_taxa_ = scs_forest_num_taxa(root);
-        scratch_.resize(static_cast<size_t>(scs_host_threads()));
+        scratch_.resize(static_cast<size_t>(std::max(scs_host_threads(), kMaxWorkers)));
         for (Scratch &sc : scratch_) sc.reset(num_taxa_);
         std::vector<Task> wave, next;
         const int32_t root_slot = add_node(out_, -1, -1);
@@ -232,8 +235,8 @@ class Driver {
             }
             results.emplace_back();
             results.back().task = i;
-            if ((rc = split_large(task, results.back()))) return rc;
         }
+        if ((rc = split_large_all(wave, results))) return rc;
         if (!small.empty() && (rc = split_small(wave, small, results))) return rc;
 
         // children of every split node: restriction of the forests is independent per node, so the
@@ -267,34 +270,88 @@ class Driver {
                                 tree_weight);
     }
 
-    int split_large(Task &task, SplitResult &res) {
+    // Host buffers for one node's tours (one set per worker).
+    struct TourBuffers {
+        std::vector<int64_t> off;
+        std::vector<int32_t> tax, dep, root;
+        std::vector<double> val, wgt;
+    };
+
+    int split_large(scs_ctx *ctx, TourBuffers &buf, Scratch &scratch, Task &task, SplitResult &res) {
         const scs_forest *f = task.forest;
         const std::vector<int32_t> &taxa = task.taxa;
         const int n = static_cast<int>(taxa.size());
         const int T = scs_forest_num_trees(f);
         const int64_t L = scs_forest_num_leaves(f);
-        off_.resize(T + 1);
-        tax_.resize(L + 1);
-        dep_.resize(L + 1);
-        val_.resize(L + 1);
-        root_.resize(T + 1);
-        wgt_.resize(T + 1);
-        int rc;
-        {
-            Stopwatch sw(&out_.seconds[3]);
-            rc = tours_of(f, taxa, scratch_[0].local, off_.data(), tax_.data(), dep_.data(), val_.data(), root_.data(),
-                          wgt_.data());
-        }
+        buf.off.resize(T + 1);
+        buf.tax.resize(L + 1);
+        buf.dep.resize(L + 1);
+        buf.val.resize(L + 1);
+        buf.root.resize(T + 1);
+        buf.wgt.resize(T + 1);
+        int rc = tours_of(f, taxa, scratch.local, buf.off.data(), buf.tax.data(), buf.dep.data(), buf.val.data(),
+                          buf.root.data(), buf.wgt.data());
         if (rc) return rc;
         res.part.resize(n);
+        // the seed only picks the Lanczos start vector; tie it to the output slot so that it does not
+        // depend on the order in which concurrent workers finish
+        return scs_node_split_host(ctx, n, T, L, buf.off.data(), buf.tax.data(), buf.dep.data(), buf.val.data(),
+                                   buf.root.data(), buf.wgt.data(), contract_, seed_ + static_cast<uint64_t>(task.slot),
+                                   res.part.data(), &res.stats);
+    }
+
+    // The staged path is a chain of small launches and a few host round trips per node: latency, not
+    // throughput.  Nodes of one wave are independent, so those that fit a worker's workspace are driven
+    // by several host threads at once, each with its own context (stream + workspace) on the same GPU;
+    // the GPU overlaps their kernels.  The few very large nodes stay on the main context, one at a time.
+    int split_large_all(std::vector<Task> &wave, std::vector<SplitResult> &results) {
+        if (results.empty()) return SCS_OK;
         Stopwatch sw(&out_.seconds[0]);
-        rc = scs_node_split_host(ctx_, n, T, L, off_.data(), tax_.data(), dep_.data(), val_.data(), root_.data(),
-                                 wgt_.data(), contract_, seed_ + static_cast<uint64_t>(out_.nodes_large + out_.nodes_small),
-                                 res.part.data(), &res.stats);
+        std::vector<int> serial, concurrent;
+        for (int r = 0; r < static_cast<int>(results.size()); ++r) {
+            const Task &task = wave[results[r].task];
+            out_.pair_visits += scs_forest_pair_visits(task.forest);
+            (static_cast<int>(task.taxa.size()) > kConcurrentMax ? serial : concurrent).push_back(r);
+        }
+        out_.nodes_large += static_cast<int64_t>(results.size());
+        if (buffers_.empty()) buffers_.resize(1);
+        for (int r : serial) {
+            const int rc = split_large(ctx_, buffers_[0], scratch_[0], wave[results[r].task], results[r]);
+            if (rc) return rc;
+        }
+        const int jobs = static_cast<int>(concurrent.size());
+        if (jobs == 0) return SCS_OK;
+        const int workers = std::max(1, std::min({kMaxWorkers, jobs, scs_host_threads()}));
+        int rc = ensure_workers(ctx_, workers);
         if (rc) return rc;
-        out_.nodes_large += 1;
-        out_.pair_visits += scs_forest_pair_visits(f);
-        return SCS_OK;
+        if (static_cast<int>(buffers_.size()) < workers) buffers_.resize(workers);
+        int first_error = SCS_OK;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(workers) if (workers > 1)
+        for (int i = 0; i < jobs; ++i) {
+            const int w = omp_get_thread_num();
+            scs_ctx *ctx = w == 0 ? ctx_ : ctx_->workers[w - 1];
+            cudaSetDevice(ctx->device);
+            SplitResult &res = results[concurrent[i]];
+            const int status = split_large(ctx, buffers_[w], scratch_[w], wave[res.task], res);
+            if (status) {
+                if (ctx != ctx_) ctx_->last_error = ctx->last_error;
+#pragma omp atomic write
+                first_error = status;
+            }
+        }
+        // fold the workers' counters into the main context
+        for (scs_ctx *worker : ctx_->workers) {
+            ctx_->launches += worker->launches;
+            ctx_->h2d_bytes += worker->h2d_bytes;
+            ctx_->d2h_bytes += worker->d2h_bytes;
+            worker->launches = 0;
+            worker->h2d_bytes = worker->d2h_bytes = 0;
+            for (int k = 0; k < 8; ++k) {
+                ctx_->stage_seconds[k] += worker->stage_seconds[k];
+                worker->stage_seconds[k] = 0.0;
+            }
+        }
+        return first_error;
     }
 
     int split_small(std::vector<Task> &wave, const std::vector<size_t> &small, std::vector<SplitResult> &results) {
@@ -434,6 +491,7 @@ class Driver {
     scs_supertree &out_;
     int num_taxa_ = 0;
     std::vector<Scratch> scratch_;
+    std::vector<TourBuffers> buffers_;
     std::vector<int64_t> off_;
     std::vector<int32_t> tax_, dep_, root_, part_;
     std::vector<double> val_, wgt_;
