@@ -272,6 +272,8 @@ int64_t scs_supertree_shared_prefix(const scs_supertree *tree);
 /* Per wave of the breadth-first recursion: number of sub-problems and the largest one's taxon count.
  * Returns the number of waves; either array may be NULL (size them with scs_supertree_counters). */
 int scs_supertree_wave_info(const scs_supertree *tree, int32_t *tasks, int32_t *max_n);
+/* Per wave, 3 doubles: seconds in GPU splits, in forest restriction, in the whole wave. */
+int scs_supertree_wave_seconds(const scs_supertree *tree, double *seconds3);
 int scs_supertree_destroy(scs_supertree *tree);
 int64_t scs_supertree_num_nodes(const scs_supertree *tree);
 int scs_supertree_nodes(const scs_supertree *tree, int32_t *parent, int32_t *taxon);

@@ -126,6 +126,7 @@ SIGNATURES: dict[str, tuple] = {
     "scs_supertree_build_sharded": (c_int, [_P, _P, c_int, c_int, c_uint64, c_int, c_int, c_int, POINTER(_P)]),
     "scs_supertree_shared_prefix": (c_int64, [_P]),
     "scs_supertree_wave_info": (c_int, [_P, _P, _P]),
+    "scs_supertree_wave_seconds": (c_int, [_P, _P]),
     "scs_supertree_destroy": (c_int, [_P]),
     "scs_supertree_num_nodes": (c_int64, [_P]),
     "scs_supertree_nodes": (c_int, [_P, _P, _P]),

@@ -36,6 +36,7 @@ struct scs_supertree {
     int64_t pair_visits = 0;
     double seconds[4] = {0, 0, 0, 0};  // large-node splits, small-node batches, restriction, tours
     std::vector<int32_t> wave_tasks, wave_max_n;  // per wave: sub-problems in it, largest taxon count
+    std::vector<double> wave_seconds;             // per wave: 3 numbers (GPU splits, restriction, everything)
     int64_t shared_prefix = 0;  // sharded build: output nodes [0, shared_prefix) are identical on every rank
 };
 
@@ -152,7 +153,12 @@ class Driver {
             out_.wave_tasks.push_back(static_cast<int32_t>(wave.size()));
             out_.wave_max_n.push_back(max_n);
             next.clear();
+            const double before_gpu = out_.seconds[0] + out_.seconds[1], before_restrict = out_.seconds[2];
+            const auto wave_start = std::chrono::steady_clock::now();
             rc = process_wave(wave, next);
+            out_.wave_seconds.push_back(out_.seconds[0] + out_.seconds[1] - before_gpu);
+            out_.wave_seconds.push_back(out_.seconds[2] - before_restrict);
+            out_.wave_seconds.push_back(std::chrono::duration<double>(std::chrono::steady_clock::now() - wave_start).count());
             for (Task &t : wave)
                 if (t.owned) scs_forest_destroy(t.forest);
             wave.clear();
@@ -621,6 +627,12 @@ int scs_supertree_build(scs_ctx *ctx, const scs_forest *forest, int weighting, i
 }
 
 int64_t scs_supertree_shared_prefix(const scs_supertree *tree) { return tree ? tree->shared_prefix : 0; }
+
+int scs_supertree_wave_seconds(const scs_supertree *tree, double *seconds3) {
+    if (!tree || !seconds3) return SCS_ERR_INVALID;
+    std::memcpy(seconds3, tree->wave_seconds.data(), sizeof(double) * tree->wave_seconds.size());
+    return static_cast<int>(tree->wave_seconds.size() / 3);
+}
 
 int scs_supertree_wave_info(const scs_supertree *tree, int32_t *tasks, int32_t *max_n) {
     if (!tree) return SCS_ERR_INVALID;

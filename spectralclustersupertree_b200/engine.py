@@ -207,10 +207,13 @@ class Engine:
             wave_tasks = np.zeros(max(waves.value, 1), dtype=np.int32)
             wave_max_n = np.zeros(max(waves.value, 1), dtype=np.int32)
             self._lib.scs_supertree_wave_info(handle, ptr(wave_tasks), ptr(wave_max_n))
+            wave_seconds = np.zeros((max(waves.value, 1), 3))
+            self._lib.scs_supertree_wave_seconds(handle, ptr(wave_seconds))
             out = {"parent": parent, "taxon": taxon, "nodes_small": small.value, "nodes_large": large.value,
                    "waves": waves.value, "pair_visits": pairs.value, "records": [],
                    "shared_prefix": int(self._lib.scs_supertree_shared_prefix(handle)),
                    "wave_tasks": wave_tasks[: waves.value].tolist(), "wave_max_n": wave_max_n[: waves.value].tolist(),
+                   "wave_seconds": wave_seconds[: waves.value].tolist(),
                    "seconds": dict(zip(("large_nodes", "small_batches", "restrict", "tours"), seconds.tolist(), strict=True))}  # fmt: skip
             if record:
                 for i in range(self._lib.scs_supertree_num_records(handle)):

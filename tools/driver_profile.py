@@ -34,6 +34,10 @@ def main() -> None:
               f"small {built['nodes_small']} large {built['nodes_large']} waves {built['waves']} "
               f"launches {engine.launch_count - launches}")
         print("   staged path: " + ", ".join(f"{k} {v:.3f}" for k, v in stages.items()))
+        if i == 2:
+            print("   wave: tasks max_n | gpu ms, restrict ms, total ms")
+            for w, (tasks, max_n, sec) in enumerate(zip(built["wave_tasks"], built["wave_max_n"], built["wave_seconds"], strict=True)):
+                print(f"   {w:3d}: {tasks:5d} {max_n:6d} | {1e3 * sec[0]:7.2f} {1e3 * sec[1]:7.2f} {1e3 * sec[2]:7.2f}")
 
 
 if __name__ == "__main__":
