@@ -365,7 +365,9 @@ int launch_rows(scs_ctx *ctx, int n, int words, int cols_per_chunk, int nchunks,
                 const int32_t *occ, double *W, int32_t *C, uint32_t *adj_bits, uint32_t *max_bits,
                 double *degree_part, int32_t *bad) {
     auto kernel = pcg_rows_kernel<CountT, kWriteC>;
-    SCS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    // always the same (maximal) opt-in size: contexts on other host threads launch this kernel concurrently
+    const size_t optin = ctx->smem_optin > 4096 ? ctx->smem_optin - 2048 : 46 * 1024;
+    SCS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(optin)));
     dim3 grid(n, nchunks);
     if (n >= kProfileMinSize) {
         // algorithmic bytes: W + both bit matrices + occ/degree written once, C if asked

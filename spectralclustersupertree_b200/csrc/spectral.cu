@@ -969,8 +969,7 @@ int spectral_bipartition(scs_ctx *ctx, int m, const double *W, const double *deg
     if (P <= 8192) {
         auto kernel = two_means_1d<true>;
         const size_t smem = static_cast<size_t>(P) * sizeof(double);
-        if (smem > 48 * 1024)
-            SCS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        SCS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));  // constant
         kernel<<<1, kOneCta, smem, ctx->stream>>>(m, P, yvec, b.isd, embed, sorted, side, b.ritz + 12);
     } else {
         two_means_1d<false><<<1, kOneCta, 0, ctx->stream>>>(m, P, yvec, b.isd, embed, sorted, side, b.ritz + 12);
