@@ -122,7 +122,7 @@ int contract_with_labels(scs_ctx *ctx, int n, const double *W, const uint32_t *a
     fill_members<<<blocks, 256, 0, ctx->stream>>>(n, group, gptr, cursor, members);
     SCS_LAUNCHED(ctx, "fill_members");
 
-    const size_t budget = ctx->smem_optin > 4096 ? ctx->smem_optin - 2048 : 46 * 1024;
+    const size_t budget = ctx->smem_optin > 8192 ? ctx->smem_optin - 4096 : 44 * 1024;
     const int max_cols = static_cast<int>(budget / sizeof(unsigned long long));
     int nchunks = ceil_div(m, max_cols);
     const int cols_per_chunk = ceil_div(m, nchunks);

@@ -366,7 +366,7 @@ int launch_rows(scs_ctx *ctx, int n, int words, int cols_per_chunk, int nchunks,
                 double *degree_part, int32_t *bad) {
     auto kernel = pcg_rows_kernel<CountT, kWriteC>;
     // always the same (maximal) opt-in size: contexts on other host threads launch this kernel concurrently
-    const size_t optin = ctx->smem_optin > 4096 ? ctx->smem_optin - 2048 : 46 * 1024;
+    const size_t optin = ctx->smem_optin > 8192 ? ctx->smem_optin - 4096 : 44 * 1024;
     SCS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(optin)));
     dim3 grid(n, nchunks);
     if (n >= kProfileMinSize) {
@@ -441,7 +441,7 @@ int pcg_build(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offsets
     // column chunking: the whole row if it fits in shared memory, else equal chunks of 32-multiples
     const bool narrow = T < 65536;
     const size_t per_col = sizeof(double) + (narrow ? sizeof(uint16_t) : sizeof(int32_t));
-    const size_t budget = ctx->smem_optin > 4096 ? ctx->smem_optin - 2048 : 46 * 1024;
+    const size_t budget = ctx->smem_optin > 8192 ? ctx->smem_optin - 4096 : 44 * 1024;
     const int max_cols = static_cast<int>((budget / per_col) / 32 * 32);
     const int padded = words * 32;
     int nchunks = ceil_div(padded, max_cols);
