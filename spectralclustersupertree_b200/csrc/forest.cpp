@@ -24,6 +24,7 @@
 
 #include "forest.hpp"
 
+#include <malloc.h>
 #include <omp.h>
 
 static int g_host_threads = 0;
@@ -50,6 +51,16 @@ void finish_tree(scs_forest &f, int64_t base, int64_t count) {
 
 extern "C" {
 
+static void tune_allocator_once() {
+    static bool done = false;
+    if (done) return;
+    done = true;
+    // forests of tens of MB are allocated and freed at every recursion node: keep the freed blocks in
+    // the process heap instead of returning them to the OS, so re-use does not page-fault again
+    mallopt(M_MMAP_THRESHOLD, 32 << 20);  // glibc caps this at 32 MB
+    mallopt(M_TRIM_THRESHOLD, 1 << 30);
+}
+
 int scs_set_host_threads(int threads) {
     if (threads < 0) return SCS_ERR_INVALID;
     g_host_threads = threads;
@@ -65,6 +76,7 @@ int scs_forest_create(int T, const int64_t *node_offsets, const int32_t *parent,
     const int64_t M = node_offsets[T];
     if (M < 0 || (M > 0 && (!parent || !taxon))) return SCS_ERR_INVALID;
     if (T > 0 && !tree_weight) return SCS_ERR_INVALID;
+    tune_allocator_once();
     scs_forest *f = new (std::nothrow) scs_forest();
     if (!f) return SCS_ERR_INVALID;
     f->num_taxa = num_taxa;
@@ -147,7 +159,8 @@ int scs_forest_induce(const scs_forest *f, const uint8_t *keep, scs_forest **out
     const int T = f->num_trees();
     const int64_t M = f->node_offsets.back();
     // pass 1 (trees in parallel): which nodes survive, and their index in the restricted tree
-    std::vector<int32_t> new_index(M > 0 ? M : 1);
+    FlatArray<int32_t> new_index;  // written for every node of every kept tree in pass 1
+    new_index.resize_uninitialized(M > 0 ? M : 1);
     std::vector<int32_t> kept_nodes(T + 1, 0), kept_tips(T + 1, 0);
     const bool threaded = M > kParallelNodes;
 #pragma omp parallel if (threaded) num_threads(scs_host_threads())
@@ -192,10 +205,10 @@ int scs_forest_induce(const scs_forest *f, const uint8_t *keep, scs_forest **out
         g->source.push_back(f->source[t]);
     }
     const int64_t M_out = out_base[T];
-    g->parent.resize(M_out);
-    g->length.resize(M_out);
-    g->support.resize(M_out);
-    g->taxon.resize(M_out);
+    g->parent.resize_uninitialized(M_out);
+    g->length.resize_uninitialized(M_out);
+    g->support.resize_uninitialized(M_out);
+    g->taxon.resize_uninitialized(M_out);
     // pass 2 (trees in parallel): write the restricted trees
 #pragma omp parallel for schedule(dynamic, 4) if (threaded) num_threads(scs_host_threads())
     for (int t = 0; t < T; ++t) {

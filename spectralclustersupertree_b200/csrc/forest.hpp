@@ -2,15 +2,53 @@
 #pragma once
 
 #include <cstdint>
+#include <cstdlib>
+#include <cstring>
 #include <vector>
+
+// A plain array that is NOT value-initialised when sized: the per-node arrays of a restricted forest
+// are written exactly once, by all host threads, so a serial zero-fill (and its serial page faults)
+// would cost as much as the restriction itself.
+template <typename T>
+class FlatArray {
+  public:
+    FlatArray() = default;
+    FlatArray(const FlatArray &) = delete;
+    FlatArray &operator=(const FlatArray &) = delete;
+    ~FlatArray() { std::free(data_); }
+    void resize_uninitialized(size_t n) {
+        std::free(data_);
+        data_ = n ? static_cast<T *>(std::malloc(n * sizeof(T))) : nullptr;
+        size_ = data_ ? n : 0;
+    }
+    void assign(const T *first, const T *last) {
+        resize_uninitialized(static_cast<size_t>(last - first));
+        if (size_) std::memcpy(data_, first, size_ * sizeof(T));
+    }
+    void assign(size_t n, T value) {
+        resize_uninitialized(n);
+        for (size_t i = 0; i < size_; ++i) data_[i] = value;
+    }
+    T *data() { return data_; }
+    const T *data() const { return data_; }
+    size_t size() const { return size_; }
+    T &operator[](size_t i) { return data_[i]; }
+    const T &operator[](size_t i) const { return data_[i]; }
+    const T *begin() const { return data_; }
+    const T *end() const { return data_ + size_; }
+
+  private:
+    T *data_ = nullptr;
+    size_t size_ = 0;
+};
 
 struct scs_forest {
     int num_taxa = 0;
     std::vector<int64_t> node_offsets{0};  // [T + 1]
-    std::vector<int32_t> parent;           // index within the tree, -1 for the root; parent < child
-    std::vector<double> length;            // NaN = missing
-    std::vector<double> support;           // NaN = missing
-    std::vector<int32_t> taxon;            // tips: global taxon id, internal nodes: -1
+    FlatArray<int32_t> parent;             // index within the tree, -1 for the root; parent < child
+    FlatArray<double> length;              // NaN = missing
+    FlatArray<double> support;             // NaN = missing
+    FlatArray<int32_t> taxon;              // tips: global taxon id, internal nodes: -1
     std::vector<double> weight;            // [T]
     std::vector<int32_t> source;           // [T] index of the tree in the forest first created
     std::vector<int64_t> leaf_offsets{0};  // [T + 1] tips that appear in tours (a lone tip has none)
