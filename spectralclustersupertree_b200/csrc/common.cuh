@@ -100,6 +100,9 @@ struct scs_ctx {
     bool small_configured = false;
     bool batch_configured = false;
     bool tail_configured = false;
+    bool rows_configured[4] = {false, false, false, false};
+    bool contract_configured = false;
+    bool kmeans_configured = false;
     int small_limit = 64;  // nodes up to this size take the one-CTA path (0 disables it)
     double pending_units = 0.0;  // leaf-pair visits of the node being built (set by host entry points)
     cudaEvent_t timer_start = nullptr, timer_stop = nullptr;

@@ -131,7 +131,10 @@ int contract_with_labels(scs_ctx *ctx, int n, const double *W, const uint32_t *a
     double *part;
     if ((rc = reserve_as(ctx, SLOT_DEGREE_PART, static_cast<size_t>(m) * nchunks, &part))) return rc;
     // always the same (maximal) opt-in size: contexts on other host threads launch this kernel concurrently
-    SCS_CUDA(ctx, cudaFuncSetAttribute(contract_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(budget)));
+    if (!ctx->contract_configured) {
+        SCS_CUDA(ctx, cudaFuncSetAttribute(contract_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(budget)));
+        ctx->contract_configured = true;
+    }
     contract_rows<<<dim3(m, nchunks), kThreads, smem, ctx->stream>>>(n, m, words, cols_per_chunk, W, adj_bits, group,
                                                                      gptr, members, Wc, part);
     SCS_LAUNCHED(ctx, "contract_rows");

@@ -250,7 +250,7 @@ class Driver {
         {
             Stopwatch sw(&out_.seconds[2]);
             const int count = static_cast<int>(results.size());
-#pragma omp parallel for schedule(dynamic, 1) if (count >= 8) num_threads(scs_host_threads())
+#pragma omp parallel for schedule(dynamic, 1) if (count >= 2 * scs_host_threads()) num_threads(scs_host_threads())
             for (int r = 0; r < count; ++r)
                 plan(wave[results[r].task], results[r], scratch_[static_cast<size_t>(omp_get_thread_num())]);
         }

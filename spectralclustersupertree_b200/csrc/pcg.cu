@@ -366,8 +366,12 @@ int launch_rows(scs_ctx *ctx, int n, int words, int cols_per_chunk, int nchunks,
                 double *degree_part, int32_t *bad) {
     auto kernel = pcg_rows_kernel<CountT, kWriteC>;
     // always the same (maximal) opt-in size: contexts on other host threads launch this kernel concurrently
-    const size_t optin = ctx->smem_optin > 8192 ? ctx->smem_optin - 4096 : 44 * 1024;
-    SCS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(optin)));
+    bool &configured = ctx->rows_configured[(sizeof(CountT) == 2 ? 0 : 2) + (kWriteC ? 1 : 0)];
+    if (!configured) {
+        const size_t optin = ctx->smem_optin > 8192 ? ctx->smem_optin - 4096 : 44 * 1024;
+        SCS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(optin)));
+        configured = true;
+    }
     dim3 grid(n, nchunks);
     if (n >= kProfileMinSize) {
         // algorithmic bytes: W + both bit matrices + occ/degree written once, C if asked

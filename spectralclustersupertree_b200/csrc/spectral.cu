@@ -969,7 +969,10 @@ int spectral_bipartition(scs_ctx *ctx, int m, const double *W, const double *deg
     if (P <= 8192) {
         auto kernel = two_means_1d<true>;
         const size_t smem = static_cast<size_t>(P) * sizeof(double);
-        SCS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));  // constant
+        if (!ctx->kmeans_configured) {
+            SCS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
+            ctx->kmeans_configured = true;
+        }
         kernel<<<1, kOneCta, smem, ctx->stream>>>(m, P, yvec, b.isd, embed, sorted, side, b.ritz + 12);
     } else {
         two_means_1d<false><<<1, kOneCta, 0, ctx->stream>>>(m, P, yvec, b.isd, embed, sorted, side, b.ritz + 12);
