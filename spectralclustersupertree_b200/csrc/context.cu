@@ -27,19 +27,20 @@ int reserve(scs_ctx *ctx, Slot slot, size_t bytes, void **out) {
     DeviceBuffer &buf = ctx->slots[slot];
     if (bytes == 0) bytes = 16;
     if (buf.bytes < bytes) {
-        // grow geometrically: recursion nodes shrink, so the first (largest) node sizes everything
-        size_t want = bytes + bytes / 8 + 256;
+        // Stream-ordered allocation: growing a slot neither synchronises the device (cudaFree would)
+        // nor stalls the other contexts working on this GPU; the old block is released in stream
+        // order, after the work already queued on it.  Recursion nodes shrink, so the first (largest)
+        // node sizes everything; the pool keeps released blocks for the next growth.
+        const size_t want = bytes + bytes / 4 + 256;
         if (buf.ptr) {
-            // work queued on the stream may still read the old allocation
-            SCS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            SCS_CUDA(ctx, cudaFree(buf.ptr));
+            SCS_CUDA(ctx, cudaFreeAsync(buf.ptr, ctx->stream));
             buf.ptr = nullptr;
             buf.bytes = 0;
         }
-        cudaError_t err = cudaMalloc(&buf.ptr, want);
+        cudaError_t err = cudaMallocAsync(&buf.ptr, want, ctx->stream);
         if (err != cudaSuccess) {
             buf.ptr = nullptr;
-            return fail(ctx, SCS_ERR_CUDA, "cudaMalloc (workspace)", err);
+            return fail(ctx, SCS_ERR_CUDA, "cudaMallocAsync (workspace)", err);
         }
         buf.bytes = want;
     }
@@ -55,7 +56,7 @@ int reserve_pinned(scs_ctx *ctx, size_t bytes, void **out) {
             ctx->pinned = nullptr;
             ctx->pinned_bytes = 0;
         }
-        size_t want = bytes < 4096 ? 4096 : bytes + bytes / 8;
+        size_t want = bytes < 4096 ? 4096 : 2 * bytes;
         SCS_CUDA(ctx, cudaMallocHost(&ctx->pinned, want));
         ctx->pinned_bytes = want;
     }
@@ -313,6 +314,15 @@ int scs_ctx_create(int device, void *stream, scs_ctx **out) {
         delete ctx;
         return SCS_ERR_CUDA;
     }
+    {
+        // never hand pooled workspace back to the driver between recursion nodes
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t threshold = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+        }
+        cudaGetLastError();
+    }
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
     if (stream) {
@@ -335,7 +345,8 @@ int scs_ctx_destroy(scs_ctx *ctx) {
     ctx->workers.clear();
     cudaStreamSynchronize(ctx->stream);
     for (auto &buf : ctx->slots)
-        if (buf.ptr) cudaFree(buf.ptr);
+        if (buf.ptr) cudaFreeAsync(buf.ptr, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->pinned_io) cudaFreeHost(ctx->pinned_io);
     for (auto &rec : ctx->profile) {
@@ -543,7 +554,7 @@ int scs_node_split_host(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *le
             ctx->pinned_io = nullptr;
             ctx->pinned_io_bytes = 0;
         }
-        const size_t want = total + total / 4 + 4096;
+        const size_t want = 2 * total + 4096;  // pinned allocations synchronise the device: grow rarely
         SCS_CUDA(ctx, cudaMallocHost(&ctx->pinned_io, want));
         ctx->pinned_io_bytes = want;
     }

@@ -542,7 +542,7 @@ int scs_nodes_split_small_host(scs_ctx *ctx, int num_nodes, const scs_small_node
             ctx->pinned_io = nullptr;
             ctx->pinned_io_bytes = 0;
         }
-        const size_t want = total + total / 4 + 4096;
+        const size_t want = 2 * total + 4096;
         SCS_CUDA(ctx, cudaMallocHost(&ctx->pinned_io, want));
         ctx->pinned_io_bytes = want;
     }
