@@ -45,8 +45,9 @@ typedef enum {
                                  (sklearn raises ValueError there, _spectral.py:699) */
     SCS_ERR_NO_CONVERGE = -5, /* eigensolver hit its restart limit */
     SCS_ERR_INPUT = -6,       /* malformed leaf tour (taxon id out of range, ...) */
-    SCS_ERR_EMPTY = -7        /* a recursion node was left without source trees (the reference raises
+    SCS_ERR_EMPTY = -7,       /* a recursion node was left without source trees (the reference raises
                                  ValueError "There must be at least one tree ...", scs.py:63-65) */
+    SCS_ERR_PEER = -8         /* a device-side wait for a peer GPU ran out of time (sharded nodes) */
 } scs_status;
 
 /* What happened at one recursion node (the "near-ties reported" clause of the parity contract). */
@@ -286,6 +287,38 @@ int64_t scs_supertree_num_records(const scs_supertree *tree);
 int scs_supertree_record_size(const scs_supertree *tree, int64_t index);
 int scs_supertree_record(const scs_supertree *tree, int64_t index, int32_t *taxa, int32_t *part,
                          scs_node_stats *stats);
+
+/* ---- one recursion node over several GPUs of one NVLink box (one process per GPU) ------------- *
+ * The reference is single-process (scs.py:239 n_jobs=1); this is the B200 answer to its largest
+ * recursion nodes.  A node with >= min_n taxa is ROW-SHARDED: rank r builds and keeps rows
+ * [r * ceil(n / world), ...) of W (every row is its own tree-ordered sum, so the result stays bit-exact),
+ * pushes its adjacency-bit rows and degrees into the peers' exchange windows over NVLink, and every
+ * Lanczos step is one kernel that computes the rank's slice of y = D^-1/2 W D^-1/2 x, stores it into
+ * every peer's window and waits for the peers' slices (compute + all-gather + barrier in one launch).
+ * Components, contraction groups and the Lanczos vector work are replicated, so every rank ends with
+ * the same partition as the single-GPU path, bit for bit.
+ *
+ * Protocol: every rank calls scs_shard_create (allocates its window, returns a cudaIpcMemHandle_t as
+ * 64 opaque bytes), the caller all-gathers the handles (torch.distributed, MPI, a file ...), every
+ * rank calls scs_shard_connect_ipc with all of them in rank order.  While engaged, every rank must
+ * issue the same sequence of node calls (scs_node_split_* / scs_supertree_build_sharded do).
+ * scs_shard_destroy must only be called after all ranks finished their last node (host barrier). */
+#define SCS_IPC_HANDLE_BYTES 64
+int scs_shard_create(scs_ctx *ctx, int rank, int world, int n_max, unsigned char *handle_out);
+int scs_shard_connect_ipc(scs_ctx *ctx, const unsigned char *handles /* world * 64 bytes */);
+/* Peers that live in the same process (one context per GPU, or several on one GPU): plain pointers. */
+int scs_shard_window(scs_ctx *ctx, void **window_dev, size_t *bytes);
+int scs_shard_connect_ptrs(scs_ctx *ctx, void *const *windows /* world pointers, own included */);
+/* While engaged, nodes with min_n <= n <= n_max handed to this context take the sharded path. */
+int scs_shard_engage(scs_ctx *ctx, int on);
+/* min_n: smallest node that is shared out (default 4096; <= 0 keeps it); timeout_seconds: bound on
+ * every device-side wait for a peer (default 20; <= 0 keeps it). */
+int scs_shard_configure(scs_ctx *ctx, int min_n, double timeout_seconds);
+/* A barrier over the ranks through the windows (signal every peer, wait for every peer). */
+int scs_shard_barrier(scs_ctx *ctx);
+/* Recursion nodes this context processed on the sharded path. */
+int64_t scs_shard_nodes(const scs_ctx *ctx);
+int scs_shard_destroy(scs_ctx *ctx);
 
 #ifdef __cplusplus
 }

@@ -21,6 +21,8 @@ SCS_ERR_TOO_SMALL = -4
 SCS_ERR_NO_CONVERGE = -5
 SCS_ERR_INPUT = -6
 SCS_ERR_EMPTY = -7
+SCS_ERR_PEER = -8
+IPC_HANDLE_BYTES = 64
 
 
 class NodeStats(ctypes.Structure):
@@ -135,6 +137,15 @@ SIGNATURES: dict[str, tuple] = {
     "scs_supertree_num_records": (c_int64, [_P]),
     "scs_supertree_record_size": (c_int, [_P, c_int64]),
     "scs_supertree_record": (c_int, [_P, c_int64, _P, _P, POINTER(NodeStats)]),
+    "scs_shard_create": (c_int, [_P, c_int, c_int, c_int, _P]),
+    "scs_shard_connect_ipc": (c_int, [_P, _P]),
+    "scs_shard_window": (c_int, [_P, POINTER(_P), POINTER(c_size_t)]),
+    "scs_shard_connect_ptrs": (c_int, [_P, _P]),
+    "scs_shard_engage": (c_int, [_P, c_int]),
+    "scs_shard_configure": (c_int, [_P, c_int, c_double]),
+    "scs_shard_barrier": (c_int, [_P]),
+    "scs_shard_nodes": (c_int64, [_P]),
+    "scs_shard_destroy": (c_int, [_P]),
 }
 
 _LIB: ctypes.CDLL | None = None

@@ -19,7 +19,7 @@ CSRC = PKG / "csrc"
 INCLUDE = PKG.parent / "include"
 LIB = PKG / "libscs_b200.so"
 
-SOURCES = ["context.cu", "pcg.cu", "components.cu", "contract.cu", "spectral.cu", "small.cu", "driver.cu", "forest.cpp"]
+SOURCES = ["context.cu", "pcg.cu", "components.cu", "contract.cu", "spectral.cu", "small.cu", "shard.cu", "driver.cu", "forest.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
@@ -42,7 +42,7 @@ def needs_build() -> bool:
     if not LIB.is_file():
         return True
     built = LIB.stat().st_mtime
-    deps = [CSRC / s for s in SOURCES] + [CSRC / "common.cuh", CSRC / "forest.hpp", INCLUDE / "scs_b200.h"]
+    deps = [CSRC / s for s in SOURCES] + [CSRC / "common.cuh", CSRC / "shard.cuh", CSRC / "forest.hpp", INCLUDE / "scs_b200.h"]
     return any(d.stat().st_mtime > built for d in deps)
 
 

@@ -69,6 +69,49 @@ enum Slot : int {
     SLOT_COUNT
 };
 
+constexpr int kMaxPeers = 16;  // GPUs that can share one recursion node (shard.cu)
+
+// Where the pieces of a rank's exchange window live (byte offsets; the same on every rank).
+struct ShardLayout {
+    size_t vec[2] = {0, 0};  // double-buffered all-gather target of the sharded matvec, n_max doubles each
+    size_t degree = 0, degree_c = 0;  // n_max doubles each
+    size_t adj_bits = 0, max_bits = 0;  // n_max * words(n_max) uint32 each
+    size_t W = 0;  // this rank's row block of W: rows_per_rank(n_max) * n_max doubles
+    size_t total = 0;
+};
+
+// Row-sharded recursion nodes over the GPUs of one box (shard.cu / shard.cuh).
+struct ShardState {
+    bool connected = false;  // peers' windows are mapped
+    bool engaged = false;    // the caller guarantees that every rank issues the same node calls
+    int rank = 0, world = 1;
+    int n_max = 0;           // largest node the window was sized for
+    int min_n = 4096;        // nodes with fewer taxa stay on one GPU
+    unsigned long long epoch = 0;  // synchronisation points issued so far
+    int parity = 0;          // which vec buffer the next sharded matvec fills
+    double timeout_s = 20.0;  // bound on every device-side wait
+    unsigned char *window = nullptr;  // own window (cudaMalloc)
+    unsigned char *peer[kMaxPeers] = {};  // mapped windows, peer[rank] == window
+    bool opened[kMaxPeers] = {};  // mapped with cudaIpcOpenMemHandle by this context
+    ShardLayout layout;
+    int64_t nodes = 0;  // recursion nodes that took the sharded path
+};
+
+// Rows [row0, row1) of a row-sharded matrix live on this rank; row1 < 0 means "not sharded".
+struct RowBlock {
+    int row0 = 0, row1 = -1;
+    bool sharded() const { return row1 >= 0; }
+};
+
+inline int shard_rows_per_rank(int n, int world) { return (n + world - 1) / world; }
+inline RowBlock shard_block(int n, int rank, int world) {
+    const int per = shard_rows_per_rank(n, world);
+    RowBlock b;
+    b.row0 = rank * per < n ? rank * per : n;
+    b.row1 = b.row0 + per < n ? b.row0 + per : n;
+    return b;
+}
+
 }  // namespace scs
 
 struct scs_ctx {
@@ -109,6 +152,7 @@ struct scs_ctx {
     // shape of the node most recently processed by scs_node_split_host
     int last_n = 0;
     int last_m = 0;
+    scs::ShardState shard;
 };
 
 namespace scs {
@@ -174,10 +218,12 @@ __device__ __forceinline__ double order_value(unsigned long long k) {
 int ensure_workers(scs_ctx *ctx, int count);
 
 // ---- stage entry points implemented in the other translation units ------------------------
+// `rows`: build only those rows (W / C then point at the row block: row a is at (a - row0) * n; the
+// bit matrices and degree stay full-size and are indexed by the global row).
 int pcg_build(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offsets,
               const int32_t *leaf_taxon, const int32_t *adj_depth, const double *adj_val,
               const int32_t *root_depth, const double *tree_weight, double *W, int32_t *C,
-              int32_t *occ, uint32_t *adj_bits, uint32_t *max_bits, double *degree);
+              int32_t *occ, uint32_t *adj_bits, uint32_t *max_bits, double *degree, RowBlock rows = RowBlock());
 
 int components(scs_ctx *ctx, int n, const uint32_t *bits, int32_t *label, int32_t *n_components_host);
 
@@ -185,11 +231,15 @@ int components_async(scs_ctx *ctx, int n, const uint32_t *bits, int32_t *label, 
 
 int contract(scs_ctx *ctx, int n, const double *W, const uint32_t *adj_bits, const uint32_t *max_bits,
              int32_t *group, int32_t *m_host, double *Wc, double *degree_c);
+// `rows` (sharded): only contracted rows [row0, row1) are produced, into the row block Wc; W is then read
+// through the peers' windows (row u of W lives on rank u / rows_per_rank(n)).
 int contract_with_labels(scs_ctx *ctx, int n, const double *W, const uint32_t *adj_bits, const int32_t *label, int m,
-                         int32_t *group, double *Wc, double *degree_c);
+                         int32_t *group, double *Wc, double *degree_c, RowBlock rows = RowBlock());
 
+// `rows` (sharded): W is this rank's row block; every operator application is the fused
+// matvec + all-gather over the peers' windows, everything else is replicated on every rank.
 int spectral_bipartition(scs_ctx *ctx, int m, const double *W, const double *degree, uint64_t seed,
-                         int32_t *side, scs_node_stats *stats_host);
+                         int32_t *side, scs_node_stats *stats_host, RowBlock rows = RowBlock());
 
 int normalized_matvec(scs_ctx *ctx, int m, const double *W, const double *isd, const double *x, double *y);
 
@@ -211,5 +261,23 @@ int node_split(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offset
                const int32_t *adj_depth, const double *adj_val, const int32_t *root_depth,
                const double *tree_weight, int contract_edges, uint64_t seed, int32_t *part_dev,
                int32_t *part_host, scs_node_stats *stats);
+
+// ---- sharded nodes (shard.cu) -----------------------------------------------------------------------
+bool shard_applies(const scs_ctx *ctx, int n);
+// A barrier over the ranks on the context's stream (signal every peer, wait for every peer).
+int shard_barrier(scs_ctx *ctx);
+// Copy [offset, offset + bytes) of this rank's window into the same place of every peer's window.
+int shard_push(scs_ctx *ctx, size_t offset, size_t bytes);
+// Next epoch / vec buffer for a fused matvec + all-gather (spectral.cu launches the kernel itself).
+struct ShardMatvecTicket {
+    unsigned long long epoch;
+    size_t vec_offset;
+    unsigned long long timeout_ns;
+};
+ShardMatvecTicket shard_next_matvec(scs_ctx *ctx);
+int node_split_sharded(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offsets, const int32_t *leaf_taxon,
+                       const int32_t *adj_depth, const double *adj_val, const int32_t *root_depth,
+                       const double *tree_weight, int contract_edges, uint64_t seed, int32_t *part_dev,
+                       int32_t *part_host, scs_node_stats *stats);
 
 }  // namespace scs

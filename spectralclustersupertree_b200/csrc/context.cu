@@ -142,6 +142,9 @@ int node_split(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offset
                const int32_t *adj_depth, const double *adj_val, const int32_t *root_depth,
                const double *tree_weight, int contract_edges, uint64_t seed, int32_t *part_dev,
                int32_t *part_host, scs_node_stats *stats) {
+    if (shard_applies(ctx, n))
+        return node_split_sharded(ctx, n, T, L, leaf_offsets, leaf_taxon, adj_depth, adj_val, root_depth, tree_weight,
+                                  contract_edges, seed, part_dev, part_host, stats);
     const int words = scs_bit_words(n);
     const size_t nn = static_cast<size_t>(n) * n;
     double *W, *Wc, *degree, *degree_c;
@@ -289,6 +292,7 @@ const char *scs_status_string(int status) {
     case SCS_ERR_NO_CONVERGE: return "eigensolver did not converge";
     case SCS_ERR_INPUT: return "malformed input";
     case SCS_ERR_EMPTY: return "there must be at least one tree to make a supertree";
+    case SCS_ERR_PEER: return "a wait for a peer GPU timed out";
     default: return "unknown status";
     }
 }
@@ -344,6 +348,7 @@ int scs_ctx_destroy(scs_ctx *ctx) {
     for (scs_ctx *worker : ctx->workers) scs_ctx_destroy(worker);
     ctx->workers.clear();
     cudaStreamSynchronize(ctx->stream);
+    scs_shard_destroy(ctx);
     for (auto &buf : ctx->slots)
         if (buf.ptr) cudaFreeAsync(buf.ptr, ctx->stream);
     cudaStreamSynchronize(ctx->stream);

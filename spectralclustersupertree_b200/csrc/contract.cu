@@ -37,16 +37,24 @@ __global__ void fill_members(int n, const int32_t *__restrict__ group, const int
     members[group_ptr[gidx] + atomicAdd(&cursor[gidx], 1)] = v;
 }
 
-// one CTA per contracted vertex A (and per column chunk of the contracted matrix)
+// Where the rows of W live: one block when the node is on one GPU, else rank r's window holds rows
+// [r * rows_per_rank, (r + 1) * rows_per_rank) and the others are read over NVLink.
+struct WRows {
+    const double *block[kMaxPeers];
+    int rows_per_rank;
+};
+
+// one CTA per contracted vertex A (and per column chunk of the contracted matrix); the CTA of
+// blockIdx.x produces contracted row A = A0 + blockIdx.x into row blockIdx.x of Wc
 __global__ void __launch_bounds__(kThreads)
-contract_rows(int n, int m, int words, int cols_per_chunk, const double *__restrict__ W,
+contract_rows(int n, int m, int A0, int words, int cols_per_chunk, const WRows W,
               const uint32_t *__restrict__ adj_bits, const int32_t *__restrict__ group,
               const int32_t *__restrict__ group_ptr, const int32_t *__restrict__ members,
               double *__restrict__ Wc, double *__restrict__ degree_part) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long *best = reinterpret_cast<unsigned long long *>(smem_raw);
     __shared__ double warp_sum[kThreads / 32];
-    const int A = blockIdx.x;
+    const int A = A0 + blockIdx.x;
     const int c0 = blockIdx.y * cols_per_chunk;
     const int ncols = min(cols_per_chunk, m - c0);
     const int tid = threadIdx.x;
@@ -56,7 +64,8 @@ contract_rows(int n, int m, int words, int cols_per_chunk, const double *__restr
     for (int mi = mb; mi < me; ++mi) {
         const int u = members[mi];
         const uint32_t *bits_u = adj_bits + static_cast<size_t>(u) * words;
-        const double *W_u = W + static_cast<size_t>(u) * n;
+        const int owner = u / W.rows_per_rank;
+        const double *W_u = W.block[owner] + static_cast<size_t>(u - owner * W.rows_per_rank) * n;
         for (int v = tid; v < n; v += kThreads) {
             if ((bits_u[v >> 5] >> (v & 31)) & 1u) {
                 const int B = group[v];
@@ -68,7 +77,7 @@ contract_rows(int n, int m, int words, int cols_per_chunk, const double *__restr
     }
     __syncthreads();
     double partial = 0.0;
-    double *out = Wc + static_cast<size_t>(A) * m + c0;
+    double *out = Wc + static_cast<size_t>(blockIdx.x) * m + c0;
     for (int c = tid; c < ncols; c += kThreads) {
         const unsigned long long k = best[c];
         const double x = k ? order_value(k) : 0.0;
@@ -86,9 +95,10 @@ contract_rows(int n, int m, int words, int cols_per_chunk, const double *__restr
     }
 }
 
-__global__ void sum_parts(int m, int nchunks, const double *__restrict__ part, double *__restrict__ out) {
-    int a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= m) return;
+__global__ void sum_parts(int m, int row0, int row1, int nchunks, const double *__restrict__ part,
+                          double *__restrict__ out) {
+    int a = row0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= row1) return;
     double s = 0.0;
     for (int c = 0; c < nchunks; ++c) s += part[static_cast<size_t>(c) * m + a];
     out[a] = s;
@@ -98,7 +108,7 @@ __global__ void sum_parts(int m, int nchunks, const double *__restrict__ part, d
 
 // The merge itself, given the max-graph component labels (label[v] = smallest member) and their number m.
 int contract_with_labels(scs_ctx *ctx, int n, const double *W, const uint32_t *adj_bits, const int32_t *label, int m,
-                         int32_t *group, double *Wc, double *degree_c) {
+                         int32_t *group, double *Wc, double *degree_c, RowBlock rows) {
     const int words = scs_bit_words(n);
     int32_t *flags, *rank, *gptr, *cursor, *members;
     int rc;
@@ -135,11 +145,25 @@ int contract_with_labels(scs_ctx *ctx, int n, const double *W, const uint32_t *a
         SCS_CUDA(ctx, cudaFuncSetAttribute(contract_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(budget)));
         ctx->contract_configured = true;
     }
-    contract_rows<<<dim3(m, nchunks), kThreads, smem, ctx->stream>>>(n, m, words, cols_per_chunk, W, adj_bits, group,
-                                                                     gptr, members, Wc, part);
+    WRows where;
+    int A0 = 0, A1 = m;
+    if (rows.sharded()) {
+        // W (the argument) is ignored: row u is in the window of rank u / rows_per_rank(n)
+        const ShardState &sh = ctx->shard;
+        for (int r = 0; r < sh.world; ++r) where.block[r] = reinterpret_cast<const double *>(sh.peer[r] + sh.layout.W);
+        where.rows_per_rank = shard_rows_per_rank(n, sh.world);
+        A0 = rows.row0;
+        A1 = rows.row1;
+    } else {
+        where.block[0] = W;
+        where.rows_per_rank = n;
+    }
+    if (A1 <= A0) return SCS_OK;
+    contract_rows<<<dim3(A1 - A0, nchunks), kThreads, smem, ctx->stream>>>(n, m, A0, words, cols_per_chunk, where,
+                                                                           adj_bits, group, gptr, members, Wc, part);
     SCS_LAUNCHED(ctx, "contract_rows");
     if (degree_c) {
-        sum_parts<<<ceil_div(m, 256), 256, 0, ctx->stream>>>(m, nchunks, part, degree_c);
+        sum_parts<<<ceil_div(A1 - A0, 256), 256, 0, ctx->stream>>>(m, A0, A1, nchunks, part, degree_c);
         SCS_LAUNCHED(ctx, "sum_parts");
     }
     return SCS_OK;

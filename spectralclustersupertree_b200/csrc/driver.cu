@@ -144,6 +144,11 @@ class Driver {
         wave.push_back(Task{const_cast<scs_forest *>(root), false, root_slot, {}});
         scratch_[0].present_taxa(root, wave[0].taxa);
         int rc = SCS_OK;
+        // While all ranks still walk the same frontier, nodes large enough are shared out over the GPUs
+        // (shard.cu); once the frontier is dealt out the ranks work alone.
+        const ShardState &sh = ctx_->shard;
+        const bool cooperative = world_ > 1 && sh.connected && sh.world == world_ && sh.rank == rank_;
+        ctx_->shard.engaged = cooperative;
         while (!wave.empty() && rc == SCS_OK) {
             if (world_ > 1 && !partitioned_ && should_partition(wave)) partition(wave);
             if (wave.empty()) break;
@@ -166,6 +171,7 @@ class Driver {
         }
         for (Task &t : wave)  // only non-empty after an error: the sub-problems that were never started
             if (t.owned) scs_forest_destroy(t.forest);
+        ctx_->shard.engaged = false;
         return rc;
     }
 
@@ -197,6 +203,7 @@ class Driver {
 
     void partition(std::vector<Task> &wave) {
         partitioned_ = true;
+        ctx_->shard.engaged = false;
         out_.shared_prefix = static_cast<int64_t>(out_.parent.size());
         std::vector<size_t> order(wave.size());
         for (size_t i = 0; i < order.size(); ++i) order[i] = i;
@@ -317,7 +324,8 @@ class Driver {
         for (int r = 0; r < static_cast<int>(results.size()); ++r) {
             const Task &task = wave[results[r].task];
             out_.pair_visits += scs_forest_pair_visits(task.forest);
-            (static_cast<int>(task.taxa.size()) > kConcurrentMax ? serial : concurrent).push_back(r);
+            const int n = static_cast<int>(task.taxa.size());
+            (n > kConcurrentMax || shard_applies(ctx_, n) ? serial : concurrent).push_back(r);
         }
         out_.nodes_large += static_cast<int64_t>(results.size());
         if (buffers_.empty()) buffers_.resize(1);

@@ -98,10 +98,10 @@ __global__ void pcg_fill_inverse(int n, int64_t L, const int32_t *__restrict__ l
 
 // The atomics above leave each taxon's leaf list in arbitrary order; leaves are numbered tree
 // by tree, so sorting a list ascending restores tree input order.  Rank sort, one CTA per row.
-__global__ void pcg_sort_inverse(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ inv,
+__global__ void pcg_sort_inverse(int row0, const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ inv,
                                  int32_t *__restrict__ inv_sorted) {
     __shared__ int32_t stage[1024];
-    const int a = blockIdx.x;
+    const int a = row0 + blockIdx.x;
     const int base = row_ptr[a];
     const int cnt = row_ptr[a + 1] - base;
     for (int i0 = 0; i0 < cnt; i0 += blockDim.x) {
@@ -233,7 +233,7 @@ __device__ __forceinline__ void advance(const TreeHeader *headers, int batch, in
 
 template <typename CountT, bool kWriteC>
 __global__ void __launch_bounds__(kRowThreads)
-pcg_rows_kernel(int n, int words_per_row, int cols_per_chunk, int64_t L,
+pcg_rows_kernel(int n, int row0, int words_per_row, int cols_per_chunk, int64_t L,
                 const int64_t *__restrict__ leaf_offsets, const int32_t *__restrict__ leaf_taxon,
                 const LcaEntry *__restrict__ st, const int32_t *__restrict__ root_depth,
                 const double *__restrict__ tree_weight,
@@ -247,7 +247,7 @@ pcg_rows_kernel(int n, int words_per_row, int cols_per_chunk, int64_t L,
     __shared__ TreeHeader headers[kHeaderBatch];
     __shared__ double warp_sum[kWarps];
 
-    const int a = blockIdx.x;
+    const int a = row0 + blockIdx.x;  // W / C point at the row block: its first row is row0
     const int col0 = blockIdx.y * cols_per_chunk;
     const int ncols = min(cols_per_chunk, n - col0);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -312,13 +312,13 @@ pcg_rows_kernel(int n, int words_per_row, int cols_per_chunk, int64_t L,
 
     // ---- write the finished row --------------------------------------------------------------
     const int occ_a = occ[a];
-    double *Wrow = W + static_cast<size_t>(a) * n + col0;
+    double *Wrow = W + static_cast<size_t>(blockIdx.x) * n + col0;
     double partial = 0.0;
     for (int c = tid; c < ncols; c += kRowThreads) {
         const double x = accW[c];
         Wrow[c] = x;
         partial += x;
-        if (kWriteC) C[static_cast<size_t>(a) * n + col0 + c] = static_cast<int32_t>(accC[c]);
+        if (kWriteC) C[static_cast<size_t>(blockIdx.x) * n + col0 + c] = static_cast<int32_t>(accC[c]);
     }
     const int word0 = col0 >> 5;
     const int nwords = (ncols + 31) >> 5;
@@ -349,16 +349,17 @@ pcg_rows_kernel(int n, int words_per_row, int cols_per_chunk, int64_t L,
     }
 }
 
-__global__ void pcg_sum_degree_parts(int n, int nchunks, const double *__restrict__ part, double *__restrict__ degree) {
-    int a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= n) return;
+__global__ void pcg_sum_degree_parts(int n, int row0, int row1, int nchunks, const double *__restrict__ part,
+                                     double *__restrict__ degree) {
+    int a = row0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= row1) return;
     double s = 0.0;
     for (int c = 0; c < nchunks; ++c) s += part[static_cast<size_t>(c) * n + a];
     degree[a] = s;
 }
 
 template <typename CountT, bool kWriteC>
-int launch_rows(scs_ctx *ctx, int n, int words, int cols_per_chunk, int nchunks, size_t smem, int64_t L,
+int launch_rows(scs_ctx *ctx, int n, int row0, int nrows, int words, int cols_per_chunk, int nchunks, size_t smem, int64_t L,
                 const int64_t *leaf_offsets, const int32_t *leaf_taxon, const LcaEntry *st,
                 const int32_t *root_depth, const double *tree_weight,
                 const int32_t *leaf_tree, const int32_t *row_ptr, const int32_t *inv_sorted,
@@ -372,13 +373,13 @@ int launch_rows(scs_ctx *ctx, int n, int words, int cols_per_chunk, int nchunks,
         SCS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(optin)));
         configured = true;
     }
-    dim3 grid(n, nchunks);
+    dim3 grid(nrows, nchunks);
     if (n >= kProfileMinSize) {
         // algorithmic bytes: W + both bit matrices + occ/degree written once, C if asked
-        const double out_bytes = 8.0 * n * n + (C ? 4.0 * n * n : 0.0) + 8.0 * n * words + 12.0 * n;
+        const double out_bytes = 8.0 * nrows * n + (C ? 4.0 * nrows * n : 0.0) + 8.0 * nrows * words + 12.0 * nrows;
         profile_begin(ctx, PROFILE_PCG_ROWS, out_bytes, ctx->pending_units);
     }
-    kernel<<<grid, kRowThreads, smem, ctx->stream>>>(n, words, cols_per_chunk, L, leaf_offsets, leaf_taxon, st,
+    kernel<<<grid, kRowThreads, smem, ctx->stream>>>(n, row0, words, cols_per_chunk, L, leaf_offsets, leaf_taxon, st,
                                                      root_depth, tree_weight, leaf_tree, row_ptr,
                                                      inv_sorted, occ, W, C, adj_bits, max_bits, degree_part, bad);
     if (n >= kProfileMinSize) profile_end(ctx);
@@ -397,7 +398,11 @@ int exclusive_scan(scs_ctx *ctx, int n, const int32_t *in, int32_t *out) {
 int pcg_build(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offsets,
               const int32_t *leaf_taxon, const int32_t *adj_depth, const double *adj_val,
               const int32_t *root_depth, const double *tree_weight, double *W, int32_t *C,
-              int32_t *occ, uint32_t *adj_bits, uint32_t *max_bits, double *degree) {
+              int32_t *occ, uint32_t *adj_bits, uint32_t *max_bits, double *degree, RowBlock rows) {
+    const int row0 = rows.sharded() ? rows.row0 : 0;
+    const int row1 = rows.sharded() ? rows.row1 : n;
+    const int nrows = row1 - row0;
+    if (row0 < 0 || row1 > n || nrows < 0) return fail(ctx, SCS_ERR_INVALID, "pcg_build: bad row block");
     if (n <= 0 || T < 0 || L < 0 || L >= (1ll << 31) || !W || !occ || !adj_bits)
         return fail(ctx, SCS_ERR_INVALID, "pcg_build: bad argument");
     if (T > 0 && (!leaf_offsets || !root_depth || !tree_weight))
@@ -428,8 +433,10 @@ int pcg_build(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offsets
     if (L > 0) {
         pcg_fill_inverse<<<ceil_div(L, 256), 256, 0, ctx->stream>>>(n, L, leaf_taxon, row_ptr, cursor, inv);
         SCS_LAUNCHED(ctx, "pcg_fill_inverse");
-        pcg_sort_inverse<<<n, 128, 0, ctx->stream>>>(row_ptr, inv, inv_sorted);
-        SCS_LAUNCHED(ctx, "pcg_sort_inverse");
+        if (nrows > 0) {
+            pcg_sort_inverse<<<nrows, 128, 0, ctx->stream>>>(row0, row_ptr, inv, inv_sorted);
+            SCS_LAUNCHED(ctx, "pcg_sort_inverse");
+        }
     }
     // a tree has at most n leaves (distinct taxa), so ceil(log2(n)) doubling levels always suffice
     int levels = 1;
@@ -455,15 +462,16 @@ int pcg_build(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offsets
     if ((rc = reserve_as(ctx, SLOT_DEGREE_PART, static_cast<size_t>(n) * nchunks, &degree_part))) return rc;
 
 #define SCS_ROWS(CT, WC)                                                                                      \
-    launch_rows<CT, WC>(ctx, n, words, cols_per_chunk, nchunks, smem, L, leaf_offsets, leaf_taxon, st,          \
+    launch_rows<CT, WC>(ctx, n, row0, nrows, words, cols_per_chunk, nchunks, smem, L, leaf_offsets, leaf_taxon, st, \
                         root_depth, tree_weight, leaf_tree, row_ptr, inv_sorted, occ, W, C, adj_bits, max_bits, \
                         degree_part, scalars)
+    if (nrows == 0) return SCS_OK;
     if (narrow) rc = C ? SCS_ROWS(uint16_t, true) : SCS_ROWS(uint16_t, false);
     else rc = C ? SCS_ROWS(int32_t, true) : SCS_ROWS(int32_t, false);
 #undef SCS_ROWS
     if (rc) return rc;
     if (degree) {
-        pcg_sum_degree_parts<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(n, nchunks, degree_part, degree);
+        pcg_sum_degree_parts<<<ceil_div(nrows, 256), 256, 0, ctx->stream>>>(n, row0, row1, nchunks, degree_part, degree);
         SCS_LAUNCHED(ctx, "pcg_sum_degree_parts");
     }
     return SCS_OK;

@@ -19,6 +19,7 @@
 // random Lloyd restarts, which makes the partition deterministic.
 
 #include "common.cuh"
+#include "shard.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -190,8 +191,90 @@ matvec_row_per_warp(int m, const double *__restrict__ W, const double *__restric
     if (lane == 0) y[row] = isd[row] * acc;
 }
 
-int launch_matvec(scs_ctx *ctx, int m, const double *W, const double *isd, const double *z, double *y,
-                  const int32_t *done = nullptr) {
+int launch_matvec_single(scs_ctx *ctx, int m, const double *W, const double *isd, const double *z, double *y,
+                         const int32_t *done);
+
+// Row-sharded operator fused with its all-gather (one process per GPU, rows [row0, row0 + gridDim.x) of
+// W on this rank): every CTA computes one entry of y and stores it straight into the `vec` buffer of
+// EVERY rank's exchange window over NVLink; the last CTA to finish raises this rank's flag in every
+// window and then waits until every rank has raised its flag here, so when the kernel ends the whole
+// vector is in this rank's window.  Every entry is computed by the same code whatever rank owns the row,
+// so the assembled vector is bit-identical to the single-GPU matvec's.
+// kWarpRows mirrors the single-GPU choice (one warp per row below 2048 columns, one CTA per row above), so
+// that the summation order of every entry is the same in both paths.
+template <bool kWarpRows>
+__global__ void __launch_bounds__(kMvThreads)
+matvec_rows_allgather(int m, int row0, int nrows, const double *__restrict__ W, const double *__restrict__ isd,
+                      const double *__restrict__ z, const PeerTable peers, size_t vec_offset,
+                      unsigned long long epoch, unsigned long long timeout_ns, const int32_t *__restrict__ done) {
+    __shared__ double part[kMvThreads / 32];
+    __shared__ unsigned int last;
+    if (done && *done) return;  // the same on every rank: nobody signals, nobody waits
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (kWarpRows) {
+        const int local = blockIdx.x * (kMvThreads / 32) + warp;
+        if (local < nrows) {
+            double acc = row_dot_partial(W + static_cast<size_t>(local) * m, z, m, lane, 32);
+            acc = warp_sum(acc);
+            acc = __shfl_sync(0xffffffffu, acc, 0);
+            const double out = isd[row0 + local] * acc;
+            if (lane < peers.world) reinterpret_cast<double *>(peers.window[lane] + vec_offset)[row0 + local] = out;
+            __threadfence_system();
+        }
+    } else {
+        const int row = row0 + blockIdx.x;
+        double acc = row_dot_partial(W + static_cast<size_t>(blockIdx.x) * m, z, m, threadIdx.x, kMvThreads);
+        acc = warp_sum(acc);
+        if (lane == 0) part[warp] = acc;
+        __syncthreads();
+        if (warp == 0) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < kMvThreads / 32; ++w) s += part[w];
+            const double out = isd[row] * s;
+            if (lane < peers.world) reinterpret_cast<double *>(peers.window[lane] + vec_offset)[row] = out;
+            __threadfence_system();
+        }
+    }
+    __syncthreads();  // every store of this CTA is fenced before its ticket is drawn
+    if (threadIdx.x == 0) {
+        ShardHeader *mine = reinterpret_cast<ShardHeader *>(peers.window[peers.rank]);
+        last = atomicInc(&mine->ticket, gridDim.x - 1) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && threadIdx.x < 32) peer_signal_and_wait(peers, epoch, timeout_ns);
+}
+
+int launch_matvec(scs_ctx *ctx, int m, const double *W, const double *isd, const double *z, double **y,
+                  const int32_t *done = nullptr, RowBlock rows = RowBlock()) {
+    if (rows.sharded()) {
+        // the result lands in the window (double-buffered); *y is redirected there
+        const ShardState &sh = ctx->shard;
+        const ShardMatvecTicket ticket = shard_next_matvec(ctx);
+        PeerTable peers;
+        for (int r = 0; r < kMaxPeers; ++r) peers.window[r] = sh.peer[r];
+        peers.rank = sh.rank;
+        peers.world = sh.world;
+        const int nrows = rows.row1 - rows.row0;
+        *y = reinterpret_cast<double *>(sh.window + ticket.vec_offset);
+        if (nrows <= 0) return fail(ctx, SCS_ERR_INVALID, "sharded matvec: a rank owns no rows");
+        if (m >= kProfileMinSize)
+            profile_begin(ctx, PROFILE_MATVEC, 8.0 * nrows * m + 8.0 * m + 8.0 * nrows * (1 + sh.world), 2.0 * nrows * m);
+        if (m >= 2048)
+            matvec_rows_allgather<false><<<nrows, kMvThreads, 0, ctx->stream>>>(
+                m, rows.row0, nrows, W, isd, z, peers, ticket.vec_offset, ticket.epoch, ticket.timeout_ns, done);
+        else
+            matvec_rows_allgather<true><<<ceil_div(nrows, kMvThreads / 32), kMvThreads, 0, ctx->stream>>>(
+                m, rows.row0, nrows, W, isd, z, peers, ticket.vec_offset, ticket.epoch, ticket.timeout_ns, done);
+        if (m >= kProfileMinSize) profile_end(ctx);
+        SCS_LAUNCHED(ctx, "matvec_rows_allgather");
+        return SCS_OK;
+    }
+    return launch_matvec_single(ctx, m, W, isd, z, *y, done);
+}
+
+int launch_matvec_single(scs_ctx *ctx, int m, const double *W, const double *isd, const double *z, double *y,
+                         const int32_t *done) {
     if (m >= 2048) {
         // algorithmic bytes: W once + read z, isd, write y
         if (m >= kProfileMinSize) profile_begin(ctx, PROFILE_MATVEC, 8.0 * m * m + 24.0 * m, 2.0 * m * m);
@@ -747,7 +830,7 @@ int normalized_matvec(scs_ctx *ctx, int m, const double *W, const double *isd, c
     if ((rc = reserve_as(ctx, SLOT_UVEC, static_cast<size_t>(m), &z))) return rc;
     scale_vector<<<ceil_div(m, 256), 256, 0, ctx->stream>>>(m, isd, x, z);
     SCS_LAUNCHED(ctx, "scale_vector");
-    return launch_matvec(ctx, m, W, isd, z, y);
+    return launch_matvec_single(ctx, m, W, isd, z, y, nullptr);
 }
 
 namespace {
@@ -770,15 +853,16 @@ struct LanczosBuffers {
 // Largest eigenpair of N = D^-1/2 W D^-1/2 on the orthogonal complement of the first `ndefl` rows of
 // `basis`.  Lanczos vectors go to rows ndefl, ndefl+1, ...; the Ritz vector to `y` (and isd .* y to z).
 int lanczos_largest(scs_ctx *ctx, int m, const double *W, const LanczosBuffers &b, int ndefl, uint64_t seed,
-                    double *y, LanczosOutcome *out) {
+                    double *y, LanczosOutcome *out, RowBlock rows) {
     const int dim = m - ndefl;  // dimension of the deflated space
     const int jmax = dim < kMaxBasis ? dim : kMaxBasis;
     const int vec_blocks = ceil_div(m, kVecThreads);
     double *v0 = b.basis + static_cast<size_t>(ndefl - 1) * m;  // v_k lives at v0 + k m
+    double *w = b.w;  // the vector being orthogonalised: b.w, or the window buffer a sharded matvec filled
     auto orthogonalise = [&](int nb, double *h) -> int {
-        multi_dot<<<nb, kVecThreads, 0, ctx->stream>>>(m, b.basis, b.w, h);
+        multi_dot<<<nb, kVecThreads, 0, ctx->stream>>>(m, b.basis, w, h);
         SCS_LAUNCHED(ctx, "multi_dot");
-        multi_axpy<<<vec_blocks, kVecThreads, nb * sizeof(double), ctx->stream>>>(m, nb, b.basis, h, b.w);
+        multi_axpy<<<vec_blocks, kVecThreads, nb * sizeof(double), ctx->stream>>>(m, nb, b.basis, h, w);
         SCS_LAUNCHED(ctx, "multi_axpy");
         return SCS_OK;
     };
@@ -792,6 +876,7 @@ int lanczos_largest(scs_ctx *ctx, int m, const double *W, const LanczosBuffers &
     }
     const size_t tail_smem = (static_cast<size_t>(m) + 6 * (kMaxBasis + 8)) * sizeof(double);
     for (int attempt = 0; attempt <= kMaxRestarts && !out->converged; ++attempt) {
+        w = b.w;
         if (attempt == 0) {
             random_start<<<vec_blocks, kVecThreads, 0, ctx->stream>>>(m, seed, b.w);
             SCS_LAUNCHED(ctx, "random_start");
@@ -813,10 +898,10 @@ int lanczos_largest(scs_ctx *ctx, int m, const double *W, const LanczosBuffers &
             while (j <= jmax && !done) {
                 const int chunk_end = std::min(jmax, j == 1 ? 16 : j + 3);  // chunks end on check steps
                 for (; j <= chunk_end; ++j) {
-                    if ((rc = launch_matvec(ctx, m, W, b.isd, b.z, b.w, b.state + 1))) return rc;
+                    if ((rc = launch_matvec(ctx, m, W, b.isd, b.z, &w, b.state + 1, rows))) return rc;
                     const int check = j == jmax || (j % 4) == 0;
                     lanczos_tail<<<1, kOneCta, tail_smem, ctx->stream>>>(
-                        m, j, ndefl + j, ndefl - 1 + j, check, b.basis, b.w, b.isd, b.alpha, b.beta,
+                        m, j, ndefl + j, ndefl - 1 + j, check, b.basis, w, b.isd, b.alpha, b.beta,
                         v0 + static_cast<size_t>(j + 1) * m, b.z, b.state, b.coef, b.ritz);
                     SCS_LAUNCHED(ctx, "lanczos_tail");
                 }
@@ -842,15 +927,15 @@ int lanczos_largest(scs_ctx *ctx, int m, const double *W, const LanczosBuffers &
         } else {
             if ((rc = orthogonalise(ndefl, b.h1))) return rc;
             if ((rc = orthogonalise(ndefl, b.h2))) return rc;
-            normalize_step<<<1, kOneCta, 0, ctx->stream>>>(m, 0, 0, b.w, b.isd, b.h1, b.h2, b.alpha, b.beta, v0 + m, b.z,
+            normalize_step<<<1, kOneCta, 0, ctx->stream>>>(m, 0, 0, w, b.isd, b.h1, b.h2, b.alpha, b.beta, v0 + m, b.z,
                                                            b.state);
             SCS_LAUNCHED(ctx, "normalize_step");
             for (int j = 1; j <= jmax; ++j) {
-                if ((rc = launch_matvec(ctx, m, W, b.isd, b.z, b.w))) return rc;
+                if ((rc = launch_matvec(ctx, m, W, b.isd, b.z, &w, nullptr, rows))) return rc;
                 out->matvecs += 1;
                 if ((rc = orthogonalise(ndefl + j, b.h1))) return rc;
                 if ((rc = orthogonalise(ndefl + j, b.h2))) return rc;
-                normalize_step<<<1, kOneCta, 0, ctx->stream>>>(m, j, ndefl - 1 + j, b.w, b.isd, b.h1, b.h2, b.alpha,
+                normalize_step<<<1, kOneCta, 0, ctx->stream>>>(m, j, ndefl - 1 + j, w, b.isd, b.h1, b.h2, b.alpha,
                                                                b.beta, v0 + static_cast<size_t>(j + 1) * m, b.z, b.state);
                 SCS_LAUNCHED(ctx, "normalize_step");
                 jdone = j;
@@ -886,7 +971,8 @@ int lanczos_largest(scs_ctx *ctx, int m, const double *W, const LanczosBuffers &
 }  // namespace
 
 int spectral_bipartition(scs_ctx *ctx, int m, const double *W, const double *degree, uint64_t seed, int32_t *side,
-                         scs_node_stats *stats) {
+                         scs_node_stats *stats, RowBlock rows) {
+    if (rows.sharded() && !degree) return fail(ctx, SCS_ERR_INVALID, "sharded spectral step needs the degrees");
     if (m < 2 || !W || !side || !stats) return fail(ctx, SCS_ERR_INVALID, "spectral_bipartition: bad argument");
     int rc;
     if (m == 2) {
@@ -939,15 +1025,16 @@ int spectral_bipartition(scs_ctx *ctx, int m, const double *W, const double *deg
     stats->solver = 3;
     LanczosOutcome first;
     const auto t_lanczos = std::chrono::steady_clock::now();
-    if ((rc = lanczos_largest(ctx, m, W, b, 1, seed, yvec, &first))) return rc;
+    if ((rc = lanczos_largest(ctx, m, W, b, 1, seed, yvec, &first, rows))) return rc;
     ctx->stage_seconds[5] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_lanczos).count();
     stats->matvecs = first.matvecs;
     stats->restarts = first.restarts;
 
     // true residual of the accepted pair: one more operator application (z = isd .* y is current)
-    if ((rc = launch_matvec(ctx, m, W, b.isd, b.z, b.w))) return rc;
+    double *Ny = b.w;
+    if ((rc = launch_matvec(ctx, m, W, b.isd, b.z, &Ny, nullptr, rows))) return rc;
     stats->matvecs += 1;
-    true_residual<<<1, kOneCta, 0, ctx->stream>>>(m, yvec, b.w, b.ritz, b.ritz + 8);
+    true_residual<<<1, kOneCta, 0, ctx->stream>>>(m, yvec, Ny, b.ritz, b.ritz + 8);
     SCS_LAUNCHED(ctx, "true_residual");
     SCS_CUDA(ctx, cudaMemcpyAsync(pin + 8, b.ritz + 8, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
 
@@ -959,7 +1046,7 @@ int spectral_bipartition(scs_ctx *ctx, int m, const double *W, const double *deg
         SCS_CUDA(ctx, cudaMemcpyAsync(b.basis + m, yvec, sizeof(double) * m, cudaMemcpyDeviceToDevice, ctx->stream));
         LanczosOutcome second;
         b.ritz += 16;  // keep the first pair's scalars
-        rc = lanczos_largest(ctx, m, W, b, 2, seed + 0x5bd1e995u, y2, &second);
+        rc = lanczos_largest(ctx, m, W, b, 2, seed + 0x5bd1e995u, y2, &second, rows);
         b.ritz -= 16;
         if (rc) return rc;
         stats->matvecs += second.matvecs;

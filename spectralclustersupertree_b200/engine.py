@@ -227,6 +227,45 @@ class Engine:
         finally:
             self._lib.scs_supertree_destroy(handle)
 
+    # -- one node over several GPUs (csrc/shard.cu) -------------------------------------------------
+    def shard_create(self, rank: int, world: int, n_max: int) -> bytes:
+        """Allocate this rank's exchange window; returns its IPC handle (64 opaque bytes) for the peers."""
+        handle = (ctypes.c_ubyte * _lib.IPC_HANDLE_BYTES)()
+        _check(self._lib.scs_shard_create(self._ctx, rank, world, n_max, ctypes.addressof(handle)), self._ctx)
+        return bytes(handle)
+
+    def shard_connect(self, handles: Sequence[bytes]) -> None:
+        """Map the peers' windows from their IPC handles (all ranks' handles, in rank order)."""
+        blob = b"".join(handles)
+        buf = (ctypes.c_ubyte * len(blob)).from_buffer_copy(blob)
+        _check(self._lib.scs_shard_connect_ipc(self._ctx, ctypes.addressof(buf)), self._ctx)
+
+    def shard_window(self) -> int:
+        out, size = ctypes.c_void_p(), ctypes.c_size_t(0)
+        _check(self._lib.scs_shard_window(self._ctx, ctypes.byref(out), ctypes.byref(size)), self._ctx)
+        return out.value
+
+    def shard_connect_local(self, windows: Sequence[int]) -> None:
+        """Peers in this process (one Engine per GPU, or several on one GPU): raw window pointers."""
+        arr = (ctypes.c_void_p * len(windows))(*windows)
+        _check(self._lib.scs_shard_connect_ptrs(self._ctx, ctypes.addressof(arr)), self._ctx)
+
+    def shard_engage(self, on: bool = True) -> None:
+        _check(self._lib.scs_shard_engage(self._ctx, int(on)), self._ctx)
+
+    def shard_configure(self, min_n: int = 0, timeout_seconds: float = 0.0) -> None:
+        _check(self._lib.scs_shard_configure(self._ctx, int(min_n), float(timeout_seconds)), self._ctx)
+
+    def shard_barrier(self) -> None:
+        _check(self._lib.scs_shard_barrier(self._ctx), self._ctx)
+
+    @property
+    def shard_nodes(self) -> int:
+        return int(self._lib.scs_shard_nodes(self._ctx))
+
+    def shard_destroy(self) -> None:
+        _check(self._lib.scs_shard_destroy(self._ctx), self._ctx)
+
     # -- single stages on explicit device buffers (parity tests, profiling, bench) ---------------
     def upload_tours(self, tours) -> dict:
         """Device copies of a ``LeafTours`` (free with ``free_tours``)."""
