@@ -267,12 +267,14 @@ class Replay:
     FIELDS = (("leaf_offsets", np.int64), ("leaf_taxon", np.int32), ("adj_depth", np.int32),
               ("adj_val", np.float64), ("root_depth", np.int32), ("tree_weight", np.float64))  # fmt: skip
 
-    def __init__(self, engine, nodes: list, small_limit: int = 64) -> None:
+    def __init__(self, engine, nodes: list, small_limit: int = 64, shared: list | None = None) -> None:
         from spectralclustersupertree_b200 import _lib
 
         self.engine = engine
         self.lib = _lib.load()
         self.pair_visits = [t.pair_updates() for t, _ in nodes]
+        shared = shared or [False] * len(nodes)
+        self.shared_of = {id(t): s for (t, _), s in zip(nodes, shared, strict=True)}
         large = [(t, seed) for t, seed in nodes if t.n > small_limit]
         small = [t for t, _ in nodes if t.n <= small_limit]
         self.bytes = 0
@@ -285,7 +287,7 @@ class Replay:
             pos = dict.fromkeys(host, 0)
             for tours, seed in large:
                 T, L = tours.num_trees, tours.num_leaves
-                entry = {"n": tours.n, "T": T, "L": L, "seed": seed}
+                entry = {"n": tours.n, "T": T, "L": L, "seed": seed, "shared": self.shared_of[id(tours)]}
                 for key, count in (("leaf_offsets", T + 1), ("leaf_taxon", L), ("adj_depth", L), ("adj_val", L),
                                    ("root_depth", T), ("tree_weight", T)):  # fmt: skip
                     entry[key] = dev[key] + pos[key] * host[key].itemsize
@@ -319,7 +321,12 @@ class Replay:
 
     def run(self, contract_edges: bool = True) -> None:
         for entry in self.large:
+            # nodes the ranks share out (row-sharded over the GPUs) are replayed the same way
+            if entry["shared"]:
+                self.engine.shard_engage(True)
             self.engine.node_split_dev(entry, self.part, contract_edges=contract_edges, seed=entry["seed"])
+            if entry["shared"]:
+                self.engine.shard_engage(False)
         if self.small_count:
             d = self.small_dev
             status = self.lib.scs_nodes_split_small_dev(
@@ -382,6 +389,14 @@ def gpu_line(args, arrays: dict) -> dict:
 
     host_threads = max(1, min(16, (os.cpu_count() or 1) // world))
     set_host_threads(host_threads)
+    if dist is not None and args.shard_min_n > 0:
+        # exchange windows for the nodes that are row-sharded over the GPUs (csrc/shard.cu): every rank
+        # exports its window as a CUDA IPC handle, all-gathered here, mapped by every peer
+        handles = [None] * world
+        dist.all_gather_object(handles, engine.shard_create(rank, world, len(arrays["names"])))
+        engine.shard_connect(handles)
+        engine.shard_configure(min_n=args.shard_min_n, timeout_seconds=30.0)
+        dist.barrier()
 
     def new_forest():
         return Forest.from_arrays(arrays["node_offsets"], arrays["parent"], arrays["length"], arrays["support"],
@@ -401,7 +416,9 @@ def gpu_line(args, arrays: dict) -> dict:
                         node_hook=lambda f, seed: recorded.__setitem__(f.taxa().tobytes(), (f.tours(weighting), seed)))  # fmt: skip
     traced = engine.supertree_build(new_forest(), weighting, record=True, rank=rank, world=world)
     mine = [recorded[taxa.tobytes()] for taxa, _, _ in traced["records"]]
-    replay = Replay(engine, mine)
+    sharing = dist is not None and args.shard_min_n > 0
+    shared = [sharing and i < traced["shared_records"] and t.n >= args.shard_min_n for i, (t, _) in enumerate(mine)]
+    replay = Replay(engine, mine, shared=shared)
     spectral = [st for _, _, st in traced["records"] if st.n_components == 1]
     all_visits = [t.pair_updates() for t, _ in recorded.values()]
     job = {
@@ -419,6 +436,7 @@ def gpu_line(args, arrays: dict) -> dict:
         "nodes_small": traced["nodes_small"],
         "nodes_large": traced["nodes_large"],
         "resident_tour_bytes": int(replay.bytes),
+        "nodes_row_sharded_over_gpus": int(sum(shared)),
     }
 
     def barrier():
@@ -509,8 +527,9 @@ def gpu_line(args, arrays: dict) -> dict:
                         "over ranks)",
             "e2e_is": "scs_forest_create + scs_supertree_build over the C ABI from flat host arrays to the flat "
                       "supertree (wall clock; native breadth-first recursion, per-wave H2D of tours and D2H of "
-                      "partitions; for N > 1 the frontier is dealt out over the ranks and the outputs are "
-                      "all-gathered)",
+                      "partitions; for N > 1 recursion nodes with >= --shard-min-n taxa are row-sharded over the "
+                      "GPUs (fused matvec + all-gather over NVLink peer windows), then the frontier is dealt out "
+                      "over the ranks and the outputs are all-gathered)",
             "e2e_host_seconds": host_split,
             "host_threads_per_rank": host_threads,
             "supertree_tips": tips,
@@ -539,6 +558,9 @@ def gpu_line(args, arrays: dict) -> dict:
         if out.is_dir():
             (out / f"workload_{args.workload}.json").write_text(json.dumps({args.workload: job}, indent=1) + "\n")
     replay.close()
+    if dist is not None:
+        engine.synchronize()
+        dist.barrier()  # nobody may unmap a window a peer is still using
     engine.close()
     if dist is not None:
         dist.destroy_process_group()
@@ -553,6 +575,9 @@ def main() -> None:
     parser.add_argument("--impl", default="b200", choices=["b200", "reference"])
     parser.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     parser.add_argument("--no-cpu-baseline", action="store_true")
+    parser.add_argument("--shard-min-n", type=int, default=4096,
+                        help="N > 1: recursion nodes with at least this many taxa are row-sharded over the GPUs "
+                             "(0: never; the ranks then only share out the independent sub-problems)")
     args = parser.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     if args.impl == "reference":

@@ -215,6 +215,12 @@ int scs_forest_taxa(const scs_forest *f, uint8_t *present);
  * ignore_missing=True, as_rooted=True) does; trees left with < 2 tips are dropped with their
  * weight (scs.py:444-453). */
 int scs_forest_induce(const scs_forest *f, const uint8_t *keep, scs_forest **out);
+/* All the restrictions of one recursion node (the loop scs.py:139-155) in one call, spread over the host
+ * threads by (part, tree): out[c] = the forest restricted to the taxa x with part[x] == c, c = 0..count-1
+ * (other values of part[x] drop the taxon).  present[num_taxa] (may be NULL) must be zero on entry and is
+ * set to 1 for every taxon that is still a tip of some restricted tree. */
+int scs_forest_induce_parts(const scs_forest *f, const int32_t *part, int count, scs_forest **out,
+                            uint8_t *present);
 /* Leaf tours of the forest for one weighting (0 one, 1 branch, 2 depth, 3 bootstrap;
  * scs.py:555-567); local_id[num_taxa] maps global taxon id -> vertex id.  Output arrays are
  * sized by scs_forest_num_trees / scs_forest_num_leaves. */
@@ -270,6 +276,9 @@ int scs_supertree_build(scs_ctx *ctx, const scs_forest *forest, int weighting, i
 int scs_supertree_build_sharded(scs_ctx *ctx, const scs_forest *forest, int weighting, int contract_edges,
                                 uint64_t seed, int record_nodes, int rank, int world, scs_supertree **out);
 int64_t scs_supertree_shared_prefix(const scs_supertree *tree);
+/* Recursion nodes (records [0, this)) processed before the frontier was dealt out: the same on every
+ * rank, and the ones that are shared out over the GPUs when a shard group is connected. */
+int64_t scs_supertree_shared_records(const scs_supertree *tree);
 /* Per wave of the breadth-first recursion: number of sub-problems and the largest one's taxon count.
  * Returns the number of waves; either array may be NULL (size them with scs_supertree_counters). */
 int scs_supertree_wave_info(const scs_supertree *tree, int32_t *tasks, int32_t *max_n);

@@ -114,6 +114,7 @@ SIGNATURES: dict[str, tuple] = {
     "scs_forest_tree": (c_int, [_P, c_int, _P, _P, _P, _P]),
     "scs_forest_taxa": (c_int, [_P, _P]),
     "scs_forest_induce": (c_int, [_P, _P, POINTER(_P)]),
+    "scs_forest_induce_parts": (c_int, [_P, _P, c_int, _P, _P]),
     "scs_forest_tours": (c_int, [_P, c_int, _P, _P, _P, _P, _P, _P, _P]),
     "scs_forest_split": (
         c_int,
@@ -127,6 +128,7 @@ SIGNATURES: dict[str, tuple] = {
     "scs_supertree_build": (c_int, [_P, _P, c_int, c_int, c_uint64, c_int, POINTER(_P)]),
     "scs_supertree_build_sharded": (c_int, [_P, _P, c_int, c_int, c_uint64, c_int, c_int, c_int, POINTER(_P)]),
     "scs_supertree_shared_prefix": (c_int64, [_P]),
+    "scs_supertree_shared_records": (c_int64, [_P]),
     "scs_supertree_wave_info": (c_int, [_P, _P, _P]),
     "scs_supertree_wave_seconds": (c_int, [_P, _P]),
     "scs_supertree_destroy": (c_int, [_P]),

@@ -38,13 +38,23 @@ struct scs_supertree {
     std::vector<int32_t> wave_tasks, wave_max_n;  // per wave: sub-problems in it, largest taxon count
     std::vector<double> wave_seconds;             // per wave: 3 numbers (GPU splits, restriction, everything)
     int64_t shared_prefix = 0;  // sharded build: output nodes [0, shared_prefix) are identical on every rank
+    int64_t shared_records = 0;  // recursion nodes processed while every rank still walked the same frontier
 };
 
 namespace scs {
 
 namespace {
 
-constexpr int kMaxWorkers = 4;        // host threads (contexts) driving staged nodes concurrently
+constexpr int kMaxWorkers = 16;       // upper bound on the contexts driving staged nodes concurrently
+// how many of them are used (default 4; SCS_NODE_WORKERS overrides, for tuning)
+int node_workers() {
+    static const int value = [] {
+        const char *env = std::getenv("SCS_NODE_WORKERS");
+        const int v = env ? std::atoi(env) : 4;
+        return v < 1 ? 1 : (v > kMaxWorkers ? kMaxWorkers : v);
+    }();
+    return value;
+}
 constexpr int kConcurrentMax = 4096;  // nodes above this many taxa run one at a time on the main context
 
 struct Stopwatch {
@@ -164,8 +174,15 @@ class Driver {
             out_.wave_seconds.push_back(out_.seconds[0] + out_.seconds[1] - before_gpu);
             out_.wave_seconds.push_back(out_.seconds[2] - before_restrict);
             out_.wave_seconds.push_back(std::chrono::duration<double>(std::chrono::steady_clock::now() - wave_start).count());
+            const auto t_destroy = std::chrono::steady_clock::now();
             for (Task &t : wave)
                 if (t.owned) scs_forest_destroy(t.forest);
+            if (trace_) {
+                const double destroy = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_destroy).count();
+                std::fprintf(stderr, "[scs driver] wave %d: tasks %zu, induce %.2f ms, present_taxa %.2f ms, destroy %.2f ms\n",
+                             static_cast<int>(out_.waves), wave.size(), 1e3 * trace_induce_, 1e3 * trace_present_, 1e3 * destroy);
+                trace_induce_ = trace_present_ = 0.0;
+            }
             wave.clear();
             wave.swap(next);
         }
@@ -252,23 +269,17 @@ class Driver {
         if ((rc = split_large_all(wave, results))) return rc;
         if (!small.empty() && (rc = split_small(wave, small, results))) return rc;
 
-        // children of every split node: restriction of the forests is independent per node, so the
-        // nodes of a wave are planned by all host threads; emission into the output stays serial
+        // children of every split node (scs.py:136-171).  The restrictions of the whole wave run as ONE
+        // batch over all host threads: (child, source tree) pairs are the work items, so a wave of two huge
+        // restrictions is spread as evenly as one of a thousand small ones.
         {
             Stopwatch sw(&out_.seconds[2]);
-            const int count = static_cast<int>(results.size());
-#pragma omp parallel for schedule(dynamic, 1) if (count >= 2 * scs_host_threads()) num_threads(scs_host_threads())
-            for (int r = 0; r < count; ++r)
-                plan(wave[results[r].task], results[r], scratch_[static_cast<size_t>(omp_get_thread_num())]);
-        }
-        for (SplitResult &res : results) {
-            if (res.rc) rc = res.rc;
-        }
-        if (rc) {
-            for (SplitResult &res : results)
-                for (Child &child : res.children)
-                    if (child.forest) scs_forest_destroy(child.forest);
-            return rc;
+            if ((rc = plan_wave(wave, results))) {
+                for (SplitResult &res : results)
+                    for (Child &child : res.children)
+                        if (child.forest) scs_forest_destroy(child.forest);
+                return rc;
+            }
         }
         for (SplitResult &res : results) emit(wave[res.task], res, next);
         return SCS_OK;
@@ -335,7 +346,7 @@ class Driver {
         }
         const int jobs = static_cast<int>(concurrent.size());
         if (jobs == 0) return SCS_OK;
-        const int workers = std::max(1, std::min({kMaxWorkers, jobs, scs_host_threads()}));
+        const int workers = std::max(1, std::min({node_workers(), jobs, scs_host_threads()}));
         int rc = ensure_workers(ctx_, workers);
         if (rc) return rc;
         if (static_cast<int>(buffers_.size()) < workers) buffers_.resize(workers);
@@ -428,55 +439,75 @@ class Driver {
         return SCS_OK;
     }
 
-    // ref: scs.py:136-171 -- what the children of a split node are (thread-safe: touches only `res`)
-    void plan(const Task &task, SplitResult &res, Scratch &scratch) {
-        const std::vector<int32_t> &taxa = task.taxa;
-        const int n = static_cast<int>(taxa.size());
-        const int parts = res.stats.n_components != 1 ? res.stats.n_components : 2;
-        const int32_t *part = res.part.data();
-        // bucket the vertices by part, keeping ascending taxon order inside each
-        std::vector<int32_t> start(parts + 1, 0);
-        for (int v = 0; v < n; ++v) {
-            if (part[v] < 0 || part[v] >= parts) {
-                res.rc = SCS_ERR_INVALID;
-                return;
+    // ref: scs.py:136-171 -- what the children of the split nodes of a wave are
+    int plan_wave(const std::vector<Task> &wave, std::vector<SplitResult> &results) {
+        struct Pending {
+            SplitResult *res;
+            size_t child;       // index into res->children
+            std::vector<int32_t> members;  // taxa of the component, ascending
+        };
+        std::vector<Pending> pending;
+        std::vector<scs_induce_job> jobs;
+        if (owner_.size() < static_cast<size_t>(num_taxa_)) owner_.assign(static_cast<size_t>(num_taxa_), -1);
+        if (present_.size() < static_cast<size_t>(num_taxa_)) present_.assign(static_cast<size_t>(num_taxa_), 0);
+        std::vector<int32_t> start, members, cursor;
+        for (SplitResult &res : results) {
+            const Task &task = wave[res.task];
+            const std::vector<int32_t> &taxa = task.taxa;
+            const int n = static_cast<int>(taxa.size());
+            const int parts = res.stats.n_components != 1 ? res.stats.n_components : 2;
+            const int32_t *part = res.part.data();
+            // bucket the vertices by part, keeping ascending taxon order inside each
+            start.assign(parts + 1, 0);
+            for (int v = 0; v < n; ++v) {
+                if (part[v] < 0 || part[v] >= parts) return fail(ctx_, SCS_ERR_INVALID, "a partition label is out of range");
+                start[part[v] + 1] += 1;
             }
-            start[part[v] + 1] += 1;
-        }
-        for (int c = 0; c < parts; ++c) start[c + 1] += start[c];
-        std::vector<int32_t> members(n), cursor(start.begin(), start.end() - 1);
-        for (int v = 0; v < n; ++v) members[cursor[part[v]]++] = taxa[v];
-        for (int c = 0; c < parts; ++c) {
-            const int32_t *comp = members.data() + start[c];
-            const int size = start[c + 1] - start[c];
-            if (size == 0) continue;
-            res.children.emplace_back();
-            Child &child = res.children.back();
-            if (size <= 2) {  // ref: scs.py:143-145
-                child.star.assign(comp, comp + size);
-                continue;
-            }
-            for (int i = 0; i < size; ++i) scratch.keep[comp[i]] = 1;
-            const int rc = scs_forest_induce(task.forest, scratch.keep.data(), &child.forest);
-            for (int i = 0; i < size; ++i) scratch.keep[comp[i]] = 0;
-            if (rc) {
-                res.rc = rc;
-                return;
-            }
-            if (scs_forest_num_trees(child.forest) == 0) continue;  // raises when its wave is processed
-            scratch.present_taxa(child.forest, child.taxa);
-            if (static_cast<int>(child.taxa.size()) != size) {  // ref: scs.py:168-171
-                size_t ci = 0;
-                for (int i = 0; i < size; ++i) {
-                    while (ci < child.taxa.size() && child.taxa[ci] < comp[i]) ++ci;
-                    if (ci >= child.taxa.size() || child.taxa[ci] != comp[i]) child.missing.push_back(comp[i]);
+            for (int c = 0; c < parts; ++c) start[c + 1] += start[c];
+            members.resize(n);
+            cursor.assign(start.begin(), start.end() - 1);
+            for (int v = 0; v < n; ++v) members[cursor[part[v]]++] = taxa[v];
+            for (int c = 0; c < parts; ++c) {
+                const int32_t *comp = members.data() + start[c];
+                const int size = start[c + 1] - start[c];
+                if (size == 0) continue;
+                res.children.emplace_back();
+                Child &child = res.children.back();
+                if (size <= 2) {  // ref: scs.py:143-145
+                    child.star.assign(comp, comp + size);
+                    for (int i = 0; i < size; ++i) owner_[comp[i]] = -1;
+                    continue;
                 }
+                const int32_t job = static_cast<int32_t>(jobs.size());
+                for (int i = 0; i < size; ++i) owner_[comp[i]] = job;
+                scs_induce_job spec;
+                spec.src = task.forest;
+                jobs.push_back(spec);
+                pending.push_back(Pending{&res, res.children.size() - 1, std::vector<int32_t>(comp, comp + size)});
             }
         }
+        const auto t_induce = std::chrono::steady_clock::now();
+        const int rc = scs_forest_induce_batch(jobs.data(), static_cast<int>(jobs.size()), owner_.data(), present_.data());
+        if (trace_) trace_induce_ += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_induce).count();
+        if (rc) return fail(ctx_, rc, "restricting the source trees");
+        for (size_t j = 0; j < jobs.size(); ++j) {
+            Child &child = pending[j].res->children[pending[j].child];
+            child.forest = jobs[j].out;
+            // taxa of the component that are a tip of some kept tree; the others are attached as singleton
+            // children (ref: scs.py:168-171).  A child left without trees raises when its wave is processed.
+            const bool empty = scs_forest_num_trees(child.forest) == 0;
+            for (int32_t x : pending[j].members) {
+                if (present_[x]) child.taxa.push_back(x);
+                else if (!empty) child.missing.push_back(x);
+                present_[x] = 0;
+            }
+        }
+        return SCS_OK;
     }
 
     // ref: scs.py:139-174 -- attach the children to the output tree and queue the sub-problems
     void emit(Task &task, SplitResult &res, std::vector<Task> &next) {
+        if (!partitioned_) out_.shared_records += 1;
         if (record_) {
             scs_supertree::Record rec;
             rec.taxa = task.taxa;
@@ -502,9 +533,13 @@ class Driver {
     bool record_;
     int rank_ = 0, world_ = 1;
     bool partitioned_ = false;
+    const bool trace_ = std::getenv("SCS_DRIVER_TRACE") != nullptr;
+    double trace_induce_ = 0.0, trace_present_ = 0.0;  // thread-seconds (summed over host threads)
     scs_supertree &out_;
     int num_taxa_ = 0;
     std::vector<Scratch> scratch_;
+    std::vector<int32_t> owner_;    // global taxon id -> restriction job of the current wave
+    std::vector<uint8_t> present_;  // scratch of plan_wave (all zero between waves)
     std::vector<TourBuffers> buffers_;
     std::vector<int64_t> off_;
     std::vector<int32_t> tax_, dep_, root_, part_;
@@ -635,6 +670,8 @@ int scs_supertree_build(scs_ctx *ctx, const scs_forest *forest, int weighting, i
 }
 
 int64_t scs_supertree_shared_prefix(const scs_supertree *tree) { return tree ? tree->shared_prefix : 0; }
+
+int64_t scs_supertree_shared_records(const scs_supertree *tree) { return tree ? tree->shared_records : 0; }
 
 int scs_supertree_wave_seconds(const scs_supertree *tree, double *seconds3) {
     if (!tree || !seconds3) return SCS_ERR_INVALID;

@@ -16,6 +16,8 @@
 
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -241,6 +243,257 @@ int scs_forest_induce(const scs_forest *f, const uint8_t *keep, scs_forest **out
         }
     }
     *out = g;
+    return SCS_OK;
+}
+
+}  // extern "C" (the batch restriction below is internal to the library)
+
+namespace {
+
+// Which nodes of a tree survive when only tips with owner[taxon] == job are kept: one bottom-up pass
+// (pre-order puts every node after its parent) for the kept-tip counts and the number of children that
+// still carry kept tips, one top-down pass for the new indices.  Returns the number of retained nodes
+// (0: fewer than two tips are left and the tree is dropped, scs.py:447-448); idx[k] = new index or -1.
+inline int32_t mark_retained(const int32_t *par, const int32_t *tax, int64_t count, const int32_t *owner, int32_t job,
+                             std::vector<int32_t> &cnt, std::vector<int32_t> &live, std::vector<int32_t> &idx,
+                             int32_t *tips_out) {
+    *tips_out = 0;
+    if (count < 3) return 0;
+    cnt.assign(count, 0);
+    live.assign(count, 0);
+    int32_t kept = 0;
+    for (int64_t k = count - 1; k >= 1; --k) {
+        int32_t c = cnt[k];
+        if (tax[k] >= 0) {
+            c = owner[tax[k]] == job;
+            cnt[k] = c;
+            kept += c;
+        }
+        if (c) {
+            cnt[par[k]] += c;
+            live[par[k]] += 1;
+        }
+    }
+    if (kept < 2) return 0;
+    *tips_out = kept;
+    idx.resize(count);
+    int32_t next = 0;
+    for (int64_t k = 0; k < count; ++k) {
+        const bool retained = cnt[k] > 0 && (tax[k] >= 0 || live[k] >= 2);
+        idx[k] = retained ? next++ : -1;
+    }
+    return next;
+}
+
+// Restricted trees are first written to per-thread staging (their sizes are only known once they are
+// built), then copied to their place in the output forests.
+struct Staging {
+    std::vector<int32_t> parent, taxon;
+    std::vector<double> length, support;
+    void clear() {
+        parent.clear();
+        taxon.clear();
+        length.clear();
+        support.clear();
+    }
+};
+
+struct StagedTree {
+    int32_t nodes = 0, tips = 0, thread = 0;
+    int64_t offset = 0;  // in the thread's staging, then (after the layout) in the output forest
+};
+
+// The staging buffers are kept between calls (a wave of the recursion re-uses what the previous one
+// touched instead of page-faulting fresh memory); a concurrent caller simply uses buffers of its own.
+std::vector<Staging> g_staging;
+omp_lock_t g_staging_lock;
+bool g_staging_lock_ready = false;
+
+}  // namespace
+
+int scs_forest_induce_batch(scs_induce_job *jobs, int count, const int32_t *owner, uint8_t *present) {
+    if (count <= 0) return SCS_OK;
+    if (!jobs || !owner || !present) return SCS_ERR_INVALID;
+    // work items: (run of jobs with the same source forest, tree of that forest); the children of one
+    // recursion node are consecutive jobs, so a source tree is restricted to all of them while it is in cache
+    std::vector<int> run_first, run_last;  // jobs [first, last) share a source
+    std::vector<int64_t> run_item{0};      // first item of the run
+    std::vector<int64_t> job_tree{0};      // index of (job, tree 0) in `staged`
+    int64_t nodes = 0;
+    for (int j = 0; j < count; ++j) {
+        if (!jobs[j].src) return SCS_ERR_INVALID;
+        job_tree.push_back(job_tree.back() + jobs[j].src->num_trees());
+        if (j == 0 || jobs[j].src != jobs[j - 1].src) {
+            run_first.push_back(j);
+            run_last.push_back(j + 1);
+            run_item.push_back(run_item.back() + jobs[j].src->num_trees());
+            nodes += jobs[j].src->node_offsets.back();
+        } else {
+            run_last.back() = j + 1;
+        }
+    }
+    const int64_t items = run_item.back();
+    const int runs = static_cast<int>(run_first.size());
+    std::vector<int32_t> item_run(items);
+    for (int r = 0; r < runs; ++r)
+        for (int64_t i = run_item[r]; i < run_item[r + 1]; ++i) item_run[i] = r;
+    std::vector<StagedTree> staged(job_tree.back());
+    const bool threaded = nodes > kParallelNodes;
+    const int threads = threaded ? scs_host_threads() : 1;
+
+#pragma omp critical(scs_staging_init)
+    if (!g_staging_lock_ready) {
+        omp_init_lock(&g_staging_lock);
+        g_staging_lock_ready = true;
+    }
+    std::vector<Staging> own;
+    const bool shared_pool = omp_test_lock(&g_staging_lock) != 0;
+    std::vector<Staging> &pool = shared_pool ? g_staging : own;
+    if (static_cast<int>(pool.size()) < threads) pool.resize(threads);
+
+    static const bool trace = std::getenv("SCS_DRIVER_TRACE") != nullptr;
+    const double t_begin = omp_get_wtime();
+    // pass 1: build every restricted tree in staging
+#pragma omp parallel if (threaded) num_threads(threads)
+    {
+        const int me = omp_get_thread_num();
+        Staging &st = pool[me];
+        st.clear();
+        std::vector<int32_t> cnt, live, idx;
+#pragma omp for schedule(dynamic, 8)
+        for (int64_t i = 0; i < items; ++i) {
+            const int r = item_run[i];
+            const scs_forest *f = jobs[run_first[r]].src;
+            const int t = static_cast<int>(i - run_item[r]);
+            const int64_t base = f->node_offsets[t], cnt_nodes = f->node_offsets[t + 1] - base;
+            const int32_t *par = f->parent.data() + base;
+            const int32_t *tax = f->taxon.data() + base;
+            const double *len = f->length.data() + base;
+            const double *sup = f->support.data() + base;
+            for (int j = run_first[r]; j < run_last[r]; ++j) {
+                StagedTree &out = staged[job_tree[j] + t];
+                int32_t tips = 0;
+                const int32_t kept = mark_retained(par, tax, cnt_nodes, owner, j, cnt, live, idx, &tips);
+                if (kept == 0) continue;
+                out.nodes = kept;
+                out.tips = tips;
+                out.thread = me;
+                out.offset = static_cast<int64_t>(st.parent.size());
+                const size_t at = st.parent.size();
+                st.parent.resize(at + kept);
+                st.taxon.resize(at + kept);
+                st.length.resize(at + kept);
+                st.support.resize(at + kept);
+                int32_t *o_par = st.parent.data() + at;
+                int32_t *o_tax = st.taxon.data() + at;
+                double *o_len = st.length.data() + at;
+                double *o_sup = st.support.data() + at;
+                for (int64_t k = 0; k < cnt_nodes; ++k) {
+                    const int32_t q = idx[k];
+                    if (q < 0) continue;
+                    if (q == 0) {  // first retained node in pre-order: the new root, its own length is dropped
+                        o_par[0] = -1;
+                        o_len[0] = std::nan("");
+                    } else {
+                        double acc = len[k];
+                        int64_t a = par[k];
+                        while (idx[a] < 0) {     // merged unary ancestors, bottom-up
+                            acc = len[a] + acc;  // NaN (missing) propagates like None
+                            a = par[a];
+                        }
+                        o_par[q] = idx[a];
+                        o_len[q] = acc;
+                    }
+                    o_sup[q] = sup[k];
+                    o_tax[q] = tax[k];
+                    if (tax[k] >= 0) present[tax[k]] = 1;  // racing writers all store 1
+                }
+            }
+        }
+    }
+    // layout of every output forest
+    const double t_pass1 = omp_get_wtime();
+    int rc = SCS_OK;
+    std::vector<int64_t> dest(staged.size(), 0);
+    for (int j = 0; j < count && rc == SCS_OK; ++j) {
+        scs_forest *g = new (std::nothrow) scs_forest();
+        if (!g) {
+            rc = SCS_ERR_INVALID;
+            break;
+        }
+        const scs_forest *f = jobs[j].src;
+        g->num_taxa = f->num_taxa;
+        int64_t at = 0;
+        const int T = f->num_trees();
+        for (int t = 0; t < T; ++t) {
+            const StagedTree &tree = staged[job_tree[j] + t];
+            if (tree.nodes == 0) continue;
+            dest[job_tree[j] + t] = at;
+            at += tree.nodes;
+            g->node_offsets.push_back(at);
+            g->leaf_offsets.push_back(g->leaf_offsets.back() + tree.tips);
+            g->weight.push_back(f->weight[t]);
+            g->source.push_back(f->source[t]);
+        }
+        g->parent.resize_uninitialized(at);
+        g->length.resize_uninitialized(at);
+        g->support.resize_uninitialized(at);
+        g->taxon.resize_uninitialized(at);
+        jobs[j].out = g;
+    }
+    const double t_layout = omp_get_wtime();
+    if (rc != SCS_OK) {
+        for (int j = 0; j < count; ++j) {
+            delete jobs[j].out;
+            jobs[j].out = nullptr;
+        }
+    } else {
+        // pass 2: staging -> output forests
+        const int64_t total = static_cast<int64_t>(staged.size());
+        std::vector<int32_t> tree_job(total);
+        for (int j = 0; j < count; ++j)
+            for (int64_t i = job_tree[j]; i < job_tree[j + 1]; ++i) tree_job[i] = j;
+#pragma omp parallel for schedule(dynamic, 32) if (threaded) num_threads(threads)
+        for (int64_t i = 0; i < total; ++i) {
+            const StagedTree &tree = staged[i];
+            if (tree.nodes == 0) continue;
+            const Staging &st = pool[tree.thread];
+            scs_forest *g = jobs[tree_job[i]].out;
+            const size_t n = static_cast<size_t>(tree.nodes);
+            std::memcpy(g->parent.data() + dest[i], st.parent.data() + tree.offset, n * sizeof(int32_t));
+            std::memcpy(g->taxon.data() + dest[i], st.taxon.data() + tree.offset, n * sizeof(int32_t));
+            std::memcpy(g->length.data() + dest[i], st.length.data() + tree.offset, n * sizeof(double));
+            std::memcpy(g->support.data() + dest[i], st.support.data() + tree.offset, n * sizeof(double));
+        }
+    }
+    if (shared_pool) omp_unset_lock(&g_staging_lock);
+    if (trace)
+        std::fprintf(stderr, "[scs induce] jobs %d items %lld trees %zu: pass1 %.2f ms, layout %.2f ms, pass2 %.2f ms\n", count,
+                     static_cast<long long>(items), staged.size(), 1e3 * (t_pass1 - t_begin), 1e3 * (t_layout - t_pass1),
+                     1e3 * (omp_get_wtime() - t_layout));
+    return rc;
+}
+
+extern "C" {
+
+/* The loop scs.py:139-155 in one call: out[c] = the forest restricted to the taxa x with part[x] == c,
+ * c = 0..count-1 (part[x] < 0 or >= count: the taxon is dropped); present[x] (may be NULL) is set to 1
+ * for every taxon left in some restricted tree. */
+int scs_forest_induce_parts(const scs_forest *f, const int32_t *part, int count, scs_forest **out, uint8_t *present) {
+    if (!f || !part || count < 0 || !out) return SCS_ERR_INVALID;
+    std::vector<scs_induce_job> jobs(static_cast<size_t>(count));
+    for (int c = 0; c < count; ++c) {
+        jobs[c].src = f;
+        out[c] = nullptr;
+    }
+    std::vector<uint8_t> scratch;
+    if (!present) {
+        scratch.assign(f->num_taxa ? f->num_taxa : 1, 0);
+        present = scratch.data();
+    }
+    const int rc = scs_forest_induce_batch(jobs.data(), count, part, present);
+    if (rc) return rc;
+    for (int c = 0; c < count; ++c) out[c] = jobs[c].out;
     return SCS_OK;
 }
 

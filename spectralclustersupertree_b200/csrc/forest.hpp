@@ -58,3 +58,15 @@ struct scs_forest {
 
 // Host threads used by the forest operations and the recursion driver (0 = OpenMP's default).
 int scs_host_threads();
+
+// Many restrictions at once (the children of every node of one wave of the recursion).  Job j keeps the
+// tips x of `src` with owner[x] == j: the sub-problems of a wave have disjoint taxon sets, so one
+// owner[] array (global taxon id -> job) serves the whole wave.  All (job, tree) pairs are spread over the
+// host threads, which balances a wave of two huge restrictions as well as one of a thousand small ones.
+// `out` receives the restricted forest; present[x] is set to 1 for every taxon that is a tip of a kept
+// tree (the caller clears it), so the taxa of the child need no further scan (scs.py:708-725).
+struct scs_induce_job {
+    const scs_forest *src = nullptr;
+    scs_forest *out = nullptr;
+};
+int scs_forest_induce_batch(scs_induce_job *jobs, int count, const int32_t *owner, uint8_t *present);

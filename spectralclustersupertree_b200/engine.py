@@ -212,6 +212,7 @@ class Engine:
             out = {"parent": parent, "taxon": taxon, "nodes_small": small.value, "nodes_large": large.value,
                    "waves": waves.value, "pair_visits": pairs.value, "records": [],
                    "shared_prefix": int(self._lib.scs_supertree_shared_prefix(handle)),
+                   "shared_records": int(self._lib.scs_supertree_shared_records(handle)),
                    "wave_tasks": wave_tasks[: waves.value].tolist(), "wave_max_n": wave_max_n[: waves.value].tolist(),
                    "wave_seconds": wave_seconds[: waves.value].tolist(),
                    "seconds": dict(zip(("large_nodes", "small_batches", "restrict", "tours"), seconds.tolist(), strict=True))}  # fmt: skip
@@ -602,6 +603,21 @@ class Forest:
         if status != _lib.SCS_OK:
             raise ScsError(status, "scs_forest_induce")
         return Forest(handle, self.names)
+
+    def induce_parts(self, part_of_taxon: np.ndarray, count: int) -> tuple[list["Forest"], np.ndarray]:
+        """All restrictions of one recursion node at once (ref: scs.py:139-155): forest ``c`` keeps the
+        taxa with ``part_of_taxon[x] == c``.  Also returns the taxa still present in some restricted tree."""
+        part = np.ascontiguousarray(part_of_taxon, dtype=np.int32)
+        if len(part) < self.num_taxa:
+            msg = "part_of_taxon needs one entry per global taxon id"
+            raise ValueError(msg)
+        handles = (ctypes.c_void_p * max(count, 1))()
+        present = np.zeros(max(self.num_taxa, 1), dtype=np.uint8)
+        status = self._lib.scs_forest_induce_parts(self._handle, ptr(part), count, ctypes.addressof(handles), ptr(present))
+        if status != _lib.SCS_OK:
+            raise ScsError(status, "scs_forest_induce_parts")
+        forests = [Forest(ctypes.c_void_p(handles[c]), self.names) for c in range(count)]
+        return forests, np.flatnonzero(present[: self.num_taxa]).astype(np.int32)
 
     def tours(self, weighting: str, local_id: np.ndarray | None = None):
         """Leaf tours (``flatten.LeafTours``) with vertex ids = rank among the taxa present."""

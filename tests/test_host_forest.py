@@ -113,3 +113,30 @@ def test_forest_rejects_malformed_arrays():
         Forest.from_arrays([0, 3], [-1, 2, 0], None, None, [-1, 0, 1], [1.0], ["a", "b"])
     with pytest.raises(ScsError):  # tip without a taxon id
         Forest.from_arrays([0, 3], [-1, 0, 0], None, None, [-1, 0, -1], [1.0], ["a", "b"])
+
+
+@pytest.mark.parametrize("name", ["dcm_iq", "s_300x40_branch_weighted", "c2_500x50_branch"])
+@pytest.mark.parametrize("parts", [2, 5])
+def test_induce_parts_equals_one_restriction_per_part(name, parts):
+    """The batched restriction the recursion driver uses (all children of a node in one pass over the
+    host threads) against ``induce`` part by part: same trees, same arrays, bit for bit."""
+    case = load_case(name)
+    names = case["names"]
+    forest = Forest.from_trees(parse(case["lines"]), case["weights"], names)
+    rng = np.random.RandomState(11)
+    part = rng.randint(0, parts + 1, size=len(names)).astype(np.int32)
+    part[part == parts] = -1  # some taxa belong to no part (stars / dropped)
+    subs, present = forest.induce_parts(part, parts)
+    assert len(subs) == parts
+    seen = []
+    for c, sub in enumerate(subs):
+        want = forest.induce(np.flatnonzero(part == c).astype(np.int32))
+        assert sub.num_trees == want.num_trees
+        assert sub.num_leaves == want.num_leaves
+        assert np.array_equal(sub.weights(), want.weights())
+        for t in range(sub.num_trees):
+            for got_arr, want_arr in zip(sub.tree_arrays(t), want.tree_arrays(t), strict=True):
+                assert np.array_equal(got_arr, want_arr, equal_nan=True)
+        assert_same_tours(sub.tours(case["weighting"]), want.tours(case["weighting"]))
+        seen.append(want.taxa())
+    assert np.array_equal(present, np.sort(np.concatenate(seen)))
