@@ -52,6 +52,8 @@ WORKLOADS = {
     "c2": (500, 50, "branch", 2000, False),
     "c3": (1000, 100, "branch", 3000, True),
     "c4": (10000, 1000, "depth", 4000, False),
+    # not a bench line (generation alone takes minutes): tools/run_workload.py runs it at 1/2/4/8 GPUs
+    "c5": (50000, 5000, "branch", 5000, False),
 }
 
 
