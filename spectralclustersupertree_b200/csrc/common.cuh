@@ -42,7 +42,7 @@ enum Slot : int {
     SLOT_INV,
     SLOT_INV_SORTED,
     SLOT_DEGREE_PART,
-    SLOT_SPARSE,
+    SLOT_LINKS,
     // components / contraction
     SLOT_UF_PARENT,
     SLOT_LABEL,

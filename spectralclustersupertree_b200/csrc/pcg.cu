@@ -5,23 +5,23 @@
 //
 // Layout.  Source trees arrive as leaf tours (flatten.py / forest.cpp): leaves in depth-first order
 // and, for consecutive leaves i, i+1, the depth and weighting value of their LCA.  The LCA of the
-// leaves at tour positions p < q is the shallowest entry of adj[p..q-1]: a range-minimum query.
-// pcg_sparse_table builds, once per tree, the classic doubling table over (depth, position) keys
-// (level j holds the minimum of 2^j consecutive entries), so every leaf pair's LCA is two table
-// reads and a min -- no pointer chasing, no per-row rescan of the tour.
+// leaves at tour positions p < q is the shallowest entry of adj[p..q-1].  Seen from one leaf p, that running
+// minimum is a staircase: it changes once per ancestor of the leaf, and all leaves between two steps share
+// their LCA with p.  pcg_tour_links stores, per tour entry, the nearest strictly shallower entry on either
+// side, so a row CTA recovers the staircase of a tree with ~depth dependent reads.
 //
 // Kernel shape.  One CTA owns one row `a` of W (one taxon) and keeps the row's accumulators in
 // shared memory (8 B weight + 2/4 B count per column).  It visits the trees containing `a` in
-// input order (their headers are staged 64 at a time, so the dependent loads that locate a tree
-// overlap); for each, every thread takes other leaves q of the tree, looks up LCA(a, q) and, unless
-// it is the root (scs.py:570-579: pairs separated by the root are not proper clusters), adds
-// fl(val(LCA) * w_t) to column taxon(q) (scs.py:644-658).  Within a tree every leaf is a distinct
-// column, so threads never collide; one barrier separates consecutive trees, so every W entry is
-// summed in tree input order with separately rounded multiply and add (scs.py:655-657) --
-// bit-identical to the reference, no atomics on W, and W[a][b] == W[b][a] bit for bit.  The finished
-// row is written once, coalesced, together with its adjacency bits (C > 0, scs.py:651-652),
-// max-graph bits (C == max(occ_a, occ_b), scs.py:302-305) and its row sum (the degree the spectral
-// step needs), so the co-occurrence matrix never has to be written to HBM unless the caller asks.
+// input order, 32 at a time: two threads per tree walk the leaf's chains into (boundary, term) segments in
+// shared memory; then every thread takes leaves q of the tree that share a non-root LCA with `a` (pairs
+// separated by the root are no proper clusters, scs.py:570-579, and are never touched), finds q's segment
+// (5-step search, conflict-free) and adds fl(val(LCA) * w_t) to column taxon(q) (scs.py:644-658).  Within a
+// tree every leaf is a distinct column, so threads never collide; one barrier separates consecutive trees,
+// so every W entry is summed in tree input order with separately rounded multiply and add
+// (scs.py:655-657) -- bit-identical to the reference, no atomics on W, and W[a][b] == W[b][a] bit for
+// bit.  The finished row is written once, coalesced, together with its adjacency bits (C > 0,
+// scs.py:651-652), max-graph bits (C == max(occ_a, occ_b), scs.py:302-305) and its row sum (the degree the
+// spectral step needs), so the co-occurrence matrix never has to be written to HBM unless the caller asks.
 //
 // Rows wider than shared memory (n > ~22k columns) are split into column chunks (gridDim.y);
 // each chunk CTA walks the same trees and keeps only its columns.
@@ -34,8 +34,7 @@ namespace {
 
 constexpr int kRowThreads = 512;  // 2 CTAs/SM at n = 10^4 (100 KB of row accumulators each): 32 warps/SM
 constexpr int kWarps = kRowThreads / 32;
-constexpr int kHeaderBatch = 64;  // (row, tree) incidences whose headers are staged together
-constexpr unsigned long long kNoKey = ~0ull;
+constexpr size_t kRowsStaticSmem = 16 * 1024;  // room left for the row kernel's static shared memory (TreeBatch)
 
 // ---- index: leaf -> tree, occurrences, taxon -> leaves ------------------------------------
 __global__ void pcg_index_leaves(int n, int T, int64_t L, const int64_t *__restrict__ leaf_offsets,
@@ -120,123 +119,275 @@ __global__ void pcg_sort_inverse(int row0, const int32_t *__restrict__ row_ptr, 
     }
 }
 
-// ---- range-minimum table over the consecutive-leaf LCAs --------------------------------------------
-// st[j * L + g] = the shallowest adj entry among [g, g + 2^j) of the same tree, as {key, value} with
-// key = depth << 32 | position in tree (ties: leftmost; equal depth in a range means the same node) and
-// value = the weighting value of that LCA, so a lookup needs no second, dependent read.
-// One CTA per tree builds all levels of its tree.
-struct __align__(16) LcaEntry {
-    unsigned long long key;
+// ---- per-tree links: nearest strictly shallower tour entry on either side ----------------------------
+// adj entry i of a tree is the LCA of its leaves i and i + 1.  For a leaf at tour position p the LCA with
+// the leaves to its right is the running minimum of adj[p..]: it changes exactly at the chain
+// p -> next_right[p] -> next_right[next_right[p]] ... (next_right[i] = first j > i with a strictly smaller
+// depth; equal depths inside a range are the same node), one step per ancestor of the leaf, and likewise to
+// the left.  pcg_tour_links stores, per entry, both links and the weighting value, so that a row CTA gets
+// the whole "staircase" of (leaf range, value) segments of a tree from ~depth dependent 16-byte reads
+// instead of one range-minimum query per leaf pair.  Entries at root depth are marked: every pair they
+// separate has the root as LCA and is no proper cluster (scs.py:570-579).
+struct __align__(16) LinkEntry {
+    int32_t next_right, next_left;  // entry index within the tree, kNone, or kRootLevel for both
     double val;
 };
+constexpr int32_t kNone = -1;
+constexpr int32_t kRootLevel = -2;
 
+// One CTA per tree.  Block minima over 32 and 1024 entries (shared memory) bound every search to
+// O(32 + 32 + k / 1024) probes, independent for every entry.
 __global__ void __launch_bounds__(256)
-pcg_sparse_table(int64_t L, int levels, const int64_t *__restrict__ leaf_offsets,
-                 const int32_t *__restrict__ adj_depth, const double *__restrict__ adj_val, LcaEntry *st) {
+pcg_tour_links(int n, const int64_t *__restrict__ leaf_offsets, const int32_t *__restrict__ adj_depth,
+               const double *__restrict__ adj_val, const int32_t *__restrict__ root_depth,
+               LinkEntry *__restrict__ links) {
+    extern __shared__ int32_t link_smem[];
     const int t = blockIdx.x;
     const int64_t tb = leaf_offsets[t];
-    const int k = static_cast<int>(leaf_offsets[t + 1] - tb);
-    const int entries = k - 1;  // adj entries of this tree (the last leaf has none)
-    for (int i = threadIdx.x; i < k; i += blockDim.x) {
-        LcaEntry e;
-        e.key = i < entries
-                    ? (static_cast<unsigned long long>(static_cast<uint32_t>(adj_depth[tb + i])) << 32) | static_cast<uint32_t>(i)
-                    : kNoKey;
-        e.val = i < entries ? adj_val[tb + i] : 0.0;
-        st[tb + i] = e;
+    const int m = static_cast<int>(leaf_offsets[t + 1] - tb) - 1;  // adj entries of this tree
+    if (m <= 0 || m >= n) return;  // nothing to link / a repeated taxon (the row kernel flags it)
+    const int32_t *D = adj_depth + tb;
+    const int nb1 = (m + 31) >> 5, nb2 = (nb1 + 31) >> 5;
+    int32_t *B1 = link_smem, *B2 = link_smem + nb1;
+    const int lane = threadIdx.x & 31;
+    for (int i0 = (threadIdx.x >> 5) << 5; i0 < m; i0 += blockDim.x) {  // a warp per 32-entry block
+        int v = i0 + lane < m ? D[i0 + lane] : INT32_MAX;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, off));
+        if (lane == 0) B1[i0 >> 5] = v;
     }
-    for (int j = 1; j < levels; ++j) {
-        const int span = 1 << j;
-        if (span > entries) break;
-        __syncthreads();
-        const LcaEntry *prev = st + static_cast<size_t>(j - 1) * L + tb;
-        LcaEntry *cur = st + static_cast<size_t>(j) * L + tb;
-        for (int i = threadIdx.x; i + span <= entries; i += blockDim.x) {
-            const LcaEntry x = prev[i], y = prev[i + (span >> 1)];
-            cur[i] = x.key < y.key ? x : y;
+    __syncthreads();
+    for (int b0 = (threadIdx.x >> 5) << 5; b0 < nb1; b0 += blockDim.x) {
+        int v = b0 + lane < nb1 ? B1[b0 + lane] : INT32_MAX;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, off));
+        if (lane == 0) B2[b0 >> 5] = v;
+    }
+    __syncthreads();
+    const int rd = root_depth[t];
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        const int d = D[i];
+        LinkEntry e;
+        e.val = adj_val[tb + i];
+        if (d == rd) {
+            e.next_right = e.next_left = kRootLevel;
+            links[tb + i] = e;
+            continue;
         }
+        // ---- to the right: own block, blocks of the own superblock, superblocks, then back down
+        int j = i + 1;
+        {
+            const int end1 = min(m, ((i >> 5) + 1) << 5);
+            while (j < end1 && D[j] >= d) ++j;
+            if (j == end1 && j < m) {
+                int b = j >> 5;
+                const int endb = min(nb1, ((b >> 5) + 1) << 5);
+                while (b < endb && B1[b] >= d) ++b;
+                if (b == endb && b < nb1) {
+                    int s = b >> 5;
+                    while (s < nb2 && B2[s] >= d) ++s;
+                    if (s < nb2) {
+                        b = s << 5;
+                        while (B1[b] >= d) ++b;
+                    } else {
+                        b = nb1;
+                    }
+                }
+                if (b < nb1) {
+                    j = b << 5;
+                    while (D[j] >= d) ++j;
+                } else {
+                    j = m;
+                }
+            }
+        }
+        e.next_right = j < m ? j : kNone;
+        // ---- to the left, mirrored
+        j = i - 1;
+        {
+            const int end1 = (i >> 5) << 5;  // first entry of the own block
+            while (j >= end1 && D[j] >= d) --j;
+            if (j < end1 && j >= 0) {
+                int b = j >> 5;
+                const int endb = (b >> 5) << 5;  // first block of the own superblock
+                while (b >= endb && B1[b] >= d) --b;
+                if (b < endb && b >= 0) {
+                    int s = b >> 5;
+                    while (s >= 0 && B2[s] >= d) --s;
+                    if (s >= 0) {
+                        b = (s << 5) + 31;
+                        while (B1[b] >= d) --b;
+                    } else {
+                        b = -1;
+                    }
+                }
+                if (b >= 0) {
+                    j = min(m - 1, (b << 5) + 31);
+                    while (D[j] >= d) --j;
+                } else {
+                    j = -1;
+                }
+            }
+        }
+        e.next_left = j >= 0 ? j : kNone;
+        links[tb + i] = e;
     }
 }
 
 // ---- the row kernel -----------------------------------------------------------------------
+constexpr int kTreeBatch = 32;  // (row, tree) incidences staged together
+constexpr int kChain = 15;      // chain steps per side kept per tree; longer chains continue in further rounds
+constexpr int kSlots = 2 * kChain + 2;  // == 32: boundaries of one tree, ascending
+static_assert(kSlots == 32, "the segment search below is a 5-step binary search over 32 boundaries");
+constexpr int32_t kFar = 1 << 30;
+
 struct TreeHeader {
     int64_t base;  // first leaf of the tree in the tour arrays
     double weight;
-    int leaves, position, root_depth, pad;
+    int leaves, position;
 };
 
-constexpr int kPerThread = 2;                          // visits per thread per segment
-constexpr int kSegment = kRowThreads * kPerThread;     // visits per segment
+// What a row CTA knows about the trees of the current batch.  For tree e, a leaf q of the tree lies in
+// segment idx iff bound[e][idx] < q <= bound[e][idx + 1]; the segment's pairs (a, leaf q) all have the same
+// LCA and get term[e][idx].  The middle segment (kChain, kChain + 1] is the part already handled (at first
+// the leaf of the row itself); left segments grow downwards from it, right segments upwards.
+struct TreeBatch {
+    TreeHeader header[kTreeBatch];
+    double term[kTreeBatch][kSlots];
+    int32_t bound[kTreeBatch][kSlots];
+    int32_t left_count[kTreeBatch], right_count[kTreeBatch];  // leaves in the left / right segments
+    int32_t low[kTreeBatch], high[kTreeBatch];               // first / last boundary in use
+    int32_t resume[kTreeBatch][2];                           // chain entry to continue from, or kNone
+    uint32_t unfinished;                                     // bit e: tree e has a chain to continue
+};
+
+// Walk one side of the chain of tree e (thread-serial: one dependent 16-byte read per ancestor).
+__device__ void walk_chain(TreeBatch &tb, int e, int side, bool first, const LinkEntry *__restrict__ links) {
+    const TreeHeader h = tb.header[e];
+    const LinkEntry *lk = links + h.base;
+    int32_t *bound = tb.bound[e];
+    double *term = tb.term[e];
+    int c = 0;
+    if (side == 1) {
+        int i;
+        if (first) {
+            bound[kChain + 1] = h.position;
+            i = (h.leaves >= 2 && h.position <= h.leaves - 2) ? h.position : kNone;
+        } else {
+            bound[kChain + 1] = bound[tb.high[e]];
+            i = tb.resume[e][1];
+        }
+        while (i >= 0 && c < kChain) {
+            const LinkEntry r = lk[i];
+            if (r.next_right == kRootLevel) { i = kNone; break; }
+            term[kChain + 1 + c] = __dmul_rn(r.val, h.weight);
+            bound[kChain + 2 + c] = r.next_right < 0 ? h.leaves - 1 : r.next_right;
+            ++c;
+            i = r.next_right;
+        }
+        tb.high[e] = kChain + 1 + c;
+        tb.resume[e][1] = i;
+        tb.right_count[e] = bound[kChain + 1 + c] - bound[kChain + 1];
+        for (int idx = kChain + 2 + c; idx < kSlots; ++idx) bound[idx] = kFar;
+    } else {
+        int i;
+        if (first) {
+            bound[kChain] = h.position - 1;
+            i = (h.leaves >= 2 && h.position >= 1 && h.position <= h.leaves - 1) ? h.position - 1 : kNone;
+        } else {
+            bound[kChain] = bound[tb.low[e]];
+            i = tb.resume[e][0];
+        }
+        while (i >= 0 && c < kChain) {
+            const LinkEntry r = lk[i];
+            if (r.next_left == kRootLevel) { i = kNone; break; }
+            term[kChain - 1 - c] = __dmul_rn(r.val, h.weight);
+            bound[kChain - 1 - c] = r.next_left;  // kNone == -1: the segment starts at the first leaf
+            ++c;
+            i = r.next_left;
+        }
+        tb.low[e] = kChain - c;
+        tb.resume[e][0] = i;
+        tb.left_count[e] = bound[kChain] - bound[kChain - c];
+        for (int idx = kChain - c - 1; idx >= 0; --idx) bound[idx] = -kFar;
+    }
+}
+
+// A thread visits runs of kRun consecutive leaves of one side of a tree: one segment search per run, then
+// the segment index only moves forward (consecutive leaves cross at most one boundary).  A step covers
+// kRowThreads runs of one tree.
+#ifndef SCS_RUN
+#define SCS_RUN 4
+#endif
+constexpr int kRun = SCS_RUN;
 
 struct Pending {
-    int col[kPerThread];     // column of the chunk, or -1
-    double term[kPerThread];  // fl(val(LCA) * w_t)
+    int taxon[kRun];  // taxa of the run's leaves (raw global loads: first used after the next barrier)
+    int q0, len, idx;  // first leaf, leaves in the run (0: nothing to do), segment of the first leaf
 };
 
-// Everything a segment needs from global memory, into registers.  v enumerates the other leaves of the
-// tree: v < p is leaf v, v >= p is leaf v + 1.
-__device__ __forceinline__ LcaEntry load_entry(const LcaEntry *p) {
-    const ulonglong2 raw = *reinterpret_cast<const ulonglong2 *>(p);  // one 16-byte load
-    LcaEntry e;
-    e.key = raw.x;
-    e.val = __longlong_as_double(static_cast<long long>(raw.y));
-    return e;
+__device__ __forceinline__ int runs_of(int leaves) { return (leaves + kRun - 1) / kRun; }
+
+// Run u of tree e (left runs first, then right runs).  Warp-uniform precondition: (u & ~31) < runs.
+__device__ __forceinline__ void load_run(const TreeBatch &tb, int e, int u, int nl, int nr,
+                                         const int32_t *__restrict__ leaf_taxon, Pending &out) {
+    const int32_t *bound = tb.bound[e];
+    const int lruns = runs_of(nl);
+    const bool left = u < lruns;
+    const int r = left ? u : u - lruns;
+    const int first = (left ? bound[tb.low[e]] : bound[kChain + 1]) + 1;
+    out.q0 = first + r * kRun;
+    out.len = max(0, min(kRun, (left ? nl : nr) - r * kRun));
+    const int32_t *src = leaf_taxon + tb.header[e].base + out.q0;
+#pragma unroll
+    for (int j = 0; j < kRun; ++j) out.taxon[j] = j < out.len ? src[j] : -1;
+    int idx = 0;
+#pragma unroll
+    for (int step = kSlots / 2; step > 0; step >>= 1)
+        if (bound[idx + step] < out.q0) idx += step;
+    out.idx = idx;
 }
 
-__device__ __forceinline__ void load_segment(const TreeHeader &h, int seg, int64_t L,
-                                             const LcaEntry *__restrict__ st,
-                                             const int32_t *__restrict__ leaf_taxon, int col0, int ncols, int tid,
-                                             Pending &out) {
-    const int p = h.position;
-    const LcaEntry *st_t = st + h.base;
-    const int32_t *taxon_t = leaf_taxon + h.base;
-    LcaEntry x[kPerThread], y[kPerThread];
-    int col[kPerThread];
+template <typename CountT>
+__device__ __forceinline__ void apply_run(const TreeBatch &tb, int e, const Pending &p, int col0, int ncols,
+                                          double *accW, CountT *accC) {
+    if (__all_sync(0xffffffffu, p.len == 0)) return;
+    const int32_t *bound = tb.bound[e];
+    const double *term = tb.term[e];
+    int idx = p.idx;
+    double t = term[idx];
+    int next_bound = bound[idx + 1];
+    int col[kRun];
+    double w[kRun];
+    // all loads of the run, then all stores: the leaves of a tree are distinct columns
 #pragma unroll
-    for (int r = 0; r < kPerThread; ++r) {
-        const int v = seg * kSegment + r * kRowThreads + tid;
-        col[r] = -1;
-        x[r].key = y[r].key = kNoKey;
-        x[r].val = y[r].val = 0.0;
-        if (v < h.leaves - 1) {
-            const int q = v < p ? v : v + 1;
-            const int lo = v < p ? q : p;  // adj entries [lo, lo + len) lie between the two leaves
-            const int len = v < p ? p - q : q - p;
-            const int j = 31 - __clz(len);
-            const LcaEntry *level = st_t + static_cast<size_t>(j) * L;
-            x[r] = load_entry(level + lo);
-            y[r] = load_entry(level + lo + len - (1 << j));
-            col[r] = taxon_t[q] - col0;
+    for (int j = 0; j < kRun; ++j) {
+        if (j < p.len && p.q0 + j > next_bound) {
+            ++idx;
+            t = term[idx];
+            next_bound = bound[idx + 1];
         }
+        const int c = p.taxon[j] - col0;
+        col[j] = (j < p.len && static_cast<unsigned>(c) < static_cast<unsigned>(ncols)) ? c : -1;
+        if (col[j] >= 0) w[j] = __dadd_rn(accW[col[j]], t);
     }
 #pragma unroll
-    for (int r = 0; r < kPerThread; ++r) {
-        const LcaEntry e = x[r].key < y[r].key ? x[r] : y[r];
-        const bool proper = col[r] != -1 && static_cast<int>(e.key >> 32) != h.root_depth &&
-                            static_cast<unsigned>(col[r]) < static_cast<unsigned>(ncols);
-        out.col[r] = proper ? col[r] : -1;
-        out.term[r] = __dmul_rn(e.val, h.weight);
-    }
-}
-
-// next (tree, segment) of the batch
-__device__ __forceinline__ void advance(const TreeHeader *headers, int batch, int &e, int &seg) {
-    if (e >= batch) return;
-    ++seg;
-    if (seg * kSegment >= headers[e].leaves - 1) {
-        seg = 0;
-        do {
-            ++e;
-        } while (e < batch && headers[e].leaves < 2);
-    }
+    for (int j = 0; j < kRun; ++j)
+        if (col[j] >= 0) accW[col[j]] = w[j];
+    CountT cnt[kRun];
+#pragma unroll
+    for (int j = 0; j < kRun; ++j)
+        if (col[j] >= 0) cnt[j] = accC[col[j]];
+#pragma unroll
+    for (int j = 0; j < kRun; ++j)
+        if (col[j] >= 0) accC[col[j]] = static_cast<CountT>(cnt[j] + 1);
 }
 
 template <typename CountT, bool kWriteC>
-__global__ void __launch_bounds__(kRowThreads)
-pcg_rows_kernel(int n, int row0, int words_per_row, int cols_per_chunk, int64_t L,
+__global__ void __launch_bounds__(kRowThreads, 2)
+pcg_rows_kernel(int n, int row0, int words_per_row, int cols_per_chunk,
                 const int64_t *__restrict__ leaf_offsets, const int32_t *__restrict__ leaf_taxon,
-                const LcaEntry *__restrict__ st, const int32_t *__restrict__ root_depth,
-                const double *__restrict__ tree_weight,
+                const LinkEntry *__restrict__ links, const double *__restrict__ tree_weight,
                 const int32_t *__restrict__ leaf_tree, const int32_t *__restrict__ row_ptr,
                 const int32_t *__restrict__ inv_sorted, const int32_t *__restrict__ occ,
                 double *__restrict__ W, int32_t *__restrict__ C, uint32_t *__restrict__ adj_bits,
@@ -244,7 +395,7 @@ pcg_rows_kernel(int n, int row0, int words_per_row, int cols_per_chunk, int64_t 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *accW = reinterpret_cast<double *>(smem_raw);
     CountT *accC = reinterpret_cast<CountT *>(accW + cols_per_chunk);
-    __shared__ TreeHeader headers[kHeaderBatch];
+    __shared__ TreeBatch tb;
     __shared__ double warp_sum[kWarps];
 
     const int a = row0 + blockIdx.x;  // W / C point at the row block: its first row is row0
@@ -259,53 +410,94 @@ pcg_rows_kernel(int n, int row0, int words_per_row, int cols_per_chunk, int64_t 
 
     const int ebase = row_ptr[a];
     const int cnt = row_ptr[a + 1] - ebase;
-    for (int e0 = 0; e0 < cnt; e0 += kHeaderBatch) {
-        const int batch = min(kHeaderBatch, cnt - e0);
-        __syncthreads();  // the previous batch's headers (and the initialisation) are done with
+    for (int e0 = 0; e0 < cnt; e0 += kTreeBatch) {
+        const int batch = min(kTreeBatch, cnt - e0);
+        __syncthreads();  // the previous batch (and the initialisation) is done with
         if (tid < batch) {
             const int g = inv_sorted[ebase + e0 + tid];
             const int t = leaf_tree[g];
-            const int64_t tb = leaf_offsets[t];
+            const int64_t base = leaf_offsets[t];
             TreeHeader h;
-            h.base = tb;
+            h.base = base;
             h.weight = tree_weight[t];
-            h.leaves = static_cast<int>(leaf_offsets[t + 1] - tb);
-            if (h.leaves > n) {  // more leaves than taxa: a taxon is repeated, the table would be too shallow
+            h.leaves = static_cast<int>(leaf_offsets[t + 1] - base);
+            if (h.leaves > n) {  // more leaves than taxa: a taxon is repeated
                 *bad = 1;
                 h.leaves = 0;
             }
-            h.position = static_cast<int>(g - tb);
-            h.root_depth = root_depth[t];
-            h.pad = 0;
-            headers[tid] = h;
+            h.position = static_cast<int>(g - base);
+            tb.header[tid] = h;
+        }
+        if (tid == 0) tb.unfinished = 0;
+        __syncthreads();
+        if (tid < 2 * batch) {
+            walk_chain(tb, tid >> 1, tid & 1, true, links);
+            if (tb.resume[tid >> 1][tid & 1] >= 0) atomicOr(&tb.unfinished, 1u << (tid >> 1));
         }
         __syncthreads();
-        // Software pipeline over segments of kSegment visits: the loads of the next segment (table,
-        // taxon, value: three dependent L2 round trips) are issued before the shared-memory updates of
-        // the current one, and each thread keeps kPerThread independent chains in flight.  Only the
-        // updates are ordered: a barrier whenever the tree changes (segments of one tree touch
-        // distinct columns).
-        int next_e = 0, next_seg = 0;
-        Pending cur, nxt;
-        load_segment(headers[0], 0, L, st, leaf_taxon, col0, ncols, tid, cur);
-        int cur_e = 0;
-        advance(headers, batch, next_e, next_seg);
-        while (true) {
-            const bool more = next_e < batch;
-            if (more) load_segment(headers[next_e], next_seg, L, st, leaf_taxon, col0, ncols, tid, nxt);
-#pragma unroll
-            for (int r = 0; r < kPerThread; ++r) {
-                const int c = cur.col[r];
-                if (c >= 0) {
-                    accW[c] = __dadd_rn(accW[c], cur.term[r]);
-                    accC[c] = static_cast<CountT>(accC[c] + 1);
+        // Trees are consumed in input order, one barrier between consecutive trees (the next tree may touch
+        // the same columns; within a tree every leaf is a distinct column).  Software pipeline over steps of
+        // kRowThreads runs: the taxon loads and segment search of the next step are issued before the
+        // shared-memory update of the current one, and the loaded taxon is first used after the barrier.  A
+        // tree whose chain did not fit in kChain steps ends a pipelined run; it is continued round by round
+        // before the trees after it.
+        int first = 0;
+        while (first < batch) {
+            // trees [first, stop) are complete, except possibly the last one
+            const uint32_t open = tb.unfinished >> first;
+            const bool unfinished = open != 0;
+            const int stop = unfinished ? first + __ffs(open) : batch;
+            int e = first, u0 = 0, nl = 0, nr = 0;
+            auto counts = [&](int tree, int &l, int &r) {
+                l = tb.left_count[tree];
+                r = tb.right_count[tree];
+                return l + r;
+            };
+            while (e < stop && counts(e, nl, nr) == 0) ++e;
+            if (e < stop) {
+                Pending cur, nxt;
+                cur.len = nxt.len = 0;
+                if ((tid & ~31) < runs_of(nl) + runs_of(nr)) load_run(tb, e, tid, nl, nr, leaf_taxon, cur);
+                while (true) {
+                    // the step after (e, u0)
+                    int ne = e, nu0 = u0 + kRowThreads, nnl = nl, nnr = nr;
+                    if (nu0 >= runs_of(nl) + runs_of(nr)) {
+                        nu0 = 0;
+                        do {
+                            ++ne;
+                        } while (ne < stop && counts(ne, nnl, nnr) == 0);
+                    }
+                    const bool more = ne < stop;
+                    nxt.len = 0;
+                    if (more && nu0 + (tid & ~31) < runs_of(nnl) + runs_of(nnr))
+                        load_run(tb, ne, nu0 + tid, nnl, nnr, leaf_taxon, nxt);
+                    apply_run(tb, e, cur, col0, ncols, accW, accC);
+                    if (!more) break;
+                    if (ne != e) __syncthreads();
+                    cur = nxt;
+                    e = ne;
+                    u0 = nu0;
+                    nl = nnl;
+                    nr = nnr;
                 }
             }
-            if (!more) break;
-            if (next_e != cur_e) __syncthreads();  // tree order: the next tree may touch the same columns
-            cur = nxt;
-            cur_e = next_e;
-            advance(headers, batch, next_e, next_seg);
+            __syncthreads();
+            if (unfinished) {
+                const int eu = stop - 1;
+                while (tb.resume[eu][0] >= 0 || tb.resume[eu][1] >= 0) {
+                    __syncthreads();  // everybody has read resume[]
+                    if (tid < 2) walk_chain(tb, eu, tid, false, links);
+                    __syncthreads();
+                    const int l2 = tb.left_count[eu], r2 = tb.right_count[eu];
+                    for (int u = tid; (u & ~31) < runs_of(l2) + runs_of(r2); u += kRowThreads) {
+                        Pending cur;
+                        load_run(tb, eu, u, l2, r2, leaf_taxon, cur);
+                        apply_run(tb, eu, cur, col0, ncols, accW, accC);
+                    }
+                    __syncthreads();
+                }
+            }
+            first = stop;
         }
     }
     __syncthreads();
@@ -359,9 +551,9 @@ __global__ void pcg_sum_degree_parts(int n, int row0, int row1, int nchunks, con
 }
 
 template <typename CountT, bool kWriteC>
-int launch_rows(scs_ctx *ctx, int n, int row0, int nrows, int words, int cols_per_chunk, int nchunks, size_t smem, int64_t L,
-                const int64_t *leaf_offsets, const int32_t *leaf_taxon, const LcaEntry *st,
-                const int32_t *root_depth, const double *tree_weight,
+int launch_rows(scs_ctx *ctx, int n, int row0, int nrows, int words, int cols_per_chunk, int nchunks, size_t smem,
+                const int64_t *leaf_offsets, const int32_t *leaf_taxon, const LinkEntry *links,
+                const double *tree_weight,
                 const int32_t *leaf_tree, const int32_t *row_ptr, const int32_t *inv_sorted,
                 const int32_t *occ, double *W, int32_t *C, uint32_t *adj_bits, uint32_t *max_bits,
                 double *degree_part, int32_t *bad) {
@@ -369,7 +561,7 @@ int launch_rows(scs_ctx *ctx, int n, int row0, int nrows, int words, int cols_pe
     // always the same (maximal) opt-in size: contexts on other host threads launch this kernel concurrently
     bool &configured = ctx->rows_configured[(sizeof(CountT) == 2 ? 0 : 2) + (kWriteC ? 1 : 0)];
     if (!configured) {
-        const size_t optin = ctx->smem_optin > 8192 ? ctx->smem_optin - 4096 : 44 * 1024;
+        const size_t optin = ctx->smem_optin > 2 * kRowsStaticSmem ? ctx->smem_optin - kRowsStaticSmem : 32 * 1024;
         SCS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(optin)));
         configured = true;
     }
@@ -379,8 +571,8 @@ int launch_rows(scs_ctx *ctx, int n, int row0, int nrows, int words, int cols_pe
         const double out_bytes = 8.0 * nrows * n + (C ? 4.0 * nrows * n : 0.0) + 8.0 * nrows * words + 12.0 * nrows;
         profile_begin(ctx, PROFILE_PCG_ROWS, out_bytes, ctx->pending_units);
     }
-    kernel<<<grid, kRowThreads, smem, ctx->stream>>>(n, row0, words, cols_per_chunk, L, leaf_offsets, leaf_taxon, st,
-                                                     root_depth, tree_weight, leaf_tree, row_ptr,
+    kernel<<<grid, kRowThreads, smem, ctx->stream>>>(n, row0, words, cols_per_chunk, leaf_offsets, leaf_taxon, links,
+                                                     tree_weight, leaf_tree, row_ptr,
                                                      inv_sorted, occ, W, C, adj_bits, max_bits, degree_part, bad);
     if (n >= kProfileMinSize) profile_end(ctx);
     SCS_LAUNCHED(ctx, "pcg_rows_kernel");
@@ -438,21 +630,23 @@ int pcg_build(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offsets
             SCS_LAUNCHED(ctx, "pcg_sort_inverse");
         }
     }
-    // a tree has at most n leaves (distinct taxa), so ceil(log2(n)) doubling levels always suffice
-    int levels = 1;
-    while ((1 << levels) < n) ++levels;
-    LcaEntry *st;
-    if ((rc = reserve_as(ctx, SLOT_SPARSE, static_cast<size_t>(levels) * static_cast<size_t>(L > 0 ? L : 1), &st)))
-        return rc;
+    LinkEntry *links;
+    if ((rc = reserve_as(ctx, SLOT_LINKS, static_cast<size_t>(L > 0 ? L : 1), &links))) return rc;
     if (L > 0 && T > 0) {
-        pcg_sparse_table<<<T, 256, 0, ctx->stream>>>(L, levels, leaf_offsets, adj_depth, adj_val, st);
-        SCS_LAUNCHED(ctx, "pcg_sparse_table");
+        // block minima of a tree's tour: a tree has at most n leaves (distinct taxa; checked in the kernel)
+        const int nb1 = ceil_div(n, 32), nb2 = ceil_div(nb1, 32);
+        const size_t link_smem = sizeof(int32_t) * (static_cast<size_t>(nb1) + nb2 + 2);
+        if (link_smem > 48 * 1024)
+            SCS_CUDA(ctx, cudaFuncSetAttribute(pcg_tour_links, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               static_cast<int>(link_smem)));
+        pcg_tour_links<<<T, 256, link_smem, ctx->stream>>>(n, leaf_offsets, adj_depth, adj_val, root_depth, links);
+        SCS_LAUNCHED(ctx, "pcg_tour_links");
     }
 
     // column chunking: the whole row if it fits in shared memory, else equal chunks of 32-multiples
     const bool narrow = T < 65536;
     const size_t per_col = sizeof(double) + (narrow ? sizeof(uint16_t) : sizeof(int32_t));
-    const size_t budget = ctx->smem_optin > 8192 ? ctx->smem_optin - 4096 : 44 * 1024;
+    const size_t budget = ctx->smem_optin > 2 * kRowsStaticSmem ? ctx->smem_optin - kRowsStaticSmem : 32 * 1024;
     const int max_cols = static_cast<int>((budget / per_col) / 32 * 32);
     const int padded = words * 32;
     int nchunks = ceil_div(padded, max_cols);
@@ -462,9 +656,9 @@ int pcg_build(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offsets
     if ((rc = reserve_as(ctx, SLOT_DEGREE_PART, static_cast<size_t>(n) * nchunks, &degree_part))) return rc;
 
 #define SCS_ROWS(CT, WC)                                                                                      \
-    launch_rows<CT, WC>(ctx, n, row0, nrows, words, cols_per_chunk, nchunks, smem, L, leaf_offsets, leaf_taxon, st, \
-                        root_depth, tree_weight, leaf_tree, row_ptr, inv_sorted, occ, W, C, adj_bits, max_bits, \
-                        degree_part, scalars)
+    launch_rows<CT, WC>(ctx, n, row0, nrows, words, cols_per_chunk, nchunks, smem, leaf_offsets, leaf_taxon, links, \
+                        tree_weight, leaf_tree, row_ptr, inv_sorted, occ, W, C, adj_bits, max_bits, degree_part, \
+                        scalars)
     if (nrows == 0) return SCS_OK;
     if (narrow) rc = C ? SCS_ROWS(uint16_t, true) : SCS_ROWS(uint16_t, false);
     else rc = C ? SCS_ROWS(int32_t, true) : SCS_ROWS(int32_t, false);
