@@ -52,26 +52,33 @@ WORKLOADS = {
     "c2": (500, 50, "branch", 2000, False),
     "c3": (1000, 100, "branch", 3000, True),
     "c4": (10000, 1000, "depth", 4000, False),
-    # not a bench line (generation alone takes minutes): tools/run_workload.py runs it at 1/2/4/8 GPUs
+    # not a bench line: tools/run_workload.py runs it at 1/2/4/8 GPUs
     "c5": (50000, 5000, "branch", 5000, False),
 }
+# generated with one random stream per source tree by a pool of processes (synthetic.make_forest_arrays)
+POOLED_WORKLOADS = {"c5"}
 
 
 def describe(workload: str) -> str:
     n, t, weighting, seed, tw = WORKLOADS[workload]
     extra = ", tree weights U[0.5,2]" if tw else ""
+    streams = ", one random stream per source tree" if workload in POOLED_WORKLOADS else ""
     return (
         f"{workload}: {n} taxa x {t} source trees (birth-death model tree, SMIDGen-style subsets, 5% NNI noise), "
-        f"pcg_weighting={weighting}{extra}, seed {seed}"
+        f"pcg_weighting={weighting}{extra}, seed {seed}{streams}"
     )
 
 
 def make_workload(workload: str) -> dict:
-    from spectralclustersupertree_b200.synthetic import make_problem
+    from spectralclustersupertree_b200.synthetic import make_forest_arrays, make_problem
 
     n, t, weighting, seed, tw = WORKLOADS[workload]
-    prob = make_problem(n, t, weighting, seed, tree_weights=tw)
-    arrays = prob.forest_arrays()
+    if workload in POOLED_WORKLOADS:
+        world = max(1, int(os.environ.get("WORLD_SIZE", "1")))  # every rank generates the same trees
+        arrays = make_forest_arrays(n, t, weighting, seed, tree_weights=tw,
+                                    workers=max(1, min(32, (os.cpu_count() or 1) // world)))
+    else:
+        arrays = make_problem(n, t, weighting, seed, tree_weights=tw).forest_arrays()
     arrays["weighting"] = weighting
     return arrays
 

@@ -353,6 +353,44 @@ class Problem:
                 for s in self.sources]  # fmt: skip
 
 
+def _source_tree(index: _ModelIndex, clades: list[int], t: int, n: int, weighting: str, nni_fraction: float,
+                 rng: np.random.RandomState) -> Topology:
+    """Source tree ``t`` of the recipe, drawing from ``rng``."""
+    cap = math.ceil(0.25 * n)
+    if t == 0:
+        k = max(4, math.ceil(0.2 * n))
+        positions = rng.choice(n, size=min(k, n), replace=False)
+    else:
+        x = clades[rng.randint(len(clades))]
+        lo, hi = index.lo[x], index.hi[x]
+        inside = np.arange(lo, hi)
+        chosen = inside[rng.random_sample(len(inside)) < 0.5]
+        if len(chosen) > cap:
+            chosen = rng.choice(chosen, size=cap, replace=False)
+        if len(chosen) < 4:
+            chosen = rng.choice(inside, size=min(4, len(inside)), replace=False)
+        outside = n - (hi - lo)
+        if outside > 0:
+            o = rng.randint(outside)
+            o = o if o < lo else o + (hi - lo)
+            chosen = np.append(chosen, o)
+        positions = chosen
+    topo = index.induce(np.asarray(positions, dtype=np.int64), weighting == "branch")
+    tips = sum(1 for c in topo.children if not c)
+    _nni(topo, math.ceil(nni_fraction * tips), rng)
+    if weighting == "bootstrap":
+        for x in range(len(topo.children)):
+            if topo.children[x]:
+                topo.support[x] = float(rng.randint(50, 101))
+    return topo
+
+
+def _clades(index: _ModelIndex, model: Topology, n: int) -> list[int]:
+    min_clade = math.ceil(0.05 * n)
+    clades = [x for x in index.lo if index.hi[x] - index.lo[x] >= min_clade and x != model.root]
+    return clades or [model.root]
+
+
 def make_problem(
     n: int,
     num_trees: int,
@@ -366,41 +404,97 @@ def make_problem(
     rng = np.random.RandomState(seed)
     model = birth_death_tree(n, rng)
     index = _ModelIndex(model)
-    keep_lengths = weighting == "branch"
-    min_clade = math.ceil(0.05 * n)
-    cap = math.ceil(0.25 * n)
-    clades = [x for x in index.lo if index.hi[x] - index.lo[x] >= min_clade and x != model.root]
-    if not clades:
-        clades = [model.root]
-    sources: list[Topology] = []
-    for t in range(num_trees):
-        if t == 0:
-            k = max(4, math.ceil(0.2 * n))
-            positions = rng.choice(n, size=min(k, n), replace=False)
-        else:
-            x = clades[rng.randint(len(clades))]
-            lo, hi = index.lo[x], index.hi[x]
-            inside = np.arange(lo, hi)
-            chosen = inside[rng.random_sample(len(inside)) < 0.5]
-            if len(chosen) > cap:
-                chosen = rng.choice(chosen, size=cap, replace=False)
-            if len(chosen) < 4:
-                chosen = rng.choice(inside, size=min(4, len(inside)), replace=False)
-            outside = n - (hi - lo)
-            if outside > 0:
-                o = rng.randint(outside)
-                o = o if o < lo else o + (hi - lo)
-                chosen = np.append(chosen, o)
-            positions = chosen
-        topo = index.induce(np.asarray(positions, dtype=np.int64), keep_lengths)
-        tips = sum(1 for c in topo.children if not c)
-        _nni(topo, math.ceil(nni_fraction * tips), rng)
-        if weighting == "bootstrap":
-            for x in range(len(topo.children)):
-                if topo.children[x]:
-                    topo.support[x] = float(rng.randint(50, 101))
-        sources.append(topo)
+    clades = _clades(index, model, n)
+    sources = [_source_tree(index, clades, t, n, weighting, nni_fraction, rng) for t in range(num_trees)]
     weights = None
     if tree_weights:
         weights = [float(w) for w in rng.uniform(0.5, 2.0, size=num_trees)]
     return Problem(n=n, model=model, sources=sources, weights=weights, weighting=weighting, seed=seed)
+
+
+# ---- large workloads: per-tree random streams, trees generated and flattened by a pool of processes ----
+_POOL_STATE: dict = {}
+
+
+def _flat_chunk(trees: tuple[int, int]):
+    """Worker: source trees [t0, t1) as flat pre-order arrays; tips carry the model tip number."""
+    st = _POOL_STATE
+    parent: list[int] = []
+    tip: list[int] = []
+    length: list[float] = []
+    support: list[float] = []
+    sizes: list[int] = []
+    nan = float("nan")
+    keep_lengths = st["weighting"] == "branch"
+    keep_support = st["weighting"] == "bootstrap"
+    for t in range(*trees):
+        rng = np.random.RandomState([st["seed"], t + 1])
+        s = _source_tree(st["index"], st["clades"], t, st["n"], st["weighting"], st["nni_fraction"], rng)
+        base = len(parent)
+        stack = [(s.root, -1)]
+        while stack:
+            x, up = stack.pop()
+            k = len(parent) - base
+            parent.append(up)
+            kids = s.children[x]
+            tip.append(-1 if kids else int(s.tip_name[x][1:]))
+            ln = s.length[x] if keep_lengths else None
+            sp = s.support[x] if keep_support else None
+            length.append(nan if ln is None else float(ln))
+            support.append(nan if sp is None else float(sp))
+            stack.extend((c, k) for c in reversed(kids))
+        sizes.append(len(parent) - base)
+    return (np.asarray(sizes, dtype=np.int64), np.asarray(parent, dtype=np.int32), np.asarray(tip, dtype=np.int32),
+            np.asarray(length, dtype=np.float64), np.asarray(support, dtype=np.float64))  # fmt: skip
+
+
+def make_forest_arrays(
+    n: int,
+    num_trees: int,
+    weighting: str,
+    seed: int,
+    *,
+    tree_weights: bool = False,
+    nni_fraction: float = 0.05,
+    workers: int | None = None,
+) -> dict:
+    """Same recipe and output as ``make_problem(...).forest_arrays()``, for workloads too large to generate
+    on one core: the model tree comes from ``RandomState(seed)``, source tree ``t`` from its own stream
+    ``RandomState([seed, t + 1])``, so the trees can be made by a pool of forked processes and the result does
+    not depend on the number of workers.  (A different problem instance than ``make_problem`` with the same
+    seed, which draws everything from one stream.)"""
+    import multiprocessing as mp
+    import os
+
+    rng = np.random.RandomState(seed)
+    model = birth_death_tree(n, rng)
+    index = _ModelIndex(model)
+    _POOL_STATE.update(index=index, clades=_clades(index, model, n), n=n, weighting=weighting, seed=seed,
+                       nni_fraction=nni_fraction)  # fmt: skip
+    workers = max(1, workers or min(32, os.cpu_count() or 1))
+    step = max(1, min(64, num_trees // (4 * workers) or 1))
+    chunks = [(t0, min(num_trees, t0 + step)) for t0 in range(0, num_trees, step)]
+    if workers == 1:
+        parts = [_flat_chunk(c) for c in chunks]
+    else:
+        with mp.get_context("fork").Pool(workers) as pool:
+            parts = pool.map(_flat_chunk, chunks, chunksize=1)
+    _POOL_STATE.clear()
+    sizes = np.concatenate([p[0] for p in parts])
+    tip = np.concatenate([p[2] for p in parts])
+    found = np.unique(tip[tip >= 0])
+    names = sorted(f"t{i}" for i in found)
+    rank = np.full(n, -1, dtype=np.int32)
+    for i, name in enumerate(names):
+        rank[int(name[1:])] = i
+    taxon = np.where(tip >= 0, rank[np.maximum(tip, 0)], -1).astype(np.int32)
+    weights = rng.uniform(0.5, 2.0, size=num_trees) if tree_weights else np.ones(num_trees)
+    return {
+        "names": names,
+        "node_offsets": np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64),
+        "parent": np.concatenate([p[1] for p in parts]),
+        "length": np.concatenate([p[3] for p in parts]),
+        "support": np.concatenate([p[4] for p in parts]),
+        "taxon": taxon,
+        "weights": np.asarray(weights, dtype=np.float64),
+    }
