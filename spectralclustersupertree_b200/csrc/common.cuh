@@ -43,6 +43,9 @@ enum Slot : int {
     SLOT_INV_SORTED,
     SLOT_DEGREE_PART,
     SLOT_LINKS,
+    SLOT_BUCKET_COUNT,
+    SLOT_BUCKET_PTR,
+    SLOT_ENTRIES,
     // components / contraction
     SLOT_UF_PARENT,
     SLOT_LABEL,
@@ -120,6 +123,7 @@ struct scs_ctx {
     bool own_stream = false;
     int sm_count = 148;
     size_t smem_optin = 0;
+    size_t smem_per_sm = 0;
     int64_t launches = 0;
     std::string last_error;
     scs::DeviceBuffer slots[scs::SLOT_COUNT];
@@ -143,7 +147,7 @@ struct scs_ctx {
     bool small_configured = false;
     bool batch_configured = false;
     bool tail_configured = false;
-    bool rows_configured[4] = {false, false, false, false};
+    bool rows_configured[8] = {false, false, false, false, false, false, false, false};
     bool contract_configured = false;
     bool kmeans_configured = false;
     int small_limit = 64;  // nodes up to this size take the one-CTA path (0 disables it)

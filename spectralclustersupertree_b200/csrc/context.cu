@@ -329,6 +329,7 @@ int scs_ctx_create(int device, void *stream, scs_ctx **out) {
     }
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    ctx->smem_per_sm = prop.sharedMemPerMultiprocessor;
     if (stream) {
         ctx->stream = static_cast<cudaStream_t>(stream);
     } else {

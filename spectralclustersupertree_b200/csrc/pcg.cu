@@ -234,8 +234,57 @@ pcg_tour_links(int n, const int64_t *__restrict__ leaf_offsets, const int32_t *_
     }
 }
 
+// ---- buckets: every tree's leaves, grouped by the warp that owns their column ------------------------
+// Column c of a row lives in column chunk y = c / cols_per_chunk (one CTA each) and, inside the chunk, belongs to
+// warp (c - y * cols_per_chunk) % W of that CTA.  bucket (t, y * W + w) lists the leaves of tree t whose columns
+// that warp owns, as entries {tour position, accumulator slot}.  A warp that walks its own buckets tree by tree
+// touches columns nobody else touches: W is summed in tree input order without a single barrier between trees,
+// and a chunk CTA reads only its own share of every tree.
+struct BucketShape {
+    int cols_per_chunk, warps_log2, buckets;  // buckets = chunks * warps
+};
+
+__device__ __forceinline__ void bucket_of(const BucketShape &bs, int c, int &bucket, int &slot) {
+    const int y = c / bs.cols_per_chunk;
+    const int lc = c - y * bs.cols_per_chunk;
+    bucket = (y << bs.warps_log2) + (lc & ((1 << bs.warps_log2) - 1));
+    slot = lc >> bs.warps_log2;
+}
+
+__global__ void pcg_bucket_count(int n, int64_t L, BucketShape bs, const int32_t *__restrict__ leaf_taxon,
+                                 const int32_t *__restrict__ leaf_tree, int32_t *__restrict__ count) {
+    int64_t g = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (g >= L) return;
+    const int c = leaf_taxon[g];
+    if (c < 0 || c >= n) return;  // flagged by pcg_index_leaves
+    int bucket, slot;
+    bucket_of(bs, c, bucket, slot);
+    atomicAdd(&count[static_cast<size_t>(leaf_tree[g]) * bs.buckets + bucket], 1);
+}
+
+// Entries of a bucket are in arbitrary order: the leaves of a tree are distinct columns, so the order in which a
+// warp adds one tree's terms cannot be observed.
+template <typename EntryT>
+__global__ void pcg_bucket_fill(int n, int64_t L, BucketShape bs, const int64_t *__restrict__ leaf_offsets,
+                                const int32_t *__restrict__ leaf_taxon, const int32_t *__restrict__ leaf_tree,
+                                const int32_t *__restrict__ bucket_ptr, int32_t *__restrict__ cursor,
+                                EntryT *__restrict__ entries) {
+    int64_t g = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (g >= L) return;
+    const int c = leaf_taxon[g];
+    if (c < 0 || c >= n) return;
+    const int t = leaf_tree[g];
+    int bucket, slot;
+    bucket_of(bs, c, bucket, slot);
+    const size_t cell = static_cast<size_t>(t) * bs.buckets + bucket;
+    const int at = bucket_ptr[cell] + atomicAdd(&cursor[cell], 1);
+    const uint32_t pos = static_cast<uint32_t>(g - leaf_offsets[t]);
+    if (sizeof(EntryT) == 4) entries[at] = static_cast<EntryT>((pos << 16) | static_cast<uint32_t>(slot));
+    else entries[at] = static_cast<EntryT>((static_cast<unsigned long long>(pos) << 32) | static_cast<uint32_t>(slot));
+}
+
 // ---- the row kernel -----------------------------------------------------------------------
-constexpr int kTreeBatch = 32;  // (row, tree) incidences staged together
+constexpr int kTreeBatch = 32;  // (row, tree) incidences staged together: one per lane
 constexpr int kChain = 15;      // chain steps per side kept per tree; longer chains continue in further rounds
 constexpr int kSlots = 2 * kChain + 2;  // == 32: boundaries of one tree, ascending
 static_assert(kSlots == 32, "the segment search below is a 5-step binary search over 32 boundaries");
@@ -244,21 +293,22 @@ constexpr int32_t kFar = 1 << 30;
 struct TreeHeader {
     int64_t base;  // first leaf of the tree in the tour arrays
     double weight;
-    int leaves, position;
+    int leaves, position, tree, pad;
 };
 
-// What a row CTA knows about the trees of the current batch.  For tree e, a leaf q of the tree lies in
+// What a row CTA knows about the trees of the current batch.  For tree e, the leaf at tour position q lies in
 // segment idx iff bound[e][idx] < q <= bound[e][idx + 1]; the segment's pairs (a, leaf q) all have the same
-// LCA and get term[e][idx].  The middle segment (kChain, kChain + 1] is the part already handled (at first
-// the leaf of the row itself); left segments grow downwards from it, right segments upwards.
-struct TreeBatch {
+// LCA and get term[e][idx].  Segments [low, kChain) are to the left of the row's own leaf, (kChain, high) to its
+// right; the middle segment kChain is the part already handled (at first the leaf of the row itself); what
+// lies outside [low, high) is separated from the row's leaf by the root, or not reached yet.
+struct __align__(16) TreeBatch {
     TreeHeader header[kTreeBatch];
     double term[kTreeBatch][kSlots];
     int32_t bound[kTreeBatch][kSlots];
-    int32_t left_count[kTreeBatch], right_count[kTreeBatch];  // leaves in the left / right segments
-    int32_t low[kTreeBatch], high[kTreeBatch];               // first / last boundary in use
-    int32_t resume[kTreeBatch][2];                           // chain entry to continue from, or kNone
-    uint32_t unfinished;                                     // bit e: tree e has a chain to continue
+    int32_t pivot[kTreeBatch][kSlots / 4];      // bound[4j + 3]: the first level of the segment search
+    int32_t low[kTreeBatch], high[kTreeBatch];  // first / last boundary in use
+    int32_t resume[kTreeBatch][2];              // chain entry to continue from, or kNone
+    uint32_t unfinished;                        // bit e: tree e has a chain to continue
 };
 
 // Walk one side of the chain of tree e (thread-serial: one dependent 16-byte read per ancestor).
@@ -287,8 +337,8 @@ __device__ void walk_chain(TreeBatch &tb, int e, int side, bool first, const Lin
         }
         tb.high[e] = kChain + 1 + c;
         tb.resume[e][1] = i;
-        tb.right_count[e] = bound[kChain + 1 + c] - bound[kChain + 1];
         for (int idx = kChain + 2 + c; idx < kSlots; ++idx) bound[idx] = kFar;
+        for (int j = kSlots / 8; j < kSlots / 4; ++j) tb.pivot[e][j] = bound[4 * j + 3];
     } else {
         int i;
         if (first) {
@@ -298,7 +348,7 @@ __device__ void walk_chain(TreeBatch &tb, int e, int side, bool first, const Lin
             bound[kChain] = bound[tb.low[e]];
             i = tb.resume[e][0];
         }
-        while (i >= 0 && c < kChain) {
+        while (i >= 0 && c < kChain - 1) {  // boundary 0 stays a pad: the search below starts from it
             const LinkEntry r = lk[i];
             if (r.next_left == kRootLevel) { i = kNone; break; }
             term[kChain - 1 - c] = __dmul_rn(r.val, h.weight);
@@ -308,102 +358,89 @@ __device__ void walk_chain(TreeBatch &tb, int e, int side, bool first, const Lin
         }
         tb.low[e] = kChain - c;
         tb.resume[e][0] = i;
-        tb.left_count[e] = bound[kChain] - bound[kChain - c];
         for (int idx = kChain - c - 1; idx >= 0; --idx) bound[idx] = -kFar;
+        for (int j = 0; j < kSlots / 8; ++j) tb.pivot[e][j] = bound[4 * j + 3];
     }
 }
 
-// A thread visits runs of kRun consecutive leaves of one side of a tree: one segment search per run, then
-// the segment index only moves forward (consecutive leaves cross at most one boundary).  A step covers
-// kRowThreads runs of one tree.
-#ifndef SCS_RUN
-#define SCS_RUN 4
-#endif
-constexpr int kRun = SCS_RUN;
-
-struct Pending {
-    int taxon[kRun];  // taxa of the run's leaves (raw global loads: first used after the next barrier)
-    int q0, len, idx;  // first leaf, leaves in the run (0: nothing to do), segment of the first leaf
-};
-
-__device__ __forceinline__ int runs_of(int leaves) { return (leaves + kRun - 1) / kRun; }
-
-// Run u of tree e (left runs first, then right runs).  Warp-uniform precondition: (u & ~31) < runs.
-__device__ __forceinline__ void load_run(const TreeBatch &tb, int e, int u, int nl, int nr,
-                                         const int32_t *__restrict__ leaf_taxon, Pending &out) {
-    const int32_t *bound = tb.bound[e];
-    const int lruns = runs_of(nl);
-    const bool left = u < lruns;
-    const int r = left ? u : u - lruns;
-    const int first = (left ? bound[tb.low[e]] : bound[kChain + 1]) + 1;
-    out.q0 = first + r * kRun;
-    out.len = max(0, min(kRun, (left ? nl : nr) - r * kRun));
-    const int32_t *src = leaf_taxon + tb.header[e].base + out.q0;
-#pragma unroll
-    for (int j = 0; j < kRun; ++j) out.taxon[j] = j < out.len ? src[j] : -1;
-    int idx = 0;
-#pragma unroll
-    for (int step = kSlots / 2; step > 0; step >>= 1)
-        if (bound[idx + step] < out.q0) idx += step;
-    out.idx = idx;
+template <typename EntryT>
+__device__ __forceinline__ void unpack(EntryT en, int &pos, int &slot) {
+    if (sizeof(EntryT) == 4) {
+        pos = static_cast<int>(static_cast<uint32_t>(en) >> 16);
+        slot = static_cast<int>(static_cast<uint32_t>(en) & 0xffffu);
+    } else {
+        pos = static_cast<int>(static_cast<unsigned long long>(en) >> 32);
+        slot = static_cast<int>(static_cast<unsigned long long>(en) & 0xffffffffull);
+    }
 }
 
-template <typename CountT>
-__device__ __forceinline__ void apply_run(const TreeBatch &tb, int e, const Pending &p, int col0, int ncols,
-                                          double *accW, CountT *accC) {
-    if (__all_sync(0xffffffffu, p.len == 0)) return;
-    const int32_t *bound = tb.bound[e];
+// count += 1 in one shared-memory operation: 16-bit counters are added to as halves of their 32-bit word (a
+// counter never exceeds the number of trees, so no carry crosses into the upper half)
+__device__ __forceinline__ void bump(uint16_t *counts, int slot) {
+    atomicAdd(reinterpret_cast<unsigned int *>(counts) + (slot >> 1), 1u << ((slot & 1) << 4));
+}
+__device__ __forceinline__ void bump(int32_t *counts, int slot) { atomicAdd(counts + slot, 1); }
+
+// One warp, one tree: every entry of the warp's bucket gets its segment and, if the segment is live, its term.
+// Segment search over the tree's 32 ascending boundaries in two levels: 7 pivots (bound[3], bound[7], ...) held
+// in registers pick a block of four, one 16-byte shared load fetches the block (the whole warp reads one
+// 128-byte row: a single wavefront).
+template <typename CountT, typename EntryT>
+__device__ __forceinline__ void visit_bucket(const TreeBatch &tb, int e, int ptr, int end, int lane, int slot0,
+                                             const EntryT *__restrict__ entries, double *accW, CountT *accC) {
+    if (ptr >= end) return;
+    const int low = tb.low[e], high = tb.high[e];
+    if (low == kChain && high == kChain + 1) return;  // nothing but root-separated pairs
+    const int4 *bound4 = reinterpret_cast<const int4 *>(tb.bound[e]);
     const double *term = tb.term[e];
-    int idx = p.idx;
-    double t = term[idx];
-    int next_bound = bound[idx + 1];
-    int col[kRun];
-    double w[kRun];
-    // all loads of the run, then all stores: the leaves of a tree are distinct columns
-#pragma unroll
-    for (int j = 0; j < kRun; ++j) {
-        if (j < p.len && p.q0 + j > next_bound) {
-            ++idx;
-            t = term[idx];
-            next_bound = bound[idx + 1];
+    const int4 pa = *reinterpret_cast<const int4 *>(&tb.pivot[e][0]);
+    const int4 pb = *reinterpret_cast<const int4 *>(&tb.pivot[e][4]);
+    EntryT en = ptr + lane < end ? entries[ptr + lane] : EntryT(0);
+    for (int i = ptr; i < end; i += 32) {
+        const bool live = i + lane < end;
+        const EntryT cur = en;
+        if (i + 32 + lane < end) en = entries[i + 32 + lane];
+        int q, slot;
+        unpack(cur, q, slot);
+        slot += slot0;  // the warp's slots start at slot0
+        const int blk = (pa.x < q) + (pa.y < q) + (pa.z < q) + (pa.w < q) + (pb.x < q) + (pb.y < q) + (pb.z < q);
+        const int4 b = bound4[blk];
+        const int idx = 4 * blk - 1 + (b.x < q) + (b.y < q) + (b.z < q) + (b.w < q);  // bound[0] < q always
+        if (live && idx >= low && idx < high && idx != kChain) {
+            accW[slot] = __dadd_rn(accW[slot], term[idx]);
+            bump(accC, slot);
         }
-        const int c = p.taxon[j] - col0;
-        col[j] = (j < p.len && static_cast<unsigned>(c) < static_cast<unsigned>(ncols)) ? c : -1;
-        if (col[j] >= 0) w[j] = __dadd_rn(accW[col[j]], t);
     }
-#pragma unroll
-    for (int j = 0; j < kRun; ++j)
-        if (col[j] >= 0) accW[col[j]] = w[j];
-    CountT cnt[kRun];
-#pragma unroll
-    for (int j = 0; j < kRun; ++j)
-        if (col[j] >= 0) cnt[j] = accC[col[j]];
-#pragma unroll
-    for (int j = 0; j < kRun; ++j)
-        if (col[j] >= 0) accC[col[j]] = static_cast<CountT>(cnt[j] + 1);
 }
 
-template <typename CountT, bool kWriteC>
+// blockDim.x = 32 * W threads (W = 1 << bs.warps_log2); dynamic shared memory: W * stride accumulators.
+template <typename CountT, bool kWriteC, typename EntryT>
 __global__ void __launch_bounds__(kRowThreads, 2)
-pcg_rows_kernel(int n, int row0, int words_per_row, int cols_per_chunk,
-                const int64_t *__restrict__ leaf_offsets, const int32_t *__restrict__ leaf_taxon,
-                const LinkEntry *__restrict__ links, const double *__restrict__ tree_weight,
-                const int32_t *__restrict__ leaf_tree, const int32_t *__restrict__ row_ptr,
-                const int32_t *__restrict__ inv_sorted, const int32_t *__restrict__ occ,
+pcg_rows_kernel(int n, int row0, int words_per_row, BucketShape bs, int stride,
+                const int64_t *__restrict__ leaf_offsets, const LinkEntry *__restrict__ links,
+                const double *__restrict__ tree_weight, const int32_t *__restrict__ leaf_tree,
+                const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ inv_sorted,
+                const int32_t *__restrict__ occ, const int32_t *__restrict__ bucket_ptr,
+                const EntryT *__restrict__ entries,
                 double *__restrict__ W, int32_t *__restrict__ C, uint32_t *__restrict__ adj_bits,
                 uint32_t *__restrict__ max_bits, double *__restrict__ degree_part, int32_t *__restrict__ bad) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int nwarps = 1 << bs.warps_log2, nthreads = nwarps << 5;
+    const int slots_total = stride << bs.warps_log2;
     double *accW = reinterpret_cast<double *>(smem_raw);
-    CountT *accC = reinterpret_cast<CountT *>(accW + cols_per_chunk);
+    CountT *accC = reinterpret_cast<CountT *>(accW + slots_total);
     __shared__ TreeBatch tb;
     __shared__ double warp_sum[kWarps];
 
     const int a = row0 + blockIdx.x;  // W / C point at the row block: its first row is row0
+    const int cols_per_chunk = bs.cols_per_chunk;
     const int col0 = blockIdx.y * cols_per_chunk;
     const int ncols = min(cols_per_chunk, n - col0);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int my_bucket = (blockIdx.y << bs.warps_log2) + warp;
+    const int slot0 = warp * stride;  // the slots of this warp's columns start here
 
-    for (int c = tid; c < cols_per_chunk; c += kRowThreads) {
+    for (int c = tid; c < slots_total; c += nthreads) {
         accW[c] = 0.0;
         accC[c] = 0;
     }
@@ -426,75 +463,42 @@ pcg_rows_kernel(int n, int row0, int words_per_row, int cols_per_chunk,
                 h.leaves = 0;
             }
             h.position = static_cast<int>(g - base);
+            h.tree = t;
+            h.pad = 0;
             tb.header[tid] = h;
         }
         if (tid == 0) tb.unfinished = 0;
         __syncthreads();
-        if (tid < 2 * batch) {
-            walk_chain(tb, tid >> 1, tid & 1, true, links);
-            if (tb.resume[tid >> 1][tid & 1] >= 0) atomicOr(&tb.unfinished, 1u << (tid >> 1));
+        for (int w = tid; w < 2 * batch; w += nthreads) {
+            walk_chain(tb, w >> 1, w & 1, true, links);
+            if (tb.resume[w >> 1][w & 1] >= 0) atomicOr(&tb.unfinished, 1u << (w >> 1));
+        }
+        // lane e keeps where this warp's bucket of tree e starts and ends
+        int my_ptr = 0, my_end = 0;
+        if (lane < batch) {
+            const size_t cell = static_cast<size_t>(tb.header[lane].tree) * bs.buckets + my_bucket;
+            my_ptr = bucket_ptr[cell];
+            my_end = bucket_ptr[cell + 1];
+            if (tb.header[lane].leaves == 0) my_end = my_ptr;
         }
         __syncthreads();
-        // Trees are consumed in input order, one barrier between consecutive trees (the next tree may touch
-        // the same columns; within a tree every leaf is a distinct column).  Software pipeline over steps of
-        // kRowThreads runs: the taxon loads and segment search of the next step are issued before the
-        // shared-memory update of the current one, and the loaded taxon is first used after the barrier.  A
-        // tree whose chain did not fit in kChain steps ends a pipelined run; it is continued round by round
-        // before the trees after it.
+        // Every warp goes through the trees in input order on its own: no barrier between trees.  A tree whose
+        // chain did not fit in kChain steps is continued round by round, CTA-wide, before the trees after it.
         int first = 0;
         while (first < batch) {
-            // trees [first, stop) are complete, except possibly the last one
             const uint32_t open = tb.unfinished >> first;
-            const bool unfinished = open != 0;
-            const int stop = unfinished ? first + __ffs(open) : batch;
-            int e = first, u0 = 0, nl = 0, nr = 0;
-            auto counts = [&](int tree, int &l, int &r) {
-                l = tb.left_count[tree];
-                r = tb.right_count[tree];
-                return l + r;
-            };
-            while (e < stop && counts(e, nl, nr) == 0) ++e;
-            if (e < stop) {
-                Pending cur, nxt;
-                cur.len = nxt.len = 0;
-                if ((tid & ~31) < runs_of(nl) + runs_of(nr)) load_run(tb, e, tid, nl, nr, leaf_taxon, cur);
-                while (true) {
-                    // the step after (e, u0)
-                    int ne = e, nu0 = u0 + kRowThreads, nnl = nl, nnr = nr;
-                    if (nu0 >= runs_of(nl) + runs_of(nr)) {
-                        nu0 = 0;
-                        do {
-                            ++ne;
-                        } while (ne < stop && counts(ne, nnl, nnr) == 0);
-                    }
-                    const bool more = ne < stop;
-                    nxt.len = 0;
-                    if (more && nu0 + (tid & ~31) < runs_of(nnl) + runs_of(nnr))
-                        load_run(tb, ne, nu0 + tid, nnl, nnr, leaf_taxon, nxt);
-                    apply_run(tb, e, cur, col0, ncols, accW, accC);
-                    if (!more) break;
-                    if (ne != e) __syncthreads();
-                    cur = nxt;
-                    e = ne;
-                    u0 = nu0;
-                    nl = nnl;
-                    nr = nnr;
-                }
-            }
-            __syncthreads();
-            if (unfinished) {
+            const int stop = open != 0 ? first + __ffs(open) : batch;
+            for (int e = first; e < stop; ++e)
+                visit_bucket(tb, e, __shfl_sync(0xffffffffu, my_ptr, e), __shfl_sync(0xffffffffu, my_end, e), lane,
+                             slot0, entries, accW, accC);
+            if (open != 0) {
                 const int eu = stop - 1;
+                const int ptr = __shfl_sync(0xffffffffu, my_ptr, eu), end = __shfl_sync(0xffffffffu, my_end, eu);
                 while (tb.resume[eu][0] >= 0 || tb.resume[eu][1] >= 0) {
-                    __syncthreads();  // everybody has read resume[]
+                    __syncthreads();  // everybody has read resume[] and is done with the tree's segments
                     if (tid < 2) walk_chain(tb, eu, tid, false, links);
                     __syncthreads();
-                    const int l2 = tb.left_count[eu], r2 = tb.right_count[eu];
-                    for (int u = tid; (u & ~31) < runs_of(l2) + runs_of(r2); u += kRowThreads) {
-                        Pending cur;
-                        load_run(tb, eu, u, l2, r2, leaf_taxon, cur);
-                        apply_run(tb, eu, cur, col0, ncols, accW, accC);
-                    }
-                    __syncthreads();
+                    visit_bucket(tb, eu, ptr, end, lane, slot0, entries, accW, accC);
                 }
             }
             first = stop;
@@ -503,22 +507,21 @@ pcg_rows_kernel(int n, int row0, int words_per_row, int cols_per_chunk,
     __syncthreads();
 
     // ---- write the finished row --------------------------------------------------------------
+    const int wmask = nwarps - 1;
+    auto slot_of = [&](int c) { return (c & wmask) * stride + (c >> bs.warps_log2); };
     const int occ_a = occ[a];
     double *Wrow = W + static_cast<size_t>(blockIdx.x) * n + col0;
-    double partial = 0.0;
-    for (int c = tid; c < ncols; c += kRowThreads) {
-        const double x = accW[c];
-        Wrow[c] = x;
-        partial += x;
-        if (kWriteC) C[static_cast<size_t>(blockIdx.x) * n + col0 + c] = static_cast<int32_t>(accC[c]);
+    for (int c = tid; c < ncols; c += nthreads) {
+        Wrow[c] = accW[slot_of(c)];
+        if (kWriteC) C[static_cast<size_t>(blockIdx.x) * n + col0 + c] = static_cast<int32_t>(accC[slot_of(c)]);
     }
     const int word0 = col0 >> 5;
     const int nwords = (ncols + 31) >> 5;
-    for (int j = warp; j < nwords; j += kWarps) {
+    for (int j = warp; j < nwords; j += nwarps) {
         const int c = (j << 5) + lane;
         bool edge = false, top = false;
         if (c < ncols) {
-            const int cc = static_cast<int>(accC[c]);
+            const int cc = static_cast<int>(accC[slot_of(c)]);
             edge = cc > 0;
             if (edge && max_bits != nullptr) top = cc == max(occ_a, occ[col0 + c]);
         }
@@ -529,10 +532,15 @@ pcg_rows_kernel(int n, int row0, int words_per_row, int cols_per_chunk,
             if (max_bits != nullptr) max_bits[static_cast<size_t>(a) * words_per_row + word0 + j] = tb2;
         }
     }
-    // row sum in a fixed order: strided per-thread sums, shuffle tree, then warps in order
+    // row sum in a fixed order (the same for every CTA size): virtual thread v < kRowThreads sums columns
+    // v, v + kRowThreads, ...; shuffle tree per virtual warp; then the virtual warps in order
+    for (int vw = warp; vw < kWarps; vw += nwarps) {
+        double part = 0.0;
+        for (int c = (vw << 5) + lane; c < ncols; c += kRowThreads) part += accW[slot_of(c)];
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) partial += __shfl_down_sync(0xffffffffu, partial, off);
-    if (lane == 0) warp_sum[warp] = partial;
+        for (int off = 16; off > 0; off >>= 1) part += __shfl_down_sync(0xffffffffu, part, off);
+        if (lane == 0) warp_sum[vw] = part;
+    }
     __syncthreads();
     if (tid == 0) {
         double s = 0.0;
@@ -550,16 +558,16 @@ __global__ void pcg_sum_degree_parts(int n, int row0, int row1, int nchunks, con
     degree[a] = s;
 }
 
-template <typename CountT, bool kWriteC>
-int launch_rows(scs_ctx *ctx, int n, int row0, int nrows, int words, int cols_per_chunk, int nchunks, size_t smem,
-                const int64_t *leaf_offsets, const int32_t *leaf_taxon, const LinkEntry *links,
-                const double *tree_weight,
+template <typename CountT, bool kWriteC, typename EntryT>
+int launch_rows(scs_ctx *ctx, int n, int row0, int nrows, int words, BucketShape bs, int stride, int nchunks, size_t smem,
+                const int64_t *leaf_offsets, const LinkEntry *links, const double *tree_weight,
                 const int32_t *leaf_tree, const int32_t *row_ptr, const int32_t *inv_sorted,
-                const int32_t *occ, double *W, int32_t *C, uint32_t *adj_bits, uint32_t *max_bits,
-                double *degree_part, int32_t *bad) {
-    auto kernel = pcg_rows_kernel<CountT, kWriteC>;
+                const int32_t *occ, const int32_t *bucket_ptr, const void *entries, double *W, int32_t *C,
+                uint32_t *adj_bits, uint32_t *max_bits, double *degree_part, int32_t *bad) {
+    auto kernel = pcg_rows_kernel<CountT, kWriteC, EntryT>;
     // always the same (maximal) opt-in size: contexts on other host threads launch this kernel concurrently
-    bool &configured = ctx->rows_configured[(sizeof(CountT) == 2 ? 0 : 2) + (kWriteC ? 1 : 0)];
+    bool &configured =
+        ctx->rows_configured[(sizeof(CountT) == 2 ? 0 : 2) + (kWriteC ? 1 : 0) + (sizeof(EntryT) == 4 ? 0 : 4)];
     if (!configured) {
         const size_t optin = ctx->smem_optin > 2 * kRowsStaticSmem ? ctx->smem_optin - kRowsStaticSmem : 32 * 1024;
         SCS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(optin)));
@@ -571,9 +579,9 @@ int launch_rows(scs_ctx *ctx, int n, int row0, int nrows, int words, int cols_pe
         const double out_bytes = 8.0 * nrows * n + (C ? 4.0 * nrows * n : 0.0) + 8.0 * nrows * words + 12.0 * nrows;
         profile_begin(ctx, PROFILE_PCG_ROWS, out_bytes, ctx->pending_units);
     }
-    kernel<<<grid, kRowThreads, smem, ctx->stream>>>(n, row0, words, cols_per_chunk, leaf_offsets, leaf_taxon, links,
-                                                     tree_weight, leaf_tree, row_ptr,
-                                                     inv_sorted, occ, W, C, adj_bits, max_bits, degree_part, bad);
+    kernel<<<grid, 32 << bs.warps_log2, smem, ctx->stream>>>(
+        n, row0, words, bs, stride, leaf_offsets, links, tree_weight, leaf_tree, row_ptr, inv_sorted, occ, bucket_ptr,
+        static_cast<const EntryT *>(entries), W, C, adj_bits, max_bits, degree_part, bad);
     if (n >= kProfileMinSize) profile_end(ctx);
     SCS_LAUNCHED(ctx, "pcg_rows_kernel");
     return SCS_OK;
@@ -643,25 +651,66 @@ int pcg_build(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offsets
         SCS_LAUNCHED(ctx, "pcg_tour_links");
     }
 
-    // column chunking: the whole row if it fits in shared memory, else equal chunks of 32-multiples
+    // column chunking: the whole row if it fits in shared memory, else equal chunks of 32-multiples; inside a
+    // chunk the columns are dealt out to the CTA's warps (slot = warp * stride + column / warps)
     const bool narrow = T < 65536;
     const size_t per_col = sizeof(double) + (narrow ? sizeof(uint16_t) : sizeof(int32_t));
     const size_t budget = ctx->smem_optin > 2 * kRowsStaticSmem ? ctx->smem_optin - kRowsStaticSmem : 32 * 1024;
-    const int max_cols = static_cast<int>((budget / per_col) / 32 * 32);
+    BucketShape bs;
+    bs.warps_log2 = 4;
+    const int warps = 1 << bs.warps_log2;
+    // two CTAs per SM hide each other's latencies: a chunk gets at most half an SM's shared memory (a chunk CTA
+    // reads only its own share of every tree, so more chunks cost little)
+    const size_t row_static = sizeof(TreeBatch) + 256;  // + warp_sum, alignment
+    const size_t half_sm = ctx->smem_per_sm > 4 * kRowsStaticSmem ? ctx->smem_per_sm / 2 - 1024 - row_static : budget;
+    const size_t chunk_budget = half_sm < budget ? half_sm : budget;
+    // slots = warps * stride <= cols + 2 * warps (stride rounded up and made odd)
+    const int max_cols = static_cast<int>(((chunk_budget - 16) / per_col - 2 * warps) / 32 * 32);
     const int padded = words * 32;
     int nchunks = ceil_div(padded, max_cols);
-    int cols_per_chunk = ceil_div(ceil_div(padded, nchunks), 32) * 32;
-    nchunks = ceil_div(n, cols_per_chunk);
-    const size_t smem = static_cast<size_t>(cols_per_chunk) * per_col + 16;
+    bs.cols_per_chunk = ceil_div(ceil_div(padded, nchunks), 32) * 32;
+    nchunks = ceil_div(n, bs.cols_per_chunk);
+    bs.buckets = nchunks * warps;
+    const int stride = ceil_div(bs.cols_per_chunk, warps) | 1;  // odd: the write-out reads a column per lane
+    const size_t smem = static_cast<size_t>(stride) * warps * per_col + 16;
     if ((rc = reserve_as(ctx, SLOT_DEGREE_PART, static_cast<size_t>(n) * nchunks, &degree_part))) return rc;
-
-#define SCS_ROWS(CT, WC)                                                                                      \
-    launch_rows<CT, WC>(ctx, n, row0, nrows, words, cols_per_chunk, nchunks, smem, leaf_offsets, leaf_taxon, links, \
-                        tree_weight, leaf_tree, row_ptr, inv_sorted, occ, W, C, adj_bits, max_bits, degree_part, \
-                        scalars)
     if (nrows == 0) return SCS_OK;
-    if (narrow) rc = C ? SCS_ROWS(uint16_t, true) : SCS_ROWS(uint16_t, false);
-    else rc = C ? SCS_ROWS(int32_t, true) : SCS_ROWS(int32_t, false);
+
+    // buckets: count, scan, fill
+    const bool packed = n <= 65535;  // tour positions and slots fit 16 bits each
+    const size_t cells = static_cast<size_t>(T) * bs.buckets;
+    if (cells + 1 >= (1ull << 31)) return fail(ctx, SCS_ERR_INVALID, "pcg_build: too many tree buckets");
+    int32_t *bucket_count, *bucket_ptr;
+    void *entries;
+    if ((rc = reserve_as(ctx, SLOT_BUCKET_COUNT, cells + 1, &bucket_count))) return rc;
+    if ((rc = reserve_as(ctx, SLOT_BUCKET_PTR, cells + 2, &bucket_ptr))) return rc;
+    if ((rc = reserve(ctx, SLOT_ENTRIES, (static_cast<size_t>(L) + 1) * (packed ? 4 : 8), &entries))) return rc;
+    SCS_CUDA(ctx, cudaMemsetAsync(bucket_count, 0, sizeof(int32_t) * (cells + 1), ctx->stream));
+    if (L > 0) {
+        pcg_bucket_count<<<ceil_div(L, 256), 256, 0, ctx->stream>>>(n, L, bs, leaf_taxon, leaf_tree, bucket_count);
+        SCS_LAUNCHED(ctx, "pcg_bucket_count");
+    }
+    if ((rc = exclusive_scan(ctx, static_cast<int>(cells), bucket_count, bucket_ptr))) return rc;
+    SCS_CUDA(ctx, cudaMemsetAsync(bucket_count, 0, sizeof(int32_t) * (cells + 1), ctx->stream));
+    if (L > 0) {
+        if (packed)
+            pcg_bucket_fill<uint32_t><<<ceil_div(L, 256), 256, 0, ctx->stream>>>(
+                n, L, bs, leaf_offsets, leaf_taxon, leaf_tree, bucket_ptr, bucket_count, static_cast<uint32_t *>(entries));
+        else
+            pcg_bucket_fill<unsigned long long><<<ceil_div(L, 256), 256, 0, ctx->stream>>>(
+                n, L, bs, leaf_offsets, leaf_taxon, leaf_tree, bucket_ptr, bucket_count,
+                static_cast<unsigned long long *>(entries));
+        SCS_LAUNCHED(ctx, "pcg_bucket_fill");
+    }
+
+#define SCS_ROWS(CT, WC, ET)                                                                                        \
+    launch_rows<CT, WC, ET>(ctx, n, row0, nrows, words, bs, stride, nchunks, smem, leaf_offsets, links, tree_weight, \
+                            leaf_tree, row_ptr, inv_sorted, occ, bucket_ptr, entries, W, C, adj_bits, max_bits,     \
+                            degree_part, scalars)
+#define SCS_ROWS_E(CT, WC) (packed ? SCS_ROWS(CT, WC, uint32_t) : SCS_ROWS(CT, WC, unsigned long long))
+    if (narrow) rc = C ? SCS_ROWS_E(uint16_t, true) : SCS_ROWS_E(uint16_t, false);
+    else rc = C ? SCS_ROWS_E(int32_t, true) : SCS_ROWS_E(int32_t, false);
+#undef SCS_ROWS_E
 #undef SCS_ROWS
     if (rc) return rc;
     if (degree) {
