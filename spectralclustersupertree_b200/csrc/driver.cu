@@ -67,12 +67,16 @@ struct Stopwatch {
 struct Task {
     scs_forest *forest;
     bool owned;
-    int32_t slot;                // output node this task fills in
+    int32_t slot;                // output node this task fills in (node id: see Driver::add)
     std::vector<int32_t> taxa;   // taxa present in the forest, ascending (scs.py:708-725)
+    bool shared = false;         // cooperative build: every rank processes this node (row-sharded over the GPUs)
 };
 
 // What one split recursion node turns into (scs.py:136-171), computed off the critical path.
+enum ChildKind : int { CHILD_OWN = 0, CHILD_SHARED = 1, CHILD_DEALT_HERE = 2, CHILD_DEALT_AWAY = 3 };
+
 struct Child {
+    int kind = CHILD_OWN;          // cooperative build: who continues with this component
     std::vector<int32_t> star;     // <= 2 taxa: a tip or a star (scs.py:143-145) ...
     scs_forest *forest = nullptr;  // ... else the restricted forest of the component
     std::vector<int32_t> taxa;     // taxa present in that forest
@@ -110,34 +114,6 @@ struct Scratch {
     }
 };
 
-int32_t add_node(scs_supertree &out, int32_t parent, int32_t taxon) {
-    out.parent.push_back(parent);
-    out.taxon.push_back(taxon);
-    return static_cast<int32_t>(out.parent.size() - 1);
-}
-
-// ref: scs.py:728-746 + _connect_trees :390-408 -- one name stays a tip, more become a star
-void fill_star(scs_supertree &out, int32_t slot, const int32_t *taxa, int count) {
-    if (count == 1) {
-        out.taxon[slot] = taxa[0];
-        return;
-    }
-    for (int i = 0; i < count; ++i) add_node(out, slot, taxa[i]);
-}
-
-// topology-only copy of the single remaining tree (ref: scs.py:96-98)
-int fill_tree(scs_supertree &out, int32_t slot, const scs_forest *f) {
-    int64_t count = 0;
-    int rc = scs_forest_tree_info(f, 0, &count, nullptr, nullptr);
-    if (rc) return rc;
-    std::vector<int32_t> par(count), tax(count), where(count);
-    if ((rc = scs_forest_tree(f, 0, par.data(), nullptr, nullptr, tax.data()))) return rc;
-    where[0] = slot;
-    out.taxon[slot] = tax[0];
-    for (int64_t k = 1; k < count; ++k) where[k] = add_node(out, where[par[k]], tax[k]);
-    return SCS_OK;
-}
-
 class Driver {
   public:
     Driver(scs_ctx *ctx, int weighting, int contract_edges, uint64_t seed, bool record, int rank, int world,
@@ -150,17 +126,32 @@ class Driver {
         scratch_.resize(static_cast<size_t>(std::max(scs_host_threads(), kMaxWorkers)));
         for (Scratch &sc : scratch_) sc.reset(num_taxa_);
         std::vector<Task> wave, next;
-        const int32_t root_slot = add_node(out_, -1, -1);
+        // While all ranks still walk the same frontier, nodes large enough are shared out over the GPUs
+        // (shard.cu).  Cooperative build (exchange windows connected): see the comment at stays_shared().
+        const ShardState &sh = ctx_->shard;
+        cooperative_ = world_ > 1 && sh.connected && sh.world == world_ && sh.rank == rank_;
+        ctx_->shard.engaged = cooperative_;
+        const int32_t root_slot = add(-1, -1, cooperative_);
         wave.push_back(Task{const_cast<scs_forest *>(root), false, root_slot, {}});
         scratch_[0].present_taxa(root, wave[0].taxa);
+        if (cooperative_) {
+            load_.assign(static_cast<size_t>(world_), 0.0);
+            const int n_root = static_cast<int>(wave[0].taxa.size());
+            wave[0].shared = stays_shared(n_root);
+            if (!wave[0].shared && deal(n_root) != rank_) wave.clear();  // a small job: one rank does it all
+        }
         int rc = SCS_OK;
-        // While all ranks still walk the same frontier, nodes large enough are shared out over the GPUs
-        // (shard.cu); once the frontier is dealt out the ranks work alone.
-        const ShardState &sh = ctx_->shard;
-        const bool cooperative = world_ > 1 && sh.connected && sh.world == world_ && sh.rank == rank_;
-        ctx_->shard.engaged = cooperative;
-        while (!wave.empty() && rc == SCS_OK) {
-            if (world_ > 1 && !partitioned_ && should_partition(wave)) partition(wave);
+        bool shared_phase = cooperative_;
+        while (rc == SCS_OK) {
+            if (wave.empty()) {
+                if (!shared_phase) break;
+                // the shared frontier is exhausted: from here on this rank works through its own backlog alone
+                shared_phase = false;
+                ctx_->shard.engaged = false;
+                wave.swap(backlog_);
+                if (wave.empty()) break;
+            }
+            if (world_ > 1 && !cooperative_ && !partitioned_ && should_partition(wave)) partition(wave);
             if (wave.empty()) break;
             out_.waves += 1;
             int32_t max_n = 0;
@@ -188,7 +179,11 @@ class Driver {
         }
         for (Task &t : wave)  // only non-empty after an error: the sub-problems that were never started
             if (t.owned) scs_forest_destroy(t.forest);
+        for (Task &t : backlog_)
+            if (t.owned) scs_forest_destroy(t.forest);
+        backlog_.clear();
         ctx_->shard.engaged = false;
+        if (rc == SCS_OK && cooperative_) finish_cooperative();
         return rc;
     }
 
@@ -200,6 +195,83 @@ class Driver {
     // until the frontier is wide enough; then the frontier is dealt out (largest estimated cost first,
     // to the least loaded rank) and each rank finishes only its own sub-problems.  The caller
     // concatenates the ranks' outputs past the shared prefix (no collective on the data path).
+    // ---- output nodes ------------------------------------------------------------------------------------
+    // Node ids: id >= 0 is a node of this rank's own list (out_.parent / out_.taxon); id <= -2 is node -2 - id of
+    // the shared list, which only exists in a cooperative build and is identical on every rank (except for a
+    // taxon its owner writes into a dealt slot).  -1 is "no parent".
+    int32_t add(int32_t parent, int32_t taxon, bool shared) {
+        if (shared) {
+            sh_parent_.push_back(parent);
+            sh_taxon_.push_back(taxon);
+            return -2 - static_cast<int32_t>(sh_parent_.size() - 1);
+        }
+        out_.parent.push_back(parent);
+        out_.taxon.push_back(taxon);
+        return static_cast<int32_t>(out_.parent.size() - 1);
+    }
+    void set_taxon(int32_t id, int32_t taxon) {
+        if (id >= 0) out_.taxon[id] = taxon;
+        else sh_taxon_[-2 - id] = taxon;
+    }
+
+    // ref: scs.py:728-746 + _connect_trees :390-408 -- one name stays a tip, more become a star
+    void fill_star(int32_t slot, const int32_t *taxa, int count, bool shared) {
+        if (count == 1) {
+            set_taxon(slot, taxa[0]);
+            return;
+        }
+        for (int i = 0; i < count; ++i) add(slot, taxa[i], shared);
+    }
+
+    // topology-only copy of the single remaining tree (ref: scs.py:96-98)
+    int fill_tree(int32_t slot, const scs_forest *f, bool shared) {
+        int64_t count = 0;
+        int rc = scs_forest_tree_info(f, 0, &count, nullptr, nullptr);
+        if (rc) return rc;
+        std::vector<int32_t> par(count), tax(count), where(count);
+        if ((rc = scs_forest_tree(f, 0, par.data(), nullptr, nullptr, tax.data()))) return rc;
+        where[0] = slot;
+        set_taxon(slot, tax[0]);
+        for (int64_t k = 1; k < count; ++k) where[k] = add(where[par[k]], tax[k], shared);
+        return SCS_OK;
+    }
+
+    // ---- cooperative build (exchange windows connected) -----------------------------------------------------
+    // A component of at least shard.min_n taxa stays SHARED: every rank keeps its forest and the node is
+    // row-sharded over the GPUs.  A smaller component is DEALT at once, with everything below it, to the
+    // rank with the least estimated work so far (every rank takes the same decision from the same partition,
+    // nobody talks); only its owner restricts the source trees to it.  Ranks first walk the shared frontier in
+    // lock-step, wave by wave, putting what is dealt to them on a backlog, and then work through the backlog
+    // alone.  Shared nodes go to a list that is identical on every rank and becomes the shared prefix of the
+    // output; the caller joins the ranks' outputs as in the non-cooperative build.
+    bool stays_shared(int size) const { return cooperative_ && size >= ctx_->shard.min_n; }
+    int deal(int size) {
+        const double n = static_cast<double>(size);
+        const int r = static_cast<int>(std::min_element(load_.begin(), load_.end()) - load_.begin());
+        load_[r] += n + n * n / 2.0e5;  // small nodes cost per node (latency), large ones per leaf pair
+        return r;
+    }
+    void finish_cooperative() {
+        const int32_t S = static_cast<int32_t>(sh_parent_.size());
+        auto final_index = [S](int32_t id) { return id >= 0 ? S + id : (id == -1 ? -1 : -2 - id); };
+        std::vector<int32_t> parent(sh_parent_.size() + out_.parent.size()), taxon(parent.size());
+        for (int32_t i = 0; i < S; ++i) {
+            parent[i] = final_index(sh_parent_[i]);
+            taxon[i] = sh_taxon_[i];
+        }
+        for (size_t j = 0; j < out_.parent.size(); ++j) {
+            parent[S + j] = final_index(out_.parent[j]);
+            taxon[S + j] = out_.taxon[j];
+        }
+        out_.parent.swap(parent);
+        out_.taxon.swap(taxon);
+        out_.shared_prefix = S;
+        out_.shared_records = static_cast<int64_t>(sh_records_.size());
+        sh_records_.insert(sh_records_.end(), std::make_move_iterator(out_.records.begin()),
+                           std::make_move_iterator(out_.records.end()));
+        out_.records.swap(sh_records_);
+    }
+
     static double task_cost(const Task &t) {
         const double n = static_cast<double>(t.taxa.size());
         return static_cast<double>(scs_forest_pair_visits(t.forest)) + 64.0 * n * n + 2.0e4;
@@ -251,12 +323,12 @@ class Driver {
             const int T = scs_forest_num_trees(task.forest);
             if (T == 0) return fail(ctx_, SCS_ERR_EMPTY, "a component is covered by no source tree (scs.py:63-65)");
             if (T == 1) {
-                if ((rc = fill_tree(out_, task.slot, task.forest))) return rc;
+                if ((rc = fill_tree(task.slot, task.forest, task.shared))) return rc;
                 continue;
             }
             const int n = static_cast<int>(task.taxa.size());
             if (n <= 2) {
-                fill_star(out_, task.slot, task.taxa.data(), n);
+                fill_star(task.slot, task.taxa.data(), n, task.shared);
                 continue;
             }
             if (n <= ctx_->small_limit) {
@@ -478,6 +550,13 @@ class Driver {
                     for (int i = 0; i < size; ++i) owner_[comp[i]] = -1;
                     continue;
                 }
+                if (task.shared) {
+                    child.kind = stays_shared(size) ? CHILD_SHARED : (deal(size) == rank_ ? CHILD_DEALT_HERE : CHILD_DEALT_AWAY);
+                    if (child.kind == CHILD_DEALT_AWAY) {  // its owner restricts the trees to it
+                        for (int i = 0; i < size; ++i) owner_[comp[i]] = -1;
+                        continue;
+                    }
+                }
                 const int32_t job = static_cast<int32_t>(jobs.size());
                 for (int i = 0; i < size; ++i) owner_[comp[i]] = job;
                 scs_induce_job spec;
@@ -507,23 +586,29 @@ class Driver {
 
     // ref: scs.py:139-174 -- attach the children to the output tree and queue the sub-problems
     void emit(Task &task, SplitResult &res, std::vector<Task> &next) {
-        if (!partitioned_) out_.shared_records += 1;
+        if (!partitioned_ && !cooperative_) out_.shared_records += 1;
         if (record_) {
             scs_supertree::Record rec;
             rec.taxa = task.taxa;
             rec.part = res.part;
             rec.stats = res.stats;
-            out_.records.push_back(std::move(rec));
+            (task.shared ? sh_records_ : out_.records).push_back(std::move(rec));
         }
         for (Child &child : res.children) {
-            const int32_t slot = add_node(out_, task.slot, -1);
+            // the children of a shared node are shared nodes: every rank creates them, in the same order
+            const int32_t slot = add(task.slot, -1, task.shared);
+            if (child.kind == CHILD_DEALT_AWAY) continue;
             if (!child.forest) {
-                fill_star(out_, slot, child.star.data(), static_cast<int>(child.star.size()));
+                fill_star(slot, child.star.data(), static_cast<int>(child.star.size()), task.shared);
                 continue;
             }
-            next.push_back(Task{child.forest, true, slot, std::move(child.taxa)});
+            const bool stays = child.kind == CHILD_SHARED;
+            (child.kind == CHILD_DEALT_HERE ? backlog_ : next)
+                .push_back(Task{child.forest, true, slot, std::move(child.taxa), stays});
             child.forest = nullptr;
-            for (int32_t x : child.missing) add_node(out_, task.slot, x);
+            // taxa in no restricted tree (scs.py:168-171): known to whoever restricted, i.e. to every rank only
+            // if the child stays shared
+            for (int32_t x : child.missing) add(task.slot, x, task.shared && stays);
         }
     }
 
@@ -533,6 +618,11 @@ class Driver {
     bool record_;
     int rank_ = 0, world_ = 1;
     bool partitioned_ = false;
+    bool cooperative_ = false;
+    std::vector<double> load_;                         // cooperative build: estimated work dealt to each rank
+    std::vector<Task> backlog_;                        // ... and the sub-problems dealt to this rank
+    std::vector<int32_t> sh_parent_, sh_taxon_;        // ... the shared node list
+    std::vector<scs_supertree::Record> sh_records_;    // ... records of the shared nodes
     const bool trace_ = std::getenv("SCS_DRIVER_TRACE") != nullptr;
     double trace_induce_ = 0.0, trace_present_ = 0.0;  // thread-seconds (summed over host threads)
     scs_supertree &out_;

@@ -204,3 +204,73 @@ def test_large_graph_properties(engine):
     W, C, occ = scs_oracle.pcg_dense_c(trees, [1.0] * len(trees), "depth", tid)
     assert np.array_equal(a["W"], W)
     assert np.array_equal(unpack_bits(a["adj_bits"], len(names)), C > 0)
+
+
+def _caterpillar(names, rng, lengths=True):
+    """A maximally deep tree over ``names`` (every internal node has one leaf child), leaves in random order."""
+    order = list(rng.permutation(names))
+    fmt = (lambda: f":{rng.uniform(0.01, 3.0):.6f}") if lengths else (lambda: "")
+    s = f"({order[0]}{fmt()},{order[1]}{fmt()})"
+    for x in order[2:]:
+        s = f"({s}{fmt()},{x}{fmt()})" if rng.rand() < 0.5 else f"({x}{fmt()},{s}{fmt()})"
+    return s + ";"
+
+
+def _bushy(names, rng, lengths=True):
+    """Random tree with polytomies over ``names``."""
+    fmt = (lambda: f":{rng.uniform(0.01, 3.0):.6f}") if lengths else (lambda: "")
+    items = [f"{x}{fmt()}" for x in rng.permutation(names)]
+    while len(items) > 1:
+        k = min(len(items), int(rng.choice([2, 2, 2, 3, 5])))
+        picked = [items.pop(int(rng.randint(len(items)))) for _ in range(k)]
+        inner = "(" + ",".join(picked) + ")"
+        items.append(inner + (fmt() if len(items) > 0 else ""))
+    return items[0].rsplit(")", 1)[0] + ");"
+
+
+@pytest.mark.parametrize("weighting", ["branch", "depth", "one"])
+def test_pcg_deep_trees_bit_exact(engine, weighting):
+    """Leaves with far more ancestors than one round of the row kernel's chain walk holds (15 a side), on
+    either side of the leaf, together with polytomies: the continuation rounds must visit every pair once,
+    in tree order."""
+    rng = np.random.RandomState(77)
+    names = [f"x{i:03d}" for i in range(140)]
+    lines, weights = [], []
+    for t in range(24):
+        sub = list(rng.choice(names, size=int(rng.randint(3, 120)), replace=False))
+        make = _caterpillar if t % 3 else _bushy
+        lines.append(make(sub, rng, lengths=weighting == "branch"))
+        weights.append(float(rng.uniform(0.5, 2.0)))
+    trees = parse(lines)
+    tid = {x: i for i, x in enumerate(names)}
+    W, C, occ = scs_oracle.pcg_dense_c(trees, weights, weighting, tid)
+    out = engine.pcg_build(flatten_trees(trees, weights, weighting, tid))
+    assert np.array_equal(out["W"], W)
+    assert np.array_equal(out["C"], C)
+    assert np.array_equal(out["occ"], occ)
+    assert np.array_equal(unpack_bits(out["adj_bits"], len(names)), C > 0)
+
+
+def test_pcg_rows_in_column_chunks_bit_exact(engine):
+    """More taxa than one CTA's shared memory holds columns for (10 080 at two CTAs per SM): every row is built
+    by several chunk CTAs, each reading only its own buckets of every tree."""
+    rng = np.random.RandomState(5)
+    n = 10500
+    names = [f"x{i:05d}" for i in range(n)]
+    lines, weights = [], []
+    for t in range(16):
+        sub = list(rng.choice(names, size=int(rng.randint(50, 700)), replace=False))
+        lines.append((_bushy if t % 2 else _caterpillar)(sub, rng))
+        weights.append(float(rng.uniform(0.5, 2.0)))
+    # one tree that covers both ends of the taxon range, so that pairs across chunks exist
+    lines.append(_bushy(names[:40] + names[-40:], rng))
+    weights.append(1.25)
+    trees = parse(lines)
+    tid = {x: i for i, x in enumerate(names)}
+    W, C, occ = scs_oracle.pcg_dense_c(trees, weights, "branch", tid)
+    out = engine.pcg_build(flatten_trees(trees, weights, "branch", tid), want_counts=False)
+    assert np.array_equal(out["W"], W)
+    assert np.array_equal(out["occ"], occ)
+    assert np.array_equal(unpack_bits(out["adj_bits"], n), C > 0)
+    top = np.maximum(occ[:, None], occ[None, :])
+    assert np.array_equal(unpack_bits(out["max_bits"], n), (C > 0) & (C == top))
