@@ -42,9 +42,9 @@ if str(ROOT) not in sys.path:
 
 METRIC = "construct_supertree wall-time at 10k taxa/1k trees"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of matvec_row_per_cta at m = 8765, from the
-# round-1 `ncu --set full` capture (profiles/r01_ncu_full_matvec_raw.csv); algorithmic bytes 614.8 MB
+# round-1 `ncu --set full` capture (profiles/r01_ncu_full_matvec_final_raw.csv); algorithmic bytes 614.8 MB
 NCU_MATVEC_TRAFFIC = {"bytes_per_launch": 618.2e6, "algorithmic_bytes": 614.8e6, "m": 8765,
-                      "source": "profiles/r01_ncu_full_matvec_raw.csv"}
+                      "source": "profiles/r01_ncu_full_matvec_final_raw.csv"}
 
 # name -> (taxa, trees, weighting, seed, tree weights)   (BASELINE.json configs; seed = 1000 * index)
 WORKLOADS = {
