@@ -240,9 +240,10 @@ def reference_line(args, arrays: dict) -> dict:
     """``--impl reference``: the CPU oracle port, each step = the bounded sample."""
     times = []
     detail = {}
-    for i in range(args.warmup + args.steps):
+    warmup = min(args.warmup, 1)  # a 30-second CPU sample needs no more than one untimed pass
+    for i in range(warmup + args.steps):
         detail = oracle_top_node(arrays)
-        if i >= args.warmup:
+        if i >= warmup:
             times.append(detail["seconds"])
     sample_s = statistics.mean(times)
     ratio = workload_ratio(args.workload)
@@ -511,7 +512,11 @@ def gpu_line(args, arrays: dict) -> dict:
             "avg_launch_us": 1e3 * matvec["ms"] / matvec["launches"],
             "bytes_per_launch": matvec["bytes"] / matvec["launches"],
             "share_of_step": matvec["ms"] / sum(dev_ms),
-            "traffic": NCU_MATVEC_TRAFFIC,
+            # DRAM bytes per launch: the ncu capture's traffic / algorithmic ratio (m = 8765 launch) applied to
+            # this run's average launch
+            "traffic": matvec["bytes"] / matvec["launches"] * NCU_MATVEC_TRAFFIC["bytes_per_launch"]
+            / NCU_MATVEC_TRAFFIC["algorithmic_bytes"],
+            "traffic_detail": NCU_MATVEC_TRAFFIC,
         })  # fmt: skip
     roofline_rows = None
     if rows["launches"] and rows["ms"] > 0:

@@ -199,6 +199,16 @@ int scs_forest_create(int T, const int64_t *node_offsets, const int32_t *parent,
                       const double *support, const int32_t *taxon, const double *tree_weight,
                       int num_taxa, scs_forest **out);
 int scs_forest_destroy(scs_forest *f);
+/* Newick text (one tree per line, as load_trees reads it: /root/reference/src/sc_supertree/load.py:21-22)
+ * straight into a forest, without node objects.  Label rules are those of cogent3.make_tree that the
+ * reference's tests rely on: ':x' is a branch length, a numeric label on an internal node is its support
+ * (tests/test_spectral_cluster_supertree.py:186-187, 217-219); every tree gets weight 1.  *names receives the
+ * sorted tip names (global taxon id = position), each terminated by a NUL byte, *names_bytes their total
+ * size; release it with scs_free.  SCS_ERR_INPUT on a syntax error (scs_newick_last_error: "line N: ..."). */
+int scs_forest_parse_newick(const char *text, size_t bytes, scs_forest **out, char **names, size_t *names_bytes,
+                            int *num_taxa);
+const char *scs_newick_last_error(void);
+void scs_free(void *ptr);
 int scs_forest_num_trees(const scs_forest *f);
 int64_t scs_forest_num_nodes(const scs_forest *f);
 int64_t scs_forest_num_leaves(const scs_forest *f);

@@ -19,7 +19,7 @@ CSRC = PKG / "csrc"
 INCLUDE = PKG.parent / "include"
 LIB = PKG / "libscs_b200.so"
 
-SOURCES = ["context.cu", "pcg.cu", "components.cu", "contract.cu", "spectral.cu", "small.cu", "shard.cu", "driver.cu", "forest.cpp"]
+SOURCES = ["context.cu", "pcg.cu", "components.cu", "contract.cu", "spectral.cu", "small.cu", "shard.cu", "driver.cu", "forest.cpp", "newick.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

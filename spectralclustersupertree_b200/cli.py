@@ -7,8 +7,8 @@ from typing import Literal
 import click
 
 from . import __version__
-from .load import load_trees
-from .scs import construct_supertree
+from .load import load_forest
+from .scs import supertree_of_forest
 
 
 @click.command(no_args_is_help=True)
@@ -36,10 +36,14 @@ def scs(
     disable_contraction: bool,
 ) -> None:
     """Run spectral cluster supertree over the given set of source trees."""
-    source_trees = load_trees(in_file)
-    supertree = construct_supertree(
-        source_trees,
-        pcg_weighting=pcg_weighting.lower(),
+    # load_trees + construct_supertree (ref: cli.py:33-38) without the detour over node objects
+    forest = load_forest(in_file)
+    if forest.num_trees == 0:  # ref: scs.py:63-65
+        msg = "There must be at least one tree to make a supertree."
+        raise ValueError(msg)
+    supertree = supertree_of_forest(
+        forest,
+        pcg_weighting.lower(),
         contract_edges=not disable_contraction,
     )
     supertree.write(out_file)

@@ -525,6 +525,29 @@ class Forest:
             offsets.append(len(parent))
         return cls.from_arrays(offsets, parent, length, support, taxon, list(weights), names)
 
+    @classmethod
+    def from_newick(cls, text: bytes | str) -> "Forest":
+        """Line-separated Newick text straight into the flat store (``scs_forest_parse_newick``): no node
+        objects.  Raises ``NewickError`` on a syntax error, like ``make_tree``."""
+        from .tree import NewickError
+
+        lib = _lib.load()
+        data = text.encode("utf-8") if isinstance(text, str) else bytes(text)
+        handle, names_ptr = ctypes.c_void_p(), ctypes.c_void_p()
+        names_bytes, num_taxa = ctypes.c_size_t(), ctypes.c_int()
+        status = lib.scs_forest_parse_newick(data, len(data), ctypes.byref(handle), ctypes.byref(names_ptr),
+                                             ctypes.byref(names_bytes), ctypes.byref(num_taxa))  # fmt: skip
+        if status == _lib.SCS_ERR_INPUT:
+            raise NewickError(lib.scs_newick_last_error().decode())
+        if status != _lib.SCS_OK:
+            raise ScsError(status, "scs_forest_parse_newick")
+        try:
+            raw = ctypes.string_at(names_ptr, names_bytes.value)
+        finally:
+            lib.scs_free(names_ptr)
+        names = [part.decode("utf-8") for part in raw.split(b"\0")[: num_taxa.value]]
+        return cls(handle, names)
+
     def close(self) -> None:
         if getattr(self, "_handle", None):
             self._lib.scs_forest_destroy(self._handle)

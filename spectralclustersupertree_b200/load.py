@@ -24,3 +24,13 @@ def load_trees(source_tree_file: str | os.PathLike) -> list[PhyloNode]:
     """
     with Path(source_tree_file).open() as f:
         return [make_tree(line.strip()) for line in f]
+
+
+def load_forest(source_tree_file: str | os.PathLike):
+    """The same file as ``load_trees`` reads, parsed natively into the flat source-tree store
+    (``engine.Forest``, ``scs_forest_parse_newick``) without building a node object per tree node: what the
+    ``scs`` command uses, since at 10 000 taxa x 1 000 trees the node objects cost more than the supertree.
+    Feed the result to ``scs.supertree_of_forest``."""
+    from .engine import Forest
+
+    return Forest.from_newick(Path(source_tree_file).read_bytes())

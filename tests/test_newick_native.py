@@ -1,0 +1,110 @@
+"""CPU: ``scs_forest_parse_newick`` (Newick text -> flat forest, no node objects) against the Python path
+``load_trees`` + ``Forest.from_trees`` on the reference's fixtures, its inline known-answer cases and syntax
+corner cases.  Host code only: no GPU is touched."""
+
+from __future__ import annotations
+
+import json
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN, kat_cases
+from spectralclustersupertree_b200.engine import Forest
+from spectralclustersupertree_b200.load import load_forest, load_trees
+from spectralclustersupertree_b200.tree import NewickError, make_tree
+
+
+def assert_same_forest(native: Forest, lines: list[str]) -> None:
+    trees = [make_tree(s.strip()) for s in lines]
+    names = sorted({x for t in trees for x in t.get_tip_names()})
+    python = Forest.from_trees(trees, [1.0] * len(trees), names)
+    try:
+        assert list(native.names) == names
+        assert native.num_trees == python.num_trees == len(lines)
+        for t in range(len(lines)):
+            for a, b in zip(native.tree_arrays(t), python.tree_arrays(t), strict=True):
+                assert np.array_equal(a, b, equal_nan=True), (t, lines[t][:80])
+        assert np.array_equal(native.weights(), python.weights())
+    finally:
+        python.close()
+
+
+@pytest.mark.parametrize("name", ["dcm", "dcm_iq", "supertriplets"])
+def test_fixture_files_parse_to_the_same_forest(name):
+    lines = json.loads((GOLDEN / f"fixture_{name}.json").read_text())["trees"]
+    native = Forest.from_newick("\n".join(lines) + "\n")
+    try:
+        assert_same_forest(native, lines)
+    finally:
+        native.close()
+
+
+def test_known_answer_cases_parse_to_the_same_forest():
+    for case in kat_cases():
+        lines = case["trees"]
+        native = Forest.from_newick("\n".join(lines))
+        try:
+            assert_same_forest(native, lines)
+        finally:
+            native.close()
+
+
+def test_syntax_corner_cases():
+    lines = [
+        "((a:1.5,b:2e-3)90:0.25,(c,'d e':1)inner:3,f)root;",  # support, internal name, quoted label, polytomy
+        "  ( (a , b)[a comment [nested]] , ( c , \"it''s\" ) ) ;",  # whitespace, comments, the other quote
+        "(a:1,(b:0,c:-0.5)100.0:1E2);",  # zero / negative lengths, float support
+        "a;",  # a lone tip
+        "((,),x);",  # unnamed tips
+        "(a,b)",  # no terminating ';'
+        "('a''b':+.5,b:5.);",
+    ]
+    native = Forest.from_newick("\n".join(lines))
+    try:
+        assert_same_forest(native, lines)
+    finally:
+        native.close()
+
+
+@pytest.mark.parametrize(
+    "text",
+    ["(a,b;", "(a,b));", "(a,b);x", "(a,b)c d;", "(a:x,b);", "(a,'b);", "(a,b)[open;", "", "(a,b);\n\n(c,d);", "a b;"],
+)
+def test_syntax_errors_are_newick_errors(text):
+    lines = text.split("\n") if text else [""]
+    with pytest.raises(NewickError):
+        for s in lines:
+            make_tree(s.strip())
+    with pytest.raises(NewickError):
+        Forest.from_newick(text if text else "\n")
+
+
+def test_load_forest_reads_what_load_trees_reads(tmp_path):
+    lines = json.loads((GOLDEN / "fixture_supertriplets.json").read_text())["trees"]
+    path = tmp_path / "source.tre"
+    path.write_text("\n".join(lines) + "\n")
+    forest = load_forest(path)
+    try:
+        assert forest.num_trees == len(load_trees(path)) == len(lines)
+        assert_same_forest(forest, lines)
+    finally:
+        forest.close()
+
+
+def test_many_lines_use_the_threaded_path():
+    rng = np.random.RandomState(3)
+    names = [f"t{i}" for i in range(400)]
+    lines = []
+    for _ in range(600):
+        sub = list(rng.choice(names, size=int(rng.randint(2, 60)), replace=False))
+        items = [f"{x}:{rng.uniform(0, 2):.5f}" for x in sub]
+        while len(items) > 1:
+            a, b = items.pop(int(rng.randint(len(items)))), items.pop(int(rng.randint(len(items))))
+            items.append(f"({a},{b}){int(rng.randint(50, 101))}:{rng.uniform(0, 2):.5f}")
+        lines.append(items[0].rsplit(")", 1)[0] + ");")
+    native = Forest.from_newick("\n".join(lines))
+    try:
+        assert_same_forest(native, lines)
+    finally:
+        native.close()
