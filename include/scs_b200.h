@@ -93,6 +93,9 @@ int scs_ctx_timer_stop(scs_ctx *ctx, double *ms);
  * and the spectral split in one single-CTA launch (dense Jacobi); larger ones take the staged path
  * (union-find, max-merge, Lanczos).  0 sends every node down the staged path. */
 int scs_ctx_set_small_node_limit(scs_ctx *ctx, int limit);
+/* Graph build: use the 8-byte {tour position, slot} bucket entries that nodes of 65 536 taxa or more need
+ * at every size (on = 1; for tests of that path). */
+int scs_ctx_set_wide_entries(scs_ctx *ctx, int on);
 /* Host wall clock spent per stage of the staged (> 64 vertices) node path since the last reset:
  * [0] enqueue graph build + components, [1] wait for them, [2] enqueue contraction, [3] spectral step,
  * [4] result copy, [5] Lanczos iterations within [3]. */

@@ -79,6 +79,7 @@ SIGNATURES: dict[str, tuple] = {
     "scs_ctx_timer_start": (c_int, [_P]),
     "scs_ctx_timer_stop": (c_int, [_P, POINTER(c_double)]),
     "scs_ctx_set_small_node_limit": (c_int, [_P, c_int]),
+    "scs_ctx_set_wide_entries": (c_int, [_P, c_int]),
     "scs_ctx_stage_seconds": (c_int, [_P, _P, c_int]),
     "scs_ctx_flush_l2": (c_int, [_P]),
     "scs_ctx_profile_enable": (c_int, [_P, c_int]),

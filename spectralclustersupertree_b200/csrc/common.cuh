@@ -150,6 +150,7 @@ struct scs_ctx {
     bool rows_configured[8] = {false, false, false, false, false, false, false, false};
     bool contract_configured = false;
     bool kmeans_configured = false;
+    bool wide_entries = false;  // graph build: 8-byte bucket entries even where 4 bytes would do (tests)
     int small_limit = 64;  // nodes up to this size take the one-CTA path (0 disables it)
     double pending_units = 0.0;  // leaf-pair visits of the node being built (set by host entry points)
     cudaEvent_t timer_start = nullptr, timer_stop = nullptr;

@@ -410,6 +410,12 @@ int scs_ctx_set_small_node_limit(scs_ctx *ctx, int limit) {
     return SCS_OK;
 }
 
+int scs_ctx_set_wide_entries(scs_ctx *ctx, int on) {
+    if (!ctx) return SCS_ERR_INVALID;
+    ctx->wide_entries = on != 0;
+    return SCS_OK;
+}
+
 int scs_ctx_stage_seconds(scs_ctx *ctx, double *seconds8, int reset) {
     if (!ctx || !seconds8) return SCS_ERR_INVALID;
     for (int i = 0; i < 8; ++i) {

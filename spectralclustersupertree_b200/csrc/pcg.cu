@@ -677,7 +677,7 @@ int pcg_build(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offsets
     if (nrows == 0) return SCS_OK;
 
     // buckets: count, scan, fill
-    const bool packed = n <= 65535;  // tour positions and slots fit 16 bits each
+    const bool packed = n <= 65535 && !ctx->wide_entries;  // tour positions and slots fit 16 bits each
     const size_t cells = static_cast<size_t>(T) * bs.buckets;
     if (cells + 1 >= (1ull << 31)) return fail(ctx, SCS_ERR_INVALID, "pcg_build: too many tree buckets");
     int32_t *bucket_count, *bucket_ptr;

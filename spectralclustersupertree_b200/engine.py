@@ -100,6 +100,10 @@ class Engine:
         """Largest recursion node (vertices) that takes the one-CTA path; 0 forces the staged path."""
         _check(self._lib.scs_ctx_set_small_node_limit(self._ctx, limit), self._ctx)
 
+    def set_wide_entries(self, on: bool) -> None:
+        """Graph build with the 8-byte bucket entries of nodes with >= 65 536 taxa at every size (tests)."""
+        _check(self._lib.scs_ctx_set_wide_entries(self._ctx, int(on)), self._ctx)
+
     def stage_seconds(self, reset: bool = True) -> dict:
         """Host wall clock per stage of the staged node path (``scs_ctx_stage_seconds``)."""
         out = np.zeros(8)

@@ -274,3 +274,18 @@ def test_pcg_rows_in_column_chunks_bit_exact(engine):
     assert np.array_equal(unpack_bits(out["adj_bits"], n), C > 0)
     top = np.maximum(occ[:, None], occ[None, :])
     assert np.array_equal(unpack_bits(out["max_bits"], n), (C > 0) & (C == top))
+
+
+def test_pcg_wide_bucket_entries_bit_exact(engine):
+    """Nodes with 65 536 taxa or more keep {tour position, slot} in 8-byte entries; the same path at a size the
+    oracle can check."""
+    case = load_case("c2_500x50_branch")
+    ref = case["pcg"]
+    engine.set_wide_entries(True)
+    try:
+        out = engine.pcg_build(tours_of(case), want_counts=True)
+    finally:
+        engine.set_wide_entries(False)
+    assert np.array_equal(out["W"], ref["W"])
+    assert np.array_equal(out["C"], ref["C"])
+    assert np.array_equal(out["occ"], ref["occ"])
