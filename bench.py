@@ -41,7 +41,8 @@ if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
 
 METRIC = "construct_supertree wall-time at 10k taxa/1k trees"
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of matvec_row_per_cta at m = 8765, from the
+PROFILE_MIN_N = 4096  # csrc/common.cuh kProfileMinSize: launches timed one by one (matrices larger than L2)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the matvec (one CTA per row) at m = 8765, from the
 # round-1 `ncu --set full` capture (profiles/r01_ncu_full_matvec_final_raw.csv); algorithmic bytes 614.8 MB
 NCU_MATVEC_TRAFFIC = {"bytes_per_launch": 618.2e6, "algorithmic_bytes": 614.8e6, "m": 8765,
                       "source": "profiles/r01_ncu_full_matvec_final_raw.csv"}
@@ -504,7 +505,7 @@ def gpu_line(args, arrays: dict) -> dict:
 
     peak, peak_src = measured_peak_gbs()
     roofline = {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
-                "kernel": "matvec_row_per_cta (y = D^-1/2 W D^-1/2 x, fp64, m >= 2048)", "peak_source": peak_src}  # fmt: skip
+                "kernel": "matvec_rows<256> (y = D^-1/2 W D^-1/2 x, fp64; the launches with m >= 4096: W exceeds the 126 MB L2)", "peak_source": peak_src}  # fmt: skip
     if matvec["launches"] and matvec["ms"] > 0:
         achieved = matvec["bytes"] / (matvec["ms"] * 1e-3) / 1e9
         roofline.update({
@@ -520,9 +521,9 @@ def gpu_line(args, arrays: dict) -> dict:
         })  # fmt: skip
     roofline_rows = None
     if rows["launches"] and rows["ms"] > 0:
-        visits = sum(v for (t, _), v in zip(mine, replay.pair_visits, strict=True) if t.n >= 2048) * args.steps
+        visits = sum(v for (t, _), v in zip(mine, replay.pair_visits, strict=True) if t.n >= PROFILE_MIN_N) * args.steps
         roofline_rows = {
-            "kernel": "pcg_rows_kernel (leaf-pair LCA weighting -> W rows, adjacency bits, degree), n >= 2048",
+            "kernel": "pcg_rows_kernel (leaf-pair LCA weighting -> W rows, adjacency bits, degree), n >= 4096",
             "bound": "shared-memory / issue (not HBM): ordered leaf-pair visits per second",
             "pair_visits_per_s": visits / (rows["ms"] * 1e-3),
             "write_GBps": rows["bytes"] / (rows["ms"] * 1e-3) / 1e9,
@@ -545,6 +546,7 @@ def gpu_line(args, arrays: dict) -> dict:
                       "GPUs (fused matvec + all-gather over NVLink peer windows), then the frontier is dealt out "
                       "over the ranks and the outputs are all-gathered)",
             "e2e_host_seconds": host_split,
+            "e2e_step_seconds": [round(x, 4) for x in e2e_s],
             "host_threads_per_rank": host_threads,
             "supertree_tips": tips,
             "job": job,

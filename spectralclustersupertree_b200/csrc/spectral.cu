@@ -147,10 +147,22 @@ __device__ __forceinline__ double row_dot_partial(const double *__restrict__ row
         acc3 = fma(d.x, zb[2 * (v + 3 * nthr)], acc3);
         acc3 = fma(d.y, zb[2 * (v + 3 * nthr) + 1], acc3);
     }
-    for (; v < nvec; v += nthr) {
+    // what is left of the row (fewer than 4 nthr vectors): again all loads at once, clamped to the last vector
+    // and masked, not one dependent load after the other
+    if (v < nvec) {
+        const int last = nvec - 1;
+        const int vb = v + nthr, vc = v + 2 * nthr;
+        const double mb = vb < nvec ? 1.0 : 0.0, mc = vc < nvec ? 1.0 : 0.0;
+        const int ib = min(vb, last), ic = min(vc, last);
         const double2 a = load_stream(body + v);
+        const double2 b = load_stream(body + ib);
+        const double2 c = load_stream(body + ic);
         acc0 = fma(a.x, zb[2 * v], acc0);
         acc0 = fma(a.y, zb[2 * v + 1], acc0);
+        acc1 = fma(b.x * mb, zb[2 * ib], acc1);
+        acc1 = fma(b.y * mb, zb[2 * ib + 1], acc1);
+        acc2 = fma(c.x * mc, zb[2 * ic], acc2);
+        acc2 = fma(c.y * mc, zb[2 * ic + 1], acc2);
     }
     double acc = (acc0 + acc1) + (acc2 + acc3);
     if (t == 0) {
@@ -160,39 +172,62 @@ __device__ __forceinline__ double row_dot_partial(const double *__restrict__ row
     return acc;
 }
 
-// one CTA per row (m large: a row is tens of KB)
-__global__ void __launch_bounds__(kMvThreads)
-matvec_row_per_cta(int m, const double *__restrict__ W, const double *__restrict__ isd,
-                   const double *__restrict__ z, double *__restrict__ y, const int32_t *__restrict__ done) {
-    __shared__ double part[kMvThreads / 32];
-    if (done && *done) return;
-    const int row = blockIdx.x;
-    double acc = row_dot_partial(W + static_cast<size_t>(row) * m, z, m, threadIdx.x, kMvThreads);
+// A CTA of kMvThreads threads works on kMvThreads / kGroup rows, kGroup threads each:
+//   kGroup = 32   a warp per row: short rows (m < 2048);
+//   kGroup = 256  a CTA per row: long rows (tens of KB), many waves.
+// 64 and 128 threads per row exist for tuning (SCS_MATVEC_GROUP); measured under ncu on the C4 nodes they are
+// within noise of 256 at every size from 2362 to 8765 columns (tools/matvec_bench.py, profiles/README.md): a
+// 45 MB matrix takes 13 us whatever the shape -- launch ramp and tail, not the row split, separate it from the
+// 7 us of the HBM roofline.
+// The partial sums of a row are combined in a fixed order (lanes by shuffle tree, then warps in order), the
+// same in the single-GPU and in the row-sharded kernel, so both produce the same bits.
+__host__ __device__ constexpr int mv_group_of(int m) { return m < 2048 ? 32 : kMvThreads; }
+
+// Row `row` of W (stored at `Wrow`) times z, by the kGroup threads of the calling group; the result is valid
+// in the group's first thread.  `part` holds kMvThreads / 32 doubles.
+template <int kGroup>
+__device__ __forceinline__ double group_row_dot(const double *__restrict__ Wrow, const double *__restrict__ z, int m,
+                                                double *part) {
+    const int t = threadIdx.x % kGroup, warp = threadIdx.x >> 5;
+    double acc = row_dot_partial(Wrow, z, m, t, kGroup);
     acc = warp_sum(acc);
-    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    if (kGroup == 32) return acc;
+    if ((threadIdx.x & 31) == 0) part[warp] = acc;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        double s = 0.0;
+    double s = 0.0;
+    if (t == 0) {
 #pragma unroll
-        for (int w = 0; w < kMvThreads / 32; ++w) s += part[w];
-        y[row] = isd[row] * s;
+        for (int w = 0; w < kGroup / 32; ++w) s += part[warp + w];
     }
+    return s;
 }
 
-// one warp per row (m small: the whole matrix is L2-resident and rows are short)
+template <int kGroup>
 __global__ void __launch_bounds__(kMvThreads)
-matvec_row_per_warp(int m, const double *__restrict__ W, const double *__restrict__ isd,
-                    const double *__restrict__ z, double *__restrict__ y, const int32_t *__restrict__ done) {
-    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (row >= m || (done && *done)) return;
-    double acc = row_dot_partial(W + static_cast<size_t>(row) * m, z, m, lane, 32);
-    acc = warp_sum(acc);
-    if (lane == 0) y[row] = isd[row] * acc;
+matvec_rows(int m, const double *__restrict__ W, const double *__restrict__ isd, const double *__restrict__ z,
+            double *__restrict__ y, const int32_t *__restrict__ done) {
+    __shared__ double part[kMvThreads / 32];
+    if (done && *done) return;
+    constexpr int kRows = kMvThreads / kGroup;
+    const int row = blockIdx.x * kRows + threadIdx.x / kGroup;
+    const bool live = row < m;
+    // rows past the end redo the last row (every thread must reach the barrier in group_row_dot)
+    const double s = group_row_dot<kGroup>(W + static_cast<size_t>(live ? row : m - 1) * m, z, m, part);
+    if (live && threadIdx.x % kGroup == 0) y[row] = isd[row] * s;
 }
 
 int launch_matvec_single(scs_ctx *ctx, int m, const double *W, const double *isd, const double *z, double *y,
                          const int32_t *done);
+
+// threads per row; SCS_MATVEC_GROUP (32 / 64 / 128 / 256) overrides the choice for rows of >= 2048 columns (tuning)
+int matvec_group(int m) {
+    static const int forced = [] {
+        const char *env = std::getenv("SCS_MATVEC_GROUP");
+        const int v = env ? std::atoi(env) : 0;
+        return (v == 32 || v == 64 || v == 128 || v == 256) ? v : 0;
+    }();
+    return forced && m >= 2048 ? forced : mv_group_of(m);
+}
 
 // Row-sharded operator fused with its all-gather (one process per GPU, rows [row0, row0 + gridDim.x) of
 // W on this rank): every CTA computes one entry of y and stores it straight into the `vec` buffer of
@@ -202,7 +237,7 @@ int launch_matvec_single(scs_ctx *ctx, int m, const double *W, const double *isd
 // so the assembled vector is bit-identical to the single-GPU matvec's.
 // kWarpRows mirrors the single-GPU choice (one warp per row below 2048 columns, one CTA per row above), so
 // that the summation order of every entry is the same in both paths.
-template <bool kWarpRows>
+template <int kGroup>
 __global__ void __launch_bounds__(kMvThreads)
 matvec_rows_allgather(int m, int row0, int nrows, const double *__restrict__ W, const double *__restrict__ isd,
                       const double *__restrict__ z, const PeerTable peers, size_t vec_offset,
@@ -210,31 +245,17 @@ matvec_rows_allgather(int m, int row0, int nrows, const double *__restrict__ W, 
     __shared__ double part[kMvThreads / 32];
     __shared__ unsigned int last;
     if (done && *done) return;  // the same on every rank: nobody signals, nobody waits
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (kWarpRows) {
-        const int local = blockIdx.x * (kMvThreads / 32) + warp;
-        if (local < nrows) {
-            double acc = row_dot_partial(W + static_cast<size_t>(local) * m, z, m, lane, 32);
-            acc = warp_sum(acc);
-            acc = __shfl_sync(0xffffffffu, acc, 0);
-            const double out = isd[row0 + local] * acc;
-            if (lane < peers.world) reinterpret_cast<double *>(peers.window[lane] + vec_offset)[row0 + local] = out;
-            __threadfence_system();
-        }
-    } else {
-        const int row = row0 + blockIdx.x;
-        double acc = row_dot_partial(W + static_cast<size_t>(blockIdx.x) * m, z, m, threadIdx.x, kMvThreads);
-        acc = warp_sum(acc);
-        if (lane == 0) part[warp] = acc;
-        __syncthreads();
-        if (warp == 0) {
-            double s = 0.0;
-#pragma unroll
-            for (int w = 0; w < kMvThreads / 32; ++w) s += part[w];
-            const double out = isd[row] * s;
-            if (lane < peers.world) reinterpret_cast<double *>(peers.window[lane] + vec_offset)[row] = out;
-            __threadfence_system();
-        }
+    constexpr int kRows = kMvThreads / kGroup;
+    const int local = blockIdx.x * kRows + threadIdx.x / kGroup;
+    const bool live = local < nrows;
+    double s = group_row_dot<kGroup>(W + static_cast<size_t>(live ? local : nrows - 1) * m, z, m, part);
+    // the group's first warp stores the entry into every rank's window
+    s = __shfl_sync(0xffffffffu, s, 0);
+    if (live && threadIdx.x % kGroup < 32) {
+        const int lane = threadIdx.x & 31;
+        const double out = isd[row0 + local] * s;
+        if (lane < peers.world) reinterpret_cast<double *>(peers.window[lane] + vec_offset)[row0 + local] = out;
+        __threadfence_system();
     }
     __syncthreads();  // every store of this CTA is fenced before its ticket is drawn
     if (threadIdx.x == 0) {
@@ -260,12 +281,16 @@ int launch_matvec(scs_ctx *ctx, int m, const double *W, const double *isd, const
         if (nrows <= 0) return fail(ctx, SCS_ERR_INVALID, "sharded matvec: a rank owns no rows");
         if (m >= kProfileMinSize)
             profile_begin(ctx, PROFILE_MATVEC, 8.0 * nrows * m + 8.0 * m + 8.0 * nrows * (1 + sh.world), 2.0 * nrows * m);
-        if (m >= 2048)
-            matvec_rows_allgather<false><<<nrows, kMvThreads, 0, ctx->stream>>>(
-                m, rows.row0, nrows, W, isd, z, peers, ticket.vec_offset, ticket.epoch, ticket.timeout_ns, done);
-        else
-            matvec_rows_allgather<true><<<ceil_div(nrows, kMvThreads / 32), kMvThreads, 0, ctx->stream>>>(
-                m, rows.row0, nrows, W, isd, z, peers, ticket.vec_offset, ticket.epoch, ticket.timeout_ns, done);
+#define SCS_MV_AG(G)                                                                                          \
+    matvec_rows_allgather<G><<<ceil_div(nrows, kMvThreads / G), kMvThreads, 0, ctx->stream>>>(                \
+        m, rows.row0, nrows, W, isd, z, peers, ticket.vec_offset, ticket.epoch, ticket.timeout_ns, done)
+        switch (matvec_group(m)) {
+        case 32: SCS_MV_AG(32); break;
+        case 64: SCS_MV_AG(64); break;
+        case 128: SCS_MV_AG(128); break;
+        default: SCS_MV_AG(256); break;
+        }
+#undef SCS_MV_AG
         if (m >= kProfileMinSize) profile_end(ctx);
         SCS_LAUNCHED(ctx, "matvec_rows_allgather");
         return SCS_OK;
@@ -275,17 +300,18 @@ int launch_matvec(scs_ctx *ctx, int m, const double *W, const double *isd, const
 
 int launch_matvec_single(scs_ctx *ctx, int m, const double *W, const double *isd, const double *z, double *y,
                          const int32_t *done) {
-    if (m >= 2048) {
-        // algorithmic bytes: W once + read z, isd, write y
-        if (m >= kProfileMinSize) profile_begin(ctx, PROFILE_MATVEC, 8.0 * m * m + 24.0 * m, 2.0 * m * m);
-        matvec_row_per_cta<<<m, kMvThreads, 0, ctx->stream>>>(m, W, isd, z, y, done);
-        if (m >= kProfileMinSize) profile_end(ctx);
-        SCS_LAUNCHED(ctx, "matvec_row_per_cta");
-    } else {
-        matvec_row_per_warp<<<ceil_div(static_cast<int64_t>(m) * 32, kMvThreads), kMvThreads, 0, ctx->stream>>>(
-            m, W, isd, z, y, done);
-        SCS_LAUNCHED(ctx, "matvec_row_per_warp");
+    // algorithmic bytes: W once + read z, isd, write y
+    if (m >= kProfileMinSize) profile_begin(ctx, PROFILE_MATVEC, 8.0 * m * m + 24.0 * m, 2.0 * m * m);
+#define SCS_MV(G) matvec_rows<G><<<ceil_div(m, kMvThreads / G), kMvThreads, 0, ctx->stream>>>(m, W, isd, z, y, done)
+    switch (matvec_group(m)) {
+    case 32: SCS_MV(32); break;
+    case 64: SCS_MV(64); break;
+    case 128: SCS_MV(128); break;
+    default: SCS_MV(256); break;
     }
+#undef SCS_MV
+    if (m >= kProfileMinSize) profile_end(ctx);
+    SCS_LAUNCHED(ctx, "matvec_rows");
     return SCS_OK;
 }
 
