@@ -8,6 +8,7 @@ same stub for a maintainer of the reference.
 from __future__ import annotations
 
 import ctypes
+import os
 from ctypes import POINTER, c_char_p, c_double, c_int, c_int32, c_int64, c_size_t, c_uint8, c_uint64, c_void_p
 from pathlib import Path
 
@@ -168,6 +169,10 @@ def load() -> ctypes.CDLL:
             "(there is no CPU fallback for the CUDA path)"
         )
         raise LibraryMissingError(msg)
+    # Row-sharded nodes wait on the device for kernels of other contexts; a kernel whose code is loaded lazily at
+    # its first launch can block behind such a wait when the contexts share a process (the in-process multi-rank
+    # tests), so ask for all kernels up front.  Only effective before the CUDA runtime initialises.
+    os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
     lib = ctypes.CDLL(str(LIB_PATH))
     for name, (restype, argtypes) in SIGNATURES.items():
         fn = getattr(lib, name)

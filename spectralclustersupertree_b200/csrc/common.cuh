@@ -221,6 +221,9 @@ __device__ __forceinline__ double order_value(unsigned long long k) {
 }
 #endif
 
+// Large buffers of `ctx` sized for a node of n taxa, T trees, L leaves (context.cu).
+int prewarm_node(scs_ctx *ctx, int n, int T, int64_t L);
+
 // Make sure ctx->workers holds at least `count - 1` extra contexts (the main context is worker 0).
 int ensure_workers(scs_ctx *ctx, int count);
 

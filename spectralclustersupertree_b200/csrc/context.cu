@@ -278,6 +278,42 @@ int node_split(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offset
 
 using namespace scs;
 
+// Size the large buffers of a context for a node of n taxa, T trees, L leaves before it is used.  The driver
+// calls this for every worker context with the largest node of a wave, so that which worker happens to draw
+// which node (dynamic scheduling) never decides whether a timed run pays for a first allocation.
+namespace scs {
+int prewarm_node(scs_ctx *ctx, int n, int T, int64_t L) {
+    DeviceGuard guard(ctx->device);
+    const size_t nT = static_cast<size_t>(T), nL = static_cast<size_t>(L), nn = static_cast<size_t>(n) * n;
+    const size_t total = (nT + 1) * sizeof(int64_t) + nL * (sizeof(double) + 2 * sizeof(int32_t)) +
+                         nT * (sizeof(double) + sizeof(int32_t)) + 64;
+    if (ctx->pinned_io_bytes < total) {
+        if (ctx->pinned_io) {
+            SCS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            SCS_CUDA(ctx, cudaFreeHost(ctx->pinned_io));
+            ctx->pinned_io = nullptr;
+            ctx->pinned_io_bytes = 0;
+        }
+        const size_t want = 2 * total + 4096;
+        SCS_CUDA(ctx, cudaMallocHost(&ctx->pinned_io, want));
+        ctx->pinned_io_bytes = want;
+    }
+    const size_t words = static_cast<size_t>(scs_bit_words(n));
+    const size_t basis = static_cast<size_t>((n - 1 < 256 ? n - 1 : 256) + 3) * n;
+    void *p;
+    int rc;
+    if ((rc = reserve(ctx, SLOT_TOUR_OFFSETS, total, &p))) return rc;
+    if ((rc = reserve(ctx, SLOT_W, 8 * nn, &p))) return rc;
+    if ((rc = reserve(ctx, SLOT_WC, 8 * nn, &p))) return rc;
+    if ((rc = reserve(ctx, SLOT_ADJ_BITS, 4 * n * words, &p))) return rc;
+    if ((rc = reserve(ctx, SLOT_MAX_BITS, 4 * n * words, &p))) return rc;
+    if ((rc = reserve(ctx, SLOT_BASIS, 8 * basis, &p))) return rc;
+    if ((rc = reserve(ctx, SLOT_LINKS, 16 * (nL + 1), &p))) return rc;
+    if ((rc = reserve(ctx, SLOT_ENTRIES, 8 * (nL + 1), &p))) return rc;
+    return SCS_OK;
+}
+}  // namespace scs
+
 extern "C" {
 
 int scs_version(void) { return 100; }

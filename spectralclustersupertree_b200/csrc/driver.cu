@@ -422,6 +422,19 @@ class Driver {
         int rc = ensure_workers(ctx_, workers);
         if (rc) return rc;
         if (static_cast<int>(buffers_.size()) < workers) buffers_.resize(workers);
+        {
+            // any worker may draw the largest node of the wave: size them all for it now
+            int big_n = 0, big_T = 0;
+            int64_t big_L = 0;
+            for (int r : concurrent) {
+                const Task &task = wave[results[r].task];
+                big_n = std::max(big_n, static_cast<int>(task.taxa.size()));
+                big_T = std::max(big_T, scs_forest_num_trees(task.forest));
+                big_L = std::max<int64_t>(big_L, scs_forest_num_leaves(task.forest));
+            }
+            for (int w = 0; w < workers; ++w)
+                if ((rc = prewarm_node(w == 0 ? ctx_ : ctx_->workers[w - 1], big_n, big_T, big_L))) return rc;
+        }
         int first_error = SCS_OK;
 #pragma omp parallel for schedule(dynamic, 1) num_threads(workers) if (workers > 1)
         for (int i = 0; i < jobs; ++i) {

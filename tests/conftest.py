@@ -3,6 +3,11 @@ everything else runs on CPU (oracle vs golden vectors, host logic, symbol checks
 
 from __future__ import annotations
 
+import os
+
+# see spectralclustersupertree_b200/_lib.py: load every kernel before ranks start waiting for each other on the device
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+
 import sys
 from pathlib import Path
 
