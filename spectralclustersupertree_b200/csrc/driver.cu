@@ -19,6 +19,7 @@
 #include <chrono>
 #include <cmath>
 #include <memory>
+#include <thread>
 
 #include <omp.h>
 
@@ -46,11 +47,11 @@ namespace scs {
 namespace {
 
 constexpr int kMaxWorkers = 16;       // upper bound on the contexts driving staged nodes concurrently
-// how many of them are used (default 4; SCS_NODE_WORKERS overrides, for tuning)
+// how many of them are used (default 8; SCS_NODE_WORKERS overrides, for tuning)
 int node_workers() {
     static const int value = [] {
         const char *env = std::getenv("SCS_NODE_WORKERS");
-        const int v = env ? std::atoi(env) : 4;
+        const int v = env ? std::atoi(env) : 8;
         return v < 1 ? 1 : (v > kMaxWorkers ? kMaxWorkers : v);
     }();
     return value;
@@ -338,8 +339,28 @@ class Driver {
             results.emplace_back();
             results.back().task = i;
         }
-        if ((rc = split_large_all(wave, results))) return rc;
-        if (!small.empty() && (rc = split_small(wave, small, results))) return rc;
+        if (!small.empty() && !results.empty() && small_context() != nullptr) {
+            // both kinds of nodes in this wave: the batch of small nodes runs on its own context (stream) and
+            // host thread next to the large nodes, which are a chain of small launches and round trips
+            std::vector<SplitResult> small_results;
+            int small_rc = SCS_OK;
+            std::thread helper([&] {
+                cudaSetDevice(ctx_->device);
+                small_rc = split_small(small_ctx_, scratch_small_, wave, small, small_results);
+            });
+            rc = split_large_all(wave, results);
+            helper.join();
+            fold_counters(small_ctx_);
+            if (rc == SCS_OK && small_rc != SCS_OK) {
+                ctx_->last_error = small_ctx_->last_error;
+                rc = small_rc;
+            }
+            if (rc) return rc;
+            for (SplitResult &res : small_results) results.push_back(std::move(res));
+        } else {
+            if ((rc = split_large_all(wave, results))) return rc;
+            if (!small.empty() && (rc = split_small(ctx_, scratch_, wave, small, results))) return rc;
+        }
 
         // children of every split node (scs.py:136-171).  The restrictions of the whole wave run as ONE
         // batch over all host threads: (child, source tree) pairs are the work items, so a wave of two huge
@@ -406,7 +427,11 @@ class Driver {
         std::vector<int> serial, concurrent;
         for (int r = 0; r < static_cast<int>(results.size()); ++r) {
             const Task &task = wave[results[r].task];
-            out_.pair_visits += scs_forest_pair_visits(task.forest);
+            {
+                const int64_t visits = scs_forest_pair_visits(task.forest);
+#pragma omp atomic
+                out_.pair_visits += visits;
+            }
             const int n = static_cast<int>(task.taxa.size());
             (n > kConcurrentMax || shard_applies(ctx_, n) ? serial : concurrent).push_back(r);
         }
@@ -449,23 +474,39 @@ class Driver {
                 first_error = status;
             }
         }
-        // fold the workers' counters into the main context
-        for (scs_ctx *worker : ctx_->workers) {
-            ctx_->launches += worker->launches;
-            ctx_->h2d_bytes += worker->h2d_bytes;
-            ctx_->d2h_bytes += worker->d2h_bytes;
-            worker->launches = 0;
-            worker->h2d_bytes = worker->d2h_bytes = 0;
-            for (int k = 0; k < 8; ++k) {
-                ctx_->stage_seconds[k] += worker->stage_seconds[k];
-                worker->stage_seconds[k] = 0.0;
-            }
-        }
+        for (scs_ctx *worker : ctx_->workers) fold_counters(worker);
         return first_error;
     }
 
-    int split_small(std::vector<Task> &wave, const std::vector<size_t> &small, std::vector<SplitResult> &results) {
+    // fold another context's counters into the main context
+    void fold_counters(scs_ctx *other) {
+        ctx_->launches += other->launches;
+        ctx_->h2d_bytes += other->h2d_bytes;
+        ctx_->d2h_bytes += other->d2h_bytes;
+        other->launches = 0;
+        other->h2d_bytes = other->d2h_bytes = 0;
+        for (int k = 0; k < 8; ++k) {
+            ctx_->stage_seconds[k] += other->stage_seconds[k];
+            other->stage_seconds[k] = 0.0;
+        }
+    }
+
+    // The context the batch of small nodes uses when it runs next to the large nodes (the last worker slot).
+    scs_ctx *small_context() {
+        if (small_ctx_) return small_ctx_;
+        if (scs_host_threads() < 2) return nullptr;
+        if (ensure_workers(ctx_, kMaxWorkers + 1) != SCS_OK) return nullptr;
+        small_ctx_ = ctx_->workers[kMaxWorkers - 1];
+        small_ctx_->small_limit = ctx_->small_limit;
+        scratch_small_.resize(scratch_.size());
+        for (Scratch &sc : scratch_small_) sc.reset(num_taxa_);
+        return small_ctx_;
+    }
+
+    int split_small(scs_ctx *ctx, std::vector<Scratch> &scratch, std::vector<Task> &wave,
+                    const std::vector<size_t> &small, std::vector<SplitResult> &results) {
         const int B = static_cast<int>(small.size());
+        int64_t visits = 0;
         std::vector<scs_small_node> nodes(B);
         int64_t L_total = 0, T_total = 0, N_total = 0;
         for (int b = 0; b < B; ++b) {
@@ -478,7 +519,11 @@ class Driver {
             L_total += scs_forest_num_leaves(f);
             T_total += nodes[b].num_trees;
             N_total += nodes[b].n;
-            out_.pair_visits += scs_forest_pair_visits(f);
+            visits += scs_forest_pair_visits(f);
+        }
+        {
+#pragma omp atomic
+            out_.pair_visits += visits;
         }
         off_.resize(T_total + B);
         tax_.resize(L_total + 1);
@@ -492,7 +537,7 @@ class Driver {
 #pragma omp parallel for schedule(dynamic, 8) if (B >= 32) num_threads(scs_host_threads())
             for (int b = 0; b < B; ++b) {
                 const scs_forest *f = wave[small[b]].forest;
-                const int rc = tours_of(f, wave[small[b]].taxa, scratch_[static_cast<size_t>(omp_get_thread_num())].local,
+                const int rc = tours_of(f, wave[small[b]].taxa, scratch[static_cast<size_t>(omp_get_thread_num())].local,
                                         off_.data() + nodes[b].tree_base + b, tax_.data() + nodes[b].leaf_base,
                                         dep_.data() + nodes[b].leaf_base, val_.data() + nodes[b].leaf_base,
                                         root_.data() + nodes[b].tree_base, wgt_.data() + nodes[b].tree_base);
@@ -508,7 +553,7 @@ class Driver {
         int rc;
         {
             Stopwatch sw(&out_.seconds[1]);
-            rc = scs_nodes_split_small_host(ctx_, B, nodes.data(), L_total, T_total, off_.data(), tax_.data(),
+            rc = scs_nodes_split_small_host(ctx, B, nodes.data(), L_total, T_total, off_.data(), tax_.data(),
                                             dep_.data(), val_.data(), root_.data(), wgt_.data(), contract_,
                                             part_.data(), stats.data());
         }
@@ -640,7 +685,8 @@ class Driver {
     double trace_induce_ = 0.0, trace_present_ = 0.0;  // thread-seconds (summed over host threads)
     scs_supertree &out_;
     int num_taxa_ = 0;
-    std::vector<Scratch> scratch_;
+    std::vector<Scratch> scratch_, scratch_small_;
+    scs_ctx *small_ctx_ = nullptr;
     std::vector<int32_t> owner_;    // global taxon id -> restriction job of the current wave
     std::vector<uint8_t> present_;  // scratch of plan_wave (all zero between waves)
     std::vector<TourBuffers> buffers_;
