@@ -47,6 +47,12 @@ void finish_tree(scs_forest &f, int64_t base, int64_t count) {
     if (count > 1)
         for (int64_t k = 0; k < count; ++k) tips += f.taxon[base + k] >= 0;
     f.leaf_offsets.push_back(f.leaf_offsets.back() + tips);
+    // internal nodes with a single child?  (children of k directly follow it in pre-order: count them)
+    std::vector<int32_t> kids(static_cast<size_t>(count), 0);
+    for (int64_t k = 1; k < count; ++k) kids[f.parent[base + k]] += 1;
+    bool branching = true;
+    for (int64_t k = 0; k < count && branching; ++k) branching = f.taxon[base + k] >= 0 || kids[k] >= 2;
+    f.branching.push_back(branching ? 1 : 0);
 }
 
 }  // namespace
@@ -205,6 +211,7 @@ int scs_forest_induce(const scs_forest *f, const uint8_t *keep, scs_forest **out
         g->leaf_offsets.push_back(g->leaf_offsets.back() + kept_tips[t]);
         g->weight.push_back(f->weight[t]);
         g->source.push_back(f->source[t]);
+        g->branching.push_back(1);
     }
     const int64_t M_out = out_base[T];
     g->parent.resize_uninitialized(M_out);
@@ -299,8 +306,8 @@ struct Staging {
 };
 
 struct StagedTree {
-    int32_t nodes = 0, tips = 0, thread = 0;
-    int64_t offset = 0;  // in the thread's staging, then (after the layout) in the output forest
+    int32_t nodes = 0, tips = 0, thread = 0;  // thread < 0: copied verbatim from the source forest at `offset`
+    int64_t offset = 0;  // in the thread's staging (or the source forest)
 };
 
 // The staging buffers are kept between calls (a wave of the recursion re-uses what the previous one
@@ -359,7 +366,7 @@ int scs_forest_induce_batch(scs_induce_job *jobs, int count, const int32_t *owne
         const int me = omp_get_thread_num();
         Staging &st = pool[me];
         st.clear();
-        std::vector<int32_t> cnt, live, idx;
+        std::vector<int32_t> cnt, live, idx, hist;
 #pragma omp for schedule(dynamic, 8)
         for (int64_t i = 0; i < items; ++i) {
             const int r = item_run[i];
@@ -370,8 +377,31 @@ int scs_forest_induce_batch(scs_induce_job *jobs, int count, const int32_t *owne
             const int32_t *tax = f->taxon.data() + base;
             const double *len = f->length.data() + base;
             const double *sup = f->support.data() + base;
+            // how many tips of this tree each job of the run keeps: most (job, tree) pairs need no second look
+            const int run_jobs = run_last[r] - run_first[r];
+            hist.assign(static_cast<size_t>(run_jobs), 0);
+            int32_t tree_tips = 0;
+            for (int64_t k = 0; k < cnt_nodes; ++k) {
+                if (tax[k] < 0) continue;
+                ++tree_tips;
+                const int32_t o = owner[tax[k]] - run_first[r];
+                if (o >= 0 && o < run_jobs) hist[o] += 1;
+            }
             for (int j = run_first[r]; j < run_last[r]; ++j) {
                 StagedTree &out = staged[job_tree[j] + t];
+                const int32_t mine = hist[j - run_first[r]];
+                if (mine < 2 || cnt_nodes < 3) continue;  // scs.py:447-448: the tree is dropped
+                if (mine == tree_tips && f->branching[t]) {
+                    // every tip stays and there is no unary node to merge: the restricted tree is the tree itself
+                    // (its root loses its length); copied straight from the source in pass 2
+                    out.nodes = static_cast<int32_t>(cnt_nodes);
+                    out.tips = mine;
+                    out.thread = -1;
+                    out.offset = base;
+                    for (int64_t k = 0; k < cnt_nodes; ++k)
+                        if (tax[k] >= 0) present[tax[k]] = 1;
+                    continue;
+                }
                 int32_t tips = 0;
                 const int32_t kept = mark_retained(par, tax, cnt_nodes, owner, j, cnt, live, idx, &tips);
                 if (kept == 0) continue;
@@ -434,6 +464,7 @@ int scs_forest_induce_batch(scs_induce_job *jobs, int count, const int32_t *owne
             g->leaf_offsets.push_back(g->leaf_offsets.back() + tree.tips);
             g->weight.push_back(f->weight[t]);
             g->source.push_back(f->source[t]);
+            g->branching.push_back(1);
         }
         g->parent.resize_uninitialized(at);
         g->length.resize_uninitialized(at);
@@ -457,9 +488,18 @@ int scs_forest_induce_batch(scs_induce_job *jobs, int count, const int32_t *owne
         for (int64_t i = 0; i < total; ++i) {
             const StagedTree &tree = staged[i];
             if (tree.nodes == 0) continue;
-            const Staging &st = pool[tree.thread];
             scs_forest *g = jobs[tree_job[i]].out;
             const size_t n = static_cast<size_t>(tree.nodes);
+            if (tree.thread < 0) {
+                const scs_forest *f = jobs[tree_job[i]].src;
+                std::memcpy(g->parent.data() + dest[i], f->parent.data() + tree.offset, n * sizeof(int32_t));
+                std::memcpy(g->taxon.data() + dest[i], f->taxon.data() + tree.offset, n * sizeof(int32_t));
+                std::memcpy(g->length.data() + dest[i], f->length.data() + tree.offset, n * sizeof(double));
+                std::memcpy(g->support.data() + dest[i], f->support.data() + tree.offset, n * sizeof(double));
+                g->length[dest[i]] = std::nan("");  // the root's own length is dropped
+                continue;
+            }
+            const Staging &st = pool[tree.thread];
             std::memcpy(g->parent.data() + dest[i], st.parent.data() + tree.offset, n * sizeof(int32_t));
             std::memcpy(g->taxon.data() + dest[i], st.taxon.data() + tree.offset, n * sizeof(int32_t));
             std::memcpy(g->length.data() + dest[i], st.length.data() + tree.offset, n * sizeof(double));

@@ -52,6 +52,8 @@ struct scs_forest {
     std::vector<double> weight;            // [T]
     std::vector<int32_t> source;           // [T] index of the tree in the forest first created
     std::vector<int64_t> leaf_offsets{0};  // [T + 1] tips that appear in tours (a lone tip has none)
+    std::vector<uint8_t> branching;        // [T] 1: every internal node has at least two children (always true for
+                                           // a restricted tree); such a tree restricted to ALL its tips is itself
     int num_trees() const { return static_cast<int>(weight.size()); }
 };
 

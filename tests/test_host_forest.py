@@ -140,3 +140,43 @@ def test_induce_parts_equals_one_restriction_per_part(name, parts):
         assert_same_tours(sub.tours(case["weighting"]), want.tours(case["weighting"]))
         seen.append(want.taxa())
     assert np.array_equal(present, np.sort(np.concatenate(seen)))
+
+
+def test_induce_parts_keeps_whole_trees_verbatim():
+    """Parts that swallow whole source trees (the common case deep in the recursion): the batched restriction
+    copies such a tree as it is, unless it has unary nodes to merge; either way the result equals ``induce``.
+    Applied twice, so that restricted forests are restricted again."""
+    lines = [
+        "((a:1,b:2):0.5,(c:3,d:4)90:0.25,e:5);",  # whole in part 0
+        "((a:1,(b:2):7):0.5,((c:3)));",  # unary nodes, whole in part 0: must still be merged
+        "((f:1,g:2):1,(h:3,(i:4,j:5):6):2);",  # whole in part 1
+        "((a:1,f:2):1,(b:3,g:4):2,c:1);",  # split between the parts
+        "(a:1,b:1);",  # two tips, whole in part 0
+        "(a:1,f:1);",  # one tip per part: dropped from both
+        "k;",  # a lone tip of no part
+    ]
+    trees = parse(lines)
+    names = sorted({x for t in trees for x in t.get_tip_names()})
+    forest = Forest.from_trees(trees, [1.0, 2.0, 0.5, 1.5, 1.0, 1.0, 1.0], names)
+    part = np.array([0 if x in "abcde" else (1 if x in "fghij" else -1) for x in names], dtype=np.int32)
+
+    def check(src: Forest, part: np.ndarray, parts: int) -> list[Forest]:
+        subs, present = src.induce_parts(part, parts)
+        seen = []
+        for c, sub in enumerate(subs):
+            want = src.induce(np.flatnonzero(part == c).astype(np.int32))
+            assert sub.num_trees == want.num_trees
+            assert np.array_equal(sub.weights(), want.weights())
+            for t in range(sub.num_trees):
+                for got_arr, want_arr in zip(sub.tree_arrays(t), want.tree_arrays(t), strict=True):
+                    assert np.array_equal(got_arr, want_arr, equal_nan=True), (c, t)
+            assert_same_tours(sub.tours("branch"), want.tours("branch"))
+            seen.append(want.taxa())
+        assert np.array_equal(present, np.sort(np.concatenate(seen)))
+        return subs
+
+    first = check(forest, part, 2)
+    assert first[0].num_trees == 4 and first[1].num_trees == 2
+    # again: part 0's forest split into {a, b} | {c, d, e}; its whole-tree copies are restricted for real now
+    again = np.array([0 if x in "ab" else (1 if x in "cde" else -1) for x in names], dtype=np.int32)
+    check(first[0], again, 2)
