@@ -506,6 +506,11 @@ def gpu_line(args, arrays: dict) -> dict:
     peak, peak_src = measured_peak_gbs()
     roofline = {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
                 "kernel": "matvec_rows<256> (y = D^-1/2 W D^-1/2 x, fp64; the launches with m >= 4096: W exceeds the 126 MB L2)", "peak_source": peak_src}  # fmt: skip
+    if sharing:
+        # every launch of that size is then the row-sharded kernel: its time includes the all-gather of the
+        # result over NVLink and the wait for the slowest rank
+        roofline["kernel"] = ("matvec_rows_allgather<256> (this rank's row block of y = D^-1/2 W D^-1/2 x fused with the "
+                              "all-gather of y into every peer's window and the barrier; m >= 4096)")
     if matvec["launches"] and matvec["ms"] > 0:
         achieved = matvec["bytes"] / (matvec["ms"] * 1e-3) / 1e9
         roofline.update({

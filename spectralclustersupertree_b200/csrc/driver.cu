@@ -532,9 +532,11 @@ class Driver {
         root_.resize(T_total + 1);
         wgt_.resize(T_total + 1);
         int tours_rc = SCS_OK;
+        // next to the large nodes (own context) the host threads are shared with their workers: a small team
+        const int tour_threads = ctx == ctx_ ? scs_host_threads() : std::max(1, std::min(4, scs_host_threads() / 4));
         {
             Stopwatch sw(&out_.seconds[3]);
-#pragma omp parallel for schedule(dynamic, 8) if (B >= 32) num_threads(scs_host_threads())
+#pragma omp parallel for schedule(dynamic, 8) if (B >= 32) num_threads(tour_threads)
             for (int b = 0; b < B; ++b) {
                 const scs_forest *f = wave[small[b]].forest;
                 const int rc = tours_of(f, wave[small[b]].taxa, scratch[static_cast<size_t>(omp_get_thread_num())].local,
