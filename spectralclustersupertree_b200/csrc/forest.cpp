@@ -20,6 +20,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <utility>
 #include <vector>
 
 #include "scs_b200.h"
@@ -295,13 +296,48 @@ inline int32_t mark_retained(const int32_t *par, const int32_t *tax, int64_t cou
 // Restricted trees are first written to per-thread staging (their sizes are only known once they are
 // built), then copied to their place in the output forests.
 struct Staging {
-    std::vector<int32_t> parent, taxon;
-    std::vector<double> length, support;
-    void clear() {
-        parent.clear();
-        taxon.clear();
-        length.clear();
-        support.clear();
+    // grown by doubling, never value-initialised: every element is written right after it is claimed
+    int32_t *parent = nullptr, *taxon = nullptr;
+    double *length = nullptr, *support = nullptr;
+    size_t size = 0, capacity = 0;
+    Staging() = default;
+    Staging(const Staging &) = delete;
+    Staging &operator=(const Staging &) = delete;
+    Staging(Staging &&o) noexcept { *this = std::move(o); }
+    Staging &operator=(Staging &&o) noexcept {
+        release();
+        parent = o.parent, taxon = o.taxon, length = o.length, support = o.support;
+        size = o.size, capacity = o.capacity;
+        o.parent = o.taxon = nullptr;
+        o.length = o.support = nullptr;
+        o.size = o.capacity = 0;
+        return *this;
+    }
+    ~Staging() { release(); }
+    void release() {
+        std::free(parent);
+        std::free(taxon);
+        std::free(length);
+        std::free(support);
+        parent = taxon = nullptr;
+        length = support = nullptr;
+        size = capacity = 0;
+    }
+    void clear() { size = 0; }
+    // room for `count` more nodes; returns the index of the first
+    size_t claim(size_t count) {
+        if (size + count > capacity) {
+            size_t want = capacity ? capacity : (1u << 16);
+            while (want < size + count) want *= 2;
+            parent = static_cast<int32_t *>(std::realloc(parent, want * sizeof(int32_t)));
+            taxon = static_cast<int32_t *>(std::realloc(taxon, want * sizeof(int32_t)));
+            length = static_cast<double *>(std::realloc(length, want * sizeof(double)));
+            support = static_cast<double *>(std::realloc(support, want * sizeof(double)));
+            capacity = want;
+        }
+        const size_t at = size;
+        size += count;
+        return at;
     }
 };
 
@@ -366,7 +402,7 @@ int scs_forest_induce_batch(scs_induce_job *jobs, int count, const int32_t *owne
         const int me = omp_get_thread_num();
         Staging &st = pool[me];
         st.clear();
-        std::vector<int32_t> cnt, live, idx, hist;
+        std::vector<int32_t> cnt, live, idx, hist, pair;
 #pragma omp for schedule(dynamic, 8)
         for (int64_t i = 0; i < items; ++i) {
             const int r = item_run[i];
@@ -377,8 +413,97 @@ int scs_forest_induce_batch(scs_induce_job *jobs, int count, const int32_t *owne
             const int32_t *tax = f->taxon.data() + base;
             const double *len = f->length.data() + base;
             const double *sup = f->support.data() + base;
-            // how many tips of this tree each job of the run keeps: most (job, tree) pairs need no second look
             const int run_jobs = run_last[r] - run_first[r];
+            if (run_jobs == 2 && cnt_nodes >= 3) {
+                // The two sides of a bipartition (the usual run) in two passes over the tree instead of seven:
+                // bottom-up, per node and side the kept tips below it, the children that carry some, and how
+                // many nodes survive; top-down, both restricted trees written at once.
+                const int32_t j0 = run_first[r];
+                pair.assign(static_cast<size_t>(cnt_nodes) * 4, 0);  // per node: tips[2], live children[2]
+                int32_t tips2[2] = {0, 0}, kept2[2] = {0, 0}, tree_tips = 0;
+                for (int64_t k = cnt_nodes - 1; k >= 0; --k) {
+                    int32_t *me4 = pair.data() + 4 * k;
+                    const bool tip = tax[k] >= 0;
+                    if (tip) {
+                        ++tree_tips;
+                        const int32_t o = owner[tax[k]] - j0;
+                        if (o == 0 || o == 1) {
+                            me4[o] = 1;
+                            tips2[o] += 1;
+                        }
+                    }
+                    for (int h = 0; h < 2; ++h) {
+                        const int32_t c = me4[h];
+                        if (!c) continue;
+                        kept2[h] += tip || me4[2 + h] >= 2;
+                        if (k > 0) {
+                            int32_t *up4 = pair.data() + 4 * static_cast<int64_t>(par[k]);
+                            up4[h] += c;
+                            up4[2 + h] += 1;
+                        }
+                    }
+                }
+                int32_t *o_par[2] = {nullptr, nullptr}, *o_tax[2] = {nullptr, nullptr};
+                double *o_len[2] = {nullptr, nullptr}, *o_sup[2] = {nullptr, nullptr};
+                bool build[2] = {false, false};
+                for (int h = 0; h < 2; ++h) {
+                    StagedTree &out = staged[job_tree[j0 + h] + t];
+                    if (tips2[h] < 2) continue;  // scs.py:447-448: the tree is dropped
+                    if (tips2[h] == tree_tips && f->branching[t]) {
+                        out.nodes = static_cast<int32_t>(cnt_nodes);  // kept whole: copied from the source in pass 2
+                        out.tips = tips2[h];
+                        out.thread = -1;
+                        out.offset = base;
+                        for (int64_t k = 0; k < cnt_nodes; ++k)
+                            if (tax[k] >= 0) present[tax[k]] = 1;
+                        continue;
+                    }
+                    out.nodes = kept2[h];
+                    out.tips = tips2[h];
+                    out.thread = me;
+                    const size_t at = st.claim(static_cast<size_t>(kept2[h]));
+                    out.offset = static_cast<int64_t>(at);
+                    build[h] = true;
+                }
+                for (int h = 0; h < 2; ++h) {  // pointers only now: the second claim may have moved the buffers
+                    if (!build[h]) continue;
+                    const size_t at = static_cast<size_t>(staged[job_tree[j0 + h] + t].offset);
+                    o_par[h] = st.parent + at;
+                    o_tax[h] = st.taxon + at;
+                    o_len[h] = st.length + at;
+                    o_sup[h] = st.support + at;
+                }
+                if (!build[0] && !build[1]) continue;
+                idx.assign(static_cast<size_t>(cnt_nodes) * 2, -1);  // new index per node and side
+                int32_t next2[2] = {0, 0};
+                for (int64_t k = 0; k < cnt_nodes; ++k) {
+                    const int32_t *me4 = pair.data() + 4 * k;
+                    const bool tip = tax[k] >= 0;
+                    for (int h = 0; h < 2; ++h) {
+                        if (!build[h] || !me4[h] || !(tip || me4[2 + h] >= 2)) continue;
+                        const int32_t q = next2[h]++;
+                        idx[2 * k + h] = q;
+                        if (q == 0) {  // first retained node in pre-order: the new root, its own length is dropped
+                            o_par[h][0] = -1;
+                            o_len[h][0] = std::nan("");
+                        } else {
+                            double acc = len[k];
+                            int64_t a = par[k];
+                            while (idx[2 * a + h] < 0) {  // merged unary ancestors, bottom-up
+                                acc = len[a] + acc;       // NaN (missing) propagates like None
+                                a = par[a];
+                            }
+                            o_par[h][q] = idx[2 * a + h];
+                            o_len[h][q] = acc;
+                        }
+                        o_sup[h][q] = sup[k];
+                        o_tax[h][q] = tax[k];
+                        if (tip) present[tax[k]] = 1;  // racing writers all store 1
+                    }
+                }
+                continue;
+            }
+            // how many tips of this tree each job of the run keeps: most (job, tree) pairs need no second look
             hist.assign(static_cast<size_t>(run_jobs), 0);
             int32_t tree_tips = 0;
             for (int64_t k = 0; k < cnt_nodes; ++k) {
@@ -408,16 +533,12 @@ int scs_forest_induce_batch(scs_induce_job *jobs, int count, const int32_t *owne
                 out.nodes = kept;
                 out.tips = tips;
                 out.thread = me;
-                out.offset = static_cast<int64_t>(st.parent.size());
-                const size_t at = st.parent.size();
-                st.parent.resize(at + kept);
-                st.taxon.resize(at + kept);
-                st.length.resize(at + kept);
-                st.support.resize(at + kept);
-                int32_t *o_par = st.parent.data() + at;
-                int32_t *o_tax = st.taxon.data() + at;
-                double *o_len = st.length.data() + at;
-                double *o_sup = st.support.data() + at;
+                const size_t at = st.claim(static_cast<size_t>(kept));
+                out.offset = static_cast<int64_t>(at);
+                int32_t *o_par = st.parent + at;
+                int32_t *o_tax = st.taxon + at;
+                double *o_len = st.length + at;
+                double *o_sup = st.support + at;
                 for (int64_t k = 0; k < cnt_nodes; ++k) {
                     const int32_t q = idx[k];
                     if (q < 0) continue;
@@ -445,16 +566,28 @@ int scs_forest_induce_batch(scs_induce_job *jobs, int count, const int32_t *owne
     const double t_pass1 = omp_get_wtime();
     int rc = SCS_OK;
     std::vector<int64_t> dest(staged.size(), 0);
-    for (int j = 0; j < count && rc == SCS_OK; ++j) {
+    // every job lays out its own forest: independent, so spread over the host threads as well (deep waves have
+    // thousands of jobs and hundreds of thousands of little trees)
+#pragma omp parallel for schedule(dynamic, 16) if (threaded && count >= 64) num_threads(threads)
+    for (int j = 0; j < count; ++j) {
         scs_forest *g = new (std::nothrow) scs_forest();
+        jobs[j].out = g;
         if (!g) {
+#pragma omp atomic write
             rc = SCS_ERR_INVALID;
-            break;
+            continue;
         }
         const scs_forest *f = jobs[j].src;
         g->num_taxa = f->num_taxa;
         int64_t at = 0;
         const int T = f->num_trees();
+        int kept_trees = 0;
+        for (int t = 0; t < T; ++t) kept_trees += staged[job_tree[j] + t].nodes != 0;
+        g->node_offsets.reserve(static_cast<size_t>(kept_trees) + 1);
+        g->leaf_offsets.reserve(static_cast<size_t>(kept_trees) + 1);
+        g->weight.reserve(static_cast<size_t>(kept_trees));
+        g->source.reserve(static_cast<size_t>(kept_trees));
+        g->branching.assign(static_cast<size_t>(kept_trees), 1);
         for (int t = 0; t < T; ++t) {
             const StagedTree &tree = staged[job_tree[j] + t];
             if (tree.nodes == 0) continue;
@@ -464,13 +597,11 @@ int scs_forest_induce_batch(scs_induce_job *jobs, int count, const int32_t *owne
             g->leaf_offsets.push_back(g->leaf_offsets.back() + tree.tips);
             g->weight.push_back(f->weight[t]);
             g->source.push_back(f->source[t]);
-            g->branching.push_back(1);
         }
         g->parent.resize_uninitialized(at);
         g->length.resize_uninitialized(at);
         g->support.resize_uninitialized(at);
         g->taxon.resize_uninitialized(at);
-        jobs[j].out = g;
     }
     const double t_layout = omp_get_wtime();
     if (rc != SCS_OK) {
@@ -500,10 +631,10 @@ int scs_forest_induce_batch(scs_induce_job *jobs, int count, const int32_t *owne
                 continue;
             }
             const Staging &st = pool[tree.thread];
-            std::memcpy(g->parent.data() + dest[i], st.parent.data() + tree.offset, n * sizeof(int32_t));
-            std::memcpy(g->taxon.data() + dest[i], st.taxon.data() + tree.offset, n * sizeof(int32_t));
-            std::memcpy(g->length.data() + dest[i], st.length.data() + tree.offset, n * sizeof(double));
-            std::memcpy(g->support.data() + dest[i], st.support.data() + tree.offset, n * sizeof(double));
+            std::memcpy(g->parent.data() + dest[i], st.parent + tree.offset, n * sizeof(int32_t));
+            std::memcpy(g->taxon.data() + dest[i], st.taxon + tree.offset, n * sizeof(int32_t));
+            std::memcpy(g->length.data() + dest[i], st.length + tree.offset, n * sizeof(double));
+            std::memcpy(g->support.data() + dest[i], st.support + tree.offset, n * sizeof(double));
         }
     }
     if (shared_pool) omp_unset_lock(&g_staging_lock);
