@@ -43,17 +43,18 @@ bool is_tip(const scs_forest &f, int64_t base, int64_t count, int64_t k) {
     return k + 1 >= count || f.parent[base + k + 1] != k;
 }
 
-void finish_tree(scs_forest &f, int64_t base, int64_t count) {
+// Tips that appear in tours (a lone tip has none) and whether every internal node has at least two children.
+void tree_shape(const scs_forest &f, int64_t base, int64_t count, std::vector<int32_t> &kids, int64_t *tips_out,
+                uint8_t *branching_out) {
     int64_t tips = 0;
     if (count > 1)
         for (int64_t k = 0; k < count; ++k) tips += f.taxon[base + k] >= 0;
-    f.leaf_offsets.push_back(f.leaf_offsets.back() + tips);
-    // internal nodes with a single child?  (children of k directly follow it in pre-order: count them)
-    std::vector<int32_t> kids(static_cast<size_t>(count), 0);
+    *tips_out = tips;
+    kids.assign(static_cast<size_t>(count), 0);
     for (int64_t k = 1; k < count; ++k) kids[f.parent[base + k]] += 1;
     bool branching = true;
     for (int64_t k = 0; k < count && branching; ++k) branching = f.taxon[base + k] >= 0 || kids[k] >= 2;
-    f.branching.push_back(branching ? 1 : 0);
+    *branching_out = branching ? 1 : 0;
 }
 
 }  // namespace
@@ -98,22 +99,39 @@ int scs_forest_create(int T, const int64_t *node_offsets, const int32_t *parent,
     else f->support.assign(M, std::nan(""));
     f->weight.assign(tree_weight, tree_weight + T);
     f->source.resize(T);
-    for (int t = 0; t < T; ++t) {
-        f->source[t] = t;
-        const int64_t base = node_offsets[t], count = node_offsets[t + 1] - base;
-        bool ok = count >= 1 && parent[base] == -1;
-        for (int64_t k = 1; ok && k < count; ++k) ok = parent[base + k] >= 0 && parent[base + k] < k;
-        for (int64_t k = 0; ok && k < count; ++k) {
-            const bool tip = is_tip(*f, base, count, k);
-            const int32_t x = taxon[base + k];
-            ok = tip ? (x >= 0 && x < num_taxa) : x == -1;
+    f->branching.assign(static_cast<size_t>(T), 1);
+    std::vector<int64_t> tips(static_cast<size_t>(T), 0);
+    bool all_ok = true;
+    // validation and shape of every tree: independent, over the host threads
+#pragma omp parallel if (M > kParallelNodes) num_threads(scs_host_threads())
+    {
+        std::vector<int32_t> kids;
+#pragma omp for schedule(dynamic, 8)
+        for (int t = 0; t < T; ++t) {
+            f->source[t] = t;
+            const int64_t base = node_offsets[t], count = node_offsets[t + 1] - base;
+            bool ok = count >= 1 && parent[base] == -1;
+            for (int64_t k = 1; ok && k < count; ++k) ok = parent[base + k] >= 0 && parent[base + k] < k;
+            for (int64_t k = 0; ok && k < count; ++k) {
+                const bool tip = is_tip(*f, base, count, k);
+                const int32_t x = taxon[base + k];
+                ok = tip ? (x >= 0 && x < num_taxa) : x == -1;
+            }
+            if (!ok) {
+#pragma omp atomic write
+                all_ok = false;
+                continue;
+            }
+            tree_shape(*f, base, count, kids, &tips[t], &f->branching[t]);
         }
-        if (!ok) {
-            delete f;
-            return SCS_ERR_INPUT;
-        }
-        finish_tree(*f, base, count);
     }
+    if (!all_ok) {
+        delete f;
+        return SCS_ERR_INPUT;
+    }
+    f->leaf_offsets.resize(static_cast<size_t>(T) + 1);
+    f->leaf_offsets[0] = 0;
+    for (int t = 0; t < T; ++t) f->leaf_offsets[t + 1] = f->leaf_offsets[t] + tips[t];
     *out = f;
     return SCS_OK;
 }
