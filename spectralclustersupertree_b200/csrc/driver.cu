@@ -115,6 +115,91 @@ struct Scratch {
     }
 };
 
+// ---- a batch of small nodes from host memory: staging area + run -------------------------------------------
+// The tours of the batch go through ONE pinned buffer and one H2D copy.  small_stage() sizes the buffer and
+// says where each array lives in it, so the driver can flatten the tours straight into pinned memory;
+// small_run() copies, launches small_batch_kernel and brings partitions and stats back.
+struct SmallStage {
+    size_t o_nodes = 0, o_off = 0, o_val = 0, o_w = 0, o_tax = 0, o_dep = 0, o_root = 0, total = 0;
+    unsigned char *base = nullptr;  // pinned host memory
+    scs_small_node *nodes() const { return reinterpret_cast<scs_small_node *>(base + o_nodes); }
+    int64_t *off() const { return reinterpret_cast<int64_t *>(base + o_off); }
+    double *val() const { return reinterpret_cast<double *>(base + o_val); }
+    double *w() const { return reinterpret_cast<double *>(base + o_w); }
+    int32_t *tax() const { return reinterpret_cast<int32_t *>(base + o_tax); }
+    int32_t *dep() const { return reinterpret_cast<int32_t *>(base + o_dep); }
+    int32_t *root() const { return reinterpret_cast<int32_t *>(base + o_root); }
+};
+
+int small_stage(scs_ctx *ctx, int num_nodes, int64_t L_total, int64_t T_total, SmallStage *st) {
+    const size_t nB = static_cast<size_t>(num_nodes), nL = static_cast<size_t>(L_total), nT = static_cast<size_t>(T_total);
+    st->o_nodes = 0;
+    st->o_off = st->o_nodes + nB * sizeof(scs_small_node);
+    st->o_val = st->o_off + (nT + nB) * sizeof(int64_t);
+    st->o_w = st->o_val + nL * sizeof(double);
+    st->o_tax = st->o_w + nT * sizeof(double);
+    st->o_dep = st->o_tax + nL * sizeof(int32_t);
+    st->o_root = st->o_dep + nL * sizeof(int32_t);
+    st->total = st->o_root + nT * sizeof(int32_t) + 64;
+    if (ctx->pinned_io_bytes < st->total) {
+        if (ctx->pinned_io) {
+            SCS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            SCS_CUDA(ctx, cudaFreeHost(ctx->pinned_io));
+            ctx->pinned_io = nullptr;
+            ctx->pinned_io_bytes = 0;
+        }
+        const size_t want = 2 * st->total + 4096;
+        SCS_CUDA(ctx, cudaMallocHost(&ctx->pinned_io, want));
+        ctx->pinned_io_bytes = want;
+    }
+    st->base = static_cast<unsigned char *>(ctx->pinned_io);
+    return SCS_OK;
+}
+
+int small_run(scs_ctx *ctx, int num_nodes, const SmallStage &st, int contract_edges, int32_t *part,
+              scs_node_stats *stats) {
+    int64_t N_total = 0;
+    const scs_small_node *nodes = st.nodes();
+    for (int b = 0; b < num_nodes; ++b) {
+        if (nodes[b].n < 1 || nodes[b].n > kSmallNode || nodes[b].num_trees < 0)
+            return fail(ctx, SCS_ERR_INVALID, "small batch: node size out of range");
+        N_total += nodes[b].n;
+    }
+    const size_t nB = static_cast<size_t>(num_nodes);
+    unsigned char *dev;
+    int rc;
+    if ((rc = reserve_as(ctx, SLOT_TOUR_OFFSETS, st.total, &dev))) return rc;
+    SCS_CUDA(ctx, cudaMemcpyAsync(dev, st.base, st.total - 64, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->h2d_bytes += static_cast<int64_t>(st.total - 64);
+
+    int32_t *part_dev, *bad_dev;
+    scs_node_stats *stats_dev;
+    if ((rc = reserve_as(ctx, SLOT_PART, static_cast<size_t>(N_total), &part_dev))) return rc;
+    if ((rc = reserve_as(ctx, SLOT_NODE_STATS, nB, &stats_dev))) return rc;
+    if ((rc = reserve_as(ctx, SLOT_SCALARS, 64, &bad_dev))) return rc;
+    SCS_CUDA(ctx, cudaMemsetAsync(bad_dev, 0, sizeof(int32_t), ctx->stream));
+    rc = small_batch(ctx, num_nodes, reinterpret_cast<const scs_small_node *>(dev + st.o_nodes),
+                     reinterpret_cast<const int64_t *>(dev + st.o_off), reinterpret_cast<const int32_t *>(dev + st.o_tax),
+                     reinterpret_cast<const int32_t *>(dev + st.o_dep), reinterpret_cast<const double *>(dev + st.o_val),
+                     reinterpret_cast<const int32_t *>(dev + st.o_root), reinterpret_cast<const double *>(dev + st.o_w),
+                     contract_edges, part_dev, stats_dev, bad_dev);
+    if (rc) return rc;
+    void *pin_v;
+    if ((rc = reserve_pinned(ctx, 64, &pin_v))) return rc;
+    SCS_CUDA(ctx, cudaMemcpyAsync(part, part_dev, sizeof(int32_t) * N_total, cudaMemcpyDeviceToHost, ctx->stream));
+    SCS_CUDA(ctx, cudaMemcpyAsync(stats, stats_dev, sizeof(scs_node_stats) * nB, cudaMemcpyDeviceToHost, ctx->stream));
+    SCS_CUDA(ctx, cudaMemcpyAsync(pin_v, bad_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SCS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->d2h_bytes += static_cast<int64_t>(sizeof(int32_t) * N_total + sizeof(scs_node_stats) * nB);
+    if (*static_cast<int32_t *>(pin_v) != 0) return fail(ctx, SCS_ERR_INPUT, "leaf tour: taxon id out of range");
+    for (int b = 0; b < num_nodes; ++b)
+        if (stats[b].solver == -1) {
+            stats[b].solver = 0;
+            return fail(ctx, SCS_ERR_TOO_SMALL, "spectral step on a graph contracted to one vertex");
+        }
+    return SCS_OK;
+}
+
 class Driver {
   public:
     Driver(scs_ctx *ctx, int weighting, int contract_edges, uint64_t seed, bool record, int rank, int world,
@@ -525,12 +610,11 @@ class Driver {
 #pragma omp atomic
             out_.pair_visits += visits;
         }
-        off_.resize(T_total + B);
-        tax_.resize(L_total + 1);
-        dep_.resize(L_total + 1);
-        val_.resize(L_total + 1);
-        root_.resize(T_total + 1);
-        wgt_.resize(T_total + 1);
+        // the tours are flattened straight into the pinned staging area of the batch
+        SmallStage stage;
+        int rc = small_stage(ctx, B, L_total, T_total, &stage);
+        if (rc) return rc;
+        std::memcpy(stage.nodes(), nodes.data(), sizeof(scs_small_node) * static_cast<size_t>(B));
         int tours_rc = SCS_OK;
         // next to the large nodes (own context) the host threads are shared with their workers: a small team
         const int tour_threads = ctx == ctx_ ? scs_host_threads() : std::max(1, std::min(4, scs_host_threads() / 4));
@@ -539,25 +623,22 @@ class Driver {
 #pragma omp parallel for schedule(dynamic, 8) if (B >= 32) num_threads(tour_threads)
             for (int b = 0; b < B; ++b) {
                 const scs_forest *f = wave[small[b]].forest;
-                const int rc = tours_of(f, wave[small[b]].taxa, scratch[static_cast<size_t>(omp_get_thread_num())].local,
-                                        off_.data() + nodes[b].tree_base + b, tax_.data() + nodes[b].leaf_base,
-                                        dep_.data() + nodes[b].leaf_base, val_.data() + nodes[b].leaf_base,
-                                        root_.data() + nodes[b].tree_base, wgt_.data() + nodes[b].tree_base);
-                if (rc) {
+                const int status = tours_of(f, wave[small[b]].taxa, scratch[static_cast<size_t>(omp_get_thread_num())].local,
+                                            stage.off() + nodes[b].tree_base + b, stage.tax() + nodes[b].leaf_base,
+                                            stage.dep() + nodes[b].leaf_base, stage.val() + nodes[b].leaf_base,
+                                            stage.root() + nodes[b].tree_base, stage.w() + nodes[b].tree_base);
+                if (status) {
 #pragma omp atomic write
-                    tours_rc = rc;
+                    tours_rc = status;
                 }
             }
         }
         if (tours_rc) return tours_rc;
         part_.resize(N_total);
         std::vector<scs_node_stats> stats(B);
-        int rc;
         {
             Stopwatch sw(&out_.seconds[1]);
-            rc = scs_nodes_split_small_host(ctx, B, nodes.data(), L_total, T_total, off_.data(), tax_.data(),
-                                            dep_.data(), val_.data(), root_.data(), wgt_.data(), contract_,
-                                            part_.data(), stats.data());
+            rc = small_run(ctx, B, stage, contract_, part_.data(), stats.data());
         }
         if (rc) return rc;
         out_.nodes_small += B;
@@ -692,9 +773,7 @@ class Driver {
     std::vector<int32_t> owner_;    // global taxon id -> restriction job of the current wave
     std::vector<uint8_t> present_;  // scratch of plan_wave (all zero between waves)
     std::vector<TourBuffers> buffers_;
-    std::vector<int64_t> off_;
-    std::vector<int32_t> tax_, dep_, root_, part_;
-    std::vector<double> val_, wgt_;
+    std::vector<int32_t> part_;
 };
 
 }  // namespace
@@ -709,81 +788,25 @@ int scs_nodes_split_small_host(scs_ctx *ctx, int num_nodes, const scs_small_node
                                int64_t T_total, const int64_t *leaf_offsets, const int32_t *leaf_taxon,
                                const int32_t *adj_depth, const double *adj_val, const int32_t *root_depth,
                                const double *tree_weight, int contract_edges, int32_t *part, scs_node_stats *stats) {
-    if (!ctx || num_nodes < 0 || !nodes || !part || !stats) return SCS_ERR_INVALID;
+    if (!ctx || num_nodes < 0 || !nodes || !part || !stats || L_total < 0 || T_total < 0) return SCS_ERR_INVALID;
     if (num_nodes == 0) return SCS_OK;
     cudaSetDevice(ctx->device);
-    int64_t N_total = 0;
-    for (int b = 0; b < num_nodes; ++b) {
-        if (nodes[b].n < 1 || nodes[b].n > kSmallNode || nodes[b].num_trees < 0)
-            return fail(ctx, SCS_ERR_INVALID, "small batch: node size out of range");
-        N_total += nodes[b].n;
-    }
-    // one pinned staging buffer, one H2D copy
+    SmallStage st;
+    int rc = small_stage(ctx, num_nodes, L_total, T_total, &st);
+    if (rc) return rc;
     const size_t nB = static_cast<size_t>(num_nodes), nL = static_cast<size_t>(L_total), nT = static_cast<size_t>(T_total);
-    const size_t b_nodes = nB * sizeof(scs_small_node);
-    const size_t b_off = (nT + nB) * sizeof(int64_t);
-    const size_t b_val = nL * sizeof(double);
-    const size_t b_w = nT * sizeof(double);
-    const size_t b_tax = nL * sizeof(int32_t);
-    const size_t b_dep = nL * sizeof(int32_t);
-    const size_t b_root = nT * sizeof(int32_t);
-    const size_t o_nodes = 0, o_off = o_nodes + b_nodes, o_val = o_off + b_off, o_w = o_val + b_val, o_tax = o_w + b_w,
-                 o_dep = o_tax + b_tax, o_root = o_dep + b_dep, total = o_root + b_root + 64;
-    if (ctx->pinned_io_bytes < total) {
-        if (ctx->pinned_io) {
-            SCS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            SCS_CUDA(ctx, cudaFreeHost(ctx->pinned_io));
-            ctx->pinned_io = nullptr;
-            ctx->pinned_io_bytes = 0;
-        }
-        const size_t want = 2 * total + 4096;
-        SCS_CUDA(ctx, cudaMallocHost(&ctx->pinned_io, want));
-        ctx->pinned_io_bytes = want;
-    }
-    unsigned char *stage = static_cast<unsigned char *>(ctx->pinned_io);
-    std::memcpy(stage + o_nodes, nodes, b_nodes);
-    std::memcpy(stage + o_off, leaf_offsets, b_off);
+    std::memcpy(st.nodes(), nodes, nB * sizeof(scs_small_node));
+    std::memcpy(st.off(), leaf_offsets, (nT + nB) * sizeof(int64_t));
     if (nL) {
-        std::memcpy(stage + o_val, adj_val, b_val);
-        std::memcpy(stage + o_tax, leaf_taxon, b_tax);
-        std::memcpy(stage + o_dep, adj_depth, b_dep);
+        std::memcpy(st.val(), adj_val, nL * sizeof(double));
+        std::memcpy(st.tax(), leaf_taxon, nL * sizeof(int32_t));
+        std::memcpy(st.dep(), adj_depth, nL * sizeof(int32_t));
     }
     if (nT) {
-        std::memcpy(stage + o_w, tree_weight, b_w);
-        std::memcpy(stage + o_root, root_depth, b_root);
+        std::memcpy(st.w(), tree_weight, nT * sizeof(double));
+        std::memcpy(st.root(), root_depth, nT * sizeof(int32_t));
     }
-    unsigned char *dev;
-    int rc;
-    if ((rc = reserve_as(ctx, SLOT_TOUR_OFFSETS, total, &dev))) return rc;
-    SCS_CUDA(ctx, cudaMemcpyAsync(dev, stage, total - 64, cudaMemcpyHostToDevice, ctx->stream));
-    ctx->h2d_bytes += static_cast<int64_t>(total - 64);
-
-    int32_t *part_dev, *bad_dev;
-    scs_node_stats *stats_dev;
-    if ((rc = reserve_as(ctx, SLOT_PART, static_cast<size_t>(N_total), &part_dev))) return rc;
-    if ((rc = reserve_as(ctx, SLOT_NODE_STATS, nB, &stats_dev))) return rc;
-    if ((rc = reserve_as(ctx, SLOT_SCALARS, 64, &bad_dev))) return rc;
-    SCS_CUDA(ctx, cudaMemsetAsync(bad_dev, 0, sizeof(int32_t), ctx->stream));
-    rc = small_batch(ctx, num_nodes, reinterpret_cast<const scs_small_node *>(dev + o_nodes),
-                     reinterpret_cast<const int64_t *>(dev + o_off), reinterpret_cast<const int32_t *>(dev + o_tax),
-                     reinterpret_cast<const int32_t *>(dev + o_dep), reinterpret_cast<const double *>(dev + o_val),
-                     reinterpret_cast<const int32_t *>(dev + o_root), reinterpret_cast<const double *>(dev + o_w),
-                     contract_edges, part_dev, stats_dev, bad_dev);
-    if (rc) return rc;
-    void *pin_v;
-    if ((rc = reserve_pinned(ctx, 64, &pin_v))) return rc;
-    SCS_CUDA(ctx, cudaMemcpyAsync(part, part_dev, sizeof(int32_t) * N_total, cudaMemcpyDeviceToHost, ctx->stream));
-    SCS_CUDA(ctx, cudaMemcpyAsync(stats, stats_dev, sizeof(scs_node_stats) * nB, cudaMemcpyDeviceToHost, ctx->stream));
-    SCS_CUDA(ctx, cudaMemcpyAsync(pin_v, bad_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    SCS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->d2h_bytes += static_cast<int64_t>(sizeof(int32_t) * N_total + sizeof(scs_node_stats) * nB);
-    if (*static_cast<int32_t *>(pin_v) != 0) return fail(ctx, SCS_ERR_INPUT, "leaf tour: taxon id out of range");
-    for (int b = 0; b < num_nodes; ++b)
-        if (stats[b].solver == -1) {
-            stats[b].solver = 0;
-            return fail(ctx, SCS_ERR_TOO_SMALL, "spectral step on a graph contracted to one vertex");
-        }
-    return SCS_OK;
+    return small_run(ctx, num_nodes, st, contract_edges, part, stats);
 }
 
 int scs_nodes_split_small_dev(scs_ctx *ctx, int num_nodes, const scs_small_node *nodes_dev,
