@@ -108,3 +108,60 @@ def test_many_lines_use_the_threaded_path():
         assert_same_forest(native, lines)
     finally:
         native.close()
+
+
+def test_random_newick_agrees_with_the_python_parser():
+    """Property test: random trees rendered with random spacing, quoting, comments, lengths and supports parse
+    to the same forest natively and through ``make_tree``."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    label = st.one_of(
+        st.sampled_from(["a", "b", "c", "d", "e", "f", "g", "t12", "x_1", "Homo sapiens", "it's", "7up", "1e3x"]),
+        st.text(alphabet="abcXYZ019_-.", min_size=1, max_size=6),
+    )
+    number = st.one_of(st.integers(0, 1000).map(str), st.floats(0, 50, allow_nan=False).map(lambda v: f"{v:.6g}"),
+                       st.sampled_from(["1e-3", "2.5E+1", ".5", "5.", "-0.25"]))  # fmt: skip
+
+    def quote(name: str, how: int) -> str:
+        plain = all(ch not in "(),:;[]'\" \t" for ch in name)
+        if how == 0 and plain:
+            return name
+        q = "'" if how != 2 else '"'
+        return q + name.replace(q, q + q) + q
+
+    @st.composite
+    def newick(draw, depth=0):
+        space = draw(st.sampled_from(["", "", " ", "\t", " [c] ", "[x[y]z]"]))
+        if depth >= 4 or draw(st.integers(0, 3)) == 0:
+            text = quote(draw(label), draw(st.integers(0, 2)))
+        else:
+            kids = [draw(newick(depth + 1)) for _ in range(draw(st.integers(1, 4)))]
+            text = "(" + ",".join(kids) + ")"
+            tag = draw(st.integers(0, 3))
+            if tag == 1:
+                text += draw(number)  # support
+            elif tag == 2:
+                text += quote("n" + draw(label), draw(st.integers(0, 2)))  # an internal name
+        if draw(st.booleans()):
+            text += space + ":" + space + draw(number)
+        return space + text + space
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.lists(newick(), min_size=1, max_size=5), st.booleans())
+    def check(trees, semicolon):
+        lines = [t + (";" if semicolon else "") for t in trees]
+        try:
+            for s in lines:
+                make_tree(s.strip())
+        except NewickError:
+            with pytest.raises(NewickError):
+                Forest.from_newick("\n".join(lines))
+            return
+        native = Forest.from_newick("\n".join(lines))
+        try:
+            assert_same_forest(native, lines)
+        finally:
+            native.close()
+
+    check()
