@@ -289,3 +289,43 @@ def test_pcg_wide_bucket_entries_bit_exact(engine):
     assert np.array_equal(out["W"], ref["W"])
     assert np.array_equal(out["C"], ref["C"])
     assert np.array_equal(out["occ"], ref["occ"])
+
+
+def test_full_size_workload_against_the_c_oracle(engine):
+    """BASELINE's 10 000-taxon x 1 000-tree workload, top-level recursion node: the whole W (10^8 entries), the
+    occurrences and the adjacency against the C oracle, plus the size-independent properties (symmetry, degree =
+    row sums, determinism of a second build)."""
+    import bench
+
+    arrays = bench.make_workload("c4")
+    n = len(arrays["names"])
+    roots, child_ptr, child_idx, tip_taxon, own = bench.oracle_children_csr(arrays)
+    W, C, occ = scs_oracle.pcg_dense_c_arrays(n, roots, child_ptr, child_idx, tip_taxon, own, arrays["weights"],
+                                              arrays["weighting"])  # fmt: skip
+    forest = Forest.from_arrays(arrays["node_offsets"], arrays["parent"], arrays["length"], arrays["support"],
+                                arrays["taxon"], arrays["weights"], arrays["names"])  # fmt: skip
+    try:
+        taxa, part, stats = engine.forest_split(forest, arrays["weighting"], seed=0)
+        got = engine.last_node_buffers()
+        assert np.array_equal(taxa, np.arange(n))
+        assert np.array_equal(got["W"], W)
+        assert np.array_equal(got["occ"], occ)
+        adjacency = unpack_bits(got["adj_bits"], n)
+        assert np.array_equal(adjacency, C > 0)
+        del C, adjacency
+        assert np.array_equal(got["W"], got["W"].T)
+        assert np.array_equal(got["degree"], W.sum(axis=1))  # depth weighting, unit weights: integers, any order
+        from scipy.sparse import csr_matrix
+        from scipy.sparse.csgraph import connected_components
+
+        # depth >= 1 wherever an edge exists; scipy numbers components by their smallest vertex, like the library
+        count, label = connected_components(csr_matrix(W > 0), directed=False)
+        assert stats.n_components == count
+        if count > 1:
+            assert np.array_equal(part, label)
+        engine.forest_split(forest, arrays["weighting"], seed=0)
+        again = engine.last_node_buffers()
+        assert np.array_equal(again["W"], got["W"])
+        assert np.array_equal(again["adj_bits"], got["adj_bits"])
+    finally:
+        forest.close()
