@@ -1,4 +1,4 @@
-"""``load_trees``: a line-separated Newick file -> list of trees (ref: src/sc_supertree/load.py:7-23)."""
+"""Reading source trees: ``load_trees`` (ref: src/sc_supertree/load.py:7-23) and its flat twin ``load_forest``."""
 
 from __future__ import annotations
 
@@ -9,21 +9,16 @@ from .tree import PhyloNode, make_tree
 
 
 def load_trees(source_tree_file: str | os.PathLike) -> list[PhyloNode]:
-    """Load a line-separated file of Newick-formatted trees.
+    """The trees of a file that holds one Newick string per line, in file order.
 
-    Parameters
-    ----------
-    source_tree_file : str | bytes | os.PathLike
-        The path to the source tree file.
-
-    Returns
-    -------
-    list[PhyloNode]
-        A list of all source trees in the file.
-
+    Same contract as the reference's ``load_trees``: every line is stripped and parsed on its own (an empty
+    line is a syntax error), and the result is a list of tree objects ready for ``construct_supertree``.
     """
-    with Path(source_tree_file).open() as f:
-        return [make_tree(line.strip()) for line in f]
+    trees: list[PhyloNode] = []
+    with Path(source_tree_file).open() as handle:
+        for line in handle:
+            trees.append(make_tree(line.strip()))
+    return trees
 
 
 def load_forest(source_tree_file: str | os.PathLike):
