@@ -201,6 +201,10 @@ int scs_set_host_threads(int threads);
 int scs_forest_create(int T, const int64_t *node_offsets, const int32_t *parent, const double *length,
                       const double *support, const int32_t *taxon, const double *tree_weight,
                       int num_taxa, scs_forest **out);
+/* Why the last scs_forest_create on this thread returned SCS_ERR_INPUT ("" if it did not): a malformed
+ * pre-order tree, or a taxon that labels two tips of one source tree (rejected: the graph kernels give every
+ * leaf of a tree its own column). */
+const char *scs_forest_last_error(void);
 int scs_forest_destroy(scs_forest *f);
 /* Newick text (one tree per line, as load_trees reads it: /root/reference/src/sc_supertree/load.py:21-22)
  * straight into a forest, without node objects.  Label rules are those of cogent3.make_tree that the

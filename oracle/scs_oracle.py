@@ -293,12 +293,30 @@ def construct_supertree(
     random_state: np.random.RandomState | None = None,
     use_c: bool = False,
     trace: list | None = None,
+    timers: dict | None = None,
+    node_hook=None,
+    defer: list | None = None,
+    defer_max_taxa: int = 0,
 ) -> PhyloNode:
     """CPU restatement of the reference's ``construct_supertree`` (ref: scs.py:18-174).
 
     ``trace``, when given, receives one dict per recursion node (sorted vertex names, number of
-    components, spectral partition) for node-by-node parity checks.
+    components, spectral partition) for node-by-node parity checks.  ``timers`` accumulates wall-clock
+    seconds per stage (``pcg``, ``components``, ``contract``, ``spectral``, ``induce``, ``hook``);
+    ``node_hook(record, Wc, side, groups)`` is called at every spectral node (its time goes to
+    ``hook`` and is therefore separable from the reference-equivalent work); if it returns an array, the
+    recursion continues with those labels instead of sklearn's.  ``defer`` (a list) makes the recursion stop
+    at components of at most ``defer_max_taxa`` taxa: a placeholder tip is put where the sub-problem's supertree
+    belongs and ``(placeholder, trees, weights)`` is appended (``construct_supertree_parallel`` solves them in a
+    process pool).
     """
+    import time as _time
+
+    def _lap(key, since):
+        if timers is not None:
+            timers[key] = timers.get(key, 0.0) + (_time.perf_counter() - since)
+        return _time.perf_counter()
+
     if random_state is None:
         random_state = np.random.RandomState()
     if len(trees) == 0:
@@ -334,23 +352,35 @@ def construct_supertree(
     names = sorted(all_names)
     taxon_id = {name: i for i, name in enumerate(names)}
     build = pcg_dense_c if use_c else pcg_dense
+    mark = _time.perf_counter()
     W, C, occ = build(trees, weights, pcg_weighting, taxon_id)
+    mark = _lap("pcg", mark)
     label = graph_components(C > 0)
     reps = np.unique(label)
+    mark = _lap("components", mark)
     record = {"names": names, "n_components": len(reps)}
     if len(reps) == 1:
         groups = np.arange(len(names), dtype=np.int32)
         Wc = W
         if contract_edges:
             groups, Wc, _ = contract_dense(W, C, occ)
+        mark = _lap("contract", mark)
         side = spectral_bipartition(Wc, random_state)
-        parts = [{names[v] for v in range(len(names)) if side[groups[v]] == s} for s in (0, 1)]
+        mark = _lap("spectral", mark)
         record["contracted_size"] = int(Wc.shape[0])
+        if node_hook is not None:
+            # the hook may return replacement labels (tools/oracle_run.py steers RNG-dependent k-means nodes)
+            replacement = node_hook(record, Wc, side, groups)
+            if replacement is not None:
+                side = replacement
+            mark = _lap("hook", mark)
+        parts = [{names[v] for v in range(len(names)) if side[groups[v]] == s} for s in (0, 1)]
         record["partition"] = [sorted(p) for p in parts]
     else:
         parts = [{names[v] for v in np.flatnonzero(label == r)} for r in reps]
     if trace is not None:
         trace.append(record)
+    del W, C
 
     child_trees: list[PhyloNode] = []
     for component in parts:
@@ -358,6 +388,7 @@ def construct_supertree(
             child_trees.append(_star(component))
             continue
         new_trees, new_weights = [], []
+        mark = _time.perf_counter()
         for tree, weight in zip(trees, weights, strict=True):  # ref: scs.py:444-453
             if len(component.intersection(tree.get_tip_names())) < 2:
                 continue
@@ -365,22 +396,108 @@ def construct_supertree(
             sub.name = "root"
             new_trees.append(sub)
             new_weights.append(weight)
-        child_trees.append(
-            construct_supertree(
-                new_trees,
-                new_weights,
-                pcg_weighting,
-                contract_edges=contract_edges,
-                random_state=random_state,
-                use_c=use_c,
-                trace=trace,
+        _lap("induce", mark)
+        if defer is not None and len(component) <= defer_max_taxa and len(new_trees) > 0:
+            placeholder = PhyloNode(f"__deferred_{len(defer)}__")
+            defer.append((placeholder, new_trees, new_weights))
+            child_trees.append(placeholder)
+        else:
+            child_trees.append(
+                construct_supertree(
+                    new_trees,
+                    new_weights,
+                    pcg_weighting,
+                    contract_edges=contract_edges,
+                    random_state=random_state,
+                    use_c=use_c,
+                    trace=trace,
+                    timers=timers,
+                    node_hook=node_hook,
+                    defer=defer,
+                    defer_max_taxa=defer_max_taxa,
+                )
             )
-        )
         seen: set[str] = set()
         for tree in new_trees:
             seen.update(tree.get_tip_names())
         child_trees.extend(_star((x,)) for x in sorted(component.difference(seen)))
     return _connect(child_trees)
+
+
+# ---- the same recursion with the independent sub-problems spread over the host cores ------------------
+# The reference is single-process (ref: scs.py:239 n_jobs=1); sub-problems below a split are independent
+# (ref: scs.py:139-166), so a CPU baseline "with all the host threads it can use" runs the top of the recursion
+# serially (its BLAS calls use every core) and hands the components of at most ``defer_max_taxa`` taxa to a pool
+# of forked worker processes.  Used by bench.py's reference arm only.
+_DEFERRED: list = []
+_DEFERRED_ARGS: dict = {}
+
+
+def _solve_deferred(index: int):
+    import time as _time
+
+    _placeholder, trees, weights = _DEFERRED[index]
+    timers: dict = {}
+    trace: list = []
+    t0 = _time.perf_counter()
+    try:
+        from threadpoolctl import threadpool_limits
+
+        limiter = threadpool_limits(limits=1)  # one BLAS thread per worker process
+    except Exception:  # noqa: BLE001
+        limiter = None
+    tree = construct_supertree(
+        trees, weights, _DEFERRED_ARGS["weighting"], contract_edges=_DEFERRED_ARGS["contract_edges"],
+        random_state=np.random.RandomState(1 + index), use_c=True, trace=trace, timers=timers,
+    )  # fmt: skip
+    if limiter is not None:
+        limiter.restore_original_limits()
+    spectral = sum(1 for r in trace if "partition" in r)
+    return index, tree.get_newick(), len(trace), spectral, timers, _time.perf_counter() - t0
+
+
+def construct_supertree_parallel(trees, weights, pcg_weighting: str, *, contract_edges: bool = True,
+                                 workers: int = 0, defer_max_taxa: int = 1500, timers: dict | None = None,
+                                 info: dict | None = None) -> PhyloNode:  # fmt: skip
+    """``construct_supertree`` with sub-problems of at most ``defer_max_taxa`` taxa solved by ``workers`` forked
+    processes (0 = one per host core).  Same algorithm per node; the RNG stream of a sub-problem is seeded by
+    its index instead of continuing the parent's."""
+    import multiprocessing as mp
+    import os
+
+    from spectralclustersupertree_b200.tree import make_tree
+
+    global _DEFERRED, _DEFERRED_ARGS  # noqa: PLW0603
+    workers = workers or (os.cpu_count() or 1)
+    deferred: list = []
+    trace: list = []
+    top = construct_supertree(
+        trees, weights, pcg_weighting, contract_edges=contract_edges, random_state=np.random.RandomState(0),
+        use_c=True, trace=trace, timers=timers, defer=deferred, defer_max_taxa=defer_max_taxa,
+    )  # fmt: skip
+    nodes, spectral = len(trace), sum(1 for r in trace if "partition" in r)
+    pool_timers: dict = {}
+    if deferred:
+        _DEFERRED = deferred
+        _DEFERRED_ARGS = {"weighting": pcg_weighting, "contract_edges": contract_edges}
+        order = sorted(range(len(deferred)), key=lambda i: -sum(len(t.get_tip_names()) for t in deferred[i][1]))
+        with mp.get_context("fork").Pool(min(workers, len(deferred))) as pool:
+            for index, newick, n_nodes, n_spectral, part_timers, _seconds in pool.imap_unordered(_solve_deferred, order):
+                sub = make_tree(newick)
+                placeholder = deferred[index][0]
+                placeholder.name = sub.name
+                placeholder.children = []
+                for child in list(sub.children):
+                    placeholder.append(child)
+                nodes += n_nodes
+                spectral += n_spectral
+                for key, value in part_timers.items():
+                    pool_timers[key] = pool_timers.get(key, 0.0) + value
+        _DEFERRED = []
+    if info is not None:
+        info.update({"recursion_nodes": nodes, "spectral_nodes": spectral, "deferred_subproblems": len(deferred),
+                     "workers": workers, "pool_cpu_seconds": pool_timers})  # fmt: skip
+    return top
 
 
 def _star(names) -> PhyloNode:

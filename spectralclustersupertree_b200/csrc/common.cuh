@@ -193,6 +193,7 @@ int reserve_pinned(scs_ctx *ctx, size_t bytes, void **out);
 
 enum ProfileKind : int { PROFILE_MATVEC = 0, PROFILE_PCG_ROWS = 1, PROFILE_KINDS = 2 };
 constexpr int kSmallNode = 64;  // recursion nodes up to this many vertices take the one-CTA path (small.cu)
+constexpr int kSmallMaxTrees = 65535;  // ... if they have at most this many source trees (16-bit co-occurrence counts)
 // the per-launch roofline timers cover the launches whose matrix exceeds the 126 MB L2 (8 n^2 bytes > L2 from
 // n = 3969); smaller matrices stay L2-resident across the matvecs of a Lanczos run: no HBM roofline there
 constexpr int kProfileMinSize = 4096;

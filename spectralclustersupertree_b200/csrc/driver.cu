@@ -163,6 +163,8 @@ int small_run(scs_ctx *ctx, int num_nodes, const SmallStage &st, int contract_ed
     for (int b = 0; b < num_nodes; ++b) {
         if (nodes[b].n < 1 || nodes[b].n > kSmallNode || nodes[b].num_trees < 0)
             return fail(ctx, SCS_ERR_INVALID, "small batch: node size out of range");
+        if (nodes[b].num_trees > kSmallMaxTrees)
+            return fail(ctx, SCS_ERR_INVALID, "small batch: more than 65 535 source trees at a node (use scs_node_split_*)");
         N_total += nodes[b].n;
     }
     const size_t nB = static_cast<size_t>(num_nodes);
@@ -417,7 +419,7 @@ class Driver {
                 fill_star(task.slot, task.taxa.data(), n, task.shared);
                 continue;
             }
-            if (n <= ctx_->small_limit) {
+            if (n <= ctx_->small_limit && T <= kSmallMaxTrees) {
                 small.push_back(i);
                 continue;
             }
@@ -430,7 +432,11 @@ class Driver {
             std::vector<SplitResult> small_results;
             int small_rc = SCS_OK;
             std::thread helper([&] {
-                cudaSetDevice(ctx_->device);
+                const cudaError_t err = cudaSetDevice(ctx_->device);
+                if (err != cudaSuccess) {
+                    small_rc = fail(small_ctx_, SCS_ERR_CUDA, "cudaSetDevice (small-node thread)", err);
+                    return;
+                }
                 small_rc = split_small(small_ctx_, scratch_small_, wave, small, small_results);
             });
             rc = split_large_all(wave, results);
@@ -550,9 +556,11 @@ class Driver {
         for (int i = 0; i < jobs; ++i) {
             const int w = omp_get_thread_num();
             scs_ctx *ctx = w == 0 ? ctx_ : ctx_->workers[w - 1];
-            cudaSetDevice(ctx->device);
             SplitResult &res = results[concurrent[i]];
-            const int status = split_large(ctx, buffers_[w], scratch_[w], wave[res.task], res);
+            const cudaError_t dev_err = cudaSetDevice(ctx->device);
+            const int status = dev_err != cudaSuccess
+                                   ? fail(ctx, SCS_ERR_CUDA, "cudaSetDevice (node worker thread)", dev_err)
+                                   : split_large(ctx, buffers_[w], scratch_[w], wave[res.task], res);
             if (status) {
                 if (ctx != ctx_) ctx_->last_error = ctx->last_error;
 #pragma omp atomic write

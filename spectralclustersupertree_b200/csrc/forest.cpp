@@ -31,6 +31,7 @@
 #include <omp.h>
 
 static int g_host_threads = 0;
+static thread_local const char *g_forest_error = "";
 
 int scs_host_threads() { return g_host_threads > 0 ? g_host_threads : omp_get_max_threads(); }
 
@@ -101,25 +102,38 @@ int scs_forest_create(int T, const int64_t *node_offsets, const int32_t *parent,
     f->source.resize(T);
     f->branching.assign(static_cast<size_t>(T), 1);
     std::vector<int64_t> tips(static_cast<size_t>(T), 0);
-    bool all_ok = true;
+    bool all_ok = true, repeated = false;
+    g_forest_error = "";
     // validation and shape of every tree: independent, over the host threads
 #pragma omp parallel if (M > kParallelNodes) num_threads(scs_host_threads())
     {
         std::vector<int32_t> kids;
+        // a taxon may label one tip of a tree only: the graph kernels give every leaf of a tree its own column
+        // and add to it without atomics (pcg.cu, small.cu)
+        std::vector<int32_t> seen_in(static_cast<size_t>(num_taxa > 0 ? num_taxa : 1), -1);
 #pragma omp for schedule(dynamic, 8)
         for (int t = 0; t < T; ++t) {
             f->source[t] = t;
             const int64_t base = node_offsets[t], count = node_offsets[t + 1] - base;
             bool ok = count >= 1 && parent[base] == -1;
             for (int64_t k = 1; ok && k < count; ++k) ok = parent[base + k] >= 0 && parent[base + k] < k;
+            bool twice = false;
             for (int64_t k = 0; ok && k < count; ++k) {
                 const bool tip = is_tip(*f, base, count, k);
                 const int32_t x = taxon[base + k];
                 ok = tip ? (x >= 0 && x < num_taxa) : x == -1;
+                if (ok && tip) {
+                    if (seen_in[x] == t) twice = true;
+                    seen_in[x] = t;
+                }
             }
-            if (!ok) {
+            if (!ok || twice) {
 #pragma omp atomic write
                 all_ok = false;
+                if (twice) {
+#pragma omp atomic write
+                    repeated = true;
+                }
                 continue;
             }
             tree_shape(*f, base, count, kids, &tips[t], &f->branching[t]);
@@ -127,6 +141,8 @@ int scs_forest_create(int T, const int64_t *node_offsets, const int32_t *parent,
     }
     if (!all_ok) {
         delete f;
+        g_forest_error = repeated ? "a taxon labels more than one tip of a source tree"
+                                  : "a source tree is not a valid pre-order tree (parent indices / tip taxa)";
         return SCS_ERR_INPUT;
     }
     f->leaf_offsets.resize(static_cast<size_t>(T) + 1);
@@ -135,6 +151,8 @@ int scs_forest_create(int T, const int64_t *node_offsets, const int32_t *parent,
     *out = f;
     return SCS_OK;
 }
+
+const char *scs_forest_last_error(void) { return g_forest_error; }
 
 int scs_forest_destroy(scs_forest *f) {
     delete f;

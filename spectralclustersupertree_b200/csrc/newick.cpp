@@ -260,7 +260,8 @@ int scs_forest_parse_newick(const char *text, size_t bytes, scs_forest **out, ch
     const int rc = scs_forest_create(T, offsets.data(), parent.data(), length.data(), support.data(), taxon.data(),
                                      weight.data(), static_cast<int>(names.size()), out);
     if (rc) {
-        g_parse_error = "the parsed trees are not a valid forest";
+        g_parse_error = scs_forest_last_error();
+        if (g_parse_error.empty()) g_parse_error = "the parsed trees are not a valid forest";
         return rc;
     }
     size_t total = 0;

@@ -447,6 +447,16 @@ small_batch_kernel(const scs_small_node *__restrict__ nodes, const int64_t *__re
     const int tid = threadIdx.x;
     const scs_small_node node = nodes[blockIdx.x];
     const int n = node.n;
+    if (node.num_trees > kSmallMaxTrees || n < 1 || n > kN) {
+        // the co-occurrence counts are 16-bit here (the staged path switches to 32-bit counts at 65 536 trees,
+        // pcg.cu `narrow`); the host entry points route such nodes to the staged path -- refuse loudly if one
+        // arrives anyway
+        if (tid == 0) {
+            *bad = 1;
+            stats[blockIdx.x].solver = -1;
+        }
+        return;
+    }
     for (int e = tid; e < n * n; e += kThreads) {
         S.A[e / n][e % n] = 0.0;
         S.cnt[e / n][e % n] = 0;

@@ -491,7 +491,7 @@ class Forest:
             len(names), ctypes.byref(handle),
         )  # fmt: skip
         if status != _lib.SCS_OK:
-            raise ScsError(status, "scs_forest_create")
+            raise ScsError(status, "scs_forest_create: " + lib.scs_forest_last_error().decode())
         return cls(handle, names)
 
     @classmethod

@@ -9,7 +9,7 @@ import json
 import numpy as np
 import pytest
 
-from helpers import GOLDEN, compare_with_reference_trace, kat_cases, load_case, parse, rf
+from helpers import GOLDEN, compare_with_reference_trace, kat_cases, load_case, parse, rf, rf_outside
 from spectralclustersupertree_b200 import construct_supertree, load_trees
 from spectralclustersupertree_b200.tree import NotCompleted, make_tree
 
@@ -37,8 +37,8 @@ def test_reference_fixtures(engine, name):
 
 @pytest.mark.parametrize(
     "name",
-    ["dcm", "dcm_iq", "supertriplets", "c1_100x30_depth", "c2_500x50_branch", "s_200x40_bootstrap",
-     "s_300x40_branch_weighted", "s_150x40_one"],
+    ["dcm", "dcm_iq", "supertriplets", "c1_100x30_depth", "c2_500x50_branch", "c3_1000x100_branch_weighted",
+     "s_200x40_bootstrap", "s_300x40_branch_weighted", "s_150x40_one"],
 )  # fmt: skip
 def test_node_by_node_against_reference_trace(engine, name):
     case = load_case(name)
@@ -46,18 +46,22 @@ def test_node_by_node_against_reference_trace(engine, name):
     tree = construct_supertree(
         parse(case["lines"]), case["weights"], case["weighting"], engine=engine, trace=trace
     )
-    report = compare_with_reference_trace(trace, case["nodes"])
+    report = compare_with_reference_trace(trace, case["nodes"], name)
     by_names = {tuple(r["names"]): r for r in case["nodes"]}
     for rec in trace:
         ref = by_names.get(tuple(rec["names"]))
         if ref is None or "eigenvalues" not in ref or rec["contracted_size"] < 3:
             continue
-        assert abs(rec["stats"]["eig"][1] - ref["eigenvalues"][1]) < 1e-6, rec["names"]
+        assert abs(rec["stats"]["eig"][1] - ref["eigenvalues"][1]) < 1e-6, rec["names"]  # Fiedler eigenvalue: 1e-6
     assert sorted(tree.get_tip_names()) == case["names"]
-    if report["tie_divergences"] == 0:
+    reference = make_tree(case["supertree"])
+    divergent = report.pop("divergent_sets")
+    # the supertrees may differ only below a recorded divergence (RF = 0 when there is none)
+    assert rf_outside(tree, reference, divergent) == 0
+    if not divergent:
         assert len(trace) == len(case["nodes"])
-        assert rf(tree, make_tree(case["supertree"])) == 0
-    print(name, report)
+        assert rf(tree, reference) == 0
+    print(name, {k: v for k, v in report.items() if k != "divergent_nodes"}, "RF", rf(tree, reference))
 
 
 def test_argument_errors(engine):
@@ -186,7 +190,7 @@ def test_batched_small_nodes_are_bit_exact(engine):
     fused: list = []
     construct_supertree(trees, case["weights"], case["weighting"], engine=engine, trace=fused)
     ref = load_case("s_300x40_branch_weighted")["nodes"]
-    report = compare_with_reference_trace(fused, ref)
+    report = compare_with_reference_trace(fused, ref, "s_300x40_branch_weighted")
     assert report["compared"] >= 100
 
 

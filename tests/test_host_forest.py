@@ -180,3 +180,15 @@ def test_induce_parts_keeps_whole_trees_verbatim():
     # again: part 0's forest split into {a, b} | {c, d, e}; its whole-tree copies are restricted for real now
     again = np.array([0 if x in "ab" else (1 if x in "cde" else -1) for x in names], dtype=np.int32)
     check(first[0], again, 2)
+
+
+def test_a_taxon_on_two_tips_of_one_tree_is_rejected():
+    """The graph kernels give every leaf of a tree its own column (no atomics on W): a source tree that
+    carries the same taxon twice is refused when the forest is made, with a message saying so."""
+    from spectralclustersupertree_b200.engine import ScsError
+
+    trees = [make_tree("((a,b),(c,d));"), make_tree("(a,a,(b,c));")]
+    with pytest.raises(ScsError, match="more than one tip"):
+        Forest.from_trees(trees, [1.0, 1.0])
+    with pytest.raises(Exception, match="more than one tip"):
+        Forest.from_newick("((a,b),(c,d));\n(a,a,(b,c));\n")

@@ -56,7 +56,7 @@ def test_syntax_corner_cases():
         "  ( (a , b)[a comment [nested]] , ( c , \"it''s\" ) ) ;",  # whitespace, comments, the other quote
         "(a:1,(b:0,c:-0.5)100.0:1E2);",  # zero / negative lengths, float support
         "a;",  # a lone tip
-        "((,),x);",  # unnamed tips
+        "((,y),x);",  # an unnamed tip (two of them would be the same taxon twice: rejected)
         "(a,b)",  # no terminating ';'
         "('a''b':+.5,b:5.);",
     ]
@@ -152,10 +152,14 @@ def test_random_newick_agrees_with_the_python_parser():
     def check(trees, semicolon):
         lines = [t + (";" if semicolon else "") for t in trees]
         try:
-            for s in lines:
-                make_tree(s.strip())
+            parsed = [make_tree(s.strip()) for s in lines]
         except NewickError:
             with pytest.raises(NewickError):
+                Forest.from_newick("\n".join(lines))
+            return
+        if any(len(set(t.get_tip_names())) != len(t.get_tip_names()) for t in parsed):
+            # the same taxon on two tips of one tree: refused when the forest is made
+            with pytest.raises(NewickError, match="more than one tip"):
                 Forest.from_newick("\n".join(lines))
             return
         native = Forest.from_newick("\n".join(lines))

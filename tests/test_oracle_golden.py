@@ -7,7 +7,7 @@ from __future__ import annotations
 import numpy as np
 import pytest
 
-from helpers import CASES, compare_with_reference_trace, kat_cases, load_case, parse, rf
+from helpers import CASES, compare_with_reference_trace, kat_cases, load_case, parse, rf, rf_outside
 from oracle import scs_oracle
 from spectralclustersupertree_b200.tree import make_tree
 
@@ -67,8 +67,9 @@ def test_oracle_recursion_matches_reference_trace(name):
         parse(case["lines"]), case["weights"], case["weighting"], random_state=np.random.RandomState(0),
         use_c=True, trace=trace,
     )  # fmt: skip
-    report = compare_with_reference_trace(trace, case["nodes"])
-    if report["tie_divergences"] == 0:
+    report = compare_with_reference_trace(trace, case["nodes"], name)
+    assert rf_outside(tree, make_tree(case["supertree"]), report["divergent_sets"]) == 0
+    if not report["divergent_sets"]:
         assert len(trace) == len(case["nodes"])
         assert rf(tree, make_tree(case["supertree"])) == 0
     if case["expected"] is not None:
