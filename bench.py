@@ -18,9 +18,15 @@ is quoted on).  Three clocks are reported in one JSON line:
 * ``roofline`` -- the Laplacian matvec (the kernel BASELINE.json's metric names), timed per launch
   with CUDA events inside the timed steps, against the measured HBM peak.
 
-``cpu_baseline`` / ``--impl reference`` time the CPU oracle port of the reference (oracle/: the
-reference is pure Python and needs cogent3, which is not installable here -- DESIGN.md) on a bounded
-sample: the job's top-level recursion node.
+``--impl reference`` times the CPU oracle port of the reference (oracle/: the reference is pure Python
+and needs cogent3, which is not installable here -- DESIGN.md) on the WHOLE job: every step is one full
+``construct_supertree`` recursion of the same workload on the host cores (C graph build, numpy components
+and contraction, sklearn ``SpectralClustering`` called as the reference calls it, Python tree restriction;
+independent sub-problems spread over a pool of worker processes).  Nothing is extrapolated: the value is a
+measured wall time.  Because one such run takes minutes at c4, the number of timed runs is capped by
+``--reference-budget-s`` (at least one is always timed; ``steps_timed`` says how many).
+``cpu_baseline`` in the GPU arm's line is the same measurement when the whole job fits the bounded-sample
+budget (c1-c3), else the job's top-level recursion node alone, reported as what it is: a lower bound.
 """
 
 from __future__ import annotations
@@ -42,10 +48,9 @@ if str(ROOT) not in sys.path:
 
 METRIC = "construct_supertree wall-time at 10k taxa/1k trees"
 PROFILE_MIN_N = 4096  # csrc/common.cuh kProfileMinSize: launches timed one by one (matrices larger than L2)
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the matvec (one CTA per row) at m = 8765, from the
-# round-1 `ncu --set full` capture (profiles/r01_ncu_full_matvec_final_raw.csv); algorithmic bytes 614.8 MB
-NCU_MATVEC_TRAFFIC = {"bytes_per_launch": 618.2e6, "algorithmic_bytes": 614.8e6, "m": 8765,
-                      "source": "profiles/r01_ncu_full_matvec_final_raw.csv"}
+# dram__bytes_read.sum + dram__bytes_write.sum of one matvec launch, read from the summary tools/ncu_summary.py
+# writes from this round's `ncu --set full` capture (null when no capture has been summarised)
+NCU_TRAFFIC_FILE = ROOT / "profiles" / "r02_ncu_matvec_traffic.json"
 
 # name -> (taxa, trees, weighting, seed, tree weights)   (BASELINE.json configs; seed = 1000 * index)
 WORKLOADS = {
@@ -197,17 +202,6 @@ def oracle_top_node(arrays: dict) -> dict:
         _, Wc, _ = scs_oracle.contract_dense(W, C, occ)
         spectral_n = Wc.shape[0]
         scs_oracle.spectral_bipartition(Wc, np.random.RandomState(0))
-    else:
-        # the graph is disconnected at the top: the spectral stage first runs one level down, on
-        # the largest component; time sklearn on that component's graph so the sample covers it
-        sizes = np.bincount(label)
-        big = np.flatnonzero(label == np.argmax(sizes))
-        if len(big) >= 3:
-            sub = np.ix_(big, big)
-            _, Wc, _ = scs_oracle.contract_dense(W[sub], C[sub], occ[big])
-            if Wc.shape[0] >= 2 and len(np.unique(scs_oracle.graph_components(Wc > 0))) == 1:
-                spectral_n = Wc.shape[0]
-                scs_oracle.spectral_bipartition(Wc, np.random.RandomState(0))
     t3 = time.perf_counter()
     return {
         "seconds": t3 - t0,
@@ -220,47 +214,66 @@ def oracle_top_node(arrays: dict) -> dict:
     }
 
 
-def workload_ratio(workload: str) -> dict | None:
-    """Whole-job / top-level-node work ratio recorded by a GPU run (profiles/workloads.json)."""
-    path = ROOT / "profiles" / "workloads.json"
-    if not path.is_file():
-        return None
-    return json.loads(path.read_text()).get(workload)
-
-
 def cpu_threads() -> int:
-    try:
-        from threadpoolctl import threadpool_info
-
-        return max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
-    except Exception:  # noqa: BLE001
-        return os.cpu_count() or 1
+    return os.cpu_count() or 1
 
 
-def reference_line(args, arrays: dict) -> dict:
-    """``--impl reference``: the CPU oracle port, each step = the bounded sample."""
+def oracle_whole_job(workload: str) -> dict:
+    """One full ``construct_supertree`` recursion of the workload on the CPU oracle port, measured.
+
+    The trees are handed over as ``PhyloNode`` objects (built outside the timed region, as the reference
+    receives them); the top of the recursion runs in this process (its BLAS calls use every core), components of
+    at most 1 500 taxa are solved by a pool of forked worker processes, one per host core."""
+    from oracle import scs_oracle
+    from spectralclustersupertree_b200.synthetic import make_problem
+
+    n, t, weighting, seed, tw = WORKLOADS[workload]
+    prob = make_problem(n, t, weighting, seed, tree_weights=tw)
+    trees = prob.phylonodes()
+    weights = [1.0] * len(trees) if prob.weights is None else list(prob.weights)
+    scs_oracle._c_lib()
+    timers: dict = {}
+    info: dict = {}
+    t0 = time.perf_counter()
+    tree = scs_oracle.construct_supertree_parallel(trees, weights, weighting, workers=cpu_threads(),
+                                                   defer_max_taxa=1500, timers=timers, info=info)  # fmt: skip
+    seconds = time.perf_counter() - t0
+    return {"seconds": seconds, "top_stage_seconds": timers, "tips": len(tree.get_tip_names()), **info}
+
+
+def whole_job_sample(workload: str, detail: dict) -> str:
+    top = ", ".join(f"{k} {v:.1f}" for k, v in detail["top_stage_seconds"].items())
+    return (
+        f"the whole {workload} job, measured: every one of its {detail['recursion_nodes']} recursion nodes "
+        f"({detail['spectral_nodes']} through sklearn SpectralClustering) on the CPU oracle port -- C graph build, "
+        f"numpy components/contraction, Python tree restriction; serial part (nodes > 1500 taxa) [{top}] s, "
+        f"{detail['deferred_subproblems']} sub-problems over {detail['workers']} worker processes"
+    )
+
+
+def reference_line(args) -> dict:
+    """``--impl reference``: the CPU oracle port on the whole job; every step is a full measured run."""
     times = []
     detail = {}
-    warmup = min(args.warmup, 1)  # a 30-second CPU sample needs no more than one untimed pass
-    for i in range(warmup + args.steps):
-        detail = oracle_top_node(arrays)
-        if i >= warmup:
-            times.append(detail["seconds"])
-    sample_s = statistics.mean(times)
-    ratio = workload_ratio(args.workload)
-    scale = ratio["pair_visits_total"] / ratio["pair_visits_top"] if ratio else 1.0
-    value = sample_s * scale
-    sample = (
-        f"top-level recursion node of {args.workload} (C oracle graph build over all trees {detail['pcg_s']:.1f} s, "
-        f"components {detail['components_s']:.1f} s, contraction + sklearn SpectralClustering on "
-        f"{detail['spectral_n']} vertices {detail['spectral_s']:.1f} s) = {sample_s:.1f} s measured; "
-        f"whole job extrapolated x{scale:.2f} by leaf-pair updates over all recursion nodes"
-    )
+    budget = args.reference_budget_s
+    started = time.perf_counter()
+    first = oracle_whole_job(args.workload)  # doubles as the warm-up when there is time for more
+    runs_fit = int(budget // max(first["seconds"], 1e-9))
+    if args.warmup == 0 or runs_fit < 2:
+        times.append(first["seconds"])
+        detail = first
+    for _ in range(args.steps - len(times)):
+        if time.perf_counter() - started + first["seconds"] > budget:
+            break
+        detail = oracle_whole_job(args.workload)
+        times.append(detail["seconds"])
+    value = statistics.mean(times)
+    sample = whole_job_sample(args.workload, detail) + f"; {len(times)} full run(s) timed within the {budget:.0f} s budget"
     cores = cpu_threads()
     return {
         "metric": METRIC, "value": value, "unit": "s", "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": sample_s * 1e3, "higher_is_better": False, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "steps_timed": len(times), "warmup": args.warmup, "ms_per_step": value * 1e3, "higher_is_better": False,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": describe(args.workload)},
         "cpu_baseline": {"value": value, "unit": "s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -376,6 +389,35 @@ def gather_supertree(dist, built: dict, local_rank: int):
         host = everyone[r].cpu().numpy()
         parts.append((host[0, :count], host[1, :count], prefix))
     return merge_sharded(parts)
+
+
+def profile_step(args, arrays: dict) -> dict:
+    """One product-path job inside a cudaProfilerStart/Stop bracket (the step ncu captures)."""
+    from spectralclustersupertree_b200 import _lib
+    from spectralclustersupertree_b200.engine import Engine, Forest, set_host_threads
+
+    engine = Engine(0)
+    set_host_threads(max(1, min(16, os.cpu_count() or 1)))
+    lib = _lib.load()
+
+    def forest():
+        return Forest.from_arrays(arrays["node_offsets"], arrays["parent"], arrays["length"], arrays["support"],
+                                  arrays["taxon"], arrays["weights"], arrays["names"])  # fmt: skip
+
+    engine.supertree_build(forest(), arrays["weighting"])  # warm-up: workspaces sized, modules loaded
+    engine.synchronize()
+    before = engine.launch_count
+    lib.scs_profiler_range(1)
+    t0 = time.perf_counter()
+    built = engine.supertree_build(forest(), arrays["weighting"])
+    engine.synchronize()
+    seconds = time.perf_counter() - t0
+    lib.scs_profiler_range(0)
+    out = {"workload": describe(args.workload), "step_seconds_under_profiler": seconds,
+           "gpu_launches_in_step": int(engine.launch_count - before), "waves": built["waves"],
+           "nodes_small": built["nodes_small"], "nodes_large": built["nodes_large"]}  # fmt: skip
+    engine.close()
+    return out
 
 
 def gpu_line(args, arrays: dict) -> dict:
@@ -518,12 +560,13 @@ def gpu_line(args, arrays: dict) -> dict:
             "avg_launch_us": 1e3 * matvec["ms"] / matvec["launches"],
             "bytes_per_launch": matvec["bytes"] / matvec["launches"],
             "share_of_step": matvec["ms"] / sum(dev_ms),
-            # DRAM bytes per launch: the ncu capture's traffic / algorithmic ratio (m = 8765 launch) applied to
-            # this run's average launch
-            "traffic": matvec["bytes"] / matvec["launches"] * NCU_MATVEC_TRAFFIC["bytes_per_launch"]
-            / NCU_MATVEC_TRAFFIC["algorithmic_bytes"],
-            "traffic_detail": NCU_MATVEC_TRAFFIC,
         })  # fmt: skip
+        # DRAM bytes of one launch as ncu measured them (dram__bytes_read.sum + dram__bytes_write.sum of this
+        # round's `ncu --set full` capture of the largest matvec launch of this workload); null without a capture
+        if NCU_TRAFFIC_FILE.is_file():
+            captured = json.loads(NCU_TRAFFIC_FILE.read_text())
+            roofline["traffic"] = captured.get("dram_bytes_per_launch")
+            roofline["traffic_detail"] = captured
     roofline_rows = None
     if rows["launches"] and rows["ms"] > 0:
         visits = sum(v for (t, _), v in zip(mine, replay.pair_visits, strict=True) if t.n >= PROFILE_MIN_N) * args.steps
@@ -564,17 +607,23 @@ def gpu_line(args, arrays: dict) -> dict:
         "roofline_pcg_rows": roofline_rows,
     }  # fmt: skip
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        detail = oracle_top_node(arrays)
-        scale = job["pair_visits_total"] / max(job["pair_visits_top"], 1)
-        line["cpu_baseline"] = {
-            "value": detail["seconds"] * scale, "unit": "s", "cores": cpu_threads(), "kind": "port",
-            "sample": (
-                f"top-level recursion node of {args.workload} on the CPU oracle (C graph build {detail['pcg_s']:.1f} s, "
-                f"components {detail['components_s']:.1f} s, contraction + sklearn SpectralClustering on "
-                f"{detail['spectral_n']} vertices {detail['spectral_s']:.1f} s) = {detail['seconds']:.1f} s measured; "
-                f"whole job extrapolated x{scale:.2f} by leaf-pair updates over all recursion nodes"
-            ),
-        }  # fmt: skip
+        if args.workload in ("c1", "c2", "c3"):
+            # the whole job fits the bounded-sample budget: measured end to end
+            detail = oracle_whole_job(args.workload)
+            line["cpu_baseline"] = {"value": detail["seconds"], "unit": "s", "cores": cpu_threads(), "kind": "port",
+                                    "sample": whole_job_sample(args.workload, detail)}  # fmt: skip
+        else:
+            detail = oracle_top_node(arrays)
+            line["cpu_baseline"] = {
+                "value": detail["seconds"], "unit": "s", "cores": cpu_threads(), "kind": "port",
+                "sample": (
+                    f"LOWER BOUND -- one of the job's {job['recursion_nodes']} recursion nodes only: the top-level node of "
+                    f"{args.workload} on the CPU oracle port (C graph build {detail['pcg_s']:.1f} s, components "
+                    f"{detail['components_s']:.1f} s, contraction + sklearn SpectralClustering on {detail['spectral_n']} "
+                    f"vertices {detail['spectral_s']:.1f} s), measured; the whole job is measured by "
+                    f"`bench.py --impl reference` (profiles/README.md)"
+                ),
+            }  # fmt: skip
         out = ROOT / "gpurun_out"
         if out.is_dir():
             (out / f"workload_{args.workload}.json").write_text(json.dumps({args.workload: job}, indent=1) + "\n")
@@ -596,6 +645,13 @@ def main() -> None:
     parser.add_argument("--impl", default="b200", choices=["b200", "reference"])
     parser.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     parser.add_argument("--no-cpu-baseline", action="store_true")
+    parser.add_argument("--reference-budget-s", type=float, default=600.0,
+                        help="--impl reference: stop starting new full CPU runs after this many seconds "
+                             "(one run is always timed)")
+    parser.add_argument("--profile-step", action="store_true",
+                        help="for ncu: no recording pass, no replay, no CPU baseline -- one warm-up job, then exactly "
+                             "one scs_supertree_build bracketed by cudaProfilerStart/Stop "
+                             "(ncu --profile-from-start off captures that step only)")
     parser.add_argument("--shard-min-n", type=int, default=4096,
                         help="N > 1: recursion nodes with at least this many taxa are row-sharded over the GPUs "
                              "(0: never; the ranks then only share out the independent sub-problems)")
@@ -604,7 +660,10 @@ def main() -> None:
     if args.impl == "reference":
         if rank != 0:
             return
-        print(json.dumps(reference_line(args, make_workload(args.workload))), flush=True)
+        print(json.dumps(reference_line(args)), flush=True)
+        return
+    if args.profile_step:
+        print(json.dumps(profile_step(args, make_workload(args.workload))), flush=True)
         return
     line = gpu_line(args, make_workload(args.workload))
     if rank == 0:

@@ -109,6 +109,10 @@ int scs_ctx_flush_l2(scs_ctx *ctx);
 int scs_ctx_profile_enable(scs_ctx *ctx, int on);
 int scs_ctx_profile_read(scs_ctx *ctx, int kind, int64_t *launches, double *ms, double *bytes, double *units);
 
+/* cudaProfilerStart (on = 1) / cudaProfilerStop (on = 0): brackets the step `ncu --profile-from-start off`
+ * captures (bench.py --profile-step). */
+int scs_profiler_range(int on);
+
 /* ---- proper cluster graph: replaces _proper_cluster_graph_edges + _dfs_pcg_weights
  *      (scs.py:495-583, 586-663) ---------------------------------------------------------- *
  * in : n vertices, T trees, L leaves in total;

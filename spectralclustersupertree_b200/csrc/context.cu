@@ -10,6 +10,8 @@
 #include <chrono>
 #include <cmath>
 
+#include <cuda_profiler_api.h>
+
 namespace scs {
 
 int fail(scs_ctx *ctx, int status, const char *what, cudaError_t err) {
@@ -509,6 +511,11 @@ int scs_ctx_profile_read(scs_ctx *ctx, int kind, int64_t *launches, double *ms, 
     if (bytes) *bytes = total_bytes;
     if (units) *units = total_units;
     return SCS_OK;
+}
+
+int scs_profiler_range(int on) {
+    const cudaError_t err = on ? cudaProfilerStart() : cudaProfilerStop();
+    return err == cudaSuccess ? SCS_OK : SCS_ERR_CUDA;
 }
 
 int scs_pcg_build_dev(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offsets_dev,

@@ -1,0 +1,38 @@
+#!/bin/bash
+# Round-2 GPU session driver: tools/gpu_session.sh <stage> ...   (run on the GPU box through gpurun)
+# Every stage writes under gpurun_out/; an ncu / sanitizer stage only runs after the same command exited 0 plainly.
+set -u
+mkdir -p gpurun_out
+tag=${TAG:-r02}
+for stage in "$@"; do
+  echo "=== stage $stage ($(date +%T))"
+  case $stage in
+    tests)
+      python -m pytest tests -m gpu -q -x --durations=8 > gpurun_out/${tag}_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/${tag}_pytest_gpu.log ;;
+    tests_all)
+      python -m pytest tests -m gpu -q --durations=8 > gpurun_out/${tag}_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/${tag}_pytest_gpu.log ;;
+    bench_small)
+      for w in c1 c2 c3; do
+        python bench.py --workload $w --steps 5 --warmup 3 > gpurun_out/${tag}_bench_$w.json 2> gpurun_out/${tag}_bench_$w.err; echo "bench $w rc=$?"
+      done ;;
+    bench)
+      python bench.py --steps 5 --warmup 3 > gpurun_out/${tag}_bench_c4.json 2> gpurun_out/${tag}_bench_c4.err; echo "bench c4 rc=$?"; head -c 600 gpurun_out/${tag}_bench_c4.json ;;
+    launches)
+      python bench.py --profile-step > gpurun_out/${tag}_profile_step.json 2> gpurun_out/${tag}_profile_step.err; rc=$?; echo "profile-step rc=$rc"; cat gpurun_out/${tag}_profile_step.json
+      if [ $rc -eq 0 ]; then
+        ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+            --log-file gpurun_out/${tag}_launches_step.csv python bench.py --profile-step > gpurun_out/${tag}_launches_step.out 2>&1; echo "ncu launches rc=$?"
+        python tools/ncu_summary.py launches gpurun_out/${tag}_launches_step.csv > gpurun_out/${tag}_launches_step_summary.csv; head -30 gpurun_out/${tag}_launches_step_summary.csv
+      fi ;;
+    sanitize)
+      python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_smoke.log 2>&1; rc=$?; echo "smoke rc=$rc"; tail -2 gpurun_out/${tag}_smoke.log
+      if [ $rc -eq 0 ]; then
+        timeout 900 compute-sanitizer --tool memcheck --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_sanitizer_memcheck_smoke.log 2>&1; echo "memcheck rc=$?"; tail -4 gpurun_out/${tag}_sanitizer_memcheck_smoke.log
+        timeout 900 compute-sanitizer --tool racecheck --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_sanitizer_racecheck_smoke.log 2>&1; echo "racecheck rc=$?"; tail -4 gpurun_out/${tag}_sanitizer_racecheck_smoke.log
+      fi ;;
+    reference)
+      python bench.py --impl reference --steps 1 --warmup 0 --reference-budget-s 1200 > gpurun_out/${tag}_bench_c4_reference.json 2> gpurun_out/${tag}_bench_c4_reference.err; echo "reference rc=$?"; head -c 400 gpurun_out/${tag}_bench_c4_reference.json ;;
+    *) echo "unknown stage $stage" ;;
+  esac
+done
+echo "=== done ($(date +%T))"
