@@ -488,6 +488,8 @@ def gpu_line(args, arrays: dict) -> dict:
         "wave_max_n": traced["wave_max_n"],
         "nodes_small": traced["nodes_small"],
         "nodes_large": traced["nodes_large"],
+        "nodes_medium_batched": traced["nodes_medium"],
+        "nodes_medium_rerun_per_node": traced["nodes_rerun"],
         "resident_tour_bytes": int(replay.bytes),
         "nodes_row_sharded_over_gpus": int(sum(shared)),
     }

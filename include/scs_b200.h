@@ -93,6 +93,11 @@ int scs_ctx_timer_stop(scs_ctx *ctx, double *ms);
  * and the spectral split in one single-CTA launch (dense Jacobi); larger ones take the staged path
  * (union-find, max-merge, Lanczos).  0 sends every node down the staged path. */
 int scs_ctx_set_small_node_limit(scs_ctx *ctx, int limit);
+/* Recursion nodes above the small-node limit with at most `limit` vertices (default and maximum 4096) are
+ * processed by scs_supertree_build as ONE batch per wave of the recursion: every stage of the node path (graph
+ * build, components, contraction, Lanczos steps in lock-step, 2-means) is one launch over all of them.
+ * 0 sends them down the per-node staged path instead. */
+int scs_ctx_set_medium_node_limit(scs_ctx *ctx, int limit);
 /* Graph build: use the 8-byte {tour position, slot} bucket entries that nodes of 65 536 taxa or more need
  * at every size (on = 1; for tests of that path). */
 int scs_ctx_set_wide_entries(scs_ctx *ctx, int on);
@@ -313,6 +318,9 @@ int scs_supertree_counters(const scs_supertree *tree, int64_t *nodes_small, int6
 /* Host wall-clock seconds the build spent in: [0] large-node splits, [1] small-node batches,
  * [2] restricting forests, [3] flattening tours. */
 int scs_supertree_seconds(const scs_supertree *tree, double *seconds4);
+/* Recursion nodes that went through the batched medium-node path, how many of those had to be re-run through the
+ * per-node path (eigensolver restart / repeated-eigenvalue check), and the host seconds spent in the batches. */
+int scs_supertree_medium_info(const scs_supertree *tree, int64_t *nodes_medium, int64_t *nodes_rerun, double *seconds);
 int64_t scs_supertree_num_records(const scs_supertree *tree);
 int scs_supertree_record_size(const scs_supertree *tree, int64_t index);
 int scs_supertree_record(const scs_supertree *tree, int64_t index, int32_t *taxa, int32_t *part,

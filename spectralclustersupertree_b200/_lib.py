@@ -80,6 +80,7 @@ SIGNATURES: dict[str, tuple] = {
     "scs_ctx_timer_start": (c_int, [_P]),
     "scs_ctx_timer_stop": (c_int, [_P, POINTER(c_double)]),
     "scs_ctx_set_small_node_limit": (c_int, [_P, c_int]),
+    "scs_ctx_set_medium_node_limit": (c_int, [_P, c_int]),
     "scs_ctx_set_wide_entries": (c_int, [_P, c_int]),
     "scs_ctx_stage_seconds": (c_int, [_P, _P, c_int]),
     "scs_ctx_flush_l2": (c_int, [_P]),
@@ -142,6 +143,7 @@ SIGNATURES: dict[str, tuple] = {
     "scs_supertree_num_nodes": (c_int64, [_P]),
     "scs_supertree_nodes": (c_int, [_P, _P, _P]),
     "scs_supertree_counters": (c_int, [_P, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)]),
+    "scs_supertree_medium_info": (c_int, [_P, POINTER(c_int64), POINTER(c_int64), POINTER(ctypes.c_double)]),
     "scs_supertree_seconds": (c_int, [_P, _P]),
     "scs_supertree_num_records": (c_int64, [_P]),
     "scs_supertree_record_size": (c_int, [_P, c_int64]),

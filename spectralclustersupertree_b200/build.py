@@ -19,7 +19,8 @@ CSRC = PKG / "csrc"
 INCLUDE = PKG.parent / "include"
 LIB = PKG / "libscs_b200.so"
 
-SOURCES = ["context.cu", "pcg.cu", "components.cu", "contract.cu", "spectral.cu", "small.cu", "shard.cu", "driver.cu", "forest.cpp", "newick.cpp"]
+SOURCES = ["context.cu", "pcg.cu", "components.cu", "contract.cu", "spectral.cu", "medium.cu", "small.cu", "shard.cu", "driver.cu", "forest.cpp", "newick.cpp"]
+HEADERS = ["common.cuh", "shard.cuh", "forest.hpp", "spectral_dev.cuh", "uf.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
@@ -38,26 +39,56 @@ def find_nvcc() -> str:
     return nvcc
 
 
+OBJ_DIR = PKG.parent / "build" / "obj"
+
+
+def _stale(target: Path, deps: list[Path]) -> bool:
+    return not target.is_file() or any(d.stat().st_mtime > target.stat().st_mtime for d in deps)
+
+
 def needs_build() -> bool:
-    if not LIB.is_file():
-        return True
-    built = LIB.stat().st_mtime
-    deps = [CSRC / s for s in SOURCES] + [CSRC / "common.cuh", CSRC / "shard.cuh", CSRC / "forest.hpp", INCLUDE / "scs_b200.h"]
-    return any(d.stat().st_mtime > built for d in deps)
+    deps = [CSRC / s for s in SOURCES + HEADERS] + [INCLUDE / "scs_b200.h"]
+    return _stale(LIB, deps)
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
+    """Every source is compiled to its own object (in parallel, only when it or a header changed), then linked."""
+    from concurrent.futures import ThreadPoolExecutor
+
     if not force and not needs_build():
         return LIB
-    cmd = [find_nvcc(), *NVCC_FLAGS, f"-I{INCLUDE}", f"-I{CSRC}"]
-    if verbose:
-        cmd += ["-Xptxas", "-v"]
-    cmd += [str(CSRC / s) for s in SOURCES] + ["-o", str(LIB)]
-    proc = subprocess.run(cmd, capture_output=True, text=True, check=False)
-    if verbose or proc.returncode != 0:
-        sys.stderr.write(proc.stdout + proc.stderr)
+    nvcc = find_nvcc()
+    OBJ_DIR.mkdir(parents=True, exist_ok=True)
+    headers = [CSRC / h for h in HEADERS] + [INCLUDE / "scs_b200.h"]
+    compile_flags = [f for f in NVCC_FLAGS if f not in ("-shared", "-lgomp")]
+
+    def compile_one(name: str):
+        src = CSRC / name
+        obj = OBJ_DIR / (name + ".o")
+        if not force and not _stale(obj, [src, *headers]):
+            return obj, None
+        cmd = [nvcc, *compile_flags, f"-I{INCLUDE}", f"-I{CSRC}"]
+        if verbose:
+            cmd += ["-Xptxas", "-v"]
+        cmd += ["-c", str(src), "-o", str(obj)]
+        return obj, subprocess.run(cmd, capture_output=True, text=True, check=False)
+
+    with ThreadPoolExecutor(max_workers=8) as pool:
+        done = list(pool.map(compile_one, SOURCES))
+    failed = False
+    for _obj, proc in done:
+        if proc is not None and (verbose or proc.returncode != 0):
+            sys.stderr.write(proc.stdout + proc.stderr)
+        failed = failed or (proc is not None and proc.returncode != 0)
+    if failed:
+        msg = "nvcc failed"
+        raise RuntimeError(msg)
+    link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC,-fopenmp", "-lgomp",
+            *[str(obj) for obj, _ in done], "-o", str(LIB)]  # fmt: skip
+    proc = subprocess.run(link, capture_output=True, text=True, check=False)
     if proc.returncode != 0:
-        msg = f"nvcc failed with exit code {proc.returncode}"
+        sys.stderr.write(proc.stdout + proc.stderr)
+        msg = f"link failed with exit code {proc.returncode}"
         raise RuntimeError(msg)
     return LIB
 

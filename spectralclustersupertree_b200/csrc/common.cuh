@@ -13,6 +13,8 @@
 
 namespace scs {
 
+constexpr int kMediumMaxDefault = 4096;
+
 // A grow-only device allocation; a context keeps one per purpose so steady-state recursion
 // nodes allocate nothing.
 struct DeviceBuffer {
@@ -69,6 +71,15 @@ enum Slot : int {
     SLOT_SPEC_SCALARS,
     SLOT_L2_FLUSH,
     SLOT_NODE_STATS,
+    // batched medium-node path (medium.cu)
+    SLOT_MED_NODES,
+    SLOT_MED_ROW_NODE,
+    SLOT_MED_TREE_NODE,
+    SLOT_MED_STATE,
+    SLOT_MED_VEC,
+    SLOT_MED_SMALL,
+    SLOT_MED_STAGE,
+    SLOT_SCAN_SUMS,
     SLOT_COUNT
 };
 
@@ -104,6 +115,20 @@ struct ShardState {
 struct RowBlock {
     int row0 = 0, row1 = -1;
     bool sharded() const { return row1 >= 0; }
+};
+
+// One recursion node of a batch of medium-sized nodes (medium.cu): where its rows, trees and matrices live in
+// the batch's concatenated buffers.  Filled on the host, read-only on the device.
+struct MedNode {
+    int32_t n, words;         // vertices; 32-bit words per adjacency-bit row
+    int32_t row_base;         // first row of the node in the batch's global row space
+    int32_t tree_begin, tree_end;  // its trees in the batch's tree arrays
+    int32_t jcap;             // Lanczos vectors its basis block can hold (min(n - 1, kMaxBasis))
+    int64_t w_off;            // first element of its n x n block in the W (and Wc) buffer
+    int64_t bit_off;          // first word of its bit rows in the adjacency / max-graph buffers
+    int64_t basis_off;        // first element of its (jcap + 3) x n basis block
+    int64_t part_off;         // where its n partition labels go in the caller's part array
+    uint64_t seed;            // picks the Lanczos start vector
 };
 
 inline int shard_rows_per_rank(int n, int world) { return (n + world - 1) / world; }
@@ -150,6 +175,8 @@ struct scs_ctx {
     bool rows_configured[8] = {false, false, false, false, false, false, false, false};
     bool contract_configured = false;
     bool kmeans_configured = false;
+    bool medium_configured = false;
+    int medium_limit = scs::kMediumMaxDefault;  // nodes up to this size (and above small_limit) go through the batched path
     bool wide_entries = false;  // graph build: 8-byte bucket entries even where 4 bytes would do (tests)
     int small_limit = 64;  // nodes up to this size take the one-CTA path (0 disables it)
     double pending_units = 0.0;  // leaf-pair visits of the node being built (set by host entry points)
@@ -253,6 +280,26 @@ int spectral_bipartition(scs_ctx *ctx, int m, const double *W, const double *deg
                          int32_t *side, scs_node_stats *stats_host, RowBlock rows = RowBlock());
 
 int normalized_matvec(scs_ctx *ctx, int m, const double *W, const double *isd, const double *x, double *y);
+
+// Graph build of a batch of nodes in one set of launches (pcg.cu): R rows in all, T trees, L leaves; the tours are
+// concatenated with absolute leaf offsets; W / bit matrices are addressed through the node table.
+int pcg_build_batch(scs_ctx *ctx, int R, int T, int64_t L, int max_n, int max_trees, const MedNode *nodes_dev,
+                    const int32_t *tree_node, const int32_t *row_node, const int64_t *leaf_offsets,
+                    const int32_t *leaf_taxon, const int32_t *adj_depth, const double *adj_val,
+                    const int32_t *root_depth, const double *tree_weight, double *W, int32_t *occ, uint32_t *adj_bits,
+                    uint32_t *max_bits, double *degree, int32_t *bad_dev);
+
+constexpr int kMediumMax = kMediumMaxDefault;  // recursion nodes up to this many vertices can go through the batched path
+
+// A batch of recursion nodes (kSmallNode < n <= kMediumMax is what the driver sends), every stage one launch over
+// all of them (medium.cu).  Tours: concatenated, node b owns trees [tree_begin[b], tree_begin[b+1]) and their
+// leaves; leaf_offsets[T + 1] absolute; all tour pointers are device pointers.  part_dev receives the labels of
+// node b at part_off[b]; stats_host[b] its record.  needs_rerun[b] is set when the node has to go through
+// scs_node_split_* instead (eigensolver restart or a repeated-eigenvalue check: rare).
+int medium_batch(scs_ctx *ctx, int B, const int32_t *node_n, const int32_t *tree_begin, const int64_t *part_off,
+                 const uint64_t *seeds, int T, int64_t L, const int64_t *leaf_offsets, const int32_t *leaf_taxon,
+                 const int32_t *adj_depth, const double *adj_val, const int32_t *root_depth, const double *tree_weight,
+                 int contract_edges, int32_t *part_dev, scs_node_stats *stats_host, uint8_t *needs_rerun);
 
 // Components, contraction and the spectral split of a graph of <= kSmallNode vertices in one launch;
 // part / out_dev / group_out / Wc_out are device pointers (the last two may be null).

@@ -33,9 +33,10 @@ struct scs_supertree {
         scs_node_stats stats;
     };
     std::vector<Record> records;  // one per recursion node that reached the GPU (if requested)
-    int64_t nodes_small = 0, nodes_large = 0, waves = 0;
+    int64_t nodes_small = 0, nodes_large = 0, nodes_medium = 0, nodes_rerun = 0, waves = 0;
     int64_t pair_visits = 0;
     double seconds[4] = {0, 0, 0, 0};  // large-node splits, small-node batches, restriction, tours
+    double medium_seconds = 0.0;       // medium-node batches (without their tours)
     std::vector<int32_t> wave_tasks, wave_max_n;  // per wave: sub-problems in it, largest taxon count
     std::vector<double> wave_seconds;             // per wave: 3 numbers (GPU splits, restriction, everything)
     int64_t shared_prefix = 0;  // sharded build: output nodes [0, shared_prefix) are identical on every rank
@@ -247,10 +248,10 @@ class Driver {
             out_.wave_tasks.push_back(static_cast<int32_t>(wave.size()));
             out_.wave_max_n.push_back(max_n);
             next.clear();
-            const double before_gpu = out_.seconds[0] + out_.seconds[1], before_restrict = out_.seconds[2];
+            const double before_gpu = out_.seconds[0] + out_.seconds[1] + out_.medium_seconds, before_restrict = out_.seconds[2];
             const auto wave_start = std::chrono::steady_clock::now();
             rc = process_wave(wave, next);
-            out_.wave_seconds.push_back(out_.seconds[0] + out_.seconds[1] - before_gpu);
+            out_.wave_seconds.push_back(out_.seconds[0] + out_.seconds[1] + out_.medium_seconds - before_gpu);
             out_.wave_seconds.push_back(out_.seconds[2] - before_restrict);
             out_.wave_seconds.push_back(std::chrono::duration<double>(std::chrono::steady_clock::now() - wave_start).count());
             const auto t_destroy = std::chrono::steady_clock::now();
@@ -403,7 +404,7 @@ class Driver {
     }
 
     int process_wave(std::vector<Task> &wave, std::vector<Task> &next) {
-        std::vector<size_t> small;
+        std::vector<size_t> small, medium;
         std::vector<SplitResult> results;
         int rc;
         for (size_t i = 0; i < wave.size(); ++i) {
@@ -423,34 +424,55 @@ class Driver {
                 small.push_back(i);
                 continue;
             }
+            if (n <= ctx_->medium_limit && !shard_applies(ctx_, n)) {
+                medium.push_back(i);
+                continue;
+            }
             results.emplace_back();
             results.back().task = i;
         }
-        if (!small.empty() && !results.empty() && small_context() != nullptr) {
-            // both kinds of nodes in this wave: the batch of small nodes runs on its own context (stream) and
-            // host thread next to the large nodes, which are a chain of small launches and round trips
-            std::vector<SplitResult> small_results;
-            int small_rc = SCS_OK;
-            std::thread helper([&] {
-                const cudaError_t err = cudaSetDevice(ctx_->device);
-                if (err != cudaSuccess) {
-                    small_rc = fail(small_ctx_, SCS_ERR_CUDA, "cudaSetDevice (small-node thread)", err);
-                    return;
-                }
-                small_rc = split_small(small_ctx_, scratch_small_, wave, small, small_results);
-            });
+        // The three kinds of nodes of a wave run next to each other: the batch of small nodes and the batch of
+        // medium nodes each on its own context (stream) and host thread, the large nodes on this thread.
+        {
+            std::vector<SplitResult> small_results, medium_results;
+            int small_rc = SCS_OK, medium_rc = SCS_OK;
+            const bool busy_here = !results.empty();
+            const bool small_aside = !small.empty() && (busy_here || !medium.empty()) && small_context() != nullptr;
+            const bool medium_aside = !medium.empty() && busy_here && medium_context() != nullptr;
+            std::thread small_thread, medium_thread;
+            if (small_aside)
+                small_thread = std::thread([&] {
+                    const cudaError_t err = cudaSetDevice(ctx_->device);
+                    small_rc = err != cudaSuccess ? fail(small_ctx_, SCS_ERR_CUDA, "cudaSetDevice (small-node thread)", err)
+                                                  : split_small(small_ctx_, scratch_small_, wave, small, small_results);
+                });
+            if (medium_aside)
+                medium_thread = std::thread([&] {
+                    const cudaError_t err = cudaSetDevice(ctx_->device);
+                    medium_rc = err != cudaSuccess ? fail(medium_ctx_, SCS_ERR_CUDA, "cudaSetDevice (medium-node thread)", err)
+                                                   : split_medium(medium_ctx_, scratch_medium_, wave, medium, medium_results);
+                });
             rc = split_large_all(wave, results);
-            helper.join();
-            fold_counters(small_ctx_);
+            if (rc == SCS_OK && !medium.empty() && !medium_aside) rc = split_medium(ctx_, scratch_, wave, medium, results);
+            if (rc == SCS_OK && !small.empty() && !small_aside) rc = split_small(ctx_, scratch_, wave, small, results);
+            if (small_thread.joinable()) small_thread.join();
+            if (medium_thread.joinable()) medium_thread.join();
+            if (small_aside) fold_counters(small_ctx_);
+            if (medium_aside) fold_counters(medium_ctx_);
+            out_.medium_seconds += medium_seconds_ - medium_tour_seconds_;
+            out_.seconds[3] += medium_tour_seconds_;
+            medium_seconds_ = medium_tour_seconds_ = 0.0;
             if (rc == SCS_OK && small_rc != SCS_OK) {
                 ctx_->last_error = small_ctx_->last_error;
                 rc = small_rc;
             }
+            if (rc == SCS_OK && medium_rc != SCS_OK) {
+                ctx_->last_error = medium_ctx_->last_error;
+                rc = medium_rc;
+            }
             if (rc) return rc;
+            for (SplitResult &res : medium_results) results.push_back(std::move(res));
             for (SplitResult &res : small_results) results.push_back(std::move(res));
-        } else {
-            if ((rc = split_large_all(wave, results))) return rc;
-            if (!small.empty() && (rc = split_small(ctx_, scratch_, wave, small, results))) return rc;
         }
 
         // children of every split node (scs.py:136-171).  The restrictions of the whole wave run as ONE
@@ -594,6 +616,124 @@ class Driver {
         scratch_small_.resize(scratch_.size());
         for (Scratch &sc : scratch_small_) sc.reset(num_taxa_);
         return small_ctx_;
+    }
+
+    // The context of the batch of medium nodes when it runs next to the large nodes (the last worker slot but one).
+    scs_ctx *medium_context() {
+        if (medium_ctx_) return medium_ctx_;
+        if (scs_host_threads() < 2) return nullptr;
+        if (ensure_workers(ctx_, kMaxWorkers + 1) != SCS_OK) return nullptr;
+        medium_ctx_ = ctx_->workers[kMaxWorkers - 2];
+        scratch_medium_.resize(scratch_.size());
+        for (Scratch &sc : scratch_medium_) sc.reset(num_taxa_);
+        return medium_ctx_;
+    }
+
+    // All nodes of a wave between the small-node limit and the medium-node limit in one batch (csrc/medium.cu): their
+    // tours are flattened into one pinned staging area (absolute leaf offsets), copied in one piece, and every
+    // stage of the node path is one launch over the whole batch.
+    int split_medium(scs_ctx *ctx, std::vector<Scratch> &scratch, std::vector<Task> &wave,
+                     const std::vector<size_t> &medium, std::vector<SplitResult> &results) {
+        const int B = static_cast<int>(medium.size());
+        Stopwatch sw_all(&medium_seconds_);  // merged into the totals after the wave's threads are joined
+        std::vector<int32_t> node_n(B), tree_begin(B + 1, 0);
+        std::vector<int64_t> leaf_base(B + 1, 0), part_off(B + 1, 0);
+        std::vector<uint64_t> seeds(B);
+        int64_t visits = 0;
+        for (int b = 0; b < B; ++b) {
+            const Task &task = wave[medium[b]];
+            node_n[b] = static_cast<int32_t>(task.taxa.size());
+            tree_begin[b + 1] = tree_begin[b] + scs_forest_num_trees(task.forest);
+            leaf_base[b + 1] = leaf_base[b] + scs_forest_num_leaves(task.forest);
+            part_off[b + 1] = part_off[b] + node_n[b];
+            seeds[b] = seed_ + static_cast<uint64_t>(task.slot);
+            visits += scs_forest_pair_visits(task.forest);
+        }
+        {
+#pragma omp atomic
+            out_.pair_visits += visits;
+        }
+        const size_t nT = static_cast<size_t>(tree_begin[B]), nL = static_cast<size_t>(leaf_base[B]);
+        // staging layout: offsets | values | weights | taxa | depths | root depths
+        const size_t o_off = 0, o_val = o_off + (nT + 1) * sizeof(int64_t), o_w = o_val + nL * sizeof(double),
+                     o_tax = o_w + nT * sizeof(double), o_dep = o_tax + nL * sizeof(int32_t),
+                     o_root = o_dep + nL * sizeof(int32_t), total = o_root + nT * sizeof(int32_t) + 64;
+        if (ctx->pinned_io_bytes < total) {
+            if (ctx->pinned_io) {
+                SCS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                SCS_CUDA(ctx, cudaFreeHost(ctx->pinned_io));
+                ctx->pinned_io = nullptr;
+                ctx->pinned_io_bytes = 0;
+            }
+            const size_t want = 2 * total + 4096;
+            SCS_CUDA(ctx, cudaMallocHost(&ctx->pinned_io, want));
+            ctx->pinned_io_bytes = want;
+        }
+        unsigned char *stage = static_cast<unsigned char *>(ctx->pinned_io);
+        int64_t *s_off = reinterpret_cast<int64_t *>(stage + o_off);
+        double *s_val = reinterpret_cast<double *>(stage + o_val), *s_w = reinterpret_cast<double *>(stage + o_w);
+        int32_t *s_tax = reinterpret_cast<int32_t *>(stage + o_tax), *s_dep = reinterpret_cast<int32_t *>(stage + o_dep),
+                *s_root = reinterpret_cast<int32_t *>(stage + o_root);
+        int tours_rc = SCS_OK;
+        const int tour_threads = ctx == ctx_ ? scs_host_threads() : std::max(1, scs_host_threads() / 2);
+        {
+            Stopwatch sw(&medium_tour_seconds_);
+#pragma omp parallel num_threads(tour_threads) if (B >= 2)
+            {
+                std::vector<int64_t> own_off;
+#pragma omp for schedule(dynamic, 1)
+                for (int b = 0; b < B; ++b) {
+                    const Task &task = wave[medium[b]];
+                    const int T = tree_begin[b + 1] - tree_begin[b];
+                    own_off.resize(static_cast<size_t>(T) + 1);
+                    const int status = tours_of(task.forest, task.taxa, scratch[static_cast<size_t>(omp_get_thread_num())].local,
+                                                own_off.data(), s_tax + leaf_base[b], s_dep + leaf_base[b], s_val + leaf_base[b],
+                                                s_root + tree_begin[b], s_w + tree_begin[b]);
+                    for (int t = 0; t < T; ++t) s_off[tree_begin[b] + t] = leaf_base[b] + own_off[t];
+                    if (status) {
+#pragma omp atomic write
+                        tours_rc = status;
+                    }
+                }
+            }
+            s_off[nT] = leaf_base[B];
+        }
+        if (tours_rc) return tours_rc;
+        unsigned char *dev;
+        int rc;
+        if ((rc = reserve_as(ctx, SLOT_TOUR_OFFSETS, total, &dev))) return rc;
+        SCS_CUDA(ctx, cudaMemcpyAsync(dev, stage, total - 64, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->h2d_bytes += static_cast<int64_t>(total - 64);
+        int32_t *part_dev;
+        if ((rc = reserve_as(ctx, SLOT_PART, static_cast<size_t>(part_off[B]) + 1, &part_dev))) return rc;
+        std::vector<scs_node_stats> stats(B);
+        std::vector<uint8_t> rerun(B, 0);
+        rc = medium_batch(ctx, B, node_n.data(), tree_begin.data(), part_off.data(), seeds.data(), static_cast<int>(nT),
+                          static_cast<int64_t>(nL), reinterpret_cast<const int64_t *>(dev + o_off),
+                          reinterpret_cast<const int32_t *>(dev + o_tax), reinterpret_cast<const int32_t *>(dev + o_dep),
+                          reinterpret_cast<const double *>(dev + o_val), reinterpret_cast<const int32_t *>(dev + o_root),
+                          reinterpret_cast<const double *>(dev + o_w), contract_, part_dev, stats.data(), rerun.data());
+        if (rc) return rc;
+        std::vector<int32_t> part(static_cast<size_t>(part_off[B]) + 1);
+        SCS_CUDA(ctx, cudaMemcpyAsync(part.data(), part_dev, sizeof(int32_t) * part_off[B], cudaMemcpyDeviceToHost, ctx->stream));
+        SCS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->d2h_bytes += static_cast<int64_t>(sizeof(int32_t)) * part_off[B];
+        out_.nodes_medium += B;
+        if (medium_buffers_.empty()) medium_buffers_.resize(1);
+        for (int b = 0; b < B; ++b) {
+            results.emplace_back();
+            SplitResult &res = results.back();
+            res.task = medium[b];
+            if (rerun[b]) {
+                // eigensolver restart / repeated-eigenvalue check: the per-node path has both
+                out_.nodes_rerun += 1;
+                if ((rc = split_large(ctx, medium_buffers_[0], scratch[0], wave[medium[b]], res))) return rc;
+                continue;
+            }
+            res.part.assign(part.data() + part_off[b], part.data() + part_off[b + 1]);
+            res.stats = stats[b];
+        }
+        return SCS_OK;
     }
 
     int split_small(scs_ctx *ctx, std::vector<Scratch> &scratch, std::vector<Task> &wave,
@@ -776,8 +916,10 @@ class Driver {
     double trace_induce_ = 0.0, trace_present_ = 0.0;  // thread-seconds (summed over host threads)
     scs_supertree &out_;
     int num_taxa_ = 0;
-    std::vector<Scratch> scratch_, scratch_small_;
-    scs_ctx *small_ctx_ = nullptr;
+    std::vector<Scratch> scratch_, scratch_small_, scratch_medium_;
+    scs_ctx *small_ctx_ = nullptr, *medium_ctx_ = nullptr;
+    std::vector<TourBuffers> medium_buffers_;
+    double medium_seconds_ = 0.0, medium_tour_seconds_ = 0.0;  // written by the thread that runs the medium batch
     std::vector<int32_t> owner_;    // global taxon id -> restriction job of the current wave
     std::vector<uint8_t> present_;  // scratch of plan_wave (all zero between waves)
     std::vector<TourBuffers> buffers_;
@@ -896,6 +1038,14 @@ int scs_supertree_counters(const scs_supertree *tree, int64_t *nodes_small, int6
     if (nodes_large) *nodes_large = tree->nodes_large;
     if (waves) *waves = tree->waves;
     if (pair_visits) *pair_visits = tree->pair_visits;
+    return SCS_OK;
+}
+
+int scs_supertree_medium_info(const scs_supertree *tree, int64_t *nodes_medium, int64_t *nodes_rerun, double *seconds) {
+    if (!tree) return SCS_ERR_INVALID;
+    if (nodes_medium) *nodes_medium = tree->nodes_medium;
+    if (nodes_rerun) *nodes_rerun = tree->nodes_rerun;
+    if (seconds) *seconds = tree->medium_seconds;
     return SCS_OK;
 }
 

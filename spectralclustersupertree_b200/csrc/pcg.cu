@@ -37,9 +37,18 @@ constexpr int kWarps = kRowThreads / 32;
 constexpr size_t kRowsStaticSmem = 16 * 1024;  // room left for the row kernel's static shared memory (TreeBatch)
 
 // ---- index: leaf -> tree, occurrences, taxon -> leaves ------------------------------------
+// Batched build (medium.cu): the trees of several recursion nodes are concatenated, tree t belongs to node
+// tree_node[t], and the rows of all nodes form one global row space (row = nodes[b].row_base + vertex id).
+// `batch.nodes == nullptr` is the single-node build: one node of n vertices, row == vertex id.
+struct BatchView {
+    const MedNode *nodes = nullptr;
+    const int32_t *tree_node = nullptr;  // [T]
+    const int32_t *row_node = nullptr;   // [rows]
+};
+
 __global__ void pcg_index_leaves(int n, int T, int64_t L, const int64_t *__restrict__ leaf_offsets,
                                  const int32_t *__restrict__ leaf_taxon, int32_t *__restrict__ leaf_tree,
-                                 int32_t *__restrict__ occ, int32_t *__restrict__ bad) {
+                                 int32_t *__restrict__ occ, int32_t *__restrict__ bad, BatchView batch) {
     int64_t g = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     if (g >= L) return;
     int lo = 0, hi = T;  // largest t with leaf_offsets[t] <= g
@@ -49,8 +58,14 @@ __global__ void pcg_index_leaves(int n, int T, int64_t L, const int64_t *__restr
     }
     leaf_tree[g] = lo;
     int a = leaf_taxon[g];
+    int base = 0;
+    if (batch.nodes) {
+        const MedNode &nd = batch.nodes[batch.tree_node[lo]];
+        n = nd.n;
+        base = nd.row_base;
+    }
     if (a < 0 || a >= n) { *bad = 1; return; }
-    atomicAdd(&occ[a], 1);
+    atomicAdd(&occ[base + a], 1);
 }
 
 // out[i] = sum of in[0..i), out[n] = total.  One block.
@@ -85,12 +100,19 @@ __global__ void exclusive_scan_i32(int n, const int32_t *__restrict__ in, int32_
 }
 
 __global__ void pcg_fill_inverse(int n, int64_t L, const int32_t *__restrict__ leaf_taxon,
-                                 const int32_t *__restrict__ row_ptr, int32_t *__restrict__ cursor,
-                                 int32_t *__restrict__ inv) {
+                                 const int32_t *__restrict__ leaf_tree, const int32_t *__restrict__ row_ptr,
+                                 int32_t *__restrict__ cursor, int32_t *__restrict__ inv, BatchView batch) {
     int64_t g = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     if (g >= L) return;
     int a = leaf_taxon[g];
+    int base = 0;
+    if (batch.nodes) {
+        const MedNode &nd = batch.nodes[batch.tree_node[leaf_tree[g]]];
+        n = nd.n;
+        base = nd.row_base;
+    }
     if (a < 0 || a >= n) return;  // flagged by pcg_index_leaves
+    a += base;
     int slot = atomicAdd(&cursor[a], 1);
     inv[row_ptr[a] + slot] = static_cast<int32_t>(g);
 }
@@ -423,7 +445,8 @@ pcg_rows_kernel(int n, int row0, int words_per_row, BucketShape bs, int stride,
                 const int32_t *__restrict__ occ, const int32_t *__restrict__ bucket_ptr,
                 const EntryT *__restrict__ entries,
                 double *__restrict__ W, int32_t *__restrict__ C, uint32_t *__restrict__ adj_bits,
-                uint32_t *__restrict__ max_bits, double *__restrict__ degree_part, int32_t *__restrict__ bad) {
+                uint32_t *__restrict__ max_bits, double *__restrict__ degree_part, int32_t *__restrict__ bad,
+                BatchView batch) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nwarps = 1 << bs.warps_log2, nthreads = nwarps << 5;
     const int slots_total = stride << bs.warps_log2;
@@ -433,6 +456,20 @@ pcg_rows_kernel(int n, int row0, int words_per_row, BucketShape bs, int stride,
     __shared__ double warp_sum[kWarps];
 
     const int a = row0 + blockIdx.x;  // W / C point at the row block: its first row is row0
+    // batched: `a` is a row of the global row space; the node it belongs to says how wide the row is and where
+    // its outputs go (occ, row_ptr, degree are indexed by the global row)
+    const int degree_stride = n;  // rows of the (global) row space: degree_part is [chunk][row]
+    int occ_base = 0;
+    size_t w_row = static_cast<size_t>(blockIdx.x) * n;
+    size_t bits_row = static_cast<size_t>(a) * words_per_row;
+    if (batch.nodes) {
+        const MedNode &nd = batch.nodes[batch.row_node[a]];
+        n = nd.n;
+        occ_base = nd.row_base;
+        const int a_loc = a - nd.row_base;
+        w_row = static_cast<size_t>(nd.w_off) + static_cast<size_t>(a_loc) * n;
+        bits_row = static_cast<size_t>(nd.bit_off) + static_cast<size_t>(a_loc) * nd.words;
+    }
     const int cols_per_chunk = bs.cols_per_chunk;
     const int col0 = blockIdx.y * cols_per_chunk;
     const int ncols = min(cols_per_chunk, n - col0);
@@ -510,10 +547,10 @@ pcg_rows_kernel(int n, int row0, int words_per_row, BucketShape bs, int stride,
     const int wmask = nwarps - 1;
     auto slot_of = [&](int c) { return (c & wmask) * stride + (c >> bs.warps_log2); };
     const int occ_a = occ[a];
-    double *Wrow = W + static_cast<size_t>(blockIdx.x) * n + col0;
+    double *Wrow = W + w_row + col0;
     for (int c = tid; c < ncols; c += nthreads) {
         Wrow[c] = accW[slot_of(c)];
-        if (kWriteC) C[static_cast<size_t>(blockIdx.x) * n + col0 + c] = static_cast<int32_t>(accC[slot_of(c)]);
+        if (kWriteC) C[w_row + col0 + c] = static_cast<int32_t>(accC[slot_of(c)]);
     }
     const int word0 = col0 >> 5;
     const int nwords = (ncols + 31) >> 5;
@@ -523,13 +560,13 @@ pcg_rows_kernel(int n, int row0, int words_per_row, BucketShape bs, int stride,
         if (c < ncols) {
             const int cc = static_cast<int>(accC[slot_of(c)]);
             edge = cc > 0;
-            if (edge && max_bits != nullptr) top = cc == max(occ_a, occ[col0 + c]);
+            if (edge && max_bits != nullptr) top = cc == max(occ_a, occ[occ_base + col0 + c]);
         }
         const uint32_t eb = __ballot_sync(0xffffffffu, edge);
         const uint32_t tb2 = __ballot_sync(0xffffffffu, top);
         if (lane == 0) {
-            adj_bits[static_cast<size_t>(a) * words_per_row + word0 + j] = eb;
-            if (max_bits != nullptr) max_bits[static_cast<size_t>(a) * words_per_row + word0 + j] = tb2;
+            adj_bits[bits_row + word0 + j] = eb;
+            if (max_bits != nullptr) max_bits[bits_row + word0 + j] = tb2;
         }
     }
     // row sum in a fixed order (the same for every CTA size): virtual thread v < kRowThreads sums columns
@@ -545,7 +582,7 @@ pcg_rows_kernel(int n, int row0, int words_per_row, BucketShape bs, int stride,
     if (tid == 0) {
         double s = 0.0;
         for (int wi = 0; wi < kWarps; ++wi) s += warp_sum[wi];
-        degree_part[static_cast<size_t>(blockIdx.y) * n + a] = s;
+        degree_part[static_cast<size_t>(blockIdx.y) * degree_stride + a] = s;
     }
 }
 
@@ -563,7 +600,7 @@ int launch_rows(scs_ctx *ctx, int n, int row0, int nrows, int words, BucketShape
                 const int64_t *leaf_offsets, const LinkEntry *links, const double *tree_weight,
                 const int32_t *leaf_tree, const int32_t *row_ptr, const int32_t *inv_sorted,
                 const int32_t *occ, const int32_t *bucket_ptr, const void *entries, double *W, int32_t *C,
-                uint32_t *adj_bits, uint32_t *max_bits, double *degree_part, int32_t *bad) {
+                uint32_t *adj_bits, uint32_t *max_bits, double *degree_part, int32_t *bad, BatchView batch = BatchView()) {
     auto kernel = pcg_rows_kernel<CountT, kWriteC, EntryT>;
     // always the same (maximal) opt-in size: contexts on other host threads launch this kernel concurrently
     bool &configured =
@@ -574,24 +611,93 @@ int launch_rows(scs_ctx *ctx, int n, int row0, int nrows, int words, BucketShape
         configured = true;
     }
     dim3 grid(nrows, nchunks);
-    if (n >= kProfileMinSize) {
+    if (n >= kProfileMinSize && !batch.nodes) {
         // algorithmic bytes: W + both bit matrices + occ/degree written once, C if asked
         const double out_bytes = 8.0 * nrows * n + (C ? 4.0 * nrows * n : 0.0) + 8.0 * nrows * words + 12.0 * nrows;
         profile_begin(ctx, PROFILE_PCG_ROWS, out_bytes, ctx->pending_units);
     }
     kernel<<<grid, 32 << bs.warps_log2, smem, ctx->stream>>>(
         n, row0, words, bs, stride, leaf_offsets, links, tree_weight, leaf_tree, row_ptr, inv_sorted, occ, bucket_ptr,
-        static_cast<const EntryT *>(entries), W, C, adj_bits, max_bits, degree_part, bad);
-    if (n >= kProfileMinSize) profile_end(ctx);
+        static_cast<const EntryT *>(entries), W, C, adj_bits, max_bits, degree_part, bad, batch);
+    if (n >= kProfileMinSize && !batch.nodes) profile_end(ctx);
     SCS_LAUNCHED(ctx, "pcg_rows_kernel");
     return SCS_OK;
 }
 
 }  // namespace
 
+// Long inputs: per-tile sums (kScanTile elements per CTA), a one-CTA scan of the tile sums, then every tile scanned
+// again from its offset.  Integer sums: any order gives the same result.
+constexpr int kScanTile = 4096;
+
+__global__ void __launch_bounds__(1024) scan_tile_sums(int n, const int32_t *__restrict__ in, int32_t *__restrict__ sums) {
+    __shared__ int32_t warp_part[32];
+    const int base = blockIdx.x * kScanTile;
+    int32_t acc = 0;
+    for (int i = threadIdx.x; i < kScanTile; i += 1024)
+        if (base + i < n) acc += in[base + i];
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+    if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int32_t v = warp_part[threadIdx.x];
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+        if (threadIdx.x == 0) sums[blockIdx.x] = v;
+    }
+}
+
+// thread t owns elements [4t, 4t + 4) of the tile
+__global__ void __launch_bounds__(1024) scan_tiles(int n, const int32_t *__restrict__ in, const int32_t *__restrict__ tile_offset,
+                                                  int32_t *__restrict__ out) {
+    __shared__ int32_t warp_part[32];
+    const int base = blockIdx.x * kScanTile + threadIdx.x * 4;
+    int32_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = base + k < n ? in[base + k] : 0;
+    const int32_t mine = v[0] + v[1] + v[2] + v[3];
+    int32_t inc = mine;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int off = 1; off < 32; off <<= 1) {
+        const int32_t o = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= off) inc += o;
+    }
+    if (lane == 31) warp_part[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int32_t w = warp_part[lane];
+        for (int off = 1; off < 32; off <<= 1) {
+            const int32_t o = __shfl_up_sync(0xffffffffu, w, off);
+            if (lane >= off) w += o;
+        }
+        warp_part[lane] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    int32_t run = tile_offset[blockIdx.x] + (warp ? warp_part[warp - 1] : 0) + inc - mine;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (base + k < n) out[base + k] = run;
+        run += v[k];
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 1023) out[n] = tile_offset[gridDim.x];
+}
+
 int exclusive_scan(scs_ctx *ctx, int n, const int32_t *in, int32_t *out) {
-    exclusive_scan_i32<<<1, 1024, 0, ctx->stream>>>(n, in, out);
+    if (n <= 2 * kScanTile) {
+        exclusive_scan_i32<<<1, 1024, 0, ctx->stream>>>(n, in, out);
+        SCS_LAUNCHED(ctx, "exclusive_scan_i32");
+        return SCS_OK;
+    }
+    const int tiles = ceil_div(n, kScanTile);
+    int32_t *sums;
+    int rc;
+    if ((rc = reserve_as(ctx, SLOT_SCAN_SUMS, 2 * static_cast<size_t>(tiles) + 2, &sums))) return rc;
+    int32_t *offsets = sums + tiles;  // tiles + 1 entries
+    scan_tile_sums<<<tiles, 1024, 0, ctx->stream>>>(n, in, sums);
+    SCS_LAUNCHED(ctx, "scan_tile_sums");
+    exclusive_scan_i32<<<1, 1024, 0, ctx->stream>>>(tiles, sums, offsets);
     SCS_LAUNCHED(ctx, "exclusive_scan_i32");
+    scan_tiles<<<tiles, 1024, 0, ctx->stream>>>(n, in, offsets, out);
+    SCS_LAUNCHED(ctx, "scan_tiles");
     return SCS_OK;
 }
 
@@ -626,12 +732,13 @@ int pcg_build(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offsets
     SCS_CUDA(ctx, cudaMemsetAsync(scalars, 0, sizeof(int32_t) * 64, ctx->stream));
     if (L > 0) {
         pcg_index_leaves<<<ceil_div(L, 256), 256, 0, ctx->stream>>>(n, T, L, leaf_offsets, leaf_taxon, leaf_tree, occ,
-                                                                   scalars);
+                                                                   scalars, BatchView());
         SCS_LAUNCHED(ctx, "pcg_index_leaves");
     }
     if ((rc = exclusive_scan(ctx, n, occ, row_ptr))) return rc;
     if (L > 0) {
-        pcg_fill_inverse<<<ceil_div(L, 256), 256, 0, ctx->stream>>>(n, L, leaf_taxon, row_ptr, cursor, inv);
+        pcg_fill_inverse<<<ceil_div(L, 256), 256, 0, ctx->stream>>>(n, L, leaf_taxon, leaf_tree, row_ptr, cursor, inv,
+                                                                   BatchView());
         SCS_LAUNCHED(ctx, "pcg_fill_inverse");
         if (nrows > 0) {
             pcg_sort_inverse<<<nrows, 128, 0, ctx->stream>>>(row0, row_ptr, inv, inv_sorted);
@@ -718,6 +825,92 @@ int pcg_build(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offsets
         SCS_LAUNCHED(ctx, "pcg_sum_degree_parts");
     }
     return SCS_OK;
+}
+
+
+// The same pipeline over a batch of nodes (see BatchView): index, inverse lists, links, buckets and ONE launch of
+// the row kernel with a CTA per row of the global row space.  Every node fits one column chunk.
+int pcg_build_batch(scs_ctx *ctx, int R, int T, int64_t L, int max_n, int max_trees, const MedNode *nodes_dev,
+                    const int32_t *tree_node, const int32_t *row_node, const int64_t *leaf_offsets,
+                    const int32_t *leaf_taxon, const int32_t *adj_depth, const double *adj_val,
+                    const int32_t *root_depth, const double *tree_weight, double *W, int32_t *occ, uint32_t *adj_bits,
+                    uint32_t *max_bits, double *degree, int32_t *bad_dev) {
+    if (R <= 0 || T < 0 || L < 0 || L >= (1ll << 31) || max_n <= 0 || max_n > 65535 || !nodes_dev || !tree_node ||
+        !row_node || !W || !occ || !adj_bits || !degree || !bad_dev)
+        return fail(ctx, SCS_ERR_INVALID, "pcg_build_batch: bad argument");
+    BatchView batch;
+    batch.nodes = nodes_dev;
+    batch.tree_node = tree_node;
+    batch.row_node = row_node;
+    int32_t *leaf_tree, *row_ptr, *cursor, *inv, *inv_sorted;
+    int rc;
+    if ((rc = reserve_as(ctx, SLOT_LEAF_TREE, static_cast<size_t>(L) + 1, &leaf_tree))) return rc;
+    if ((rc = reserve_as(ctx, SLOT_ROW_PTR, static_cast<size_t>(R) + 1, &row_ptr))) return rc;
+    if ((rc = reserve_as(ctx, SLOT_CURSOR, static_cast<size_t>(R), &cursor))) return rc;
+    if ((rc = reserve_as(ctx, SLOT_INV, static_cast<size_t>(L) + 1, &inv))) return rc;
+    if ((rc = reserve_as(ctx, SLOT_INV_SORTED, static_cast<size_t>(L) + 1, &inv_sorted))) return rc;
+    SCS_CUDA(ctx, cudaMemsetAsync(occ, 0, sizeof(int32_t) * R, ctx->stream));
+    SCS_CUDA(ctx, cudaMemsetAsync(cursor, 0, sizeof(int32_t) * R, ctx->stream));
+    if (L > 0) {
+        pcg_index_leaves<<<ceil_div(L, 256), 256, 0, ctx->stream>>>(max_n, T, L, leaf_offsets, leaf_taxon, leaf_tree, occ,
+                                                                   bad_dev, batch);
+        SCS_LAUNCHED(ctx, "pcg_index_leaves");
+    }
+    if ((rc = exclusive_scan(ctx, R, occ, row_ptr))) return rc;
+    if (L > 0) {
+        pcg_fill_inverse<<<ceil_div(L, 256), 256, 0, ctx->stream>>>(max_n, L, leaf_taxon, leaf_tree, row_ptr, cursor, inv,
+                                                                   batch);
+        SCS_LAUNCHED(ctx, "pcg_fill_inverse");
+        pcg_sort_inverse<<<R, 128, 0, ctx->stream>>>(0, row_ptr, inv, inv_sorted);
+        SCS_LAUNCHED(ctx, "pcg_sort_inverse");
+    }
+    LinkEntry *links;
+    if ((rc = reserve_as(ctx, SLOT_LINKS, static_cast<size_t>(L > 0 ? L : 1), &links))) return rc;
+    if (L > 0 && T > 0) {
+        // a tree of a node has at most max_n leaves (more: a repeated taxon, flagged by the row kernel)
+        const int nb1 = ceil_div(max_n + 1, 32), nb2 = ceil_div(nb1, 32);
+        const size_t link_smem = sizeof(int32_t) * (static_cast<size_t>(nb1) + nb2 + 2);
+        pcg_tour_links<<<T, 256, link_smem, ctx->stream>>>(max_n + 1, leaf_offsets, adj_depth, adj_val, root_depth, links);
+        SCS_LAUNCHED(ctx, "pcg_tour_links");
+    }
+    const bool narrow = max_trees < 65536;
+    const size_t per_col = sizeof(double) + (narrow ? sizeof(uint16_t) : sizeof(int32_t));
+    BucketShape bs;
+    bs.warps_log2 = 4;
+    const int warps = 1 << bs.warps_log2;
+    bs.cols_per_chunk = ceil_div(max_n, 32) * 32;  // one chunk per row
+    bs.buckets = warps;
+    const int stride = ceil_div(bs.cols_per_chunk, warps) | 1;
+    const size_t smem = static_cast<size_t>(stride) * warps * per_col + 16;
+    const size_t cells = static_cast<size_t>(T) * bs.buckets;
+    if (cells + 1 >= (1ull << 31)) return fail(ctx, SCS_ERR_INVALID, "pcg_build_batch: too many tree buckets");
+    int32_t *bucket_count, *bucket_ptr;
+    void *entries;
+    if ((rc = reserve_as(ctx, SLOT_BUCKET_COUNT, cells + 1, &bucket_count))) return rc;
+    if ((rc = reserve_as(ctx, SLOT_BUCKET_PTR, cells + 2, &bucket_ptr))) return rc;
+    if ((rc = reserve(ctx, SLOT_ENTRIES, (static_cast<size_t>(L) + 1) * 4, &entries))) return rc;
+    SCS_CUDA(ctx, cudaMemsetAsync(bucket_count, 0, sizeof(int32_t) * (cells + 1), ctx->stream));
+    if (L > 0) {
+        pcg_bucket_count<<<ceil_div(L, 256), 256, 0, ctx->stream>>>(max_n, L, bs, leaf_taxon, leaf_tree, bucket_count);
+        SCS_LAUNCHED(ctx, "pcg_bucket_count");
+    }
+    if ((rc = exclusive_scan(ctx, static_cast<int>(cells), bucket_count, bucket_ptr))) return rc;
+    SCS_CUDA(ctx, cudaMemsetAsync(bucket_count, 0, sizeof(int32_t) * (cells + 1), ctx->stream));
+    if (L > 0) {
+        pcg_bucket_fill<uint32_t><<<ceil_div(L, 256), 256, 0, ctx->stream>>>(
+            max_n, L, bs, leaf_offsets, leaf_taxon, leaf_tree, bucket_ptr, bucket_count, static_cast<uint32_t *>(entries));
+        SCS_LAUNCHED(ctx, "pcg_bucket_fill");
+    }
+    // the row kernel writes the row sums straight into `degree` (one chunk: degree_part[0][row])
+    if (narrow)
+        rc = launch_rows<uint16_t, false, uint32_t>(ctx, R, 0, R, 0, bs, stride, 1, smem, leaf_offsets, links, tree_weight,
+                                                    leaf_tree, row_ptr, inv_sorted, occ, bucket_ptr, entries, W, nullptr,
+                                                    adj_bits, max_bits, degree, bad_dev, batch);
+    else
+        rc = launch_rows<int32_t, false, uint32_t>(ctx, R, 0, R, 0, bs, stride, 1, smem, leaf_offsets, links, tree_weight,
+                                                   leaf_tree, row_ptr, inv_sorted, occ, bucket_ptr, entries, W, nullptr,
+                                                   adj_bits, max_bits, degree, bad_dev, batch);
+    return rc;
 }
 
 }  // namespace scs

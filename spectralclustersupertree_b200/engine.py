@@ -100,6 +100,11 @@ class Engine:
         """Largest recursion node (vertices) that takes the one-CTA path; 0 forces the staged path."""
         _check(self._lib.scs_ctx_set_small_node_limit(self._ctx, limit), self._ctx)
 
+    def set_medium_node_limit(self, limit: int) -> None:
+        """Nodes above the small-node limit with at most ``limit`` vertices (max 4096) go through the batched
+        medium-node path of the native driver; 0 sends them down the per-node staged path."""
+        _check(self._lib.scs_ctx_set_medium_node_limit(self._ctx, limit), self._ctx)
+
     def set_wide_entries(self, on: bool) -> None:
         """Graph build with the 8-byte bucket entries of nodes with >= 65 536 taxa at every size (tests)."""
         _check(self._lib.scs_ctx_set_wide_entries(self._ctx, int(on)), self._ctx)
@@ -208,12 +213,15 @@ class Engine:
                                              ctypes.byref(pairs))  # fmt: skip
             seconds = np.zeros(4)
             self._lib.scs_supertree_seconds(handle, ptr(seconds))
+            medium, rerun, medium_s = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_double(0.0)
+            self._lib.scs_supertree_medium_info(handle, ctypes.byref(medium), ctypes.byref(rerun), ctypes.byref(medium_s))
             wave_tasks = np.zeros(max(waves.value, 1), dtype=np.int32)
             wave_max_n = np.zeros(max(waves.value, 1), dtype=np.int32)
             self._lib.scs_supertree_wave_info(handle, ptr(wave_tasks), ptr(wave_max_n))
             wave_seconds = np.zeros((max(waves.value, 1), 3))
             self._lib.scs_supertree_wave_seconds(handle, ptr(wave_seconds))
             out = {"parent": parent, "taxon": taxon, "nodes_small": small.value, "nodes_large": large.value,
+                   "nodes_medium": medium.value, "nodes_rerun": rerun.value, "medium_seconds": medium_s.value,
                    "waves": waves.value, "pair_visits": pairs.value, "records": [],
                    "shared_prefix": int(self._lib.scs_supertree_shared_prefix(handle)),
                    "shared_records": int(self._lib.scs_supertree_shared_records(handle)),

@@ -221,3 +221,51 @@ def test_sharded_build_joins_to_the_same_supertree(engine, name, world):
     assert rf(a, b) == 0
     # the replicated waves are solved by every rank, the rest exactly once
     assert nodes >= whole["nodes_small"] + whole["nodes_large"]
+
+
+@pytest.mark.parametrize("name", ["c2_500x50_branch", "c3_1000x100_branch_weighted", "s_300x40_branch_weighted",
+                                  "s_200x40_bootstrap", "dcm"])  # fmt: skip
+def test_medium_batch_matches_per_node_path(engine, name):
+    """csrc/medium.cu (all nodes of a wave between 65 and 4096 taxa in one batch, Lanczos in lock-step) against the
+    per-node staged path: same components, contraction sizes and partitions on every recursion node, Fiedler
+    eigenvalues to 1e-9."""
+    from spectralclustersupertree_b200.engine import Forest
+
+    case = load_case(name)
+    trees = parse(case["lines"])
+
+    def build():
+        forest = Forest.from_trees(trees, case["weights"], case["names"])
+        return engine.supertree_build(forest, case["weighting"], record=True)
+
+    batched = build()
+    engine.set_medium_node_limit(0)
+    try:
+        staged = build()
+    finally:
+        engine.set_medium_node_limit(4096)
+    assert staged["nodes_medium"] == 0
+    by_taxa = {taxa.tobytes(): (part, stats) for taxa, part, stats in staged["records"]}
+    compared = 0
+    for taxa, part, stats in batched["records"]:
+        if len(taxa) <= 64:
+            continue
+        other = by_taxa.get(taxa.tobytes())
+        if other is None:
+            continue  # below a tie where the two solvers may legitimately differ
+        compared += 1
+        opart, ostats = other
+        assert stats.n_components == ostats.n_components
+        assert stats.contracted_size == ostats.contracted_size
+        if stats.n_components != 1:
+            assert np.array_equal(part, opart)
+            continue
+        if stats.contracted_size >= 3:
+            assert abs(stats.eig[1] - ostats.eig[1]) < 1e-9
+            assert stats.residual < 1e-10
+        if not ((stats.tie_flag | ostats.tie_flag) & 3):
+            assert np.array_equal(part, opart) or np.array_equal(part, 1 - opart)
+            assert stats.kmeans_stable_splits == ostats.kmeans_stable_splits
+    if name != "dcm":
+        assert batched["nodes_medium"] > 0 and compared > 0
+    assert int((batched["taxon"] >= 0).sum()) == int((staged["taxon"] >= 0).sum())
