@@ -284,58 +284,82 @@ def reference_line(args) -> dict:
 # the GPU arm
 # ---------------------------------------------------------------------------------------------
 class Replay:
-    """The recursion nodes one rank processes, as leaf tours resident in HBM, for the device-only
-    timed pass: every node with more than 64 taxa through ``scs_node_split_dev``, all smaller ones in
-    one launch of the batched small-node kernel (``scs_nodes_split_small_dev``)."""
+    """The recursion nodes one rank processes, as leaf tours resident in HBM, for the device-only timed pass.
+    The nodes are replayed wave by wave, as the native driver issues them: per wave every node above
+    ``medium_limit`` taxa through ``scs_node_split_dev``, all nodes between the two limits in one batch
+    (``scs_nodes_split_medium_dev``), all nodes up to ``small_limit`` in one launch of the small-node kernel
+    (``scs_nodes_split_small_dev``)."""
 
     FIELDS = (("leaf_offsets", np.int64), ("leaf_taxon", np.int32), ("adj_depth", np.int32),
               ("adj_val", np.float64), ("root_depth", np.int32), ("tree_weight", np.float64))  # fmt: skip
 
-    def __init__(self, engine, nodes: list, small_limit: int = 64, shared: list | None = None) -> None:
+    def __init__(self, engine, nodes: list, waves: list, small_limit: int = 64, medium_limit: int = 4096,
+                 shared: list | None = None) -> None:
         from spectralclustersupertree_b200 import _lib
 
         self.engine = engine
         self.lib = _lib.load()
         self.pair_visits = [t.pair_updates() for t, _ in nodes]
         shared = shared or [False] * len(nodes)
-        self.shared_of = {id(t): s for (t, _), s in zip(nodes, shared, strict=True)}
-        large = [(t, seed) for t, seed in nodes if t.n > small_limit]
-        small = [t for t, _ in nodes if t.n <= small_limit]
         self.bytes = 0
         self.buffers = []
-        # large nodes: concatenated arrays, one entry of device pointers per node
-        self.large = []
-        if large:
-            host = {k: np.concatenate([getattr(t, k) for t, _ in large]).astype(d) for k, d in self.FIELDS}
-            dev = {k: self._upload(v) for k, v in host.items()}
-            pos = dict.fromkeys(host, 0)
-            for tours, seed in large:
-                T, L = tours.num_trees, tours.num_leaves
-                entry = {"n": tours.n, "T": T, "L": L, "seed": seed, "shared": self.shared_of[id(tours)]}
-                for key, count in (("leaf_offsets", T + 1), ("leaf_taxon", L), ("adj_depth", L), ("adj_val", L),
-                                   ("root_depth", T), ("tree_weight", T)):  # fmt: skip
-                    entry[key] = dev[key] + pos[key] * host[key].itemsize
-                    pos[key] += count
-                self.large.append(entry)
+        self.waves = []
         self.part = engine.alloc(4 * max([t.n for t, _ in nodes] + [1]))
-        # small nodes: the layout of scs_small_node (include/scs_b200.h)
-        self.small_count = len(small)
-        if small:
-            desc = np.zeros(len(small), dtype=np.dtype([("n", "<i4"), ("num_trees", "<i4"), ("leaf_base", "<i8"),
-                                                        ("tree_base", "<i8"), ("vertex_base", "<i8")]))  # fmt: skip
-            L = T = N = 0
-            for b, t in enumerate(small):
-                desc[b] = (t.n, t.num_trees, L, T, N)
-                L += t.num_leaves
-                T += t.num_trees
-                N += t.n
-            host = {k: np.concatenate([getattr(t, k) for t in small]).astype(d) for k, d in self.FIELDS}
-            self.small_dev = {k: self._upload(v) for k, v in host.items()}
-            self.small_desc = self._upload(desc)
-            self.small_part = engine.alloc(4 * max(N, 1))
-            self.small_stats = engine.alloc(80 * len(small))
-            self.buffers += [self.small_part, self.small_stats]
         self.buffers.append(self.part)
+        for wave in sorted(set(waves)):
+            members = [(t, seed, sh) for (t, seed), w, sh in zip(nodes, waves, shared, strict=True) if w == wave]
+            large = [(t, seed, sh) for t, seed, sh in members if t.n > medium_limit or sh]
+            medium = [(t, seed) for t, seed, sh in members if small_limit < t.n <= medium_limit and not sh]
+            small = [t for t, _, sh in members if t.n <= small_limit and not sh]
+            entry = {"large": [], "medium": None, "small": None}
+            if large:
+                host = {k: np.concatenate([getattr(t, k) for t, _, _ in large]).astype(d) for k, d in self.FIELDS}
+                dev = {k: self._upload(v) for k, v in host.items()}
+                pos = dict.fromkeys(host, 0)
+                for tours, seed, sh in large:
+                    T, L = tours.num_trees, tours.num_leaves
+                    item = {"n": tours.n, "T": T, "L": L, "seed": seed, "shared": sh}
+                    for key, count in (("leaf_offsets", T + 1), ("leaf_taxon", L), ("adj_depth", L), ("adj_val", L),
+                                       ("root_depth", T), ("tree_weight", T)):  # fmt: skip
+                        item[key] = dev[key] + pos[key] * host[key].itemsize
+                        pos[key] += count
+                    entry["large"].append(item)
+            if medium:
+                host = {k: np.concatenate([getattr(t, k) for t, _ in medium]).astype(d) for k, d in self.FIELDS
+                        if k != "leaf_offsets"}  # fmt: skip
+                offsets, base = [], 0
+                for t, _ in medium:
+                    offsets.append(t.leaf_offsets[:-1].astype(np.int64) + base)
+                    base += t.num_leaves
+                host["leaf_offsets"] = np.concatenate(offsets + [np.array([base], dtype=np.int64)])
+                dev = {k: self._upload(v) for k, v in host.items()}
+                sizes = np.array([t.n for t, _ in medium], dtype=np.int32)
+                tree_begin = np.concatenate([[0], np.cumsum([t.num_trees for t, _ in medium])]).astype(np.int32)
+                part_off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+                entry["medium"] = {
+                    "dev": dev, "B": len(medium), "n": sizes, "tree_begin": tree_begin, "part_off": part_off,
+                    "seeds": np.array([seed & 0xFFFFFFFFFFFFFFFF for _, seed in medium], dtype=np.uint64),
+                    "T": int(tree_begin[-1]), "L": int(base), "part": engine.alloc(4 * int(part_off[-1]) + 16),
+                    "stats": (_lib.NodeStats * len(medium))(), "rerun": np.zeros(len(medium), dtype=np.uint8),
+                }  # fmt: skip
+                self.buffers.append(entry["medium"]["part"])
+            if small:
+                # the layout of scs_small_node (include/scs_b200.h)
+                desc = np.zeros(len(small), dtype=np.dtype([("n", "<i4"), ("num_trees", "<i4"), ("leaf_base", "<i8"),
+                                                            ("tree_base", "<i8"), ("vertex_base", "<i8")]))  # fmt: skip
+                L = T = N = 0
+                for b, t in enumerate(small):
+                    desc[b] = (t.n, t.num_trees, L, T, N)
+                    L += t.num_leaves
+                    T += t.num_trees
+                    N += t.n
+                host = {k: np.concatenate([getattr(t, k) for t in small]).astype(d) for k, d in self.FIELDS}
+                entry["small"] = {"dev": {k: self._upload(v) for k, v in host.items()}, "desc": self._upload(desc),
+                                  "count": len(small), "part": engine.alloc(4 * max(N, 1)),
+                                  "stats": engine.alloc(80 * len(small))}  # fmt: skip
+                self.buffers += [entry["small"]["part"], entry["small"]["stats"]]
+            self.waves.append(entry)
+        self.reruns = 0
 
     def _upload(self, array: np.ndarray) -> int:
         self.bytes += array.nbytes
@@ -344,22 +368,38 @@ class Replay:
         return dev
 
     def run(self, contract_edges: bool = True) -> None:
-        for entry in self.large:
-            # nodes the ranks share out (row-sharded over the GPUs) are replayed the same way
-            if entry["shared"]:
-                self.engine.shard_engage(True)
-            self.engine.node_split_dev(entry, self.part, contract_edges=contract_edges, seed=entry["seed"])
-            if entry["shared"]:
-                self.engine.shard_engage(False)
-        if self.small_count:
-            d = self.small_dev
-            status = self.lib.scs_nodes_split_small_dev(
-                self.engine.handle, self.small_count, self.small_desc, d["leaf_offsets"], d["leaf_taxon"],
-                d["adj_depth"], d["adj_val"], d["root_depth"], d["tree_weight"], int(contract_edges),
-                self.small_part, self.small_stats,
-            )  # fmt: skip
-            if status != 0:
-                raise RuntimeError(f"scs_nodes_split_small_dev failed with status {status}")
+        from spectralclustersupertree_b200.engine import ptr
+
+        for wave in self.waves:
+            for entry in wave["large"]:
+                # nodes the ranks share out (row-sharded over the GPUs) are replayed the same way
+                if entry["shared"]:
+                    self.engine.shard_engage(True)
+                self.engine.node_split_dev(entry, self.part, contract_edges=contract_edges, seed=entry["seed"])
+                if entry["shared"]:
+                    self.engine.shard_engage(False)
+            med = wave["medium"]
+            if med is not None:
+                d = med["dev"]
+                status = self.lib.scs_nodes_split_medium_dev(
+                    self.engine.handle, med["B"], ptr(med["n"]), ptr(med["tree_begin"]), ptr(med["part_off"]),
+                    ptr(med["seeds"]), med["T"], med["L"], d["leaf_offsets"], d["leaf_taxon"], d["adj_depth"],
+                    d["adj_val"], d["root_depth"], d["tree_weight"], int(contract_edges), med["part"], med["stats"],
+                    ptr(med["rerun"]),
+                )  # fmt: skip
+                if status != 0:
+                    raise RuntimeError(f"scs_nodes_split_medium_dev failed with status {status}")
+                self.reruns += int(med["rerun"].sum())
+            sm = wave["small"]
+            if sm is not None:
+                d = sm["dev"]
+                status = self.lib.scs_nodes_split_small_dev(
+                    self.engine.handle, sm["count"], sm["desc"], d["leaf_offsets"], d["leaf_taxon"],
+                    d["adj_depth"], d["adj_val"], d["root_depth"], d["tree_weight"], int(contract_edges),
+                    sm["part"], sm["stats"],
+                )  # fmt: skip
+                if status != 0:
+                    raise RuntimeError(f"scs_nodes_split_small_dev failed with status {status}")
 
     def close(self) -> None:
         for d in self.buffers:
@@ -471,7 +511,7 @@ def gpu_line(args, arrays: dict) -> dict:
     mine = [recorded[taxa.tobytes()] for taxa, _, _ in traced["records"]]
     sharing = dist is not None and args.shard_min_n > 0
     shared = [sharing and i < traced["shared_records"] and t.n >= args.shard_min_n for i, (t, _) in enumerate(mine)]
-    replay = Replay(engine, mine, shared=shared)
+    replay = Replay(engine, mine, traced["record_waves"], shared=shared)
     spectral = [st for _, _, st in traced["records"] if st.n_components == 1]
     all_visits = [t.pair_updates() for t, _ in recorded.values()]
     job = {
@@ -588,8 +628,9 @@ def gpu_line(args, arrays: dict) -> dict:
             "workload": describe(args.workload),
             "l2": "flushed between timed steps (256 MB write); the top-level W (0.8 GB) exceeds L2 by itself",
             "value_is": "every recursion node of this rank's share of the job replayed from leaf tours resident in "
-                        "HBM: nodes > 64 taxa one by one, all smaller nodes in one batched launch (CUDA events; max "
-                        "over ranks)",
+                        "HBM, wave by wave as the native driver issues them: per wave the nodes > 4096 taxa one by one, "
+                        "the nodes of 65..4096 taxa as one batch (one launch per stage), the nodes <= 64 taxa in one "
+                        "launch (CUDA events on one stream; max over ranks)",
             "e2e_is": "scs_forest_create + scs_supertree_build over the C ABI from flat host arrays to the flat "
                       "supertree (wall clock; native breadth-first recursion, per-wave H2D of tours and D2H of "
                       "partitions; for N > 1 recursion nodes with >= --shard-min-n taxa are row-sharded over the "

@@ -285,6 +285,22 @@ int scs_nodes_split_small_dev(scs_ctx *ctx, int num_nodes, const scs_small_node 
                               const int32_t *root_depth_dev, const double *tree_weight_dev,
                               int contract_edges, int32_t *part_dev, scs_node_stats *stats_dev);
 
+/* ---- a batch of medium-sized recursion nodes, one launch per stage ------------------------------------ *
+ * Nodes of at most 4096 vertices (scs_supertree_build sends those above the small-node limit): the block
+ * scs.py:108-134 for every node of the batch, every stage -- graph build, components, contraction, the Lanczos
+ * steps in lock-step, 2-means -- ONE launch over all of them.  Host arrays: node_n[num_nodes],
+ * tree_begin[num_nodes + 1] (node b owns trees [tree_begin[b], tree_begin[b + 1]) of the concatenated tours),
+ * part_offset[num_nodes] (where its labels go in part_dev), seeds[num_nodes].  Device arrays: the tours of all
+ * nodes, concatenated, leaf_offsets[T + 1] ABSOLUTE; leaf_taxon holds vertex ids local to the node.
+ * stats[num_nodes] and needs_rerun[num_nodes] are host arrays; needs_rerun[b] = 1 asks the caller to send node b
+ * through scs_node_split_* instead (eigensolver restart after 256 steps, or the deflated second run that settles a
+ * repeated Fiedler eigenvalue: rare).  Returns after the results landed. */
+int scs_nodes_split_medium_dev(scs_ctx *ctx, int num_nodes, const int32_t *node_n, const int32_t *tree_begin,
+                               const int64_t *part_offset, const uint64_t *seeds, int T, int64_t L,
+                               const int64_t *leaf_offsets_dev, const int32_t *leaf_taxon_dev, const int32_t *adj_depth_dev,
+                               const double *adj_val_dev, const int32_t *root_depth_dev, const double *tree_weight_dev,
+                               int contract_edges, int32_t *part_dev, scs_node_stats *stats, uint8_t *needs_rerun);
+
 /* ---- the whole recursion (scs.py:96-174) as a native work-list ------------------------------- *
  * Breadth-first over the independent sub-problems: every frontier node with <= 64 taxa goes to the
  * GPU in one batched launch, larger ones through scs_node_split_host.  The result is the supertree
@@ -323,6 +339,8 @@ int scs_supertree_seconds(const scs_supertree *tree, double *seconds4);
 int scs_supertree_medium_info(const scs_supertree *tree, int64_t *nodes_medium, int64_t *nodes_rerun, double *seconds);
 int64_t scs_supertree_num_records(const scs_supertree *tree);
 int scs_supertree_record_size(const scs_supertree *tree, int64_t index);
+/* Wave of the breadth-first recursion (0 = the top-level node) in which record `index` was processed. */
+int scs_supertree_record_wave(const scs_supertree *tree, int64_t index);
 int scs_supertree_record(const scs_supertree *tree, int64_t index, int32_t *taxa, int32_t *part,
                          scs_node_stats *stats);
 

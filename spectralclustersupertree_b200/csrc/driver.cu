@@ -31,6 +31,7 @@ struct scs_supertree {
     struct Record {
         std::vector<int32_t> taxa, part;
         scs_node_stats stats;
+        int32_t wave = 0;  // wave of the breadth-first recursion that processed the node
     };
     std::vector<Record> records;  // one per recursion node that reached the GPU (if requested)
     int64_t nodes_small = 0, nodes_large = 0, nodes_medium = 0, nodes_rerun = 0, waves = 0;
@@ -881,6 +882,7 @@ class Driver {
             rec.taxa = task.taxa;
             rec.part = res.part;
             rec.stats = res.stats;
+            rec.wave = static_cast<int32_t>(out_.waves - 1);
             (task.shared ? sh_records_ : out_.records).push_back(std::move(rec));
         }
         for (Child &child : res.children) {
@@ -1056,6 +1058,23 @@ int64_t scs_supertree_num_records(const scs_supertree *tree) {
 int scs_supertree_record_size(const scs_supertree *tree, int64_t index) {
     if (!tree || index < 0 || index >= static_cast<int64_t>(tree->records.size())) return SCS_ERR_INVALID;
     return static_cast<int>(tree->records[index].taxa.size());
+}
+
+int scs_supertree_record_wave(const scs_supertree *tree, int64_t index) {
+    if (!tree || index < 0 || index >= static_cast<int64_t>(tree->records.size())) return SCS_ERR_INVALID;
+    return tree->records[index].wave;
+}
+
+int scs_nodes_split_medium_dev(scs_ctx *ctx, int num_nodes, const int32_t *node_n, const int32_t *tree_begin,
+                               const int64_t *part_offset, const uint64_t *seeds, int T, int64_t L,
+                               const int64_t *leaf_offsets_dev, const int32_t *leaf_taxon_dev, const int32_t *adj_depth_dev,
+                               const double *adj_val_dev, const int32_t *root_depth_dev, const double *tree_weight_dev,
+                               int contract_edges, int32_t *part_dev, scs_node_stats *stats, uint8_t *needs_rerun) {
+    if (!ctx) return SCS_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    return medium_batch(ctx, num_nodes, node_n, tree_begin, part_offset, seeds, T, L, leaf_offsets_dev, leaf_taxon_dev,
+                        adj_depth_dev, adj_val_dev, root_depth_dev, tree_weight_dev, contract_edges, part_dev, stats,
+                        needs_rerun);
 }
 
 int scs_supertree_record(const scs_supertree *tree, int64_t index, int32_t *taxa, int32_t *part, scs_node_stats *stats) {

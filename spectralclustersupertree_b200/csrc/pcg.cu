@@ -446,7 +446,7 @@ pcg_rows_kernel(int n, int row0, int words_per_row, BucketShape bs, int stride,
                 const EntryT *__restrict__ entries,
                 double *__restrict__ W, int32_t *__restrict__ C, uint32_t *__restrict__ adj_bits,
                 uint32_t *__restrict__ max_bits, double *__restrict__ degree_part, int32_t *__restrict__ bad,
-                BatchView batch) {
+                BatchView view) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nwarps = 1 << bs.warps_log2, nthreads = nwarps << 5;
     const int slots_total = stride << bs.warps_log2;
@@ -462,8 +462,8 @@ pcg_rows_kernel(int n, int row0, int words_per_row, BucketShape bs, int stride,
     int occ_base = 0;
     size_t w_row = static_cast<size_t>(blockIdx.x) * n;
     size_t bits_row = static_cast<size_t>(a) * words_per_row;
-    if (batch.nodes) {
-        const MedNode &nd = batch.nodes[batch.row_node[a]];
+    if (view.nodes) {
+        const MedNode &nd = view.nodes[view.row_node[a]];
         n = nd.n;
         occ_base = nd.row_base;
         const int a_loc = a - nd.row_base;

@@ -236,6 +236,8 @@ class Engine:
                     stats = NodeStats()
                     self._lib.scs_supertree_record(handle, i, ptr(taxa), ptr(part), ctypes.byref(stats))
                     out["records"].append((taxa, part, stats))
+                out["record_waves"] = [int(self._lib.scs_supertree_record_wave(handle, i))
+                                       for i in range(len(out["records"]))]
             return out
         finally:
             self._lib.scs_supertree_destroy(handle)
