@@ -437,6 +437,8 @@ def profile_step(args, arrays: dict) -> dict:
     from spectralclustersupertree_b200.engine import Engine, Forest, set_host_threads
 
     engine = Engine(0)
+    if args.small_limit >= 0:
+        engine.set_small_node_limit(args.small_limit)
     set_host_threads(max(1, min(16, os.cpu_count() or 1)))
     lib = _lib.load()
 
@@ -476,6 +478,8 @@ def gpu_line(args, arrays: dict) -> dict:
         dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dist = dist_mod
     engine = Engine(local_rank)
+    if args.small_limit >= 0:
+        engine.set_small_node_limit(args.small_limit)
     weighting = arrays["weighting"]
     # torchrun exports OMP_NUM_THREADS=1; give every rank its share of the host cores instead
     from spectralclustersupertree_b200.engine import set_host_threads
@@ -511,7 +515,8 @@ def gpu_line(args, arrays: dict) -> dict:
     mine = [recorded[taxa.tobytes()] for taxa, _, _ in traced["records"]]
     sharing = dist is not None and args.shard_min_n > 0
     shared = [sharing and i < traced["shared_records"] and t.n >= args.shard_min_n for i, (t, _) in enumerate(mine)]
-    replay = Replay(engine, mine, traced["record_waves"], shared=shared)
+    replay = Replay(engine, mine, traced["record_waves"], shared=shared,
+                    small_limit=args.small_limit if args.small_limit >= 0 else 64)
     spectral = [st for _, _, st in traced["records"] if st.n_components == 1]
     all_visits = [t.pair_updates() for t, _ in recorded.values()]
     job = {
@@ -691,6 +696,9 @@ def main() -> None:
     parser.add_argument("--reference-budget-s", type=float, default=600.0,
                         help="--impl reference: stop starting new full CPU runs after this many seconds "
                              "(one run is always timed)")
+    parser.add_argument("--small-limit", type=int, default=-1,
+                        help="tuning: nodes up to this many taxa take the one-CTA small-node path (default: the "
+                             "library's, 64); larger ones up to 4096 the batched medium path")
     parser.add_argument("--profile-step", action="store_true",
                         help="for ncu: no recording pass, no replay, no CPU baseline -- one warm-up job, then exactly "
                              "one scs_supertree_build bracketed by cudaProfilerStart/Stop "

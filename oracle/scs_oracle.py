@@ -123,6 +123,7 @@ def _c_lib():
             _build.build()
         lib = ctypes.CDLL(str(path))
         lib.pcg_oracle_dense.restype = ctypes.c_int
+        lib.pcg_oracle_rows.restype = ctypes.c_int
         _C_LIB = lib
     return _C_LIB
 
@@ -185,6 +186,25 @@ def pcg_dense_c_arrays(n, roots, child_ptr, child_idx, tip_taxon, own, weights, 
         msg = f"pcg_oracle_dense failed with code {rc}"
         raise RuntimeError(msg)
     return W, C, occ
+
+
+def pcg_rows_c_arrays(n, roots, child_ptr, child_idx, tip_taxon, own, weights, weighting: str, row_lo: int, row_hi: int):
+    """Rows [row_lo, row_hi) of the dense W and C (oracle/pcg_oracle.c:pcg_oracle_rows): the same ordered sums as
+    ``pcg_dense_c_arrays`` without the n x n memory, for checks at 50 000 taxa."""
+    lib = _c_lib()
+    rows = row_hi - row_lo
+    W = np.zeros((rows, n), dtype=np.float64)
+    C = np.zeros((rows, n), dtype=np.int32)
+    w = np.ascontiguousarray(np.asarray(list(weights), dtype=np.float64))
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    rc = lib.pcg_oracle_rows(
+        ctypes.c_int64(n), ctypes.c_int64(len(roots)), p(roots), p(child_ptr), p(child_idx), p(tip_taxon), p(own),
+        p(w), ctypes.c_int(WEIGHTINGS.index(weighting)), ctypes.c_int64(row_lo), ctypes.c_int64(row_hi), p(W), p(C),
+    )  # fmt: skip
+    if rc != 0:
+        msg = f"pcg_oracle_rows failed with code {rc}"
+        raise RuntimeError(msg)
+    return W, C
 
 
 # ---------------------------------------------------------------------------------------------

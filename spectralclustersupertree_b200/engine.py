@@ -401,6 +401,40 @@ class Engine:
             for d in (d_W, d_s, d_x, d_y):
                 self.free(d)
 
+    def last_node_pointers(self) -> dict:
+        """Device addresses and shape of the node most recently split (``scs_node_last_buffers``): for checks that
+        cannot afford host copies of whole matrices."""
+        n, m = ctypes.c_int(0), ctypes.c_int(0)
+        ptrs = [ctypes.c_void_p() for _ in range(7)]
+        _check(
+            self._lib.scs_node_last_buffers(self._ctx, ctypes.byref(n), ctypes.byref(m), *[ctypes.byref(p) for p in ptrs]),
+            self._ctx,
+        )
+        names = ("W", "adj_bits", "max_bits", "occ", "degree", "Wc", "group")
+        out = {k: p.value for k, p in zip(names, ptrs, strict=True)}
+        out.update({"n": n.value, "m": m.value})
+        return out
+
+    def last_node_rows(self, row_lo: int, row_hi: int) -> tuple[np.ndarray, np.ndarray]:
+        """Rows [row_lo, row_hi) of W and of the adjacency bits of the node most recently split."""
+        p = self.last_node_pointers()
+        n = p["n"]
+        words = self._lib.scs_bit_words(n)
+        W = self.to_host(p["W"] + 8 * row_lo * n, (row_hi - row_lo, n), np.float64)
+        bits = self.to_host(p["adj_bits"] + 4 * row_lo * words, (row_hi - row_lo, words), np.uint32)
+        return W, bits
+
+    def matvec_on_device(self, m: int, W_dev: int, isd_dev: int, x: np.ndarray) -> np.ndarray:
+        """y = D^-1/2 W D^-1/2 x with W and 1/sqrt(d) already on the device (``scs_normalized_matvec_dev``)."""
+        d_x = self.to_device(np.ascontiguousarray(x, dtype=np.float64))
+        d_y = self.alloc(8 * m)
+        try:
+            _check(self._lib.scs_normalized_matvec_dev(self._ctx, m, W_dev, isd_dev, d_x, d_y), self._ctx)
+            return self.to_host(d_y, (m,), np.float64)
+        finally:
+            self.free(d_x)
+            self.free(d_y)
+
     def last_node_buffers(self) -> dict:
         """Host copies of the device buffers of the node most recently split (parity tests)."""
         n, m = ctypes.c_int(0), ctypes.c_int(0)

@@ -52,3 +52,55 @@ def test_every_recursion_node_against_the_oracle_trace(engine, workload):
     assert not outside, (len(outside), len(ours ^ reference))
     assert int((built["taxon"] >= 0).sum()) == len(names)
     print(workload, {k: v for k, v in report.items() if k != "divergent_nodes"}, "RF", len(ours ^ reference))
+
+
+def test_c5_top_level_rows_and_fiedler_value(engine):
+    """C5 (50 000 taxa x 5 000 trees, branch): the 20 GB W of the top-level node cannot be compared whole, so
+    (1) blocks of its rows are compared bit for bit with the C oracle restricted to those rows
+    (oracle/pcg_oracle.c:pcg_oracle_rows, itself pinned to the dense oracle by tests/test_oracle_golden.py), and
+    (2) the Fiedler eigenvalue of the first connected recursion node below it is compared (1e-6) with ARPACK
+    (scipy eigsh) iterating on the same device-resident operator through scs_normalized_matvec_dev."""
+    import bench
+    from oracle import scs_oracle
+    from scipy.sparse.linalg import LinearOperator, eigsh
+    from spectralclustersupertree_b200.engine import unpack_bits
+
+    arrays, forest = _workload_forest("c5")
+    n = len(arrays["names"])
+    taxa, part, stats = engine.forest_split(forest, "branch", contract_edges=True, seed=1)
+    assert len(taxa) == n
+    csr = bench.oracle_children_csr(arrays)
+    rng = np.random.RandomState(11)
+    for lo in (0, int(rng.randint(1000, n - 1000)), n - 8):
+        Wg, bits = engine.last_node_rows(lo, lo + 8)
+        Wo, Co = scs_oracle.pcg_rows_c_arrays(n, *csr, arrays["weights"], "branch", lo, lo + 8)
+        assert np.array_equal(Wg, Wo), lo  # bit-exact, branch weighting
+        assert np.array_equal(unpack_bits(bits, n), Co > 0), lo
+    # walk down the largest component until a node goes through the spectral step
+    sub = forest
+    for _ in range(12):
+        if stats.n_components == 1:
+            break
+        sub = sub.induce(taxa[part == np.argmax(np.bincount(part))])
+        taxa, part, stats = engine.forest_split(sub, "branch", contract_edges=True, seed=1)
+    assert stats.n_components == 1 and stats.solver == 3
+    p = engine.last_node_pointers()
+    m = p["m"] if p["m"] else p["n"]
+    W_dev = p["Wc"] if p["m"] and p["m"] != p["n"] else p["W"]
+    ones = np.ones(m)
+    d_ones = engine.to_device(ones)
+    try:
+        degree = engine.matvec_on_device(m, W_dev, d_ones, ones)  # isd = 1, x = 1: the row sums
+    finally:
+        engine.free(d_ones)
+    isd = np.where(degree > 0, 1.0 / np.sqrt(np.where(degree > 0, degree, 1.0)), 1.0)
+    d_isd = engine.to_device(isd)
+    try:
+        op = LinearOperator((m, m), matvec=lambda x: engine.matvec_on_device(m, W_dev, d_isd, x), dtype=np.float64)
+        vals = eigsh(op, k=3, which="LA", tol=1e-12, v0=np.ones(m), return_eigenvectors=False)
+    finally:
+        engine.free(d_isd)
+    vals = np.sort(vals)[::-1]  # 1 (trivial), then 1 - lambda_2
+    assert abs(vals[0] - 1.0) < 1e-9
+    assert abs((1.0 - vals[1]) - stats.eig[1]) < 1e-6, (1.0 - vals[1], stats.eig[1])
+    print("c5: n", n, "spectral node m", m, "lambda2", stats.eig[1], "ARPACK", 1.0 - vals[1], "matvecs", stats.matvecs)

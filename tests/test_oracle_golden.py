@@ -91,3 +91,18 @@ def test_oracle_eigenvalues_match_trace():
     vals, _ = scs_oracle.normalized_affinity_eigs(Wc, 3)
     assert np.allclose(vals, node["eigenvalues"], atol=1e-10)
     assert ref["W"].shape[0] == len(case["names"])
+
+
+@pytest.mark.parametrize("name", ["c2_500x50_branch", "s_200x40_bootstrap", "supertriplets"])
+def test_row_block_oracle_equals_the_dense_oracle(name):
+    """oracle/pcg_oracle.c:pcg_oracle_rows (tip-wise, a block of rows) against pcg_oracle_dense (node-wise, the whole
+    matrix) and against the reference's own W: bit for bit."""
+    case = load_case(name)
+    trees = parse(case["lines"])
+    tid = {x: i for i, x in enumerate(case["names"])}
+    arrs = scs_oracle.children_csr(trees, tid, case["weighting"])
+    n = len(tid)
+    for lo, hi in [(0, 7), (n // 2, n // 2 + 13), (n - 5, n)]:
+        Wr, Cr = scs_oracle.pcg_rows_c_arrays(n, *arrs, case["weights"], case["weighting"], lo, hi)
+        assert np.array_equal(Wr, case["pcg"]["W"][lo:hi])
+        assert np.array_equal(Cr, case["pcg"]["C"][lo:hi])

@@ -17,6 +17,8 @@ for stage in "$@"; do
       done ;;
     bench)
       python bench.py --steps 5 --warmup 3 > gpurun_out/${tag}_bench_c4.json 2> gpurun_out/${tag}_bench_c4.err; echo "bench c4 rc=$?"; head -c 600 gpurun_out/${tag}_bench_c4.json ;;
+    bench32)
+      python bench.py --steps 5 --warmup 3 --small-limit 32 --no-cpu-baseline > gpurun_out/${tag}_bench_c4_small32.json 2> gpurun_out/${tag}_bench_c4_small32.err; echo "bench c4 small32 rc=$?"; head -c 300 gpurun_out/${tag}_bench_c4_small32.json ;;
     launches)
       python bench.py --profile-step > gpurun_out/${tag}_profile_step.json 2> gpurun_out/${tag}_profile_step.err; rc=$?; echo "profile-step rc=$rc"; cat gpurun_out/${tag}_profile_step.json
       if [ $rc -eq 0 ]; then
