@@ -98,6 +98,10 @@ int scs_ctx_set_small_node_limit(scs_ctx *ctx, int limit);
  * build, components, contraction, Lanczos steps in lock-step, 2-means) is one launch over all of them.
  * 0 sends them down the per-node staged path instead. */
 int scs_ctx_set_medium_node_limit(scs_ctx *ctx, int limit);
+/* scs_supertree_build on one GPU keeps the source trees resident on the device for the whole recursion: tours and
+ * the restriction of the trees to the children of a split (scs.py:411-455) are computed there (on = 1, the default).
+ * on = 0 keeps them on the host (flat arrays restricted by the host threads, tours copied to the device per wave). */
+int scs_ctx_set_device_forest(scs_ctx *ctx, int on);
 /* Graph build: use the 8-byte {tour position, slot} bucket entries that nodes of 65 536 taxa or more need
  * at every size (on = 1; for tests of that path). */
 int scs_ctx_set_wide_entries(scs_ctx *ctx, int on);

@@ -176,6 +176,7 @@ struct scs_ctx {
     bool contract_configured = false;
     bool kmeans_configured = false;
     bool medium_configured = false;
+    bool device_forest = true;  // scs_supertree_build on one GPU keeps the source trees on the device (devdriver.cu)
     int medium_limit = scs::kMediumMaxDefault;  // nodes up to this size (and above small_limit) go through the batched path
     bool wide_entries = false;  // graph build: 8-byte bucket entries even where 4 bytes would do (tests)
     int small_limit = 64;  // nodes up to this size take the one-CTA path (0 disables it)
@@ -292,12 +293,13 @@ int pcg_build_batch(scs_ctx *ctx, int R, int T, int64_t L, int max_n, int max_tr
 constexpr int kMediumMax = kMediumMaxDefault;  // recursion nodes up to this many vertices can go through the batched path
 
 // A batch of recursion nodes (kSmallNode < n <= kMediumMax is what the driver sends), every stage one launch over
-// all of them (medium.cu).  Tours: concatenated, node b owns trees [tree_begin[b], tree_begin[b+1]) and their
-// leaves; leaf_offsets[T + 1] absolute; all tour pointers are device pointers.  part_dev receives the labels of
-// node b at part_off[b]; stats_host[b] its record.  needs_rerun[b] is set when the node has to go through
-// scs_node_split_* instead (eigensolver restart or a repeated-eigenvalue check: rare).
-int medium_batch(scs_ctx *ctx, int B, const int32_t *node_n, const int32_t *tree_begin, const int64_t *part_off,
-                 const uint64_t *seeds, int T, int64_t L, const int64_t *leaf_offsets, const int32_t *leaf_taxon,
+// all of them (medium.cu).  Tours: concatenated, node b owns trees [tree_begin[b], tree_end[b]) (ascending, disjoint;
+// trees in between belong to nobody and are skipped) and their leaves; leaf_offsets[T + 1] absolute; all tour
+// pointers are device pointers.  part_dev receives the labels of node b at part_off[b]; stats_host[b] its record.
+// needs_rerun[b] is set when the node has to go through scs_node_split_* instead (eigensolver restart or a
+// repeated-eigenvalue check: rare).
+int medium_batch(scs_ctx *ctx, int B, const int32_t *node_n, const int32_t *tree_begin, const int32_t *tree_end,
+                 const int64_t *part_off, const uint64_t *seeds, int T, int64_t L, const int64_t *leaf_offsets, const int32_t *leaf_taxon,
                  const int32_t *adj_depth, const double *adj_val, const int32_t *root_depth, const double *tree_weight,
                  int contract_edges, int32_t *part_dev, scs_node_stats *stats_host, uint8_t *needs_rerun);
 
@@ -308,10 +310,12 @@ int small_node(scs_ctx *ctx, int n, int contract_edges, const double *W, const u
                double *Wc_out);
 
 // A batch of small nodes, one CTA each, graph build included; all pointers are device pointers.
+// absolute_offsets: leaf_offsets[tree_base + t] is the absolute tour position of tree t of a node (the device forest's
+// layout); otherwise node b reads leaf_offsets[tree_base + b + t], relative to its leaf_base (scs_small_node's layout).
 int small_batch(scs_ctx *ctx, int num_nodes, const scs_small_node *nodes_dev, const int64_t *leaf_offsets,
                 const int32_t *leaf_taxon, const int32_t *adj_depth, const double *adj_val, const int32_t *root_depth,
                 const double *tree_weight, int contract_edges, int32_t *part_dev, scs_node_stats *stats_dev,
-                int32_t *bad_dev);
+                int32_t *bad_dev, int absolute_offsets = 0);
 
 // One recursion node on device-resident tours.  part_dev[n] receives the component index or side;
 // if part_host is not null the result is also copied there before the function returns.

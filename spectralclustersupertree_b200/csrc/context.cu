@@ -454,6 +454,12 @@ int scs_ctx_set_medium_node_limit(scs_ctx *ctx, int limit) {
     return SCS_OK;
 }
 
+int scs_ctx_set_device_forest(scs_ctx *ctx, int on) {
+    if (!ctx) return SCS_ERR_INVALID;
+    ctx->device_forest = on != 0;
+    return SCS_OK;
+}
+
 int scs_ctx_set_wide_entries(scs_ctx *ctx, int on) {
     if (!ctx) return SCS_ERR_INVALID;
     ctx->wide_entries = on != 0;

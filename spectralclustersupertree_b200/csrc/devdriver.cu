@@ -1,0 +1,458 @@
+// The supertree recursion with the source trees resident on the device.
+//
+// Same control flow as driver.cu (the reference's construct_supertree, /root/reference/src/sc_supertree/scs.py:96-174,
+// breadth-first over the independent sub-problems), but the forests never come back to the host: the original trees
+// are uploaded once; per wave the leaf tours of every sub-problem are derived on the device (devforest.cu: df_tours),
+// the nodes are split there (small batch / medium batch / per-node path, all reading the same device-resident
+// tours), and the trees are restricted to the children on the device (devforest_restrict, the replacement of
+// _generate_induced_trees_with_weights, scs.py:411-455).  What crosses the bus per wave is bookkeeping: vertex ids
+// and part owners of the taxa down (4 bytes per taxon each), partitions, per-node records, per-child tree counts and
+// a presence byte per taxon up.  The host keeps what the reference keeps outside its tree objects: which taxa belong
+// to which sub-problem, and the output tree.
+
+#include "common.cuh"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <thread>
+
+#include "devforest.cuh"
+#include "driver.hpp"
+#include "forest.hpp"
+
+namespace scs {
+
+namespace {
+
+struct Stopwatch {
+    double *sink;
+    std::chrono::steady_clock::time_point t0;
+    explicit Stopwatch(double *s) : sink(s), t0(std::chrono::steady_clock::now()) {}
+    ~Stopwatch() { *sink += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
+// A sub-problem of the current wave: a set of taxa and its trees in the wave's device forest.
+struct Job {
+    int32_t slot = 0;           // output node it fills in
+    std::vector<int32_t> taxa;  // taxa present in its trees, ascending (vertex id = rank; scs.py:708-725)
+    DevJobInfo where{};         // its trees / leaves / nodes in the wave's forest
+    int64_t leaves = 0;         // tour positions of its trees
+};
+
+__global__ void relative_offsets(int count, const int64_t *__restrict__ absolute, int64_t *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = absolute[i] - absolute[0];
+}
+
+class DeviceDriver {
+  public:
+    DeviceDriver(scs_ctx *ctx, int weighting, int contract_edges, uint64_t seed, bool record, scs_supertree *out)
+        : ctx_(ctx), weighting_(weighting), contract_(contract_edges), seed_(seed), record_(record), out_(*out) {}
+
+    ~DeviceDriver() {
+        forest_[0].free_all(ctx_);
+        forest_[1].free_all(ctx_);
+        tours_.free_all(ctx_);
+        release(ctx_, vertex_dev_);
+        release(ctx_, offsets_rel_);
+        release(ctx_, small_desc_dev_);
+        release(ctx_, part_dev_);
+        release(ctx_, flags_dev_);
+        cudaStreamSynchronize(ctx_->stream);
+    }
+
+    int run(const scs_forest *root) {
+        num_taxa_ = scs_forest_num_taxa(root);
+        int rc;
+        {
+            Stopwatch sw(&out_.seconds[3]);
+            if ((rc = devforest_upload(ctx_, root, weighting_, &forest_[0]))) return rc;
+        }
+        vertex_.assign(static_cast<size_t>(num_taxa_ > 0 ? num_taxa_ : 1), -1);
+        owner_.assign(vertex_.size(), -1);
+        present_.assign(vertex_.size(), 0);
+        if ((rc = grow(ctx_, flags_dev_, 64 * sizeof(int32_t)))) return rc;
+        SCS_CUDA(ctx_, cudaMemsetAsync(flags_dev_.ptr, 0, 64 * sizeof(int32_t), ctx_->stream));
+
+        std::vector<Job> wave(1), next;
+        wave[0].slot = add(-1, -1);
+        {
+            std::vector<uint8_t> seen(vertex_.size(), 0);
+            for (int32_t x : root->taxon)
+                if (x >= 0) seen[x] = 1;
+            for (int x = 0; x < num_taxa_; ++x)
+                if (seen[x]) wave[0].taxa.push_back(x);
+        }
+        const int T = root->num_trees();
+        wave[0].where.trees = T;
+        wave[0].where.first_tree_nodes = T > 0 ? root->node_offsets[1] - root->node_offsets[0] : 0;
+        wave[0].where.pair_visits = scs_forest_pair_visits(root);
+        wave[0].leaves = root->leaf_offsets.back();
+        cur_ = 0;
+        while (!wave.empty()) {
+            out_.waves += 1;
+            int32_t max_n = 0;
+            for (const Job &job : wave) max_n = std::max<int32_t>(max_n, static_cast<int32_t>(job.taxa.size()));
+            out_.wave_tasks.push_back(static_cast<int32_t>(wave.size()));
+            out_.wave_max_n.push_back(max_n);
+            const double before_gpu = out_.seconds[0] + out_.seconds[1] + out_.medium_seconds, before_restrict = out_.seconds[2];
+            const auto wave_start = std::chrono::steady_clock::now();
+            next.clear();
+            if ((rc = process_wave(wave, next))) return rc;
+            out_.wave_seconds.push_back(out_.seconds[0] + out_.seconds[1] + out_.medium_seconds - before_gpu);
+            out_.wave_seconds.push_back(out_.seconds[2] - before_restrict);
+            out_.wave_seconds.push_back(std::chrono::duration<double>(std::chrono::steady_clock::now() - wave_start).count());
+            wave.swap(next);
+        }
+        return SCS_OK;
+    }
+
+  private:
+    // ---- output nodes (scs.py:390-408, 728-746) -----------------------------------------------------------------------
+    int32_t add(int32_t parent, int32_t taxon) {
+        out_.parent.push_back(parent);
+        out_.taxon.push_back(taxon);
+        return static_cast<int32_t>(out_.parent.size() - 1);
+    }
+    void fill_star(int32_t slot, const int32_t *taxa, int count) {  // one name stays a tip, more become a star
+        if (count == 1) {
+            out_.taxon[slot] = taxa[0];
+            return;
+        }
+        for (int i = 0; i < count; ++i) add(slot, taxa[i]);
+    }
+
+    struct Split {
+        size_t job = 0;
+        int64_t part_at = 0;  // where its labels are in part_
+        scs_node_stats stats{};
+        int32_t parts = 0, part_base = 0;
+    };
+
+    int process_wave(std::vector<Job> &wave, std::vector<Job> &next) {
+        const DevForest &forest = forest_[cur_];
+        int rc;
+        // ---- what each sub-problem is (scs.py:96-106) -------------------------------------------------------------------
+        std::vector<size_t> single, small, medium, large;
+        for (size_t i = 0; i < wave.size(); ++i) {
+            const Job &job = wave[i];
+            const int n = static_cast<int>(job.taxa.size());
+            if (job.where.trees == 0) return fail(ctx_, SCS_ERR_EMPTY, "a component is covered by no source tree (scs.py:63-65)");
+            if (job.where.trees == 1) single.push_back(i);
+            else if (n <= 2) fill_star(job.slot, job.taxa.data(), n);
+            else if (n <= ctx_->small_limit && job.where.trees <= kSmallMaxTrees) small.push_back(i);
+            else if (n <= ctx_->medium_limit) medium.push_back(i);
+            else large.push_back(i);
+        }
+        if (!single.empty() && (rc = copy_single_trees(wave, single))) return rc;
+        std::vector<Split> splits;
+        if (!small.empty() || !medium.empty() || !large.empty()) {
+            // ---- tours of the whole wave on the device -----------------------------------------------------------------
+            {
+                Stopwatch sw(&out_.seconds[3]);
+                for (const std::vector<size_t> *kind : {&small, &medium, &large})
+                    for (size_t i : *kind) {
+                        const std::vector<int32_t> &taxa = wave[i].taxa;
+                        for (size_t v = 0; v < taxa.size(); ++v) vertex_[taxa[v]] = static_cast<int32_t>(v);
+                    }
+                if ((rc = upload_ints(vertex_dev_, vertex_.data(), vertex_.size()))) return rc;
+                if ((rc = devforest_tours(ctx_, forest, weighting_, vertex_dev_.as<int32_t>(), &tours_, flags_dev_.as<int32_t>())))
+                    return rc;
+            }
+            // ---- split the nodes: labels of all of them land in one array ----------------------------------------------
+            int64_t labels = 0;
+            for (const std::vector<size_t> *kind : {&large, &medium, &small})
+                for (size_t i : *kind) {
+                    Split s;
+                    s.job = i;
+                    s.part_at = labels;
+                    labels += static_cast<int64_t>(wave[i].taxa.size());
+                    splits.push_back(s);
+                    out_.pair_visits += wave[i].where.pair_visits;
+                }
+            part_.resize(static_cast<size_t>(labels) + 1);
+            if ((rc = grow(ctx_, part_dev_, (static_cast<size_t>(labels) + 1) * sizeof(int32_t)))) return rc;
+            size_t at = 0;
+            if (!large.empty()) {
+                Stopwatch sw(&out_.seconds[0]);
+                for (size_t k = 0; k < large.size(); ++k)
+                    if ((rc = split_large(wave[large[k]], splits[at + k]))) return rc;
+                out_.nodes_large += static_cast<int64_t>(large.size());
+            }
+            at += large.size();
+            if (!medium.empty()) {
+                Stopwatch sw(&out_.medium_seconds);
+                if ((rc = split_medium(wave, medium, splits.data() + at))) return rc;
+            }
+            at += medium.size();
+            if (!small.empty()) {
+                Stopwatch sw(&out_.seconds[1]);
+                if ((rc = split_small(wave, small, splits.data() + at))) return rc;
+                out_.nodes_small += static_cast<int64_t>(small.size());
+            }
+            // labels of every node of the wave, and the malformed-input flags, in one copy each
+            SCS_CUDA(ctx_, cudaMemcpyAsync(part_.data(), part_dev_.as<int32_t>(), sizeof(int32_t) * static_cast<size_t>(labels),
+                                           cudaMemcpyDeviceToHost, ctx_->stream));
+            int32_t flags[4] = {0, 0, 0, 0};
+            SCS_CUDA(ctx_, cudaMemcpyAsync(flags, flags_dev_.ptr, sizeof(flags), cudaMemcpyDeviceToHost, ctx_->stream));
+            SCS_CUDA(ctx_, cudaStreamSynchronize(ctx_->stream));
+            ctx_->d2h_bytes += static_cast<int64_t>(sizeof(int32_t)) * labels;
+            if (flags[0]) return fail(ctx_, SCS_ERR_INPUT, "leaf tour: taxon id out of range");
+            if (flags[1]) return fail(ctx_, SCS_ERR_INPUT, "bootstrap weighting: an internal node without support");
+            for (const Split &s : splits)
+                if (s.stats.solver == -1) return fail(ctx_, SCS_ERR_TOO_SMALL, "spectral step on a graph contracted to one vertex");
+        }
+        if (splits.empty()) return SCS_OK;
+        // ---- children (scs.py:136-171) ---------------------------------------------------------------------------------
+        Stopwatch sw(&out_.seconds[2]);
+        return plan_children(wave, splits, next);
+    }
+
+    int upload_ints(GrowBuf &dev, const int32_t *host, size_t count) {
+        int rc;
+        if ((rc = grow(ctx_, dev, count * sizeof(int32_t)))) return rc;
+        void *pin_v;
+        if ((rc = reserve_pinned(ctx_, count * sizeof(int32_t) + 256, &pin_v))) return rc;
+        std::memcpy(pin_v, host, count * sizeof(int32_t));
+        SCS_CUDA(ctx_, cudaMemcpyAsync(dev.ptr, pin_v, count * sizeof(int32_t), cudaMemcpyHostToDevice, ctx_->stream));
+        // the pinned block is reused by the calls that follow: the copy must have left it
+        SCS_CUDA(ctx_, cudaStreamSynchronize(ctx_->stream));
+        ctx_->h2d_bytes += static_cast<int64_t>(count * sizeof(int32_t));
+        return SCS_OK;
+    }
+
+    // topology-only copies of the single remaining trees (scs.py:96-98), fetched in one piece
+    int copy_single_trees(const std::vector<Job> &wave, const std::vector<size_t> &single) {
+        const int count = static_cast<int>(single.size());
+        std::vector<int64_t> first(count), nodes(count);
+        int64_t total = 0;
+        for (int i = 0; i < count; ++i) {
+            first[i] = wave[single[i]].where.node_begin;
+            nodes[i] = wave[single[i]].where.first_tree_nodes;
+            total += nodes[i];
+        }
+        std::vector<int32_t> par(static_cast<size_t>(total) + 1), tax(static_cast<size_t>(total) + 1);
+        int rc = devforest_fetch_trees(ctx_, forest_[cur_], count, first.data(), nodes.data(), par.data(), tax.data());
+        if (rc) return rc;
+        int64_t at = 0;
+        std::vector<int32_t> where;
+        for (int i = 0; i < count; ++i) {
+            const int32_t slot = wave[single[i]].slot;
+            where.assign(static_cast<size_t>(nodes[i]), 0);
+            where[0] = slot;
+            out_.taxon[slot] = tax[at];
+            for (int64_t k = 1; k < nodes[i]; ++k) where[k] = add(where[par[at + k]], tax[at + k]);
+            at += nodes[i];
+        }
+        return SCS_OK;
+    }
+
+    // ---- the three node paths, all on the wave's device-resident tours --------------------------------------------------
+    int split_large(const Job &job, Split &s) {
+        const DevForest &forest = forest_[cur_];
+        const int n = static_cast<int>(job.taxa.size());
+        const int T = job.where.trees;
+        int rc;
+        if ((rc = grow(ctx_, offsets_rel_, (static_cast<size_t>(T) + 1) * sizeof(int64_t)))) return rc;
+        relative_offsets<<<ceil_div(T + 1, 256), 256, 0, ctx_->stream>>>(T + 1, forest.leaf_off.as<int64_t>() + job.where.tree_begin,
+                                                                        offsets_rel_.as<int64_t>());
+        SCS_LAUNCHED(ctx_, "relative_offsets");
+        const int64_t L = job.leaves;
+        ctx_->pending_units = static_cast<double>(job.where.pair_visits);
+        std::memset(&s.stats, 0, sizeof(s.stats));
+        s.stats.eig[1] = s.stats.eig[2] = s.stats.residual = s.stats.margin = std::nan("");
+        rc = node_split(ctx_, n, T, L, offsets_rel_.as<int64_t>(), tours_.leaf_taxon.as<int32_t>() + job.where.leaf_begin,
+                        tours_.adj_depth.as<int32_t>() + job.where.leaf_begin, tours_.adj_val.as<double>() + job.where.leaf_begin,
+                        tours_.root_depth.as<int32_t>() + job.where.tree_begin, forest.weight.as<double>() + job.where.tree_begin,
+                        contract_, seed_ + static_cast<uint64_t>(job.slot), part_dev_.as<int32_t>() + s.part_at, nullptr,
+                        &s.stats);
+        ctx_->pending_units = 0.0;
+        return rc;
+    }
+
+    int split_medium(std::vector<Job> &wave, const std::vector<size_t> &medium, Split *splits) {
+        const DevForest &forest = forest_[cur_];
+        const int B = static_cast<int>(medium.size());
+        std::vector<int32_t> node_n(B), tree_begin(B), tree_end(B);
+        std::vector<int64_t> part_off(B);
+        std::vector<uint64_t> seeds(B);
+        for (int b = 0; b < B; ++b) {
+            const Job &job = wave[medium[b]];
+            node_n[b] = static_cast<int32_t>(job.taxa.size());
+            tree_begin[b] = job.where.tree_begin;
+            tree_end[b] = job.where.tree_begin + job.where.trees;
+            part_off[b] = splits[b].part_at;
+            seeds[b] = seed_ + static_cast<uint64_t>(job.slot);
+        }
+        std::vector<scs_node_stats> stats(B);
+        std::vector<uint8_t> rerun(B, 0);
+        int rc = medium_batch(ctx_, B, node_n.data(), tree_begin.data(), tree_end.data(), part_off.data(), seeds.data(),
+                              static_cast<int>(forest.trees), forest.leaves, forest.leaf_off.as<int64_t>(),
+                              tours_.leaf_taxon.as<int32_t>(), tours_.adj_depth.as<int32_t>(), tours_.adj_val.as<double>(),
+                              tours_.root_depth.as<int32_t>(), forest.weight.as<double>(), contract_, part_dev_.as<int32_t>(),
+                              stats.data(), rerun.data());
+        if (rc) return rc;
+        out_.nodes_medium += B;
+        for (int b = 0; b < B; ++b) {
+            splits[b].stats = stats[b];
+            if (!rerun[b]) continue;
+            // eigensolver restart / repeated-eigenvalue check: the per-node path has both
+            out_.nodes_rerun += 1;
+            if ((rc = split_large(wave[medium[b]], splits[b]))) return rc;
+        }
+        return SCS_OK;
+    }
+
+    int split_small(std::vector<Job> &wave, const std::vector<size_t> &small, Split *splits) {
+        const DevForest &forest = forest_[cur_];
+        const int B = static_cast<int>(small.size());
+        std::vector<scs_small_node> desc(B);
+        for (int b = 0; b < B; ++b) {
+            const Job &job = wave[small[b]];
+            desc[b].n = static_cast<int32_t>(job.taxa.size());
+            desc[b].num_trees = job.where.trees;
+            desc[b].leaf_base = job.where.leaf_begin;
+            desc[b].tree_base = job.where.tree_begin;
+            desc[b].vertex_base = splits[b].part_at;
+        }
+        int rc;
+        const size_t bytes = sizeof(scs_small_node) * static_cast<size_t>(B);
+        if ((rc = grow(ctx_, small_desc_dev_, bytes))) return rc;
+        void *pin_v;
+        if ((rc = reserve_pinned(ctx_, bytes + sizeof(scs_node_stats) * static_cast<size_t>(B) + 512, &pin_v))) return rc;
+        unsigned char *pin = static_cast<unsigned char *>(pin_v);
+        std::memcpy(pin, desc.data(), bytes);
+        SCS_CUDA(ctx_, cudaMemcpyAsync(small_desc_dev_.ptr, pin, bytes, cudaMemcpyHostToDevice, ctx_->stream));
+        ctx_->h2d_bytes += static_cast<int64_t>(bytes);
+        scs_node_stats *stats_dev;
+        if ((rc = reserve_as(ctx_, SLOT_NODE_STATS, static_cast<size_t>(B), &stats_dev))) return rc;
+        rc = small_batch(ctx_, B, small_desc_dev_.as<scs_small_node>(), forest.leaf_off.as<int64_t>(), tours_.leaf_taxon.as<int32_t>(),
+                         tours_.adj_depth.as<int32_t>(), tours_.adj_val.as<double>(), tours_.root_depth.as<int32_t>(),
+                         forest.weight.as<double>(), contract_, part_dev_.as<int32_t>(), stats_dev, flags_dev_.as<int32_t>(), 1);
+        if (rc) return rc;
+        scs_node_stats *stats_pin = reinterpret_cast<scs_node_stats *>(pin + ((bytes + 255) & ~static_cast<size_t>(255)));
+        SCS_CUDA(ctx_, cudaMemcpyAsync(stats_pin, stats_dev, sizeof(scs_node_stats) * static_cast<size_t>(B), cudaMemcpyDeviceToHost,
+                                       ctx_->stream));
+        SCS_CUDA(ctx_, cudaStreamSynchronize(ctx_->stream));
+        ctx_->d2h_bytes += static_cast<int64_t>(sizeof(scs_node_stats)) * B;
+        for (int b = 0; b < B; ++b) splits[b].stats = stats_pin[b];
+        return SCS_OK;
+    }
+
+    // ---- what the split nodes turn into (scs.py:136-171): stars, sub-problems with restricted trees, singletons ---------
+    int plan_children(std::vector<Job> &wave, std::vector<Split> &splits, std::vector<Job> &next) {
+        const int J = static_cast<int>(wave.size());
+        std::vector<int32_t> job_tree_begin(static_cast<size_t>(J) + 1, 0), job_parts(J, 0), job_part_base(J, 0);
+        for (int j = 0; j < J; ++j) job_tree_begin[j] = wave[j].where.tree_begin;
+        job_tree_begin[J] = static_cast<int32_t>(forest_[cur_].trees);
+        std::sort(splits.begin(), splits.end(), [](const Split &a, const Split &b) { return a.job < b.job; });
+        struct Pending {
+            int32_t parent_slot;
+            std::vector<int32_t> members;  // taxa of the component, ascending
+        };
+        std::vector<Pending> pending;      // one per new job
+        std::vector<int32_t> part_newjob;  // global part -> new job or -1
+        std::vector<int32_t> start, members, cursor;
+        for (Split &s : splits) {
+            const Job &job = wave[s.job];
+            const std::vector<int32_t> &taxa = job.taxa;
+            const int n = static_cast<int>(taxa.size());
+            const int parts = s.stats.n_components != 1 ? s.stats.n_components : 2;
+            const int32_t *part = part_.data() + s.part_at;
+            if (record_) {
+                scs_supertree::Record rec;
+                rec.taxa = taxa;
+                rec.part.assign(part, part + n);
+                rec.stats = s.stats;
+                rec.wave = static_cast<int32_t>(out_.waves - 1);
+                out_.records.push_back(std::move(rec));
+            }
+            start.assign(parts + 1, 0);
+            for (int v = 0; v < n; ++v) {
+                if (part[v] < 0 || part[v] >= parts) return fail(ctx_, SCS_ERR_INVALID, "a partition label is out of range");
+                start[part[v] + 1] += 1;
+            }
+            for (int c = 0; c < parts; ++c) start[c + 1] += start[c];
+            members.resize(n);
+            cursor.assign(start.begin(), start.end() - 1);
+            for (int v = 0; v < n; ++v) members[cursor[part[v]]++] = taxa[v];
+            s.parts = parts;
+            s.part_base = static_cast<int32_t>(part_newjob.size());
+            job_parts[s.job] = parts;
+            job_part_base[s.job] = s.part_base;
+            for (int c = 0; c < parts; ++c) {
+                const int32_t *comp = members.data() + start[c];
+                const int size = start[c + 1] - start[c];
+                if (size == 0) {
+                    part_newjob.push_back(-1);
+                    continue;
+                }
+                const int32_t child_slot = add(job.slot, -1);
+                if (size <= 2) {  // scs.py:143-145
+                    fill_star(child_slot, comp, size);
+                    for (int i = 0; i < size; ++i) owner_[comp[i]] = -1;
+                    part_newjob.push_back(-1);
+                    continue;
+                }
+                const int32_t gp = static_cast<int32_t>(part_newjob.size());
+                for (int i = 0; i < size; ++i) owner_[comp[i]] = gp;
+                part_newjob.push_back(static_cast<int32_t>(pending.size()));
+                pending.push_back(Pending{job.slot, std::vector<int32_t>(comp, comp + size)});
+                pending_slot_.push_back(child_slot);
+            }
+        }
+        const int new_jobs = static_cast<int>(pending.size());
+        std::vector<DevJobInfo> info(static_cast<size_t>(new_jobs) + 1);
+        if (new_jobs > 0) {
+            const int rc = devforest_restrict(ctx_, forest_[cur_], J, job_tree_begin.data(), job_parts.data(), job_part_base.data(),
+                                              static_cast<int>(part_newjob.size()), part_newjob.data(), new_jobs, owner_.data(),
+                                              num_taxa_, &forest_[1 - cur_], info.data(), present_.data());
+            if (rc) return rc;
+        }
+        // taxa of finished sub-problems keep no owner
+        for (const Split &s : splits)
+            for (int32_t x : wave[s.job].taxa) owner_[x] = -1;
+        for (int j = 0; j < new_jobs; ++j) {
+            Job child;
+            child.slot = pending_slot_[j];
+            child.where = info[j];
+            // jobs are laid out in order: the leaves of a job end where the next job's begin
+            child.leaves = (j + 1 < new_jobs ? info[j + 1].leaf_begin : forest_[1 - cur_].leaves) - info[j].leaf_begin;
+            // taxa of the component that are a tip of some kept tree; the others are attached as singleton children of
+            // the parent (scs.py:168-171).  A child left without trees raises when its wave is processed.
+            const bool empty = info[j].trees == 0;
+            for (int32_t x : pending[j].members) {
+                if (present_[x]) child.taxa.push_back(x);
+                else if (!empty) add(pending[j].parent_slot, x);
+            }
+            next.push_back(std::move(child));
+        }
+        pending_slot_.clear();
+        cur_ = 1 - cur_;
+        return SCS_OK;
+    }
+
+    scs_ctx *ctx_;
+    int weighting_, contract_;
+    uint64_t seed_;
+    bool record_;
+    scs_supertree &out_;
+    int num_taxa_ = 0;
+    DevForest forest_[2];
+    int cur_ = 0;
+    DevTours tours_;
+    GrowBuf vertex_dev_, offsets_rel_, small_desc_dev_, part_dev_, flags_dev_;
+    std::vector<int32_t> vertex_, owner_, part_, pending_slot_;
+    std::vector<uint8_t> present_;
+};
+
+}  // namespace
+
+int run_device_driver(scs_ctx *ctx, const scs_forest *forest, int weighting, int contract_edges, uint64_t seed, bool record,
+                      scs_supertree *out) {
+    DeviceDriver driver(ctx, weighting, contract_edges, seed, record, out);
+    return driver.run(forest);
+}
+
+}  // namespace scs

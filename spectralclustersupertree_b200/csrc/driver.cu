@@ -24,25 +24,7 @@
 #include <omp.h>
 
 #include "forest.hpp"
-
-struct scs_supertree {
-    std::vector<int32_t> parent;  // parent[i] < i; -1 for the root
-    std::vector<int32_t> taxon;   // global taxon id for tips, -1 for internal nodes
-    struct Record {
-        std::vector<int32_t> taxa, part;
-        scs_node_stats stats;
-        int32_t wave = 0;  // wave of the breadth-first recursion that processed the node
-    };
-    std::vector<Record> records;  // one per recursion node that reached the GPU (if requested)
-    int64_t nodes_small = 0, nodes_large = 0, nodes_medium = 0, nodes_rerun = 0, waves = 0;
-    int64_t pair_visits = 0;
-    double seconds[4] = {0, 0, 0, 0};  // large-node splits, small-node batches, restriction, tours
-    double medium_seconds = 0.0;       // medium-node batches (without their tours)
-    std::vector<int32_t> wave_tasks, wave_max_n;  // per wave: sub-problems in it, largest taxon count
-    std::vector<double> wave_seconds;             // per wave: 3 numbers (GPU splits, restriction, everything)
-    int64_t shared_prefix = 0;  // sharded build: output nodes [0, shared_prefix) are identical on every rank
-    int64_t shared_records = 0;  // recursion nodes processed while every rank still walked the same frontier
-};
+#include "driver.hpp"
 
 namespace scs {
 
@@ -709,7 +691,7 @@ class Driver {
         if ((rc = reserve_as(ctx, SLOT_PART, static_cast<size_t>(part_off[B]) + 1, &part_dev))) return rc;
         std::vector<scs_node_stats> stats(B);
         std::vector<uint8_t> rerun(B, 0);
-        rc = medium_batch(ctx, B, node_n.data(), tree_begin.data(), part_off.data(), seeds.data(), static_cast<int>(nT),
+        rc = medium_batch(ctx, B, node_n.data(), tree_begin.data(), tree_begin.data() + 1, part_off.data(), seeds.data(), static_cast<int>(nT),
                           static_cast<int64_t>(nL), reinterpret_cast<const int64_t *>(dev + o_off),
                           reinterpret_cast<const int32_t *>(dev + o_tax), reinterpret_cast<const int32_t *>(dev + o_dep),
                           reinterpret_cast<const double *>(dev + o_val), reinterpret_cast<const int32_t *>(dev + o_root),
@@ -982,8 +964,14 @@ int scs_supertree_build_sharded(scs_ctx *ctx, const scs_forest *forest, int weig
     *out = nullptr;
     cudaSetDevice(ctx->device);
     std::unique_ptr<scs_supertree> result(new scs_supertree());
-    Driver driver(ctx, weighting, contract_edges, seed, record_nodes != 0, rank, world, result.get());
-    int rc = driver.run(forest);
+    int rc;
+    if (world == 1 && ctx->device_forest) {
+        // one GPU: the source trees stay on the device for the whole recursion (devdriver.cu)
+        rc = run_device_driver(ctx, forest, weighting, contract_edges, seed, record_nodes != 0, result.get());
+    } else {
+        Driver driver(ctx, weighting, contract_edges, seed, record_nodes != 0, rank, world, result.get());
+        rc = driver.run(forest);
+    }
     if (rc) return rc;
     if (world > 1 && result->shared_prefix == 0) result->shared_prefix = static_cast<int64_t>(result->parent.size());
     *out = result.release();
@@ -1072,7 +1060,7 @@ int scs_nodes_split_medium_dev(scs_ctx *ctx, int num_nodes, const int32_t *node_
                                int contract_edges, int32_t *part_dev, scs_node_stats *stats, uint8_t *needs_rerun) {
     if (!ctx) return SCS_ERR_INVALID;
     cudaSetDevice(ctx->device);
-    return medium_batch(ctx, num_nodes, node_n, tree_begin, part_offset, seeds, T, L, leaf_offsets_dev, leaf_taxon_dev,
+    return medium_batch(ctx, num_nodes, node_n, tree_begin, tree_begin + 1, part_offset, seeds, T, L, leaf_offsets_dev, leaf_taxon_dev,
                         adj_depth_dev, adj_val_dev, root_depth_dev, tree_weight_dev, contract_edges, part_dev, stats,
                         needs_rerun);
 }

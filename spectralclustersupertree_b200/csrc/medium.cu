@@ -87,12 +87,13 @@ __global__ void med_fill_maps(int B, int R, int T, const MedNode *__restrict__ n
         row_node[i] = lo;
     }
     if (i < T) {
-        int lo = 0, hi = B;  // last node with tree_begin <= i that has trees: nodes without trees share a tree_begin
+        int lo = 0, hi = B;  // last node with tree_begin <= i (of a run of equal tree_begin values the last owns tree i)
         while (hi - lo > 1) {
             const int mid = (lo + hi) >> 1;
             if (nodes[mid].tree_begin <= i) lo = mid; else hi = mid;
         }
-        tree_node[i] = lo;  // the last of a run of equal tree_begin values is the one that owns tree i
+        // trees between the nodes' ranges belong to sub-problems that are not part of this batch
+        tree_node[i] = (i >= nodes[lo].tree_begin && i < nodes[lo].tree_end) ? lo : -1;
     }
 }
 
@@ -556,12 +557,12 @@ int carve(unsigned char *&cursor, size_t count, T **out) {
 
 }  // namespace
 
-int medium_batch(scs_ctx *ctx, int B, const int32_t *node_n, const int32_t *tree_begin, const int64_t *part_off,
-                 const uint64_t *seeds, int T, int64_t L, const int64_t *leaf_offsets, const int32_t *leaf_taxon,
+int medium_batch(scs_ctx *ctx, int B, const int32_t *node_n, const int32_t *tree_begin, const int32_t *tree_end,
+                 const int64_t *part_off, const uint64_t *seeds, int T, int64_t L, const int64_t *leaf_offsets, const int32_t *leaf_taxon,
                  const int32_t *adj_depth, const double *adj_val, const int32_t *root_depth, const double *tree_weight,
                  int contract_edges, int32_t *part_dev, scs_node_stats *stats_host, uint8_t *needs_rerun) {
     if (B <= 0) return SCS_OK;
-    if (!node_n || !tree_begin || !part_off || !seeds || !part_dev || !stats_host || !needs_rerun || T < 0 || L < 0)
+    if (!node_n || !tree_begin || !tree_end || !part_off || !seeds || !part_dev || !stats_host || !needs_rerun || T < 0 || L < 0)
         return fail(ctx, SCS_ERR_INVALID, "medium batch: bad argument");
     // ---- node table -------------------------------------------------------------------------------------------------
     std::vector<MedNode> nodes(static_cast<size_t>(B));
@@ -570,14 +571,14 @@ int medium_batch(scs_ctx *ctx, int B, const int32_t *node_n, const int32_t *tree
     for (int b = 0; b < B; ++b) {
         const int n = node_n[b];
         if (n < 1 || n > kMediumMax) return fail(ctx, SCS_ERR_INVALID, "medium batch: node size out of range");
-        if (tree_begin[b] < 0 || tree_begin[b + 1] < tree_begin[b] || tree_begin[b + 1] > T)
+        if (tree_begin[b] < 0 || tree_end[b] < tree_begin[b] || tree_end[b] > T || (b > 0 && tree_begin[b] < tree_end[b - 1]))
             return fail(ctx, SCS_ERR_INVALID, "medium batch: tree ranges out of order");
         MedNode &nd = nodes[b];
         nd.n = n;
         nd.words = scs_bit_words(n);
         nd.row_base = static_cast<int32_t>(R);
         nd.tree_begin = tree_begin[b];
-        nd.tree_end = tree_begin[b + 1];
+        nd.tree_end = tree_end[b];
         nd.jcap = std::min(n - 1, kMaxBasis);
         nd.w_off = w_total;
         nd.bit_off = bit_total;
@@ -591,7 +592,6 @@ int medium_batch(scs_ctx *ctx, int B, const int32_t *node_n, const int32_t *tree
         max_n = std::max(max_n, n);
         max_trees = std::max(max_trees, nd.tree_end - nd.tree_begin);
     }
-    if (tree_begin[0] != 0 || tree_begin[B] != T) return fail(ctx, SCS_ERR_INVALID, "medium batch: trees not covered by the nodes");
     if (R >= (1ll << 31)) return fail(ctx, SCS_ERR_INVALID, "medium batch: too many rows");
 
     // ---- workspace ---------------------------------------------------------------------------------------------------

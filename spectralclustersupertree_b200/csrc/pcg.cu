@@ -60,7 +60,9 @@ __global__ void pcg_index_leaves(int n, int T, int64_t L, const int64_t *__restr
     int a = leaf_taxon[g];
     int base = 0;
     if (batch.nodes) {
-        const MedNode &nd = batch.nodes[batch.tree_node[lo]];
+        const int b = batch.tree_node[lo];
+        if (b < 0) return;  // a tree of a sub-problem that is not in this batch
+        const MedNode &nd = batch.nodes[b];
         n = nd.n;
         base = nd.row_base;
     }
@@ -107,7 +109,9 @@ __global__ void pcg_fill_inverse(int n, int64_t L, const int32_t *__restrict__ l
     int a = leaf_taxon[g];
     int base = 0;
     if (batch.nodes) {
-        const MedNode &nd = batch.nodes[batch.tree_node[leaf_tree[g]]];
+        const int b = batch.tree_node[leaf_tree[g]];
+        if (b < 0) return;
+        const MedNode &nd = batch.nodes[b];
         n = nd.n;
         base = nd.row_base;
     }

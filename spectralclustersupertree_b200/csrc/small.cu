@@ -441,7 +441,7 @@ small_batch_kernel(const scs_small_node *__restrict__ nodes, const int64_t *__re
                    const int32_t *__restrict__ leaf_taxon, const int32_t *__restrict__ adj_depth,
                    const double *__restrict__ adj_val, const int32_t *__restrict__ root_depth,
                    const double *__restrict__ tree_weight, int contract_edges, int32_t *__restrict__ part,
-                   scs_node_stats *__restrict__ stats, int32_t *__restrict__ bad) {
+                   scs_node_stats *__restrict__ stats, int32_t *__restrict__ bad, int absolute_offsets) {
     extern __shared__ __align__(16) unsigned char raw[];
     SmallShared &S = *reinterpret_cast<SmallShared *>(raw);
     const int tid = threadIdx.x;
@@ -463,9 +463,11 @@ small_batch_kernel(const scs_small_node *__restrict__ nodes, const int64_t *__re
     }
     if (tid < n) S.occ[tid] = 0;
     __syncthreads();
-    const int64_t *offs = leaf_offsets + node.tree_base + blockIdx.x;  // T + 1 offsets per node
+    // T + 1 offsets per node, relative to its first leaf -- or the forest's absolute offsets
+    const int64_t *offs = leaf_offsets + node.tree_base + (absolute_offsets ? 0 : blockIdx.x);
+    const int64_t leaf_base = absolute_offsets ? 0 : node.leaf_base;
     for (int t = 0; t < node.num_trees; ++t) {
-        const int64_t tb = node.leaf_base + offs[t];
+        const int64_t tb = leaf_base + offs[t];
         const int k = static_cast<int>(offs[t + 1] - offs[t]);
         const double w = tree_weight[node.tree_base + t];
         const int rd = root_depth[node.tree_base + t];
@@ -541,7 +543,7 @@ int small_node(scs_ctx *ctx, int n, int contract_edges, const double *W, const u
 int small_batch(scs_ctx *ctx, int num_nodes, const scs_small_node *nodes_dev, const int64_t *leaf_offsets,
                 const int32_t *leaf_taxon, const int32_t *adj_depth, const double *adj_val, const int32_t *root_depth,
                 const double *tree_weight, int contract_edges, int32_t *part_dev, scs_node_stats *stats_dev,
-                int32_t *bad_dev) {
+                int32_t *bad_dev, int absolute_offsets) {
     if (num_nodes <= 0) return SCS_OK;
     const size_t smem = sizeof(SmallShared);
     if (!ctx->batch_configured) {
@@ -551,7 +553,7 @@ int small_batch(scs_ctx *ctx, int num_nodes, const scs_small_node *nodes_dev, co
     }
     small_batch_kernel<<<num_nodes, kThreads, smem, ctx->stream>>>(nodes_dev, leaf_offsets, leaf_taxon, adj_depth,
                                                                   adj_val, root_depth, tree_weight, contract_edges,
-                                                                  part_dev, stats_dev, bad_dev);
+                                                                  part_dev, stats_dev, bad_dev, absolute_offsets);
     SCS_LAUNCHED(ctx, "small_batch_kernel");
     return SCS_OK;
 }

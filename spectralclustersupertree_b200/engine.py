@@ -105,6 +105,11 @@ class Engine:
         medium-node path of the native driver; 0 sends them down the per-node staged path."""
         _check(self._lib.scs_ctx_set_medium_node_limit(self._ctx, limit), self._ctx)
 
+    def set_device_forest(self, on: bool) -> None:
+        """Native single-GPU build: keep the source trees on the device for the whole recursion (default) or on
+        the host (restriction by the host threads, tours copied per wave)."""
+        _check(self._lib.scs_ctx_set_device_forest(self._ctx, int(bool(on))), self._ctx)
+
     def set_wide_entries(self, on: bool) -> None:
         """Graph build with the 8-byte bucket entries of nodes with >= 65 536 taxa at every size (tests)."""
         _check(self._lib.scs_ctx_set_wide_entries(self._ctx, int(on)), self._ctx)

@@ -269,3 +269,39 @@ def test_medium_batch_matches_per_node_path(engine, name):
     if name != "dcm":
         assert batched["nodes_medium"] > 0 and compared > 0
     assert int((batched["taxon"] >= 0).sum()) == int((staged["taxon"] >= 0).sum())
+
+
+@pytest.mark.parametrize("name", ["dcm", "dcm_iq", "supertriplets", "c2_500x50_branch", "c3_1000x100_branch_weighted",
+                                  "s_300x40_branch_weighted", "s_200x40_bootstrap", "s_150x40_one"])  # fmt: skip
+def test_device_resident_forest_matches_host_forest(engine, name):
+    """csrc/devdriver.cu + devforest.cu (source trees resident in HBM: tours and the restriction to the children of
+    every split computed on the device) against csrc/driver.cu + forest.cpp (flat trees restricted by the host
+    threads): the same recursion nodes with the same vertex sets, the same partitions, eigenvalues equal to the last
+    bits (the restricted branch lengths are the same sums in the same order), the same supertree."""
+    from helpers import flat_clades
+    from spectralclustersupertree_b200.engine import Forest
+
+    case = load_case(name)
+    trees = parse(case["lines"])
+
+    def build():
+        forest = Forest.from_trees(trees, case["weights"], case["names"])
+        return engine.supertree_build(forest, case["weighting"], record=True)
+
+    on_device = build()
+    engine.set_device_forest(False)
+    try:
+        on_host = build()
+    finally:
+        engine.set_device_forest(True)
+    assert len(on_device["records"]) == len(on_host["records"])
+    by_taxa = {taxa.tobytes(): (part, stats) for taxa, part, stats in on_host["records"]}
+    for taxa, part, stats in on_device["records"]:
+        opart, ostats = by_taxa[taxa.tobytes()]
+        assert stats.n_components == ostats.n_components
+        assert stats.contracted_size == ostats.contracted_size
+        assert np.array_equal(part, opart)
+        if stats.n_components == 1 and stats.contracted_size >= 3:
+            assert stats.eig[1] == ostats.eig[1], (len(taxa), stats.eig[1], ostats.eig[1])
+    assert flat_clades(on_device["parent"], on_device["taxon"]) == flat_clades(on_host["parent"], on_host["taxon"])
+    assert sorted(on_device["taxon"][on_device["taxon"] >= 0]) == sorted(on_host["taxon"][on_host["taxon"] >= 0])
