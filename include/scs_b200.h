@@ -228,6 +228,12 @@ int scs_forest_destroy(scs_forest *f);
 int scs_forest_parse_newick(const char *text, size_t bytes, scs_forest **out, char **names, size_t *names_bytes,
                             int *num_taxa);
 const char *scs_newick_last_error(void);
+/* The flat supertree (scs_supertree_nodes: parent[i] < i, taxon >= 0 on tips) as Newick text without node objects:
+ * replaces PhyloNode.write of the result (/root/reference/src/sc_supertree/cli.py:39).  names: the sorted tip
+ * names, NUL-terminated one after the other (as scs_forest_parse_newick returns them).  *text receives a
+ * NUL-terminated string ending in ';' (release with scs_free), *text_bytes its length. */
+int scs_flat_tree_newick(int64_t num_nodes, const int32_t *parent, const int32_t *taxon, const char *names,
+                         size_t names_bytes, int num_taxa, char **text, size_t *text_bytes);
 void scs_free(void *ptr);
 int scs_forest_num_trees(const scs_forest *f);
 int64_t scs_forest_num_nodes(const scs_forest *f);

@@ -284,6 +284,95 @@ int scs_forest_parse_newick(const char *text, size_t bytes, scs_forest **out, ch
     return SCS_OK;
 }
 
+/* The flat supertree as Newick text, straight from the arrays (replaces building node objects for
+ * PhyloNode.write, /root/reference/src/sc_supertree/cli.py:39): children in index order, tip labels quoted as
+ * cogent3 quotes them (single quotes around a label with blanks or Newick punctuation, a quote doubled), no
+ * branch lengths (the supertree has none), terminated by ';'. */
+int scs_flat_tree_newick(int64_t num_nodes, const int32_t *parent, const int32_t *taxon, const char *names,
+                         size_t names_bytes, int num_taxa, char **text_out, size_t *text_bytes) {
+    if (num_nodes <= 0 || !parent || !taxon || !names || !text_out || !text_bytes || num_taxa < 0) return SCS_ERR_INVALID;
+    *text_out = nullptr;
+    *text_bytes = 0;
+    std::vector<const char *> label(static_cast<size_t>(num_taxa));
+    std::vector<size_t> label_len(static_cast<size_t>(num_taxa));
+    {
+        size_t at = 0;
+        for (int x = 0; x < num_taxa; ++x) {
+            if (at >= names_bytes) return SCS_ERR_INVALID;
+            label[x] = names + at;
+            const void *end = std::memchr(names + at, '\0', names_bytes - at);
+            if (!end) return SCS_ERR_INVALID;
+            label_len[x] = static_cast<size_t>(static_cast<const char *>(end) - (names + at));
+            at += label_len[x] + 1;
+        }
+    }
+    // children of every node, in index order
+    std::vector<int64_t> first(static_cast<size_t>(num_nodes) + 1, 0);
+    if (parent[0] != -1) return SCS_ERR_INVALID;
+    for (int64_t k = 1; k < num_nodes; ++k) {
+        if (parent[k] < 0 || parent[k] >= k) return SCS_ERR_INVALID;
+        first[parent[k] + 1] += 1;
+    }
+    for (int64_t k = 0; k < num_nodes; ++k) first[k + 1] += first[k];
+    std::vector<int32_t> child(static_cast<size_t>(num_nodes));
+    {
+        std::vector<int64_t> cursor(first.begin(), first.end() - 1);
+        for (int64_t k = 1; k < num_nodes; ++k) child[cursor[parent[k]]++] = static_cast<int32_t>(k);
+    }
+    std::string text;
+    text.reserve(static_cast<size_t>(num_nodes) * 8);
+    auto put_label = [&](int32_t x) {
+        const char *s = label[x];
+        const size_t n = label_len[x];
+        bool plain = n > 0;
+        for (size_t i = 0; i < n && plain; ++i) plain = std::strchr(" ()[]':;,\t\n", s[i]) == nullptr;
+        if (plain || n == 0) {
+            text.append(s, n);
+            return;
+        }
+        text.push_back('\'');
+        for (size_t i = 0; i < n; ++i) {
+            if (s[i] == '\'') text.push_back('\'');
+            text.push_back(s[i]);
+        }
+        text.push_back('\'');
+    };
+    // iterative depth-first walk: (node, next child to visit)
+    std::vector<std::pair<int32_t, int64_t>> stack;
+    stack.emplace_back(0, first[0]);
+    if (first[1] == first[0]) {  // a single node
+        if (taxon[0] >= 0 && taxon[0] < num_taxa) put_label(taxon[0]);
+    } else {
+        text.push_back('(');
+        while (!stack.empty()) {
+            auto &top = stack.back();
+            const int32_t node = top.first;
+            if (top.second == first[node + 1]) {
+                text.push_back(')');
+                stack.pop_back();
+                continue;
+            }
+            if (top.second != first[node]) text.push_back(',');
+            const int32_t c = child[top.second++];
+            if (first[c + 1] == first[c]) {
+                if (taxon[c] < 0 || taxon[c] >= num_taxa) return SCS_ERR_INVALID;
+                put_label(taxon[c]);
+            } else {
+                text.push_back('(');
+                stack.emplace_back(c, first[c]);
+            }
+        }
+    }
+    text.push_back(';');
+    char *buf = static_cast<char *>(std::malloc(text.size() + 1));
+    if (!buf) return SCS_ERR_INVALID;
+    std::memcpy(buf, text.data(), text.size());
+    buf[text.size()] = '\0';
+    *text_out = buf;
+    *text_bytes = text.size();
+    return SCS_OK;
+}
+
 void scs_free(void *ptr) { std::free(ptr); }
 
 }  // extern "C"

@@ -193,6 +193,43 @@ def supertree_of_forest(
     return result
 
 
+def flat_newick(parent, taxon, names: Sequence[str]) -> str:
+    """Newick text of the native driver's flat result, written natively (``scs_flat_tree_newick``): what
+    ``_tree_from_flat(...).get_newick()`` gives, without a node object per node."""
+    import ctypes
+
+    from . import _lib
+    from ._lib import ptr
+
+    lib = _lib.load()
+    blob = b"".join(name.encode("utf-8") + b"\0" for name in names)
+    parent = np.ascontiguousarray(parent, dtype=np.int32)
+    taxon = np.ascontiguousarray(taxon, dtype=np.int32)
+    text, size = ctypes.c_void_p(), ctypes.c_size_t()
+    status = lib.scs_flat_tree_newick(len(parent), ptr(parent), ptr(taxon), blob, len(blob), len(names),
+                                      ctypes.byref(text), ctypes.byref(size))  # fmt: skip
+    if status != 0:
+        msg = f"scs_flat_tree_newick failed with status {status}"
+        raise RuntimeError(msg)
+    try:
+        return ctypes.string_at(text.value, size.value).decode("utf-8")
+    finally:
+        lib.scs_free(text)
+
+
+def supertree_newick_of_forest(forest: Forest, pcg_weighting: str = "one", *, contract_edges: bool = True, seed: int = 0,
+                               engine: Engine | None = None) -> str:
+    """``supertree_of_forest`` for callers that only want the Newick text (the ``scs`` command): flat forest in,
+    native recursion, native Newick emission -- no node objects at either end."""
+    if pcg_weighting not in WEIGHTINGS:
+        msg = f"Invalid weighting strategy selected: '{pcg_weighting}'"
+        raise ValueError(msg)
+    if engine is None:
+        engine = default_engine()
+    built = engine.supertree_build(forest, pcg_weighting, contract_edges=contract_edges, seed=seed)
+    return flat_newick(built["parent"], built["taxon"], forest.names)
+
+
 def _tree_from_flat(parent, taxon, names: Sequence[str]) -> PhyloNode:
     """PhyloNode tree of the native driver's flat result (parent[i] < i, children in index order)."""
     nodes = [PhyloNode(names[x]) if x >= 0 else PhyloNode("root") for x in taxon.tolist()]

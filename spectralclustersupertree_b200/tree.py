@@ -205,6 +205,52 @@ class PhyloNode:
                     break
         return sub
 
+    def rooted(self, edge_name: str) -> "PhyloNode":
+        """A copy re-rooted on the branch above the node called ``edge_name`` (what ``outgroup_root`` needs,
+        ref: _app.py:88-92): the new root has two children, that node and the rest of the tree; the branch's length,
+        if known, is split evenly between them."""
+        copy = self.copy()
+        target = next((n for n in copy.preorder() if n.name == edge_name), None)
+        if target is None or target.parent is None:
+            msg = f"cannot root on '{edge_name}'"
+            raise ValueError(msg)
+        # walk from the target's parent up to the old root, reversing the parent links
+        path = []
+        node = target.parent
+        while node is not None:
+            path.append(node)
+            node = node.parent
+        half = None if target.length is None else target.length / 2
+        below, below_length = target, target.length
+        path[0].children.remove(target)
+        for k, node in enumerate(path):
+            up = path[k + 1] if k + 1 < len(path) else None
+            own_length = node.length
+            if up is not None:
+                up.children.remove(node)
+                node.children.append(up)
+            node.parent = below if below is not target else None
+            node.length = below_length if below is not target else half
+            below, below_length = node, own_length
+        root = PhyloNode("root")
+        target.length = half
+        root.append(target)
+        root.append(path[0])
+        for node in path[1:]:
+            node.parent = path[path.index(node) - 1]
+        # an old root left with a single child is merged into it
+        old_root = path[-1]
+        if len(old_root.children) == 1 and old_root.parent is not None:
+            only = old_root.children[0]
+            if only.length is not None and old_root.length is not None:
+                only.length = only.length + old_root.length
+            else:
+                only.length = None
+            holder = old_root.parent
+            holder.children[holder.children.index(old_root)] = only
+            only.parent = holder
+        return root
+
     def sorted(self, sort_order: Iterable[str] | None = None) -> "PhyloNode":
         """A copy with children ordered by the smallest rank among their tips.
 

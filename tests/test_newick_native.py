@@ -169,3 +169,42 @@ def test_random_newick_agrees_with_the_python_parser():
             native.close()
 
     check()
+
+
+def test_flat_supertree_is_written_as_newick_natively():
+    """``scs_flat_tree_newick`` (no node objects) against ``_tree_from_flat(...).get_newick()``, names that need quoting
+    included; the text parses back to the same tree."""
+    from spectralclustersupertree_b200.scs import _tree_from_flat, flat_newick
+
+    rng = np.random.RandomState(9)
+    names = sorted(["a", "b c", "it's", "t(1)", "x:y", "plain_1", "7up", "semi;colon", "comma,name", "z"])
+    for _ in range(25):
+        count_tips = int(rng.randint(1, len(names) + 1))
+        tips = list(rng.permutation(len(names))[:count_tips])
+        # random flat tree: parent[i] < i, tips carry taxa
+        parent, taxon = [-1], [-1 if count_tips > 1 else int(tips[0])]
+        open_internal = [0] if count_tips > 1 else []
+        pending = list(tips) if count_tips > 1 else []
+        while pending:
+            host = int(rng.choice(open_internal))
+            if len(pending) > 2 and rng.random_sample() < 0.4:
+                parent.append(host)
+                taxon.append(-1)
+                open_internal.append(len(parent) - 1)
+                # an internal node must end up with children: give it two tips right away
+                for _k in range(2):
+                    parent.append(len(open_internal) and open_internal[-1])
+                    taxon.append(int(pending.pop()))
+            else:
+                parent.append(host)
+                taxon.append(int(pending.pop()))
+        parent_a, taxon_a = np.array(parent, dtype=np.int32), np.array(taxon, dtype=np.int32)
+        # internal nodes without children would read as tips: drop such cases
+        has_child = np.zeros(len(parent), dtype=bool)
+        has_child[parent_a[1:]] = True
+        if ((taxon_a < 0) & ~has_child).any():
+            continue
+        text = flat_newick(parent_a, taxon_a, names)
+        expected = _tree_from_flat(parent_a, taxon_a, names)
+        assert text == expected.get_newick()
+        assert make_tree(text).clade_sets() == expected.clade_sets()
