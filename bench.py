@@ -654,6 +654,22 @@ def gpu_line(args, arrays: dict) -> dict:
         "roofline": roofline,
         "roofline_pcg_rows": roofline_rows,
     }  # fmt: skip
+    if rank == 0 and world == 1 and args.workload != "c5":
+        # the drop-in itself: construct_supertree(list of tree objects) -- C-level flattening of the node objects,
+        # native build, node objects of the result (the objects themselves are built outside the timed call)
+        from spectralclustersupertree_b200 import construct_supertree
+        from spectralclustersupertree_b200.synthetic import make_problem
+
+        n_, t_, w_, seed_, tw_ = WORKLOADS[args.workload]
+        problem = make_problem(n_, t_, w_, seed_, tree_weights=tw_)
+        objects = problem.phylonodes()
+        construct_supertree(objects, problem.weights, w_, engine=engine)  # warm
+        t0 = time.perf_counter()
+        result = construct_supertree(objects, problem.weights, w_, engine=engine)
+        line["e2e_python_api"] = {"value": time.perf_counter() - t0, "unit": "s",
+                                  "call": "construct_supertree(list[PhyloNode], weights, pcg_weighting) -> PhyloNode",
+                                  "tips": len(result.get_tip_names())}  # fmt: skip
+        del objects, problem
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         if args.workload in ("c1", "c2", "c3"):
             # the whole job fits the bounded-sample budget: measured end to end

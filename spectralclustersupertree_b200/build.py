@@ -93,5 +93,23 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+def build_fastflatten(force: bool = False) -> Path | None:
+    """The CPython accelerator of ``Forest.from_trees`` (csrc/fastflatten.c): host-side glue, optional."""
+    import sysconfig
+
+    src = CSRC / "fastflatten.c"
+    out = PKG / ("_fastflatten" + (sysconfig.get_config_var("EXT_SUFFIX") or ".so"))
+    if not force and not _stale(out, [src]):
+        return out
+    include = sysconfig.get_paths()["include"]
+    cmd = ["gcc", "-O2", "-shared", "-fPIC", "-Wall", f"-I{include}", str(src), "-o", str(out), "-lm"]
+    proc = subprocess.run(cmd, capture_output=True, text=True, check=False)
+    if proc.returncode != 0:
+        sys.stderr.write(proc.stdout + proc.stderr)
+        return None
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_fastflatten(force="--force" in sys.argv))

@@ -1,0 +1,164 @@
+/* CPython accelerator for Forest.from_trees: walks tree objects that expose the PhyloNode surface the reference
+ * touches (`children` / iteration, `name`, `length`, `support`; /root/reference/src/sc_supertree/scs.py:570,624-631,
+ * 560-564) straight into the flat pre-order arrays of scs_forest_create, ~100 ns per node instead of the ~8 us of the
+ * Python loop it replaces (construct_supertree(list[PhyloNode]) at 10 000 taxa x 1 000 trees: 1.3 M nodes).
+ * Host-side glue only: nothing here computes; a missing build falls back to the Python loop in engine.py. */
+#define PY_SSIZE_T_CLEAN
+#include <Python.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef struct {
+    char *data;
+    size_t size, cap;
+} Buf;
+
+static int buf_push(Buf *b, const void *src, size_t n)
+{
+    if (b->size + n > b->cap) {
+        size_t cap = b->cap ? b->cap : 1 << 16;
+        while (cap < b->size + n) cap *= 2;
+        char *p = (char *)realloc(b->data, cap);
+        if (!p) return -1;
+        b->data = p;
+        b->cap = cap;
+    }
+    memcpy(b->data + b->size, src, n);
+    b->size += n;
+    return 0;
+}
+
+static double number_or_nan(PyObject *obj)
+{
+    if (obj == NULL || obj == Py_None) return NAN;
+    double v = PyFloat_AsDouble(obj);
+    if (v == -1.0 && PyErr_Occurred()) return NAN; /* caller checks PyErr_Occurred */
+    return v;
+}
+
+/* children of a node as a new reference to a list */
+static PyObject *children_of(PyObject *node, PyObject *s_children)
+{
+    PyObject *kids = PyObject_GetAttr(node, s_children);
+    if (kids == NULL) {
+        PyErr_Clear();
+        return PySequence_List(node); /* iteration over the node yields its children (ref: scs.py:570) */
+    }
+    if (PyList_Check(kids)) return kids;
+    PyObject *as_list = PySequence_List(kids);
+    Py_DECREF(kids);
+    return as_list;
+}
+
+/* flatten(trees) -> (offsets:int64 bytes, parent:int32 bytes, length:f64 bytes, support:f64 bytes, taxon:int32 bytes,
+ *                    names:list)   taxon holds the index of the tip's name in `names` (first-seen order), -1 inside */
+static PyObject *flatten(PyObject *self, PyObject *args)
+{
+    PyObject *trees;
+    (void)self;
+    if (!PyArg_ParseTuple(args, "O", &trees)) return NULL;
+    PyObject *seq = PySequence_Fast(trees, "trees must be a sequence");
+    if (!seq) return NULL;
+    PyObject *s_children = PyUnicode_InternFromString("children");
+    PyObject *s_name = PyUnicode_InternFromString("name");
+    PyObject *s_length = PyUnicode_InternFromString("length");
+    PyObject *s_support = PyUnicode_InternFromString("support");
+    PyObject *name_ids = PyDict_New(), *names = PyList_New(0);
+    Buf offsets = {0}, parent = {0}, length = {0}, support = {0}, taxon = {0}, stack = {0};
+    PyObject *result = NULL;
+    int64_t total = 0;
+    if (buf_push(&offsets, &total, sizeof total)) goto oom;
+    const Py_ssize_t T = PySequence_Fast_GET_SIZE(seq);
+    for (Py_ssize_t t = 0; t < T; ++t) {
+        struct Item { PyObject *node; int32_t up; } item;
+        item.node = PySequence_Fast_GET_ITEM(seq, t);
+        Py_INCREF(item.node);
+        item.up = -1;
+        stack.size = 0;
+        if (buf_push(&stack, &item, sizeof item)) goto oom;
+        const int64_t base = total;
+        while (stack.size) {
+            stack.size -= sizeof item;
+            memcpy(&item, stack.data + stack.size, sizeof item);
+            PyObject *node = item.node;
+            const int32_t k = (int32_t)(total - base);
+            PyObject *len_o = PyObject_GetAttr(node, s_length);
+            if (!len_o) PyErr_Clear();
+            PyObject *sup_o = PyObject_GetAttr(node, s_support);
+            if (!sup_o) PyErr_Clear();
+            const double len_v = number_or_nan(len_o), sup_v = number_or_nan(sup_o);
+            Py_XDECREF(len_o);
+            Py_XDECREF(sup_o);
+            if (PyErr_Occurred()) { Py_DECREF(node); goto fail; }
+            PyObject *kids = children_of(node, s_children);
+            if (!kids) { Py_DECREF(node); goto fail; }
+            const Py_ssize_t nk = PyList_GET_SIZE(kids);
+            int32_t tax = -1;
+            if (nk == 0) {
+                PyObject *name = PyObject_GetAttr(node, s_name);
+                if (!name) { Py_DECREF(kids); Py_DECREF(node); goto fail; }
+                PyObject *id = PyDict_GetItemWithError(name_ids, name); /* borrowed */
+                if (!id) {
+                    if (PyErr_Occurred()) { Py_DECREF(name); Py_DECREF(kids); Py_DECREF(node); goto fail; }
+                    tax = (int32_t)PyList_GET_SIZE(names);
+                    PyObject *fresh = PyLong_FromLong(tax);
+                    if (!fresh || PyDict_SetItem(name_ids, name, fresh) || PyList_Append(names, name)) {
+                        Py_XDECREF(fresh); Py_DECREF(name); Py_DECREF(kids); Py_DECREF(node); goto fail;
+                    }
+                    Py_DECREF(fresh);
+                } else {
+                    tax = (int32_t)PyLong_AsLong(id);
+                }
+                Py_DECREF(name);
+            }
+            if (buf_push(&parent, &item.up, sizeof(int32_t)) || buf_push(&length, &len_v, sizeof len_v) ||
+                buf_push(&support, &sup_v, sizeof sup_v) || buf_push(&taxon, &tax, sizeof tax)) {
+                Py_DECREF(kids); Py_DECREF(node); goto oom;
+            }
+            total += 1;
+            for (Py_ssize_t c = nk - 1; c >= 0; --c) { /* reversed: the first child is popped first (pre-order) */
+                struct Item child;
+                child.node = PyList_GET_ITEM(kids, c);
+                Py_INCREF(child.node);
+                child.up = k;
+                if (buf_push(&stack, &child, sizeof child)) { Py_DECREF(child.node); Py_DECREF(kids); Py_DECREF(node); goto oom; }
+            }
+            Py_DECREF(kids);
+            Py_DECREF(node);
+        }
+        if (buf_push(&offsets, &total, sizeof total)) goto oom;
+    }
+    result = Py_BuildValue("(y#y#y#y#y#O)", offsets.data, (Py_ssize_t)offsets.size, parent.data ? parent.data : "",
+                           (Py_ssize_t)parent.size, length.data ? length.data : "", (Py_ssize_t)length.size,
+                           support.data ? support.data : "", (Py_ssize_t)support.size, taxon.data ? taxon.data : "",
+                           (Py_ssize_t)taxon.size, names);
+    goto done;
+oom:
+    PyErr_NoMemory();
+fail:
+    /* release the nodes still on the stack */
+    while (stack.size) {
+        struct Item { PyObject *node; int32_t up; } item;
+        stack.size -= sizeof item;
+        memcpy(&item, stack.data + stack.size, sizeof item);
+        Py_DECREF(item.node);
+    }
+done:
+    free(offsets.data); free(parent.data); free(length.data); free(support.data); free(taxon.data); free(stack.data);
+    Py_DECREF(name_ids);
+    Py_DECREF(names);
+    Py_DECREF(s_children); Py_DECREF(s_name); Py_DECREF(s_length); Py_DECREF(s_support);
+    Py_DECREF(seq);
+    return result;
+}
+
+static PyMethodDef methods[] = {
+    {"flatten", flatten, METH_VARARGS, "Flatten tree objects into pre-order arrays (see engine.Forest.from_trees)."},
+    {NULL, NULL, 0, NULL},
+};
+
+static struct PyModuleDef module = {PyModuleDef_HEAD_INIT, "_fastflatten", NULL, -1, methods, NULL, NULL, NULL, NULL};
+
+PyMODINIT_FUNC PyInit__fastflatten(void) { return PyModule_Create(&module); }

@@ -502,6 +502,26 @@ def set_host_threads(threads: int) -> None:
 _DEFAULT: Engine | None = None
 
 
+_FASTFLATTEN = None
+
+
+def _fastflatten():
+    """The CPython accelerator of ``Forest.from_trees`` (csrc/fastflatten.c), built on first use; None if it cannot be
+    built or imported (the Python loop below is then used: host-side glue, not compute)."""
+    global _FASTFLATTEN  # noqa: PLW0603
+    if _FASTFLATTEN is None:
+        try:
+            from . import build as _build
+
+            _build.build_fastflatten()
+            from . import _fastflatten as module
+
+            _FASTFLATTEN = module
+        except Exception:  # noqa: BLE001
+            _FASTFLATTEN = False
+    return _FASTFLATTEN or None
+
+
 def default_engine() -> Engine:
     """The process-wide engine used by ``construct_supertree`` (device from ``SCS_B200_DEVICE``)."""
     global _DEFAULT  # noqa: PLW0603
@@ -547,6 +567,21 @@ class Forest:
     def from_trees(cls, trees: Sequence, weights: Sequence[float], names: Sequence[str] | None = None) -> "Forest":
         """Flatten tree objects exposing the PhyloNode surface (children iteration, ``name``,
         ``length``, ``support``; ref: scs.py:570,624-631,560-564)."""
+        fast = _fastflatten()
+        if fast is not None:
+            # csrc/fastflatten.c: one C-level walk over the node objects; tips numbered in first-seen order there,
+            # renumbered here by rank in the sorted name list (global taxon id = rank of the name)
+            raw_off, raw_par, raw_len, raw_sup, raw_tax, seen = fast.flatten(list(trees))
+            if names is None:
+                names = sorted(seen)
+            taxon_id = {name: i for i, name in enumerate(names)}
+            remap = np.fromiter((taxon_id[name] for name in seen), dtype=np.int32, count=len(seen))
+            taxon = np.frombuffer(raw_tax, dtype=np.int32)
+            if len(remap):
+                taxon = np.where(taxon >= 0, remap[np.maximum(taxon, 0)], -1).astype(np.int32)
+            return cls.from_arrays(np.frombuffer(raw_off, dtype=np.int64), np.frombuffer(raw_par, dtype=np.int32),
+                                   np.frombuffer(raw_len, dtype=np.float64), np.frombuffer(raw_sup, dtype=np.float64),
+                                   taxon, list(weights), names)  # fmt: skip
         if names is None:
             found: set[str] = set()
             for tree in trees:
