@@ -577,8 +577,9 @@ def gpu_line(args, arrays: dict) -> dict:
         built, merged = e2e_step()
         engine.synchronize()
         e2e_s.append(time.perf_counter() - t0)
-        for k in host_split:
+        for k in built["seconds"]:
             host_split[k] += built["seconds"][k] / args.steps
+        host_split["medium_batches"] = host_split.get("medium_batches", 0.0) + built["medium_seconds"] / args.steps
         barrier()
     h2d1, d2h1 = engine.io_bytes()
     clocks = sampler.stop()

@@ -10,7 +10,7 @@ for stage in "$@"; do
     tests)
       python -m pytest tests -m gpu -q -x --durations=8 > gpurun_out/${tag}_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/${tag}_pytest_gpu.log ;;
     tests_all)
-      python -m pytest tests -m gpu -q --durations=8 > gpurun_out/${tag}_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/${tag}_pytest_gpu.log ;;
+      python -m pytest tests -m gpu -q --durations=8 --deselect tests/test_gpu_fullsize.py::test_c5_top_level_rows_and_fiedler_value > gpurun_out/${tag}_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/${tag}_pytest_gpu.log ;;
     bench_small)
       for w in c1 c2 c3; do
         python bench.py --workload $w --steps 5 --warmup 3 > gpurun_out/${tag}_bench_$w.json 2> gpurun_out/${tag}_bench_$w.err; echo "bench $w rc=$?"
@@ -32,6 +32,10 @@ for stage in "$@"; do
         timeout 900 compute-sanitizer --tool memcheck --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_sanitizer_memcheck_smoke.log 2>&1; echo "memcheck rc=$?"; tail -4 gpurun_out/${tag}_sanitizer_memcheck_smoke.log
         timeout 900 compute-sanitizer --tool racecheck --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_sanitizer_racecheck_smoke.log 2>&1; echo "racecheck rc=$?"; tail -4 gpurun_out/${tag}_sanitizer_racecheck_smoke.log
       fi ;;
+    parity)
+      python tools/parity_report.py --out gpurun_out/${tag}_PARITY.json > gpurun_out/${tag}_parity.log 2>&1; echo "parity rc=$?"; tail -3 gpurun_out/${tag}_parity.log ;;
+    c5test)
+      python -m pytest tests/test_gpu_fullsize.py -q -k c5 -s > gpurun_out/${tag}_pytest_c5.log 2>&1; echo "c5 test rc=$?"; tail -5 gpurun_out/${tag}_pytest_c5.log ;;
     reference)
       python bench.py --impl reference --steps 1 --warmup 0 --reference-budget-s 1200 > gpurun_out/${tag}_bench_c4_reference.json 2> gpurun_out/${tag}_bench_c4_reference.err; echo "reference rc=$?"; head -c 400 gpurun_out/${tag}_bench_c4_reference.json ;;
     *) echo "unknown stage $stage" ;;
