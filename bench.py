@@ -455,7 +455,10 @@ def profile_step(args, arrays: dict) -> dict:
     engine.synchronize()
     seconds = time.perf_counter() - t0
     lib.scs_profiler_range(0)
+    cycles = np.zeros(2, dtype=np.uint64)
+    lib.scs_debug_small_cycles(engine.handle, cycles.ctypes.data, 0)
     out = {"workload": describe(args.workload), "step_seconds_under_profiler": seconds,
+           "small_kernel_cycles_since_start": {"graph_build": int(cycles[0]), "after_build": int(cycles[1])},
            "gpu_launches_in_step": int(engine.launch_count - before), "waves": built["waves"],
            "nodes_small": built["nodes_small"], "nodes_large": built["nodes_large"]}  # fmt: skip
     engine.close()

@@ -118,6 +118,10 @@ int scs_ctx_flush_l2(scs_ctx *ctx);
 int scs_ctx_profile_enable(scs_ctx *ctx, int on);
 int scs_ctx_profile_read(scs_ctx *ctx, int kind, int64_t *launches, double *ms, double *bytes, double *units);
 
+/* Profiling aid: SM cycles the batched small-node kernel spent, summed over its CTAs since the last reset, in
+ * [0] the graph build from the tours and [1] components + contraction + eigensolver + 2-means (device-wide
+ * counters: meaningful with one context at a time). */
+int scs_debug_small_cycles(scs_ctx *ctx, uint64_t *cycles2, int reset);
 /* cudaProfilerStart (on = 1) / cudaProfilerStop (on = 0): brackets the step `ncu --profile-from-start off`
  * captures (bench.py --profile-step). */
 int scs_profiler_range(int on);

@@ -317,6 +317,9 @@ int small_batch(scs_ctx *ctx, int num_nodes, const scs_small_node *nodes_dev, co
                 const double *tree_weight, int contract_edges, int32_t *part_dev, scs_node_stats *stats_dev,
                 int32_t *bad_dev, int absolute_offsets = 0);
 
+// SM cycles the batched small-node kernel spent in its graph build / in everything after it, summed over CTAs.
+int small_cycles(scs_ctx *ctx, unsigned long long *out2, int reset);
+
 // One recursion node on device-resident tours.  part_dev[n] receives the component index or side;
 // if part_host is not null the result is also copied there before the function returns.
 int node_split(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offsets, const int32_t *leaf_taxon,

@@ -525,6 +525,16 @@ int scs_ctx_profile_read(scs_ctx *ctx, int kind, int64_t *launches, double *ms, 
     return SCS_OK;
 }
 
+int scs_debug_small_cycles(scs_ctx *ctx, uint64_t *cycles2, int reset) {
+    if (!ctx || !cycles2) return SCS_ERR_INVALID;
+    DeviceGuard guard(ctx->device);
+    unsigned long long raw[2] = {0, 0};
+    const int rc = small_cycles(ctx, raw, reset);
+    cycles2[0] = raw[0];
+    cycles2[1] = raw[1];
+    return rc;
+}
+
 int scs_profiler_range(int on) {
     const cudaError_t err = on ? cudaProfilerStart() : cudaProfilerStop();
     return err == cudaSuccess ? SCS_OK : SCS_ERR_CUDA;

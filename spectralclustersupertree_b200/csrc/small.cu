@@ -430,6 +430,10 @@ small_node_kernel(int n, int words, int contract_edges, const double *__restrict
     small_finish(S, n, contract_edges, part, out, group_out, Wc_out);
 }
 
+// Cycle counters of the batched kernel, summed over its CTAs: [0] graph build, [1] everything after it (profiling aid:
+// scs_debug_small_cycles).
+__device__ unsigned long long g_small_cycles[2];
+
 // ---- batched entry: one CTA per node builds the node's graph from its leaf tours in shared memory
 //      (the reference's _proper_cluster_graph_edges, scs.py:495-663) and finishes it ------------------
 // Trees are taken in input order with a barrier between them; inside a tree thread i owns the pairs
@@ -447,6 +451,7 @@ small_batch_kernel(const scs_small_node *__restrict__ nodes, const int64_t *__re
     const int tid = threadIdx.x;
     const scs_small_node node = nodes[blockIdx.x];
     const int n = node.n;
+    const long long clock_start = clock64();
     if (node.num_trees > kSmallMaxTrees || n < 1 || n > kN) {
         // the co-occurrence counts are 16-bit here (the staged path switches to 32-bit counts at 65 536 trees,
         // pcg.cu `narrow`); the host entry points route such nodes to the staged path -- refuse loudly if one
@@ -483,27 +488,39 @@ small_batch_kernel(const scs_small_node *__restrict__ nodes, const int64_t *__re
             if (a < 0 || a >= n) *bad = 1;
         }
         __syncthreads();
-        if (tid < k) {
-            const int a = S.tour_taxon[tid];
+        // four threads share a leaf i: each walks the whole staircase (the running minimum needs every j) but adds
+        // only every fourth pair; a pair is stored once, at [smaller vertex][larger vertex], and mirrored after the
+        // last tree -- every entry still receives its terms in tree order, one rounded multiply and one rounded add
+        // each, so the sums are the reference's bit for bit
+        const int i = tid & (kN - 1), q = tid >> 6;
+        if (i < k) {
+            const int a = S.tour_taxon[i];
             if (a >= 0 && a < n) {
-                S.occ[a] += 1;
-                int best_depth = 0x7fffffff, best_idx = tid;
-                for (int j = tid + 1; j < k; ++j) {
+                if (q == 0) S.occ[a] += 1;
+                int best_depth = 0x7fffffff, best_idx = i;
+                for (int j = i + 1; j < k; ++j) {
                     const int d = S.tour_depth[j - 1];
                     if (d < best_depth) { best_depth = d; best_idx = j - 1; }  // leftmost shallowest entry
                     if (best_depth == rd) break;  // the root separates everything further right too
+                    if (((j - i - 1) & 3) != q) continue;
                     const int b = S.tour_taxon[j];
                     if (b < 0 || b >= n) continue;
-                    const double term = __dmul_rn(S.tour_val[best_idx], w);
-                    S.A[a][b] = __dadd_rn(S.A[a][b], term);
-                    S.A[b][a] = __dadd_rn(S.A[b][a], term);
-                    S.cnt[a][b] += 1;
-                    S.cnt[b][a] += 1;
+                    const int lo = min(a, b), hi = max(a, b);
+                    S.A[lo][hi] = __dadd_rn(S.A[lo][hi], __dmul_rn(S.tour_val[best_idx], w));
+                    S.cnt[lo][hi] += 1;
                 }
             }
         }
         __syncthreads();
     }
+    for (int e = tid; e < n * n; e += kThreads) {  // mirror the upper triangle
+        const int r = e / n, c = e % n;
+        if (r > c) {
+            S.A[r][c] = S.A[c][r];
+            S.cnt[r][c] = S.cnt[c][r];
+        }
+    }
+    __syncthreads();
     if (tid < n) {
         unsigned long long a = 0, m = 0;
         const int occ_a = S.occ[tid];
@@ -518,7 +535,12 @@ small_batch_kernel(const scs_small_node *__restrict__ nodes, const int64_t *__re
         S.mx[tid] = contract_edges ? m : 0ull;
     }
     __syncthreads();
+    const long long clock_built = clock64();
     small_finish(S, n, contract_edges, part + node.vertex_base, stats + blockIdx.x, nullptr, nullptr);
+    if (tid == 0) {
+        atomicAdd(&g_small_cycles[0], static_cast<unsigned long long>(clock_built - clock_start));
+        atomicAdd(&g_small_cycles[1], static_cast<unsigned long long>(clock64() - clock_built));
+    }
 }
 
 }  // namespace
@@ -537,6 +559,16 @@ int small_node(scs_ctx *ctx, int n, int contract_edges, const double *W, const u
                                                          contract_edges ? max_bits : nullptr, part, out_dev, group_out,
                                                          Wc_out);
     SCS_LAUNCHED(ctx, "small_node_kernel");
+    return SCS_OK;
+}
+
+int small_cycles(scs_ctx *ctx, unsigned long long *out2, int reset) {
+    SCS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    SCS_CUDA(ctx, cudaMemcpyFromSymbol(out2, g_small_cycles, 2 * sizeof(unsigned long long)));
+    if (reset) {
+        const unsigned long long zero[2] = {0, 0};
+        SCS_CUDA(ctx, cudaMemcpyToSymbol(g_small_cycles, zero, sizeof(zero)));
+    }
     return SCS_OK;
 }
 
