@@ -56,7 +56,7 @@ class DeviceDriver {
         tours_.free_all(ctx_);
         release(ctx_, vertex_dev_);
         release(ctx_, offsets_rel_);
-        release(ctx_, small_desc_dev_);
+        if (tours_ready_) cudaEventDestroy(tours_ready_);
         release(ctx_, part_dev_);
         release(ctx_, flags_dev_);
         cudaStreamSynchronize(ctx_->stream);
@@ -173,23 +173,72 @@ class DeviceDriver {
                 }
             part_.resize(static_cast<size_t>(labels) + 1);
             if ((rc = grow(ctx_, part_dev_, (static_cast<size_t>(labels) + 1) * sizeof(int32_t)))) return rc;
-            size_t at = 0;
+            // The three kinds of nodes run next to each other: the batch of small nodes and the batch of medium nodes
+            // each on its own context (stream, workspace) and host thread, the large nodes on this one.  All read the
+            // wave's tours and write disjoint ranges of the label array; the other streams wait for the tours.
+            const size_t at_medium = large.size(), at_small = large.size() + medium.size();
+            // this thread takes the large nodes, else the medium batch, else the small batch; the others go aside
+            scs_ctx *small_ctx = ctx_, *medium_ctx = ctx_;
+            if (scs_host_threads() >= 2 && ensure_workers(ctx_, 3) == SCS_OK) {
+                if (!small.empty() && (!large.empty() || !medium.empty())) small_ctx = ctx_->workers[0];
+                if (!medium.empty() && !large.empty()) medium_ctx = ctx_->workers[1];
+            }
+            if (small_ctx != ctx_ || medium_ctx != ctx_) {
+                if (!tours_ready_) SCS_CUDA(ctx_, cudaEventCreateWithFlags(&tours_ready_, cudaEventDisableTiming));
+                SCS_CUDA(ctx_, cudaEventRecord(tours_ready_, ctx_->stream));
+            }
+            int small_rc = SCS_OK, medium_rc = SCS_OK;
+            double small_s = 0.0, medium_s = 0.0;
+            std::vector<size_t> reruns;
+            auto run_small = [&](scs_ctx *ctx) {
+                Stopwatch sw(&small_s);
+                small_rc = split_small(ctx, wave, small, splits.data() + at_small);
+            };
+            auto run_medium = [&](scs_ctx *ctx) {
+                Stopwatch sw(&medium_s);
+                medium_rc = split_medium(ctx, wave, medium, splits.data() + at_medium, reruns);
+            };
+            auto aside = [&](scs_ctx *ctx, auto &work, int *status) {
+                return std::thread([this, ctx, &work, status] {
+                    cudaError_t err = cudaSetDevice(ctx_->device);
+                    if (err == cudaSuccess) err = cudaStreamWaitEvent(ctx->stream, tours_ready_, 0);
+                    if (err != cudaSuccess) {
+                        *status = fail(ctx, SCS_ERR_CUDA, "starting a batch next to the other nodes of the wave", err);
+                        return;
+                    }
+                    work(ctx);
+                });
+            };
+            std::thread small_thread, medium_thread;
+            if (!small.empty() && small_ctx != ctx_) small_thread = aside(small_ctx, run_small, &small_rc);
+            if (!medium.empty() && medium_ctx != ctx_) medium_thread = aside(medium_ctx, run_medium, &medium_rc);
             if (!large.empty()) {
                 Stopwatch sw(&out_.seconds[0]);
-                for (size_t k = 0; k < large.size(); ++k)
-                    if ((rc = split_large(wave[large[k]], splits[at + k]))) return rc;
+                for (size_t k = 0; k < large.size() && rc == SCS_OK; ++k) rc = split_large(wave[large[k]], splits[k]);
                 out_.nodes_large += static_cast<int64_t>(large.size());
             }
-            at += large.size();
-            if (!medium.empty()) {
-                Stopwatch sw(&out_.medium_seconds);
-                if ((rc = split_medium(wave, medium, splits.data() + at))) return rc;
-            }
-            at += medium.size();
-            if (!small.empty()) {
-                Stopwatch sw(&out_.seconds[1]);
-                if ((rc = split_small(wave, small, splits.data() + at))) return rc;
-                out_.nodes_small += static_cast<int64_t>(small.size());
+            if (rc == SCS_OK && !medium.empty() && medium_ctx == ctx_) run_medium(ctx_);
+            if (rc == SCS_OK && !small.empty() && small_ctx == ctx_) run_small(ctx_);
+            if (small_thread.joinable()) small_thread.join();
+            if (medium_thread.joinable()) medium_thread.join();
+            for (scs_ctx *other : {small_ctx, medium_ctx})
+                if (other != ctx_) {
+                    if (rc == SCS_OK && (other == small_ctx ? small_rc : medium_rc) != SCS_OK) ctx_->last_error = other->last_error;
+                    ctx_->launches += other->launches;
+                    ctx_->h2d_bytes += other->h2d_bytes;
+                    ctx_->d2h_bytes += other->d2h_bytes;
+                    other->launches = other->h2d_bytes = other->d2h_bytes = 0;
+                }
+            out_.seconds[1] += small_s;
+            out_.medium_seconds += medium_s;
+            if (rc == SCS_OK) rc = small_rc ? small_rc : medium_rc;
+            if (rc) return rc;
+            out_.nodes_small += static_cast<int64_t>(small.size());
+            out_.nodes_medium += static_cast<int64_t>(medium.size());
+            // eigensolver restart / repeated-eigenvalue check of a medium node: the per-node path has both
+            for (size_t b : reruns) {
+                out_.nodes_rerun += 1;
+                if ((rc = split_large(wave[medium[b]], splits[at_medium + b]))) return rc;
             }
             // labels of every node of the wave, and the malformed-input flags, in one copy each
             SCS_CUDA(ctx_, cudaMemcpyAsync(part_.data(), part_dev_.as<int32_t>(), sizeof(int32_t) * static_cast<size_t>(labels),
@@ -271,7 +320,8 @@ class DeviceDriver {
         return rc;
     }
 
-    int split_medium(std::vector<Job> &wave, const std::vector<size_t> &medium, Split *splits) {
+    int split_medium(scs_ctx *ctx, std::vector<Job> &wave, const std::vector<size_t> &medium, Split *splits,
+                     std::vector<size_t> &reruns) {
         const DevForest &forest = forest_[cur_];
         const int B = static_cast<int>(medium.size());
         std::vector<int32_t> node_n(B), tree_begin(B), tree_end(B);
@@ -287,24 +337,20 @@ class DeviceDriver {
         }
         std::vector<scs_node_stats> stats(B);
         std::vector<uint8_t> rerun(B, 0);
-        int rc = medium_batch(ctx_, B, node_n.data(), tree_begin.data(), tree_end.data(), part_off.data(), seeds.data(),
+        int rc = medium_batch(ctx, B, node_n.data(), tree_begin.data(), tree_end.data(), part_off.data(), seeds.data(),
                               static_cast<int>(forest.trees), forest.leaves, forest.leaf_off.as<int64_t>(),
                               tours_.leaf_taxon.as<int32_t>(), tours_.adj_depth.as<int32_t>(), tours_.adj_val.as<double>(),
                               tours_.root_depth.as<int32_t>(), forest.weight.as<double>(), contract_, part_dev_.as<int32_t>(),
                               stats.data(), rerun.data());
         if (rc) return rc;
-        out_.nodes_medium += B;
         for (int b = 0; b < B; ++b) {
             splits[b].stats = stats[b];
-            if (!rerun[b]) continue;
-            // eigensolver restart / repeated-eigenvalue check: the per-node path has both
-            out_.nodes_rerun += 1;
-            if ((rc = split_large(wave[medium[b]], splits[b]))) return rc;
+            if (rerun[b]) reruns.push_back(static_cast<size_t>(b));
         }
         return SCS_OK;
     }
 
-    int split_small(std::vector<Job> &wave, const std::vector<size_t> &small, Split *splits) {
+    int split_small(scs_ctx *ctx, std::vector<Job> &wave, const std::vector<size_t> &small, Split *splits) {
         const DevForest &forest = forest_[cur_];
         const int B = static_cast<int>(small.size());
         std::vector<scs_small_node> desc(B);
@@ -318,24 +364,25 @@ class DeviceDriver {
         }
         int rc;
         const size_t bytes = sizeof(scs_small_node) * static_cast<size_t>(B);
-        if ((rc = grow(ctx_, small_desc_dev_, bytes))) return rc;
+        scs_small_node *desc_dev;
+        if ((rc = reserve_as(ctx, SLOT_MED_NODES, static_cast<size_t>(B), &desc_dev))) return rc;
         void *pin_v;
-        if ((rc = reserve_pinned(ctx_, bytes + sizeof(scs_node_stats) * static_cast<size_t>(B) + 512, &pin_v))) return rc;
+        if ((rc = reserve_pinned(ctx, bytes + sizeof(scs_node_stats) * static_cast<size_t>(B) + 512, &pin_v))) return rc;
         unsigned char *pin = static_cast<unsigned char *>(pin_v);
         std::memcpy(pin, desc.data(), bytes);
-        SCS_CUDA(ctx_, cudaMemcpyAsync(small_desc_dev_.ptr, pin, bytes, cudaMemcpyHostToDevice, ctx_->stream));
-        ctx_->h2d_bytes += static_cast<int64_t>(bytes);
+        SCS_CUDA(ctx, cudaMemcpyAsync(desc_dev, pin, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->h2d_bytes += static_cast<int64_t>(bytes);
         scs_node_stats *stats_dev;
-        if ((rc = reserve_as(ctx_, SLOT_NODE_STATS, static_cast<size_t>(B), &stats_dev))) return rc;
-        rc = small_batch(ctx_, B, small_desc_dev_.as<scs_small_node>(), forest.leaf_off.as<int64_t>(), tours_.leaf_taxon.as<int32_t>(),
+        if ((rc = reserve_as(ctx, SLOT_NODE_STATS, static_cast<size_t>(B), &stats_dev))) return rc;
+        rc = small_batch(ctx, B, desc_dev, forest.leaf_off.as<int64_t>(), tours_.leaf_taxon.as<int32_t>(),
                          tours_.adj_depth.as<int32_t>(), tours_.adj_val.as<double>(), tours_.root_depth.as<int32_t>(),
                          forest.weight.as<double>(), contract_, part_dev_.as<int32_t>(), stats_dev, flags_dev_.as<int32_t>(), 1);
         if (rc) return rc;
         scs_node_stats *stats_pin = reinterpret_cast<scs_node_stats *>(pin + ((bytes + 255) & ~static_cast<size_t>(255)));
-        SCS_CUDA(ctx_, cudaMemcpyAsync(stats_pin, stats_dev, sizeof(scs_node_stats) * static_cast<size_t>(B), cudaMemcpyDeviceToHost,
-                                       ctx_->stream));
-        SCS_CUDA(ctx_, cudaStreamSynchronize(ctx_->stream));
-        ctx_->d2h_bytes += static_cast<int64_t>(sizeof(scs_node_stats)) * B;
+        SCS_CUDA(ctx, cudaMemcpyAsync(stats_pin, stats_dev, sizeof(scs_node_stats) * static_cast<size_t>(B), cudaMemcpyDeviceToHost,
+                                       ctx->stream));
+        SCS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->d2h_bytes += static_cast<int64_t>(sizeof(scs_node_stats)) * B;
         for (int b = 0; b < B; ++b) splits[b].stats = stats_pin[b];
         return SCS_OK;
     }
@@ -442,7 +489,8 @@ class DeviceDriver {
     DevForest forest_[2];
     int cur_ = 0;
     DevTours tours_;
-    GrowBuf vertex_dev_, offsets_rel_, small_desc_dev_, part_dev_, flags_dev_;
+    GrowBuf vertex_dev_, offsets_rel_, part_dev_, flags_dev_;
+    cudaEvent_t tours_ready_ = nullptr;
     std::vector<int32_t> vertex_, owner_, part_, pending_slot_;
     std::vector<uint8_t> present_;
 };
