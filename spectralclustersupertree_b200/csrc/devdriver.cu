@@ -38,6 +38,7 @@ struct Job {
     std::vector<int32_t> taxa;  // taxa present in its trees, ascending (vertex id = rank; scs.py:708-725)
     DevJobInfo where{};         // its trees / leaves / nodes in the wave's forest
     int64_t leaves = 0;         // tour positions of its trees
+    bool shared = false;        // cooperative build: every rank holds and processes this job (row-sharded over the GPUs)
 };
 
 __global__ void relative_offsets(int count, const int64_t *__restrict__ absolute, int64_t *__restrict__ out) {
@@ -47,8 +48,10 @@ __global__ void relative_offsets(int count, const int64_t *__restrict__ absolute
 
 class DeviceDriver {
   public:
-    DeviceDriver(scs_ctx *ctx, int weighting, int contract_edges, uint64_t seed, bool record, scs_supertree *out)
-        : ctx_(ctx), weighting_(weighting), contract_(contract_edges), seed_(seed), record_(record), out_(*out) {}
+    DeviceDriver(scs_ctx *ctx, int weighting, int contract_edges, uint64_t seed, bool record, int rank, int world,
+                 scs_supertree *out)
+        : ctx_(ctx), weighting_(weighting), contract_(contract_edges), seed_(seed), record_(record), rank_(rank),
+          world_(world), out_(*out) {}
 
     ~DeviceDriver() {
         forest_[0].free_all(ctx_);
@@ -75,8 +78,10 @@ class DeviceDriver {
         if ((rc = grow(ctx_, flags_dev_, 64 * sizeof(int32_t)))) return rc;
         SCS_CUDA(ctx_, cudaMemsetAsync(flags_dev_.ptr, 0, 64 * sizeof(int32_t), ctx_->stream));
 
+        const ShardState &sh = ctx_->shard;
+        cooperative_ = world_ > 1 && sh.connected && sh.world == world_ && sh.rank == rank_;
         std::vector<Job> wave(1), next;
-        wave[0].slot = add(-1, -1);
+        wave[0].slot = add(-1, -1, cooperative_);
         {
             std::vector<uint8_t> seen(vertex_.size(), 0);
             for (int32_t x : root->taxon)
@@ -90,6 +95,12 @@ class DeviceDriver {
         wave[0].where.pair_visits = scs_forest_pair_visits(root);
         wave[0].leaves = root->leaf_offsets.back();
         cur_ = 0;
+        if (cooperative_) {
+            load_.assign(static_cast<size_t>(world_), 0.0);
+            const int n_root = static_cast<int>(wave[0].taxa.size());
+            wave[0].shared = stays_shared(n_root);
+            if (!wave[0].shared && deal(n_root) != rank_) wave.clear();  // a small job: one rank does it all
+        }
         while (!wave.empty()) {
             out_.waves += 1;
             int32_t max_n = 0;
@@ -105,22 +116,63 @@ class DeviceDriver {
             out_.wave_seconds.push_back(std::chrono::duration<double>(std::chrono::steady_clock::now() - wave_start).count());
             wave.swap(next);
         }
+        ctx_->shard.engaged = false;
+        if (cooperative_) finish_cooperative();
         return SCS_OK;
     }
 
   private:
+    bool stays_shared(int size) const { return cooperative_ && size >= ctx_->shard.min_n; }
+    int deal(int size) {
+        const double n = static_cast<double>(size);
+        const int r = static_cast<int>(std::min_element(load_.begin(), load_.end()) - load_.begin());
+        load_[r] += n + n * n / 2.0e5;  // small nodes cost per node (latency), large ones per leaf pair
+        return r;
+    }
+    void finish_cooperative() {
+        const int32_t S = static_cast<int32_t>(sh_parent_.size());
+        auto final_index = [S](int32_t id) { return id >= 0 ? S + id : (id == -1 ? -1 : -2 - id); };
+        std::vector<int32_t> parent(sh_parent_.size() + out_.parent.size()), taxon(parent.size());
+        for (int32_t i = 0; i < S; ++i) {
+            parent[i] = final_index(sh_parent_[i]);
+            taxon[i] = sh_taxon_[i];
+        }
+        for (size_t j = 0; j < out_.parent.size(); ++j) {
+            parent[S + j] = final_index(out_.parent[j]);
+            taxon[S + j] = out_.taxon[j];
+        }
+        out_.parent.swap(parent);
+        out_.taxon.swap(taxon);
+        out_.shared_prefix = S;
+        out_.shared_records = static_cast<int64_t>(sh_records_.size());
+        sh_records_.insert(sh_records_.end(), std::make_move_iterator(out_.records.begin()),
+                           std::make_move_iterator(out_.records.end()));
+        out_.records.swap(sh_records_);
+    }
+
     // ---- output nodes (scs.py:390-408, 728-746) -----------------------------------------------------------------------
-    int32_t add(int32_t parent, int32_t taxon) {
+    // Node ids: id >= 0 is a node of this rank's own list; id <= -2 is node -2 - id of the shared list (cooperative
+    // builds only); -1 is "no parent".
+    int32_t add(int32_t parent, int32_t taxon, bool shared) {
+        if (shared) {
+            sh_parent_.push_back(parent);
+            sh_taxon_.push_back(taxon);
+            return -2 - static_cast<int32_t>(sh_parent_.size() - 1);
+        }
         out_.parent.push_back(parent);
         out_.taxon.push_back(taxon);
         return static_cast<int32_t>(out_.parent.size() - 1);
     }
-    void fill_star(int32_t slot, const int32_t *taxa, int count) {  // one name stays a tip, more become a star
+    void set_taxon(int32_t id, int32_t taxon) {
+        if (id >= 0) out_.taxon[id] = taxon;
+        else sh_taxon_[-2 - id] = taxon;
+    }
+    void fill_star(int32_t slot, const int32_t *taxa, int count, bool shared) {  // one name stays a tip, more a star
         if (count == 1) {
-            out_.taxon[slot] = taxa[0];
+            set_taxon(slot, taxa[0]);
             return;
         }
-        for (int i = 0; i < count; ++i) add(slot, taxa[i]);
+        for (int i = 0; i < count; ++i) add(slot, taxa[i], shared);
     }
 
     struct Split {
@@ -140,7 +192,8 @@ class DeviceDriver {
             const int n = static_cast<int>(job.taxa.size());
             if (job.where.trees == 0) return fail(ctx_, SCS_ERR_EMPTY, "a component is covered by no source tree (scs.py:63-65)");
             if (job.where.trees == 1) single.push_back(i);
-            else if (n <= 2) fill_star(job.slot, job.taxa.data(), n);
+            else if (n <= 2) fill_star(job.slot, job.taxa.data(), n, job.shared);
+            else if (job.shared) large.push_back(i);  // row-sharded over the GPUs, every rank in the same order
             else if (n <= ctx_->small_limit && job.where.trees <= kSmallMaxTrees) small.push_back(i);
             else if (n <= ctx_->medium_limit) medium.push_back(i);
             else large.push_back(i);
@@ -289,9 +342,10 @@ class DeviceDriver {
         for (int i = 0; i < count; ++i) {
             const int32_t slot = wave[single[i]].slot;
             where.assign(static_cast<size_t>(nodes[i]), 0);
+            const bool shared = wave[single[i]].shared;
             where[0] = slot;
-            out_.taxon[slot] = tax[at];
-            for (int64_t k = 1; k < nodes[i]; ++k) where[k] = add(where[par[at + k]], tax[at + k]);
+            set_taxon(slot, tax[at]);
+            for (int64_t k = 1; k < nodes[i]; ++k) where[k] = add(where[par[at + k]], tax[at + k], shared);
             at += nodes[i];
         }
         return SCS_OK;
@@ -309,6 +363,7 @@ class DeviceDriver {
         SCS_LAUNCHED(ctx_, "relative_offsets");
         const int64_t L = job.leaves;
         ctx_->pending_units = static_cast<double>(job.where.pair_visits);
+        ctx_->shard.engaged = job.shared;
         std::memset(&s.stats, 0, sizeof(s.stats));
         s.stats.eig[1] = s.stats.eig[2] = s.stats.residual = s.stats.margin = std::nan("");
         rc = node_split(ctx_, n, T, L, offsets_rel_.as<int64_t>(), tours_.leaf_taxon.as<int32_t>() + job.where.leaf_begin,
@@ -317,6 +372,7 @@ class DeviceDriver {
                         contract_, seed_ + static_cast<uint64_t>(job.slot), part_dev_.as<int32_t>() + s.part_at, nullptr,
                         &s.stats);
         ctx_->pending_units = 0.0;
+        ctx_->shard.engaged = false;
         return rc;
     }
 
@@ -396,6 +452,7 @@ class DeviceDriver {
         std::sort(splits.begin(), splits.end(), [](const Split &a, const Split &b) { return a.job < b.job; });
         struct Pending {
             int32_t parent_slot;
+            bool parent_shared, stays;     // the parent was a shared job; the child stays shared
             std::vector<int32_t> members;  // taxa of the component, ascending
         };
         std::vector<Pending> pending;      // one per new job
@@ -413,7 +470,7 @@ class DeviceDriver {
                 rec.part.assign(part, part + n);
                 rec.stats = s.stats;
                 rec.wave = static_cast<int32_t>(out_.waves - 1);
-                out_.records.push_back(std::move(rec));
+                (job.shared ? sh_records_ : out_.records).push_back(std::move(rec));
             }
             start.assign(parts + 1, 0);
             for (int v = 0; v < n; ++v) {
@@ -435,17 +492,27 @@ class DeviceDriver {
                     part_newjob.push_back(-1);
                     continue;
                 }
-                const int32_t child_slot = add(job.slot, -1);
+                // the children of a shared job are shared output nodes: every rank creates them, in the same order
+                const int32_t child_slot = add(job.slot, -1, job.shared);
                 if (size <= 2) {  // scs.py:143-145
-                    fill_star(child_slot, comp, size);
+                    fill_star(child_slot, comp, size, job.shared);
                     for (int i = 0; i < size; ++i) owner_[comp[i]] = -1;
                     part_newjob.push_back(-1);
                     continue;
                 }
+                bool stays = false;
+                if (job.shared) {
+                    stays = stays_shared(size);
+                    if (!stays && deal(size) != rank_) {  // dealt to another rank: its owner restricts the trees to it
+                        for (int i = 0; i < size; ++i) owner_[comp[i]] = -1;
+                        part_newjob.push_back(-1);
+                        continue;
+                    }
+                }
                 const int32_t gp = static_cast<int32_t>(part_newjob.size());
                 for (int i = 0; i < size; ++i) owner_[comp[i]] = gp;
                 part_newjob.push_back(static_cast<int32_t>(pending.size()));
-                pending.push_back(Pending{job.slot, std::vector<int32_t>(comp, comp + size)});
+                pending.push_back(Pending{job.slot, job.shared, stays, std::vector<int32_t>(comp, comp + size)});
                 pending_slot_.push_back(child_slot);
             }
         }
@@ -468,10 +535,12 @@ class DeviceDriver {
             child.leaves = (j + 1 < new_jobs ? info[j + 1].leaf_begin : forest_[1 - cur_].leaves) - info[j].leaf_begin;
             // taxa of the component that are a tip of some kept tree; the others are attached as singleton children of
             // the parent (scs.py:168-171).  A child left without trees raises when its wave is processed.
+            // (known to whoever restricted: to every rank only if the child stays shared)
             const bool empty = info[j].trees == 0;
+            child.shared = pending[j].stays;
             for (int32_t x : pending[j].members) {
                 if (present_[x]) child.taxa.push_back(x);
-                else if (!empty) add(pending[j].parent_slot, x);
+                else if (!empty) add(pending[j].parent_slot, x, pending[j].parent_shared && pending[j].stays);
             }
             next.push_back(std::move(child));
         }
@@ -484,6 +553,16 @@ class DeviceDriver {
     int weighting_, contract_;
     uint64_t seed_;
     bool record_;
+    int rank_ = 0, world_ = 1;
+    // Cooperative build over several GPUs (exchange windows connected, see driver.cu): a job of at least shard.min_n taxa
+    // is SHARED -- every rank keeps its trees and the node is row-sharded over the GPUs; a smaller child of a shared
+    // job is DEALT, with everything below it, to the rank with the least estimated work so far (every rank takes the
+    // same decision from the same partition, nobody talks) and only its owner restricts the trees to it.  Shared
+    // output nodes go to a list that is identical on every rank (ids <= -2) and becomes the shared prefix.
+    bool cooperative_ = false;
+    std::vector<double> load_;
+    std::vector<int32_t> sh_parent_, sh_taxon_;
+    std::vector<scs_supertree::Record> sh_records_;
     scs_supertree &out_;
     int num_taxa_ = 0;
     DevForest forest_[2];
@@ -498,8 +577,8 @@ class DeviceDriver {
 }  // namespace
 
 int run_device_driver(scs_ctx *ctx, const scs_forest *forest, int weighting, int contract_edges, uint64_t seed, bool record,
-                      scs_supertree *out) {
-    DeviceDriver driver(ctx, weighting, contract_edges, seed, record, out);
+                      int rank, int world, scs_supertree *out) {
+    DeviceDriver driver(ctx, weighting, contract_edges, seed, record, rank, world, out);
     return driver.run(forest);
 }
 

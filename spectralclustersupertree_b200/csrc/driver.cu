@@ -965,9 +965,11 @@ int scs_supertree_build_sharded(scs_ctx *ctx, const scs_forest *forest, int weig
     cudaSetDevice(ctx->device);
     std::unique_ptr<scs_supertree> result(new scs_supertree());
     int rc;
-    if (world == 1 && ctx->device_forest) {
-        // one GPU: the source trees stay on the device for the whole recursion (devdriver.cu)
-        rc = run_device_driver(ctx, forest, weighting, contract_edges, seed, record_nodes != 0, result.get());
+    const ShardState &sh = ctx->shard;
+    const bool cooperative = world > 1 && sh.connected && sh.world == world && sh.rank == rank;
+    if (ctx->device_forest && (world == 1 || cooperative)) {
+        // the source trees stay on the device for the whole recursion (devdriver.cu)
+        rc = run_device_driver(ctx, forest, weighting, contract_edges, seed, record_nodes != 0, rank, world, result.get());
     } else {
         Driver driver(ctx, weighting, contract_edges, seed, record_nodes != 0, rank, world, result.get());
         rc = driver.run(forest);

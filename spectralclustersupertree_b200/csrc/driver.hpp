@@ -31,8 +31,10 @@ struct scs_forest;
 namespace scs {
 
 // The whole recursion with the source trees resident in HBM (devdriver.cu): restriction and tour flattening on the
-// device, one small host round trip per wave for the bookkeeping of the output tree.  One GPU.
+// device, a few small host round trips per wave for the bookkeeping of the output tree.  One GPU, or rank `rank` of
+// `world` in a cooperative build (exchange windows connected: large nodes row-sharded over the GPUs, smaller
+// sub-problems dealt out over the ranks).
 int run_device_driver(scs_ctx *ctx, const scs_forest *forest, int weighting, int contract_edges, uint64_t seed, bool record,
-                      scs_supertree *out);
+                      int rank, int world, scs_supertree *out);
 
 }  // namespace scs
