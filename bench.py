@@ -6,15 +6,15 @@ One *step* is one complete ``construct_supertree`` job on the named synthetic wo
 ``c4``: 10 000 taxa x 1 000 source trees, depth weighting -- the configuration BASELINE.json's metric
 is quoted on).  Three clocks are reported in one JSON line:
 
-* ``value``  -- the hot path alone with inputs resident in HBM: every recursion node of the job
-  (graph build, components, contraction, spectral split) replayed from leaf tours that were uploaded
-  before the timed region -- nodes with more than 64 taxa one by one, all smaller ones in one batched
-  launch; CUDA events on the engine's stream.
+* ``value``  -- the hot path alone with inputs resident in HBM: the whole recursion of the job
+  (``scs_supertree_build_resident``) from source trees that were uploaded before the timed region -- tours, graph
+  build, components, contraction, spectral split and the restriction of the trees to the children, all on the
+  device, wave by wave; CUDA events around the build.
 * ``e2e``    -- the same job through the public host-buffer path over the C ABI
   (``scs_forest_create`` + ``scs_supertree_build``): flat source trees in host memory in, flat
-  supertree out; native breadth-first recursion, tree restriction, per-wave H2D of tours and D2H of
-  partitions inside the timed region.  With N > 1 the frontier of independent sub-problems is dealt
-  out over the ranks (no data-path collective) and the outputs are all-gathered.
+  supertree out; validation of the trees, H2D of the forest, the recursion, D2H of partitions inside the timed
+  region.  With N > 1 the large recursion nodes are row-sharded over the GPUs, smaller sub-problems are dealt out
+  over the ranks (no data-path collective) and the outputs are all-gathered.
 * ``roofline`` -- the Laplacian matvec (the kernel BASELINE.json's metric names), timed per launch
   with CUDA events inside the timed steps, against the measured HBM peak.
 
@@ -283,129 +283,6 @@ def reference_line(args) -> dict:
 # ---------------------------------------------------------------------------------------------
 # the GPU arm
 # ---------------------------------------------------------------------------------------------
-class Replay:
-    """The recursion nodes one rank processes, as leaf tours resident in HBM, for the device-only timed pass.
-    The nodes are replayed wave by wave, as the native driver issues them: per wave every node above
-    ``medium_limit`` taxa through ``scs_node_split_dev``, all nodes between the two limits in one batch
-    (``scs_nodes_split_medium_dev``), all nodes up to ``small_limit`` in one launch of the small-node kernel
-    (``scs_nodes_split_small_dev``)."""
-
-    FIELDS = (("leaf_offsets", np.int64), ("leaf_taxon", np.int32), ("adj_depth", np.int32),
-              ("adj_val", np.float64), ("root_depth", np.int32), ("tree_weight", np.float64))  # fmt: skip
-
-    def __init__(self, engine, nodes: list, waves: list, small_limit: int = 64, medium_limit: int = 4096,
-                 shared: list | None = None) -> None:
-        from spectralclustersupertree_b200 import _lib
-
-        self.engine = engine
-        self.lib = _lib.load()
-        self.pair_visits = [t.pair_updates() for t, _ in nodes]
-        shared = shared or [False] * len(nodes)
-        self.bytes = 0
-        self.buffers = []
-        self.waves = []
-        self.part = engine.alloc(4 * max([t.n for t, _ in nodes] + [1]))
-        self.buffers.append(self.part)
-        for wave in sorted(set(waves)):
-            members = [(t, seed, sh) for (t, seed), w, sh in zip(nodes, waves, shared, strict=True) if w == wave]
-            large = [(t, seed, sh) for t, seed, sh in members if t.n > medium_limit or sh]
-            medium = [(t, seed) for t, seed, sh in members if small_limit < t.n <= medium_limit and not sh]
-            small = [t for t, _, sh in members if t.n <= small_limit and not sh]
-            entry = {"large": [], "medium": None, "small": None}
-            if large:
-                host = {k: np.concatenate([getattr(t, k) for t, _, _ in large]).astype(d) for k, d in self.FIELDS}
-                dev = {k: self._upload(v) for k, v in host.items()}
-                pos = dict.fromkeys(host, 0)
-                for tours, seed, sh in large:
-                    T, L = tours.num_trees, tours.num_leaves
-                    item = {"n": tours.n, "T": T, "L": L, "seed": seed, "shared": sh}
-                    for key, count in (("leaf_offsets", T + 1), ("leaf_taxon", L), ("adj_depth", L), ("adj_val", L),
-                                       ("root_depth", T), ("tree_weight", T)):  # fmt: skip
-                        item[key] = dev[key] + pos[key] * host[key].itemsize
-                        pos[key] += count
-                    entry["large"].append(item)
-            if medium:
-                host = {k: np.concatenate([getattr(t, k) for t, _ in medium]).astype(d) for k, d in self.FIELDS
-                        if k != "leaf_offsets"}  # fmt: skip
-                offsets, base = [], 0
-                for t, _ in medium:
-                    offsets.append(t.leaf_offsets[:-1].astype(np.int64) + base)
-                    base += t.num_leaves
-                host["leaf_offsets"] = np.concatenate(offsets + [np.array([base], dtype=np.int64)])
-                dev = {k: self._upload(v) for k, v in host.items()}
-                sizes = np.array([t.n for t, _ in medium], dtype=np.int32)
-                tree_begin = np.concatenate([[0], np.cumsum([t.num_trees for t, _ in medium])]).astype(np.int32)
-                part_off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
-                entry["medium"] = {
-                    "dev": dev, "B": len(medium), "n": sizes, "tree_begin": tree_begin, "part_off": part_off,
-                    "seeds": np.array([seed & 0xFFFFFFFFFFFFFFFF for _, seed in medium], dtype=np.uint64),
-                    "T": int(tree_begin[-1]), "L": int(base), "part": engine.alloc(4 * int(part_off[-1]) + 16),
-                    "stats": (_lib.NodeStats * len(medium))(), "rerun": np.zeros(len(medium), dtype=np.uint8),
-                }  # fmt: skip
-                self.buffers.append(entry["medium"]["part"])
-            if small:
-                # the layout of scs_small_node (include/scs_b200.h)
-                desc = np.zeros(len(small), dtype=np.dtype([("n", "<i4"), ("num_trees", "<i4"), ("leaf_base", "<i8"),
-                                                            ("tree_base", "<i8"), ("vertex_base", "<i8")]))  # fmt: skip
-                L = T = N = 0
-                for b, t in enumerate(small):
-                    desc[b] = (t.n, t.num_trees, L, T, N)
-                    L += t.num_leaves
-                    T += t.num_trees
-                    N += t.n
-                host = {k: np.concatenate([getattr(t, k) for t in small]).astype(d) for k, d in self.FIELDS}
-                entry["small"] = {"dev": {k: self._upload(v) for k, v in host.items()}, "desc": self._upload(desc),
-                                  "count": len(small), "part": engine.alloc(4 * max(N, 1)),
-                                  "stats": engine.alloc(80 * len(small))}  # fmt: skip
-                self.buffers += [entry["small"]["part"], entry["small"]["stats"]]
-            self.waves.append(entry)
-        self.reruns = 0
-
-    def _upload(self, array: np.ndarray) -> int:
-        self.bytes += array.nbytes
-        dev = self.engine.to_device(array)
-        self.buffers.append(dev)
-        return dev
-
-    def run(self, contract_edges: bool = True) -> None:
-        from spectralclustersupertree_b200.engine import ptr
-
-        for wave in self.waves:
-            for entry in wave["large"]:
-                # nodes the ranks share out (row-sharded over the GPUs) are replayed the same way
-                if entry["shared"]:
-                    self.engine.shard_engage(True)
-                self.engine.node_split_dev(entry, self.part, contract_edges=contract_edges, seed=entry["seed"])
-                if entry["shared"]:
-                    self.engine.shard_engage(False)
-            med = wave["medium"]
-            if med is not None:
-                d = med["dev"]
-                status = self.lib.scs_nodes_split_medium_dev(
-                    self.engine.handle, med["B"], ptr(med["n"]), ptr(med["tree_begin"]), ptr(med["part_off"]),
-                    ptr(med["seeds"]), med["T"], med["L"], d["leaf_offsets"], d["leaf_taxon"], d["adj_depth"],
-                    d["adj_val"], d["root_depth"], d["tree_weight"], int(contract_edges), med["part"], med["stats"],
-                    ptr(med["rerun"]),
-                )  # fmt: skip
-                if status != 0:
-                    raise RuntimeError(f"scs_nodes_split_medium_dev failed with status {status}")
-                self.reruns += int(med["rerun"].sum())
-            sm = wave["small"]
-            if sm is not None:
-                d = sm["dev"]
-                status = self.lib.scs_nodes_split_small_dev(
-                    self.engine.handle, sm["count"], sm["desc"], d["leaf_offsets"], d["leaf_taxon"],
-                    d["adj_depth"], d["adj_val"], d["root_depth"], d["tree_weight"], int(contract_edges),
-                    sm["part"], sm["stats"],
-                )  # fmt: skip
-                if status != 0:
-                    raise RuntimeError(f"scs_nodes_split_small_dev failed with status {status}")
-
-    def close(self) -> None:
-        for d in self.buffers:
-            self.engine.free(d)
-
-
 def gather_supertree(dist, built: dict, local_rank: int):
     """All ranks' flat outputs joined on every rank (tiny: 2 int32 per output node)."""
     import torch
@@ -509,52 +386,49 @@ def gpu_line(args, arrays: dict) -> dict:
             return built, (built["parent"], built["taxon"])
         return built, gather_supertree(dist, built, local_rank)
 
-    # recording pass (untimed): every recursion node's leaf tours, keyed by its vertex set, from the
-    # per-node Python recursion; then the nodes THIS rank processes in the (sharded) native build
-    recorded: dict = {}
-    supertree_of_forest(new_forest(), weighting, engine=engine, native=False,
-                        node_hook=lambda f, seed: recorded.__setitem__(f.taxa().tobytes(), (f.tours(weighting), seed)))  # fmt: skip
+    # one untimed build with records: what the job consists of
     traced = engine.supertree_build(new_forest(), weighting, record=True, rank=rank, world=world)
-    mine = [recorded[taxa.tobytes()] for taxa, _, _ in traced["records"]]
     sharing = dist is not None and args.shard_min_n > 0
-    shared = [sharing and i < traced["shared_records"] and t.n >= args.shard_min_n for i, (t, _) in enumerate(mine)]
-    replay = Replay(engine, mine, traced["record_waves"], shared=shared,
-                    small_limit=args.small_limit if args.small_limit >= 0 else 64)
     spectral = [st for _, _, st in traced["records"] if st.n_components == 1]
-    all_visits = [t.pair_updates() for t, _ in recorded.values()]
+    sizes = [len(taxa) for taxa, _, _ in traced["records"]]
     job = {
-        "recursion_nodes": len(recorded),
-        "recursion_nodes_this_rank": len(mine),
+        "recursion_nodes_this_rank": len(traced["records"]),
         "spectral_nodes_this_rank": len(spectral),
         "largest_spectral_m": max((st.contracted_size for st in spectral), default=0),
         "lanczos_matvecs_this_rank": sum(st.matvecs for st in spectral if st.solver == 3),
         "tie_nodes_this_rank": sum(1 for st in spectral if st.tie_flag & 3),
-        "pair_visits_total": int(sum(all_visits)),
-        "pair_visits_top": int(max(all_visits)) if all_visits else 0,
+        "pair_visits_this_rank": int(traced["pair_visits"]),
         "waves": traced["waves"],
         "wave_tasks": traced["wave_tasks"],
         "wave_max_n": traced["wave_max_n"],
-        "nodes_small": traced["nodes_small"],
-        "nodes_large": traced["nodes_large"],
-        "nodes_medium_batched": traced["nodes_medium"],
+        "nodes_small_one_launch_per_wave": traced["nodes_small"],
+        "nodes_medium_batched_per_wave": traced["nodes_medium"],
         "nodes_medium_rerun_per_node": traced["nodes_rerun"],
-        "resident_tour_bytes": int(replay.bytes),
-        "nodes_row_sharded_over_gpus": int(sum(shared)),
+        "nodes_large_per_node": traced["nodes_large"],
+        "nodes_row_sharded_over_gpus": int(sum(1 for n in sizes[: traced["shared_records"]] if sharing and n >= args.shard_min_n)),
     }
+    if world == 1:
+        job["recursion_nodes"] = len(traced["records"])
+    resident = engine.device_forest(new_forest(), weighting)
+    job["resident_forest_bytes"] = resident.nbytes
 
     def barrier():
         engine.synchronize()
         if dist is not None:
             dist.barrier()
 
+    def device_step():
+        """The hot path with its inputs resident in HBM: the whole recursion from the device forest."""
+        return engine.supertree_build_resident(resident, rank=rank, world=world)
+
     for _ in range(args.warmup):
         _, merged = e2e_step()
-        replay.run()
+        device_step()
     engine.synchronize()
     tips = int((merged[1] >= 0).sum())
 
     sampler = ClockSampler(local_rank)
-    # ---- timed: device-resident replay (value) with per-launch matvec / row-kernel timing ----------
+    # ---- timed: the recursion from the device-resident forest (value), per-launch matvec / row-kernel timing --------
     engine.profile(True)
     launches_before = engine.launch_count
     dev_ms = []
@@ -562,7 +436,7 @@ def gpu_line(args, arrays: dict) -> dict:
         engine.flush_l2()
         barrier()
         engine.timer_start()
-        replay.run()
+        device_step()
         dev_ms.append(engine.timer_stop())
         barrier()
     gpu_launches = engine.launch_count - launches_before
@@ -586,6 +460,7 @@ def gpu_line(args, arrays: dict) -> dict:
         barrier()
     h2d1, d2h1 = engine.io_bytes()
     clocks = sampler.stop()
+    resident.close()
 
     value_s = statistics.mean(dev_ms) / 1e3
     e2e_value = statistics.mean(e2e_s)
@@ -620,7 +495,7 @@ def gpu_line(args, arrays: dict) -> dict:
             roofline["traffic_detail"] = captured
     roofline_rows = None
     if rows["launches"] and rows["ms"] > 0:
-        visits = sum(v for (t, _), v in zip(mine, replay.pair_visits, strict=True) if t.n >= PROFILE_MIN_N) * args.steps
+        visits = rows["units"]
         roofline_rows = {
             "kernel": "pcg_rows_kernel (leaf-pair LCA weighting -> W rows, adjacency bits, degree), n >= 4096",
             "bound": "shared-memory / issue (not HBM): ordered leaf-pair visits per second",
@@ -636,15 +511,15 @@ def gpu_line(args, arrays: dict) -> dict:
         "config": {
             "workload": describe(args.workload),
             "l2": "flushed between timed steps (256 MB write); the top-level W (0.8 GB) exceeds L2 by itself",
-            "value_is": "every recursion node of this rank's share of the job replayed from leaf tours resident in "
-                        "HBM, wave by wave as the native driver issues them: per wave the nodes > 4096 taxa one by one, "
-                        "the nodes of 65..4096 taxa as one batch (one launch per stage), the nodes <= 64 taxa in one "
-                        "launch (CUDA events on one stream; max over ranks)",
+            "value_is": "the whole recursion from source trees already resident in HBM (scs_supertree_build_resident: tours, "
+                        "node splits and tree restriction on the device, wave by wave; per wave the nodes > 4096 taxa one "
+                        "by one, the nodes of 65..4096 taxa as one batch, the nodes <= 64 taxa in one launch); CUDA "
+                        "events around the build; max over ranks",
             "e2e_is": "scs_forest_create + scs_supertree_build over the C ABI from flat host arrays to the flat "
-                      "supertree (wall clock; native breadth-first recursion, per-wave H2D of tours and D2H of "
-                      "partitions; for N > 1 recursion nodes with >= --shard-min-n taxa are row-sharded over the "
-                      "GPUs (fused matvec + all-gather over NVLink peer windows), then the frontier is dealt out "
-                      "over the ranks and the outputs are all-gathered)",
+                      "supertree (wall clock: validation of the trees, H2D of the forest, the recursion as in value, D2H "
+                      "of partitions and bookkeeping; for N > 1 recursion nodes with >= --shard-min-n taxa are "
+                      "row-sharded over the GPUs (fused matvec + all-gather over NVLink peer windows), smaller "
+                      "sub-problems are dealt out over the ranks and the outputs are all-gathered)",
             "e2e_host_seconds": host_split,
             "e2e_step_seconds": [round(x, 4) for x in e2e_s],
             "host_threads_per_rank": host_threads,
@@ -685,7 +560,7 @@ def gpu_line(args, arrays: dict) -> dict:
             line["cpu_baseline"] = {
                 "value": detail["seconds"], "unit": "s", "cores": cpu_threads(), "kind": "port",
                 "sample": (
-                    f"LOWER BOUND -- one of the job's {job['recursion_nodes']} recursion nodes only: the top-level node of "
+                    f"LOWER BOUND -- one of the job's {job.get('recursion_nodes', '?')} recursion nodes only: the top-level node of "
                     f"{args.workload} on the CPU oracle port (C graph build {detail['pcg_s']:.1f} s, components "
                     f"{detail['components_s']:.1f} s, contraction + sklearn SpectralClustering on {detail['spectral_n']} "
                     f"vertices {detail['spectral_s']:.1f} s), measured; the whole job is measured by "
@@ -695,7 +570,6 @@ def gpu_line(args, arrays: dict) -> dict:
         out = ROOT / "gpurun_out"
         if out.is_dir():
             (out / f"workload_{args.workload}.json").write_text(json.dumps({args.workload: job}, indent=1) + "\n")
-    replay.close()
     if dist is not None:
         engine.synchronize()
         dist.barrier()  # nobody may unmap a window a peer is still using

@@ -331,6 +331,17 @@ int scs_supertree_build(scs_ctx *ctx, const scs_forest *forest, int weighting, i
  * other ranks' nodes past the prefix (parents >= prefix shift by the append offset). */
 int scs_supertree_build_sharded(scs_ctx *ctx, const scs_forest *forest, int weighting, int contract_edges,
                                 uint64_t seed, int record_nodes, int rank, int world, scs_supertree **out);
+/* The source trees uploaded once and kept in HBM between builds: scs_supertree_build does
+ * scs_device_forest_create + scs_supertree_build_resident + scs_device_forest_destroy; a caller that builds several
+ * supertrees from the same trees (other weights of the spectral step, a benchmark with inputs resident in HBM) keeps
+ * the device forest.  The weighting decides which per-node values are uploaded (branch: lengths, bootstrap:
+ * supports).  With world > 1 the build is the cooperative one (exchange windows must be connected). */
+typedef struct scs_device_forest scs_device_forest;
+int scs_device_forest_create(scs_ctx *ctx, const scs_forest *forest, int weighting, scs_device_forest **out);
+int scs_device_forest_destroy(scs_device_forest *forest);
+int64_t scs_device_forest_bytes(const scs_device_forest *forest);
+int scs_supertree_build_resident(scs_ctx *ctx, const scs_device_forest *forest, int contract_edges, uint64_t seed,
+                                 int record_nodes, int rank, int world, scs_supertree **out);
 int64_t scs_supertree_shared_prefix(const scs_supertree *tree);
 /* Recursion nodes (records [0, this)) processed before the frontier was dealt out: the same on every
  * rank, and the ones that are shared out over the GPUs when a shard group is connected. */

@@ -146,6 +146,10 @@ SIGNATURES: dict[str, tuple] = {
     "scs_supertree_num_nodes": (c_int64, [_P]),
     "scs_supertree_nodes": (c_int, [_P, _P, _P]),
     "scs_supertree_counters": (c_int, [_P, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64), POINTER(c_int64)]),
+    "scs_device_forest_create": (c_int, [_P, _P, c_int, POINTER(_P)]),
+    "scs_device_forest_destroy": (c_int, [_P]),
+    "scs_device_forest_bytes": (c_int64, [_P]),
+    "scs_supertree_build_resident": (c_int, [_P, _P, c_int, c_uint64, c_int, c_int, c_int, POINTER(_P)]),
     "scs_supertree_record_wave": (c_int, [_P, c_int64]),
     "scs_nodes_split_medium_dev": (c_int, [_P, c_int, _P, _P, _P, _P, c_int, c_int64, _P, _P, _P, _P, _P, _P, c_int, _P, _P, _P]),
     "scs_supertree_medium_info": (c_int, [_P, POINTER(c_int64), POINTER(c_int64), POINTER(ctypes.c_double)]),

@@ -21,6 +21,17 @@
 #include "driver.hpp"
 #include "forest.hpp"
 
+// Source trees uploaded once and kept on the device between builds (scs_device_forest_create): the arrays plus what the
+// recursion needs to know about them on the host.
+struct scs_device_forest {
+    scs::DevForest trees;
+    int weighting = 0;
+    int num_taxa = 0;
+    std::vector<int32_t> taxa;  // taxa present, ascending
+    int64_t first_tree_nodes = 0, pair_visits = 0, leaves = 0;
+    scs_ctx *owner = nullptr;
+};
+
 namespace scs {
 
 namespace {
@@ -65,13 +76,10 @@ class DeviceDriver {
         cudaStreamSynchronize(ctx_->stream);
     }
 
-    int run(const scs_forest *root) {
-        num_taxa_ = scs_forest_num_taxa(root);
+    int run(const scs_device_forest *root) {
+        num_taxa_ = root->num_taxa;
+        root_ = &root->trees;
         int rc;
-        {
-            Stopwatch sw(&out_.seconds[3]);
-            if ((rc = devforest_upload(ctx_, root, weighting_, &forest_[0]))) return rc;
-        }
         vertex_.assign(static_cast<size_t>(num_taxa_ > 0 ? num_taxa_ : 1), -1);
         owner_.assign(vertex_.size(), -1);
         present_.assign(vertex_.size(), 0);
@@ -82,19 +90,12 @@ class DeviceDriver {
         cooperative_ = world_ > 1 && sh.connected && sh.world == world_ && sh.rank == rank_;
         std::vector<Job> wave(1), next;
         wave[0].slot = add(-1, -1, cooperative_);
-        {
-            std::vector<uint8_t> seen(vertex_.size(), 0);
-            for (int32_t x : root->taxon)
-                if (x >= 0) seen[x] = 1;
-            for (int x = 0; x < num_taxa_; ++x)
-                if (seen[x]) wave[0].taxa.push_back(x);
-        }
-        const int T = root->num_trees();
-        wave[0].where.trees = T;
-        wave[0].where.first_tree_nodes = T > 0 ? root->node_offsets[1] - root->node_offsets[0] : 0;
-        wave[0].where.pair_visits = scs_forest_pair_visits(root);
-        wave[0].leaves = root->leaf_offsets.back();
-        cur_ = 0;
+        wave[0].taxa = root->taxa;
+        wave[0].where.trees = static_cast<int32_t>(root->trees.trees);
+        wave[0].where.first_tree_nodes = root->first_tree_nodes;
+        wave[0].where.pair_visits = root->pair_visits;
+        wave[0].leaves = root->leaves;
+        cur_ = -1;  // the first wave reads the resident forest; its children go to forest_[0]
         if (cooperative_) {
             load_.assign(static_cast<size_t>(world_), 0.0);
             const int n_root = static_cast<int>(wave[0].taxa.size());
@@ -182,8 +183,11 @@ class DeviceDriver {
         int32_t parts = 0, part_base = 0;
     };
 
+    const DevForest &current() const { return cur_ < 0 ? *root_ : forest_[cur_]; }
+    DevForest &other() { return forest_[cur_ < 0 ? 0 : 1 - cur_]; }
+
     int process_wave(std::vector<Job> &wave, std::vector<Job> &next) {
-        const DevForest &forest = forest_[cur_];
+        const DevForest &forest = current();
         int rc;
         // ---- what each sub-problem is (scs.py:96-106) -------------------------------------------------------------------
         std::vector<size_t> single, small, medium, large;
@@ -335,7 +339,7 @@ class DeviceDriver {
             total += nodes[i];
         }
         std::vector<int32_t> par(static_cast<size_t>(total) + 1), tax(static_cast<size_t>(total) + 1);
-        int rc = devforest_fetch_trees(ctx_, forest_[cur_], count, first.data(), nodes.data(), par.data(), tax.data());
+        int rc = devforest_fetch_trees(ctx_, current(), count, first.data(), nodes.data(), par.data(), tax.data());
         if (rc) return rc;
         int64_t at = 0;
         std::vector<int32_t> where;
@@ -353,7 +357,7 @@ class DeviceDriver {
 
     // ---- the three node paths, all on the wave's device-resident tours --------------------------------------------------
     int split_large(const Job &job, Split &s) {
-        const DevForest &forest = forest_[cur_];
+        const DevForest &forest = current();
         const int n = static_cast<int>(job.taxa.size());
         const int T = job.where.trees;
         int rc;
@@ -378,7 +382,7 @@ class DeviceDriver {
 
     int split_medium(scs_ctx *ctx, std::vector<Job> &wave, const std::vector<size_t> &medium, Split *splits,
                      std::vector<size_t> &reruns) {
-        const DevForest &forest = forest_[cur_];
+        const DevForest &forest = current();
         const int B = static_cast<int>(medium.size());
         std::vector<int32_t> node_n(B), tree_begin(B), tree_end(B);
         std::vector<int64_t> part_off(B);
@@ -407,7 +411,7 @@ class DeviceDriver {
     }
 
     int split_small(scs_ctx *ctx, std::vector<Job> &wave, const std::vector<size_t> &small, Split *splits) {
-        const DevForest &forest = forest_[cur_];
+        const DevForest &forest = current();
         const int B = static_cast<int>(small.size());
         std::vector<scs_small_node> desc(B);
         for (int b = 0; b < B; ++b) {
@@ -448,7 +452,7 @@ class DeviceDriver {
         const int J = static_cast<int>(wave.size());
         std::vector<int32_t> job_tree_begin(static_cast<size_t>(J) + 1, 0), job_parts(J, 0), job_part_base(J, 0);
         for (int j = 0; j < J; ++j) job_tree_begin[j] = wave[j].where.tree_begin;
-        job_tree_begin[J] = static_cast<int32_t>(forest_[cur_].trees);
+        job_tree_begin[J] = static_cast<int32_t>(current().trees);
         std::sort(splits.begin(), splits.end(), [](const Split &a, const Split &b) { return a.job < b.job; });
         struct Pending {
             int32_t parent_slot;
@@ -519,9 +523,9 @@ class DeviceDriver {
         const int new_jobs = static_cast<int>(pending.size());
         std::vector<DevJobInfo> info(static_cast<size_t>(new_jobs) + 1);
         if (new_jobs > 0) {
-            const int rc = devforest_restrict(ctx_, forest_[cur_], J, job_tree_begin.data(), job_parts.data(), job_part_base.data(),
+            const int rc = devforest_restrict(ctx_, current(), J, job_tree_begin.data(), job_parts.data(), job_part_base.data(),
                                               static_cast<int>(part_newjob.size()), part_newjob.data(), new_jobs, owner_.data(),
-                                              num_taxa_, &forest_[1 - cur_], info.data(), present_.data());
+                                              num_taxa_, &other(), info.data(), present_.data());
             if (rc) return rc;
         }
         // taxa of finished sub-problems keep no owner
@@ -532,7 +536,7 @@ class DeviceDriver {
             child.slot = pending_slot_[j];
             child.where = info[j];
             // jobs are laid out in order: the leaves of a job end where the next job's begin
-            child.leaves = (j + 1 < new_jobs ? info[j + 1].leaf_begin : forest_[1 - cur_].leaves) - info[j].leaf_begin;
+            child.leaves = (j + 1 < new_jobs ? info[j + 1].leaf_begin : other().leaves) - info[j].leaf_begin;
             // taxa of the component that are a tip of some kept tree; the others are attached as singleton children of
             // the parent (scs.py:168-171).  A child left without trees raises when its wave is processed.
             // (known to whoever restricted: to every rank only if the child stays shared)
@@ -545,7 +549,7 @@ class DeviceDriver {
             next.push_back(std::move(child));
         }
         pending_slot_.clear();
-        cur_ = 1 - cur_;
+        cur_ = cur_ < 0 ? 0 : 1 - cur_;
         return SCS_OK;
     }
 
@@ -565,8 +569,9 @@ class DeviceDriver {
     std::vector<scs_supertree::Record> sh_records_;
     scs_supertree &out_;
     int num_taxa_ = 0;
-    DevForest forest_[2];
-    int cur_ = 0;
+    const DevForest *root_ = nullptr;  // the resident source trees (read-only): the forest of the first wave
+    DevForest forest_[2];              // the forests of the later waves, written alternately
+    int cur_ = -1;
     DevTours tours_;
     GrowBuf vertex_dev_, offsets_rel_, part_dev_, flags_dev_;
     cudaEvent_t tours_ready_ = nullptr;
@@ -576,10 +581,61 @@ class DeviceDriver {
 
 }  // namespace
 
-int run_device_driver(scs_ctx *ctx, const scs_forest *forest, int weighting, int contract_edges, uint64_t seed, bool record,
-                      int rank, int world, scs_supertree *out) {
-    DeviceDriver driver(ctx, weighting, contract_edges, seed, record, rank, world, out);
+int run_device_driver(scs_ctx *ctx, const scs_device_forest *forest, int contract_edges, uint64_t seed, bool record, int rank,
+                      int world, scs_supertree *out) {
+    DeviceDriver driver(ctx, forest->weighting, contract_edges, seed, record, rank, world, out);
     return driver.run(forest);
 }
 
 }  // namespace scs
+
+using namespace scs;
+
+extern "C" {
+
+int scs_device_forest_create(scs_ctx *ctx, const scs_forest *forest, int weighting, scs_device_forest **out) {
+    if (!ctx || !forest || !out || weighting < 0 || weighting > 3) return SCS_ERR_INVALID;
+    *out = nullptr;
+    cudaSetDevice(ctx->device);
+    scs_device_forest *d = new scs_device_forest();
+    d->weighting = weighting;
+    d->num_taxa = scs_forest_num_taxa(forest);
+    d->owner = ctx;
+    const int rc = devforest_upload(ctx, forest, weighting, &d->trees);
+    if (rc) {
+        d->trees.free_all(ctx);
+        delete d;
+        return rc;
+    }
+    std::vector<uint8_t> seen(static_cast<size_t>(d->num_taxa > 0 ? d->num_taxa : 1), 0);
+    for (int32_t x : forest->taxon)
+        if (x >= 0) seen[x] = 1;
+    for (int x = 0; x < d->num_taxa; ++x)
+        if (seen[x]) d->taxa.push_back(x);
+    d->first_tree_nodes = forest->num_trees() > 0 ? forest->node_offsets[1] - forest->node_offsets[0] : 0;
+    d->pair_visits = scs_forest_pair_visits(forest);
+    d->leaves = forest->leaf_offsets.back();
+    *out = d;
+    return SCS_OK;
+}
+
+int scs_device_forest_destroy(scs_device_forest *forest) {
+    if (!forest) return SCS_OK;
+    if (forest->owner) {
+        cudaSetDevice(forest->owner->device);
+        forest->trees.free_all(forest->owner);
+        cudaStreamSynchronize(forest->owner->stream);
+    }
+    delete forest;
+    return SCS_OK;
+}
+
+int64_t scs_device_forest_bytes(const scs_device_forest *forest) {
+    if (!forest) return 0;
+    const DevForest &f = forest->trees;
+    return static_cast<int64_t>(2 * (f.trees + 1) * sizeof(int64_t) + f.nodes * 3 * sizeof(int32_t) +
+                                (f.has_length ? f.nodes * sizeof(double) : 0) + (f.has_support ? f.nodes * sizeof(double) : 0) +
+                                f.trees * (sizeof(double) + sizeof(int32_t)));
+}
+
+}  // extern "C"

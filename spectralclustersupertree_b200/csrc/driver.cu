@@ -968,12 +968,28 @@ int scs_supertree_build_sharded(scs_ctx *ctx, const scs_forest *forest, int weig
     const ShardState &sh = ctx->shard;
     const bool cooperative = world > 1 && sh.connected && sh.world == world && sh.rank == rank;
     if (ctx->device_forest && (world == 1 || cooperative)) {
-        // the source trees stay on the device for the whole recursion (devdriver.cu)
-        rc = run_device_driver(ctx, forest, weighting, contract_edges, seed, record_nodes != 0, rank, world, result.get());
+        // the source trees go to the device once and stay there for the whole recursion (devdriver.cu)
+        scs_device_forest *resident = nullptr;
+        if ((rc = scs_device_forest_create(ctx, forest, weighting, &resident))) return rc;
+        rc = run_device_driver(ctx, resident, contract_edges, seed, record_nodes != 0, rank, world, result.get());
+        scs_device_forest_destroy(resident);
     } else {
         Driver driver(ctx, weighting, contract_edges, seed, record_nodes != 0, rank, world, result.get());
         rc = driver.run(forest);
     }
+    if (rc) return rc;
+    if (world > 1 && result->shared_prefix == 0) result->shared_prefix = static_cast<int64_t>(result->parent.size());
+    *out = result.release();
+    return SCS_OK;
+}
+
+int scs_supertree_build_resident(scs_ctx *ctx, const scs_device_forest *forest, int contract_edges, uint64_t seed,
+                                 int record_nodes, int rank, int world, scs_supertree **out) {
+    if (!ctx || !forest || !out || world < 1 || rank < 0 || rank >= world) return SCS_ERR_INVALID;
+    *out = nullptr;
+    cudaSetDevice(ctx->device);
+    std::unique_ptr<scs_supertree> result(new scs_supertree());
+    const int rc = run_device_driver(ctx, forest, contract_edges, seed, record_nodes != 0, rank, world, result.get());
     if (rc) return rc;
     if (world > 1 && result->shared_prefix == 0) result->shared_prefix = static_cast<int64_t>(result->parent.size());
     *out = result.release();

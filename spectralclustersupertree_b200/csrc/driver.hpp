@@ -27,6 +27,7 @@ struct scs_supertree {
 };
 
 struct scs_forest;
+struct scs_device_forest;
 
 namespace scs {
 
@@ -34,7 +35,7 @@ namespace scs {
 // device, a few small host round trips per wave for the bookkeeping of the output tree.  One GPU, or rank `rank` of
 // `world` in a cooperative build (exchange windows connected: large nodes row-sharded over the GPUs, smaller
 // sub-problems dealt out over the ranks).
-int run_device_driver(scs_ctx *ctx, const scs_forest *forest, int weighting, int contract_edges, uint64_t seed, bool record,
-                      int rank, int world, scs_supertree *out);
+int run_device_driver(scs_ctx *ctx, const scs_device_forest *forest, int contract_edges, uint64_t seed, bool record, int rank,
+                      int world, scs_supertree *out);
 
 }  // namespace scs

@@ -208,6 +208,33 @@ class Engine:
             msg = "There must be at least one tree to make a supertree."
             raise ValueError(msg)
         _check(status, self._ctx)
+        return self._collect_supertree(handle, record)
+
+    def device_forest(self, forest: "Forest", weighting: str) -> "DeviceForest":
+        """``scs_device_forest_create``: the source trees uploaded once, to be kept in HBM between builds."""
+        handle = ctypes.c_void_p()
+        _check(self._lib.scs_device_forest_create(self._ctx, forest.handle, WEIGHTINGS.index(weighting),
+                                                  ctypes.byref(handle)), self._ctx)  # fmt: skip
+        return DeviceForest(handle, weighting)
+
+    def supertree_build_resident(self, resident: "DeviceForest", contract_edges: bool = True, seed: int = 0,
+                                 record: bool = False, rank: int = 0, world: int = 1) -> dict:
+        """``scs_supertree_build_resident``: the build of ``supertree_build`` from trees already in HBM."""
+        handle = ctypes.c_void_p()
+        status = self._lib.scs_supertree_build_resident(
+            self._ctx, resident.handle, int(bool(contract_edges)), seed & 0xFFFFFFFFFFFFFFFF, int(bool(record)), rank,
+            world, ctypes.byref(handle),
+        )  # fmt: skip
+        if status == _lib.SCS_ERR_INPUT and resident.weighting == "bootstrap":
+            msg = "unsupported operand type(s) for *: 'NoneType' and 'float'"
+            raise TypeError(msg)
+        if status == _lib.SCS_ERR_EMPTY:
+            msg = "There must be at least one tree to make a supertree."
+            raise ValueError(msg)
+        _check(status, self._ctx)
+        return self._collect_supertree(handle, record)
+
+    def _collect_supertree(self, handle, record: bool) -> dict:
         try:
             count = self._lib.scs_supertree_num_nodes(handle)
             parent = np.empty(count, dtype=np.int32)
@@ -534,6 +561,24 @@ def unpack_bits(bits: np.ndarray, n: int) -> np.ndarray:
     """Bit matrix (n x words uint32, bit b of word j = column 32 j + b) -> boolean n x n."""
     as_bytes = bits.view(np.uint8).reshape(bits.shape[0], -1)
     return np.unpackbits(as_bytes, axis=1, bitorder="little")[:, :n].astype(bool)
+
+
+class DeviceForest:
+    """Source trees resident on the device (owner of one ``scs_device_forest``)."""
+
+    def __init__(self, handle, weighting: str) -> None:
+        self._lib = _lib.load()
+        self.handle = handle
+        self.weighting = weighting
+
+    @property
+    def nbytes(self) -> int:
+        return int(self._lib.scs_device_forest_bytes(self.handle))
+
+    def close(self) -> None:
+        if self.handle:
+            self._lib.scs_device_forest_destroy(self.handle)
+            self.handle = None
 
 
 class Forest:
