@@ -148,6 +148,15 @@ int scs_pcg_build_dev(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf
                       int32_t *occ_dev, uint32_t *adj_bits_dev, uint32_t *max_bits_dev,
                       double *degree_dev);
 
+/* The same for rows [row0, row1) only: W_rows_dev holds (row1 - row0) x n doubles (row a at (a - row0) * n); the bit
+ * matrices and degree keep their full size and are written for those rows; occ is complete.  This is the unit of
+ * the row-sharded multi-GPU build (every row is its own tree-ordered sum: no reduction over ranks). */
+int scs_pcg_build_rows_dev(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offsets_dev,
+                           const int32_t *leaf_taxon_dev, const int32_t *adj_depth_dev, const double *adj_val_dev,
+                           const int32_t *root_depth_dev, const double *tree_weight_dev, int row0, int row1,
+                           double *W_rows_dev, int32_t *occ_dev, uint32_t *adj_bits_dev, uint32_t *max_bits_dev,
+                           double *degree_dev);
+
 /* ---- connected components: replaces _get_graph_components (scs.py:458-492) ---------------- *
  * label[v] = smallest vertex id of v's component; *n_components_host receives the count. */
 int scs_components_dev(scs_ctx *ctx, int n, const uint32_t *bits_dev, int32_t *label_dev,

@@ -89,6 +89,7 @@ SIGNATURES: dict[str, tuple] = {
     "scs_ctx_profile_read": (c_int, [_P, c_int, POINTER(c_int64), POINTER(c_double), POINTER(c_double), POINTER(c_double)]),
     "scs_bit_words": (c_int, [c_int]),
     "scs_pcg_build_dev": (c_int, [_P, c_int, c_int, c_int64] + [_P] * 12),
+    "scs_pcg_build_rows_dev": (c_int, [_P, c_int, c_int, c_int64, _P, _P, _P, _P, _P, _P, c_int, c_int, _P, _P, _P, _P, _P]),
     "scs_components_dev": (c_int, [_P, c_int, _P, _P, POINTER(c_int32)]),
     "scs_contract_dev": (c_int, [_P, c_int, _P, _P, _P, _P, POINTER(c_int32), _P, _P]),
     "scs_spectral_bipartition_dev": (c_int, [_P, c_int, _P, _P, c_uint64, _P, POINTER(NodeStats)]),

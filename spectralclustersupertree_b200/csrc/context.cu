@@ -550,6 +550,20 @@ int scs_pcg_build_dev(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf
                      tree_weight_dev, W_dev, C_dev, occ_dev, adj_bits_dev, max_bits_dev, degree_dev);
 }
 
+int scs_pcg_build_rows_dev(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offsets_dev,
+                           const int32_t *leaf_taxon_dev, const int32_t *adj_depth_dev, const double *adj_val_dev,
+                           const int32_t *root_depth_dev, const double *tree_weight_dev, int row0, int row1,
+                           double *W_rows_dev, int32_t *occ_dev, uint32_t *adj_bits_dev, uint32_t *max_bits_dev,
+                           double *degree_dev) {
+    if (!ctx) return SCS_ERR_INVALID;
+    DeviceGuard guard(ctx->device);
+    RowBlock rows;
+    rows.row0 = row0;
+    rows.row1 = row1;
+    return pcg_build(ctx, n, T, L, leaf_offsets_dev, leaf_taxon_dev, adj_depth_dev, adj_val_dev, root_depth_dev,
+                     tree_weight_dev, W_rows_dev, nullptr, occ_dev, adj_bits_dev, max_bits_dev, degree_dev, rows);
+}
+
 int scs_components_dev(scs_ctx *ctx, int n, const uint32_t *bits_dev, int32_t *label_dev,
                        int32_t *n_components_host) {
     if (!ctx) return SCS_ERR_INVALID;
