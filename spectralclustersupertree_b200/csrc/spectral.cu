@@ -320,6 +320,72 @@ two_means_1d(int m, int P, const double *__restrict__ y, const double *__restric
     specdev::two_means_1d_body<kShared>(m, P, y, isd, u, sorted_g, side, result);
 }
 
+template <int kStage>
+__global__ void __launch_bounds__(kOneCta)
+two_means_staged(int m, int P, const double *__restrict__ y, const double *__restrict__ isd, double *__restrict__ u,
+                 double *__restrict__ sorted_g, int32_t *__restrict__ side, double *__restrict__ result) {
+    specdev::two_means_1d_body<false, kStage>(m, P, y, isd, u, sorted_g, side, result);
+}
+
+// ---- sort of more keys than one CTA's shared memory holds: bitonic network over many CTAs ----------------------------
+// Tiles of kSortTile keys are sorted / merged in shared memory (every compare distance below the tile size); the
+// larger distances are one launch each over all pairs.  Ascending; P is a power of two >= 2 * kSortTile.
+constexpr int kSortTile = 4096;
+
+// all stages k = 2 .. kSortTile of the network on one tile (first = 1), or the distances jmax .. 1 of stage k
+__global__ void __launch_bounds__(1024)
+sort_tile(double *__restrict__ keys, int first, int k_global, int jmax) {
+    __shared__ double tile[kSortTile];
+    const int base = blockIdx.x * kSortTile, tid = threadIdx.x;
+    for (int i = tid; i < kSortTile; i += 1024) tile[i] = keys[base + i];
+    __syncthreads();
+    for (int k = first ? 2 : k_global; k <= (first ? kSortTile : k_global); k <<= 1) {
+        for (int jj = first ? k >> 1 : jmax; jj > 0; jj >>= 1) {
+            for (int i = tid; i < kSortTile; i += 1024) {
+                const int partner = i ^ jj;
+                if (partner > i) {
+                    const double x0 = tile[i], x1 = tile[partner];
+                    const bool up = ((base + i) & k) == 0;
+                    if ((x0 > x1) == up) {
+                        tile[i] = x1;
+                        tile[partner] = x0;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = tid; i < kSortTile; i += 1024) keys[base + i] = tile[i];
+}
+
+// one compare distance j >= kSortTile of stage k over the whole array
+__global__ void sort_far(double *__restrict__ keys, int P, int k, int j) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;  // pair index
+    if (t >= P / 2) return;
+    const int i = ((t / j) * 2 * j) + (t % j);  // the lower element of the pair
+    const int partner = i + j;
+    const double x0 = keys[i], x1 = keys[partner];
+    const bool up = (i & k) == 0;
+    if ((x0 > x1) == up) {
+        keys[i] = x1;
+        keys[partner] = x0;
+    }
+}
+
+int sort_keys(scs_ctx *ctx, double *keys, int P) {
+    sort_tile<<<P / kSortTile, 1024, 0, ctx->stream>>>(keys, 1, 0, 0);
+    SCS_LAUNCHED(ctx, "sort_tile");
+    for (int k = 2 * kSortTile; k <= P; k <<= 1) {
+        for (int j = k >> 1; j >= kSortTile; j >>= 1) {
+            sort_far<<<ceil_div(P / 2, 256), 256, 0, ctx->stream>>>(keys, P, k, j);
+            SCS_LAUNCHED(ctx, "sort_far");
+        }
+        sort_tile<<<P / kSortTile, 1024, 0, ctx->stream>>>(keys, 0, k, kSortTile >> 1);
+        SCS_LAUNCHED(ctx, "sort_tile");
+    }
+    return SCS_OK;
+}
+
 __global__ void trivial_pair(int32_t *side) {
     side[0] = 0;
     side[1] = 1;
@@ -572,7 +638,11 @@ int spectral_bipartition(scs_ctx *ctx, int m, const double *W, const double *deg
         }
         kernel<<<1, kOneCta, smem, ctx->stream>>>(m, P, yvec, b.isd, embed, sorted, side, b.ritz + 12);
     } else {
-        two_means_1d<false><<<1, kOneCta, 0, ctx->stream>>>(m, P, yvec, b.isd, embed, sorted, side, b.ritz + 12);
+        // more keys than one CTA sorts in shared memory: embedding and keys, a sort over many CTAs, then the rest
+        two_means_staged<1><<<1, kOneCta, 0, ctx->stream>>>(m, P, yvec, b.isd, embed, sorted, side, b.ritz + 12);
+        SCS_LAUNCHED(ctx, "two_means_staged");
+        if ((rc = sort_keys(ctx, sorted, P))) return rc;
+        two_means_staged<2><<<1, kOneCta, 0, ctx->stream>>>(m, P, yvec, b.isd, embed, sorted, side, b.ritz + 12);
     }
     SCS_LAUNCHED(ctx, "two_means_1d");
     SCS_CUDA(ctx, cudaMemcpyAsync(pin + 12, b.ritz + 12, 6 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

@@ -383,7 +383,9 @@ __device__ __forceinline__ void true_residual_body(int m, const double *__restri
     }
 }
 
-template <bool kShared>
+// kStage: 0 everything in this CTA; 1 only the sign, u and the unsorted keys (sorted_g), for a sort by many CTAs
+// (spectral.cu: sort_keys); 2 the keys in sorted_g are already sorted: everything after the sort.
+template <bool kShared, int kStage = 0>
 __device__ __forceinline__ void two_means_1d_body(int m, int P, const double *__restrict__ y, const double *__restrict__ isd, double *__restrict__ u,
              double *__restrict__ sorted_g, int32_t *__restrict__ side, double *__restrict__ result) {
     extern __shared__ double sort_s[];
@@ -394,7 +396,8 @@ __device__ __forceinline__ void two_means_1d_body(int m, int P, const double *__
     __shared__ int ibcast;
     double *keys = kShared ? sort_s : sorted_g;
     const int tid = threadIdx.x, nthr = blockDim.x;
-
+    double total = 0.0;
+    if (kStage != 2) {
     // sign: entry of largest magnitude (smallest index on ties) must be positive
     double amax = -1.0;
     int imax = 0x7fffffff;
@@ -420,7 +423,6 @@ __device__ __forceinline__ void two_means_1d_body(int m, int P, const double *__
     const int arg = ibcast < m ? ibcast : 0;
     const double sign = y[arg] * isd[arg] < 0.0 ? -1.0 : 1.0;
 
-    double total = 0.0;
     for (int i = tid; i < P; i += nthr) {
         double v = INFINITY;
         if (i < m) {
@@ -430,12 +432,17 @@ __device__ __forceinline__ void two_means_1d_body(int m, int P, const double *__
         }
         keys[i] = v;
     }
+    if (kStage == 1) return;
+    } else {
+        // the same partial sums in the same order as the stage that wrote u
+        for (int i = tid; i < m; i += nthr) total += u[i];
+    }
     total = block_sum(total, scratch);
     const double mean = total / m;
     __syncthreads();
 
     // bitonic sort, ascending
-    for (int k = 2; k <= P; k <<= 1) {
+    for (int k = 2; kStage == 0 && k <= P; k <<= 1) {
         for (int jj = k >> 1; jj > 0; jj >>= 1) {
             for (int i = tid; i < P; i += nthr) {
                 const int partner = i ^ jj;
