@@ -373,7 +373,7 @@ class DeviceDriver {
         rc = node_split(ctx_, n, T, L, offsets_rel_.as<int64_t>(), tours_.leaf_taxon.as<int32_t>() + job.where.leaf_begin,
                         tours_.adj_depth.as<int32_t>() + job.where.leaf_begin, tours_.adj_val.as<double>() + job.where.leaf_begin,
                         tours_.root_depth.as<int32_t>() + job.where.tree_begin, forest.weight.as<double>() + job.where.tree_begin,
-                        contract_, seed_ + static_cast<uint64_t>(job.slot), part_dev_.as<int32_t>() + s.part_at, nullptr,
+                        contract_, node_seed(seed_, job.taxa[0], job.taxa.size()), part_dev_.as<int32_t>() + s.part_at, nullptr,
                         &s.stats);
         ctx_->pending_units = 0.0;
         ctx_->shard.engaged = false;
@@ -393,7 +393,7 @@ class DeviceDriver {
             tree_begin[b] = job.where.tree_begin;
             tree_end[b] = job.where.tree_begin + job.where.trees;
             part_off[b] = splits[b].part_at;
-            seeds[b] = seed_ + static_cast<uint64_t>(job.slot);
+            seeds[b] = node_seed(seed_, job.taxa[0], job.taxa.size());
         }
         std::vector<scs_node_stats> stats(B);
         std::vector<uint8_t> rerun(B, 0);

@@ -506,10 +506,9 @@ class Driver {
                           buf.root.data(), buf.wgt.data());
         if (rc) return rc;
         res.part.resize(n);
-        // the seed only picks the Lanczos start vector; tie it to the output slot so that it does not
-        // depend on the order in which concurrent workers finish
+        // the seed only picks the Lanczos start vector; it is a function of the node's taxa (driver.hpp)
         return scs_node_split_host(ctx, n, T, L, buf.off.data(), buf.tax.data(), buf.dep.data(), buf.val.data(),
-                                   buf.root.data(), buf.wgt.data(), contract_, seed_ + static_cast<uint64_t>(task.slot),
+                                   buf.root.data(), buf.wgt.data(), contract_, node_seed(seed_, taxa[0], taxa.size()),
                                    res.part.data(), &res.stats);
     }
 
@@ -629,7 +628,7 @@ class Driver {
             tree_begin[b + 1] = tree_begin[b] + scs_forest_num_trees(task.forest);
             leaf_base[b + 1] = leaf_base[b] + scs_forest_num_leaves(task.forest);
             part_off[b + 1] = part_off[b] + node_n[b];
-            seeds[b] = seed_ + static_cast<uint64_t>(task.slot);
+            seeds[b] = node_seed(seed_, task.taxa[0], task.taxa.size());
             visits += scs_forest_pair_visits(task.forest);
         }
         {

@@ -2,6 +2,7 @@
 // devdriver.cu keeps them on the device).
 #pragma once
 
+#include <cstddef>
 #include <cstdint>
 #include <vector>
 
@@ -30,6 +31,13 @@ struct scs_forest;
 struct scs_device_forest;
 
 namespace scs {
+
+// Seed of a recursion node's Lanczos start vector: a function of the node itself (its smallest taxon and its size),
+// not of the output slot it happens to fill, so that both drivers, every rank of a cooperative build and every
+// dealing of the sub-problems start the eigensolver of a given node from the same vector.
+inline uint64_t node_seed(uint64_t seed, int32_t first_taxon, size_t taxa) {
+    return seed + static_cast<uint64_t>(first_taxon) * 0x9E3779B97F4A7C15ull + static_cast<uint64_t>(taxa);
+}
 
 // The whole recursion with the source trees resident in HBM (devdriver.cu): restriction and tour flattening on the
 // device, a few small host round trips per wave for the bookkeeping of the output tree.  One GPU, or rank `rank` of
