@@ -587,12 +587,12 @@ def main() -> None:
     parser.add_argument("--impl", default="b200", choices=["b200", "reference"])
     parser.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     parser.add_argument("--no-cpu-baseline", action="store_true")
-    parser.add_argument("--reference-budget-s", type=float, default=600.0,
+    parser.add_argument("--reference-budget-s", type=float, default=240.0,
                         help="--impl reference: stop starting new full CPU runs after this many seconds "
                              "(one run is always timed)")
     parser.add_argument("--small-limit", type=int, default=-1,
                         help="tuning: nodes up to this many taxa take the one-CTA small-node path (default: the "
-                             "library's, 64); larger ones up to 4096 the batched medium path")
+                             "library's, 32; capacity 64); larger ones up to 4096 the batched medium path")
     parser.add_argument("--profile-step", action="store_true",
                         help="for ncu: no recording pass, no replay, no CPU baseline -- one warm-up job, then exactly "
                              "one scs_supertree_build bracketed by cudaProfilerStart/Stop "

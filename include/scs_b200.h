@@ -105,6 +105,10 @@ int scs_ctx_set_device_forest(scs_ctx *ctx, int on);
 /* Graph build: use the 8-byte {tour position, slot} bucket entries that nodes of 65 536 taxa or more need
  * at every size (on = 1; for tests of that path). */
 int scs_ctx_set_wide_entries(scs_ctx *ctx, int on);
+/* Graph build: W is symmetric bit for bit, so by default the CTA of row a visits only the pairs (a, b > a) and a
+ * second kernel mirrors the triangle (W, the bit matrices) and sums the rows.  on = 1 makes every row CTA visit all
+ * its pairs, as the row block of a node that is sharded over several GPUs always does (tests, A/B timing). */
+int scs_ctx_set_full_rows(scs_ctx *ctx, int on);
 /* Host wall clock spent per stage of the staged (> 64 vertices) node path since the last reset:
  * [0] enqueue graph build + components, [1] wait for them, [2] enqueue contraction, [3] spectral step,
  * [4] result copy, [5] Lanczos iterations within [3]. */

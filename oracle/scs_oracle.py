@@ -217,6 +217,16 @@ def graph_components(adjacency: np.ndarray) -> np.ndarray:
     "co-occurred at least once" (``C > 0``), not ``W > 0`` (ref: scs.py:479-490, 651-652).
     """
     n = adjacency.shape[0]
+    if n >= 256:
+        # same labels as the depth-first search below, from scipy's C implementation (the search itself, done in
+        # Python as the reference does it, costs 8 s at n = 10 000 -- a CPU baseline should not be charged for that)
+        from scipy.sparse import csr_matrix
+        from scipy.sparse.csgraph import connected_components
+
+        _, comp = connected_components(csr_matrix(adjacency), directed=False)
+        smallest = np.full(comp.max() + 1, n, dtype=np.int64)
+        np.minimum.at(smallest, comp, np.arange(n))
+        return smallest[comp].astype(np.int32)
     label = np.full(n, -1, dtype=np.int32)
     for start in range(n):
         if label[start] >= 0:

@@ -83,6 +83,7 @@ SIGNATURES: dict[str, tuple] = {
     "scs_ctx_set_medium_node_limit": (c_int, [_P, c_int]),
     "scs_ctx_set_device_forest": (c_int, [_P, c_int]),
     "scs_ctx_set_wide_entries": (c_int, [_P, c_int]),
+    "scs_ctx_set_full_rows": (c_int, [_P, c_int]),
     "scs_ctx_stage_seconds": (c_int, [_P, _P, c_int]),
     "scs_ctx_flush_l2": (c_int, [_P]),
     "scs_ctx_profile_enable": (c_int, [_P, c_int]),

@@ -45,7 +45,8 @@ enum Slot : int {
     SLOT_INV_SORTED,
     SLOT_DEGREE_PART,
     SLOT_LINKS,
-    SLOT_BUCKET_COUNT,
+    SLOT_BUCKET_COUNT,  // per-leaf staircases of the graph build (LeafStairs)
+    SLOT_START16,       // per leaf: where each warp's share of the tree starts in triangle mode
     SLOT_BUCKET_PTR,
     SLOT_ENTRIES,
     // components / contraction
@@ -124,6 +125,7 @@ struct MedNode {
     int32_t row_base;         // first row of the node in the batch's global row space
     int32_t tree_begin, tree_end;  // its trees in the batch's tree arrays
     int32_t jcap;             // Lanczos vectors its basis block can hold (min(n - 1, kMaxBasis))
+    int32_t blk_base, pad0;   // first 32-row block of the node among the batch's row blocks (sum of ceil(n / 32))
     int64_t w_off;            // first element of its n x n block in the W (and Wc) buffer
     int64_t bit_off;          // first word of its bit rows in the adjacency / max-graph buffers
     int64_t basis_off;        // first element of its (jcap + 3) x n basis block
@@ -172,14 +174,19 @@ struct scs_ctx {
     bool small_configured = false;
     bool batch_configured = false;
     bool tail_configured = false;
-    bool rows_configured[8] = {false, false, false, false, false, false, false, false};
+    bool rows_configured[16] = {};
+    bool mirror_configured = false;
     bool contract_configured = false;
     bool kmeans_configured = false;
     bool medium_configured = false;
     bool device_forest = true;  // scs_supertree_build on one GPU keeps the source trees on the device (devdriver.cu)
     int medium_limit = scs::kMediumMaxDefault;  // nodes up to this size (and above small_limit) go through the batched path
     bool wide_entries = false;  // graph build: 8-byte bucket entries even where 4 bytes would do (tests)
-    int small_limit = 64;  // nodes up to this size take the one-CTA path (0 disables it)
+    bool full_rows = false;     // graph build: every row CTA visits all its pairs (no triangle + mirror; tests, A/B timing)
+    // nodes up to this size take the one-CTA path (0 disables it; capacity kSmallNode = 64).  32 by measurement: one CTA
+    // needs ~3 ms for a 64-taxon node covered by hundreds of trees (tree loop + Jacobi sweeps), which made the small
+    // batch the critical path of every wave; up to 32 taxa it stays below 1 ms and the medium batch takes the rest
+    int small_limit = 32;
     double pending_units = 0.0;  // leaf-pair visits of the node being built (set by host entry points)
     cudaEvent_t timer_start = nullptr, timer_stop = nullptr;
     // shape of the node most recently processed by scs_node_split_host
@@ -284,7 +291,7 @@ int normalized_matvec(scs_ctx *ctx, int m, const double *W, const double *isd, c
 
 // Graph build of a batch of nodes in one set of launches (pcg.cu): R rows in all, T trees, L leaves; the tours are
 // concatenated with absolute leaf offsets; W / bit matrices are addressed through the node table.
-int pcg_build_batch(scs_ctx *ctx, int R, int T, int64_t L, int max_n, int max_trees, const MedNode *nodes_dev,
+int pcg_build_batch(scs_ctx *ctx, int B, int blocks, int R, int T, int64_t L, int max_n, int max_trees, const MedNode *nodes_dev,
                     const int32_t *tree_node, const int32_t *row_node, const int64_t *leaf_offsets,
                     const int32_t *leaf_taxon, const int32_t *adj_depth, const double *adj_val,
                     const int32_t *root_depth, const double *tree_weight, double *W, int32_t *occ, uint32_t *adj_bits,

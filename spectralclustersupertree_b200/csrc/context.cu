@@ -74,7 +74,11 @@ int ensure_workers(scs_ctx *ctx, int count) {
         worker->small_limit = ctx->small_limit;
         ctx->workers.push_back(worker);
     }
-    for (scs_ctx *worker : ctx->workers) worker->small_limit = ctx->small_limit;
+    for (scs_ctx *worker : ctx->workers) {
+        worker->small_limit = ctx->small_limit;
+        worker->full_rows = ctx->full_rows;
+        worker->wide_entries = ctx->wide_entries;
+    }
     return SCS_OK;
 }
 
@@ -312,6 +316,8 @@ int prewarm_node(scs_ctx *ctx, int n, int T, int64_t L) {
     if ((rc = reserve(ctx, SLOT_BASIS, 8 * basis, &p))) return rc;
     if ((rc = reserve(ctx, SLOT_LINKS, 16 * (nL + 1), &p))) return rc;
     if ((rc = reserve(ctx, SLOT_ENTRIES, 8 * (nL + 1), &p))) return rc;
+    if ((rc = reserve(ctx, SLOT_BUCKET_COUNT, 448 * (nL + 1), &p))) return rc;  // LeafStairs (pcg.cu)
+    if ((rc = reserve(ctx, SLOT_START16, 64 * (nL + 1), &p))) return rc;
     return SCS_OK;
 }
 }  // namespace scs
@@ -463,6 +469,13 @@ int scs_ctx_set_device_forest(scs_ctx *ctx, int on) {
 int scs_ctx_set_wide_entries(scs_ctx *ctx, int on) {
     if (!ctx) return SCS_ERR_INVALID;
     ctx->wide_entries = on != 0;
+    return SCS_OK;
+}
+
+int scs_ctx_set_full_rows(scs_ctx *ctx, int on) {
+    if (!ctx) return SCS_ERR_INVALID;
+    ctx->full_rows = on != 0;
+    for (scs_ctx *worker : ctx->workers) worker->full_rows = ctx->full_rows;
     return SCS_OK;
 }
 

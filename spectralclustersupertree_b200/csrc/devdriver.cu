@@ -15,6 +15,8 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <thread>
 
 #include "devforest.cuh"
@@ -109,12 +111,22 @@ class DeviceDriver {
             out_.wave_tasks.push_back(static_cast<int32_t>(wave.size()));
             out_.wave_max_n.push_back(max_n);
             const double before_gpu = out_.seconds[0] + out_.seconds[1] + out_.medium_seconds, before_restrict = out_.seconds[2];
+            const double before[6] = {out_.seconds[0], out_.seconds[1], out_.medium_seconds, out_.seconds[3], out_.seconds[2],
+                                      restrict_device_s_};
             const auto wave_start = std::chrono::steady_clock::now();
             next.clear();
             if ((rc = process_wave(wave, next))) return rc;
             out_.wave_seconds.push_back(out_.seconds[0] + out_.seconds[1] + out_.medium_seconds - before_gpu);
             out_.wave_seconds.push_back(out_.seconds[2] - before_restrict);
             out_.wave_seconds.push_back(std::chrono::duration<double>(std::chrono::steady_clock::now() - wave_start).count());
+            if (trace_)
+                std::fprintf(stderr,
+                             "[scs devdriver] wave %2d: tasks %5zu max_n %6d | large %7.3f small %7.3f medium %7.3f tours %6.3f "
+                             "children %6.3f (device restriction %6.3f) | wave %7.3f ms\n",
+                             static_cast<int>(out_.waves - 1), wave.size(), max_n, 1e3 * (out_.seconds[0] - before[0]),
+                             1e3 * (out_.seconds[1] - before[1]), 1e3 * (out_.medium_seconds - before[2]),
+                             1e3 * (out_.seconds[3] - before[3]), 1e3 * (out_.seconds[2] - before[4]),
+                             1e3 * (restrict_device_s_ - before[5]), 1e3 * out_.wave_seconds.back());
             wave.swap(next);
         }
         ctx_->shard.engaged = false;
@@ -523,6 +535,7 @@ class DeviceDriver {
         const int new_jobs = static_cast<int>(pending.size());
         std::vector<DevJobInfo> info(static_cast<size_t>(new_jobs) + 1);
         if (new_jobs > 0) {
+            Stopwatch sw_restrict(&restrict_device_s_);
             const int rc = devforest_restrict(ctx_, current(), J, job_tree_begin.data(), job_parts.data(), job_part_base.data(),
                                               static_cast<int>(part_newjob.size()), part_newjob.data(), new_jobs, owner_.data(),
                                               num_taxa_, &other(), info.data(), present_.data());
@@ -577,6 +590,8 @@ class DeviceDriver {
     cudaEvent_t tours_ready_ = nullptr;
     std::vector<int32_t> vertex_, owner_, part_, pending_slot_;
     std::vector<uint8_t> present_;
+    double restrict_device_s_ = 0.0;  // part of seconds[2] spent in devforest_restrict (launches + its round trips)
+    const bool trace_ = std::getenv("SCS_DRIVER_TRACE") != nullptr;
 };
 
 }  // namespace

@@ -566,7 +566,7 @@ int medium_batch(scs_ctx *ctx, int B, const int32_t *node_n, const int32_t *tree
         return fail(ctx, SCS_ERR_INVALID, "medium batch: bad argument");
     // ---- node table -------------------------------------------------------------------------------------------------
     std::vector<MedNode> nodes(static_cast<size_t>(B));
-    int64_t R = 0, w_total = 0, bit_total = 0, basis_total = 0;
+    int64_t R = 0, w_total = 0, bit_total = 0, basis_total = 0, blocks = 0;
     int max_n = 0, max_trees = 0;
     for (int b = 0; b < B; ++b) {
         const int n = node_n[b];
@@ -580,6 +580,9 @@ int medium_batch(scs_ctx *ctx, int B, const int32_t *node_n, const int32_t *tree
         nd.tree_begin = tree_begin[b];
         nd.tree_end = tree_end[b];
         nd.jcap = std::min(n - 1, kMaxBasis);
+        nd.blk_base = static_cast<int32_t>(blocks);
+        nd.pad0 = 0;
+        blocks += (n + 31) / 32;
         nd.w_off = w_total;
         nd.bit_off = bit_total;
         nd.basis_off = basis_total;
@@ -658,7 +661,7 @@ int medium_batch(scs_ctx *ctx, int B, const int32_t *node_n, const int32_t *tree
     SCS_LAUNCHED(ctx, "med_clear_state");
 
     // ---- graph build ---------------------------------------------------------------------------------------------------
-    if ((rc = pcg_build_batch(ctx, Ri, T, L, max_n, max_trees, nodes_dev, tree_node, row_node, leaf_offsets, leaf_taxon,
+    if ((rc = pcg_build_batch(ctx, B, static_cast<int>(blocks), Ri, T, L, max_n, max_trees, nodes_dev, tree_node, row_node, leaf_offsets, leaf_taxon,
                               adj_depth, adj_val, root_depth, tree_weight, mb.W, mb.occ, mb.adj_bits,
                               contract_edges ? mb.max_bits : nullptr, mb.degree, bad_dev)))
         return rc;

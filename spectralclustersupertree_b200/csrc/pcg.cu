@@ -277,36 +277,91 @@ __device__ __forceinline__ void bucket_of(const BucketShape &bs, int c, int &buc
     slot = lc >> bs.warps_log2;
 }
 
-__global__ void pcg_bucket_count(int n, int64_t L, BucketShape bs, const int32_t *__restrict__ leaf_taxon,
-                                 const int32_t *__restrict__ leaf_tree, int32_t *__restrict__ count) {
-    int64_t g = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-    if (g >= L) return;
-    const int c = leaf_taxon[g];
-    if (c < 0 || c >= n) return;  // flagged by pcg_index_leaves
-    int bucket, slot;
-    bucket_of(bs, c, bucket, slot);
-    atomicAdd(&count[static_cast<size_t>(leaf_tree[g]) * bs.buckets + bucket], 1);
-}
-
-// Entries of a bucket are in arbitrary order: the leaves of a tree are distinct columns, so the order in which a
-// warp adds one tree's terms cannot be observed.
+// One warp per tree.  The leaves of a tree are distinct columns, so "sorted by (bucket, slot)" is a rank in a bitmap:
+// bit  bucket * key_stride + slot  is set for every leaf (key_stride: the slots of a bucket rounded up to whole words, so
+// every bucket starts on a word boundary), an exclusive scan of the words' popcounts gives every set bit its rank, and
+// the rank is the leaf's place among the tree's entries.  The starts of the tree's buckets fall out of the same scan
+// (no counting pass, no scan over all cells).  Entries of a bucket ascend by slot, i.e. by column: a row CTA that
+// only wants the columns beyond its own (triangle mode) finds where they start with a binary search.
 template <typename EntryT>
-__global__ void pcg_bucket_fill(int n, int64_t L, BucketShape bs, const int64_t *__restrict__ leaf_offsets,
-                                const int32_t *__restrict__ leaf_taxon, const int32_t *__restrict__ leaf_tree,
-                                const int32_t *__restrict__ bucket_ptr, int32_t *__restrict__ cursor,
-                                EntryT *__restrict__ entries) {
-    int64_t g = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-    if (g >= L) return;
-    const int c = leaf_taxon[g];
-    if (c < 0 || c >= n) return;
-    const int t = leaf_tree[g];
-    int bucket, slot;
-    bucket_of(bs, c, bucket, slot);
-    const size_t cell = static_cast<size_t>(t) * bs.buckets + bucket;
-    const int at = bucket_ptr[cell] + atomicAdd(&cursor[cell], 1);
-    const uint32_t pos = static_cast<uint32_t>(g - leaf_offsets[t]);
-    if (sizeof(EntryT) == 4) entries[at] = static_cast<EntryT>((pos << 16) | static_cast<uint32_t>(slot));
-    else entries[at] = static_cast<EntryT>((static_cast<unsigned long long>(pos) << 32) | static_cast<uint32_t>(slot));
+__global__ void __launch_bounds__(256)
+pcg_bucket_sorted(int n, int T, BucketShape bs, int key_stride, int words, const int64_t *__restrict__ leaf_offsets,
+                  const int32_t *__restrict__ leaf_taxon, int32_t *__restrict__ bucket_ptr, EntryT *__restrict__ entries,
+                  int32_t *__restrict__ start16, int32_t *__restrict__ bad, BatchView batch) {
+    extern __shared__ uint32_t bucket_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (t >= T) return;  // whole warps leave; only warp-level synchronisation below
+    uint32_t *bm = bucket_smem + static_cast<size_t>(warp) * 2 * words;
+    int32_t *pre = reinterpret_cast<int32_t *>(bm + words);
+    const int64_t tb = leaf_offsets[t];
+    const int k = static_cast<int>(leaf_offsets[t + 1] - tb);
+    const size_t cell0 = static_cast<size_t>(t) * bs.buckets;
+    if (batch.nodes) {
+        const int b = batch.tree_node[t];
+        if (b < 0) {  // a tree of a sub-problem that is not in this batch: empty buckets
+            for (int j = lane; j < bs.buckets; j += 32) bucket_ptr[cell0 + j] = static_cast<int32_t>(tb);
+            if (t == T - 1 && lane == 0) bucket_ptr[cell0 + bs.buckets] = static_cast<int32_t>(tb);
+            return;
+        }
+        n = batch.nodes[b].n;
+    }
+    for (int w = lane; w < words; w += 32) bm[w] = 0u;
+    __syncwarp();
+    for (int i = lane; i < k; i += 32) {
+        const int c = leaf_taxon[tb + i];
+        if (c < 0 || c >= n) continue;  // flagged by pcg_index_leaves
+        int bucket, slot;
+        bucket_of(bs, c, bucket, slot);
+        const int key = bucket * key_stride + slot;
+        atomicOr(&bm[key >> 5], 1u << (key & 31));
+    }
+    __syncwarp();
+    int carry = 0;
+    for (int w0 = 0; w0 < words; w0 += 32) {
+        const int w = w0 + lane;
+        const int v = w < words ? __popc(bm[w]) : 0;
+        int inc = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, inc, off);
+            if (lane >= off) inc += o;
+        }
+        if (w < words) pre[w] = carry + inc - v;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    __syncwarp();
+    for (int i = lane; i < k; i += 32) {
+        const int c = leaf_taxon[tb + i];
+        if (c < 0 || c >= n) continue;
+        int bucket, slot;
+        bucket_of(bs, c, bucket, slot);
+        const int key = bucket * key_stride + slot;
+        const int rank = pre[key >> 5] + __popc(bm[key >> 5] & ((1u << (key & 31)) - 1u));
+        const uint32_t pos = static_cast<uint32_t>(i);
+        if (sizeof(EntryT) == 4) entries[tb + rank] = static_cast<EntryT>((pos << 16) | static_cast<uint32_t>(slot));
+        else entries[tb + rank] = static_cast<EntryT>((static_cast<unsigned long long>(pos) << 32) | static_cast<uint32_t>(slot));
+        if (start16) {
+            // triangle mode: for the row of this leaf's own taxon, where each warp's entries beyond the diagonal start
+            // in the chunk that holds the diagonal -- the rank of (bucket, first slot whose column exceeds c)
+            const int y = c / bs.cols_per_chunk;
+            const int la = c - y * bs.cols_per_chunk;
+            const int nw = 1 << bs.warps_log2;
+            for (int w = 0; w < nw; ++w) {
+                const int smin = la >= w ? ((la - w) >> bs.warps_log2) + 1 : 0;
+                const int key2 = ((y << bs.warps_log2) + w) * key_stride + smin;
+                start16[(tb + i) * nw + w] =
+                    static_cast<int32_t>(tb) + pre[key2 >> 5] + __popc(bm[key2 >> 5] & ((1u << (key2 & 31)) - 1u));
+            }
+        }
+    }
+    // a repeated or invalid taxon leaves the tail of the tree's entries unranked: harmless values there (the
+    // result is rejected anyway), and the flag
+    for (int i = carry + lane; i < k; i += 32) entries[tb + i] = EntryT(0);
+    if (carry != k && lane == 0) *bad = 1;
+    for (int j = lane; j < bs.buckets; j += 32)
+        bucket_ptr[cell0 + j] = static_cast<int32_t>(tb) + pre[(j * key_stride) >> 5];
+    if (t == T - 1 && lane == 0) bucket_ptr[cell0 + bs.buckets] = static_cast<int32_t>(tb) + k;
 }
 
 // ---- the row kernel -----------------------------------------------------------------------
@@ -334,8 +389,98 @@ struct __align__(16) TreeBatch {
     int32_t pivot[kTreeBatch][kSlots / 4];      // bound[4j + 3]: the first level of the segment search
     int32_t low[kTreeBatch], high[kTreeBatch];  // first / last boundary in use
     int32_t resume[kTreeBatch][2];              // chain entry to continue from, or kNone
-    uint32_t unfinished;                        // bit e: tree e has a chain to continue
 };
+
+// The staircase of one leaf -- what TreeBatch holds for a (row, tree) incidence -- depends only on the leaf, not on
+// the row CTA that uses it.  pcg_leaf_stairs walks both chains of EVERY leaf of the node once, two threads per leaf,
+// all leaves at the same time (the walk is a chain of dependent 16-byte reads: latency-bound inside a row CTA, where
+// 64 threads walked while 448 waited; throughput-bound here), and a row CTA copies the finished staircases of its 32
+// trees with coalesced loads.  Chains longer than kChain steps a side continue in the row kernel as before.
+struct __align__(16) LeafStairs {
+    double term[kSlots];
+    int32_t bound[kSlots];
+    int32_t pivot[kSlots / 4];
+    int32_t low, high, resume0, resume1;
+    int32_t leaves, position, tree, pad;  // leaves == 0: a tree with a repeated taxon (flagged), skipped
+};
+static_assert(sizeof(LeafStairs) == 448, "row CTAs copy a staircase as 28 int4");
+constexpr int kStairsInt4 = sizeof(LeafStairs) / 16;
+
+constexpr int kStairsLeaves = 64;  // leaves per CTA of pcg_leaf_stairs (two threads each)
+
+__global__ void __launch_bounds__(2 * kStairsLeaves)
+pcg_leaf_stairs(int n, int64_t L, const int64_t *__restrict__ leaf_offsets, const int32_t *__restrict__ leaf_tree,
+                const LinkEntry *__restrict__ links, const double *__restrict__ tree_weight,
+                LeafStairs *__restrict__ stairs, int32_t *__restrict__ bad, BatchView batch) {
+    __shared__ LeafStairs staged[kStairsLeaves];  // written piecemeal by the walkers, copied out in one piece
+    const int64_t g0 = static_cast<int64_t>(blockIdx.x) * kStairsLeaves;
+    const int64_t g = g0 + (threadIdx.x >> 1);
+    const int side = threadIdx.x & 1;
+    bool active = g < L;
+    int t = 0;
+    if (active) {
+        t = leaf_tree[g];
+        if (batch.nodes) {
+            const int b = batch.tree_node[t];
+            if (b < 0) active = false;  // a tree of a sub-problem that is not in this batch
+            else n = batch.nodes[b].n;
+        }
+    }
+    if (active) {
+        const int64_t base = leaf_offsets[t];
+        int leaves = static_cast<int>(leaf_offsets[t + 1] - base);
+        const int position = static_cast<int>(g - base);
+        LeafStairs &out = staged[threadIdx.x >> 1];
+        if (leaves > n) {  // more leaves than taxa: a taxon is repeated
+            *bad = 1;
+            leaves = 0;
+        }
+        const double weight = tree_weight[t];
+        const LinkEntry *lk = links + base;
+        int c = 0;
+        if (side == 1) {
+            out.leaves = leaves;
+            out.position = position;
+            out.tree = t;
+            out.pad = 0;
+            out.bound[kChain + 1] = position;
+            int i = (leaves >= 2 && position <= leaves - 2) ? position : kNone;
+            while (i >= 0 && c < kChain) {
+                const LinkEntry r = lk[i];
+                if (r.next_right == kRootLevel) { i = kNone; break; }
+                out.term[kChain + 1 + c] = __dmul_rn(r.val, weight);
+                out.bound[kChain + 2 + c] = r.next_right < 0 ? leaves - 1 : r.next_right;
+                ++c;
+                i = r.next_right;
+            }
+            out.high = kChain + 1 + c;
+            out.resume1 = i;
+            for (int k = kChain + 2 + c; k < kSlots; ++k) out.bound[k] = kFar;
+            for (int j = kSlots / 8; j < kSlots / 4; ++j) out.pivot[j] = out.bound[4 * j + 3];
+        } else {
+            out.bound[kChain] = position - 1;
+            int i = (leaves >= 2 && position >= 1 && position <= leaves - 1) ? position - 1 : kNone;
+            while (i >= 0 && c < kChain - 1) {  // boundary 0 stays a pad: the search starts from it
+                const LinkEntry r = lk[i];
+                if (r.next_left == kRootLevel) { i = kNone; break; }
+                out.term[kChain - 1 - c] = __dmul_rn(r.val, weight);
+                out.bound[kChain - 1 - c] = r.next_left;  // kNone == -1: the segment starts at the first leaf
+                ++c;
+                i = r.next_left;
+            }
+            out.low = kChain - c;
+            out.resume0 = i;
+            for (int k = kChain - c - 1; k >= 0; --k) out.bound[k] = -kFar;
+            for (int j = 0; j < kSlots / 8; ++j) out.pivot[j] = out.bound[4 * j + 3];
+        }
+    }
+    __syncthreads();
+    const int64_t left = L - g0;
+    const int count = left < kStairsLeaves ? static_cast<int>(left) : kStairsLeaves;
+    const int4 *src = reinterpret_cast<const int4 *>(staged);
+    int4 *dst = reinterpret_cast<int4 *>(stairs + g0);
+    for (int k = threadIdx.x; k < count * kStairsInt4; k += 2 * kStairsLeaves) dst[k] = src[k];
+}
 
 // Walk one side of the chain of tree e (thread-serial: one dependent 16-byte read per ancestor).
 __device__ void walk_chain(TreeBatch &tb, int e, int side, bool first, const LinkEntry *__restrict__ links) {
@@ -439,15 +584,95 @@ __device__ __forceinline__ void visit_bucket(const TreeBatch &tb, int e, int ptr
     }
 }
 
+// One warp, trees [first, stop) of the batch at once.  A warp's share of a tree is short (a tree's leaves spread over
+// the 16 warps of every chunk: tens of entries), so going tree by tree exposes one global-memory latency per tree and
+// leaves most lanes idle.  Here the warp's shares of the trees are concatenated in tree order and taken 32 items at a
+// time, four such groups in flight: item j belongs to the tree found by a search over the running totals (held one per
+// lane), its entry is loaded, its segment looked up in that tree's staircase.  Two items of a group that hit the same
+// column come from different trees; they are applied one after the other in lane order = tree order, so every W entry
+// still receives its terms in tree input order, each with one rounded multiply and one rounded add.
+template <typename CountT, typename EntryT>
+__device__ __forceinline__ void visit_trees(const TreeBatch &tb, int first, int stop, int my_ptr, int my_end, int lane,
+                                            int slot0, const EntryT *__restrict__ entries, double *accW, CountT *accC) {
+    constexpr unsigned kAll = 0xffffffffu;
+    int cnt = 0;
+    if (lane >= first && lane < stop) {
+        cnt = my_end - my_ptr;
+        if (tb.low[lane] == kChain && tb.high[lane] == kChain + 1) cnt = 0;  // nothing but root-separated pairs
+    }
+    int inc = cnt;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int o = __shfl_up_sync(kAll, inc, off);
+        if (lane >= off) inc += o;
+    }
+    const int total = __shfl_sync(kAll, inc, 31);
+    const int base_of_mine = my_ptr - (inc - cnt);  // entry index of item j of tree `lane` = base_of_mine + j
+    constexpr int kDepth = 4;
+    for (int j0 = 0; j0 < total; j0 += 32 * kDepth) {
+        EntryT en[kDepth];
+        int tree[kDepth];
+#pragma unroll
+        for (int d = 0; d < kDepth; ++d) {
+            const int j = j0 + 32 * d + lane;
+            int e = 0;  // the first tree whose running total exceeds j
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                const int v = __shfl_sync(kAll, inc, e + step - 1);
+                if (v <= j) e += step;
+            }
+            e = j < total ? e : 0;  // (e <= 31 wherever j < total)
+            const int at = __shfl_sync(kAll, base_of_mine, e) + j;
+            tree[d] = e;
+            en[d] = j < total ? entries[at] : EntryT(0);
+        }
+#pragma unroll
+        for (int d = 0; d < kDepth; ++d) {
+            if (j0 + 32 * d >= total) break;  // warp-uniform
+            const int e = tree[d];
+            int q, slot;
+            unpack(en[d], q, slot);
+            const int4 pa = *reinterpret_cast<const int4 *>(&tb.pivot[e][0]);
+            const int4 pb = *reinterpret_cast<const int4 *>(&tb.pivot[e][4]);
+            const int blk = (pa.x < q) + (pa.y < q) + (pa.z < q) + (pa.w < q) + (pb.x < q) + (pb.y < q) + (pb.z < q);
+            const int4 b = reinterpret_cast<const int4 *>(tb.bound[e])[blk];
+            const int idx = 4 * blk - 1 + (b.x < q) + (b.y < q) + (b.z < q) + (b.w < q);  // bound[0] < q always
+            const bool hit = j0 + 32 * d + lane < total && idx >= tb.low[e] && idx < tb.high[e] && idx != kChain;
+            const double term = hit ? tb.term[e][idx] : 0.0;
+            // the items of one tree are distinct columns; the trees of the group one after the other, in order
+            const int e_first = __shfl_sync(kAll, e, 0), e_last = __reduce_max_sync(kAll, e);
+            if (e_first == e_last) {
+                if (hit) {
+                    accW[slot0 + slot] = __dadd_rn(accW[slot0 + slot], term);
+                    bump(accC, slot0 + slot);
+                }
+            } else {
+                for (int t = e_first; t <= e_last; ++t) {
+                    if (hit && e == t) {
+                        accW[slot0 + slot] = __dadd_rn(accW[slot0 + slot], term);
+                        bump(accC, slot0 + slot);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    }
+}
+
 // blockDim.x = 32 * W threads (W = 1 << bs.warps_log2); dynamic shared memory: W * stride accumulators.
-template <typename CountT, bool kWriteC, typename EntryT>
+// kTri: the CTA of row a accumulates only the columns beyond a (W is symmetric bit for bit: every pair is then
+// visited once instead of twice) and writes that part of the row and its mirror image; pcg_mirror_bits and
+// pcg_degree_rows complete the bit rows and sum the rows.  The entries of a bucket ascend by column, so each warp finds where its share of a
+// tree starts with a binary search (one lane per tree of the batch, while the first warps walk the chains).
+template <typename CountT, bool kWriteC, typename EntryT, bool kTri>
 __global__ void __launch_bounds__(kRowThreads, 2)
 pcg_rows_kernel(int n, int row0, int words_per_row, BucketShape bs, int stride,
                 const int64_t *__restrict__ leaf_offsets, const LinkEntry *__restrict__ links,
                 const double *__restrict__ tree_weight, const int32_t *__restrict__ leaf_tree,
                 const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ inv_sorted,
                 const int32_t *__restrict__ occ, const int32_t *__restrict__ bucket_ptr,
-                const EntryT *__restrict__ entries,
+                const EntryT *__restrict__ entries, const LeafStairs *__restrict__ stairs,
+                const int32_t *__restrict__ start16,
                 double *__restrict__ W, int32_t *__restrict__ C, uint32_t *__restrict__ adj_bits,
                 uint32_t *__restrict__ max_bits, double *__restrict__ degree_part, int32_t *__restrict__ bad,
                 BatchView view) {
@@ -464,13 +689,14 @@ pcg_rows_kernel(int n, int row0, int words_per_row, BucketShape bs, int stride,
     // its outputs go (occ, row_ptr, degree are indexed by the global row)
     const int degree_stride = n;  // rows of the (global) row space: degree_part is [chunk][row]
     int occ_base = 0;
+    int a_loc = a;  // the row's vertex id inside its node
     size_t w_row = static_cast<size_t>(blockIdx.x) * n;
     size_t bits_row = static_cast<size_t>(a) * words_per_row;
     if (view.nodes) {
         const MedNode &nd = view.nodes[view.row_node[a]];
         n = nd.n;
         occ_base = nd.row_base;
-        const int a_loc = a - nd.row_base;
+        a_loc = a - nd.row_base;
         w_row = static_cast<size_t>(nd.w_off) + static_cast<size_t>(a_loc) * n;
         bits_row = static_cast<size_t>(nd.bit_off) + static_cast<size_t>(a_loc) * nd.words;
     }
@@ -480,6 +706,13 @@ pcg_rows_kernel(int n, int row0, int words_per_row, BucketShape bs, int stride,
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int my_bucket = (blockIdx.y << bs.warps_log2) + warp;
     const int slot0 = warp * stride;  // the slots of this warp's columns start here
+    // triangle mode: the first slot of this warp whose column lies beyond the row's own (column = slot * W + warp)
+    int slot_min = 0;
+    if (kTri) {
+        if (a_loc >= col0 + ncols) return;  // the whole chunk lies at or before the diagonal: the mirror's part
+        const int la = a_loc - col0;
+        if (la >= warp) slot_min = ((la - warp) >> bs.warps_log2) + 1;
+    }
 
     for (int c = tid; c < slots_total; c += nthreads) {
         accW[c] = 0.0;
@@ -488,50 +721,60 @@ pcg_rows_kernel(int n, int row0, int words_per_row, BucketShape bs, int stride,
 
     const int ebase = row_ptr[a];
     const int cnt = row_ptr[a + 1] - ebase;
+    const bool diagonal_chunk = kTri && a_loc >= col0;  // this chunk holds the row's own column
+    const int4 *stairs4 = reinterpret_cast<const int4 *>(stairs);
     for (int e0 = 0; e0 < cnt; e0 += kTreeBatch) {
         const int batch = min(kTreeBatch, cnt - e0);
         __syncthreads();  // the previous batch (and the initialisation) is done with
-        if (tid < batch) {
-            const int g = inv_sorted[ebase + e0 + tid];
-            const int t = leaf_tree[g];
-            const int64_t base = leaf_offsets[t];
-            TreeHeader h;
-            h.base = base;
-            h.weight = tree_weight[t];
-            h.leaves = static_cast<int>(leaf_offsets[t + 1] - base);
-            if (h.leaves > n) {  // more leaves than taxa: a taxon is repeated
-                *bad = 1;
-                h.leaves = 0;
-            }
-            h.position = static_cast<int>(g - base);
-            h.tree = t;
-            h.pad = 0;
-            tb.header[tid] = h;
-        }
-        if (tid == 0) tb.unfinished = 0;
-        __syncthreads();
-        for (int w = tid; w < 2 * batch; w += nthreads) {
-            walk_chain(tb, w >> 1, w & 1, true, links);
-            if (tb.resume[w >> 1][w & 1] >= 0) atomicOr(&tb.unfinished, 1u << (w >> 1));
-        }
-        // lane e keeps where this warp's bucket of tree e starts and ends
+        // Lane e keeps where this warp's share of tree e starts and ends, and whether the tree's chains need further
+        // rounds.  Every warp reads this for itself: nothing here waits for another warp.
         int my_ptr = 0, my_end = 0;
+        bool my_open = false;
         if (lane < batch) {
-            const size_t cell = static_cast<size_t>(tb.header[lane].tree) * bs.buckets + my_bucket;
-            my_ptr = bucket_ptr[cell];
+            const int g = inv_sorted[ebase + e0 + lane];
+            const int4 shape = stairs4[static_cast<size_t>(g) * kStairsInt4 + 26];  // low, high, resume0, resume1
+            const int4 info = stairs4[static_cast<size_t>(g) * kStairsInt4 + 27];   // leaves, position, tree
+            const size_t cell = static_cast<size_t>(info.z) * bs.buckets + my_bucket;
             my_end = bucket_ptr[cell + 1];
-            if (tb.header[lane].leaves == 0) my_end = my_ptr;
+            // triangle mode, the chunk with the row's own column: the warp's entries beyond the diagonal start where
+            // pcg_bucket_sorted found them for this leaf; later chunks lie beyond the diagonal altogether
+            my_ptr = diagonal_chunk ? start16[static_cast<size_t>(g) * kWarps + warp] : bucket_ptr[cell];
+            if (info.x == 0) my_end = my_ptr;
+            my_open = shape.z >= 0 || shape.w >= 0;
+        }
+        const uint32_t unfinished = __ballot_sync(0xffffffffu, my_open);
+        // the finished staircases of the batch's trees (pcg_leaf_stairs): 28 int4 each, coalesced
+        for (int idx = tid; idx < batch * kStairsInt4; idx += nthreads) {
+            const int e = idx / kStairsInt4, k = idx - e * kStairsInt4;
+            const int g = inv_sorted[ebase + e0 + e];
+            const int4 v = stairs4[static_cast<size_t>(g) * kStairsInt4 + k];
+            if (k < 16) reinterpret_cast<int4 *>(tb.term[e])[k] = v;
+            else if (k < 24) reinterpret_cast<int4 *>(tb.bound[e])[k - 16] = v;
+            else if (k < 26) reinterpret_cast<int4 *>(tb.pivot[e])[k - 24] = v;
+            else if (k == 26) {
+                tb.low[e] = v.x;
+                tb.high[e] = v.y;
+                tb.resume[e][0] = v.z;
+                tb.resume[e][1] = v.w;
+            } else {
+                TreeHeader h;  // only the continuation rounds of an unfinished chain read it
+                h.leaves = v.x;
+                h.position = v.y;
+                h.tree = v.z;
+                h.pad = 0;
+                h.base = leaf_offsets[v.z];
+                h.weight = tree_weight[v.z];
+                tb.header[e] = h;
+            }
         }
         __syncthreads();
         // Every warp goes through the trees in input order on its own: no barrier between trees.  A tree whose
         // chain did not fit in kChain steps is continued round by round, CTA-wide, before the trees after it.
         int first = 0;
         while (first < batch) {
-            const uint32_t open = tb.unfinished >> first;
+            const uint32_t open = unfinished >> first;
             const int stop = open != 0 ? first + __ffs(open) : batch;
-            for (int e = first; e < stop; ++e)
-                visit_bucket(tb, e, __shfl_sync(0xffffffffu, my_ptr, e), __shfl_sync(0xffffffffu, my_end, e), lane,
-                             slot0, entries, accW, accC);
+            visit_trees(tb, first, stop, my_ptr, my_end, lane, slot0, entries, accW, accC);
             if (open != 0) {
                 const int eu = stop - 1;
                 const int ptr = __shfl_sync(0xffffffffu, my_ptr, eu), end = __shfl_sync(0xffffffffu, my_end, eu);
@@ -552,8 +795,12 @@ pcg_rows_kernel(int n, int row0, int words_per_row, BucketShape bs, int stride,
     auto slot_of = [&](int c) { return (c & wmask) * stride + (c >> bs.warps_log2); };
     const int occ_a = occ[a];
     double *Wrow = W + w_row + col0;
+    double *Wnode = W + (w_row - static_cast<size_t>(a_loc) * n);  // triangle mode: row 0 of the node's matrix
     for (int c = tid; c < ncols; c += nthreads) {
-        Wrow[c] = accW[slot_of(c)];
+        if (kTri && col0 + c < a_loc) continue;  // written, as its mirror image, by the CTA of that row
+        const double v = accW[slot_of(c)];
+        Wrow[c] = v;
+        if (kTri && col0 + c > a_loc) Wnode[static_cast<size_t>(col0 + c) * n + a_loc] = v;
         if (kWriteC) C[w_row + col0 + c] = static_cast<int32_t>(accC[slot_of(c)]);
     }
     const int word0 = col0 >> 5;
@@ -573,6 +820,7 @@ pcg_rows_kernel(int n, int row0, int words_per_row, BucketShape bs, int stride,
             if (max_bits != nullptr) max_bits[bits_row + word0 + j] = tb2;
         }
     }
+    if (kTri) return;  // the row is complete only when every row CTA is done: pcg_degree_rows sums it (in the same order)
     // row sum in a fixed order (the same for every CTA size): virtual thread v < kRowThreads sums columns
     // v, v + kRowThreads, ...; shuffle tree per virtual warp; then the virtual warps in order
     for (int vw = warp; vw < kWarps; vw += nwarps) {
@@ -599,16 +847,94 @@ __global__ void pcg_sum_degree_parts(int n, int row0, int row1, int nchunks, con
     degree[a] = s;
 }
 
-template <typename CountT, bool kWriteC, typename EntryT>
+// Triangle mode, second half.  The row kernel has written both triangles of W (every finished entry also to its
+// mirror position: a scattered 8-byte store per entry, which L2 merges with the stores of the neighbouring rows'
+// CTAs).  What is left: the bit matrices -- pcg_mirror_bits, one warp per 32 x 32 tile (I, J), I <= J, transposes the
+// tile with 32 ballots (the diagonal word keeps its upper bits) -- and the row sums -- pcg_degree_rows, one warp per
+// row, in exactly the order of the full-row kernel (virtual thread v < 512 takes columns v, v + 512, ... of a column
+// chunk; shuffle tree per virtual warp; the 16 virtual warps in order; the chunks in order), so W, the bits and the
+// degrees do not depend on the mode.
+constexpr int kMirrorWarps = 8;
+
+__global__ void __launch_bounds__(kMirrorWarps * 32)
+pcg_mirror_bits(int n, int words, int B, uint32_t *__restrict__ adj_bits, uint32_t *__restrict__ max_bits, BatchView view) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int J = blockIdx.x;
+    if (view.nodes) {
+        const int blk = blockIdx.x;
+        int lo = 0, hi = B;  // last node with blk_base <= blk
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (view.nodes[mid].blk_base <= blk) lo = mid; else hi = mid;
+        }
+        const MedNode &nd = view.nodes[lo];
+        J = blk - nd.blk_base;
+        n = nd.n;
+        words = nd.words;
+        adj_bits += nd.bit_off;
+        if (max_bits) max_bits += nd.bit_off;
+    }
+    const int I = blockIdx.y * kMirrorWarps + warp;
+    if (I > J) return;
+    const int srow = (I << 5) + lane, rowJ = (J << 5) + lane;
+    for (int which = 0; which < 2; ++which) {
+        uint32_t *bits = which == 0 ? adj_bits : max_bits;
+        if (!bits) continue;
+        const uint32_t mine = srow < n ? bits[static_cast<size_t>(srow) * words + J] : 0u;
+        uint32_t turned = 0u;
+#pragma unroll
+        for (int rp = 0; rp < 32; ++rp) {
+            const uint32_t b = __ballot_sync(0xffffffffu, (mine >> rp) & 1u);
+            if (lane == rp) turned = b;
+        }
+        if (rowJ < n) {
+            if (I < J) bits[static_cast<size_t>(rowJ) * words + I] = turned;
+            else bits[static_cast<size_t>(rowJ) * words + J] = mine | turned;  // srow == rowJ: its own upper bits
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kMirrorWarps * 32)
+pcg_degree_rows(int n, int R, int cols_per_chunk, const double *__restrict__ W, double *__restrict__ degree, BatchView view) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * kMirrorWarps + warp;  // of the (global) row space
+    if (row >= R) return;
+    const double *Wrow = W + static_cast<size_t>(row) * n;
+    if (view.nodes) {
+        const MedNode &nd = view.nodes[view.row_node[row]];
+        n = nd.n;
+        cols_per_chunk = n;
+        Wrow = W + nd.w_off + static_cast<size_t>(row - nd.row_base) * n;
+    }
+    const int nchunks = (n + cols_per_chunk - 1) / cols_per_chunk;
+    double total = 0.0;
+    for (int y = 0; y < nchunks; ++y) {
+        const int col0 = y * cols_per_chunk;
+        const int ncols = min(cols_per_chunk, n - col0);
+        double s = 0.0;
+        for (int vw = 0; vw < kWarps; ++vw) {
+            double part = 0.0;
+            for (int c = (vw << 5) + lane; c < ncols; c += kRowThreads) part += Wrow[col0 + c];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) part += __shfl_down_sync(0xffffffffu, part, off);
+            s += part;  // lane 0 holds the virtual warp's sum; the other lanes add along harmlessly
+        }
+        total = nchunks == 1 ? s : total + s;
+    }
+    if (lane == 0) degree[row] = total;
+}
+
+template <typename CountT, bool kWriteC, typename EntryT, bool kTri>
 int launch_rows(scs_ctx *ctx, int n, int row0, int nrows, int words, BucketShape bs, int stride, int nchunks, size_t smem,
                 const int64_t *leaf_offsets, const LinkEntry *links, const double *tree_weight,
                 const int32_t *leaf_tree, const int32_t *row_ptr, const int32_t *inv_sorted,
-                const int32_t *occ, const int32_t *bucket_ptr, const void *entries, double *W, int32_t *C,
+                const int32_t *occ, const int32_t *bucket_ptr, const void *entries, const LeafStairs *stairs,
+                const int32_t *start16, double *W, int32_t *C,
                 uint32_t *adj_bits, uint32_t *max_bits, double *degree_part, int32_t *bad, BatchView batch = BatchView()) {
-    auto kernel = pcg_rows_kernel<CountT, kWriteC, EntryT>;
+    auto kernel = pcg_rows_kernel<CountT, kWriteC, EntryT, kTri>;
     // always the same (maximal) opt-in size: contexts on other host threads launch this kernel concurrently
-    bool &configured =
-        ctx->rows_configured[(sizeof(CountT) == 2 ? 0 : 2) + (kWriteC ? 1 : 0) + (sizeof(EntryT) == 4 ? 0 : 4)];
+    bool &configured = ctx->rows_configured[(sizeof(CountT) == 2 ? 0 : 2) + (kWriteC ? 1 : 0) +
+                                            (sizeof(EntryT) == 4 ? 0 : 4) + (kTri ? 8 : 0)];
     if (!configured) {
         const size_t optin = ctx->smem_optin > 2 * kRowsStaticSmem ? ctx->smem_optin - kRowsStaticSmem : 32 * 1024;
         SCS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(optin)));
@@ -622,7 +948,7 @@ int launch_rows(scs_ctx *ctx, int n, int row0, int nrows, int words, BucketShape
     }
     kernel<<<grid, 32 << bs.warps_log2, smem, ctx->stream>>>(
         n, row0, words, bs, stride, leaf_offsets, links, tree_weight, leaf_tree, row_ptr, inv_sorted, occ, bucket_ptr,
-        static_cast<const EntryT *>(entries), W, C, adj_bits, max_bits, degree_part, bad, batch);
+        static_cast<const EntryT *>(entries), stairs, start16, W, C, adj_bits, max_bits, degree_part, bad, batch);
     if (n >= kProfileMinSize && !batch.nodes) profile_end(ctx);
     SCS_LAUNCHED(ctx, "pcg_rows_kernel");
     return SCS_OK;
@@ -704,6 +1030,49 @@ int exclusive_scan(scs_ctx *ctx, int n, const int32_t *in, int32_t *out) {
     SCS_LAUNCHED(ctx, "scan_tiles");
     return SCS_OK;
 }
+
+namespace {
+
+// Sorted buckets of every tree (pcg_bucket_sorted): bucket_ptr[T * buckets + 1], entries[L].
+int build_buckets(scs_ctx *ctx, int n, int T, int64_t L, const BucketShape &bs, int stride, bool packed,
+                  const int64_t *leaf_offsets, const int32_t *leaf_taxon, int32_t *bucket_ptr, void *entries,
+                  int32_t *start16, int32_t *bad, const BatchView &batch) {
+    if (T <= 0 || L <= 0) {
+        SCS_CUDA(ctx, cudaMemsetAsync(bucket_ptr, 0, sizeof(int32_t) * (static_cast<size_t>(T > 0 ? T : 0) * bs.buckets + 1),
+                                      ctx->stream));
+        return SCS_OK;
+    }
+    const int key_stride = (stride + 31) & ~31;
+    const int words = bs.buckets * (key_stride >> 5);
+    const size_t per_warp = 2 * sizeof(uint32_t) * static_cast<size_t>(words);
+    if (per_warp + 1024 > ctx->smem_optin) return fail(ctx, SCS_ERR_INVALID, "graph build: too many taxa for the bucket index");
+    int warps = static_cast<int>((40 * 1024) / per_warp);
+    warps = warps < 1 ? 1 : (warps > 8 ? 8 : warps);
+    const size_t smem = per_warp * warps;
+    auto launch = [&](auto kernel, auto *typed) -> int {
+        if (smem > 48 * 1024)
+            SCS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        kernel<<<ceil_div(T, warps), warps * 32, smem, ctx->stream>>>(n, T, bs, key_stride, words, leaf_offsets, leaf_taxon,
+                                                                    bucket_ptr, typed, start16, bad, batch);
+        SCS_LAUNCHED(ctx, "pcg_bucket_sorted");
+        return SCS_OK;
+    };
+    if (packed) return launch(pcg_bucket_sorted<uint32_t>, static_cast<uint32_t *>(entries));
+    return launch(pcg_bucket_sorted<unsigned long long>, static_cast<unsigned long long *>(entries));
+}
+
+int launch_mirror(scs_ctx *ctx, int n, int words, int cols_per_chunk, int total_blocks, int max_blocks, int B, int R,
+                  const double *W, uint32_t *adj_bits, uint32_t *max_bits, double *degree, const BatchView &batch) {
+    if (total_blocks <= 0 || R <= 0) return SCS_OK;
+    dim3 grid(total_blocks, ceil_div(max_blocks, kMirrorWarps));
+    pcg_mirror_bits<<<grid, kMirrorWarps * 32, 0, ctx->stream>>>(n, words, B, adj_bits, max_bits, batch);
+    SCS_LAUNCHED(ctx, "pcg_mirror_bits");
+    pcg_degree_rows<<<ceil_div(R, kMirrorWarps), kMirrorWarps * 32, 0, ctx->stream>>>(n, R, cols_per_chunk, W, degree, batch);
+    SCS_LAUNCHED(ctx, "pcg_degree_rows");
+    return SCS_OK;
+}
+
+}  // namespace
 
 int pcg_build(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offsets,
               const int32_t *leaf_taxon, const int32_t *adj_depth, const double *adj_val,
@@ -787,43 +1156,47 @@ int pcg_build(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offsets
     if ((rc = reserve_as(ctx, SLOT_DEGREE_PART, static_cast<size_t>(n) * nchunks, &degree_part))) return rc;
     if (nrows == 0) return SCS_OK;
 
-    // buckets: count, scan, fill
+    // buckets: every tree's entries sorted by (bucket, column)
     const bool packed = n <= 65535 && !ctx->wide_entries;  // tour positions and slots fit 16 bits each
     const size_t cells = static_cast<size_t>(T) * bs.buckets;
     if (cells + 1 >= (1ull << 31)) return fail(ctx, SCS_ERR_INVALID, "pcg_build: too many tree buckets");
-    int32_t *bucket_count, *bucket_ptr;
+    int32_t *bucket_ptr;
     void *entries;
-    if ((rc = reserve_as(ctx, SLOT_BUCKET_COUNT, cells + 1, &bucket_count))) return rc;
     if ((rc = reserve_as(ctx, SLOT_BUCKET_PTR, cells + 2, &bucket_ptr))) return rc;
     if ((rc = reserve(ctx, SLOT_ENTRIES, (static_cast<size_t>(L) + 1) * (packed ? 4 : 8), &entries))) return rc;
-    SCS_CUDA(ctx, cudaMemsetAsync(bucket_count, 0, sizeof(int32_t) * (cells + 1), ctx->stream));
+    // every pair once (upper triangle + mirror) unless the rows are one rank's block of a sharded node (the other
+    // triangle lives on the peers) or the caller wants the co-occurrence matrix as well
+    const bool tri = !rows.sharded() && C == nullptr && !ctx->full_rows;
+    int32_t *start16 = nullptr;
+    if (tri && (rc = reserve_as(ctx, SLOT_START16, (static_cast<size_t>(L) + 1) * kWarps, &start16))) return rc;
+    if ((rc = build_buckets(ctx, n, T, L, bs, stride, packed, leaf_offsets, leaf_taxon, bucket_ptr, entries, start16, scalars,
+                            BatchView())))
+        return rc;
+    // the staircase of every leaf, once for the whole node
+    LeafStairs *stairs;
+    if ((rc = reserve_as(ctx, SLOT_BUCKET_COUNT, static_cast<size_t>(L) + 1, &stairs))) return rc;
     if (L > 0) {
-        pcg_bucket_count<<<ceil_div(L, 256), 256, 0, ctx->stream>>>(n, L, bs, leaf_taxon, leaf_tree, bucket_count);
-        SCS_LAUNCHED(ctx, "pcg_bucket_count");
-    }
-    if ((rc = exclusive_scan(ctx, static_cast<int>(cells), bucket_count, bucket_ptr))) return rc;
-    SCS_CUDA(ctx, cudaMemsetAsync(bucket_count, 0, sizeof(int32_t) * (cells + 1), ctx->stream));
-    if (L > 0) {
-        if (packed)
-            pcg_bucket_fill<uint32_t><<<ceil_div(L, 256), 256, 0, ctx->stream>>>(
-                n, L, bs, leaf_offsets, leaf_taxon, leaf_tree, bucket_ptr, bucket_count, static_cast<uint32_t *>(entries));
-        else
-            pcg_bucket_fill<unsigned long long><<<ceil_div(L, 256), 256, 0, ctx->stream>>>(
-                n, L, bs, leaf_offsets, leaf_taxon, leaf_tree, bucket_ptr, bucket_count,
-                static_cast<unsigned long long *>(entries));
-        SCS_LAUNCHED(ctx, "pcg_bucket_fill");
+        pcg_leaf_stairs<<<ceil_div(L, kStairsLeaves), 2 * kStairsLeaves, 0, ctx->stream>>>(n, L, leaf_offsets, leaf_tree, links, tree_weight, stairs,
+                                                                      scalars, BatchView());
+        SCS_LAUNCHED(ctx, "pcg_leaf_stairs");
     }
 
-#define SCS_ROWS(CT, WC, ET)                                                                                        \
-    launch_rows<CT, WC, ET>(ctx, n, row0, nrows, words, bs, stride, nchunks, smem, leaf_offsets, links, tree_weight, \
-                            leaf_tree, row_ptr, inv_sorted, occ, bucket_ptr, entries, W, C, adj_bits, max_bits,     \
-                            degree_part, scalars)
-#define SCS_ROWS_E(CT, WC) (packed ? SCS_ROWS(CT, WC, uint32_t) : SCS_ROWS(CT, WC, unsigned long long))
-    if (narrow) rc = C ? SCS_ROWS_E(uint16_t, true) : SCS_ROWS_E(uint16_t, false);
-    else rc = C ? SCS_ROWS_E(int32_t, true) : SCS_ROWS_E(int32_t, false);
+#define SCS_ROWS(CT, WC, ET, TRI)                                                                                        \
+    launch_rows<CT, WC, ET, TRI>(ctx, n, row0, nrows, words, bs, stride, nchunks, smem, leaf_offsets, links, tree_weight, \
+                                 leaf_tree, row_ptr, inv_sorted, occ, bucket_ptr, entries, stairs, start16, W, C, adj_bits, \
+                                 max_bits, degree_part, scalars)
+#define SCS_ROWS_E(CT, WC, TRI) (packed ? SCS_ROWS(CT, WC, uint32_t, TRI) : SCS_ROWS(CT, WC, unsigned long long, TRI))
+    if (tri) rc = narrow ? SCS_ROWS_E(uint16_t, false, true) : SCS_ROWS_E(int32_t, false, true);
+    else if (narrow) rc = C ? SCS_ROWS_E(uint16_t, true, false) : SCS_ROWS_E(uint16_t, false, false);
+    else rc = C ? SCS_ROWS_E(int32_t, true, false) : SCS_ROWS_E(int32_t, false, false);
 #undef SCS_ROWS_E
 #undef SCS_ROWS
     if (rc) return rc;
+    if (tri) {
+        // the other triangle of W and of the bit matrices, and the row sums (into `degree`, or a scratch if unwanted)
+        return launch_mirror(ctx, n, words, bs.cols_per_chunk, words, words, 1, n, W, adj_bits, max_bits,
+                             degree ? degree : degree_part, BatchView());
+    }
     if (degree) {
         pcg_sum_degree_parts<<<ceil_div(nrows, 256), 256, 0, ctx->stream>>>(n, row0, row1, nchunks, degree_part, degree);
         SCS_LAUNCHED(ctx, "pcg_sum_degree_parts");
@@ -834,7 +1207,7 @@ int pcg_build(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offsets
 
 // The same pipeline over a batch of nodes (see BatchView): index, inverse lists, links, buckets and ONE launch of
 // the row kernel with a CTA per row of the global row space.  Every node fits one column chunk.
-int pcg_build_batch(scs_ctx *ctx, int R, int T, int64_t L, int max_n, int max_trees, const MedNode *nodes_dev,
+int pcg_build_batch(scs_ctx *ctx, int B, int blocks, int R, int T, int64_t L, int max_n, int max_trees, const MedNode *nodes_dev,
                     const int32_t *tree_node, const int32_t *row_node, const int64_t *leaf_offsets,
                     const int32_t *leaf_taxon, const int32_t *adj_depth, const double *adj_val,
                     const int32_t *root_depth, const double *tree_weight, double *W, int32_t *occ, uint32_t *adj_bits,
@@ -888,32 +1261,46 @@ int pcg_build_batch(scs_ctx *ctx, int R, int T, int64_t L, int max_n, int max_tr
     const size_t smem = static_cast<size_t>(stride) * warps * per_col + 16;
     const size_t cells = static_cast<size_t>(T) * bs.buckets;
     if (cells + 1 >= (1ull << 31)) return fail(ctx, SCS_ERR_INVALID, "pcg_build_batch: too many tree buckets");
-    int32_t *bucket_count, *bucket_ptr;
+    int32_t *bucket_ptr;
     void *entries;
-    if ((rc = reserve_as(ctx, SLOT_BUCKET_COUNT, cells + 1, &bucket_count))) return rc;
     if ((rc = reserve_as(ctx, SLOT_BUCKET_PTR, cells + 2, &bucket_ptr))) return rc;
     if ((rc = reserve(ctx, SLOT_ENTRIES, (static_cast<size_t>(L) + 1) * 4, &entries))) return rc;
-    SCS_CUDA(ctx, cudaMemsetAsync(bucket_count, 0, sizeof(int32_t) * (cells + 1), ctx->stream));
+    int32_t *start16 = nullptr;
+    if (!ctx->full_rows && (rc = reserve_as(ctx, SLOT_START16, (static_cast<size_t>(L) + 1) * kWarps, &start16))) return rc;
+    if ((rc = build_buckets(ctx, max_n, T, L, bs, stride, true, leaf_offsets, leaf_taxon, bucket_ptr, entries, start16, bad_dev,
+                            batch)))
+        return rc;
+    LeafStairs *stairs;
+    if ((rc = reserve_as(ctx, SLOT_BUCKET_COUNT, static_cast<size_t>(L) + 1, &stairs))) return rc;
     if (L > 0) {
-        pcg_bucket_count<<<ceil_div(L, 256), 256, 0, ctx->stream>>>(max_n, L, bs, leaf_taxon, leaf_tree, bucket_count);
-        SCS_LAUNCHED(ctx, "pcg_bucket_count");
+        pcg_leaf_stairs<<<ceil_div(L, kStairsLeaves), 2 * kStairsLeaves, 0, ctx->stream>>>(max_n, L, leaf_offsets, leaf_tree, links, tree_weight,
+                                                                      stairs, bad_dev, batch);
+        SCS_LAUNCHED(ctx, "pcg_leaf_stairs");
     }
-    if ((rc = exclusive_scan(ctx, static_cast<int>(cells), bucket_count, bucket_ptr))) return rc;
-    SCS_CUDA(ctx, cudaMemsetAsync(bucket_count, 0, sizeof(int32_t) * (cells + 1), ctx->stream));
-    if (L > 0) {
-        pcg_bucket_fill<uint32_t><<<ceil_div(L, 256), 256, 0, ctx->stream>>>(
-            max_n, L, bs, leaf_offsets, leaf_taxon, leaf_tree, bucket_ptr, bucket_count, static_cast<uint32_t *>(entries));
-        SCS_LAUNCHED(ctx, "pcg_bucket_fill");
+    if (!ctx->full_rows) {
+        // every pair once: the upper triangles, then the mirror (which also writes the row sums into `degree`)
+        if (narrow)
+            rc = launch_rows<uint16_t, false, uint32_t, true>(ctx, R, 0, R, 0, bs, stride, 1, smem, leaf_offsets, links,
+                                                              tree_weight, leaf_tree, row_ptr, inv_sorted, occ, bucket_ptr,
+                                                              entries, stairs, start16, W, nullptr, adj_bits, max_bits, degree,
+                                                              bad_dev, batch);
+        else
+            rc = launch_rows<int32_t, false, uint32_t, true>(ctx, R, 0, R, 0, bs, stride, 1, smem, leaf_offsets, links,
+                                                             tree_weight, leaf_tree, row_ptr, inv_sorted, occ, bucket_ptr,
+                                                             entries, stairs, start16, W, nullptr, adj_bits, max_bits, degree,
+                                                             bad_dev, batch);
+        if (rc) return rc;
+        return launch_mirror(ctx, 0, 0, 0, blocks, ceil_div(max_n, 32), B, R, W, adj_bits, max_bits, degree, batch);
     }
     // the row kernel writes the row sums straight into `degree` (one chunk: degree_part[0][row])
     if (narrow)
-        rc = launch_rows<uint16_t, false, uint32_t>(ctx, R, 0, R, 0, bs, stride, 1, smem, leaf_offsets, links, tree_weight,
-                                                    leaf_tree, row_ptr, inv_sorted, occ, bucket_ptr, entries, W, nullptr,
-                                                    adj_bits, max_bits, degree, bad_dev, batch);
+        rc = launch_rows<uint16_t, false, uint32_t, false>(ctx, R, 0, R, 0, bs, stride, 1, smem, leaf_offsets, links, tree_weight,
+                                                    leaf_tree, row_ptr, inv_sorted, occ, bucket_ptr, entries, stairs, start16,
+                                                           W, nullptr, adj_bits, max_bits, degree, bad_dev, batch);
     else
-        rc = launch_rows<int32_t, false, uint32_t>(ctx, R, 0, R, 0, bs, stride, 1, smem, leaf_offsets, links, tree_weight,
-                                                   leaf_tree, row_ptr, inv_sorted, occ, bucket_ptr, entries, W, nullptr,
-                                                   adj_bits, max_bits, degree, bad_dev, batch);
+        rc = launch_rows<int32_t, false, uint32_t, false>(ctx, R, 0, R, 0, bs, stride, 1, smem, leaf_offsets, links, tree_weight,
+                                                   leaf_tree, row_ptr, inv_sorted, occ, bucket_ptr, entries, stairs, start16,
+                                                          W, nullptr, adj_bits, max_bits, degree, bad_dev, batch);
     return rc;
 }
 

@@ -114,6 +114,10 @@ class Engine:
         """Graph build with the 8-byte bucket entries of nodes with >= 65 536 taxa at every size (tests)."""
         _check(self._lib.scs_ctx_set_wide_entries(self._ctx, int(on)), self._ctx)
 
+    def set_full_rows(self, on: bool) -> None:
+        """Graph build: every row CTA visits all its leaf pairs instead of the pairs beyond the diagonal + mirror (tests)."""
+        _check(self._lib.scs_ctx_set_full_rows(self._ctx, int(on)), self._ctx)
+
     def stage_seconds(self, reset: bool = True) -> dict:
         """Host wall clock per stage of the staged node path (``scs_ctx_stage_seconds``)."""
         out = np.zeros(8)

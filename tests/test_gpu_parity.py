@@ -284,11 +284,14 @@ def test_pcg_wide_bucket_entries_bit_exact(engine):
     engine.set_wide_entries(True)
     try:
         out = engine.pcg_build(tours_of(case), want_counts=True)
+        lean = engine.pcg_build(tours_of(case), want_counts=False)  # upper triangle + mirror
     finally:
         engine.set_wide_entries(False)
     assert np.array_equal(out["W"], ref["W"])
     assert np.array_equal(out["C"], ref["C"])
     assert np.array_equal(out["occ"], ref["occ"])
+    for key in ("W", "occ", "adj_bits", "max_bits", "degree"):
+        assert np.array_equal(lean[key], out[key]), key
 
 
 def test_full_size_workload_against_the_c_oracle(engine):

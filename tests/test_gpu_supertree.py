@@ -120,12 +120,13 @@ def test_small_node_path_agrees_with_staged_path(engine, name):
     case = load_case(name)
     fused: list = []
     staged: list = []
-    construct_supertree(parse(case["lines"]), case["weights"], case["weighting"], engine=engine, trace=fused)
-    engine.set_small_node_limit(0)
+    engine.set_small_node_limit(64)  # the one-CTA path at its full capacity (the library's default limit is 32)
     try:
+        construct_supertree(parse(case["lines"]), case["weights"], case["weighting"], engine=engine, trace=fused)
+        engine.set_small_node_limit(0)
         construct_supertree(parse(case["lines"]), case["weights"], case["weighting"], engine=engine, trace=staged)
     finally:
-        engine.set_small_node_limit(64)
+        engine.set_small_node_limit(32)
     by_names = {tuple(r["names"]): r for r in staged}
     small_nodes = 0
     for rec in fused:
@@ -269,6 +270,46 @@ def test_medium_batch_matches_per_node_path(engine, name):
     if name != "dcm":
         assert batched["nodes_medium"] > 0 and compared > 0
     assert int((batched["taxon"] >= 0).sum()) == int((staged["taxon"] >= 0).sum())
+
+
+@pytest.mark.parametrize("name", ["c2_500x50_branch", "c3_1000x100_branch_weighted", "s_200x40_bootstrap"])
+def test_triangle_graph_build_equals_full_rows(engine, name):
+    """The graph build visits every leaf pair once (row CTA a: the columns beyond a; pcg_mirror_bits and pcg_degree_rows: the other
+    triangle of W and of the bit matrices, the row sums).  With scs_ctx_set_full_rows every row CTA visits all its
+    pairs instead: the whole recursion -- batched medium nodes and per-node path -- must come out identical to the
+    last bit of every Fiedler eigenvalue, because W, the bit matrices and the degrees are."""
+    from spectralclustersupertree_b200.engine import Forest
+
+    case = load_case(name)
+    trees = parse(case["lines"])
+
+    def build():
+        forest = Forest.from_trees(trees, case["weights"], case["names"])
+        return engine.supertree_build(forest, case["weighting"], record=True)
+
+    outs = []
+    for medium_limit in (4096, 0):
+        engine.set_medium_node_limit(medium_limit)
+        try:
+            mirrored = build()
+            engine.set_full_rows(True)
+            try:
+                full = build()
+            finally:
+                engine.set_full_rows(False)
+        finally:
+            engine.set_medium_node_limit(4096)
+        outs.append(mirrored)
+        assert len(mirrored["records"]) == len(full["records"])
+        for (taxa, part, stats), (otaxa, opart, ostats) in zip(mirrored["records"], full["records"], strict=True):
+            assert np.array_equal(taxa, otaxa)
+            assert np.array_equal(part, opart)
+            assert stats.n_components == ostats.n_components and stats.contracted_size == ostats.contracted_size
+            if stats.n_components == 1 and stats.contracted_size >= 3:
+                assert stats.eig[1] == ostats.eig[1] and stats.eig[2] == ostats.eig[2]
+                assert stats.matvecs == ostats.matvecs
+        assert np.array_equal(mirrored["parent"], full["parent"]) and np.array_equal(mirrored["taxon"], full["taxon"])
+    assert outs[0]["nodes_medium"] > 0 and outs[1]["nodes_medium"] == 0
 
 
 @pytest.mark.parametrize("name", ["dcm", "dcm_iq", "supertriplets", "c2_500x50_branch", "c3_1000x100_branch_weighted",

@@ -26,6 +26,17 @@ for stage in "$@"; do
             --log-file gpurun_out/${tag}_launches_step.csv python bench.py --profile-step > gpurun_out/${tag}_launches_step.out 2>&1; echo "ncu launches rc=$?"
         python tools/ncu_summary.py launches gpurun_out/${tag}_launches_step.csv > gpurun_out/${tag}_launches_step_summary.csv; head -30 gpurun_out/${tag}_launches_step_summary.csv
       fi ;;
+    wavetrace)
+      SCS_DRIVER_TRACE=1 python tools/driver_profile.py c4 > gpurun_out/${tag}_wavetrace.log 2>&1; echo "wavetrace rc=$?"; tail -45 gpurun_out/${tag}_wavetrace.log ;;
+    ncufull)
+      # one --set full capture per heavy kernel of the profiled step (bench.py --profile-step exited 0 in stage launches)
+      for k in ${KERNELS:-matvec_rows pcg_rows_kernel small_batch_kernel}; do
+        ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:$k -c 3 -f \
+            -o gpurun_out/${tag}_ncu_$k python bench.py --profile-step > gpurun_out/${tag}_ncu_$k.out 2>&1; echo "ncu $k rc=$?"
+        ncu -i gpurun_out/${tag}_ncu_$k.ncu-rep --page raw --csv > gpurun_out/${tag}_ncu_${k}_raw.csv 2>/dev/null
+        ncu -i gpurun_out/${tag}_ncu_$k.ncu-rep --page details > gpurun_out/${tag}_ncu_${k}_details.txt 2>/dev/null
+      done
+      python tools/ncu_summary.py traffic gpurun_out/${tag}_ncu_matvec_rows_raw.csv matvec_rows gpurun_out/${tag}_ncu_matvec_traffic.json ;;
     sanitize)
       python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_smoke.log 2>&1; rc=$?; echo "smoke rc=$rc"; tail -2 gpurun_out/${tag}_smoke.log
       if [ $rc -eq 0 ]; then

@@ -45,26 +45,34 @@ def launches(path: str) -> None:
     print(f"ALL,{sum(count.values())},{whole:.1f},1.0")
 
 
+SCALE = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6,
+         "usecond": 1.0, "nsecond": 1e-3, "msecond": 1e3}
+
+
 def traffic(path: str, pattern: str, out: str | None) -> None:
-    wanted = {"dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum"}
-    per_id: dict = defaultdict(dict)
-    for row in rows_of(path):
-        if row.get("Metric Name") in wanted and re.search(pattern, row["Kernel Name"]):
-            value = float(row["Metric Value"].replace(",", ""))
-            unit = row.get("Metric Unit", "")
-            scale = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "ns": 1e-3, "us": 1.0, "ms": 1e3}.get(unit, 1.0)
-            per_id[row["ID"]][row["Metric Name"]] = value * scale
-            per_id[row["ID"]]["kernel"] = short(row["Kernel Name"])
-            per_id[row["ID"]]["grid"] = row.get("Grid Size", "")
-    launches_ = [v for v in per_id.values() if len(v) >= 5]
+    """`ncu -i x.ncu-rep --page raw --csv`: one row per launch, one column per metric, units in the second row."""
+    with open(path, newline="") as fh:
+        table = [row for row in csv.reader(fh) if row]
+    header, units = table[0], table[1]
+    col = {name: header.index(name) for name in ("Kernel Name", "Grid Size", "dram__bytes_read.sum",
+                                                 "dram__bytes_write.sum", "gpu__time_duration.sum")}
+
+    def value(row, name):
+        return float(row[col[name]].replace(",", "")) * SCALE.get(units[col[name]], 1.0)
+
+    launches_ = [row for row in table[2:] if re.search(pattern, row[col["Kernel Name"]])]
     if not launches_:
-        sys.exit("no matching launch with all three metrics")
-    best = max(launches_, key=lambda v: v["dram__bytes_read.sum"])
+        sys.exit("no matching launch")
+    best = max(launches_, key=lambda row: value(row, "dram__bytes_read.sum"))
     result = {
-        "kernel": best["kernel"], "grid": best["grid"],
-        "dram_bytes_per_launch": best["dram__bytes_read.sum"] + best["dram__bytes_write.sum"],
-        "dram_read_bytes": best["dram__bytes_read.sum"], "dram_write_bytes": best["dram__bytes_write.sum"],
-        "duration_us": best["gpu__time_duration.sum"], "launches_in_capture": len(launches_), "source": path,
+        "kernel": short(best[col["Kernel Name"]]), "grid": best[col["Grid Size"]],
+        "dram_bytes_per_launch": value(best, "dram__bytes_read.sum") + value(best, "dram__bytes_write.sum"),
+        "dram_read_bytes": value(best, "dram__bytes_read.sum"), "dram_write_bytes": value(best, "dram__bytes_write.sum"),
+        "duration_us": value(best, "gpu__time_duration.sum"), "launches_in_capture": len(launches_),
+        "all_launches": [{"grid": row[col["Grid Size"]], "duration_us": value(row, "gpu__time_duration.sum"),
+                          "dram_bytes": value(row, "dram__bytes_read.sum") + value(row, "dram__bytes_write.sum")}
+                         for row in launches_],
+        "source": path,
     }
     text = json.dumps(result, indent=1)
     print(text)
