@@ -31,9 +31,14 @@ budget (c1-c3), else the job's top-level recursion node alone, reported as what 
 
 from __future__ import annotations
 
+import os
+
+# idle OpenMP threads of the library's host-side helpers must sleep, not spin: with one process per GPU they would
+# take the cores the other ranks' driver threads need (read by the OpenMP runtime when it is first loaded)
+os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+
 import argparse
 import json
-import os
 import statistics
 import subprocess
 import sys

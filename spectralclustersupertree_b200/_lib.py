@@ -188,6 +188,10 @@ def load() -> ctypes.CDLL:
     # its first launch can block behind such a wait when the contexts share a process (the in-process multi-rank
     # tests), so ask for all kernels up front.  Only effective before the CUDA runtime initialises.
     os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+    # Idle OpenMP threads of the host-side helpers (tree validation, uploads) should sleep rather than spin: the
+    # recursion's own driver threads, and the other ranks of a multi-GPU job, need the cores.  Only effective if the
+    # OpenMP runtime has not been loaded yet (bench.py sets it before importing anything).
+    os.environ.setdefault("OMP_WAIT_POLICY", "passive")
     lib = ctypes.CDLL(str(LIB_PATH))
     for name, (restype, argtypes) in SIGNATURES.items():
         fn = getattr(lib, name)

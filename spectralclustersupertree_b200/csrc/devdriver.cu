@@ -623,8 +623,14 @@ int scs_device_forest_create(scs_ctx *ctx, const scs_forest *forest, int weighti
         return rc;
     }
     std::vector<uint8_t> seen(static_cast<size_t>(d->num_taxa > 0 ? d->num_taxa : 1), 0);
-    for (int32_t x : forest->taxon)
-        if (x >= 0) seen[x] = 1;
+    {
+        const int32_t *tax = forest->taxon.data();
+        const long long count = static_cast<long long>(forest->taxon.size());
+        uint8_t *mark = seen.data();
+#pragma omp parallel for schedule(static) num_threads(scs_host_threads() > 0 ? scs_host_threads() : 1) if (count > (1 << 20))
+        for (long long k = 0; k < count; ++k)
+            if (tax[k] >= 0) mark[tax[k]] = 1;  // racing writers all store 1
+    }
     for (int x = 0; x < d->num_taxa; ++x)
         if (seen[x]) d->taxa.push_back(x);
     d->first_tree_nodes = forest->num_trees() > 0 ? forest->node_offsets[1] - forest->node_offsets[0] : 0;

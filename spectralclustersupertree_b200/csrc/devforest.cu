@@ -424,10 +424,41 @@ int devforest_upload(scs_ctx *ctx, const scs_forest *host, int weighting, DevFor
     if ((rc = grow(ctx, out->tree_job, nT * sizeof(int32_t)))) return rc;
     if (out->has_length && (rc = grow(ctx, out->length, nM * sizeof(double)))) return rc;
     if (out->has_support && (rc = grow(ctx, out->support, nM * sizeof(double)))) return rc;
+    // Pageable memory goes to the device through two pinned chunks: the host threads fill one while the other is on
+    // the wire (a plain cudaMemcpy from pageable memory stages serially through the driver at a fraction of the
+    // link's rate: 0.26 s for the 0.8 GB of the 50 000-taxon workload).
+    constexpr size_t kChunk = 32u << 20;
+    const bool staged = nM * sizeof(double) > (8u << 20);
+    unsigned char *pin = nullptr;
+    cudaEvent_t sent[2] = {nullptr, nullptr};
+    if (staged) {
+        void *pin_v;
+        if ((rc = reserve_pinned(ctx, 2 * kChunk, &pin_v))) return rc;
+        pin = static_cast<unsigned char *>(pin_v);
+        for (cudaEvent_t &e : sent) SCS_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    int turn = 0;
+    const int copy_threads = scs_host_threads() > 0 ? scs_host_threads() : 1;
     auto put = [&](GrowBuf &dst, const void *src, size_t bytes) -> int {
         if (bytes == 0) return SCS_OK;
-        SCS_CUDA(ctx, cudaMemcpyAsync(dst.ptr, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
         ctx->h2d_bytes += static_cast<int64_t>(bytes);
+        if (!staged || bytes < (1u << 20)) {
+            SCS_CUDA(ctx, cudaMemcpyAsync(dst.ptr, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+            return SCS_OK;
+        }
+        for (size_t at = 0; at < bytes; at += kChunk, turn ^= 1) {
+            const size_t len = bytes - at < kChunk ? bytes - at : kChunk;
+            unsigned char *stage = pin + static_cast<size_t>(turn) * kChunk;
+            SCS_CUDA(ctx, cudaEventSynchronize(sent[turn]));  // the chunk's previous copy has left it
+            const long long pieces = static_cast<long long>((len + (1u << 20) - 1) >> 20);
+#pragma omp parallel for schedule(static) num_threads(copy_threads)
+            for (long long p = 0; p < pieces; ++p) {
+                const size_t o = static_cast<size_t>(p) << 20;
+                std::memcpy(stage + o, static_cast<const unsigned char *>(src) + at + o, len - o < (1u << 20) ? len - o : (1u << 20));
+            }
+            SCS_CUDA(ctx, cudaMemcpyAsync(static_cast<unsigned char *>(dst.ptr) + at, stage, len, cudaMemcpyHostToDevice, ctx->stream));
+            SCS_CUDA(ctx, cudaEventRecord(sent[turn], ctx->stream));
+        }
         return SCS_OK;
     };
     if ((rc = put(out->tree_off, host->node_offsets.data(), (nT + 1) * sizeof(int64_t)))) return rc;
@@ -441,6 +472,8 @@ int devforest_upload(scs_ctx *ctx, const scs_forest *host, int weighting, DevFor
     SCS_CUDA(ctx, cudaMemsetAsync(out->tree_job.ptr, 0, nT * sizeof(int32_t), ctx->stream));
     // `size` is a local: the copies above must have read it before it goes away
     SCS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (cudaEvent_t e : sent)
+        if (e) cudaEventDestroy(e);
     return SCS_OK;
 }
 

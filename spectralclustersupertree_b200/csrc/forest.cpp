@@ -92,12 +92,13 @@ int scs_forest_create(int T, const int64_t *node_offsets, const int32_t *parent,
     if (!f) return SCS_ERR_INVALID;
     f->num_taxa = num_taxa;
     f->node_offsets.assign(node_offsets, node_offsets + T + 1);
-    f->parent.assign(parent, parent + M);
-    f->taxon.assign(taxon, taxon + M);
-    if (length) f->length.assign(length, length + M);
-    else f->length.assign(M, std::nan(""));
-    if (support) f->support.assign(support, support + M);
-    else f->support.assign(M, std::nan(""));
+    const int copy_threads = scs_host_threads() > 0 ? scs_host_threads() : 1;
+    f->parent.assign_parallel(parent, parent + M, copy_threads);
+    f->taxon.assign_parallel(taxon, taxon + M, copy_threads);
+    if (length) f->length.assign_parallel(length, length + M, copy_threads);
+    else f->length.assign_parallel(static_cast<size_t>(M), std::nan(""), copy_threads);
+    if (support) f->support.assign_parallel(support, support + M, copy_threads);
+    else f->support.assign_parallel(static_cast<size_t>(M), std::nan(""), copy_threads);
     f->weight.assign(tree_weight, tree_weight + T);
     f->source.resize(T);
     f->branching.assign(static_cast<size_t>(T), 1);

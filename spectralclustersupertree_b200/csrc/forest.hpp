@@ -29,6 +29,23 @@ class FlatArray {
         resize_uninitialized(n);
         for (size_t i = 0; i < size_; ++i) data_[i] = value;
     }
+    // the same two, spread over the host threads (large inputs: the copy and its page faults are the cost)
+    void assign_parallel(const T *first, const T *last, int threads) {
+        resize_uninitialized(static_cast<size_t>(last - first));
+        const long long n = static_cast<long long>(size_);
+        const long long chunk = 1ll << 18;
+#pragma omp parallel for schedule(static) num_threads(threads) if (n > (4ll << 20))
+        for (long long at = 0; at < n; at += chunk) {
+            const long long len = n - at < chunk ? n - at : chunk;
+            std::memcpy(data_ + at, first + at, static_cast<size_t>(len) * sizeof(T));
+        }
+    }
+    void assign_parallel(size_t count, T value, int threads) {
+        resize_uninitialized(count);
+        const long long n = static_cast<long long>(size_);
+#pragma omp parallel for schedule(static) num_threads(threads) if (n > (4ll << 20))
+        for (long long i = 0; i < n; ++i) data_[i] = value;
+    }
     T *data() { return data_; }
     const T *data() const { return data_; }
     size_t size() const { return size_; }

@@ -37,6 +37,16 @@ for stage in "$@"; do
         ncu -i gpurun_out/${tag}_ncu_$k.ncu-rep --page details > gpurun_out/${tag}_ncu_${k}_details.txt 2>/dev/null
       done
       python tools/ncu_summary.py traffic gpurun_out/${tag}_ncu_matvec_rows_raw.csv matvec_rows gpurun_out/${tag}_ncu_matvec_traffic.json ;;
+    c5)
+      python tools/run_workload.py c5 --repeat 2 --out gpurun_out/${tag}_c5_n1.json > gpurun_out/${tag}_c5_n1.log 2>&1; echo "c5 n1 rc=$?"; cut -c1-700 gpurun_out/${tag}_c5_n1.json ;;
+    multi)
+      # N = $GPUS ranks on one box: the bench line, c5 through the product path, tree-sharded W + all-reduce beside row sharding
+      N=${GPUS:-2}
+      python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/${tag}_bench_c4_n$N.json 2> gpurun_out/${tag}_bench_c4_n$N.err; echo "bench c4 n$N rc=$?"; head -c 400 gpurun_out/${tag}_bench_c4_n$N.json; tail -3 gpurun_out/${tag}_bench_c4_n$N.err
+      python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 tools/tree_sharded_allreduce.py c4 > gpurun_out/${tag}_treeshard_c4_n$N.json 2> gpurun_out/${tag}_treeshard_c4_n$N.err; echo "treeshard n$N rc=$?"; cut -c1-600 gpurun_out/${tag}_treeshard_c4_n$N.json
+      if [ -z "${SKIP_C5:-}" ]; then
+        python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 tools/run_workload.py c5 --repeat 2 --out gpurun_out/${tag}_c5_n$N.json > gpurun_out/${tag}_c5_n$N.log 2>&1; echo "c5 n$N rc=$?"; cut -c1-700 gpurun_out/${tag}_c5_n$N.json; tail -3 gpurun_out/${tag}_c5_n$N.log
+      fi ;;
     sanitize)
       python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_smoke.log 2>&1; rc=$?; echo "smoke rc=$rc"; tail -2 gpurun_out/${tag}_smoke.log
       if [ $rc -eq 0 ]; then

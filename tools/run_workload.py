@@ -9,10 +9,15 @@ the job's counters, and a checksum of the supertree's clades so that runs at dif
 
 from __future__ import annotations
 
+import os
+
+# idle OpenMP threads of the library's host-side helpers must sleep, not spin: with one process per GPU they would
+# take the cores the other ranks' driver threads need (read by the OpenMP runtime when it is first loaded)
+os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+
 import argparse
 import hashlib
 import json
-import os
 import sys
 import time
 from pathlib import Path
@@ -89,7 +94,9 @@ def main() -> None:
         t0 = time.perf_counter()
         forest = Forest.from_arrays(a["node_offsets"], a["parent"], a["length"], a["support"], a["taxon"], a["weights"],
                                     a["names"])  # fmt: skip
+        t1 = time.perf_counter()
         built = engine.supertree_build(forest, a["weighting"], rank=rank, world=world)
+        t2 = time.perf_counter()
         if dist is not None:
             parts = [None] * world
             dist.all_gather_object(parts, (built["parent"], built["taxon"], built["shared_prefix"]))
@@ -97,10 +104,12 @@ def main() -> None:
         else:
             merged = (built["parent"], built["taxon"])
         runs.append(time.perf_counter() - t0)
+        phases = {"forest_create": t1 - t0, "build": t2 - t1, "gather_and_join": time.perf_counter() - t2}
         forest.close()
     digest, tips, internal = clade_checksum(*merged)
     line = {
-        "workload": bench.describe(args.workload), "n_gpus": world, "seconds": runs, "generate_seconds": t_make,
+        "workload": bench.describe(args.workload), "n_gpus": world, "seconds": runs, "phases_last_run": phases,
+        "generate_seconds": t_make,
         "host_seconds": built["seconds"], "nodes_small": built["nodes_small"], "nodes_large": built["nodes_large"],
         "waves": built["waves"], "wave_tasks": built["wave_tasks"], "wave_max_n": built["wave_max_n"],
         "wave_seconds_gpu_restrict_total": [[round(1e3 * v, 2) for v in w] for w in built["wave_seconds"]],
