@@ -115,6 +115,10 @@ struct ShardState {
 // Rows [row0, row1) of a row-sharded matrix live on this rank; row1 < 0 means "not sharded".
 struct RowBlock {
     int row0 = 0, row1 = -1;
+    // graph build of a row block: every row computes only the cyclic half window of columns after its own (each
+    // pair of the node once, over all ranks); the caller completes the rows from the peers' blocks
+    // (pcg_fetch_transposed), the bit matrices (pcg_symmetrize_bits) and sums them (pcg_degree_block)
+    bool half_window = false;
     bool sharded() const { return row1 >= 0; }
 };
 
@@ -270,6 +274,14 @@ int pcg_build(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offsets
               const int32_t *leaf_taxon, const int32_t *adj_depth, const double *adj_val,
               const int32_t *root_depth, const double *tree_weight, double *W, int32_t *C,
               int32_t *occ, uint32_t *adj_bits, uint32_t *max_bits, double *degree, RowBlock rows = RowBlock());
+
+// Completion of a half-window row block (see RowBlock): peer_W[r] = rank r's row block (rows [r * rows_per_rank, ...),
+// row stride n), all of them finished with their own halves; the bit matrices are the full n x n ones every rank
+// holds after the exchange of the rows.
+int pcg_fetch_transposed(scs_ctx *ctx, int n, RowBlock rows, int rows_per_rank, int world, const double *const *peer_W,
+                         double *W_block);
+int pcg_symmetrize_bits(scs_ctx *ctx, int n, uint32_t *adj_bits, uint32_t *max_bits);
+int pcg_degree_block(scs_ctx *ctx, int n, int T, RowBlock rows, const double *W_block, double *degree);
 
 int components(scs_ctx *ctx, int n, const uint32_t *bits, int32_t *label, int32_t *n_components_host);
 

@@ -677,7 +677,7 @@ __device__ __forceinline__ void visit_trees(const TreeBatch &tb, int first, int 
 // tree starts with a binary search (one lane per tree of the batch, while the first warps walk the chains).
 template <typename CountT, bool kWriteC, typename EntryT, bool kTri>
 __global__ void __launch_bounds__(kRowThreads, 2)
-pcg_rows_kernel(int n, int row0, int words_per_row, BucketShape bs, int stride,
+pcg_rows_kernel(int n, int row0, int words_per_row, BucketShape bs, int stride, int half_mode,
                 const int64_t *__restrict__ leaf_offsets, const LinkEntry *__restrict__ links,
                 const double *__restrict__ tree_weight, const int32_t *__restrict__ leaf_tree,
                 const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ inv_sorted,
@@ -717,13 +717,28 @@ pcg_rows_kernel(int n, int row0, int words_per_row, BucketShape bs, int stride,
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int my_bucket = (blockIdx.y << bs.warps_log2) + warp;
     const int slot0 = warp * stride;  // the slots of this warp's columns start here
-    // triangle mode: the first slot of this warp whose column lies beyond the row's own (column = slot * W + warp)
-    int slot_min = 0;
+    // Partial rows (kTri): the columns this CTA computes, as up to two ranges of the chunk's local columns.
+    //   half_mode 0 (one GPU): the columns beyond the diagonal, (a, n);
+    //   half_mode 1 (the row block of a node shared out over several GPUs): the cyclic half window (a, a + h] with
+    //   h = (n - 1) / 2, one more for the rows of the first half when n is even -- of every pair {a, c} exactly
+    //   one of the two rows has the other in its window, every row does half its pairs, and nothing depends on how
+    //   the rows are dealt to the ranks; the owners exchange the other half afterwards (pcg_fetch_transposed).
+    int r1b = 0, r1e = 0, r2b = 0, r2e = 0;
     if (kTri) {
-        if (a_loc >= col0 + ncols) return;  // the whole chunk lies at or before the diagonal: the mirror's part
-        const int la = a_loc - col0;
-        if (la >= warp) slot_min = ((la - warp) >> bs.warps_log2) + 1;
+        int e1 = n, e2 = 0;
+        if (half_mode) {
+            const int last = a_loc + (n - 1) / 2 + (((n & 1) == 0 && a_loc < n / 2) ? 1 : 0);  // inclusive
+            if (last < n) e1 = last + 1;
+            else e2 = last - n + 1;
+        }
+        r1b = max(a_loc + 1, col0) - col0;
+        r1e = max(min(e1, col0 + ncols) - col0, r1b);
+        r2b = 0;
+        r2e = max(min(e2, col0 + ncols) - col0, 0);
+        if (!half_mode && a_loc >= col0 + ncols) return;  // the whole chunk lies before the diagonal: the mirror's part
     }
+    // the slots of this warp inside a local column range [lb, le): column = slot * W + warp
+    auto slots_below = [&](int le) { return le > warp ? (le - warp + (1 << bs.warps_log2) - 1) >> bs.warps_log2 : 0; };
 
     for (int c = tid; c < slots_total; c += nthreads) {
         accW[c] = 0.0;
@@ -732,27 +747,48 @@ pcg_rows_kernel(int n, int row0, int words_per_row, BucketShape bs, int stride,
 
     const int ebase = row_ptr[a];
     const int cnt = row_ptr[a + 1] - ebase;
-    const bool diagonal_chunk = kTri && a_loc >= col0;  // this chunk holds the row's own column
+    const bool diagonal_chunk = kTri && !half_mode && a_loc >= col0;  // this chunk holds the row's own column
+    const int s1b = slots_below(r1b), s1e = slots_below(r1e), s2b = slots_below(r2b), s2e = slots_below(r2e);
     const int4 *stairs4 = reinterpret_cast<const int4 *>(stairs);
     for (int e0 = 0; e0 < cnt; e0 += kTreeBatch) {
         const int batch = min(kTreeBatch, cnt - e0);
         __syncthreads();  // the previous batch (and the initialisation) is done with
         // Lane e keeps where this warp's share of tree e starts and ends, and whether the tree's chains need further
         // rounds.  Every warp reads this for itself: nothing here waits for another warp.
-        int my_ptr = 0, my_end = 0;
+        int my_ptr = 0, my_end = 0, my_ptr2 = 0, my_end2 = 0;
         bool my_open = false;
         if (lane < batch) {
             const int g = inv_sorted[ebase + e0 + lane];
             const int4 shape = stairs4[static_cast<size_t>(g) * kStairsInt4 + 26];  // low, high, resume0, resume1
             const int4 info = stairs4[static_cast<size_t>(g) * kStairsInt4 + 27];   // leaves, position, tree
             const size_t cell = static_cast<size_t>(info.z) * bs.buckets + my_bucket;
-            my_end = bucket_ptr[cell + 1];
-            // triangle mode, the chunk with the row's own column: the warp's entries beyond the diagonal start where
-            // pcg_bucket_sorted found them for this leaf; later chunks lie beyond the diagonal altogether
-            my_ptr = diagonal_chunk ? start16[static_cast<size_t>(g) * kWarps + warp] : bucket_ptr[cell];
-            if (info.x == 0) my_end = my_ptr;
+            const int bucket_begin = bucket_ptr[cell], bucket_end = bucket_ptr[cell + 1];
+            if (kTri && half_mode) {
+                // the entries of a bucket ascend by slot: the two ranges of wanted slots by binary search
+                auto first_at_least = [&](int want) {
+                    int lo = bucket_begin, hi = bucket_end;
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        int q, sl;
+                        unpack(entries[mid], q, sl);
+                        if (sl < want) lo = mid + 1; else hi = mid;
+                    }
+                    return lo;
+                };
+                my_ptr = s1e > s1b ? first_at_least(s1b) : bucket_begin;
+                my_end = s1e > s1b ? first_at_least(s1e) : bucket_begin;
+                my_ptr2 = s2e > s2b ? first_at_least(s2b) : bucket_begin;
+                my_end2 = s2e > s2b ? first_at_least(s2e) : bucket_begin;
+            } else {
+                my_end = bucket_end;
+                // one GPU, the chunk with the row's own column: the warp's entries beyond the diagonal start where
+                // pcg_bucket_sorted found them for this leaf; later chunks lie beyond the diagonal altogether
+                my_ptr = diagonal_chunk ? start16[static_cast<size_t>(g) * kWarps + warp] : bucket_begin;
+            }
+            if (info.x == 0) my_end = my_ptr, my_end2 = my_ptr2;
             my_open = shape.z >= 0 || shape.w >= 0;
         }
+        const bool second_range = kTri && half_mode && s2e > s2b;  // warp-uniform
         const uint32_t unfinished = __ballot_sync(0xffffffffu, my_open);
         // the finished staircases of the batch's trees (pcg_leaf_stairs): terms and boundaries word by word (the rows
         // in shared memory are padded), the rest by one thread per tree
@@ -792,14 +828,17 @@ pcg_rows_kernel(int n, int row0, int words_per_row, BucketShape bs, int stride,
             const uint32_t open = unfinished >> first;
             const int stop = open != 0 ? first + __ffs(open) : batch;
             visit_trees(tb, first, stop, my_ptr, my_end, lane, slot0, entries, accW, accC);
+            if (second_range) visit_trees(tb, first, stop, my_ptr2, my_end2, lane, slot0, entries, accW, accC);
             if (open != 0) {
                 const int eu = stop - 1;
                 const int ptr = __shfl_sync(0xffffffffu, my_ptr, eu), end = __shfl_sync(0xffffffffu, my_end, eu);
+                const int ptr2 = __shfl_sync(0xffffffffu, my_ptr2, eu), end2 = __shfl_sync(0xffffffffu, my_end2, eu);
                 while (tb.resume[eu][0] >= 0 || tb.resume[eu][1] >= 0) {
                     __syncthreads();  // everybody has read resume[] and is done with the tree's segments
                     if (tid < 2) walk_chain(tb, eu, tid, false, links);
                     __syncthreads();
                     visit_bucket(tb, eu, ptr, end, lane, slot0, entries, accW, accC);
+                    if (second_range) visit_bucket(tb, eu, ptr2, end2, lane, slot0, entries, accW, accC);
                 }
             }
             first = stop;
@@ -814,10 +853,11 @@ pcg_rows_kernel(int n, int row0, int words_per_row, BucketShape bs, int stride,
     double *Wrow = W + w_row + col0;
     double *Wnode = W + (w_row - static_cast<size_t>(a_loc) * n);  // triangle mode: row 0 of the node's matrix
     for (int c = tid; c < ncols; c += nthreads) {
-        if (kTri && col0 + c < a_loc) continue;  // written, as its mirror image, by the CTA of that row
+        // partial rows: only what this CTA computed (and the zero on the diagonal); the rest arrives as a mirror image
+        if (kTri && !((c >= r1b && c < r1e) || (c >= r2b && c < r2e) || col0 + c == a_loc)) continue;
         const double v = accW[slot_of(c)];
         Wrow[c] = v;
-        if (kTri && col0 + c > a_loc) Wnode[static_cast<size_t>(col0 + c) * n + a_loc] = v;
+        if (kTri && !half_mode && col0 + c > a_loc) Wnode[static_cast<size_t>(col0 + c) * n + a_loc] = v;
         if (kWriteC) C[w_row + col0 + c] = static_cast<int32_t>(accC[slot_of(c)]);
     }
     const int word0 = col0 >> 5;
@@ -874,7 +914,8 @@ __global__ void pcg_sum_degree_parts(int n, int row0, int row1, int nchunks, con
 constexpr int kMirrorWarps = 8;
 
 __global__ void __launch_bounds__(kMirrorWarps * 32)
-pcg_mirror_bits(int n, int words, int B, uint32_t *__restrict__ adj_bits, uint32_t *__restrict__ max_bits, BatchView view) {
+pcg_mirror_bits(int n, int words, int B, int both, uint32_t *__restrict__ adj_bits, uint32_t *__restrict__ max_bits,
+                BatchView view) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int J = blockIdx.x;
     if (view.nodes) {
@@ -898,14 +939,24 @@ pcg_mirror_bits(int n, int words, int B, uint32_t *__restrict__ adj_bits, uint32
         uint32_t *bits = which == 0 ? adj_bits : max_bits;
         if (!bits) continue;
         const uint32_t mine = srow < n ? bits[static_cast<size_t>(srow) * words + J] : 0u;
-        uint32_t turned = 0u;
+        // both: either triangle may hold bits (half-window rows of a shared node): the symmetric closure
+        const uint32_t theirs = both && I < J && rowJ < n ? bits[static_cast<size_t>(rowJ) * words + I] : 0u;
+        uint32_t turned = 0u, turned_back = 0u;
 #pragma unroll
         for (int rp = 0; rp < 32; ++rp) {
             const uint32_t b = __ballot_sync(0xffffffffu, (mine >> rp) & 1u);
             if (lane == rp) turned = b;
         }
+        if (both && I < J) {
+#pragma unroll
+            for (int rp = 0; rp < 32; ++rp) {
+                const uint32_t b = __ballot_sync(0xffffffffu, (theirs >> rp) & 1u);
+                if (lane == rp) turned_back = b;
+            }
+            if (srow < n) bits[static_cast<size_t>(srow) * words + J] = mine | turned_back;
+        }
         if (rowJ < n) {
-            if (I < J) bits[static_cast<size_t>(rowJ) * words + I] = turned;
+            if (I < J) bits[static_cast<size_t>(rowJ) * words + I] = theirs | turned;
             else bits[static_cast<size_t>(rowJ) * words + J] = mine | turned;  // srow == rowJ: its own upper bits
         }
     }
@@ -941,8 +992,60 @@ pcg_degree_rows(int n, int R, int cols_per_chunk, const double *__restrict__ W, 
     if (lane == 0) degree[row] = total;
 }
 
+// Half-window row blocks, second half: element (a, c) of this rank's rows that lies in the window of row c rather than
+// of row a was computed by the owner of row c as (c, a).  One warp per 32 x 32 tile: the source rows are read from
+// the owners' blocks (over NVLink for a peer; 256 contiguous bytes per row), turned in shared memory, and stored.
+struct PeerBlocks {
+    const double *W[kMaxPeers];
+    int rows_per_rank;
+};
+
+__device__ __forceinline__ bool in_half_window(int n, int from, int to) {  // is column `to` in the window of row `from`
+    int d = to - from;
+    if (d < 0) d += n;
+    const int h = (n - 1) / 2 + (((n & 1) == 0 && from < n / 2) ? 1 : 0);
+    return d >= 1 && d <= h;
+}
+
+constexpr size_t kFetchSmem = sizeof(double) * kMirrorWarps * 32 * 33;
+
+__global__ void __launch_bounds__(kMirrorWarps * 32)
+pcg_fetch_transposed_kernel(int n, int row0, int row1, PeerBlocks peers, double *__restrict__ W_block) {
+    extern __shared__ __align__(16) unsigned char fetch_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double(*tile)[33] = reinterpret_cast<double(*)[33]>(fetch_raw) + static_cast<size_t>(warp) * 32;
+    const int a0 = row0 + (static_cast<int>(blockIdx.x) << 5);
+    const int c0 = (static_cast<int>(blockIdx.y) * kMirrorWarps + warp) << 5;
+    if (c0 >= n) return;
+    // is anything of this tile the other rows' part?  (corners do not decide it for a cyclic window: test every row)
+    bool any = false;
+    const int a_mine = a0 + lane;
+    for (int r = 0; r < 32; ++r) {
+        const int c = c0 + r;
+        const bool need = c < n && a_mine < row1 && in_half_window(n, c, a_mine);
+        const unsigned mask = __ballot_sync(0xffffffffu, need);
+        if (mask) {
+            any = true;
+            if (need) {
+                const int owner = c / peers.rows_per_rank;
+                tile[r][lane] = peers.W[owner][static_cast<size_t>(c - owner * peers.rows_per_rank) * n + a_mine];
+            }
+        }
+    }
+    if (!any) return;  // warp-uniform
+    __syncwarp();
+    const int c_mine = c0 + lane;
+    for (int ra = 0; ra < 32; ++ra) {
+        const int a = a0 + ra;
+        if (a >= row1) break;
+        if (c_mine < n && in_half_window(n, c_mine, a))
+            W_block[static_cast<size_t>(a - row0) * n + c_mine] = tile[lane][ra];
+    }
+}
+
 template <typename CountT, bool kWriteC, typename EntryT, bool kTri>
-int launch_rows(scs_ctx *ctx, int n, int row0, int nrows, int words, BucketShape bs, int stride, int nchunks, size_t smem,
+int launch_rows(scs_ctx *ctx, int n, int row0, int nrows, int words, BucketShape bs, int stride, int half_mode, int nchunks,
+                size_t smem,
                 const int64_t *leaf_offsets, const LinkEntry *links, const double *tree_weight,
                 const int32_t *leaf_tree, const int32_t *row_ptr, const int32_t *inv_sorted,
                 const int32_t *occ, const int32_t *bucket_ptr, const void *entries, const LeafStairs *stairs,
@@ -964,7 +1067,7 @@ int launch_rows(scs_ctx *ctx, int n, int row0, int nrows, int words, BucketShape
         profile_begin(ctx, PROFILE_PCG_ROWS, out_bytes, ctx->pending_units);
     }
     kernel<<<grid, 32 << bs.warps_log2, smem, ctx->stream>>>(
-        n, row0, words, bs, stride, leaf_offsets, links, tree_weight, leaf_tree, row_ptr, inv_sorted, occ, bucket_ptr,
+        n, row0, words, bs, stride, half_mode, leaf_offsets, links, tree_weight, leaf_tree, row_ptr, inv_sorted, occ, bucket_ptr,
         static_cast<const EntryT *>(entries), stairs, start16, W, C, adj_bits, max_bits, degree_part, bad, batch);
     if (n >= kProfileMinSize && !batch.nodes) profile_end(ctx);
     SCS_LAUNCHED(ctx, "pcg_rows_kernel");
@@ -1082,14 +1185,65 @@ int launch_mirror(scs_ctx *ctx, int n, int words, int cols_per_chunk, int total_
                   const double *W, uint32_t *adj_bits, uint32_t *max_bits, double *degree, const BatchView &batch) {
     if (total_blocks <= 0 || R <= 0) return SCS_OK;
     dim3 grid(total_blocks, ceil_div(max_blocks, kMirrorWarps));
-    pcg_mirror_bits<<<grid, kMirrorWarps * 32, 0, ctx->stream>>>(n, words, B, adj_bits, max_bits, batch);
+    pcg_mirror_bits<<<grid, kMirrorWarps * 32, 0, ctx->stream>>>(n, words, B, 0, adj_bits, max_bits, batch);
     SCS_LAUNCHED(ctx, "pcg_mirror_bits");
     pcg_degree_rows<<<ceil_div(R, kMirrorWarps), kMirrorWarps * 32, 0, ctx->stream>>>(n, R, cols_per_chunk, W, degree, batch);
     SCS_LAUNCHED(ctx, "pcg_degree_rows");
     return SCS_OK;
 }
 
+// column chunking of the row kernel: the whole row if it fits in shared memory, else equal chunks of 32-multiples
+int chunk_columns(const scs_ctx *ctx, int n, int T) {
+    const bool narrow = T < 65536;
+    const size_t per_col = sizeof(double) + (narrow ? sizeof(uint16_t) : sizeof(int32_t));
+    const size_t budget = ctx->smem_optin > 2 * kRowsStaticSmem ? ctx->smem_optin - kRowsStaticSmem : 32 * 1024;
+    const int warps = 16;
+    const size_t row_static = sizeof(TreeBatch) + 256;  // + warp_sum, alignment
+    const size_t half_sm = ctx->smem_per_sm > 4 * kRowsStaticSmem ? ctx->smem_per_sm / 2 - 1024 - row_static : budget;
+    const size_t chunk_budget = half_sm < budget ? half_sm : budget;
+    const int max_cols = static_cast<int>(((chunk_budget - 16) / per_col - 2 * warps) / 32 * 32);
+    const int padded = scs_bit_words(n) * 32;
+    const int nchunks = ceil_div(padded, max_cols);
+    return ceil_div(ceil_div(padded, nchunks), 32) * 32;
+}
+
 }  // namespace
+
+int pcg_fetch_transposed(scs_ctx *ctx, int n, RowBlock rows, int rows_per_rank, int world, const double *const *peer_W,
+                         double *W_block) {
+    const int nrows = rows.row1 - rows.row0;
+    if (nrows <= 0) return SCS_OK;
+    if (world > kMaxPeers || rows_per_rank <= 0) return fail(ctx, SCS_ERR_INVALID, "pcg_fetch_transposed: bad argument");
+    PeerBlocks peers;
+    for (int r = 0; r < kMaxPeers; ++r) peers.W[r] = r < world ? peer_W[r] : nullptr;
+    peers.rows_per_rank = rows_per_rank;
+    if (!ctx->mirror_configured) {
+        SCS_CUDA(ctx, cudaFuncSetAttribute(pcg_fetch_transposed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(kFetchSmem)));
+        ctx->mirror_configured = true;
+    }
+    dim3 grid(ceil_div(nrows, 32), ceil_div(ceil_div(n, 32), kMirrorWarps));
+    pcg_fetch_transposed_kernel<<<grid, kMirrorWarps * 32, kFetchSmem, ctx->stream>>>(n, rows.row0, rows.row1, peers, W_block);
+    SCS_LAUNCHED(ctx, "pcg_fetch_transposed_kernel");
+    return SCS_OK;
+}
+
+int pcg_symmetrize_bits(scs_ctx *ctx, int n, uint32_t *adj_bits, uint32_t *max_bits) {
+    const int words = scs_bit_words(n);
+    dim3 grid(words, ceil_div(words, kMirrorWarps));
+    pcg_mirror_bits<<<grid, kMirrorWarps * 32, 0, ctx->stream>>>(n, words, 1, 1, adj_bits, max_bits, BatchView());
+    SCS_LAUNCHED(ctx, "pcg_mirror_bits");
+    return SCS_OK;
+}
+
+int pcg_degree_block(scs_ctx *ctx, int n, int T, RowBlock rows, const double *W_block, double *degree) {
+    const int nrows = rows.row1 - rows.row0;
+    if (nrows <= 0) return SCS_OK;
+    pcg_degree_rows<<<ceil_div(nrows, kMirrorWarps), kMirrorWarps * 32, 0, ctx->stream>>>(n, nrows, chunk_columns(ctx, n, T), W_block,
+                                                                                        degree + rows.row0, BatchView());
+    SCS_LAUNCHED(ctx, "pcg_degree_rows");
+    return SCS_OK;
+}
 
 int pcg_build(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offsets,
               const int32_t *leaf_taxon, const int32_t *adj_depth, const double *adj_val,
@@ -1152,21 +1306,14 @@ int pcg_build(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offsets
     // chunk the columns are dealt out to the CTA's warps (slot = warp * stride + column / warps)
     const bool narrow = T < 65536;
     const size_t per_col = sizeof(double) + (narrow ? sizeof(uint16_t) : sizeof(int32_t));
-    const size_t budget = ctx->smem_optin > 2 * kRowsStaticSmem ? ctx->smem_optin - kRowsStaticSmem : 32 * 1024;
     BucketShape bs;
     bs.warps_log2 = 4;
     const int warps = 1 << bs.warps_log2;
     // two CTAs per SM hide each other's latencies: a chunk gets at most half an SM's shared memory (a chunk CTA
-    // reads only its own share of every tree, so more chunks cost little)
-    const size_t row_static = sizeof(TreeBatch) + 256;  // + warp_sum, alignment
-    const size_t half_sm = ctx->smem_per_sm > 4 * kRowsStaticSmem ? ctx->smem_per_sm / 2 - 1024 - row_static : budget;
-    const size_t chunk_budget = half_sm < budget ? half_sm : budget;
-    // slots = warps * stride <= cols + 2 * warps (stride rounded up and made odd)
-    const int max_cols = static_cast<int>(((chunk_budget - 16) / per_col - 2 * warps) / 32 * 32);
-    const int padded = words * 32;
-    int nchunks = ceil_div(padded, max_cols);
-    bs.cols_per_chunk = ceil_div(ceil_div(padded, nchunks), 32) * 32;
-    nchunks = ceil_div(n, bs.cols_per_chunk);
+    // reads only its own share of every tree, so more chunks cost little); slots = warps * stride <= cols + 2 * warps
+    // (stride rounded up and made odd)
+    bs.cols_per_chunk = chunk_columns(ctx, n, T);
+    const int nchunks = ceil_div(n, bs.cols_per_chunk);
     bs.buckets = nchunks * warps;
     const int stride = ceil_div(bs.cols_per_chunk, warps) | 1;  // odd: the write-out reads a column per lane
     const size_t smem = static_cast<size_t>(stride) * warps * per_col + 16;
@@ -1184,6 +1331,8 @@ int pcg_build(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offsets
     // every pair once (upper triangle + mirror) unless the rows are one rank's block of a sharded node (the other
     // triangle lives on the peers) or the caller wants the co-occurrence matrix as well
     const bool tri = !rows.sharded() && C == nullptr && !ctx->full_rows;
+    // ... or, for a row block, the cyclic half window of every row (the caller completes the block from the peers')
+    const bool half = rows.sharded() && rows.half_window && C == nullptr && !ctx->full_rows;
     int32_t *start16 = nullptr;
     if (tri && (rc = reserve_as(ctx, SLOT_START16, (static_cast<size_t>(L) + 1) * kWarps, &start16))) return rc;
     if ((rc = build_buckets(ctx, n, T, L, bs, stride, packed, leaf_offsets, leaf_taxon, bucket_ptr, entries, start16, scalars,
@@ -1199,16 +1348,18 @@ int pcg_build(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offsets
     }
 
 #define SCS_ROWS(CT, WC, ET, TRI)                                                                                        \
-    launch_rows<CT, WC, ET, TRI>(ctx, n, row0, nrows, words, bs, stride, nchunks, smem, leaf_offsets, links, tree_weight, \
+    launch_rows<CT, WC, ET, TRI>(ctx, n, row0, nrows, words, bs, stride, half ? 1 : 0, nchunks, smem, leaf_offsets, links,  \
+                                 tree_weight,                                                                            \
                                  leaf_tree, row_ptr, inv_sorted, occ, bucket_ptr, entries, stairs, start16, W, C, adj_bits, \
                                  max_bits, degree_part, scalars)
 #define SCS_ROWS_E(CT, WC, TRI) (packed ? SCS_ROWS(CT, WC, uint32_t, TRI) : SCS_ROWS(CT, WC, unsigned long long, TRI))
-    if (tri) rc = narrow ? SCS_ROWS_E(uint16_t, false, true) : SCS_ROWS_E(int32_t, false, true);
+    if (tri || half) rc = narrow ? SCS_ROWS_E(uint16_t, false, true) : SCS_ROWS_E(int32_t, false, true);
     else if (narrow) rc = C ? SCS_ROWS_E(uint16_t, true, false) : SCS_ROWS_E(uint16_t, false, false);
     else rc = C ? SCS_ROWS_E(int32_t, true, false) : SCS_ROWS_E(int32_t, false, false);
 #undef SCS_ROWS_E
 #undef SCS_ROWS
     if (rc) return rc;
+    if (half) return SCS_OK;  // W, the bits and the degrees are completed by the caller once every rank is this far
     if (tri) {
         // the other triangle of W and of the bit matrices, and the row sums (into `degree`, or a scratch if unwanted)
         return launch_mirror(ctx, n, words, bs.cols_per_chunk, words, words, 1, n, W, adj_bits, max_bits,
@@ -1297,12 +1448,12 @@ int pcg_build_batch(scs_ctx *ctx, int B, int blocks, int R, int T, int64_t L, in
     if (!ctx->full_rows) {
         // every pair once: the upper triangles, then the mirror (which also writes the row sums into `degree`)
         if (narrow)
-            rc = launch_rows<uint16_t, false, uint32_t, true>(ctx, R, 0, R, 0, bs, stride, 1, smem, leaf_offsets, links,
+            rc = launch_rows<uint16_t, false, uint32_t, true>(ctx, R, 0, R, 0, bs, stride, 0, 1, smem, leaf_offsets, links,
                                                               tree_weight, leaf_tree, row_ptr, inv_sorted, occ, bucket_ptr,
                                                               entries, stairs, start16, W, nullptr, adj_bits, max_bits, degree,
                                                               bad_dev, batch);
         else
-            rc = launch_rows<int32_t, false, uint32_t, true>(ctx, R, 0, R, 0, bs, stride, 1, smem, leaf_offsets, links,
+            rc = launch_rows<int32_t, false, uint32_t, true>(ctx, R, 0, R, 0, bs, stride, 0, 1, smem, leaf_offsets, links,
                                                              tree_weight, leaf_tree, row_ptr, inv_sorted, occ, bucket_ptr,
                                                              entries, stairs, start16, W, nullptr, adj_bits, max_bits, degree,
                                                              bad_dev, batch);
@@ -1311,11 +1462,11 @@ int pcg_build_batch(scs_ctx *ctx, int B, int blocks, int R, int T, int64_t L, in
     }
     // the row kernel writes the row sums straight into `degree` (one chunk: degree_part[0][row])
     if (narrow)
-        rc = launch_rows<uint16_t, false, uint32_t, false>(ctx, R, 0, R, 0, bs, stride, 1, smem, leaf_offsets, links, tree_weight,
+        rc = launch_rows<uint16_t, false, uint32_t, false>(ctx, R, 0, R, 0, bs, stride, 0, 1, smem, leaf_offsets, links, tree_weight,
                                                     leaf_tree, row_ptr, inv_sorted, occ, bucket_ptr, entries, stairs, start16,
                                                            W, nullptr, adj_bits, max_bits, degree, bad_dev, batch);
     else
-        rc = launch_rows<int32_t, false, uint32_t, false>(ctx, R, 0, R, 0, bs, stride, 1, smem, leaf_offsets, links, tree_weight,
+        rc = launch_rows<int32_t, false, uint32_t, false>(ctx, R, 0, R, 0, bs, stride, 0, 1, smem, leaf_offsets, links, tree_weight,
                                                    leaf_tree, row_ptr, inv_sorted, occ, bucket_ptr, entries, stairs, start16,
                                                           W, nullptr, adj_bits, max_bits, degree, bad_dev, batch);
     return rc;

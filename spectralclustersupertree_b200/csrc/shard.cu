@@ -146,7 +146,7 @@ int node_split_sharded(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *lea
     ShardState &sh = ctx->shard;
     const ShardLayout &lay = sh.layout;
     const int words = scs_bit_words(n);
-    const RowBlock rows = shard_block(n, sh.rank, sh.world);
+    RowBlock rows = shard_block(n, sh.rank, sh.world);
     const int nrows = rows.row1 - rows.row0;
     double *W = reinterpret_cast<double *>(sh.window + lay.W);
     double *degree = reinterpret_cast<double *>(sh.window + lay.degree);
@@ -180,12 +180,24 @@ int node_split_sharded(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *lea
 
     // nobody may still be reading this rank's window (W rows, bits) from the previous node
     if ((rc = shard_barrier(ctx))) return rc;
+    // Every pair of the node once over all ranks: a row computes the cyclic half window of columns after its own
+    // (pcg.cu, RowBlock::half_window); the other half of a row is the mirror image of what the owners of those rows
+    // computed, fetched from their blocks once everybody is that far.  (scs_ctx_set_full_rows: every row in full.)
+    rows.half_window = !ctx->full_rows;
     if ((rc = pcg_build(ctx, n, T, L, leaf_offsets, leaf_taxon, adj_depth, adj_val, root_depth, tree_weight, W, nullptr,
                         occ, adj_bits, contract_edges ? max_bits : nullptr, degree, rows)))
         return rc;
     const size_t row_bits = static_cast<size_t>(words) * sizeof(uint32_t);
     if ((rc = shard_push(ctx, lay.adj_bits + rows.row0 * row_bits, nrows * row_bits))) return rc;
     if (contract_edges && (rc = shard_push(ctx, lay.max_bits + rows.row0 * row_bits, nrows * row_bits))) return rc;
+    if (rows.half_window) {
+        if ((rc = shard_barrier(ctx))) return rc;  // every rank's half rows and bit rows are in place
+        const double *peer_W[kMaxPeers] = {};
+        for (int r = 0; r < sh.world; ++r) peer_W[r] = reinterpret_cast<const double *>(sh.peer[r] + lay.W);
+        if ((rc = pcg_fetch_transposed(ctx, n, rows, shard_rows_per_rank(n, sh.world), sh.world, peer_W, W))) return rc;
+        if ((rc = pcg_symmetrize_bits(ctx, n, adj_bits, contract_edges ? max_bits : nullptr))) return rc;
+        if ((rc = pcg_degree_block(ctx, n, T, rows, W, degree))) return rc;
+    }
     if ((rc = shard_push(ctx, lay.degree + sizeof(double) * rows.row0, sizeof(double) * nrows))) return rc;
     if ((rc = shard_barrier(ctx))) return rc;
 

@@ -353,6 +353,10 @@ class Engine:
             "degree": self.alloc(8 * n),
         }  # fmt: skip
         try:
+            # poison the outputs: an entry the build forgets to write must not look right by accident
+            poison = np.full(n * max(n, words) * 8, 0xFF, dtype=np.uint8)
+            for key, nbytes in (("W", 8 * n * n), ("adj_bits", 4 * n * words), ("max_bits", 4 * n * words), ("degree", 8 * n)):
+                _check(self._lib.scs_memcpy_h2d(self._ctx, bufs[key], ptr(poison), nbytes), self._ctx)
             status = self._lib.scs_pcg_build_dev(
                 self._ctx, n, dev["T"], dev["L"], dev["leaf_offsets"], dev["leaf_taxon"], dev["adj_depth"],
                 dev["adj_val"], dev["root_depth"], dev["tree_weight"], bufs["W"], bufs["C"], bufs["occ"],
