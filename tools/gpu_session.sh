@@ -43,7 +43,7 @@ for stage in "$@"; do
       # N = $GPUS ranks on one box: the bench line, c5 through the product path, tree-sharded W + all-reduce beside row sharding
       N=${GPUS:-2}
       python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/${tag}_bench_c4_n$N.json 2> gpurun_out/${tag}_bench_c4_n$N.err; echo "bench c4 n$N rc=$?"; head -c 400 gpurun_out/${tag}_bench_c4_n$N.json; tail -3 gpurun_out/${tag}_bench_c4_n$N.err
-      python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 tools/tree_sharded_allreduce.py c4 > gpurun_out/${tag}_treeshard_c4_n$N.json 2> gpurun_out/${tag}_treeshard_c4_n$N.err; echo "treeshard n$N rc=$?"; cut -c1-600 gpurun_out/${tag}_treeshard_c4_n$N.json
+      [ -z "${SKIP_TREESHARD:-}" ] && python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 tools/tree_sharded_allreduce.py c4 > gpurun_out/${tag}_treeshard_c4_n$N.json 2> gpurun_out/${tag}_treeshard_c4_n$N.err; echo "treeshard n$N rc=$?"; cut -c1-600 gpurun_out/${tag}_treeshard_c4_n$N.json
       if [ -z "${SKIP_C5:-}" ]; then
         python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 tools/run_workload.py c5 --repeat 2 --out gpurun_out/${tag}_c5_n$N.json > gpurun_out/${tag}_c5_n$N.log 2>&1; echo "c5 n$N rc=$?"; cut -c1-700 gpurun_out/${tag}_c5_n$N.json; tail -3 gpurun_out/${tag}_c5_n$N.log
       fi ;;
