@@ -518,12 +518,13 @@ def gpu_line(args, arrays: dict) -> dict:
             "l2": "flushed between timed steps (256 MB write); the top-level W (0.8 GB) exceeds L2 by itself",
             "value_is": "the whole recursion from source trees already resident in HBM (scs_supertree_build_resident: tours, "
                         "node splits and tree restriction on the device, wave by wave; per wave the nodes > 4096 taxa one "
-                        "by one, the nodes of 65..4096 taxa as one batch, the nodes <= 64 taxa in one launch); CUDA "
+                        "by one, the nodes of 33..4096 taxa as one batch, the nodes <= 32 taxa in one launch); CUDA "
                         "events around the build; max over ranks",
             "e2e_is": "scs_forest_create + scs_supertree_build over the C ABI from flat host arrays to the flat "
                       "supertree (wall clock: validation of the trees, H2D of the forest, the recursion as in value, D2H "
                       "of partitions and bookkeeping; for N > 1 recursion nodes with >= --shard-min-n taxa are "
-                      "row-sharded over the GPUs (fused matvec + all-gather over NVLink peer windows), smaller "
+                      "row-sharded over the GPUs (every leaf pair once over all ranks, the halves exchanged over NVLink; "
+                      "fused matvec + all-gather over peer windows), smaller "
                       "sub-problems are dealt out over the ranks and the outputs are all-gathered)",
             "e2e_host_seconds": host_split,
             "e2e_step_seconds": [round(x, 4) for x in e2e_s],
