@@ -178,7 +178,7 @@ struct scs_ctx {
     bool small_configured = false;
     bool batch_configured = false;
     bool tail_configured = false;
-    bool rows_configured[16] = {};
+    bool rows_configured[32] = {};
     bool mirror_configured = false;
     bool contract_configured = false;
     bool kmeans_configured = false;

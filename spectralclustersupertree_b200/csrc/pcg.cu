@@ -384,12 +384,10 @@ struct TreeHeader {
 // lies outside [low, high) is separated from the row's leaf by the root, or not reached yet.
 struct __align__(16) TreeBatch {
     TreeHeader header[kTreeBatch];
-    // rows padded by one element: a group of items spans a few trees, and the same segment of different trees must
-    // not fall on the same shared-memory bank
-    double term[kTreeBatch][kSlots + 1];
-    int32_t bound[kTreeBatch][kSlots + 1];
+    double term[kTreeBatch][kSlots];
+    int32_t bound[kTreeBatch][kSlots];
+    int32_t pivot[kTreeBatch][kSlots / 4];      // bound[4j + 3]: the first level of the segment search
     int32_t low[kTreeBatch], high[kTreeBatch];  // first / last boundary in use
-    uint32_t live[kTreeBatch];                  // bit idx: segment idx is in use (low <= idx < high, idx != kChain)
     int32_t resume[kTreeBatch][2];              // chain entry to continue from, or kNone
 };
 
@@ -511,6 +509,7 @@ __device__ void walk_chain(TreeBatch &tb, int e, int side, bool first, const Lin
         tb.high[e] = kChain + 1 + c;
         tb.resume[e][1] = i;
         for (int idx = kChain + 2 + c; idx < kSlots; ++idx) bound[idx] = kFar;
+        for (int j = kSlots / 8; j < kSlots / 4; ++j) tb.pivot[e][j] = bound[4 * j + 3];
     } else {
         int i;
         if (first) {
@@ -531,6 +530,7 @@ __device__ void walk_chain(TreeBatch &tb, int e, int side, bool first, const Lin
         tb.low[e] = kChain - c;
         tb.resume[e][0] = i;
         for (int idx = kChain - c - 1; idx >= 0; --idx) bound[idx] = -kFar;
+        for (int j = 0; j < kSlots / 8; ++j) tb.pivot[e][j] = bound[4 * j + 3];
     }
 }
 
@@ -551,25 +551,21 @@ __device__ __forceinline__ void bump(uint16_t *counts, int slot) {
     atomicAdd(reinterpret_cast<unsigned int *>(counts) + (slot >> 1), 1u << ((slot & 1) << 4));
 }
 __device__ __forceinline__ void bump(int32_t *counts, int slot) { atomicAdd(counts + slot, 1); }
-// the same, returning the count before the increment
-__device__ __forceinline__ int bump_fetch(uint16_t *counts, int slot) {
-    const int shift = (slot & 1) << 4;
-    const unsigned int old = atomicAdd(reinterpret_cast<unsigned int *>(counts) + (slot >> 1), 1u << shift);
-    return static_cast<int>((old >> shift) & 0xffffu);
-}
-__device__ __forceinline__ int bump_fetch(int32_t *counts, int slot) { return atomicAdd(counts + slot, 1); }
 
-// One warp, one tree (the further rounds of a tree whose chains did not fit kChain steps a side): every entry of the
-// warp's share gets its segment -- binary search over the tree's 32 ascending boundaries -- and, if the segment is
-// live, its term.
+// One warp, one tree: every entry of the warp's bucket gets its segment and, if the segment is live, its term.
+// Segment search over the tree's 32 ascending boundaries in two levels: 7 pivots (bound[3], bound[7], ...) held
+// in registers pick a block of four, one 16-byte shared load fetches the block (the whole warp reads one
+// 128-byte row: a single wavefront).
 template <typename CountT, typename EntryT>
 __device__ __forceinline__ void visit_bucket(const TreeBatch &tb, int e, int ptr, int end, int lane, int slot0,
                                              const EntryT *__restrict__ entries, double *accW, CountT *accC) {
     if (ptr >= end) return;
     const int low = tb.low[e], high = tb.high[e];
     if (low == kChain && high == kChain + 1) return;  // nothing but root-separated pairs
-    const int32_t *bnd = tb.bound[e];
+    const int4 *bound4 = reinterpret_cast<const int4 *>(tb.bound[e]);
     const double *term = tb.term[e];
+    const int4 pa = *reinterpret_cast<const int4 *>(&tb.pivot[e][0]);
+    const int4 pb = *reinterpret_cast<const int4 *>(&tb.pivot[e][4]);
     EntryT en = ptr + lane < end ? entries[ptr + lane] : EntryT(0);
     for (int i = ptr; i < end; i += 32) {
         const bool live = i + lane < end;
@@ -578,11 +574,9 @@ __device__ __forceinline__ void visit_bucket(const TreeBatch &tb, int e, int ptr
         int q, slot;
         unpack(cur, q, slot);
         slot += slot0;  // the warp's slots start at slot0
-        int idx = bnd[16] < q ? 16 : 0;  // the last boundary below q (bound[0] always is)
-        idx += bnd[idx + 8] < q ? 8 : 0;
-        idx += bnd[idx + 4] < q ? 4 : 0;
-        idx += bnd[idx + 2] < q ? 2 : 0;
-        idx += bnd[idx + 1] < q ? 1 : 0;
+        const int blk = (pa.x < q) + (pa.y < q) + (pa.z < q) + (pa.w < q) + (pb.x < q) + (pb.y < q) + (pb.z < q);
+        const int4 b = bound4[blk];
+        const int idx = 4 * blk - 1 + (b.x < q) + (b.y < q) + (b.z < q) + (b.w < q);  // bound[0] < q always
         if (live && idx >= low && idx < high && idx != kChain) {
             accW[slot] = __dadd_rn(accW[slot], term[idx]);
             bump(accC, slot);
@@ -638,31 +632,26 @@ __device__ __forceinline__ void visit_trees(const TreeBatch &tb, int first, int 
             const int e = tree[d];
             int q, slot;
             unpack(en[d], q, slot);
-            // the segment of position q: the last of the tree's 32 ascending boundaries below q (bound[0] is), by a
-            // binary search with 4-byte loads (a 16-byte load costs four passes through the shared-memory pipe even
-            // when the whole warp reads the same words; these five cost one each)
-            const int32_t *bnd = tb.bound[e];
-            int idx = bnd[16] < q ? 16 : 0;
-            idx += bnd[idx + 8] < q ? 8 : 0;
-            idx += bnd[idx + 4] < q ? 4 : 0;
-            idx += bnd[idx + 2] < q ? 2 : 0;
-            idx += bnd[idx + 1] < q ? 1 : 0;
-            const bool hit = j0 + 32 * d + lane < total && ((tb.live[e] >> idx) & 1u);
+            const int4 pa = *reinterpret_cast<const int4 *>(&tb.pivot[e][0]);
+            const int4 pb = *reinterpret_cast<const int4 *>(&tb.pivot[e][4]);
+            const int blk = (pa.x < q) + (pa.y < q) + (pa.z < q) + (pa.w < q) + (pb.x < q) + (pb.y < q) + (pb.z < q);
+            const int4 b = reinterpret_cast<const int4 *>(tb.bound[e])[blk];
+            const int idx = 4 * blk - 1 + (b.x < q) + (b.y < q) + (b.z < q) + (b.w < q);  // bound[0] < q always
+            const bool hit = j0 + 32 * d + lane < total && idx >= tb.low[e] && idx < tb.high[e] && idx != kChain;
             const double term = hit ? tb.term[e][idx] : 0.0;
-            const int at = slot0 + slot;
-            // Counts first, each lane learning the count it found.  Two lanes of the group on the same column (they
-            // come from different trees) then see a final count that is not theirs + 1: only in that case do the
-            // trees of the group have to be applied one after the other.
-            int found = 0;
-            if (hit) found = bump_fetch(accC, at);
-            __syncwarp();
-            const bool shared_column = hit && static_cast<int>(accC[at]) != found + 1;
-            if (!__any_sync(kAll, shared_column)) {
-                if (hit) accW[at] = __dadd_rn(accW[at], term);
+            // the items of one tree are distinct columns; the trees of the group one after the other, in order
+            const int e_first = __shfl_sync(kAll, e, 0), e_last = __reduce_max_sync(kAll, e);
+            if (e_first == e_last) {
+                if (hit) {
+                    accW[slot0 + slot] = __dadd_rn(accW[slot0 + slot], term);
+                    bump(accC, slot0 + slot);
+                }
             } else {
-                const int e_first = __shfl_sync(kAll, e, 0), e_last = __reduce_max_sync(kAll, e);
                 for (int t = e_first; t <= e_last; ++t) {
-                    if (hit && e == t) accW[at] = __dadd_rn(accW[at], term);
+                    if (hit && e == t) {
+                        accW[slot0 + slot] = __dadd_rn(accW[slot0 + slot], term);
+                        bump(accC, slot0 + slot);
+                    }
                     __syncwarp();
                 }
             }
@@ -675,9 +664,9 @@ __device__ __forceinline__ void visit_trees(const TreeBatch &tb, int first, int 
 // visited once instead of twice) and writes that part of the row and its mirror image; pcg_mirror_bits and
 // pcg_degree_rows complete the bit rows and sum the rows.  The entries of a bucket ascend by column, so each warp finds where its share of a
 // tree starts with a binary search (one lane per tree of the batch, while the first warps walk the chains).
-template <typename CountT, bool kWriteC, typename EntryT, bool kTri>
+template <typename CountT, bool kWriteC, typename EntryT, bool kTri, bool kHalf>
 __global__ void __launch_bounds__(kRowThreads, 2)
-pcg_rows_kernel(int n, int row0, int words_per_row, BucketShape bs, int stride, int half_mode,
+pcg_rows_kernel(int n, int row0, int words_per_row, BucketShape bs, int stride,
                 const int64_t *__restrict__ leaf_offsets, const LinkEntry *__restrict__ links,
                 const double *__restrict__ tree_weight, const int32_t *__restrict__ leaf_tree,
                 const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ inv_sorted,
@@ -723,6 +712,8 @@ pcg_rows_kernel(int n, int row0, int words_per_row, BucketShape bs, int stride, 
     //   h = (n - 1) / 2, one more for the rows of the first half when n is even -- of every pair {a, c} exactly
     //   one of the two rows has the other in its window, every row does half its pairs, and nothing depends on how
     //   the rows are dealt to the ranks; the owners exchange the other half afterwards (pcg_fetch_transposed).
+    constexpr bool half_mode = kHalf;  // compiled separately: the one-GPU kernel carries none of the window logic
+    static_assert(kTri || !kHalf, "half windows are partial rows");
     int r1b = 0, r1e = 0, r2b = 0, r2e = 0;
     if (kTri) {
         int e1 = n, e2 = 0;
@@ -790,35 +781,29 @@ pcg_rows_kernel(int n, int row0, int words_per_row, BucketShape bs, int stride, 
         }
         const bool second_range = kTri && half_mode && s2e > s2b;  // warp-uniform
         const uint32_t unfinished = __ballot_sync(0xffffffffu, my_open);
-        // the finished staircases of the batch's trees (pcg_leaf_stairs): terms and boundaries word by word (the rows
-        // in shared memory are padded), the rest by one thread per tree
-        const int32_t *stairs32 = reinterpret_cast<const int32_t *>(stairs);
-        constexpr int kStairsWords = sizeof(LeafStairs) / 4, kCopyWords = 3 * kSlots;  // 64 words of terms, 32 of bounds
-        for (int idx = tid; idx < batch * kCopyWords; idx += nthreads) {
-            const int e = idx / kCopyWords, k = idx - e * kCopyWords;
+        // the finished staircases of the batch's trees (pcg_leaf_stairs): 28 int4 each, coalesced
+        for (int idx = tid; idx < batch * kStairsInt4; idx += nthreads) {
+            const int e = idx / kStairsInt4, k = idx - e * kStairsInt4;
             const int g = inv_sorted[ebase + e0 + e];
-            const int32_t v = stairs32[static_cast<size_t>(g) * kStairsWords + k];
-            if (k < 2 * kSlots) reinterpret_cast<int32_t *>(tb.term[e])[k] = v;
-            else tb.bound[e][k - 2 * kSlots] = v;
-        }
-        if (tid < batch) {
-            const int e = tid;
-            const int g = inv_sorted[ebase + e0 + e];
-            const int4 shape = stairs4[static_cast<size_t>(g) * kStairsInt4 + 26];  // low, high, resume0, resume1
-            const int4 info = stairs4[static_cast<size_t>(g) * kStairsInt4 + 27];   // leaves, position, tree
-            tb.low[e] = shape.x;
-            tb.high[e] = shape.y;
-            tb.resume[e][0] = shape.z;
-            tb.resume[e][1] = shape.w;
-            tb.live[e] = (((1u << shape.y) - 1u) & ~((1u << shape.x) - 1u)) & ~(1u << kChain);  // high <= 31
-            TreeHeader h;  // only the continuation rounds of an unfinished chain read it
-            h.leaves = info.x;
-            h.position = info.y;
-            h.tree = info.z;
-            h.pad = 0;
-            h.base = leaf_offsets[info.z];
-            h.weight = tree_weight[info.z];
-            tb.header[e] = h;
+            const int4 v = stairs4[static_cast<size_t>(g) * kStairsInt4 + k];
+            if (k < 16) reinterpret_cast<int4 *>(tb.term[e])[k] = v;
+            else if (k < 24) reinterpret_cast<int4 *>(tb.bound[e])[k - 16] = v;
+            else if (k < 26) reinterpret_cast<int4 *>(tb.pivot[e])[k - 24] = v;
+            else if (k == 26) {
+                tb.low[e] = v.x;
+                tb.high[e] = v.y;
+                tb.resume[e][0] = v.z;
+                tb.resume[e][1] = v.w;
+            } else {
+                TreeHeader h;  // only the continuation rounds of an unfinished chain read it
+                h.leaves = v.x;
+                h.position = v.y;
+                h.tree = v.z;
+                h.pad = 0;
+                h.base = leaf_offsets[v.z];
+                h.weight = tree_weight[v.z];
+                tb.header[e] = h;
+            }
         }
         __syncthreads();
         // Every warp goes through the trees in input order on its own: no barrier between trees.  A tree whose
@@ -1043,18 +1028,17 @@ pcg_fetch_transposed_kernel(int n, int row0, int row1, PeerBlocks peers, double 
     }
 }
 
-template <typename CountT, bool kWriteC, typename EntryT, bool kTri>
-int launch_rows(scs_ctx *ctx, int n, int row0, int nrows, int words, BucketShape bs, int stride, int half_mode, int nchunks,
-                size_t smem,
+template <typename CountT, bool kWriteC, typename EntryT, bool kTri, bool kHalf = false>
+int launch_rows(scs_ctx *ctx, int n, int row0, int nrows, int words, BucketShape bs, int stride, int nchunks, size_t smem,
                 const int64_t *leaf_offsets, const LinkEntry *links, const double *tree_weight,
                 const int32_t *leaf_tree, const int32_t *row_ptr, const int32_t *inv_sorted,
                 const int32_t *occ, const int32_t *bucket_ptr, const void *entries, const LeafStairs *stairs,
                 const int32_t *start16, double *W, int32_t *C,
                 uint32_t *adj_bits, uint32_t *max_bits, double *degree_part, int32_t *bad, BatchView batch = BatchView()) {
-    auto kernel = pcg_rows_kernel<CountT, kWriteC, EntryT, kTri>;
+    auto kernel = pcg_rows_kernel<CountT, kWriteC, EntryT, kTri, kHalf>;
     // always the same (maximal) opt-in size: contexts on other host threads launch this kernel concurrently
     bool &configured = ctx->rows_configured[(sizeof(CountT) == 2 ? 0 : 2) + (kWriteC ? 1 : 0) +
-                                            (sizeof(EntryT) == 4 ? 0 : 4) + (kTri ? 8 : 0)];
+                                            (sizeof(EntryT) == 4 ? 0 : 4) + (kTri ? 8 : 0) + (kHalf ? 16 : 0)];
     if (!configured) {
         const size_t optin = ctx->smem_optin > 2 * kRowsStaticSmem ? ctx->smem_optin - kRowsStaticSmem : 32 * 1024;
         SCS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(optin)));
@@ -1067,7 +1051,7 @@ int launch_rows(scs_ctx *ctx, int n, int row0, int nrows, int words, BucketShape
         profile_begin(ctx, PROFILE_PCG_ROWS, out_bytes, ctx->pending_units);
     }
     kernel<<<grid, 32 << bs.warps_log2, smem, ctx->stream>>>(
-        n, row0, words, bs, stride, half_mode, leaf_offsets, links, tree_weight, leaf_tree, row_ptr, inv_sorted, occ, bucket_ptr,
+        n, row0, words, bs, stride, leaf_offsets, links, tree_weight, leaf_tree, row_ptr, inv_sorted, occ, bucket_ptr,
         static_cast<const EntryT *>(entries), stairs, start16, W, C, adj_bits, max_bits, degree_part, bad, batch);
     if (n >= kProfileMinSize && !batch.nodes) profile_end(ctx);
     SCS_LAUNCHED(ctx, "pcg_rows_kernel");
@@ -1347,15 +1331,17 @@ int pcg_build(scs_ctx *ctx, int n, int T, int64_t L, const int64_t *leaf_offsets
         SCS_LAUNCHED(ctx, "pcg_leaf_stairs");
     }
 
-#define SCS_ROWS(CT, WC, ET, TRI)                                                                                        \
-    launch_rows<CT, WC, ET, TRI>(ctx, n, row0, nrows, words, bs, stride, half ? 1 : 0, nchunks, smem, leaf_offsets, links,  \
-                                 tree_weight,                                                                            \
+#define SCS_ROWS(CT, WC, ET, TRI, HALF)                                                                                  \
+    launch_rows<CT, WC, ET, TRI, HALF>(ctx, n, row0, nrows, words, bs, stride, nchunks, smem, leaf_offsets, links,       \
+                                       tree_weight,                                                                      \
                                  leaf_tree, row_ptr, inv_sorted, occ, bucket_ptr, entries, stairs, start16, W, C, adj_bits, \
                                  max_bits, degree_part, scalars)
-#define SCS_ROWS_E(CT, WC, TRI) (packed ? SCS_ROWS(CT, WC, uint32_t, TRI) : SCS_ROWS(CT, WC, unsigned long long, TRI))
-    if (tri || half) rc = narrow ? SCS_ROWS_E(uint16_t, false, true) : SCS_ROWS_E(int32_t, false, true);
-    else if (narrow) rc = C ? SCS_ROWS_E(uint16_t, true, false) : SCS_ROWS_E(uint16_t, false, false);
-    else rc = C ? SCS_ROWS_E(int32_t, true, false) : SCS_ROWS_E(int32_t, false, false);
+#define SCS_ROWS_E(CT, WC, TRI, HALF) \
+    (packed ? SCS_ROWS(CT, WC, uint32_t, TRI, HALF) : SCS_ROWS(CT, WC, unsigned long long, TRI, HALF))
+    if (half) rc = narrow ? SCS_ROWS_E(uint16_t, false, true, true) : SCS_ROWS_E(int32_t, false, true, true);
+    else if (tri) rc = narrow ? SCS_ROWS_E(uint16_t, false, true, false) : SCS_ROWS_E(int32_t, false, true, false);
+    else if (narrow) rc = C ? SCS_ROWS_E(uint16_t, true, false, false) : SCS_ROWS_E(uint16_t, false, false, false);
+    else rc = C ? SCS_ROWS_E(int32_t, true, false, false) : SCS_ROWS_E(int32_t, false, false, false);
 #undef SCS_ROWS_E
 #undef SCS_ROWS
     if (rc) return rc;
@@ -1448,12 +1434,12 @@ int pcg_build_batch(scs_ctx *ctx, int B, int blocks, int R, int T, int64_t L, in
     if (!ctx->full_rows) {
         // every pair once: the upper triangles, then the mirror (which also writes the row sums into `degree`)
         if (narrow)
-            rc = launch_rows<uint16_t, false, uint32_t, true>(ctx, R, 0, R, 0, bs, stride, 0, 1, smem, leaf_offsets, links,
+            rc = launch_rows<uint16_t, false, uint32_t, true>(ctx, R, 0, R, 0, bs, stride, 1, smem, leaf_offsets, links,
                                                               tree_weight, leaf_tree, row_ptr, inv_sorted, occ, bucket_ptr,
                                                               entries, stairs, start16, W, nullptr, adj_bits, max_bits, degree,
                                                               bad_dev, batch);
         else
-            rc = launch_rows<int32_t, false, uint32_t, true>(ctx, R, 0, R, 0, bs, stride, 0, 1, smem, leaf_offsets, links,
+            rc = launch_rows<int32_t, false, uint32_t, true>(ctx, R, 0, R, 0, bs, stride, 1, smem, leaf_offsets, links,
                                                              tree_weight, leaf_tree, row_ptr, inv_sorted, occ, bucket_ptr,
                                                              entries, stairs, start16, W, nullptr, adj_bits, max_bits, degree,
                                                              bad_dev, batch);
@@ -1462,11 +1448,11 @@ int pcg_build_batch(scs_ctx *ctx, int B, int blocks, int R, int T, int64_t L, in
     }
     // the row kernel writes the row sums straight into `degree` (one chunk: degree_part[0][row])
     if (narrow)
-        rc = launch_rows<uint16_t, false, uint32_t, false>(ctx, R, 0, R, 0, bs, stride, 0, 1, smem, leaf_offsets, links, tree_weight,
+        rc = launch_rows<uint16_t, false, uint32_t, false>(ctx, R, 0, R, 0, bs, stride, 1, smem, leaf_offsets, links, tree_weight,
                                                     leaf_tree, row_ptr, inv_sorted, occ, bucket_ptr, entries, stairs, start16,
                                                            W, nullptr, adj_bits, max_bits, degree, bad_dev, batch);
     else
-        rc = launch_rows<int32_t, false, uint32_t, false>(ctx, R, 0, R, 0, bs, stride, 0, 1, smem, leaf_offsets, links, tree_weight,
+        rc = launch_rows<int32_t, false, uint32_t, false>(ctx, R, 0, R, 0, bs, stride, 1, smem, leaf_offsets, links, tree_weight,
                                                    leaf_tree, row_ptr, inv_sorted, occ, bucket_ptr, entries, stairs, start16,
                                                           W, nullptr, adj_bits, max_bits, degree, bad_dev, batch);
     return rc;
