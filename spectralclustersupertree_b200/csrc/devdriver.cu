@@ -609,6 +609,13 @@ using namespace scs;
 extern "C" {
 
 int scs_device_forest_create(scs_ctx *ctx, const scs_forest *forest, int weighting, scs_device_forest **out) {
+    return scs::device_forest_create(ctx, forest, weighting, false, out);
+}
+
+}  // extern "C"
+
+int scs::device_forest_create(scs_ctx *ctx, const scs_forest *forest, int weighting, bool cooperative,
+                              scs_device_forest **out) {
     if (!ctx || !forest || !out || weighting < 0 || weighting > 3) return SCS_ERR_INVALID;
     *out = nullptr;
     cudaSetDevice(ctx->device);
@@ -616,7 +623,7 @@ int scs_device_forest_create(scs_ctx *ctx, const scs_forest *forest, int weighti
     d->weighting = weighting;
     d->num_taxa = scs_forest_num_taxa(forest);
     d->owner = ctx;
-    const int rc = devforest_upload(ctx, forest, weighting, &d->trees);
+    const int rc = devforest_upload(ctx, forest, weighting, &d->trees, cooperative);
     if (rc) {
         d->trees.free_all(ctx);
         delete d;
@@ -639,6 +646,8 @@ int scs_device_forest_create(scs_ctx *ctx, const scs_forest *forest, int weighti
     *out = d;
     return SCS_OK;
 }
+
+extern "C" {
 
 int scs_device_forest_destroy(scs_device_forest *forest) {
     if (!forest) return SCS_OK;

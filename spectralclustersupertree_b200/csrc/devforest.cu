@@ -19,11 +19,14 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstddef>
+#include <cstdlib>
 #include <vector>
 
 #include <omp.h>
 
 #include "forest.hpp"
+#include "shard.cuh"
 
 namespace scs {
 
@@ -396,18 +399,10 @@ T *carve(unsigned char *&cursor, size_t count) {
 
 }  // namespace
 
-int devforest_upload(scs_ctx *ctx, const scs_forest *host, int weighting, DevForest *out) {
+int devforest_upload(scs_ctx *ctx, const scs_forest *host, int weighting, DevForest *out, bool cooperative) {
     if (!host || !out) return fail(ctx, SCS_ERR_INVALID, "devforest_upload: bad argument");
     const int64_t T = host->num_trees(), M = host->node_offsets.back();
     if (M >= (1ll << 31)) return fail(ctx, SCS_ERR_INVALID, "device forest: more than 2^31 tree nodes");
-    // subtree sizes (pre-order: the nodes of a subtree are a contiguous run), per tree, over the host threads
-    std::vector<int32_t> size(static_cast<size_t>(M > 0 ? M : 1));
-#pragma omp parallel for schedule(dynamic, 16) num_threads(scs_host_threads()) if (M > (1 << 15))
-    for (int64_t t = 0; t < T; ++t) {
-        const int64_t base = host->node_offsets[t], count = host->node_offsets[t + 1] - base;
-        for (int64_t k = 0; k < count; ++k) size[base + k] = 1;
-        for (int64_t k = count - 1; k >= 1; --k) size[base + host->parent[base + k]] += size[base + k];
-    }
     out->trees = T;
     out->nodes = M;
     out->leaves = host->leaf_offsets.back();
@@ -424,6 +419,48 @@ int devforest_upload(scs_ctx *ctx, const scs_forest *host, int weighting, DevFor
     if ((rc = grow(ctx, out->tree_job, nT * sizeof(int32_t)))) return rc;
     if (out->has_length && (rc = grow(ctx, out->length, nM * sizeof(double)))) return rc;
     if (out->has_support && (rc = grow(ctx, out->support, nM * sizeof(double)))) return rc;
+
+    // the per-node arrays, and where each starts in a rank's staging area (the W block of its exchange window)
+    struct NodeArray {
+        GrowBuf *dst;
+        const void *src;  // null: the subtree sizes, computed below
+        size_t elem, stage_off;
+    };
+    std::vector<NodeArray> arrays = {{&out->parent, host->parent.data(), sizeof(int32_t), 0},
+                                     {&out->size, nullptr, sizeof(int32_t), 0},
+                                     {&out->taxon, host->taxon.data(), sizeof(int32_t), 0}};
+    if (out->has_length) arrays.push_back({&out->length, host->length.data(), sizeof(double), 0});
+    if (out->has_support) arrays.push_back({&out->support, host->support.data(), sizeof(double), 0});
+    size_t stage_bytes = 0;
+    for (NodeArray &a : arrays) {
+        a.stage_off = stage_bytes;
+        stage_bytes += (nM * a.elem + 255) & ~static_cast<size_t>(255);
+    }
+    ShardState &sh = ctx->shard;
+    // worth it from a few million nodes (below that the barriers cost more than the link saves); tests lower the bar
+    const char *min_nodes_env = std::getenv("SCS_SHARED_UPLOAD_MIN_NODES");
+    const size_t min_nodes = min_nodes_env ? static_cast<size_t>(std::atoll(min_nodes_env)) : (1u << 22);
+    const bool share = cooperative && sh.connected && sh.world > 1 && nM > min_nodes &&
+                       sh.layout.total > sh.layout.W && stage_bytes <= sh.layout.total - sh.layout.W;
+    const int G = share ? sh.world : 1, me = share ? sh.rank : 0;
+    auto slice_begin = [&](int p) { return static_cast<int64_t>(M * static_cast<__int128>(p) / G); };
+    const int64_t lo = slice_begin(me), hi = slice_begin(me + 1);
+
+    // subtree sizes (pre-order: the nodes of a subtree are a contiguous run) of the trees that overlap this rank's
+    // slice, per tree, over the host threads
+    const int64_t *offs = host->node_offsets.data();
+    const int64_t t_lo = hi > lo ? std::upper_bound(offs, offs + T + 1, lo) - offs - 1 : 0;
+    const int64_t t_hi = hi > lo ? std::lower_bound(offs, offs + T + 1, hi) - offs : 0;
+    const int64_t size_base = T > 0 && hi > lo ? offs[t_lo] : 0;
+    std::vector<int32_t> size(static_cast<size_t>(hi > lo ? offs[t_hi] - size_base : 1));
+#pragma omp parallel for schedule(dynamic, 16) num_threads(scs_host_threads()) if (M > (1 << 15))
+    for (int64_t t = t_lo; t < t_hi; ++t) {
+        const int64_t base = offs[t], count = offs[t + 1] - base;
+        int32_t *sz = size.data() + (base - size_base);
+        for (int64_t k = 0; k < count; ++k) sz[k] = 1;
+        for (int64_t k = count - 1; k >= 1; --k) sz[host->parent[base + k]] += sz[k];
+    }
+
     // Pageable memory goes to the device through two pinned chunks: the host threads fill one while the other is on
     // the wire (a plain cudaMemcpy from pageable memory stages serially through the driver at a fraction of the
     // link's rate: 0.26 s for the 0.8 GB of the 50 000-taxon workload).
@@ -439,11 +476,11 @@ int devforest_upload(scs_ctx *ctx, const scs_forest *host, int weighting, DevFor
     }
     int turn = 0;
     const int copy_threads = scs_host_threads() > 0 ? scs_host_threads() : 1;
-    auto put = [&](GrowBuf &dst, const void *src, size_t bytes) -> int {
+    auto put = [&](void *dst, const void *src, size_t bytes) -> int {
         if (bytes == 0) return SCS_OK;
         ctx->h2d_bytes += static_cast<int64_t>(bytes);
         if (!staged || bytes < (1u << 20)) {
-            SCS_CUDA(ctx, cudaMemcpyAsync(dst.ptr, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+            SCS_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
             return SCS_OK;
         }
         for (size_t at = 0; at < bytes; at += kChunk, turn ^= 1) {
@@ -456,24 +493,52 @@ int devforest_upload(scs_ctx *ctx, const scs_forest *host, int weighting, DevFor
                 const size_t o = static_cast<size_t>(p) << 20;
                 std::memcpy(stage + o, static_cast<const unsigned char *>(src) + at + o, len - o < (1u << 20) ? len - o : (1u << 20));
             }
-            SCS_CUDA(ctx, cudaMemcpyAsync(static_cast<unsigned char *>(dst.ptr) + at, stage, len, cudaMemcpyHostToDevice, ctx->stream));
+            SCS_CUDA(ctx, cudaMemcpyAsync(static_cast<unsigned char *>(dst) + at, stage, len, cudaMemcpyHostToDevice, ctx->stream));
             SCS_CUDA(ctx, cudaEventRecord(sent[turn], ctx->stream));
         }
         return SCS_OK;
     };
-    if ((rc = put(out->tree_off, host->node_offsets.data(), (nT + 1) * sizeof(int64_t)))) return rc;
-    if ((rc = put(out->leaf_off, host->leaf_offsets.data(), (nT + 1) * sizeof(int64_t)))) return rc;
-    if ((rc = put(out->parent, host->parent.data(), nM * sizeof(int32_t)))) return rc;
-    if ((rc = put(out->size, size.data(), nM * sizeof(int32_t)))) return rc;
-    if ((rc = put(out->taxon, host->taxon.data(), nM * sizeof(int32_t)))) return rc;
-    if ((rc = put(out->weight, host->weight.data(), nT * sizeof(double)))) return rc;
-    if (out->has_length && (rc = put(out->length, host->length.data(), nM * sizeof(double)))) return rc;
-    if (out->has_support && (rc = put(out->support, host->support.data(), nM * sizeof(double)))) return rc;
+    if ((rc = put(out->tree_off.ptr, host->node_offsets.data(), (nT + 1) * sizeof(int64_t)))) return rc;
+    if ((rc = put(out->leaf_off.ptr, host->leaf_offsets.data(), (nT + 1) * sizeof(int64_t)))) return rc;
+    if ((rc = put(out->weight.ptr, host->weight.data(), nT * sizeof(double)))) return rc;
     SCS_CUDA(ctx, cudaMemsetAsync(out->tree_job.ptr, 0, nT * sizeof(int32_t), ctx->stream));
+    const size_t n_mine = static_cast<size_t>(hi - lo);
+    auto source_of = [&](const NodeArray &a) -> const unsigned char * {
+        if (a.src) return static_cast<const unsigned char *>(a.src) + static_cast<size_t>(lo) * a.elem;
+        return reinterpret_cast<const unsigned char *>(size.data() + (lo - size_base));
+    };
+    if (!share) {
+        for (const NodeArray &a : arrays)
+            if ((rc = put(a.dst->ptr, source_of(a), n_mine * a.elem))) return rc;
+    } else {
+        // nobody may still be reading this rank's W block (the last shared node of a previous build)
+        if ((rc = shard_barrier(ctx))) return rc;
+        unsigned char *stage = sh.window + sh.layout.W;
+        for (const NodeArray &a : arrays)
+            if ((rc = put(stage + a.stage_off + static_cast<size_t>(lo) * a.elem, source_of(a), n_mine * a.elem))) return rc;
+        if ((rc = shard_barrier(ctx))) return rc;  // every rank's slice is in its window
+        for (int step = 0; step < G; ++step) {
+            const int p = (me + step) % G;  // staggered so that the ranks do not all read one peer
+            const size_t b = static_cast<size_t>(slice_begin(p)), e = static_cast<size_t>(slice_begin(p + 1));
+            for (const NodeArray &a : arrays) {
+                if (e == b) continue;
+                SCS_CUDA(ctx, cudaMemcpyAsync(static_cast<unsigned char *>(a.dst->ptr) + b * a.elem,
+                                              sh.peer[p] + sh.layout.W + a.stage_off + b * a.elem, (e - b) * a.elem,
+                                              cudaMemcpyDeviceToDevice, ctx->stream));
+            }
+        }
+        if ((rc = shard_barrier(ctx))) return rc;  // the windows are free again
+    }
     // `size` is a local: the copies above must have read it before it goes away
     SCS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     for (cudaEvent_t e : sent)
         if (e) cudaEventDestroy(e);
+    if (share) {
+        // a peer that timed out in one of the barriers leaves its mark in the window header
+        unsigned int error = 0;
+        SCS_CUDA(ctx, cudaMemcpy(&error, sh.window + offsetof(ShardHeader, error), sizeof(error), cudaMemcpyDeviceToHost));
+        if (error) return fail(ctx, SCS_ERR_PEER, "device forest: a wait for a peer GPU timed out");
+    }
     return SCS_OK;
 }
 

@@ -51,7 +51,10 @@ struct DevJobInfo {
 };
 
 // Host forest -> device (job 0 owns every tree).  weighting decides which per-node values travel.
-int devforest_upload(scs_ctx *ctx, const scs_forest *host, int weighting, DevForest *out);
+// cooperative (every rank of a connected shard group calls this with the same forest): rank r sends only the r-th
+// slice of the per-node arrays over PCIe, into its exchange window, and the ranks gather the other slices from each
+// other's windows over NVLink -- the host link carries the forest once per box instead of once per GPU.
+int devforest_upload(scs_ctx *ctx, const scs_forest *host, int weighting, DevForest *out, bool cooperative = false);
 
 // Tours of every tree of the forest; taxon_vertex_dev[x] = vertex id of taxon x inside its job.
 // Sets *bootstrap_missing_host if a bootstrap weighting met a missing support at an LCA (the reference raises

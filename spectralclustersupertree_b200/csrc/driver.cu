@@ -972,7 +972,7 @@ int scs_supertree_build_sharded(scs_ctx *ctx, const scs_forest *forest, int weig
         // the source trees go to the device once and stay there for the whole recursion (devdriver.cu)
         scs_device_forest *resident = nullptr;
         const auto t0 = std::chrono::steady_clock::now();
-        if ((rc = scs_device_forest_create(ctx, forest, weighting, &resident))) return rc;
+        if ((rc = device_forest_create(ctx, forest, weighting, cooperative, &resident))) return rc;
         const auto t1 = std::chrono::steady_clock::now();
         rc = run_device_driver(ctx, resident, contract_edges, seed, record_nodes != 0, rank, world, result.get());
         const auto t2 = std::chrono::steady_clock::now();

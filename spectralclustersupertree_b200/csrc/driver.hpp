@@ -43,6 +43,9 @@ inline uint64_t node_seed(uint64_t seed, int32_t first_taxon, size_t taxa) {
 // device, a few small host round trips per wave for the bookkeeping of the output tree.  One GPU, or rank `rank` of
 // `world` in a cooperative build (exchange windows connected: large nodes row-sharded over the GPUs, smaller
 // sub-problems dealt out over the ranks).
+// scs_device_forest_create; cooperative: the ranks of a connected shard group share the upload (devforest.cuh)
+int device_forest_create(scs_ctx *ctx, const scs_forest *forest, int weighting, bool cooperative, scs_device_forest **out);
+
 int run_device_driver(scs_ctx *ctx, const scs_device_forest *forest, int contract_edges, uint64_t seed, bool record, int rank,
                       int world, scs_supertree *out);
 

@@ -66,7 +66,9 @@ def main() -> None:
     assert np.array_equal(part, part2), "partition differs from the single-GPU one"
     assert stats.eig[1] == stats2.eig[1] and stats.matvecs == stats2.matvecs, (stats.eig[1], stats2.eig[1])
 
-    # the whole job: large nodes shared out, then the frontier dealt out
+    # the whole job: large nodes shared out, then the frontier dealt out; the source trees cross PCIe once for all
+    # ranks (every rank its slice, the rest gathered from the peers' windows)
+    os.environ["SCS_SHARED_UPLOAD_MIN_NODES"] = "0"
     dist.barrier()
     built = engine.supertree_build(forest(), "branch", rank=rank, world=world)
     assert engine.shard_nodes > 1

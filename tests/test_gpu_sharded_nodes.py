@@ -130,8 +130,13 @@ def test_sharded_disconnected_node_labels_components(engine):
         ranks.close()
 
 
-def test_sharded_build_equals_single_gpu_build(engine):
-    """The native recursion with the large nodes shared out and the frontier dealt out afterwards."""
+@pytest.mark.parametrize("shared_upload", [False, True])
+def test_sharded_build_equals_single_gpu_build(engine, monkeypatch, shared_upload):
+    """The native recursion with the large nodes shared out and the frontier dealt out afterwards; with
+    shared_upload every rank sends only its slice of the source trees over PCIe and gathers the rest from the
+    peers' windows (csrc/devforest.cu: devforest_upload, cooperative)."""
+    if shared_upload:
+        monkeypatch.setenv("SCS_SHARED_UPLOAD_MIN_NODES", "0")
     arrays = make_problem(1500, 120, "branch", 99, tree_weights=True).forest_arrays()
     single = engine.supertree_build(forest_of(arrays), "branch")
     ranks = Ranks(2, n_max=1500, min_n=256)
