@@ -197,6 +197,10 @@ struct scs_ctx {
     int last_n = 0;
     int last_m = 0;
     scs::ShardState shard;
+    // device buffers of the recursion driver that survive from one build to the next (devdriver.cu): a build then
+    // allocates nothing -- fresh gigabyte-sized allocations stalled single waves by hundreds of milliseconds
+    void *driver_cache = nullptr;
+    void (*driver_cache_release)(scs_ctx *, void *) = nullptr;
 };
 
 namespace scs {

@@ -393,6 +393,8 @@ int scs_ctx_destroy(scs_ctx *ctx) {
     for (scs_ctx *worker : ctx->workers) scs_ctx_destroy(worker);
     ctx->workers.clear();
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->driver_cache && ctx->driver_cache_release) ctx->driver_cache_release(ctx, ctx->driver_cache);
+    ctx->driver_cache = nullptr;
     scs_shard_destroy(ctx);
     for (auto &buf : ctx->slots)
         if (buf.ptr) cudaFreeAsync(buf.ptr, ctx->stream);

@@ -59,22 +59,46 @@ __global__ void relative_offsets(int count, const int64_t *__restrict__ absolute
     if (i < count) out[i] = absolute[i] - absolute[0];
 }
 
+// What a context keeps between builds: the two alternating wave forests, the tours, the small per-wave arrays and the
+// device copy of the source trees of scs_supertree_build (grow-only: after the first build of a size nothing is
+// allocated any more).
+struct DriverCache {
+    DevForest forest[2];
+    DevTours tours;
+    GrowBuf vertex_dev, offsets_rel, part_dev, flags_dev;
+    scs_device_forest resident;
+};
+
+void release_driver_cache(scs_ctx *ctx, void *raw) {
+    DriverCache *cache = static_cast<DriverCache *>(raw);
+    cache->forest[0].free_all(ctx);
+    cache->forest[1].free_all(ctx);
+    cache->tours.free_all(ctx);
+    for (GrowBuf *b : {&cache->vertex_dev, &cache->offsets_rel, &cache->part_dev, &cache->flags_dev}) release(ctx, *b);
+    cache->resident.trees.free_all(ctx);
+    cudaStreamSynchronize(ctx->stream);
+    delete cache;
+}
+
+DriverCache &driver_cache(scs_ctx *ctx) {
+    if (!ctx->driver_cache) {
+        ctx->driver_cache = new DriverCache();
+        ctx->driver_cache_release = release_driver_cache;
+    }
+    return *static_cast<DriverCache *>(ctx->driver_cache);
+}
+
 class DeviceDriver {
   public:
     DeviceDriver(scs_ctx *ctx, int weighting, int contract_edges, uint64_t seed, bool record, int rank, int world,
                  scs_supertree *out)
         : ctx_(ctx), weighting_(weighting), contract_(contract_edges), seed_(seed), record_(record), rank_(rank),
-          world_(world), out_(*out) {}
+          world_(world), out_(*out), cache_(driver_cache(ctx)), forest_(cache_.forest), tours_(cache_.tours),
+          vertex_dev_(cache_.vertex_dev), offsets_rel_(cache_.offsets_rel), part_dev_(cache_.part_dev),
+          flags_dev_(cache_.flags_dev) {}
 
     ~DeviceDriver() {
-        forest_[0].free_all(ctx_);
-        forest_[1].free_all(ctx_);
-        tours_.free_all(ctx_);
-        release(ctx_, vertex_dev_);
-        release(ctx_, offsets_rel_);
         if (tours_ready_) cudaEventDestroy(tours_ready_);
-        release(ctx_, part_dev_);
-        release(ctx_, flags_dev_);
         cudaStreamSynchronize(ctx_->stream);
     }
 
@@ -583,10 +607,11 @@ class DeviceDriver {
     scs_supertree &out_;
     int num_taxa_ = 0;
     const DevForest *root_ = nullptr;  // the resident source trees (read-only): the forest of the first wave
-    DevForest forest_[2];              // the forests of the later waves, written alternately
+    DriverCache &cache_;               // the context's buffers: they outlive the build
+    DevForest (&forest_)[2];           // the forests of the later waves, written alternately
     int cur_ = -1;
-    DevTours tours_;
-    GrowBuf vertex_dev_, offsets_rel_, part_dev_, flags_dev_;
+    DevTours &tours_;
+    GrowBuf &vertex_dev_, &offsets_rel_, &part_dev_, &flags_dev_;
     cudaEvent_t tours_ready_ = nullptr;
     std::vector<int32_t> vertex_, owner_, part_, pending_slot_;
     std::vector<uint8_t> present_;
@@ -614,21 +639,14 @@ int scs_device_forest_create(scs_ctx *ctx, const scs_forest *forest, int weighti
 
 }  // extern "C"
 
-int scs::device_forest_create(scs_ctx *ctx, const scs_forest *forest, int weighting, bool cooperative,
-                              scs_device_forest **out) {
-    if (!ctx || !forest || !out || weighting < 0 || weighting > 3) return SCS_ERR_INVALID;
-    *out = nullptr;
-    cudaSetDevice(ctx->device);
-    scs_device_forest *d = new scs_device_forest();
+// (re)fill a device forest object: its arrays only ever grow
+static int device_forest_fill(scs_ctx *ctx, const scs_forest *forest, int weighting, bool cooperative, scs_device_forest *d) {
     d->weighting = weighting;
     d->num_taxa = scs_forest_num_taxa(forest);
     d->owner = ctx;
+    d->taxa.clear();
     const int rc = devforest_upload(ctx, forest, weighting, &d->trees, cooperative);
-    if (rc) {
-        d->trees.free_all(ctx);
-        delete d;
-        return rc;
-    }
+    if (rc) return rc;
     std::vector<uint8_t> seen(static_cast<size_t>(d->num_taxa > 0 ? d->num_taxa : 1), 0);
     {
         const int32_t *tax = forest->taxon.data();
@@ -643,8 +661,33 @@ int scs::device_forest_create(scs_ctx *ctx, const scs_forest *forest, int weight
     d->first_tree_nodes = forest->num_trees() > 0 ? forest->node_offsets[1] - forest->node_offsets[0] : 0;
     d->pair_visits = scs_forest_pair_visits(forest);
     d->leaves = forest->leaf_offsets.back();
+    return SCS_OK;
+}
+
+int scs::device_forest_create(scs_ctx *ctx, const scs_forest *forest, int weighting, bool cooperative,
+                              scs_device_forest **out) {
+    if (!ctx || !forest || !out || weighting < 0 || weighting > 3) return SCS_ERR_INVALID;
+    *out = nullptr;
+    cudaSetDevice(ctx->device);
+    scs_device_forest *d = new scs_device_forest();
+    const int rc = device_forest_fill(ctx, forest, weighting, cooperative, d);
+    if (rc) {
+        d->trees.free_all(ctx);
+        delete d;
+        return rc;
+    }
     *out = d;
     return SCS_OK;
+}
+
+// The device copy of the source trees scs_supertree_build works on: kept by the context between builds.
+int scs::device_forest_refresh(scs_ctx *ctx, const scs_forest *forest, int weighting, bool cooperative,
+                               const scs_device_forest **out) {
+    if (!ctx || !forest || !out || weighting < 0 || weighting > 3) return SCS_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    scs_device_forest *d = &driver_cache(ctx).resident;
+    *out = d;
+    return device_forest_fill(ctx, forest, weighting, cooperative, d);
 }
 
 extern "C" {

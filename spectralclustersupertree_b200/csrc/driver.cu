@@ -970,13 +970,12 @@ int scs_supertree_build_sharded(scs_ctx *ctx, const scs_forest *forest, int weig
     const bool cooperative = world > 1 && sh.connected && sh.world == world && sh.rank == rank;
     if (ctx->device_forest && (world == 1 || cooperative)) {
         // the source trees go to the device once and stay there for the whole recursion (devdriver.cu)
-        scs_device_forest *resident = nullptr;
+        const scs_device_forest *resident = nullptr;
         const auto t0 = std::chrono::steady_clock::now();
-        if ((rc = device_forest_create(ctx, forest, weighting, cooperative, &resident))) return rc;
+        if ((rc = device_forest_refresh(ctx, forest, weighting, cooperative, &resident))) return rc;
         const auto t1 = std::chrono::steady_clock::now();
         rc = run_device_driver(ctx, resident, contract_edges, seed, record_nodes != 0, rank, world, result.get());
         const auto t2 = std::chrono::steady_clock::now();
-        scs_device_forest_destroy(resident);
         if (std::getenv("SCS_DRIVER_TRACE")) {
             auto ms = [](auto a, auto b) { return 1e3 * std::chrono::duration<double>(b - a).count(); };
             std::fprintf(stderr, "[scs build] rank %d: forest to the device %.2f ms, recursion %.2f ms, release %.2f ms\n", rank,

@@ -46,6 +46,10 @@ inline uint64_t node_seed(uint64_t seed, int32_t first_taxon, size_t taxa) {
 // scs_device_forest_create; cooperative: the ranks of a connected shard group share the upload (devforest.cuh)
 int device_forest_create(scs_ctx *ctx, const scs_forest *forest, int weighting, bool cooperative, scs_device_forest **out);
 
+// the same into the device forest the context keeps between builds (nothing to destroy)
+int device_forest_refresh(scs_ctx *ctx, const scs_forest *forest, int weighting, bool cooperative,
+                          const scs_device_forest **out);
+
 int run_device_driver(scs_ctx *ctx, const scs_device_forest *forest, int contract_edges, uint64_t seed, bool record, int rank,
                       int world, scs_supertree *out);
 
