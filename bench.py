@@ -496,7 +496,14 @@ def gpu_line(args, arrays: dict) -> dict:
         # round's `ncu --set full` capture of the largest matvec launch of this workload); null without a capture
         if NCU_TRAFFIC_FILE.is_file():
             captured = json.loads(NCU_TRAFFIC_FILE.read_text())
-            roofline["traffic"] = captured.get("dram_bytes_per_launch")
+            # the capture is of the job's largest launch (grid = m rows); `achieved` averages launches of several
+            # sizes, so the measured bytes are scaled by the ratio measured / algorithmic of the captured launch
+            m_cap = int(str(captured.get("grid", "(0")).strip("()").split(",")[0] or 0)
+            algorithmic = 8.0 * m_cap * m_cap + 24.0 * m_cap
+            ratio = captured["dram_bytes_per_launch"] / algorithmic if algorithmic else None
+            captured["algorithmic_bytes_of_captured_launch"] = algorithmic
+            captured["measured_over_algorithmic"] = ratio
+            roofline["traffic"] = roofline["bytes_per_launch"] * ratio if ratio else captured["dram_bytes_per_launch"]
             roofline["traffic_detail"] = captured
     roofline_rows = None
     if rows["launches"] and rows["ms"] > 0:
