@@ -332,3 +332,40 @@ def test_full_size_workload_against_the_c_oracle(engine):
         assert np.array_equal(again["adj_bits"], got["adj_bits"])
     finally:
         forest.close()
+
+
+def test_more_than_65535_source_trees(engine):
+    """The co-occurrence counts of the small-node path are 16 bits wide (csrc/small.cu); nodes covered by more source
+    trees than that must be routed to the paths with 32-bit counts -- by the per-node entry point and by both
+    recursion drivers -- instead of wrapping.  65 536 trees ((a,b),(c,d)) and 1 000 trees ((a,c),(b,d)): a wrapped
+    count of 65 536 is 0 and would delete the edges a-b and c-d."""
+    t1, t2 = 65536, 1000
+    trees = t1 + t2
+    parent = np.tile(np.array([-1, 0, 1, 1, 0, 4, 4], dtype=np.int32), trees)
+    taxon = np.concatenate([np.tile(np.array([-1, -1, 0, 1, -1, 2, 3], dtype=np.int32), t1),
+                            np.tile(np.array([-1, -1, 0, 2, -1, 1, 3], dtype=np.int32), t2)])  # fmt: skip
+    offsets = np.arange(trees + 1, dtype=np.int64) * 7
+    nan = np.full(7 * trees, np.nan)
+    weights = np.ones(trees)
+    names = ["a", "b", "c", "d"]
+
+    def forest():
+        return Forest.from_arrays(offsets, parent, nan, nan, taxon, weights, names)
+
+    taxa, part, stats = engine.forest_split(forest(), "one", seed=3)
+    got = engine.last_node_buffers()
+    want = np.array([[0, t1, t2, 0], [t1, 0, 0, t2], [t2, 0, 0, t1], [0, t2, t1, 0]], dtype=np.float64)
+    assert np.array_equal(got["W"], want)
+    assert np.array_equal(got["occ"], np.full(4, trees, dtype=np.int32))
+    assert stats.n_components == 1 and stats.contracted_size == 4  # no pair is together in every tree
+    assert part[0] == part[1] and part[2] == part[3] and part[0] != part[2]
+    for device_forest in (True, False):
+        engine.set_device_forest(device_forest)
+        try:
+            built = engine.supertree_build(forest(), "one", record=True)
+        finally:
+            engine.set_device_forest(True)
+        top = built["records"][0]
+        assert top[2].n_components == 1 and top[2].contracted_size == 4
+        assert top[1][0] == top[1][1] and top[1][2] == top[1][3] and top[1][0] != top[1][2]
+        assert sorted(built["taxon"][built["taxon"] >= 0]) == [0, 1, 2, 3]
