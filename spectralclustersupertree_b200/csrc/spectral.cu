@@ -116,9 +116,9 @@ int matvec_group(int m) {
     return forced && m >= 2048 ? forced : mv_group_of(m);
 }
 
-// Row-sharded operator fused with its all-gather (one process per GPU, rows [row0, row0 + gridDim.x) of
-// W on this rank): every CTA computes one entry of y and stores it straight into the `vec` buffer of
-// EVERY rank's exchange window over NVLink; the last CTA to finish raises this rank's flag in every
+// Row-sharded operator fused with its all-gather (one process per GPU, rows [row0, row0 + nrows) of
+// W on this rank): every CTA computes entries of y into the `vec` buffer of this rank's exchange window; the
+// last CTA to finish copies the slice into every peer's window over NVLink, raises this rank's flag in every
 // window and then waits until every rank has raised its flag here, so when the kernel ends the whole
 // vector is in this rank's window.  Every entry is computed by the same code whatever rank owns the row,
 // so the assembled vector is bit-identical to the single-GPU matvec's.
@@ -135,14 +135,14 @@ matvec_rows_allgather(int m, int row0, int nrows, const double *__restrict__ W, 
     constexpr int kRows = kMvThreads / kGroup;
     const int local = blockIdx.x * kRows + threadIdx.x / kGroup;
     const bool live = local < nrows;
-    double s = group_row_dot<kGroup>(W + static_cast<size_t>(live ? local : nrows - 1) * m, z, m, part);
-    // the group's first warp stores the entry into every rank's window
-    s = __shfl_sync(0xffffffffu, s, 0);
-    if (live && threadIdx.x % kGroup < 32) {
-        const int lane = threadIdx.x & 31;
-        const double out = isd[row0 + local] * s;
-        if (lane < peers.world) reinterpret_cast<double *>(peers.window[lane] + vec_offset)[row0 + local] = out;
-        __threadfence_system();
+    const double s = group_row_dot<kGroup>(W + static_cast<size_t>(live ? local : nrows - 1) * m, z, m, part);
+    // The entry goes into this rank's OWN window with an ordinary store and a device-scope fence.  (Storing it
+    // into every peer's window from here needed a system-scope fence per CTA -- thousands of NVLink round trips per
+    // launch, which is why two GPUs were no faster than one: 70 us against 72.)
+    double *mine_vec = reinterpret_cast<double *>(peers.window[peers.rank] + vec_offset);
+    if (live && threadIdx.x % kGroup == 0) {
+        mine_vec[row0 + local] = isd[row0 + local] * s;
+        __threadfence();
     }
     __syncthreads();  // every store of this CTA is fenced before its ticket is drawn
     if (threadIdx.x == 0) {
@@ -150,7 +150,18 @@ matvec_rows_allgather(int m, int row0, int nrows, const double *__restrict__ W, 
         last = atomicInc(&mine->ticket, gridDim.x - 1) == gridDim.x - 1;
     }
     __syncthreads();
-    if (last && threadIdx.x < 32) peer_signal_and_wait(peers, epoch, timeout_ns);
+    if (!last) return;
+    // The last CTA forwards the finished slice to every peer with coalesced stores, fences once, raises this rank's
+    // flag in every window and waits until every rank has raised its flag here.
+    __threadfence();
+    for (int step = 1; step < peers.world; ++step) {
+        const int p = (peers.rank + step) % peers.world;
+        double *theirs = reinterpret_cast<double *>(peers.window[p] + vec_offset) + row0;
+        for (int i = threadIdx.x; i < nrows; i += kMvThreads) theirs[i] = __ldcg(mine_vec + row0 + i);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < 32) peer_signal_and_wait(peers, epoch, timeout_ns);
 }
 
 int launch_matvec(scs_ctx *ctx, int m, const double *W, const double *isd, const double *z, double **y,
