@@ -4,7 +4,10 @@
 // trees, scs.py:569) and in the Laplacian matvec, so a large node is ROW-SHARDED: rank r builds rows
 // [r * ceil(n / G), (r + 1) * ceil(n / G)) of W from the (replicated) leaf tours -- no reduction over trees,
 // so the fixed tree-order summation and with it bit-exactness survive, unlike a tree-sharded all-reduce --
-// and keeps only that block (n^2 / G doubles).  What the other ranks need is pushed into their exchange
+// and keeps only that block (n^2 / G doubles).  Every row computes only the cyclic half window of columns after
+// its own, so each pair of the node is visited once over all ranks; the other half of a row is fetched, as the
+// mirror image of what the owners of those rows computed, out of their W blocks (pcg.cu: RowBlock::half_window,
+// pcg_fetch_transposed).  What the other ranks need is pushed into their exchange
 // windows over NVLink (shard.cuh): the adjacency / max-graph bit rows and degrees after the build (the
 // components and contraction groups are then computed redundantly, they are cheap and deterministic),
 // and one slice of the iterate per Lanczos step, written by the matvec kernel itself
