@@ -11,7 +11,7 @@ is quoted on).  Three clocks are reported in one JSON line:
   build, components, contraction, spectral split and the restriction of the trees to the children, all on the
   device, wave by wave; CUDA events around the build.
 * ``e2e``    -- the same job through the public host-buffer path over the C ABI
-  (``scs_forest_create`` + ``scs_supertree_build``): flat source trees in host memory in, flat
+  (``scs_forest_create_view`` + ``scs_supertree_build``): flat source trees in host memory in, flat
   supertree out; validation of the trees, H2D of the forest, the recursion, D2H of partitions inside the timed
   region.  With N > 1 the large recursion nodes are row-sharded over the GPUs, smaller sub-problems are dealt out
   over the ranks (no data-path collective) and the outputs are all-gathered.
@@ -527,7 +527,8 @@ def gpu_line(args, arrays: dict) -> dict:
                         "node splits and tree restriction on the device, wave by wave; per wave the nodes > 4096 taxa one "
                         "by one, the nodes of 33..4096 taxa as one batch, the nodes <= 32 taxa in one launch); CUDA "
                         "events around the build; max over ranks",
-            "e2e_is": "scs_forest_create + scs_supertree_build over the C ABI from flat host arrays to the flat "
+            "e2e_is": "scs_forest_create_view (the caller's flat arrays validated in place, not copied) + "
+                      "scs_supertree_build over the C ABI from flat host arrays to the flat "
                       "supertree (wall clock: validation of the trees, H2D of the forest, the recursion as in value, D2H "
                       "of partitions and bookkeeping; for N > 1 recursion nodes with >= --shard-min-n taxa are "
                       "row-sharded over the GPUs (every leaf pair once over all ranks, the halves exchanged over NVLink; "

@@ -231,6 +231,12 @@ int scs_set_host_threads(int threads);
 int scs_forest_create(int T, const int64_t *node_offsets, const int32_t *parent, const double *length,
                       const double *support, const int32_t *taxon, const double *tree_weight,
                       int num_taxa, scs_forest **out);
+/* The same without copying the per-node arrays: the forest refers to the caller's parent / length / support / taxon
+ * arrays, which must stay alive and unchanged until scs_forest_destroy (node_offsets and tree_weight are copied).
+ * For callers that hold the flat trees anyway: at 50 000 taxa x 5 000 trees the copy is a gigabyte per process. */
+int scs_forest_create_view(int T, const int64_t *node_offsets, const int32_t *parent, const double *length,
+                           const double *support, const int32_t *taxon, const double *tree_weight, int num_taxa,
+                           scs_forest **out);
 /* Why the last scs_forest_create on this thread returned SCS_ERR_INPUT ("" if it did not): a malformed
  * pre-order tree, or a taxon that labels two tips of one source tree (rejected: the graph kernels give every
  * leaf of a tree its own column). */

@@ -110,6 +110,7 @@ SIGNATURES: dict[str, tuple] = {
     "scs_memcpy_d2h": (c_int, [_P, _P, _P, c_size_t]),
     "scs_set_host_threads": (c_int, [c_int]),
     "scs_forest_create": (c_int, [c_int, _P, _P, _P, _P, _P, _P, c_int, POINTER(_P)]),
+    "scs_forest_create_view": (c_int, [c_int, _P, _P, _P, _P, _P, _P, c_int, POINTER(_P)]),
     "scs_forest_destroy": (c_int, [_P]),
     "scs_forest_parse_newick": (c_int, [c_char_p, c_size_t, POINTER(_P), POINTER(_P), POINTER(c_size_t), POINTER(c_int)]),
     "scs_newick_last_error": (c_char_p, []),

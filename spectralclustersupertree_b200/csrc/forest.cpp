@@ -39,25 +39,6 @@ namespace {
 
 constexpr int64_t kParallelNodes = 1 << 15;  // forests with more nodes are processed by all host threads
 
-bool is_tip(const scs_forest &f, int64_t base, int64_t count, int64_t k) {
-    // pre-order: a node is a tip iff the next node is not its child
-    return k + 1 >= count || f.parent[base + k + 1] != k;
-}
-
-// Tips that appear in tours (a lone tip has none) and whether every internal node has at least two children.
-void tree_shape(const scs_forest &f, int64_t base, int64_t count, std::vector<int32_t> &kids, int64_t *tips_out,
-                uint8_t *branching_out) {
-    int64_t tips = 0;
-    if (count > 1)
-        for (int64_t k = 0; k < count; ++k) tips += f.taxon[base + k] >= 0;
-    *tips_out = tips;
-    kids.assign(static_cast<size_t>(count), 0);
-    for (int64_t k = 1; k < count; ++k) kids[f.parent[base + k]] += 1;
-    bool branching = true;
-    for (int64_t k = 0; k < count && branching; ++k) branching = f.taxon[base + k] >= 0 || kids[k] >= 2;
-    *branching_out = branching ? 1 : 0;
-}
-
 }  // namespace
 
 extern "C" {
@@ -78,9 +59,25 @@ int scs_set_host_threads(int threads) {
     return SCS_OK;
 }
 
+static int forest_create(int T, const int64_t *node_offsets, const int32_t *parent, const double *length,
+                         const double *support, const int32_t *taxon, const double *tree_weight, int num_taxa, bool view,
+                         scs_forest **out);
+
 int scs_forest_create(int T, const int64_t *node_offsets, const int32_t *parent, const double *length,
                       const double *support, const int32_t *taxon, const double *tree_weight, int num_taxa,
                       scs_forest **out) {
+    return forest_create(T, node_offsets, parent, length, support, taxon, tree_weight, num_taxa, false, out);
+}
+
+int scs_forest_create_view(int T, const int64_t *node_offsets, const int32_t *parent, const double *length,
+                           const double *support, const int32_t *taxon, const double *tree_weight, int num_taxa,
+                           scs_forest **out) {
+    return forest_create(T, node_offsets, parent, length, support, taxon, tree_weight, num_taxa, true, out);
+}
+
+static int forest_create(int T, const int64_t *node_offsets, const int32_t *parent, const double *length,
+                         const double *support, const int32_t *taxon, const double *tree_weight, int num_taxa, bool view,
+                         scs_forest **out) {
     if (!out) return SCS_ERR_INVALID;
     *out = nullptr;
     if (T < 0 || num_taxa < 0 || !node_offsets) return SCS_ERR_INVALID;
@@ -93,12 +90,21 @@ int scs_forest_create(int T, const int64_t *node_offsets, const int32_t *parent,
     f->num_taxa = num_taxa;
     f->node_offsets.assign(node_offsets, node_offsets + T + 1);
     const int copy_threads = scs_host_threads() > 0 ? scs_host_threads() : 1;
-    f->parent.assign_parallel(parent, parent + M, copy_threads);
-    f->taxon.assign_parallel(taxon, taxon + M, copy_threads);
-    if (length) f->length.assign_parallel(length, length + M, copy_threads);
-    else f->length.assign_parallel(static_cast<size_t>(M), std::nan(""), copy_threads);
-    if (support) f->support.assign_parallel(support, support + M, copy_threads);
-    else f->support.assign_parallel(static_cast<size_t>(M), std::nan(""), copy_threads);
+    if (view) {
+        // the per-node arrays stay the caller's (a gigabyte at 50 000 taxa x 5 000 trees: copying it costs more
+        // than validating it); arrays the caller does not have are still made here
+        f->parent.adopt(parent, parent + M);
+        f->taxon.adopt(taxon, taxon + M);
+        if (length) f->length.adopt(length, length + M);
+        if (support) f->support.adopt(support, support + M);
+    } else {
+        f->parent.assign_parallel(parent, parent + M, copy_threads);
+        f->taxon.assign_parallel(taxon, taxon + M, copy_threads);
+        if (length) f->length.assign_parallel(length, length + M, copy_threads);
+        if (support) f->support.assign_parallel(support, support + M, copy_threads);
+    }
+    if (!length) f->length.assign_parallel(static_cast<size_t>(M), std::nan(""), copy_threads);
+    if (!support) f->support.assign_parallel(static_cast<size_t>(M), std::nan(""), copy_threads);
     f->weight.assign(tree_weight, tree_weight + T);
     f->source.resize(T);
     f->branching.assign(static_cast<size_t>(T), 1);
@@ -116,16 +122,35 @@ int scs_forest_create(int T, const int64_t *node_offsets, const int32_t *parent,
         for (int t = 0; t < T; ++t) {
             f->source[t] = t;
             const int64_t base = node_offsets[t], count = node_offsets[t + 1] - base;
-            bool ok = count >= 1 && parent[base] == -1;
-            for (int64_t k = 1; ok && k < count; ++k) ok = parent[base + k] >= 0 && parent[base + k] < k;
+            // one pass: parent indices, tips (pre-order: a node is a tip iff the next node is not its child), tip
+            // taxa, repeated taxa, children per node; then whether every internal node branches
+            const int32_t *par = parent + base;
+            const int32_t *tax = taxon + base;
+            bool ok = count >= 1 && par[0] == -1;
             bool twice = false;
+            int64_t tip_count = 0;
+            kids.assign(static_cast<size_t>(count > 0 ? count : 1), 0);
             for (int64_t k = 0; ok && k < count; ++k) {
-                const bool tip = is_tip(*f, base, count, k);
-                const int32_t x = taxon[base + k];
-                ok = tip ? (x >= 0 && x < num_taxa) : x == -1;
-                if (ok && tip) {
+                if (k >= 1) {
+                    const int32_t p = par[k];
+                    if (p < 0 || p >= k) {
+                        ok = false;
+                        break;
+                    }
+                    kids[p] += 1;
+                }
+                const bool tip = k + 1 >= count || par[k + 1] != k;
+                const int32_t x = tax[k];
+                if (tip) {
+                    if (x < 0 || x >= num_taxa) {
+                        ok = false;
+                        break;
+                    }
                     if (seen_in[x] == t) twice = true;
                     seen_in[x] = t;
+                    tip_count += 1;
+                } else if (x != -1) {
+                    ok = false;
                 }
             }
             if (!ok || twice) {
@@ -137,7 +162,10 @@ int scs_forest_create(int T, const int64_t *node_offsets, const int32_t *parent,
                 }
                 continue;
             }
-            tree_shape(*f, base, count, kids, &tips[t], &f->branching[t]);
+            bool branching = true;
+            for (int64_t k = 0; k < count && branching; ++k) branching = tax[k] >= 0 || kids[k] >= 2;
+            tips[t] = count > 1 ? tip_count : 0;  // a lone tip appears in no tour
+            f->branching[t] = branching ? 1 : 0;
         }
     }
     if (!all_ok) {

@@ -15,11 +15,22 @@ class FlatArray {
     FlatArray() = default;
     FlatArray(const FlatArray &) = delete;
     FlatArray &operator=(const FlatArray &) = delete;
-    ~FlatArray() { std::free(data_); }
+    ~FlatArray() {
+        if (owned_) std::free(data_);
+    }
     void resize_uninitialized(size_t n) {
-        std::free(data_);
+        if (owned_) std::free(data_);
         data_ = n ? static_cast<T *>(std::malloc(n * sizeof(T))) : nullptr;
         size_ = data_ ? n : 0;
+        owned_ = true;
+    }
+    // refer to the caller's array instead of copying it (scs_forest_create_view: the caller keeps it alive and
+    // unchanged for as long as the forest exists); never written through
+    void adopt(const T *first, const T *last) {
+        if (owned_) std::free(data_);
+        data_ = const_cast<T *>(first);
+        size_ = static_cast<size_t>(last - first);
+        owned_ = false;
     }
     void assign(const T *first, const T *last) {
         resize_uninitialized(static_cast<size_t>(last - first));
@@ -57,6 +68,7 @@ class FlatArray {
   private:
     T *data_ = nullptr;
     size_t size_ = 0;
+    bool owned_ = true;
 };
 
 struct scs_forest {

@@ -599,7 +599,11 @@ class Forest:
 
     # -- construction --------------------------------------------------------------------------
     @classmethod
-    def from_arrays(cls, node_offsets, parent, length, support, taxon, weights, names: Sequence[str]) -> "Forest":
+    def from_arrays(cls, node_offsets, parent, length, support, taxon, weights, names: Sequence[str],
+                    copy: bool = False) -> "Forest":
+        """Flat source trees (pre-order nodes per tree) as a forest.  By default the per-node arrays are not copied
+        (``scs_forest_create_view``): the forest refers to them and this object keeps them alive -- do not modify them
+        while it exists; ``copy=True`` makes the library own a copy (``scs_forest_create``)."""
         lib = _lib.load()
         node_offsets = np.ascontiguousarray(node_offsets, dtype=np.int64)
         parent = np.ascontiguousarray(parent, dtype=np.int32)
@@ -608,13 +612,17 @@ class Forest:
         support = None if support is None else np.ascontiguousarray(support, dtype=np.float64)
         weights = np.ascontiguousarray(weights, dtype=np.float64)
         handle = ctypes.c_void_p()
-        status = lib.scs_forest_create(
+        create = lib.scs_forest_create if copy else lib.scs_forest_create_view
+        status = create(
             len(weights), ptr(node_offsets), ptr(parent), ptr(length), ptr(support), ptr(taxon), ptr(weights),
             len(names), ctypes.byref(handle),
         )  # fmt: skip
         if status != _lib.SCS_OK:
             raise ScsError(status, "scs_forest_create: " + lib.scs_forest_last_error().decode())
-        return cls(handle, names)
+        forest = cls(handle, names)
+        if not copy:
+            forest._borrowed = (parent, length, support, taxon)  # the library reads these until the forest is closed
+        return forest
 
     @classmethod
     def from_trees(cls, trees: Sequence, weights: Sequence[float], names: Sequence[str] | None = None) -> "Forest":

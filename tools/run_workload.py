@@ -1,4 +1,4 @@
-"""One synthetic workload through the product path (scs_forest_create + scs_supertree_build over the C ABI),
+"""One synthetic workload through the product path (scs_forest_create_view + scs_supertree_build over the C ABI),
 on 1 GPU or -- under torchrun -- on N GPUs with the large recursion nodes row-sharded over them.
 
     python tools/run_workload.py c5 [--repeat 2] [--shard-min-n 4096] [--out gpurun_out/c5.json]
