@@ -192,3 +192,42 @@ def test_a_taxon_on_two_tips_of_one_tree_is_rejected():
         Forest.from_trees(trees, [1.0, 1.0])
     with pytest.raises(Exception, match="more than one tip"):
         Forest.from_newick("((a,b),(c,d));\n(a,a,(b,c));\n")
+
+
+def test_forest_view_equals_forest_copy():
+    """``scs_forest_create_view`` (the forest refers to the caller's per-node arrays) against ``scs_forest_create``
+    (the library's own copy): same tours, same restrictions, same validation errors; a forest created without
+    lengths / supports still gets its own NaN arrays."""
+    from spectralclustersupertree_b200.engine import ScsError
+    from spectralclustersupertree_b200.synthetic import make_problem
+
+    arrays = make_problem(400, 60, "branch", 11, tree_weights=True).forest_arrays()
+
+    def forest(copy, **override):
+        a = {**arrays, **override}
+        return Forest.from_arrays(a["node_offsets"], a["parent"], a["length"], a["support"], a["taxon"], a["weights"],
+                                  a["names"], copy=copy)  # fmt: skip
+
+    owned, view = forest(True), forest(False)
+    for weighting in ("one", "depth", "branch"):
+        assert_same_tours(owned.tours(weighting), view.tours(weighting))
+    keep = np.arange(0, len(arrays["names"]), 3, dtype=np.int32)
+    a, b = owned.induce(keep), view.induce(keep)
+    assert a.num_trees == b.num_trees
+    assert_same_tours(a.tours("branch"), b.tours("branch"))
+    # the arrays the caller does not have are made by the library in either mode
+    bare = forest(False, length=None, support=None)
+    assert_same_tours(bare.tours("depth"), owned.tours("depth"))
+    assert np.all(bare.tours("branch").adj_val[bare.tours("branch").adj_depth > 0] >= 1.0)  # missing length counts 1
+    # validation sees the same input whoever owns it
+    broken = arrays["parent"].copy()
+    broken[5] = 7  # a parent index must be smaller than the node's own
+    for copy in (True, False):
+        with pytest.raises(ScsError):
+            forest(copy, parent=broken)
+    twice = arrays["taxon"].copy()
+    tips = np.flatnonzero(twice[: arrays["node_offsets"][1]] >= 0)
+    twice[tips[1]] = twice[tips[0]]  # the same taxon on two tips of the first tree
+    for copy in (True, False):
+        with pytest.raises(ScsError, match="more than one tip"):
+            forest(copy, taxon=twice)
