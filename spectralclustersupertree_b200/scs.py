@@ -13,7 +13,8 @@ reference (scs.py)                    here
 ``_get_graph_components``             CUDA union-find on the adjacency bits  (csrc/components.cu)
 ``_contract_proper_cluster_graph``    CUDA max-merge                         (csrc/contract.cu)
 ``spectral_cluster_graph``            CUDA Lanczos + exact 2-means           (csrc/spectral.cu)
-``_generate_induced_trees_…``         flat-array restriction, host C++       (csrc/forest.cpp)
+``_generate_induced_trees_…``         flat-array restriction on the device   (csrc/devforest.cu;
+                                      host twin for ``native=False``: csrc/forest.cpp)
 ====================================  ==========================================================
 
 There is no CPU fallback: without ``libscs_b200.so`` or a CUDA device the call raises.
@@ -77,14 +78,13 @@ def construct_supertree(
             node.name = ""
         return make_tree(trees[0].get_newick())
 
-    all_names: set[str] = set()
-    for tree in trees:
-        all_names.update(tree.get_tip_names())
-    if len(all_names) <= 2:  # ref: scs.py:105-106
-        return _star(sorted(all_names))
+    # one walk over the node objects yields the flat forest and the taxon names (ref: scs.py:100-103 collects the
+    # names with a get_tip_names() pass of its own)
+    forest = Forest.from_trees(trees, [float(w) for w in weights])
+    if len(forest.names) <= 2:  # ref: scs.py:105-106
+        return _star(forest.names)
 
     seed = 0 if random_state is None else int(random_state.randint(0, 2**31 - 1))
-    forest = Forest.from_trees(trees, [float(w) for w in weights], sorted(all_names))
     return supertree_of_forest(
         forest, pcg_weighting, contract_edges=contract_edges, seed=seed, engine=engine, trace=trace
     )

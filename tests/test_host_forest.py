@@ -231,3 +231,26 @@ def test_forest_view_equals_forest_copy():
     for copy in (True, False):
         with pytest.raises(ScsError, match="more than one tip"):
             forest(copy, taxon=twice)
+
+
+def test_from_trees_without_names_sorts_the_tip_names_it_finds():
+    """``construct_supertree`` lets the flattener collect the taxon names (no ``get_tip_names`` pass of its own,
+    ref: scs.py:100-103): taxon id = rank of the name in the sorted list, whatever order the tips are met in."""
+    case = load_case("s_300x40_branch_weighted")
+    trees = parse(case["lines"])
+    given = Forest.from_trees(trees, case["weights"], case["names"])
+    found = Forest.from_trees(trees, case["weights"])
+    assert found.names == sorted({x for t in trees for x in t.get_tip_names()}) == list(case["names"])
+    for t in range(given.num_trees):
+        for a, b in zip(given.tree_arrays(t), found.tree_arrays(t), strict=True):
+            assert np.array_equal(a, b, equal_nan=True)
+
+
+def test_two_taxa_give_a_star_without_touching_the_gpu():
+    """ref: scs.py:105-106 (and :96-98 for a single tree): decided on the host, before any device call."""
+    from spectralclustersupertree_b200 import construct_supertree
+
+    assert construct_supertree([make_tree("(a,b);"), make_tree("(b,a);")]).sorted().get_newick() == "(a,b);"
+    assert construct_supertree([make_tree("(b,a);"), make_tree("b;")], weights=[1, 2]).sorted().get_newick() == "(a,b);"
+    single = construct_supertree([make_tree("((a,b)x,(c,d)y);")])
+    assert single.sorted().same_shape(make_tree("((a,b),(c,d));").sorted())
