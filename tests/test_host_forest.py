@@ -254,3 +254,84 @@ def test_two_taxa_give_a_star_without_touching_the_gpu():
     assert construct_supertree([make_tree("(b,a);"), make_tree("b;")], weights=[1, 2]).sorted().get_newick() == "(a,b);"
     single = construct_supertree([make_tree("((a,b)x,(c,d)y);")])
     assert single.sorted().same_shape(make_tree("((a,b),(c,d));").sorted())
+
+
+def test_random_trees_restrict_like_get_sub_tree():
+    """Property test: random trees with unary chains, polytomies, missing lengths and supports.  ``induce`` and
+    ``induce_parts`` must give, node for node and bit for bit (lengths are sums whose operand order matters), the
+    arrays of ``get_sub_tree(names, ignore_missing=True, as_rooted=True)`` applied to every tree (ref: scs.py:444-453),
+    and restricting the restricted forest again must still agree."""
+    from hypothesis import HealthCheck, given, settings
+    from hypothesis import strategies as st
+
+    from spectralclustersupertree_b200.tree import PhyloNode
+
+    taxa = [f"t{i}" for i in range(12)]
+    lengths = st.one_of(st.none(), st.floats(min_value=1e-3, max_value=10.0, allow_nan=False))
+    supports = st.one_of(st.none(), st.integers(min_value=0, max_value=100).map(float))
+
+    @st.composite
+    def tree(draw):
+        tips = draw(st.lists(st.sampled_from(taxa), min_size=1, max_size=10, unique=True))
+        nodes = [PhyloNode(name, None, draw(lengths), None) for name in tips]
+        while len(nodes) > 1:
+            # join 1..3 of the current subtrees under a new internal node (1 => a unary node)
+            k = draw(st.integers(min_value=1, max_value=min(3, len(nodes))))
+            picked = [nodes.pop(draw(st.integers(min_value=0, max_value=len(nodes) - 1))) for _ in range(k)]
+            if k == 1 and not nodes and draw(st.booleans()):
+                return picked[0]
+            nodes.append(PhyloNode("", picked, draw(lengths), draw(supports)))
+            if k == 1 and len(nodes) == 1 and draw(st.booleans()):
+                break  # a unary root
+        return nodes[0]
+
+    def arrays_of(forest):
+        return [forest.tree_arrays(t) for t in range(forest.num_trees)]
+
+    def reference_restriction(trees, weights, kept_names):
+        out, out_w = [], []
+        for t, w in zip(trees, weights, strict=True):
+            if len(kept_names.intersection(t.get_tip_names())) < 2:
+                continue
+            s = t.get_sub_tree(kept_names, ignore_missing=True, as_rooted=True)
+            s.name = "root"
+            out.append(s)
+            out_w.append(w)
+        return out, out_w
+
+    def same(got: Forest, want_trees, want_weights):
+        assert got.num_trees == len(want_trees)
+        if not want_trees:
+            return
+        assert np.array_equal(got.weights(), np.asarray(want_weights, dtype=np.float64))
+        want = Forest.from_trees(want_trees, want_weights, taxa)
+        for g, w in zip(arrays_of(got), arrays_of(want), strict=True):
+            gp, gl, gs, gt = g
+            wp, wl, ws, wt = w
+            assert np.array_equal(gp, wp) and np.array_equal(gt, wt)
+            # the new root's own length is dropped by both; every other node bit for bit
+            assert np.array_equal(gl[1:], wl[1:], equal_nan=True)
+            internal = gt < 0
+            assert np.array_equal(gs[internal][1:], ws[internal][1:], equal_nan=True)
+
+    @settings(max_examples=150, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(st.lists(tree(), min_size=1, max_size=5), st.lists(st.integers(0, 2), min_size=12, max_size=12))
+    def run(trees, assignment):
+        weights = [1.0 + 0.5 * i for i in range(len(trees))]
+        forest = Forest.from_trees(trees, weights, taxa)
+        part = np.asarray(assignment, dtype=np.int32)
+        part[part == 2] = -1
+        subs, _ = forest.induce_parts(part, 2)
+        for c in (0, 1):
+            kept = {taxa[i] for i in np.flatnonzero(part == c)}
+            want_trees, want_weights = reference_restriction(trees, weights, kept)
+            same(subs[c], want_trees, want_weights)
+            same(forest.induce(np.flatnonzero(part == c).astype(np.int32)), want_trees, want_weights)
+            # once more on the restricted forest: every other kept taxon
+            again = sorted(kept)[::2]
+            if len(again) >= 2 and want_trees:
+                ids = np.asarray([taxa.index(x) for x in again], dtype=np.int32)
+                t2, w2 = reference_restriction(want_trees, want_weights, set(again))
+                same(subs[c].induce(ids), t2, w2)
+
+    run()
