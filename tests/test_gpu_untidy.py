@@ -1,0 +1,76 @@
+"""GPU: source trees that are not tidy -- internal nodes with a single child (chains of them), polytomies, nodes
+without a length, a root with a single child, two-tip trees and lone tips -- against the CPU oracle's whole recursion
+(tests/golden/ctrace_untidy_<case>.json.gz, written by tests/golden/make_untidy.py: the reference's own semantics for
+such trees, ref: scs.py:560-562, 569-579, 624-631, and ``get_sub_tree``'s merging of unary nodes at every level below
+the top, ref: scs.py:444-453).  The fixtures and the synthetic workloads only hold tidy trees; these cases put the
+unary-node and missing-value handling of the device-resident forest (csrc/devforest.cu: tours, restriction) and of
+its host twin (csrc/forest.cpp) on the same footing."""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from helpers import compare_with_ctrace, flat_clades, load_ctrace, parse
+from spectralclustersupertree_b200.engine import Forest
+from spectralclustersupertree_b200.tree import make_tree
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("case", ["branch", "bootstrap", "depth"])
+def test_untidy_source_trees_against_the_oracle_trace(engine, case):
+    ctrace = load_ctrace(f"untidy_{case}")
+    trees = parse(ctrace["lines"])
+    names = sorted({x for t in trees for x in t.get_tip_names()})
+    assert len(names) == ctrace["names"]
+    weighting = ctrace["weighting"]
+
+    def build():
+        return engine.supertree_build(Forest.from_trees(trees, ctrace["weights"], names), weighting, record=True)
+
+    built = build()
+    # every recursion node: components, contracted size, Fiedler eigenvalue (1e-6), bipartition
+    report = compare_with_ctrace(built["records"], ctrace)
+    divergent = report.pop("divergent_sets")
+    assert report["compared"] + report["orphans"] == len(built["records"])
+    if not divergent:
+        assert len(built["records"]) == len(ctrace["nodes"])
+    gid = {name: i for i, name in enumerate(names)}
+    reference = {frozenset(gid[x] for x in clade) for clade in make_tree(ctrace["supertree"]).clade_sets()
+                 if 1 < len(clade) < len(names)}  # fmt: skip
+    ours = {c for c in flat_clades(built["parent"], built["taxon"]) if len(c) < len(names)}
+    outside = [c for c in ours ^ reference if not any(c <= d for d in divergent)]
+    assert not outside, (len(outside), len(ours ^ reference))
+    assert sorted(built["taxon"][built["taxon"] >= 0].tolist()) == list(range(len(names)))
+    # the host-forest driver (flat trees restricted by the host threads) takes the same recursion, bit for bit
+    engine.set_device_forest(False)
+    try:
+        on_host = build()
+    finally:
+        engine.set_device_forest(True)
+    assert len(on_host["records"]) == len(built["records"])
+    by_taxa = {taxa.tobytes(): (part, stats) for taxa, part, stats in on_host["records"]}
+    for taxa, part, stats in built["records"]:
+        opart, ostats = by_taxa[taxa.tobytes()]
+        assert stats.n_components == ostats.n_components and stats.contracted_size == ostats.contracted_size
+        assert np.array_equal(part, opart)
+        if stats.n_components == 1 and stats.contracted_size >= 3:
+            assert stats.eig[1] == ostats.eig[1], (len(taxa), stats.eig[1], ostats.eig[1])
+    assert flat_clades(on_host["parent"], on_host["taxon"]) == flat_clades(built["parent"], built["taxon"])
+    print(case, {k: v for k, v in report.items() if k != "divergent_nodes"}, "RF", len(ours ^ reference))
+
+
+@pytest.mark.parametrize("case", ["branch", "depth"])
+def test_untidy_source_trees_through_the_python_recursion(engine, case):
+    """The same cases through the reference-shaped loop (``native=False``: one C-ABI call per recursion node, trees
+    restricted by ``Forest.induce``): the same supertree as the native driver."""
+    from spectralclustersupertree_b200.scs import supertree_of_forest
+
+    ctrace = load_ctrace(f"untidy_{case}")
+    trees = parse(ctrace["lines"])
+    names = sorted({x for t in trees for x in t.get_tip_names()})
+    a = supertree_of_forest(Forest.from_trees(trees, ctrace["weights"], names), ctrace["weighting"], engine=engine, native=True)
+    b = supertree_of_forest(Forest.from_trees(trees, ctrace["weights"], names), ctrace["weighting"], engine=engine, native=False)
+    assert a.clade_sets() == b.clade_sets()
+    assert a.clade_sets() == make_tree(ctrace["supertree"]).clade_sets()

@@ -335,3 +335,23 @@ def test_random_trees_restrict_like_get_sub_tree():
                 same(subs[c].induce(ids), t2, w2)
 
     run()
+
+
+@pytest.mark.parametrize("case", ["branch", "bootstrap", "depth"])
+def test_untidy_trees_flatten_and_parse_alike(case):
+    """The untidy golden cases (unary chains, polytomies, missing lengths, unary roots, two-tip trees, lone tips):
+    the host forest's tours equal the Python flattening, and the native Newick parser builds the forest that
+    ``make_tree`` + ``Forest.from_trees`` build."""
+    from helpers import load_ctrace
+
+    ctrace = load_ctrace(f"untidy_{case}")
+    trees = parse(ctrace["lines"])
+    names = sorted({x for t in trees for x in t.get_tip_names()})
+    tid = {x: i for i, x in enumerate(names)}
+    forest = Forest.from_trees(trees, ctrace["weights"], names)
+    assert_same_tours(forest.tours(ctrace["weighting"]), flatten_trees(trees, ctrace["weights"], ctrace["weighting"], tid))
+    parsed = Forest.from_newick("\n".join(ctrace["lines"]) + "\n")
+    assert parsed.names == names and parsed.num_trees == forest.num_trees
+    for t in range(forest.num_trees):
+        for a, b in zip(parsed.tree_arrays(t), forest.tree_arrays(t), strict=True):
+            assert np.array_equal(a, b, equal_nan=True), t

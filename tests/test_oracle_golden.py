@@ -106,3 +106,33 @@ def test_row_block_oracle_equals_the_dense_oracle(name):
         Wr, Cr = scs_oracle.pcg_rows_c_arrays(n, *arrs, case["weights"], case["weighting"], lo, hi)
         assert np.array_equal(Wr, case["pcg"]["W"][lo:hi])
         assert np.array_equal(Cr, case["pcg"]["C"][lo:hi])
+
+
+@pytest.mark.parametrize("case", ["bootstrap", "depth"])
+def test_untidy_traces_are_reproduced_by_the_oracle(case):
+    """tests/golden/ctrace_untidy_*.json.gz (source trees with unary chains, polytomies, missing lengths, unary
+    roots; made by tests/golden/make_untidy.py) pin what the GPU tests compare with: the oracle run here must give
+    the same recursion nodes, components, contracted sizes and partitions again."""
+    import sys
+
+    from pathlib import Path
+
+    from helpers import load_ctrace
+
+    tools = str(Path(__file__).resolve().parent.parent / "tools")
+    if tools not in sys.path:
+        sys.path.insert(0, tools)
+    from oracle_run import trace_recursion
+
+    ctrace = load_ctrace(f"untidy_{case}")
+    trees = parse(ctrace["lines"])
+    names = sorted({x for t in trees for x in t.get_tip_names()})
+    assert ctrace["unary_nodes"] > 50 and ctrace["polytomies"] > 10
+    _, records, tree = trace_recursion(trees, ctrace["weights"], ctrace["weighting"], names, steer=True, seeds=ctrace["seeds"])
+    assert len(records) == len(ctrace["nodes"])
+    for got, want in zip(records, ctrace["nodes"], strict=True):
+        assert (got["key"], got["n"], got["nc"], got.get("m"), got.get("part")) == (
+            want["key"], want["n"], want["nc"], want.get("m"), want.get("part"))  # fmt: skip
+        if "eig" in want:
+            assert abs(got["eig"][0] - want["eig"][0]) < 1e-9
+    assert tree.clade_sets() == make_tree(ctrace["supertree"]).clade_sets()

@@ -91,23 +91,14 @@ def small_eigs(Wc: np.ndarray):
     return float(1.0 - vals[1]), float(1.0 - vals[2]), vecs[:, 1] / s
 
 
-def run(workload: str, trace_path: Path | None, steer: bool, seeds: int) -> dict:
-    from bench import WORKLOADS, describe
+def trace_recursion(trees, weights, weighting: str, names, steer: bool, seeds: int, want_trace: bool = True):
+    """The oracle's whole recursion on ``trees`` (PhyloNode objects; ``names`` = sorted taxon names, global taxon id
+    = index).  Returns ``(summary, compact trace records, supertree)``; the records are empty without ``want_trace``."""
     from oracle import scs_oracle
-    from spectralclustersupertree_b200.synthetic import make_problem
-    from spectralclustersupertree_b200.tree import make_tree
 
-    n, t, weighting, seed, tw = WORKLOADS[workload]
-    prob = make_problem(n, t, weighting, seed, tree_weights=tw)
-    t0 = time.perf_counter()
-    trees = prob.phylonodes()
-    parse_s = time.perf_counter() - t0
-    weights = [1.0] * len(trees) if prob.weights is None else list(prob.weights)
-    names = prob.names()
     gid = {name: i for i, name in enumerate(names)}
     scs_oracle._c_lib()
     records: list[dict] = []
-    want_trace = trace_path is not None
 
     def hook(record, Wc, side, groups):
         # side: sklearn's labels per contracted vertex; groups: vertex -> contracted vertex
@@ -173,8 +164,7 @@ def run(workload: str, trace_path: Path | None, steer: bool, seeds: int) -> dict
     hook_s = timers.pop("hook", 0.0)
     total = wall - hook_s
     out = {
-        "workload": workload, "describe": describe(workload), "seconds": total, "stages": timers,
-        "other_s": total - sum(timers.values()), "phylonode_build_s": parse_s, "hook_s": hook_s,
+        "seconds": total, "stages": timers, "other_s": total - sum(timers.values()), "hook_s": hook_s,
         "recursion_nodes": len(trace), "spectral_nodes": sum(1 for r in trace if "partition" in r),
         "cores": os.cpu_count(), "steered": bool(steer and want_trace),
     }  # fmt: skip
@@ -185,16 +175,40 @@ def run(workload: str, trace_path: Path | None, steer: bool, seeds: int) -> dict
             if "_info" in rec:
                 item.update(rec["_info"])
             records.append(item)
+    return out, records, tree
+
+
+def write_trace(trace_path: Path, payload: dict, tree) -> None:
+    from spectralclustersupertree_b200.tree import make_tree
+
+    payload["supertree"] = tree.get_newick()
+    opener = gzip.open if str(trace_path).endswith(".gz") else open
+    with opener(trace_path, "wt") as fh:
+        json.dump(payload, fh)
+    # the written supertree must parse back to the same clades
+    assert make_tree(payload["supertree"]).clade_sets() == tree.clade_sets()
+
+
+def run(workload: str, trace_path: Path | None, steer: bool, seeds: int) -> dict:
+    from bench import WORKLOADS, describe
+    from spectralclustersupertree_b200.synthetic import make_problem
+
+    n, t, weighting, seed, tw = WORKLOADS[workload]
+    prob = make_problem(n, t, weighting, seed, tree_weights=tw)
+    t0 = time.perf_counter()
+    trees = prob.phylonodes()
+    parse_s = time.perf_counter() - t0
+    weights = [1.0] * len(trees) if prob.weights is None else list(prob.weights)
+    names = prob.names()
+    want_trace = trace_path is not None
+    summary, records, tree = trace_recursion(trees, weights, weighting, names, steer, seeds, want_trace)
+    out = {"workload": workload, "describe": describe(workload), "phylonode_build_s": parse_s, **summary}
+    if want_trace:
         payload = dict(out)
         payload["names"] = len(names)
         payload["nodes"] = records
-        payload["supertree"] = tree.get_newick()
         payload["seeds"] = seeds
-        opener = gzip.open if str(trace_path).endswith(".gz") else open
-        with opener(trace_path, "wt") as fh:
-            json.dump(payload, fh)
-        # the written supertree must parse back to the same clades
-        assert make_tree(payload["supertree"]).clade_sets() == tree.clade_sets()
+        write_trace(trace_path, payload, tree)
     return out
 
 
