@@ -74,3 +74,68 @@ def test_untidy_source_trees_through_the_python_recursion(engine, case):
     b = supertree_of_forest(Forest.from_trees(trees, ctrace["weights"], names), ctrace["weighting"], engine=engine, native=False)
     assert a.clade_sets() == b.clade_sets()
     assert a.clade_sets() == make_tree(ctrace["supertree"]).clade_sets()
+
+
+def test_large_untidy_job(engine):
+    """5 000 taxa x 300 untidy source trees (branch weighting, tree weights): the top-level node takes the large-node
+    path (row kernel over staircases deepened by the unary chains, Lanczos on m ~ 5 000).  W, occurrences and adjacency
+    of that node bit for bit against the C oracle, contracted size and Fiedler eigenvalue (1e-6) against the oracle's
+    contraction + ARPACK; then the whole job through the device-forest and the host-forest drivers: the same
+    recursion, node for node."""
+    import sys
+    from pathlib import Path
+
+    from oracle import scs_oracle
+    from spectralclustersupertree_b200.engine import unpack_bits
+
+    root = Path(__file__).resolve().parent
+    for extra in (root / "golden", root.parent / "tools"):
+        if str(extra) not in sys.path:
+            sys.path.insert(0, str(extra))
+    import make_untidy
+    from oracle_run import small_eigs
+
+    make_untidy.CASES["large"] = (5000, 300, "branch", 9400, True)
+    lines, weights, weighting = make_untidy.untidy_lines("large")
+    trees = parse(lines)
+    names = sorted({x for t in trees for x in t.get_tip_names()})
+    tid = {x: i for i, x in enumerate(names)}
+    assert sum(1 for t in trees for node in t.preorder() if len(node.children) == 1) > 10000
+    W, C, occ = scs_oracle.pcg_dense_c(trees, weights, weighting, tid)
+
+    forest = Forest.from_trees(trees, weights, names)
+    taxa, part, stats = engine.forest_split(forest, weighting, contract_edges=True, seed=1)
+    bufs = engine.last_node_buffers()
+    assert np.array_equal(bufs["W"], W), "W differs from the oracle"
+    assert np.array_equal(bufs["occ"], occ), "occ differs from the oracle"
+    assert np.array_equal(unpack_bits(bufs["adj_bits"], len(names)), C > 0), "adjacency differs"
+    label = scs_oracle.graph_components(C > 0)
+    assert stats.n_components == len(np.unique(label))
+    if stats.n_components == 1:
+        _, Wc, _ = scs_oracle.contract_dense(W, C, occ)
+        assert stats.contracted_size == Wc.shape[0]
+        lam2, _, _ = small_eigs(Wc)
+        assert abs(stats.eig[1] - lam2) < 1e-6, (stats.eig[1], lam2)
+    top_m = int(stats.contracted_size)
+    del W, C, bufs
+
+    def build():
+        return engine.supertree_build(Forest.from_trees(trees, weights, names), weighting, record=True)
+
+    on_device = build()
+    engine.set_device_forest(False)
+    try:
+        on_host = build()
+    finally:
+        engine.set_device_forest(True)
+    assert len(on_device["records"]) == len(on_host["records"])
+    by_taxa = {taxa.tobytes(): (part, stats) for taxa, part, stats in on_host["records"]}
+    for taxa, part, stats in on_device["records"]:
+        opart, ostats = by_taxa[taxa.tobytes()]
+        assert stats.n_components == ostats.n_components and stats.contracted_size == ostats.contracted_size
+        assert np.array_equal(part, opart), len(taxa)
+        if stats.n_components == 1 and stats.contracted_size >= 3:
+            assert stats.eig[1] == ostats.eig[1], (len(taxa), stats.eig[1], ostats.eig[1])
+    assert flat_clades(on_device["parent"], on_device["taxon"]) == flat_clades(on_host["parent"], on_host["taxon"])
+    assert sorted(on_device["taxon"][on_device["taxon"] >= 0].tolist()) == list(range(len(names)))
+    print("large untidy:", len(on_device["records"]), "recursion nodes, top-level m", top_m)
