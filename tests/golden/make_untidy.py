@@ -35,7 +35,26 @@ CASES = {
     "branch": (150, 40, "branch", 9100, True),
     "bootstrap": (120, 30, "bootstrap", 9200, False),
     "depth": (200, 40, "depth", 9300, False),
+    # the same kind of trees with contract_edges=False (ref: scs.py:23,124-133): the spectral step on the whole graph
+    "nocontract": (400, 50, "depth", 9500, False),
+    # 20 bushy trees + 12 caterpillars of ~750 tips each (tip order = model order with noise): leaf tours more than
+    # 1024 levels deep at the top of the recursion, long chains of unary nodes to merge below it
+    "caterpillar": (1500, 20, "branch", 9600, False),
 }
+NO_CONTRACTION = {"nocontract"}
+
+
+def caterpillars(n: int, count: int, rng: np.random.RandomState) -> list[str]:
+    """``count`` caterpillar trees ((((a,b),c),d),...) on random halves of t0..t{n-1}, with branch lengths."""
+    lines = []
+    for _ in range(count):
+        picked = np.flatnonzero(rng.random_sample(n) < 0.5)
+        order = picked[np.argsort(picked + rng.normal(0.0, 0.02 * n, size=len(picked)), kind="stable")]
+        text = f"(t{order[0]}:{rng.uniform(0.1, 1.0)!r},t{order[1]}:{rng.uniform(0.1, 1.0)!r})"
+        for x in order[2:]:
+            text = f"({text}:{rng.uniform(0.1, 1.0)!r},t{x}:{rng.uniform(0.1, 1.0)!r})"
+        lines.append(text + ";")
+    return lines
 
 
 def make_untidy(topo, weighting: str, rng: np.random.RandomState) -> None:
@@ -98,6 +117,10 @@ def untidy_lines(case: str) -> tuple[list[str], list[float], str]:
     inner = "75" if weighting == "bootstrap" else ""  # the only side of a unary root is weighted like any other node
     lines += [f"({tips[0]},{tips[-1]});", f"{tips[1]};", f"(({tips[2]},{tips[3]}){inner});"]
     weights += [1.5, 1.0, 2.0]
+    if case == "caterpillar":
+        extra = caterpillars(n, 12, rng)
+        lines += extra
+        weights += [1.0] * len(extra)
     return lines, weights, weighting
 
 
@@ -105,16 +128,18 @@ def main() -> None:
     from helpers import parse
     from oracle_run import trace_recursion, write_trace
 
-    for case in CASES:
+    for case in sys.argv[1:] or CASES:
         lines, weights, weighting = untidy_lines(case)
         trees = parse(lines)
         names = sorted({x for t in trees for x in t.get_tip_names()})
         unary = sum(1 for t in trees for node in t.preorder() if len(node.children) == 1)
         wide = sum(1 for t in trees for node in t.preorder() if len(node.children) > 2)
         missing = sum(1 for t in trees for node in t.preorder(include_self=False) if node.length is None)
-        summary, records, tree = trace_recursion(trees, weights, weighting, names, steer=True, seeds=12)
+        contract = case not in NO_CONTRACTION
+        summary, records, tree = trace_recursion(trees, weights, weighting, names, steer=True, seeds=12,
+                                                 contract_edges=contract)  # fmt: skip
         payload = {
-            "case": case, "weighting": weighting, "lines": lines, "weights": weights, "names": len(names),
+            "case": case, "weighting": weighting, "contract_edges": contract, "lines": lines, "weights": weights, "names": len(names),
             "unary_nodes": unary, "polytomies": wide, "nodes_without_length": missing, "nodes": records, "seeds": 12,
             **summary,
         }  # fmt: skip

@@ -18,20 +18,31 @@ from spectralclustersupertree_b200.tree import make_tree
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("case", ["branch", "bootstrap", "depth"])
+# case -> nodes where sklearn's k-means returned the same Lloyd-stable but non-optimal split for every seed tried while
+# the exact 2-means takes the optimum (reported as mismatches, like s_150x40_one in tests/helpers.py).  The caterpillar
+# case is built to have them: a caterpillar's Fiedler coordinate is a chain with many Lloyd-stable cuts (477 of its 916
+# spectral nodes have more than one), and at two nodes (m = 433 and m = 39) the reference's restarts never find the best.
+EXPECTED_MISMATCHES = {"caterpillar": 2}
+
+
+@pytest.mark.parametrize("case", ["branch", "bootstrap", "depth", "nocontract", "caterpillar"])
 def test_untidy_source_trees_against_the_oracle_trace(engine, case):
+    """``nocontract``: the same kind of trees with ``contract_edges=False`` (ref: scs.py:23, 124-133).  ``caterpillar``:
+    20 bushy trees + 12 caterpillars of ~750 tips: leaf tours more than 1 024 levels deep, long unary chains to merge."""
     ctrace = load_ctrace(f"untidy_{case}")
+    contract = ctrace.get("contract_edges", True)
     trees = parse(ctrace["lines"])
     names = sorted({x for t in trees for x in t.get_tip_names()})
     assert len(names) == ctrace["names"]
     weighting = ctrace["weighting"]
 
     def build():
-        return engine.supertree_build(Forest.from_trees(trees, ctrace["weights"], names), weighting, record=True)
+        return engine.supertree_build(Forest.from_trees(trees, ctrace["weights"], names), weighting,
+                                      contract_edges=contract, record=True)  # fmt: skip
 
     built = build()
     # every recursion node: components, contracted size, Fiedler eigenvalue (1e-6), bipartition
-    report = compare_with_ctrace(built["records"], ctrace)
+    report = compare_with_ctrace(built["records"], ctrace, expected_mismatches=EXPECTED_MISMATCHES.get(case, 0))
     divergent = report.pop("divergent_sets")
     assert report["compared"] + report["orphans"] == len(built["records"])
     if not divergent:

@@ -337,7 +337,7 @@ def test_random_trees_restrict_like_get_sub_tree():
     run()
 
 
-@pytest.mark.parametrize("case", ["branch", "bootstrap", "depth"])
+@pytest.mark.parametrize("case", ["branch", "bootstrap", "depth", "caterpillar"])
 def test_untidy_trees_flatten_and_parse_alike(case):
     """The untidy golden cases (unary chains, polytomies, missing lengths, unary roots, two-tip trees, lone tips):
     the host forest's tours equal the Python flattening, and the native Newick parser builds the forest that

@@ -108,7 +108,7 @@ def test_row_block_oracle_equals_the_dense_oracle(name):
         assert np.array_equal(Cr, case["pcg"]["C"][lo:hi])
 
 
-@pytest.mark.parametrize("case", ["bootstrap", "depth"])
+@pytest.mark.parametrize("case", ["bootstrap", "depth", "nocontract"])
 def test_untidy_traces_are_reproduced_by_the_oracle(case):
     """tests/golden/ctrace_untidy_*.json.gz (source trees with unary chains, polytomies, missing lengths, unary
     roots; made by tests/golden/make_untidy.py) pin what the GPU tests compare with: the oracle run here must give
@@ -128,7 +128,8 @@ def test_untidy_traces_are_reproduced_by_the_oracle(case):
     trees = parse(ctrace["lines"])
     names = sorted({x for t in trees for x in t.get_tip_names()})
     assert ctrace["unary_nodes"] > 50 and ctrace["polytomies"] > 10
-    _, records, tree = trace_recursion(trees, ctrace["weights"], ctrace["weighting"], names, steer=True, seeds=ctrace["seeds"])
+    _, records, tree = trace_recursion(trees, ctrace["weights"], ctrace["weighting"], names, steer=True,
+                                       seeds=ctrace["seeds"], contract_edges=ctrace.get("contract_edges", True))  # fmt: skip
     assert len(records) == len(ctrace["nodes"])
     for got, want in zip(records, ctrace["nodes"], strict=True):
         assert (got["key"], got["n"], got["nc"], got.get("m"), got.get("part")) == (

@@ -91,7 +91,8 @@ def small_eigs(Wc: np.ndarray):
     return float(1.0 - vals[1]), float(1.0 - vals[2]), vecs[:, 1] / s
 
 
-def trace_recursion(trees, weights, weighting: str, names, steer: bool, seeds: int, want_trace: bool = True):
+def trace_recursion(trees, weights, weighting: str, names, steer: bool, seeds: int, want_trace: bool = True,
+                    contract_edges: bool = True):
     """The oracle's whole recursion on ``trees`` (PhyloNode objects; ``names`` = sorted taxon names, global taxon id
     = index).  Returns ``(summary, compact trace records, supertree)``; the records are empty without ``want_trace``."""
     from oracle import scs_oracle
@@ -157,7 +158,7 @@ def trace_recursion(trees, weights, weighting: str, names, steer: bool, seeds: i
     trace: list = []
     t0 = time.perf_counter()
     tree = scs_oracle.construct_supertree(
-        trees, weights, weighting, random_state=np.random.RandomState(0), use_c=True,
+        trees, weights, weighting, random_state=np.random.RandomState(0), use_c=True, contract_edges=contract_edges,
         trace=trace, timers=timers, node_hook=hook if want_trace else None,
     )  # fmt: skip
     wall = time.perf_counter() - t0
