@@ -4,7 +4,7 @@
 
 For every golden case recorded from the UNMODIFIED reference (tests/golden/trace_*.json: the reference's three
 fixtures, C1, C2, C3 and three more synthetic cases) and for the full-size compact traces of the oracle's whole
-recursion (tests/golden/ctrace_c3 / ctrace_c4), the native build is compared node by node (components, contracted
+recursion (tests/golden/ctrace_c3 / ctrace_c4, and the five untidy-source-tree cases ctrace_untidy_*), the native build is compared node by node (components, contracted
 size, Fiedler eigenvalue, bipartition) and the final supertrees by Robinson-Foulds distance.  Divergent nodes are
 listed by type:
   eigengap_tie / margin_tie   the near-ties the parity contract allows (lambda_3 - lambda_2 < 1e-7; a vertex within
@@ -94,6 +94,41 @@ def ctrace_case(engine, workload: str) -> dict:
     }  # fmt: skip
 
 
+# mismatches known and counted (tests/test_gpu_untidy.py:EXPECTED_MISMATCHES)
+UNTIDY_CASES = {"branch": 0, "bootstrap": 0, "depth": 0, "nocontract": 0, "caterpillar": 2}
+
+
+def untidy_case(engine, case: str, expected_mismatches: int) -> dict:
+    """Source trees with unary chains, polytomies, missing lengths, unary roots (tests/golden/make_untidy.py)."""
+    import helpers
+    from spectralclustersupertree_b200.engine import Forest
+    from spectralclustersupertree_b200.tree import make_tree
+
+    ctrace = helpers.load_ctrace(f"untidy_{case}")
+    trees = helpers.parse(ctrace["lines"])
+    names = sorted({x for t in trees for x in t.get_tip_names()})
+    built = engine.supertree_build(Forest.from_trees(trees, ctrace["weights"], names), ctrace["weighting"],
+                                   contract_edges=ctrace.get("contract_edges", True), record=True)  # fmt: skip
+    report = helpers.compare_with_ctrace(built["records"], ctrace, expected_mismatches=expected_mismatches)
+    divergent = report.pop("divergent_sets")
+    gid = {name: i for i, name in enumerate(names)}
+    reference = {frozenset(gid[x] for x in clade) for clade in make_tree(ctrace["supertree"]).clade_sets()
+                 if 1 < len(clade) < len(names)}  # fmt: skip
+    ours = {c for c in helpers.flat_clades(built["parent"], built["taxon"]) if len(c) < len(names)}
+    diff = ours ^ reference
+    return {
+        "against": f"the CPU oracle's whole recursion (tests/golden/ctrace_untidy_{case}.json.gz)",
+        "weighting": ctrace["weighting"], "contract_edges": ctrace.get("contract_edges", True), "taxa": len(names),
+        "trees": len(trees), "unary_nodes": ctrace["unary_nodes"], "polytomies": ctrace["polytomies"],
+        "nodes_without_length": ctrace["nodes_without_length"], "oracle_recursion_nodes": len(ctrace["nodes"]),
+        "our_recursion_nodes": len(built["records"]), "nodes_compared": report["compared"],
+        "spectral_nodes_compared": report["spectral"], "divergences": report["divergences"],
+        "divergent_nodes": report["divergent_nodes"], "orphans": report["orphans"],
+        "max_fiedler_eigenvalue_error": report["max_eig_error"], "rf_vs_oracle_supertree": len(diff),
+        "rf_outside_divergent_subtrees": sum(1 for c in diff if not any(c <= d for d in divergent)),
+    }  # fmt: skip
+
+
 def main() -> None:
     parser = argparse.ArgumentParser()
     parser.add_argument("--out", type=Path, default=ROOT / "PARITY.json")
@@ -103,11 +138,15 @@ def main() -> None:
 
     out = {"thresholds": {"eigengap_tie": helpers.GAP_TIE, "margin_tie": helpers.MARGIN_TIE, "fiedler_eigenvalue": 1e-6,
                           "W": "bit-exact, all four weightings (tests/test_gpu_parity.py)"},
-           "golden_cases": {}, "full_size": {}}  # fmt: skip
+           "golden_cases": {}, "full_size": {}, "untidy_source_trees": {}}  # fmt: skip
     with Engine(0) as engine:
         for name in helpers.CASES:
             out["golden_cases"][name] = golden_case(engine, name)
             print(name, out["golden_cases"][name]["divergences"], "RF", out["golden_cases"][name]["rf_vs_reference_supertree"])
+        for case, allowed in UNTIDY_CASES.items():
+            out["untidy_source_trees"][case] = untidy_case(engine, case, allowed)
+            print("untidy", case, out["untidy_source_trees"][case]["divergences"], "RF",
+                  out["untidy_source_trees"][case]["rf_vs_oracle_supertree"])  # fmt: skip
         for workload in ("c3", "c4"):
             out["full_size"][workload] = ctrace_case(engine, workload)
             print(workload, out["full_size"][workload]["divergences"], "RF", out["full_size"][workload]["rf_vs_oracle_supertree"])
@@ -116,7 +155,7 @@ def main() -> None:
                  "bit for bit with the C oracle and the Fiedler eigenvalue of the first connected node with ARPACK on the same operator; "
                  "the supertree's clade checksum is identical at 1, 2, 4 and 8 GPUs (profiles/README.md)")
     totals = {"nodes_compared": 0, "spectral_nodes_compared": 0, "divergences": {}}
-    for section in ("golden_cases", "full_size"):
+    for section in ("golden_cases", "full_size", "untidy_source_trees"):
         for rep in out[section].values():
             totals["nodes_compared"] += rep["nodes_compared"]
             totals["spectral_nodes_compared"] += rep["spectral_nodes_compared"]
