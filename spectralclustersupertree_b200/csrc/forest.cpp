@@ -85,6 +85,8 @@ static int forest_create(int T, const int64_t *node_offsets, const int32_t *pare
     if (M < 0 || (M > 0 && (!parent || !taxon))) return SCS_ERR_INVALID;
     if (T > 0 && !tree_weight) return SCS_ERR_INVALID;
     tune_allocator_once();
+    const bool trace = std::getenv("SCS_FOREST_TRACE") != nullptr;
+    const double t_begin = trace ? omp_get_wtime() : 0.0;
     scs_forest *f = new (std::nothrow) scs_forest();
     if (!f) return SCS_ERR_INVALID;
     f->num_taxa = num_taxa;
@@ -111,10 +113,11 @@ static int forest_create(int T, const int64_t *node_offsets, const int32_t *pare
     std::vector<int64_t> tips(static_cast<size_t>(T), 0);
     bool all_ok = true, repeated = false;
     g_forest_error = "";
+    const double t_arrays = trace ? omp_get_wtime() : 0.0;
     // validation and shape of every tree: independent, over the host threads
 #pragma omp parallel if (M > kParallelNodes) num_threads(scs_host_threads())
     {
-        std::vector<int32_t> kids;
+        std::vector<int32_t> kids, tip_taxa;
         // a taxon may label one tip of a tree only: the graph kernels give every leaf of a tree its own column
         // and add to it without atomics (pcg.cu, small.cu)
         std::vector<int32_t> seen_in(static_cast<size_t>(num_taxa > 0 ? num_taxa : 1), -1);
@@ -122,37 +125,43 @@ static int forest_create(int T, const int64_t *node_offsets, const int32_t *pare
         for (int t = 0; t < T; ++t) {
             f->source[t] = t;
             const int64_t base = node_offsets[t], count = node_offsets[t + 1] - base;
-            // one pass: parent indices, tips (pre-order: a node is a tip iff the next node is not its child), tip
-            // taxa, repeated taxa, children per node; then whether every internal node branches
+            // Pass 1: parent indices, children per node, tips (pre-order: a node is a tip iff the next node is not its
+            // child), tip taxa in range, internal nodes unnamed.  Which nodes are tips is as good as random to a branch
+            // predictor (two mispredictions per node with `if (tip)`), so the pass accumulates flags with selects and
+            // compacts the tips' taxa; pass 2 looks for repeated taxa among those; pass 3: does every internal node branch.
             const int32_t *par = parent + base;
             const int32_t *tax = taxon + base;
-            bool ok = count >= 1 && par[0] == -1;
-            bool twice = false;
+            unsigned bad = !(count >= 1 && par[0] == -1);
+            const size_t room = static_cast<size_t>(count > 0 ? count : 0) + 1;
+            kids.assign(room, 0);  // slot `count` takes the increments of out-of-range parents
+            if (tip_taxa.size() < room) tip_taxa.resize(room);
+            int32_t *kid = kids.data(), *tip_taxon = tip_taxa.data();
+            const uint32_t taxa = static_cast<uint32_t>(num_taxa);
             int64_t tip_count = 0;
-            kids.assign(static_cast<size_t>(count > 0 ? count : 1), 0);
-            for (int64_t k = 0; ok && k < count; ++k) {
-                if (k >= 1) {
-                    const int32_t p = par[k];
-                    if (p < 0 || p >= k) {
-                        ok = false;
-                        break;
-                    }
-                    kids[p] += 1;
-                }
-                const bool tip = k + 1 >= count || par[k + 1] != k;
+            for (int64_t k = 0; k < count; ++k) {
+                const int32_t p = par[k];
+                const bool p_ok = static_cast<uint64_t>(static_cast<int64_t>(p)) < static_cast<uint64_t>(k);  // 0 <= p < k
+                bad |= static_cast<unsigned>(k >= 1) & static_cast<unsigned>(!p_ok);
+                kid[p_ok ? static_cast<int64_t>(p) : count] += 1;
+                const int32_t next_parent = k + 1 < count ? par[k + 1] : -2;
+                const bool tip = static_cast<int64_t>(next_parent) != k;
                 const int32_t x = tax[k];
-                if (tip) {
-                    if (x < 0 || x >= num_taxa) {
-                        ok = false;
-                        break;
-                    }
-                    if (seen_in[x] == t) twice = true;
-                    seen_in[x] = t;
-                    tip_count += 1;
-                } else if (x != -1) {
-                    ok = false;
+                const bool named = static_cast<uint32_t>(x) < taxa;  // 0 <= x < num_taxa
+                bad |= static_cast<unsigned>((tip & !named) | (!tip & (x != -1)));
+                tip_taxon[tip_count] = x;
+                tip_count += tip;
+            }
+            const bool ok = bad == 0;
+            unsigned twice_flag = 0;
+            if (ok) {
+                int32_t *seen = seen_in.data();
+                for (int64_t i = 0; i < tip_count; ++i) {
+                    const int32_t x = tip_taxon[i];
+                    twice_flag |= static_cast<unsigned>(seen[x] == t);
+                    seen[x] = t;
                 }
             }
+            const bool twice = twice_flag != 0;
             if (!ok || twice) {
 #pragma omp atomic write
                 all_ok = false;
@@ -162,10 +171,10 @@ static int forest_create(int T, const int64_t *node_offsets, const int32_t *pare
                 }
                 continue;
             }
-            bool branching = true;
-            for (int64_t k = 0; k < count && branching; ++k) branching = tax[k] >= 0 || kids[k] >= 2;
+            int64_t unary = 0;  // internal nodes with fewer than two children
+            for (int64_t k = 0; k < count; ++k) unary += static_cast<int64_t>(tax[k] < 0) & static_cast<int64_t>(kid[k] < 2);
             tips[t] = count > 1 ? tip_count : 0;  // a lone tip appears in no tour
-            f->branching[t] = branching ? 1 : 0;
+            f->branching[t] = unary == 0 ? 1 : 0;
         }
     }
     if (!all_ok) {
@@ -177,6 +186,10 @@ static int forest_create(int T, const int64_t *node_offsets, const int32_t *pare
     f->leaf_offsets.resize(static_cast<size_t>(T) + 1);
     f->leaf_offsets[0] = 0;
     for (int t = 0; t < T; ++t) f->leaf_offsets[t + 1] = f->leaf_offsets[t] + tips[t];
+    if (trace)
+        std::fprintf(stderr, "[scs forest] %d trees, %lld nodes, %s: arrays %.3f ms, validation %.3f ms (%d host threads)\n", T,
+                     static_cast<long long>(M), view ? "view" : "copy", 1e3 * (t_arrays - t_begin),
+                     1e3 * (omp_get_wtime() - t_arrays), scs_host_threads());
     *out = f;
     return SCS_OK;
 }

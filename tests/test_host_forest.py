@@ -113,6 +113,24 @@ def test_forest_rejects_malformed_arrays():
         Forest.from_arrays([0, 3], [-1, 2, 0], None, None, [-1, 0, 1], [1.0], ["a", "b"])
     with pytest.raises(ScsError):  # tip without a taxon id
         Forest.from_arrays([0, 3], [-1, 0, 0], None, None, [-1, 0, -1], [1.0], ["a", "b"])
+    bad = {
+        "internal node with a taxon id": ([0, 3], [-1, 0, 0], [1, 0, 1]),
+        "taxon id out of range": ([0, 3], [-1, 0, 0], [-1, 0, 2]),
+        "negative taxon id on a tip": ([0, 3], [-1, 0, 0], [-1, 0, -7]),
+        "first node is not a root": ([0, 3], [0, 0, 0], [-1, 0, 1]),
+        "negative parent below the root": ([0, 3], [-1, -1, 0], [-1, 0, 1]),
+        "a tree without nodes": ([0, 0, 3], [-1, 0, 0], [-1, 0, 1]),
+        "the last tree is wrong": ([0, 3, 6], [-1, 0, 0, -1, 0, 5], [-1, 0, 1, -1, 0, 1]),
+    }
+    for what, (offsets, parent, taxon) in bad.items():
+        weights = [1.0] * (len(offsets) - 1)
+        for copy in (False, True):
+            with pytest.raises(ScsError, match="not a valid pre-order tree"):
+                Forest.from_arrays(offsets, parent, None, None, taxon, weights, ["a", "b"], copy=copy)
+            assert what
+    # and the shapes that are fine: a lone tip, a unary chain, two trees
+    ok = Forest.from_arrays([0, 1, 4, 7], [-1, -1, 0, 1, -1, 0, 0], None, None, [0, -1, -1, 1, -1, 0, 1], [1.0, 1.0, 1.0], ["a", "b"])
+    assert ok.num_trees == 3 and ok.num_leaves == 3  # the lone tip is in no tour: 1 + 2 leaves
 
 
 @pytest.mark.parametrize("name", ["dcm_iq", "s_300x40_branch_weighted", "c2_500x50_branch"])
