@@ -38,6 +38,45 @@ static double number_or_nan(PyObject *obj)
     return v;
 }
 
+/* Direct slot access for node classes that declare `children`, `name`, `length`, `support` in __slots__ (the package's
+ * own PhyloNode does): the four attribute reads per node become pointer loads.  A class whose attributes are not all
+ * plain slot members (cogent3's PhyloNode, subclasses with properties) keeps the generic PyObject_GetAttr path. */
+typedef struct {
+    PyTypeObject *type; /* exact type the offsets belong to, NULL: none */
+    Py_ssize_t children, name, length, support;
+} SlotCache;
+
+static Py_ssize_t slot_offset(PyTypeObject *type, PyObject *attr)
+{
+    PyObject *descr = PyObject_GetAttr((PyObject *)type, attr); /* a slot member: the descriptor itself */
+    Py_ssize_t offset = -1;
+    if (descr == NULL) {
+        PyErr_Clear();
+        return -1;
+    }
+    if (Py_TYPE(descr) == &PyMemberDescr_Type) {
+        PyMemberDef *member = ((PyMemberDescrObject *)descr)->d_member;
+        if (member != NULL && member->type == Py_T_OBJECT_EX && member->offset > 0) offset = member->offset;
+    }
+    Py_DECREF(descr);
+    return offset;
+}
+
+static void slot_cache_fill(SlotCache *cache, PyObject *node, PyObject *s_children, PyObject *s_name, PyObject *s_length,
+                            PyObject *s_support)
+{
+    PyTypeObject *type = Py_TYPE(node);
+    cache->type = NULL;
+    if (type->tp_getattro != PyObject_GenericGetAttr) return; /* a custom __getattribute__ / __getattr__ */
+    cache->children = slot_offset(type, s_children);
+    cache->name = slot_offset(type, s_name);
+    cache->length = slot_offset(type, s_length);
+    cache->support = slot_offset(type, s_support);
+    if (cache->children > 0 && cache->name > 0 && cache->length > 0 && cache->support > 0) cache->type = type;
+}
+
+#define SLOT(node, offset) (*(PyObject **)((char *)(node) + (offset)))
+
 /* children of a node as a new reference to a list */
 static PyObject *children_of(PyObject *node, PyObject *s_children)
 {
@@ -68,6 +107,8 @@ static PyObject *flatten(PyObject *self, PyObject *args)
     PyObject *name_ids = PyDict_New(), *names = PyList_New(0);
     Buf offsets = {0}, parent = {0}, length = {0}, support = {0}, taxon = {0}, stack = {0};
     PyObject *result = NULL;
+    SlotCache slots = {NULL, -1, -1, -1, -1};
+    int slots_tried = 0;
     int64_t total = 0;
     if (buf_push(&offsets, &total, sizeof total)) goto oom;
     const Py_ssize_t T = PySequence_Fast_GET_SIZE(seq);
@@ -84,20 +125,39 @@ static PyObject *flatten(PyObject *self, PyObject *args)
             memcpy(&item, stack.data + stack.size, sizeof item);
             PyObject *node = item.node;
             const int32_t k = (int32_t)(total - base);
-            PyObject *len_o = PyObject_GetAttr(node, s_length);
-            if (!len_o) PyErr_Clear();
-            PyObject *sup_o = PyObject_GetAttr(node, s_support);
-            if (!sup_o) PyErr_Clear();
-            const double len_v = number_or_nan(len_o), sup_v = number_or_nan(sup_o);
-            Py_XDECREF(len_o);
-            Py_XDECREF(sup_o);
-            if (PyErr_Occurred()) { Py_DECREF(node); goto fail; }
-            PyObject *kids = children_of(node, s_children);
-            if (!kids) { Py_DECREF(node); goto fail; }
+            if (!slots_tried) { /* the first node decides whether its class qualifies for direct slot reads */
+                slots_tried = 1;
+                slot_cache_fill(&slots, node, s_children, s_name, s_length, s_support);
+            }
+            PyObject *kids = NULL;
+            double len_v, sup_v;
+            const int direct = slots.type != NULL && Py_TYPE(node) == slots.type && SLOT(node, slots.children) != NULL &&
+                               PyList_CheckExact(SLOT(node, slots.children));
+            if (direct) {
+                len_v = number_or_nan(SLOT(node, slots.length)); /* an unset slot reads as NULL: missing */
+                sup_v = number_or_nan(SLOT(node, slots.support));
+                if (PyErr_Occurred()) { Py_DECREF(node); goto fail; }
+                kids = SLOT(node, slots.children);
+                Py_INCREF(kids);
+            } else {
+                PyObject *len_o = PyObject_GetAttr(node, s_length);
+                if (!len_o) PyErr_Clear();
+                PyObject *sup_o = PyObject_GetAttr(node, s_support);
+                if (!sup_o) PyErr_Clear();
+                len_v = number_or_nan(len_o);
+                sup_v = number_or_nan(sup_o);
+                Py_XDECREF(len_o);
+                Py_XDECREF(sup_o);
+                if (PyErr_Occurred()) { Py_DECREF(node); goto fail; }
+                kids = children_of(node, s_children);
+                if (!kids) { Py_DECREF(node); goto fail; }
+            }
             const Py_ssize_t nk = PyList_GET_SIZE(kids);
             int32_t tax = -1;
             if (nk == 0) {
-                PyObject *name = PyObject_GetAttr(node, s_name);
+                PyObject *name = direct ? SLOT(node, slots.name) : NULL;
+                if (name) Py_INCREF(name);
+                else name = PyObject_GetAttr(node, s_name); /* also raises the AttributeError of an unset slot */
                 if (!name) { Py_DECREF(kids); Py_DECREF(node); goto fail; }
                 PyObject *id = PyDict_GetItemWithError(name_ids, name); /* borrowed */
                 if (!id) {

@@ -373,3 +373,60 @@ def test_untidy_trees_flatten_and_parse_alike(case):
     for t in range(forest.num_trees):
         for a, b in zip(parsed.tree_arrays(t), forest.tree_arrays(t), strict=True):
             assert np.array_equal(a, b, equal_nan=True), t
+
+
+def test_flattener_reads_slots_directly_and_other_classes_generically():
+    """csrc/fastflatten.c reads ``children`` / ``name`` / ``length`` / ``support`` straight out of the slots of a node
+    class that declares them in ``__slots__`` (the package's PhyloNode) and goes through ``getattr`` for anything else
+    (subclasses, classes with a ``__dict__``, tuples of children, cogent3's own class): same arrays either way, same
+    errors for an unset name and a length that is not a number."""
+    from spectralclustersupertree_b200.tree import PhyloNode
+
+    class Sub(PhyloNode):
+        pass
+
+    class Plain:
+        def __init__(self, name, kids=(), length=None):
+            self.name, self.children, self.length = name, list(kids), length
+
+        def __iter__(self):
+            return iter(self.children)
+
+    class TupleKids:
+        __slots__ = ("children", "length", "name", "support")
+
+        def __init__(self, name, kids=(), length=None):
+            self.name, self.children, self.length, self.support = name, tuple(kids), length, None
+
+    def shaped(cls):  # ((a:1,b:2):3,(c:1,d:4):2) in class `cls`
+        def node(name, kids=(), length=None):
+            made = cls(name, list(kids)) if cls in (PhyloNode, Sub) else cls(name, kids)
+            made.length = length
+            return made
+
+        return node("root", [node("", [node("a", (), 1.0), node("b", (), 2.0)], 3.0),
+                             node("", [node("c", (), 1.0), node("d", (), 4.0)], 2.0)])  # fmt: skip
+
+    want = Forest.from_trees([make_tree("((a:1,b:2):3,(c:1,d:4):2);")], [1.0])
+    for cls in (PhyloNode, Sub, Plain, TupleKids):
+        got = Forest.from_trees([shaped(cls)], [1.0])
+        assert got.names == want.names
+        for a, b in zip(got.tree_arrays(0), want.tree_arrays(0), strict=True):
+            assert np.array_equal(a, b, equal_nan=True), cls.__name__
+    # classes mixed within one call: the first node's class gets the direct path, the others the generic one
+    mixed = Forest.from_trees([shaped(PhyloNode), shaped(Plain), shaped(Sub)], [1.0, 1.0, 1.0])
+    for t in range(3):
+        for a, b in zip(mixed.tree_arrays(t), want.tree_arrays(0), strict=True):
+            assert np.array_equal(a, b, equal_nan=True)
+
+    class Bare:
+        __slots__ = ("children", "length", "name", "support")
+
+    bare = Bare()
+    bare.children = []
+    with pytest.raises(AttributeError):
+        Forest.from_trees([bare], [1.0])
+    odd = PhyloNode("a")
+    odd.length = "long"
+    with pytest.raises(TypeError):
+        Forest.from_trees([PhyloNode("r", [odd, PhyloNode("b")])], [1.0])
