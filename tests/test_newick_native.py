@@ -208,3 +208,38 @@ def test_flat_supertree_is_written_as_newick_natively():
         expected = _tree_from_flat(parent_a, taxon_a, names)
         assert text == expected.get_newick()
         assert make_tree(text).clade_sets() == expected.clade_sets()
+
+
+def test_branch_lengths_parse_like_float():
+    """Branch lengths go through ``std::from_chars`` where they are plain decimals and through ``strtod`` otherwise:
+    every form must give the double ``make_tree`` (Python's ``float``) gives, bit for bit, or be refused by both."""
+    import struct
+
+    rng = np.random.RandomState(3)
+    forms = ["0", "-0.0", "1", "007", "1.", ".5", "-.5", "+.5", "+3", "1e3", "1E3", "1e+3", "1e-3", "2.5E+1", "1e308", "1e-308",
+             "4.9e-324", "2e-324", "1e400", "-1e400", "1e-400", "0.1", "0.30000000000000004", "123456789012345678901234567890",
+             "3.141592653589793238462643383279", "9007199254740993", "1.7976931348623157e308", "inf", "-inf", "Infinity", "nan",
+             "1_0", "1_000.5", "1e1_0", "0_1.2_5"]  # fmt: skip
+    forms += [repr(float(v)) for v in rng.uniform(0, 1, 200)]
+    forms += [repr(float(v)) for v in 10.0 ** rng.uniform(-30, 30, 200)]
+    forms += [f"{v:.3f}" for v in rng.uniform(0, 100, 100)]
+    lines = [f"(a:{form},b:1);" for form in forms]
+    native = Forest.from_newick("\n".join(lines))
+    try:
+        assert native.num_trees == len(forms)
+        for t, form in enumerate(forms):
+            got = native.tree_arrays(t)[1][1]
+            want = make_tree(lines[t]).children[0].length
+            assert struct.pack("<d", got) == struct.pack("<d", want) or (np.isnan(got) and np.isnan(want)), (form, got, want)
+    finally:
+        native.close()
+    for form in ["0x10", "0x1p3", "1e", "e5", "--1", "1..2", "one", "_1", "1_", "1__0", "1_.5", "1._5", "-", "+", "."]:
+        line = f"(a:{form},b:1);"
+        python_refuses = False
+        try:
+            make_tree(line)
+        except NewickError:
+            python_refuses = True
+        assert python_refuses, form
+        with pytest.raises(NewickError):
+            Forest.from_newick(line + "\n")
