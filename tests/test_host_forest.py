@@ -332,7 +332,7 @@ def test_random_trees_restrict_like_get_sub_tree():
             internal = gt < 0
             assert np.array_equal(gs[internal][1:], ws[internal][1:], equal_nan=True)
 
-    @settings(max_examples=150, deadline=None, suppress_health_check=list(HealthCheck))
+    @settings(max_examples=150, deadline=None, derandomize=True, database=None, suppress_health_check=list(HealthCheck))
     @given(st.lists(tree(), min_size=1, max_size=5), st.lists(st.integers(0, 2), min_size=12, max_size=12))
     def run(trees, assignment):
         weights = [1.0 + 0.5 * i for i in range(len(trees))]

@@ -147,7 +147,7 @@ def test_random_newick_agrees_with_the_python_parser():
             text += space + ":" + space + draw(number)
         return space + text + space
 
-    @settings(max_examples=150, deadline=None)
+    @settings(max_examples=150, deadline=None, derandomize=True, database=None)
     @given(st.lists(newick(), min_size=1, max_size=5), st.booleans())
     def check(trees, semicolon):
         lines = [t + (";" if semicolon else "") for t in trees]
