@@ -430,3 +430,59 @@ def test_flattener_reads_slots_directly_and_other_classes_generically():
     odd.length = "long"
     with pytest.raises(TypeError):
         Forest.from_trees([PhyloNode("r", [odd, PhyloNode("b")])], [1.0])
+
+
+def test_validation_agrees_with_a_plain_python_checker_on_corrupted_forests():
+    """``scs_forest_create`` accumulates its checks as flags (no early exit): whatever single entry of a valid forest
+    is overwritten, it must accept or refuse exactly as the rule it implements, spelled out here in plain Python."""
+    from spectralclustersupertree_b200.engine import ScsError
+
+    def valid(offsets, parent, taxon, num_taxa) -> bool:
+        for t in range(len(offsets) - 1):
+            base, count = offsets[t], offsets[t + 1] - offsets[t]
+            if count < 1 or parent[base] != -1:
+                return False
+            seen = set()
+            for k in range(count):
+                p = parent[base + k]
+                if k >= 1 and not 0 <= p < k:
+                    return False
+                tip = k + 1 >= count or parent[base + k + 1] != k
+                x = taxon[base + k]
+                if tip:
+                    if not 0 <= x < num_taxa or x in seen:
+                        return False
+                    seen.add(x)
+                elif x != -1:
+                    return False
+        return True
+
+    case = load_case("supertriplets")
+    names = case["names"]
+    good = Forest.from_trees(parse(case["lines"]), case["weights"], names)
+    arrays = [good.tree_arrays(t) for t in range(good.num_trees)]
+    offsets = np.concatenate([[0], np.cumsum([len(a[0]) for a in arrays])]).astype(np.int64)
+    parent = np.concatenate([a[0] for a in arrays]).astype(np.int32)
+    taxon = np.concatenate([a[3] for a in arrays]).astype(np.int32)
+    weights = np.ones(good.num_trees)
+    assert valid(offsets, parent, taxon, len(names))
+    rng = np.random.RandomState(17)
+    refused = accepted = 0
+    for _ in range(400):
+        p, x = parent.copy(), taxon.copy()
+        at = int(rng.randint(len(p)))
+        if rng.random_sample() < 0.5:
+            p[at] = int(rng.randint(-2, 12)) if rng.random_sample() < 0.7 else int(rng.randint(-2, len(p)))
+        else:
+            x[at] = int(rng.choice([-1, -5, 0, int(rng.randint(len(names))), len(names), len(names) + 3]))
+        want = valid(offsets, p, x, len(names))
+        for copy in (False, True):
+            try:
+                Forest.from_arrays(offsets, p, None, None, x, weights, names, copy=copy).close()
+                got = True
+            except ScsError:
+                got = False
+            assert got == want, (at, int(p[at]), int(x[at]), want)
+        refused += not want
+        accepted += want
+    assert refused > 100 and accepted > 20
