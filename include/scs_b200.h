@@ -335,8 +335,11 @@ int scs_nodes_split_medium_dev(scs_ctx *ctx, int num_nodes, const int32_t *node_
                                int contract_edges, int32_t *part_dev, scs_node_stats *stats, uint8_t *needs_rerun);
 
 /* ---- the whole recursion (scs.py:96-174) as a native work-list ------------------------------- *
- * Breadth-first over the independent sub-problems: every frontier node with <= 64 taxa goes to the
- * GPU in one batched launch, larger ones through scs_node_split_host.  The result is the supertree
+ * Breadth-first over the independent sub-problems, wave by wave, with the source trees resident on the
+ * device (uploaded once; leaf tours and the restriction to the children of every split, scs.py:411-455, are
+ * computed there): the frontier nodes up to the small-node limit (scs_ctx_set_small_node_limit, default 32
+ * taxa) are split in ONE launch, those up to 4096 taxa go through every stage together as one batch, larger
+ * ones one by one (row-sharded over the GPUs of a connected shard group).  The result is the supertree
  * as flat arrays: parent[i] < i (-1 for the root), taxon[i] = global taxon id for tips, -1 for
  * internal nodes; children are in index order.  With record_nodes != 0 every recursion node that
  * reached the GPU is kept (vertices, part, stats) for node-by-node parity checks. */
