@@ -109,6 +109,7 @@ static PyObject *flatten(PyObject *self, PyObject *args)
     PyObject *result = NULL;
     SlotCache slots = {NULL, -1, -1, -1, -1};
     int slots_tried = 0;
+    PyTypeObject *last_tried = NULL;
     int64_t total = 0;
     if (buf_push(&offsets, &total, sizeof total)) goto oom;
     const Py_ssize_t T = PySequence_Fast_GET_SIZE(seq);
@@ -125,8 +126,11 @@ static PyObject *flatten(PyObject *self, PyObject *args)
             memcpy(&item, stack.data + stack.size, sizeof item);
             PyObject *node = item.node;
             const int32_t k = (int32_t)(total - base);
-            if (!slots_tried) { /* the first node decides whether its class qualifies for direct slot reads */
-                slots_tried = 1;
+            if (slots.type == NULL && slots_tried < 8 && Py_TYPE(node) != last_tried) {
+                /* the first few node classes met are asked whether they qualify for direct slot reads (a root may be
+                 * of another class than the nodes below it: load.LoadedTree) */
+                slots_tried += 1;
+                last_tried = Py_TYPE(node);
                 slot_cache_fill(&slots, node, s_children, s_name, s_length, s_support);
             }
             PyObject *kids = NULL;

@@ -28,6 +28,7 @@ from typing import Literal
 import numpy as np
 
 from .engine import Engine, Forest, default_engine
+from .load import untouched_forest
 from .tree import NotCompleted, PhyloNode, make_tree
 
 WEIGHTINGS = ("one", "branch", "depth", "bootstrap")
@@ -67,6 +68,16 @@ def construct_supertree(
     if len(trees) != len(weights):
         msg = f"The number of trees ({len(trees)}) and tree weights ({len(weights)}) must match."
         raise ValueError(msg)
+    # the list one load_trees call returned, untouched: its file was parsed natively into the flat store already
+    # (load.LoadedTree); building and flattening a million node objects would only reproduce that forest
+    loaded = untouched_forest(trees, weights) if len(trees) > 1 else None
+    if loaded is not None:
+        if len(loaded.names) <= 2:  # ref: scs.py:105-106
+            return _star(loaded.names)
+        seed = 0 if random_state is None else int(random_state.randint(0, 2**31 - 1))
+        return supertree_of_forest(
+            loaded, pcg_weighting, contract_edges=contract_edges, seed=seed, engine=engine, trace=trace
+        )
     pairs = [(t, w) for t, w in zip(trees, weights, strict=True) if not _is_not_completed(t)]
     if len(pairs) == 0:
         msg = "There must be at least one tree to make a supertree."
