@@ -40,6 +40,21 @@ def _is_not_completed(obj) -> bool:
     return type(obj).__name__ == "NotCompleted"  # a real cogent3 NotCompleted, when cogent3 is installed
 
 
+def _in_the_callers_class(result: PhyloNode, trees: Sequence) -> PhyloNode:
+    """The supertree as a cogent3 tree when the source trees are cogent3 trees (where cogent3 is installed the
+    reference returns its ``PhyloNode``, ref: scs.py:25,390-408); the package's own node class otherwise."""
+    module = type(trees[0]).__module__ or ""
+    if module != "cogent3" and not module.startswith("cogent3."):
+        return result
+    try:
+        import cogent3
+    except ImportError:
+        return result
+    if getattr(cogent3, "_scs_b200_shim", False):  # oracle/cogent3_shim.py: the stand-in, not the library
+        return result
+    return cogent3.make_tree(result.get_newick())
+
+
 def construct_supertree(
     trees: Sequence[PhyloNode],
     weights: Sequence[float] | None = None,
@@ -87,18 +102,19 @@ def construct_supertree(
     if len(trees) == 1:  # ref: scs.py:96-98
         for node in trees[0].iter_nontips(include_self=True):
             node.name = ""
-        return make_tree(trees[0].get_newick())
+        return _in_the_callers_class(make_tree(trees[0].get_newick()), trees)
 
     # one walk over the node objects yields the flat forest and the taxon names (ref: scs.py:100-103 collects the
     # names with a get_tip_names() pass of its own)
     forest = Forest.from_trees(trees, [float(w) for w in weights])
     if len(forest.names) <= 2:  # ref: scs.py:105-106
-        return _star(forest.names)
+        return _in_the_callers_class(_star(forest.names), trees)
 
     seed = 0 if random_state is None else int(random_state.randint(0, 2**31 - 1))
-    return supertree_of_forest(
+    result = supertree_of_forest(
         forest, pcg_weighting, contract_edges=contract_edges, seed=seed, engine=engine, trace=trace
     )
+    return _in_the_callers_class(result, trees)
 
 
 def supertree_of_forest(

@@ -114,3 +114,34 @@ def test_construct_supertree_on_an_untouched_list_needs_no_node_objects(tmp_path
         construct_supertree(trees, weights=[1.0])
     with pytest.raises(ValueError, match="Invalid weighting strategy selected: 'bogus'"):
         construct_supertree(trees, pcg_weighting="bogus")
+
+
+def test_cogent3_trees_in_cogent3_tree_out(monkeypatch):
+    """With real cogent3 trees in, the supertree is handed back as a cogent3 tree (``cogent3.make_tree`` of its
+    Newick text); the package's own class otherwise, and when ``cogent3`` is only the oracle's import shim."""
+    import sys
+    import types
+
+    from spectralclustersupertree_b200 import scs
+
+    class Foreign(PhyloNode):  # stands for cogent3.core.tree.PhyloNode: same surface, another module
+        __slots__ = ()
+
+    Foreign.__module__ = "cogent3.core.tree"
+    made = []
+
+    def fake_make_tree(text):
+        made.append(text)
+        return ("cogent3 tree of", text)
+
+    fake = types.ModuleType("cogent3")
+    fake.make_tree = fake_make_tree
+    monkeypatch.setitem(sys.modules, "cogent3", fake)
+    ours = [make_tree("(a,b);"), make_tree("(b,a);")]
+    theirs = [Foreign("root", [Foreign("a"), Foreign("b")]), Foreign("root", [Foreign("b"), Foreign("a")])]
+    assert isinstance(construct_supertree(ours), PhyloNode) and not made
+    assert construct_supertree(theirs) == ("cogent3 tree of", "(a,b);")
+    assert construct_supertree(theirs[:1])[0] == "cogent3 tree of"  # the single-tree shortcut too
+    fake._scs_b200_shim = True
+    assert isinstance(construct_supertree(theirs), PhyloNode)
+    assert scs._in_the_callers_class(ours[0], ours) is ours[0]
